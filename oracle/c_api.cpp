@@ -1,0 +1,326 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle.hpp header).
+// extern "C" surface so tests/ and bench.py's cpu_baseline can drive the CPU
+// restatement through ctypes. Never loaded by the product library.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "oracle.hpp"
+
+using namespace orc;
+
+extern "C" {
+
+struct OrcTypeGen {
+    uint32_t kind;
+    uint32_t same_type;
+    uint32_t n_types;
+    float noise_frequency;
+    float voxel_type_frequency;
+    uint32_t seed;
+};
+
+struct OrcChunk {
+    uint8_t kind;
+    uint8_t flags;
+    uint8_t face[6];  // [dim*2 + side]
+    uint8_t uniform_type;
+    int8_t uniform_sd;
+    uint8_t uniform_flags;
+    uint8_t _pad;
+    uint32_t data_offset;
+};
+
+int orc_build_generator(const SdfNode* nodes, uint32_t n, uint32_t root, void** out, char* err,
+                        size_t errcap) {
+    Generator* g = new Generator();
+    std::string e = build_generator(nodes, n, root, *g);
+    if (!e.empty()) {
+        if (err && errcap) std::snprintf(err, errcap, "%s", e.c_str());
+        delete g;
+        *out = nullptr;
+        return 1;
+    }
+    *out = g;
+    return 0;
+}
+uint32_t orc_generator_node_count(const void* g) { return (uint32_t)((const Generator*)g)->nodes.size(); }
+uint32_t orc_generator_stack_size(const void* g) { return ((const Generator*)g)->stack_size; }
+void orc_generator_nodes(const void* g, ProgNode* out) {
+    const Generator* gen = (const Generator*)g;
+    std::memcpy(out, gen->nodes.data(), gen->nodes.size() * sizeof(ProgNode));
+}
+void orc_generator_domain(const void* g, float lo[3], float hi[3]) {
+    const Generator* gen = (const Generator*)g;
+    lo[0] = gen->domain.lo.x; lo[1] = gen->domain.lo.y; lo[2] = gen->domain.lo.z;
+    hi[0] = gen->domain.hi.x; hi[1] = gen->domain.hi.y; hi[2] = gen->domain.hi.z;
+}
+void orc_generator_free(void* g) { delete (Generator*)g; }
+
+void orc_eval_chunk(const void* g, const float lo[3], float* out4096, uint8_t* decisions) {
+    const Generator* gen = (const Generator*)g;
+    std::vector<float> stack((size_t)(gen->stack_size + 1) * CHUNK_VOXELS);
+    eval_chunk(*gen, v3(lo[0], lo[1], lo[2]), stack.data(), decisions);
+    std::memcpy(out4096, stack.data(), sizeof(float) * CHUNK_VOXELS);
+}
+void orc_eval_block_preserving_gradients(const void* g, const float origin[3], int size, float* out) {
+    const Generator* gen = (const Generator*)g;
+    size_t count = (size_t)size * size * size;
+    std::vector<float> stack((size_t)(gen->stack_size + 1) * count);
+    eval_block_preserving_gradients(*gen, v3(origin[0], origin[1], origin[2]), size, stack.data());
+    std::memcpy(out, stack.data(), sizeof(float) * count);
+}
+
+void* orc_voxel_generator_create(const void* g, float voxel_extent, const OrcTypeGen* t) {
+    VoxelGenerator* vg = new VoxelGenerator();
+    vg->sdf = *(const Generator*)g;
+    vg->types.kind = t->kind;
+    vg->types.same_type = (uint8_t)t->same_type;
+    vg->types.n_types = t->n_types;
+    vg->types.noise_frequency = t->noise_frequency;
+    vg->types.voxel_type_frequency = t->voxel_type_frequency;
+    vg->types.seed = t->seed;
+    make_voxel_generator(*vg, voxel_extent);
+    return vg;
+}
+void orc_voxel_generator_info(const void* vgp, uint32_t grid_shape[3], float shifted_center[3]) {
+    const VoxelGenerator* vg = (const VoxelGenerator*)vgp;
+    for (int d = 0; d < 3; ++d) grid_shape[d] = vg->grid_shape[d];
+    shifted_center[0] = vg->shifted_center.x;
+    shifted_center[1] = vg->shifted_center.y;
+    shifted_center[2] = vg->shifted_center.z;
+}
+void orc_voxel_generator_free(void* vg) { delete (VoxelGenerator*)vg; }
+
+void orc_generate_chunk(const void* vgp, const uint32_t origin[3], Voxel* out, uint8_t sparse[2]) {
+    const VoxelGenerator* vg = (const VoxelGenerator*)vgp;
+    std::vector<float> scratch((size_t)(vg->sdf.stack_size + 1) * CHUNK_VOXELS);
+    Sparseness sp = generate_chunk(*vg, origin, out, scratch.data(), nullptr);
+    sparse[0] = sp.only_empty;
+    sparse[1] = sp.is_void;
+}
+
+void* orc_object_generate(const void* vgp, int n_threads, double* t_gen, double* t_derive) {
+    Object* obj = new Object();
+    generate_object(*(const VoxelGenerator*)vgp, *obj, n_threads, t_gen, t_derive);
+    return obj;
+}
+
+// Test fixture equivalent to the reference's ManualVoxelGenerator
+// (object.rs:3387-3561): dense per-voxel sd codes + types over `shape`.
+void* orc_object_from_dense(const int8_t* sd, const uint8_t* types, const uint32_t shape[3],
+                            float voxel_extent) {
+    Object* objp = new Object();
+    Object& obj = *objp;
+    obj.voxel_extent = voxel_extent;
+    for (int d = 0; d < 3; ++d) obj.chunk_counts[d] = (shape[d] + 15) / 16;
+    uint32_t total = obj.chunk_counts[0] * obj.chunk_counts[1] * obj.chunk_counts[2];
+    // Reuse the generic path by building a tiny generator-like loop here.
+    obj.chunks.assign(total, Chunk{});
+    std::vector<Voxel> buf(CHUNK_VOXELS);
+    uint32_t nu = 0;
+    for (uint32_t ci = 0; ci < total; ++ci) {
+        uint32_t ijk[3] = {ci / (obj.chunk_counts[2] * obj.chunk_counts[1]),
+                           (ci / obj.chunk_counts[2]) % obj.chunk_counts[1], ci % obj.chunk_counts[2]};
+        bool only_empty = true, is_void = true;
+        int idx = 0;
+        for (int a = 0; a < 16; ++a)
+            for (int b = 0; b < 16; ++b)
+                for (int c = 0; c < 16; ++c, ++idx) {
+                    uint32_t i = ijk[0] * 16 + a, j = ijk[1] * 16 + b, k = ijk[2] * 16 + c;
+                    if (i >= shape[0] || j >= shape[1] || k >= shape[2]) {
+                        buf[idx] = Voxel{TYPE_DUMMY, 127, FLAG_EMPTY};
+                    } else {
+                        size_t g = ((size_t)i * shape[1] + j) * shape[2] + k;
+                        int8_t e = sd[g];
+                        if (e < 0) {
+                            only_empty = false;
+                            is_void = false;
+                            buf[idx] = Voxel{types[g], e, 0};
+                        } else {
+                            if (!(e > VOID_LIMIT)) is_void = false;
+                            buf[idx] = Voxel{types[g], e, FLAG_EMPTY};
+                        }
+                    }
+                }
+        if (only_empty)
+            for (auto& v : buf) v.type = TYPE_DUMMY;
+        // classification identical to create_for_generated_voxels
+        Chunk c;
+        if (!is_void) {
+            if (only_empty) {
+                c.kind = CK_NONUNIFORM;
+                c.flags = CF_ONLY_EMPTY;
+            } else {
+                Voxel first = buf[0];
+                bool uniform = true;
+                uint32_t cnt[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+                int q = 0;
+                for (int a = 0; a < 16; ++a)
+                    for (int b = 0; b < 16; ++b)
+                        for (int cc = 0; cc < 16; ++cc, ++q) {
+                            const Voxel& x = buf[q];
+                            if (x.type != first.type || x.flags != first.flags || x.sd != -128) uniform = false;
+                            if (x.flags & FLAG_EMPTY) {
+                                if (a == 0) cnt[0][0]++; else if (a == 15) cnt[0][1]++;
+                                if (b == 0) cnt[1][0]++; else if (b == 15) cnt[1][1]++;
+                                if (cc == 0) cnt[2][0]++; else if (cc == 15) cnt[2][1]++;
+                            }
+                        }
+                if (uniform) {
+                    c.kind = CK_UNIFORM;
+                    first.flags |= FLAG_FULL_ADJ;
+                    c.uniform_voxel = first;
+                } else {
+                    c.kind = CK_NONUNIFORM;
+                    for (int d = 0; d < 3; ++d)
+                        for (int s = 0; s < 2; ++s)
+                            c.face[d][s] = cnt[d][s] == 256 ? FD_EMPTY : (cnt[d][s] == 0 ? FD_FULL : FD_MIXED);
+                }
+            }
+        }
+        if (c.kind == CK_NONUNIFORM) {
+            c.data_offset = nu++;
+            obj.voxels.insert(obj.voxels.end(), buf.begin(), buf.end());
+        }
+        obj.chunks[ci] = c;
+    }
+    update_occupied_chunk_ranges(obj);
+    update_occupied_voxel_ranges(obj);
+    compute_all_derived_state(obj);
+    return objp;
+}
+
+void orc_object_info(const void* op, uint32_t chunk_counts[3], uint64_t* n_voxels, uint32_t occ_chunks[6],
+                     uint32_t occ_voxels[6]) {
+    const Object* obj = (const Object*)op;
+    for (int d = 0; d < 3; ++d) {
+        chunk_counts[d] = obj->chunk_counts[d];
+        occ_chunks[2 * d] = obj->occ_chunks[d][0];
+        occ_chunks[2 * d + 1] = obj->occ_chunks[d][1];
+        occ_voxels[2 * d] = obj->occ_voxels[d][0];
+        occ_voxels[2 * d + 1] = obj->occ_voxels[d][1];
+    }
+    *n_voxels = obj->voxels.size();
+}
+void orc_object_chunks(const void* op, OrcChunk* out) {
+    const Object* obj = (const Object*)op;
+    for (size_t i = 0; i < obj->chunks.size(); ++i) {
+        const Chunk& c = obj->chunks[i];
+        OrcChunk o{};
+        o.kind = c.kind;
+        o.flags = c.flags;
+        for (int d = 0; d < 3; ++d)
+            for (int s = 0; s < 2; ++s) o.face[2 * d + s] = c.face[d][s];
+        o.uniform_type = c.uniform_voxel.type;
+        o.uniform_sd = c.uniform_voxel.sd;
+        o.uniform_flags = c.uniform_voxel.flags;
+        o.data_offset = c.data_offset;
+        out[i] = o;
+    }
+}
+void orc_object_voxels(const void* op, Voxel* out) {
+    const Object* obj = (const Object*)op;
+    std::memcpy(out, obj->voxels.data(), obj->voxels.size() * sizeof(Voxel));
+}
+uint32_t orc_object_dirty(const void* op, uint32_t* out, uint32_t cap) {
+    const Object* obj = (const Object*)op;
+    uint32_t n = (uint32_t)obj->dirty.size();
+    for (uint32_t i = 0; i < n && i < cap; ++i) out[i] = obj->dirty[i];
+    return n;
+}
+void orc_object_clear_dirty(void* op) { ((Object*)op)->dirty.clear(); }
+void orc_object_free(void* op) { delete (Object*)op; }
+
+int orc_fill_brick(const void* op, uint32_t ci, uint32_t cj, uint32_t ck, float* values, uint8_t* types,
+                   uint8_t adj6[6], uint8_t* flags) {
+    static thread_local Brick b;
+    std::memset(b.types, 255, sizeof(b.types));
+    if (!fill_brick_if_exposed(*(const Object*)op, ci, cj, ck, b, flags)) return 0;
+    std::memcpy(values, b.values, sizeof(b.values));
+    std::memcpy(types, b.types, sizeof(b.types));
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) adj6[2 * d + s] = b.adj_non_uniform[d][s];
+    return 1;
+}
+
+void* orc_mesh_create(const void* op, int n_threads, double* t_s) {
+    Mesh* m = new Mesh();
+    auto t0 = std::chrono::steady_clock::now();
+    mesh_object(*(const Object*)op, *m, n_threads);
+    auto t1 = std::chrono::steady_clock::now();
+    if (t_s) *t_s = std::chrono::duration<double>(t1 - t0).count();
+    return m;
+}
+void orc_mesh_sizes(const void* mp, uint32_t* n_vertices, uint32_t* n_indices, uint32_t* n_submeshes) {
+    const Mesh* m = (const Mesh*)mp;
+    *n_vertices = (uint32_t)(m->positions.size() / 3);
+    *n_indices = (uint32_t)m->indices.size();
+    *n_submeshes = (uint32_t)m->submeshes.size();
+}
+void orc_mesh_copy(const void* mp, float* positions, float* normals, IndexMaterials* index_materials,
+                   uint32_t* indices, Submesh* submeshes, uint32_t* vertex_ranges) {
+    const Mesh* m = (const Mesh*)mp;
+    std::memcpy(positions, m->positions.data(), m->positions.size() * 4);
+    std::memcpy(normals, m->normals.data(), m->normals.size() * 4);
+    std::memcpy(index_materials, m->index_materials.data(), m->index_materials.size() * sizeof(IndexMaterials));
+    std::memcpy(indices, m->indices.data(), m->indices.size() * 4);
+    std::memcpy(submeshes, m->submeshes.data(), m->submeshes.size() * sizeof(Submesh));
+    std::memcpy(vertex_ranges, m->vertex_ranges.data(), m->vertex_ranges.size() * 4);
+}
+void orc_mesh_free(void* mp) { delete (Mesh*)mp; }
+
+// Mesh one chunk (one iteration of sync_with_voxel_object). Returns 0 if the
+// chunk is not exposed / produced no indices; else fills counts. Buffers sized
+// for the worst case: 4913 vertices, 3*6*4913 indices.
+int orc_mesh_chunk(const void* op, uint32_t ci, uint32_t cj, uint32_t ck, uint32_t* n_vertices,
+                   uint32_t* n_indices, float* positions, float* normals, IndexMaterials* index_materials,
+                   uint16_t* indices, uint8_t* flags) {
+    ChunkMesh cm;
+    if (!mesh_chunk(*(const Object*)op, ci, cj, ck, cm, flags)) return 0;
+    *n_vertices = (uint32_t)(cm.positions.size() / 3);
+    *n_indices = (uint32_t)cm.indices.size();
+    std::memcpy(positions, cm.positions.data(), cm.positions.size() * 4);
+    std::memcpy(normals, cm.normals.data(), cm.normals.size() * 4);
+    std::memcpy(index_materials, cm.index_materials.data(), cm.index_materials.size() * sizeof(IndexMaterials));
+    std::memcpy(indices, cm.indices.data(), cm.indices.size() * 2);
+    return 1;
+}
+
+void orc_vertex_materials(const uint8_t has[8], const uint8_t mat[8], uint8_t out[16]) {
+    bool h[8];
+    for (int i = 0; i < 8; ++i) h[i] = has[i] != 0;
+    VertexMaterials m = vertex_materials_compute(h, mat);
+    std::memcpy(out, m.indices, 8);
+    std::memcpy(out + 8, m.weights, 8);
+}
+void orc_index_materials(const uint8_t vm_in[48], uint8_t out[24]) {
+    VertexMaterials vm[3];
+    for (int v = 0; v < 3; ++v) {
+        std::memcpy(vm[v].indices, vm_in + 16 * v, 8);
+        std::memcpy(vm[v].weights, vm_in + 16 * v + 8, 8);
+    }
+    const VertexMaterials* p[3] = {&vm[0], &vm[1], &vm[2]};
+    IndexMaterials im[3];
+    index_materials_for_triangle(p, im);
+    for (int v = 0; v < 3; ++v) {
+        std::memcpy(out + 8 * v, im[v].indices, 4);
+        std::memcpy(out + 8 * v + 4, im[v].weights, 4);
+    }
+}
+
+void orc_absorb_sphere(void* op, const float center[3], float radius, float influence_radius,
+                       AbsorbStats* stats) {
+    absorb_sphere(*(Object*)op, v3(center[0], center[1], center[2]), radius, influence_radius, stats);
+}
+
+float orc_simplex3(float x, float y, float z, int32_t seed) { return simplex3(x, y, z, seed); }
+float orc_fbm3(float x, float y, float z, float lac, float gain, uint32_t oct, int32_t seed) {
+    return fbm3(x, y, z, lac, gain, oct, seed);
+}
+float orc_simplex4(float x, float y, float z, float w, int32_t seed) { return simplex4(x, y, z, w, seed); }
+int8_t orc_sd_encode(float v) { return sd_encode(v); }
+float orc_sd_decode(int8_t e) { return sd_decode(e); }
+
+}  // extern "C"

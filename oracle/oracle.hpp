@@ -1,0 +1,290 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.hpp header).
+//
+// CPU restatement of the reference's `impact_voxel` hot path:
+//   atomic SDF graph → generator (atomic.rs:228-596)
+//   block evaluator with culling (atomic.rs:633-875, 1601-1848)
+//   voxel generation / classification (generation.rs:207-371, voxel_type.rs)
+//   chunked object + derived state (object.rs)
+//   18³ brick fill + Surface Nets + mesh assembly (object/sdf.rs,
+//   object/sdf/surface_nets.rs, mesh.rs)
+//   sphere absorption + dirty-chunk bookkeeping (object/intersection.rs,
+//   interaction/absorption.rs)
+// Paths are relative to /root/reference/engine/crates/impact_voxel/src/.
+//
+// PARITY PINNING: the reference is Rust and cannot be built or run here (no
+// cargo/rustc, un-vendored deps). Pinned against the reference's own golden
+// vectors: surface_nets.rs:676-877 (vertex/index materials) and the structural
+// tests in object.rs:3563-4071 / intersection.rs:1093-1348 restated in
+// tests/. The NOISE functions restate simdnoise 3.1.7 (fork e59c958e) from its
+// published algorithm; no reference test pins them → noise parity UNPINNED.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "oracle_math.hpp"
+
+namespace orc {
+
+constexpr int CHUNK_SIZE = 16;
+constexpr int CHUNK_VOXELS = 4096;
+constexpr int BRICK_SIZE = 18;
+constexpr int BRICK_CELLS = 5832;
+
+// --- voxel encoding (lib.rs:60-101, 154-269) -------------------------------
+constexpr float QUANT_STEP = 0.02f;
+constexpr float INV_QUANT_STEP = 1.0f / 0.02f;  // == 50.0f in f32
+constexpr float SD_MAX_F32 = 0.02f * 127.0f;
+constexpr float SD_MIN_F32 = 0.02f * -128.0f;
+constexpr int8_t VOID_LIMIT = 100;
+
+constexpr uint8_t FLAG_EMPTY = 1 << 0;
+constexpr uint8_t FLAG_ADJ_X_DN = 1 << 2;
+constexpr uint8_t FLAG_ADJ_Y_DN = 1 << 3;
+constexpr uint8_t FLAG_ADJ_Z_DN = 1 << 4;
+constexpr uint8_t FLAG_ADJ_X_UP = 1 << 5;
+constexpr uint8_t FLAG_ADJ_Y_UP = 1 << 6;
+constexpr uint8_t FLAG_ADJ_Z_UP = 1 << 7;
+constexpr uint8_t FLAG_FULL_ADJ = 0xFC;
+constexpr uint8_t TYPE_DUMMY = 255;
+
+struct Voxel {
+    uint8_t type;
+    int8_t sd;
+    uint8_t flags;
+};
+static_assert(sizeof(Voxel) == 3, "Voxel is 3 bytes repr(C)");
+
+// `(value * 50.0) as i8`: saturating, truncating, NaN → 0 (lib.rs:195-201)
+static inline int8_t sd_encode(float v) {
+    float s = v * INV_QUANT_STEP;
+    if (s != s) return 0;
+    if (s >= 127.0f) return 127;
+    if (s <= -128.0f) return -128;
+    return (int8_t)(int)s;
+}
+static inline float sd_decode(int8_t e) { return (float)e * QUANT_STEP; }
+
+// --- atomic SDF graph (atomic.rs:55-181) ------------------------------------
+enum NodeKind : uint32_t {
+    K_SPHERE = 0,
+    K_CAPSULE = 1,
+    K_BOX = 2,
+    K_TRANSLATION = 3,
+    K_ROTATION = 4,
+    K_SCALING = 5,
+    K_NOISE = 6,
+    K_UNION = 7,
+    K_SUBTRACTION = 8,
+    K_INTERSECTION = 9,
+};
+
+// Input node, POD (same layout as include/impact_voxel_cuda.h ivx_sdf_node).
+//   sphere:  p[0]=radius
+//   capsule: p[0]=segment_length p[1]=radius
+//   box:     p[0..3]=extents
+//   translation: child[0], p[0..3]
+//   rotation:    child[0], p[0..4] = quaternion x,y,z,w
+//   scaling:     child[0], p[0]
+//   noise:       child[0], octaves, seed, p[0]=frequency p[1]=lacunarity
+//                p[2]=persistence p[3]=amplitude
+//   union/sub/inter: child[0], child[1], p[0]=smoothness
+struct SdfNode {
+    uint32_t kind;
+    uint32_t child[2];
+    uint32_t octaves;
+    uint32_t seed;
+    float p[8];
+};
+
+// ProcessedSDFNode mirror (atomic.rs:83-102).
+//   leaf params: sphere p[0]=radius; capsule p[0]=half_segment_length p[1]=radius;
+//   box p[0..3]=half_extents; scaling p[0]; noise p[0]=frequency p[1]=lacunarity
+//   p[2]=persistence p[3]=amplitude p[4]=noise_scale; combine p[0]=smoothness
+//   p[1]=0.25/smoothness
+struct ProgNode {
+    uint32_t kind;
+    uint32_t octaves;
+    uint32_t seed;
+    uint32_t leaf_count;
+    float p[8];
+    float transform[16];  // column-major root→node
+    float dom_lo[3];
+    float dom_hi[3];
+    float margin;
+    uint32_t _pad;
+};
+
+struct Generator {
+    std::vector<ProgNode> nodes;  // post-order, DAG unrolled
+    uint32_t stack_size = 0;      // required_forward_stack_size
+    Aabb domain{{0, 0, 0}, {0, 0, 0}};
+    bool empty() const { return nodes.empty(); }
+};
+
+// Returns "" on success, else the error string (cycle / missing node).
+std::string build_generator(const SdfNode* nodes, uint32_t n, uint32_t root, Generator& out);
+
+// compute_signed_distances_for_block<16,4096> (atomic.rs:633-875)
+// `stack` must hold (stack_size+1)*4096 floats; result in stack[0..4096].
+// If `decisions` != nullptr it receives one byte per program node:
+//   leaf: 0 = evaluated, 1 = filled +margin, 2 = filled -margin
+//   noise/combine: 0 = applied, 1 = skipped; others 0.
+void eval_chunk(const Generator& g, V3 chunk_lo_root, float* stack, uint8_t* decisions);
+// compute_signed_distances_for_block_preserving_gradients<SIZE,COUNT> (atomic.rs:877-998)
+void eval_block_preserving_gradients(const Generator& g, V3 block_origin_root, int size,
+                                     float* stack);
+
+// --- noise (simdnoise 3.1.7 restatement; UNPINNED) ---------------------------
+float simplex3(float x, float y, float z, int32_t seed);
+float fbm3(float x, float y, float z, float lacunarity, float gain, uint32_t octaves,
+           int32_t seed);
+float simplex4(float x, float y, float z, float w, int32_t seed);
+
+// --- voxel generator (generation.rs:70-371, voxel_type.rs) -------------------
+struct TypeGen {
+    uint32_t kind = 0;  // 0 = Same, 1 = GradientNoise
+    uint8_t same_type = 0;
+    uint32_t n_types = 1;
+    float noise_frequency = 0;
+    float voxel_type_frequency = 0;
+    uint32_t seed = 0;
+};
+
+struct VoxelGenerator {
+    float voxel_extent = 1.0f;
+    uint32_t grid_shape[3] = {0, 0, 0};
+    V3 shifted_center{-0.5f, -0.5f, -0.5f};
+    Generator sdf;
+    TypeGen types;
+};
+void make_voxel_generator(VoxelGenerator& vg, float voxel_extent);  // SDFVoxelGenerator::new
+
+struct Sparseness {
+    bool only_empty, is_void;
+};
+// generate_chunk (generation.rs:293-371); scratch = (stack_size+1)*4096 floats,
+// type_scratch = 4096*n_types floats.
+Sparseness generate_chunk(const VoxelGenerator& vg, const uint32_t origin[3], Voxel* voxels,
+                          float* scratch, float* type_scratch);
+
+// --- chunked object (object.rs) ----------------------------------------------
+enum ChunkKind : uint8_t { CK_VOID = 0, CK_UNIFORM = 1, CK_NONUNIFORM = 2 };
+enum FaceDist : uint8_t { FD_EMPTY = 0, FD_FULL = 1, FD_MIXED = 2 };
+constexpr uint8_t CF_OBSCURED_ALL = 0x3F;
+constexpr uint8_t CF_ONLY_EMPTY = 1 << 6;
+
+struct Chunk {
+    uint8_t kind = CK_VOID;
+    Voxel uniform_voxel{0, 0, 0};
+    uint32_t data_offset = 0;
+    uint8_t face[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    uint8_t flags = 0;
+};
+
+struct Object {
+    float voxel_extent = 1.0f;
+    uint32_t chunk_counts[3] = {0, 0, 0};
+    uint32_t occ_chunks[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    uint32_t occ_voxels[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    std::vector<Chunk> chunks;
+    std::vector<Voxel> voxels;
+    std::vector<uint32_t> dirty;  // linear chunk indices, insertion order, unique
+
+    uint32_t lin(uint32_t i, uint32_t j, uint32_t k) const {
+        return (i * chunk_counts[1] + j) * chunk_counts[2] + k;
+    }
+    Chunk get_chunk(int64_t i, int64_t j, int64_t k) const {
+        if (i < 0 || j < 0 || k < 0 || i >= chunk_counts[0] || j >= chunk_counts[1] ||
+            k >= chunk_counts[2])
+            return Chunk{};
+        return chunks[lin((uint32_t)i, (uint32_t)j, (uint32_t)k)];
+    }
+    Voxel* chunk_voxels(uint32_t data_offset) { return voxels.data() + (size_t)data_offset * 4096; }
+    const Voxel* chunk_voxels(uint32_t data_offset) const {
+        return voxels.data() + (size_t)data_offset * 4096;
+    }
+    void mark_dirty(uint32_t idx);
+};
+
+// VoxelObject::generate (object.rs:239-263): generate_without_derived_state,
+// update_occupied_voxel_ranges, compute_all_derived_state (minus split detection).
+// n_threads > 1 splits the linear chunk index into contiguous ranges
+// (object.rs:423-427); result is identical.
+void generate_object(const VoxelGenerator& vg, Object& obj, int n_threads,
+                     double* t_generate_s = nullptr, double* t_derive_s = nullptr);
+void generate_without_derived_state(const VoxelGenerator& vg, Object& obj, int n_threads);
+void update_occupied_voxel_ranges(Object& obj);
+void update_occupied_chunk_ranges(Object& obj);
+void compute_all_derived_state(Object& obj);
+void update_internal_adjacencies(Voxel* chunk_voxels);
+void update_upper_boundary_adjacencies_in_ranges(Object& obj, const uint32_t r[3][2]);
+Sparseness update_all_internal_state(Chunk& c, Voxel* chunk_voxels);
+
+// --- brick + surface nets + mesh (object/sdf.rs, surface_nets.rs, mesh.rs) ---
+struct Brick {
+    float values[BRICK_CELLS];
+    uint8_t types[BRICK_CELLS];
+    bool adj_non_uniform[3][2];
+};
+// fill_sdf_for_chunk_if_exposed (object/sdf.rs:181-213); returns false if not exposed.
+bool fill_brick_if_exposed(const Object& obj, uint32_t ci, uint32_t cj, uint32_t ck, Brick& b,
+                           uint8_t* chunk_flags);
+
+struct VertexMaterials {
+    uint8_t indices[8];
+    uint8_t weights[8];
+};
+struct IndexMaterials {
+    uint8_t indices[4];
+    uint8_t weights[4];
+};
+VertexMaterials vertex_materials_compute(const bool has_voxel[8], const uint8_t mat[8]);
+void index_materials_for_triangle(const VertexMaterials* vm[3], IndexMaterials out[3]);
+
+struct ChunkMesh {
+    std::vector<float> positions;  // 3 per vertex
+    std::vector<float> normals;    // 3 per vertex
+    std::vector<VertexMaterials> vertex_materials;
+    std::vector<IndexMaterials> index_materials;
+    std::vector<uint16_t> indices;
+    std::vector<uint16_t> surface_lin;  // brick linear idx per vertex
+    std::vector<uint16_t> lin_to_vertex;
+};
+// compute_surface_nets_mesh (surface_nets.rs:131-148)
+void surface_nets(const Brick& b, float voxel_extent, V3 position_offset, ChunkMesh& out);
+
+struct Submesh {
+    uint32_t chunk_indices[3];
+    uint32_t index_offset;
+    uint32_t index_count;
+    uint32_t obscured[2][2][2];
+};
+struct Mesh {
+    std::vector<float> positions;
+    std::vector<float> normals;
+    std::vector<IndexMaterials> index_materials;
+    std::vector<uint32_t> indices;
+    std::vector<Submesh> submeshes;
+    std::vector<uint32_t> vertex_ranges;  // 2 per submesh: start, end
+};
+// VoxelObjectMesh::recreate (mesh.rs:286-354)
+void mesh_object(const Object& obj, Mesh& mesh, int n_threads = 1);
+// One chunk of VoxelObjectMesh::sync_with_voxel_object (mesh.rs:360-456): returns
+// false when the chunk is not exposed or yields an empty mesh (→ submesh removed).
+bool mesh_chunk(const Object& obj, uint32_t ci, uint32_t cj, uint32_t ck, ChunkMesh& cm,
+                uint8_t* chunk_flags);
+
+// --- modification (object/intersection.rs, interaction/absorption.rs) --------
+struct AbsorbStats {
+    uint32_t touched_chunks;
+    uint32_t touched_voxels;
+    uint32_t emptied_voxels;
+    uint32_t removed_chunks;
+};
+// apply_sphere_absorption restricted to the voxel-object side: influence sphere
+// (centre, influence_radius) and absorbing radius, all in normalized voxel space.
+void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius,
+                   AbsorbStats* stats);
+
+}  // namespace orc

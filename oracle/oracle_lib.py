@@ -1,0 +1,299 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/_build/liboracle.so (the CPU restatement of the
+reference's voxel hot path). Importable only from tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference leg. The product package
+(impact_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+VOXEL_DTYPE = np.dtype([("type", "u1"), ("sd", "i1"), ("flags", "u1")])
+CHUNK_DTYPE = np.dtype(
+    [("kind", "u1"), ("flags", "u1"), ("face", "u1", (6,)), ("uniform_type", "u1"), ("uniform_sd", "i1"),
+     ("uniform_flags", "u1"), ("_pad", "u1"), ("data_offset", "<u4")]
+)
+assert CHUNK_DTYPE.itemsize == 16
+SUBMESH_DTYPE = np.dtype(
+    [("chunk_indices", "<u4", (3,)), ("index_offset", "<u4"), ("index_count", "<u4"), ("obscured", "<u4", (8,))]
+)
+assert SUBMESH_DTYPE.itemsize == 52
+INDEX_MATERIALS_DTYPE = np.dtype([("indices", "u1", (4,)), ("weights", "u1", (4,))])
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_build_generator.restype = C.c_int
+        _lib.orc_generator_node_count.restype = C.c_uint32
+        _lib.orc_generator_stack_size.restype = C.c_uint32
+        _lib.orc_voxel_generator_create.restype = C.c_void_p
+        _lib.orc_object_generate.restype = C.c_void_p
+        _lib.orc_object_from_dense.restype = C.c_void_p
+        _lib.orc_object_dirty.restype = C.c_uint32
+        _lib.orc_mesh_create.restype = C.c_void_p
+        _lib.orc_fill_brick.restype = C.c_int
+        _lib.orc_mesh_chunk.restype = C.c_int
+        for f in ("orc_simplex3", "orc_fbm3", "orc_simplex4", "orc_sd_decode"):
+            getattr(_lib, f).restype = C.c_float
+        _lib.orc_sd_encode.restype = C.c_int8
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Generator:
+    """SDFGenerator (atomic.rs:33-40) built from an atomic node array."""
+
+    def __init__(self, nodes: np.ndarray, root: int):
+        from impact_b200.graph import PROG_NODE_DTYPE
+
+        self._prog_dtype = PROG_NODE_DTYPE
+        nodes = np.ascontiguousarray(nodes)
+        h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        rc = lib().orc_build_generator(_p(nodes), C.c_uint32(len(nodes)), C.c_uint32(root), C.byref(h), err,
+                                       C.c_size_t(256))
+        if rc != 0:
+            raise ValueError(err.value.decode())
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_generator_free(self.h)
+            self.h = None
+
+    @property
+    def node_count(self) -> int:
+        return lib().orc_generator_node_count(self.h)
+
+    @property
+    def stack_size(self) -> int:
+        return lib().orc_generator_stack_size(self.h)
+
+    def nodes(self) -> np.ndarray:
+        out = np.zeros(self.node_count, dtype=self._prog_dtype)
+        if len(out):
+            lib().orc_generator_nodes(self.h, _p(out))
+        return out
+
+    def domain(self):
+        lo = np.zeros(3, np.float32)
+        hi = np.zeros(3, np.float32)
+        lib().orc_generator_domain(self.h, _p(lo), _p(hi))
+        return lo, hi
+
+    def eval_chunk(self, lo):
+        lo = np.asarray(lo, np.float32)
+        out = np.zeros(4096, np.float32)
+        dec = np.zeros(max(1, self.node_count), np.uint8)
+        lib().orc_eval_chunk(self.h, _p(lo), _p(out), _p(dec))
+        return out, dec[: self.node_count]
+
+    def eval_block_preserving_gradients(self, origin, size: int):
+        origin = np.asarray(origin, np.float32)
+        out = np.zeros(size**3, np.float32)
+        lib().orc_eval_block_preserving_gradients(self.h, _p(origin), C.c_int(size), _p(out))
+        return out
+
+
+class VoxelGenerator:
+    """SDFVoxelGenerator (generation.rs:70-77)."""
+
+    def __init__(self, gen: Generator, voxel_extent: float, type_gen):
+        self.gen = gen
+        pod = type_gen.pod()
+        self.h = C.c_void_p(lib().orc_voxel_generator_create(gen.h, C.c_float(voxel_extent), _p(pod)))
+        gs = np.zeros(3, np.uint32)
+        sc = np.zeros(3, np.float32)
+        lib().orc_voxel_generator_info(self.h, _p(gs), _p(sc))
+        self.grid_shape = tuple(int(x) for x in gs)
+        self.shifted_center = sc
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_voxel_generator_free(self.h)
+            self.h = None
+
+    def generate_chunk(self, origin):
+        origin = np.asarray(origin, np.uint32)
+        out = np.zeros(4096, VOXEL_DTYPE)
+        sp = np.zeros(2, np.uint8)
+        lib().orc_generate_chunk(self.h, _p(origin), _p(out), _p(sp))
+        return out, bool(sp[0]), bool(sp[1])
+
+
+class Object:
+    """VoxelObject (object.rs:45-57) minus split detection."""
+
+    def __init__(self, handle):
+        self.h = C.c_void_p(handle)
+        self.t_generate = self.t_derive = 0.0
+
+    @classmethod
+    def generate(cls, vg: VoxelGenerator, n_threads: int = 1) -> "Object":
+        tg, td = C.c_double(), C.c_double()
+        o = cls(lib().orc_object_generate(vg.h, C.c_int(n_threads), C.byref(tg), C.byref(td)))
+        o.t_generate, o.t_derive = tg.value, td.value
+        return o
+
+    @classmethod
+    def from_dense(cls, sd: np.ndarray, types: np.ndarray, voxel_extent: float = 1.0) -> "Object":
+        sd = np.ascontiguousarray(sd, np.int8)
+        types = np.ascontiguousarray(types, np.uint8)
+        shape = np.asarray(sd.shape, np.uint32)
+        return cls(lib().orc_object_from_dense(_p(sd), _p(types), _p(shape), C.c_float(voxel_extent)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_object_free(self.h)
+            self.h = None
+
+    def info(self):
+        cc = np.zeros(3, np.uint32)
+        nv = C.c_uint64()
+        oc = np.zeros(6, np.uint32)
+        ov = np.zeros(6, np.uint32)
+        lib().orc_object_info(self.h, _p(cc), C.byref(nv), _p(oc), _p(ov))
+        return {"chunk_counts": tuple(int(x) for x in cc), "n_voxels": nv.value,
+                "occupied_chunk_ranges": oc.reshape(3, 2).copy(), "occupied_voxel_ranges": ov.reshape(3, 2).copy()}
+
+    def chunks(self) -> np.ndarray:
+        n = int(np.prod(self.info()["chunk_counts"]))
+        out = np.zeros(n, CHUNK_DTYPE)
+        if n:
+            lib().orc_object_chunks(self.h, _p(out))
+        return out
+
+    def voxels(self) -> np.ndarray:
+        n = self.info()["n_voxels"]
+        out = np.zeros(n, VOXEL_DTYPE)
+        if n:
+            lib().orc_object_voxels(self.h, _p(out))
+        return out
+
+    def dirty(self) -> np.ndarray:
+        n = lib().orc_object_dirty(self.h, None, C.c_uint32(0))
+        out = np.zeros(max(n, 1), np.uint32)
+        lib().orc_object_dirty(self.h, _p(out), C.c_uint32(n))
+        return out[:n]
+
+    def clear_dirty(self):
+        lib().orc_object_clear_dirty(self.h)
+
+    def fill_brick(self, ci, cj, ck):
+        values = np.zeros(5832, np.float32)
+        types = np.zeros(5832, np.uint8)
+        adj = np.zeros(6, np.uint8)
+        flags = C.c_uint8()
+        ok = lib().orc_fill_brick(self.h, C.c_uint32(ci), C.c_uint32(cj), C.c_uint32(ck), _p(values), _p(types),
+                                  _p(adj), C.byref(flags))
+        return (values, types, adj, flags.value) if ok else None
+
+    def mesh(self, n_threads: int = 1) -> "Mesh":
+        t = C.c_double()
+        m = Mesh(lib().orc_mesh_create(self.h, C.c_int(n_threads), C.byref(t)))
+        m.t_mesh = t.value
+        return m
+
+    def mesh_chunk(self, ci, cj, ck):
+        nv, ni = C.c_uint32(), C.c_uint32()
+        pos = np.zeros(4913 * 3, np.float32)
+        nrm = np.zeros(4913 * 3, np.float32)
+        im = np.zeros(4913 * 18, INDEX_MATERIALS_DTYPE)
+        idx = np.zeros(4913 * 18, np.uint16)
+        flags = C.c_uint8()
+        ok = lib().orc_mesh_chunk(self.h, C.c_uint32(ci), C.c_uint32(cj), C.c_uint32(ck), C.byref(nv), C.byref(ni),
+                                  _p(pos), _p(nrm), _p(im), _p(idx), C.byref(flags))
+        if not ok:
+            return None
+        v, i = nv.value, ni.value
+        return {"positions": pos[: 3 * v].reshape(-1, 3).copy(), "normals": nrm[: 3 * v].reshape(-1, 3).copy(),
+                "index_materials": im[:i].copy(), "indices": idx[:i].copy(), "flags": flags.value}
+
+    def absorb_sphere(self, center, radius: float, influence_radius: float):
+        center = np.asarray(center, np.float32)
+        st = np.zeros(4, np.uint32)
+        lib().orc_absorb_sphere(self.h, _p(center), C.c_float(radius), C.c_float(influence_radius), _p(st))
+        return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
+                "removed_chunks": int(st[3])}
+
+
+class Mesh:
+    """VoxelObjectMesh (mesh.rs:50-58)."""
+
+    def __init__(self, handle):
+        self.h = C.c_void_p(handle)
+        self.t_mesh = 0.0
+        nv, ni, ns = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().orc_mesh_sizes(self.h, C.byref(nv), C.byref(ni), C.byref(ns))
+        self.n_vertices, self.n_indices, self.n_submeshes = nv.value, ni.value, ns.value
+        self.positions = np.zeros((self.n_vertices, 3), np.float32)
+        self.normals = np.zeros((self.n_vertices, 3), np.float32)
+        self.index_materials = np.zeros(self.n_indices, INDEX_MATERIALS_DTYPE)
+        self.indices = np.zeros(self.n_indices, np.uint32)
+        self.submeshes = np.zeros(self.n_submeshes, SUBMESH_DTYPE)
+        self.vertex_ranges = np.zeros((self.n_submeshes, 2), np.uint32)
+        lib().orc_mesh_copy(self.h, _p(self.positions), _p(self.normals), _p(self.index_materials),
+                            _p(self.indices), _p(self.submeshes), _p(self.vertex_ranges))
+        lib().orc_mesh_free(self.h)
+        self.h = None
+
+
+def vertex_materials(has_voxel, materials):
+    has = np.asarray(has_voxel, np.uint8)
+    mat = np.asarray(materials, np.uint8)
+    out = np.zeros(16, np.uint8)
+    lib().orc_vertex_materials(_p(has), _p(mat), _p(out))
+    return out[:8].copy(), out[8:].copy()
+
+
+def index_materials(vms):
+    """vms: three (indices[8], weights[8]) pairs → three (indices[4], weights[4])."""
+    buf = np.zeros(48, np.uint8)
+    for v, (ind, w) in enumerate(vms):
+        buf[16 * v: 16 * v + 8] = ind
+        buf[16 * v + 8: 16 * v + 16] = w
+    out = np.zeros(24, np.uint8)
+    lib().orc_index_materials(_p(buf), _p(out))
+    return [(out[8 * v: 8 * v + 4].copy(), out[8 * v + 4: 8 * v + 8].copy()) for v in range(3)]
+
+
+def sd_encode(v: float) -> int:
+    return int(lib().orc_sd_encode(C.c_float(v)))
+
+
+def simplex3(x, y, z, seed):
+    return float(lib().orc_simplex3(C.c_float(x), C.c_float(y), C.c_float(z), C.c_int32(seed)))
+
+
+def fbm3(x, y, z, lac, gain, octaves, seed):
+    return float(lib().orc_fbm3(C.c_float(x), C.c_float(y), C.c_float(z), C.c_float(lac), C.c_float(gain),
+                                C.c_uint32(octaves), C.c_int32(seed)))
+
+
+def simplex4(x, y, z, w, seed):
+    return float(lib().orc_simplex4(C.c_float(x), C.c_float(y), C.c_float(z), C.c_float(w), C.c_int32(seed)))
