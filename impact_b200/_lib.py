@@ -1,0 +1,107 @@
+"""ctypes binding of impact_b200/libimpact_voxel_cuda.so (include/impact_voxel_cuda.h).
+
+The library is the product; there is no Python or CPU fallback. If the shared
+object is missing this module raises at import of `lib()`, and `ivx_create`
+fails with IVX_ERR_NO_DEVICE on a machine without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.environ.get("IMPACT_VOXEL_CUDA_LIB", os.path.join(_HERE, "libimpact_voxel_cuda.so"))
+
+IVX_OK = 0
+STATUS_NAMES = {
+    0: "IVX_OK", 1: "IVX_ERR_INVALID_ARGUMENT", 2: "IVX_ERR_GRAPH", 3: "IVX_ERR_CUDA", 4: "IVX_ERR_OUT_OF_MEMORY",
+    5: "IVX_ERR_CAPACITY", 6: "IVX_ERR_UNSUPPORTED", 7: "IVX_ERR_NO_DEVICE",
+}
+
+# every symbol include/impact_voxel_cuda.h declares
+EXPORTED_SYMBOLS = [
+    "ivx_create", "ivx_destroy", "ivx_last_error", "ivx_abi_version", "ivx_kernel_launch_count", "ivx_synchronize",
+    "ivx_program_build", "ivx_program_upload", "ivx_program_compile_host", "ivx_program_info_get", "ivx_program_nodes", "ivx_program_free",
+    "ivx_program_eval_chunks", "ivx_object_generate", "ivx_object_generate_slab", "ivx_object_info_get",
+    "ivx_object_download", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_object_absorb_sphere",
+    "ivx_object_dirty_chunks", "ivx_object_remesh_dirty",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p), ("flags", C.c_uint32)]
+
+
+class ProgramInfo(C.Structure):
+    _fields_ = [("node_count", C.c_uint32), ("stack_depth", C.c_uint32), ("domain_lo", C.c_float * 3),
+                ("domain_hi", C.c_float * 3)]
+
+
+class ObjectInfo(C.Structure):
+    _fields_ = [("voxel_extent", C.c_float), ("grid_shape", C.c_uint32 * 3), ("chunk_counts", C.c_uint32 * 3),
+                ("chunk_i_begin", C.c_uint32), ("chunk_i_end", C.c_uint32), ("n_void", C.c_uint32),
+                ("n_uniform", C.c_uint32), ("n_non_uniform", C.c_uint32), ("occupied_chunk_ranges", C.c_uint32 * 6),
+                ("occupied_voxel_ranges", C.c_uint32 * 6), ("device_bytes", C.c_uint64)]
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint32), ("n_indices", C.c_uint32), ("n_submeshes", C.c_uint32),
+                ("n_exposed_chunks", C.c_uint32), ("d_positions", C.c_void_p), ("d_normals", C.c_void_p),
+                ("d_index_materials", C.c_void_p), ("d_indices", C.c_void_p), ("d_submeshes", C.c_void_p),
+                ("d_vertex_ranges", C.c_void_p)]
+
+
+class AbsorbStats(C.Structure):
+    _fields_ = [("touched_chunks", C.c_uint32), ("touched_voxels", C.c_uint32), ("emptied_voxels", C.c_uint32),
+                ("removed_chunks", C.c_uint32), ("dirty_chunks", C.c_uint32)]
+
+
+VOXEL_DTYPE = np.dtype([("type", "u1"), ("sd", "i1"), ("flags", "u1")])
+CHUNK_DTYPE = np.dtype(
+    [("kind", "u1"), ("flags", "u1"), ("face", "u1", (6,)), ("uniform_type", "u1"), ("uniform_sd", "i1"),
+     ("uniform_flags", "u1"), ("_pad", "u1"), ("data_offset", "<u4")]
+)
+SUBMESH_DTYPE = np.dtype(
+    [("chunk_indices", "<u4", (3,)), ("index_offset", "<u4"), ("index_count", "<u4"), ("obscured", "<u4", (8,))]
+)
+INDEX_MATERIALS_DTYPE = np.dtype([("indices", "u1", (4,)), ("weights", "u1", (4,))])
+assert CHUNK_DTYPE.itemsize == 16 and SUBMESH_DTYPE.itemsize == 52 and VOXEL_DTYPE.itemsize == 3
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once). Raises OSError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise OSError(
+                f"{SO_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the voxel hot path)"
+            )
+        L = C.CDLL(SO_PATH)
+        L.ivx_last_error.restype = C.c_char_p
+        L.ivx_last_error.argtypes = [C.c_void_p]
+        L.ivx_abi_version.restype = C.c_uint32
+        L.ivx_kernel_launch_count.restype = C.c_uint64
+        L.ivx_kernel_launch_count.argtypes = [C.c_void_p]
+        L.ivx_destroy.argtypes = [C.c_void_p]
+        L.ivx_destroy.restype = None
+        L.ivx_program_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.ivx_program_free.restype = None
+        L.ivx_object_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.ivx_object_free.restype = None
+        _lib = L
+    return _lib
+
+
+class IvxError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,1090 @@
+// C ABI of libimpact_voxel_cuda.so: context, device memory pool, and the
+// host-side orchestration of the generate → derive → mesh → modify kernels.
+// See include/impact_voxel_cuda.h for the contract of each entry point.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace ivx;
+
+// ---------------------------------------------------------------------------
+struct PoolBlock {
+    void* ptr;
+    size_t size;
+    bool used;
+};
+
+struct ivx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    std::vector<PoolBlock> pool;
+    uint32_t* h_pinned = nullptr;  // 64 words of pinned scratch for counter read-back
+    uint32_t* d_scratch = nullptr; // 64 words of device counters
+
+    void* alloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        bytes = (bytes + 255) & ~(size_t)255;
+        int best = -1;
+        for (int i = 0; i < (int)pool.size(); ++i)
+            if (!pool[i].used && pool[i].size >= bytes && pool[i].size <= bytes * 2 + (1 << 20) &&
+                (best < 0 || pool[i].size < pool[best].size))
+                best = i;
+        if (best >= 0) {
+            pool[best].used = true;
+            return pool[best].ptr;
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            // release cached blocks and retry once
+            for (auto it = pool.begin(); it != pool.end();) {
+                if (!it->used) {
+                    cudaFree(it->ptr);
+                    it = pool.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+            if (cudaMalloc(&p, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        pool.push_back({p, bytes, true});
+        return p;
+    }
+    void release(void* p) {
+        if (!p) return;
+        for (auto& b : pool)
+            if (b.ptr == p) {
+                b.used = false;
+                return;
+            }
+    }
+};
+
+struct ivx_program {
+    HostProgram host;
+    ivx_node* d_nodes = nullptr;
+    Instr* d_root = nullptr;     // the whole program as an instruction list
+    uint32_t root_len = 0;
+    uint32_t* d_root_meta = nullptr;  // [0] = offset (0), [1] = length
+};
+
+struct DeviceMesh {
+    uint32_t n_vertices = 0, n_indices = 0, n_submeshes = 0, n_work = 0;
+    float* positions = nullptr;
+    float* normals = nullptr;
+    uint32_t* indices = nullptr;
+    ivx_index_materials* index_materials = nullptr;
+    ivx_chunk_submesh* submeshes = nullptr;
+    uint32_t* vertex_ranges = nullptr;
+};
+
+struct ivx_object {
+    float voxel_extent = 1.0f;
+    uint32_t grid_shape[3] = {0, 0, 0};
+    uint32_t chunk_counts[3] = {0, 0, 0};  // full grid
+    uint32_t nb[3] = {0, 0, 0};            // locally stored chunk planes (slab)
+    uint32_t first_i = 0;                  // global chunk-i of local plane 0
+    uint32_t own_begin = 0, own_end = 0;   // owned planes, global chunk-i
+    uint32_t n_chunks = 0;
+    DevChunk* d_chunks = nullptr;
+    unsigned char* d_voxels = nullptr;
+    uint32_t slot_capacity = 0, slots_used = 0;
+    uint8_t* d_dirty = nullptr;
+    uint32_t occ_voxels[6] = {0, 0, 0, 0, 0, 0};  // lo xyz, hi xyz (exclusive)
+    uint32_t n_void = 0, n_uniform = 0, n_non_uniform = 0;
+    DeviceMesh mesh;
+};
+
+namespace {
+
+#define IVX_FAIL(ctx, code, ...)                              \
+    do {                                                      \
+        char _b[512];                                         \
+        std::snprintf(_b, sizeof(_b), __VA_ARGS__);           \
+        (ctx)->err = _b;                                      \
+        return (code);                                        \
+    } while (0)
+
+#define CU(ctx, expr)                                                                               \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            cudaGetLastError();                                                                     \
+            IVX_FAIL(ctx, _e == cudaErrorMemoryAllocation ? IVX_ERR_OUT_OF_MEMORY : IVX_ERR_CUDA,   \
+                     "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);   \
+        }                                                                                           \
+    } while (0)
+
+// kernel launch through a launch_* wrapper: counts the launch
+#define KL(ctx, expr)      \
+    do {                   \
+        (ctx)->launches++; \
+        CU(ctx, expr);     \
+    } while (0)
+
+struct Tmp {
+    ivx_ctx* ctx;
+    std::vector<void*> ptrs;
+    explicit Tmp(ivx_ctx* c) : ctx(c) {}
+    ~Tmp() {
+        for (void* p : ptrs) ctx->release(p);
+    }
+    template <typename T>
+    T* get(size_t count) {
+        void* p = ctx->alloc(count * sizeof(T));
+        if (p) ptrs.push_back(p);
+        return static_cast<T*>(p);
+    }
+};
+
+int read_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t n, uint32_t* out) {
+    CU(ctx, cudaMemcpyAsync(ctx->h_pinned, d_src, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out, ctx->h_pinned, n * sizeof(uint32_t));
+    return IVX_OK;
+}
+
+void free_mesh(ivx_ctx* ctx, DeviceMesh& m) {
+    ctx->release(m.positions);
+    ctx->release(m.normals);
+    ctx->release(m.indices);
+    ctx->release(m.index_materials);
+    ctx->release(m.submeshes);
+    ctx->release(m.vertex_ranges);
+    m = DeviceMesh{};
+}
+
+// SDFVoxelGenerator::new (generation.rs:207-258)
+void derive_grid(const HostProgram& p, uint32_t grid_shape[3], float shifted_center[3]) {
+    float ext[3];
+    for (int d = 0; d < 3; ++d) ext[d] = p.domain_hi[d] - p.domain_lo[d];
+    if (p.nodes.empty() || ext[0] == 0.0f || ext[1] == 0.0f || ext[2] == 0.0f) {
+        for (int d = 0; d < 3; ++d) {
+            grid_shape[d] = 0;
+            shifted_center[d] = -0.5f;
+        }
+        return;
+    }
+    for (int d = 0; d < 3; ++d) {
+        float c = std::ceil(ext[d]);
+        uint32_t n = c > 0.0f ? (uint32_t)c : 0u;
+        grid_shape[d] = n + 2;
+        float half = 0.5f * (float)grid_shape[d];
+        float dc = 0.5f * (p.domain_lo[d] + p.domain_hi[d]);
+        shifted_center[d] = (half - dc) - 0.5f;
+    }
+}
+
+constexpr uint32_t SUPER = 4;  // super-block edge in chunks for the conservative fold
+
+int upload_program(ivx_ctx* ctx, ivx_program* prog) {
+    const auto& nodes = prog->host.nodes;
+    std::vector<Instr> root;
+    root.reserve(nodes.size());
+    for (uint32_t i = 0; i < nodes.size(); ++i) {
+        uint32_t op;
+        switch (nodes[i].kind) {
+            case IVX_SPHERE:
+            case IVX_CAPSULE:
+            case IVX_BOX: op = OP_LEAF; break;
+            case IVX_TRANSLATION:
+            case IVX_ROTATION: continue;  // baked into the leaf transforms (atomic.rs:745)
+            case IVX_SCALING: op = OP_SCALE; break;
+            case IVX_MULTIFRACTAL_NOISE: op = OP_NOISE; break;
+            default: op = OP_COMBINE; break;
+        }
+        root.push_back(Instr{(op << 28) | i, 0.0f});
+    }
+    prog->root_len = (uint32_t)root.size();
+    prog->d_nodes = static_cast<ivx_node*>(ctx->alloc(std::max<size_t>(1, nodes.size()) * sizeof(ivx_node)));
+    prog->d_root = static_cast<Instr*>(ctx->alloc(std::max<size_t>(1, root.size()) * sizeof(Instr)));
+    prog->d_root_meta = static_cast<uint32_t*>(ctx->alloc(2 * sizeof(uint32_t)));
+    if (!prog->d_nodes || !prog->d_root || !prog->d_root_meta) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "program upload: out of device memory");
+    if (!nodes.empty())
+        CU(ctx, cudaMemcpyAsync(prog->d_nodes, nodes.data(), nodes.size() * sizeof(ivx_node), cudaMemcpyHostToDevice, ctx->stream));
+    if (!root.empty())
+        CU(ctx, cudaMemcpyAsync(prog->d_root, root.data(), root.size() * sizeof(Instr), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t meta[2] = {0, prog->root_len};
+    CU(ctx, cudaMemcpyAsync(prog->d_root_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IVX_OK;
+}
+
+uint32_t persistent_grid(ivx_ctx* ctx, uint32_t n_work, int blocks_per_sm) {
+    uint32_t g = (uint32_t)(ctx->sm_count * std::max(1, blocks_per_sm));
+    return std::max(1u, std::min(n_work, g));
+}
+
+// Chooses the evaluator's stack placement: levels 0..smem_levels-1 in shared
+// memory (16 KiB each), deeper levels in a global spill buffer.
+int plan_eval_stack(ivx_ctx* ctx, uint32_t max_depth, Tmp& tmp, uint32_t n_active, EvalArgs& ea, uint32_t& grid) {
+    const int need = max_depth > 0 ? (int)max_depth - 1 : 0;
+    const int smem_levels = std::min(need, 12);
+    ea.smem_levels = smem_levels;
+    ea.spill_levels = need - smem_levels;
+    int bps = eval_max_blocks_per_sm(smem_levels);
+    if (bps < 1) bps = 1;
+    grid = persistent_grid(ctx, n_active, bps);
+    ea.spill = nullptr;
+    if (ea.spill_levels > 0) {
+        ea.spill = tmp.get<float>((size_t)grid * ea.spill_levels * 4096);
+        if (!ea.spill) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "evaluator spill buffer: out of device memory");
+    }
+    return IVX_OK;
+}
+
+int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, const ivx_type_generator* tg,
+                  uint32_t i_begin, uint32_t i_end, bool whole, ivx_object** out) {
+    if (!(voxel_extent > 0.0f)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "voxel_extent must be > 0");
+    if (tg->kind > 1) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "unknown voxel type generator kind %u", tg->kind);
+    if (tg->kind == 1 && (tg->n_types == 0 || tg->n_types > 255))
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "GradientNoise needs 1..255 voxel types");
+
+    ivx_object* obj = new (std::nothrow) ivx_object();
+    if (!obj) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "host allocation failed");
+    struct Guard {
+        ivx_ctx* c;
+        ivx_object* o;
+        ~Guard() {
+            if (o) ivx_object_free(c, o);
+        }
+    } guard{ctx, obj};
+
+    GenParams gp{};
+    derive_grid(prog->host, gp.grid_shape, gp.shifted_center);
+    for (int d = 0; d < 3; ++d) gp.chunk_counts[d] = (gp.grid_shape[d] + 15) / 16;
+    if (whole) {
+        i_begin = 0;
+        i_end = gp.chunk_counts[0];
+    }
+    if (i_begin > i_end || i_end > gp.chunk_counts[0])
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "chunk plane range [%u, %u) outside [0, %u)", i_begin, i_end, gp.chunk_counts[0]);
+    gp.ci_begin = i_begin;
+    gp.ci_end = i_end;
+    gp.types = *tg;
+    gp.n_nodes = (uint32_t)prog->host.nodes.size();
+    gp.stack_depth = prog->host.stack_depth;
+
+    obj->voxel_extent = voxel_extent;
+    for (int d = 0; d < 3; ++d) {
+        obj->grid_shape[d] = gp.grid_shape[d];
+        obj->chunk_counts[d] = gp.chunk_counts[d];
+    }
+    obj->first_i = i_begin;
+    obj->own_begin = i_begin;
+    obj->own_end = i_end;
+    obj->nb[0] = i_end - i_begin;
+    obj->nb[1] = gp.chunk_counts[1];
+    obj->nb[2] = gp.chunk_counts[2];
+    const uint32_t n = obj->nb[0] * obj->nb[1] * obj->nb[2];
+    obj->n_chunks = n;
+    if (n == 0) {
+        guard.o = nullptr;
+        *out = obj;
+        return IVX_OK;
+    }
+
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    obj->d_chunks = static_cast<DevChunk*>(ctx->alloc((size_t)n * sizeof(DevChunk)));
+    obj->d_dirty = static_cast<uint8_t*>(ctx->alloc(n));
+    if (!obj->d_chunks || !obj->d_dirty) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "chunk table: out of device memory");
+    CU(ctx, cudaMemsetAsync(obj->d_dirty, 0, n, st));
+
+    uint32_t* counters = ctx->d_scratch;  // [0] err [1] max_depth [2..7] occ [8] total caps [9] n_active [10] n_slots
+    {
+        uint32_t init[16] = {0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        CU(ctx, cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+
+    // ---- level 0: conservative fold per super-block ----
+    uint32_t snb[3];
+    for (int d = 0; d < 3; ++d) snb[d] = (obj->nb[d] + SUPER - 1) / SUPER;
+    const uint32_t n_super = snb[0] * snb[1] * snb[2];
+    const uint32_t L0 = prog->root_len;
+    Instr* sb_instrs = tmp.get<Instr>((size_t)n_super * std::max(1u, L0));
+    uint32_t* sb_off = tmp.get<uint32_t>(n_super);
+    uint32_t* sb_len = tmp.get<uint32_t>(n_super);
+    uint32_t* caps = tmp.get<uint32_t>(n);
+    uint32_t* ch_off = tmp.get<uint32_t>(n);
+    uint32_t* ch_len = tmp.get<uint32_t>(n);
+    if (!sb_instrs || !sb_off || !sb_len || !caps || !ch_off || !ch_len)
+        IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "fold buffers: out of device memory");
+    {
+        std::vector<uint32_t> h(n_super);
+        for (uint32_t b = 0; b < n_super; ++b) h[b] = b * L0;
+        CU(ctx, cudaMemcpyAsync(sb_off, h.data(), n_super * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    }
+    FoldArgs fa{};
+    fa.nodes = prog->d_nodes;
+    fa.gp = gp;
+    fa.n_blocks = n_super;
+    for (int d = 0; d < 3; ++d) fa.nb[d] = snb[d];
+    fa.block_chunks = SUPER;
+    fa.first_chunk[0] = obj->first_i;
+    fa.first_chunk[1] = fa.first_chunk[2] = 0;
+    fa.explicit_origins = nullptr;
+    fa.ratio = 1;
+    fa.parent_nb[0] = fa.parent_nb[1] = fa.parent_nb[2] = 0;
+    fa.parent_instrs = prog->d_root;
+    fa.parent_off = prog->d_root_meta;
+    fa.parent_len = prog->d_root_meta + 1;
+    fa.out_instrs = sb_instrs;
+    fa.out_off = sb_off;
+    fa.out_len = sb_len;
+    fa.chunks = nullptr;
+    fa.max_depth = counters + 1;
+    fa.occ = nullptr;
+    fa.error_flag = counters;
+    KL(ctx, launch_fold(false, fa, st));
+
+    // ---- level 1: exact fold per chunk ----
+    KL(ctx, launch_child_caps(sb_len, n, obj->nb, snb, SUPER, caps, st));
+    KL(ctx, launch_exclusive_scan(caps, ch_off, n, counters + 8, st));
+    uint32_t words[16];
+    if (int rc = read_words(ctx, counters, 16, words)) return rc;
+    if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
+    const uint32_t total_caps = words[8];
+    Instr* ch_instrs = tmp.get<Instr>(std::max<size_t>(1, total_caps));
+    if (!ch_instrs) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "chunk program arena: out of device memory");
+    FoldArgs fb = fa;
+    fb.n_blocks = n;
+    for (int d = 0; d < 3; ++d) {
+        fb.nb[d] = obj->nb[d];
+        fb.parent_nb[d] = snb[d];
+    }
+    fb.block_chunks = 1;
+    fb.ratio = SUPER;
+    fb.parent_instrs = sb_instrs;
+    fb.parent_off = sb_off;
+    fb.parent_len = sb_len;
+    fb.out_instrs = ch_instrs;
+    fb.out_off = ch_off;
+    fb.out_len = ch_len;
+    fb.chunks = obj->d_chunks;
+    fb.occ = counters + 2;
+    KL(ctx, launch_fold(true, fb, st));
+
+    // ---- slot planning ----
+    uint32_t* active_flag = tmp.get<uint32_t>(n);
+    uint32_t* slot_flag = tmp.get<uint32_t>(n);
+    uint32_t* active_scan = tmp.get<uint32_t>(n);
+    uint32_t* slot_of = tmp.get<uint32_t>(n);
+    uint32_t* active_list = tmp.get<uint32_t>(n);
+    if (!active_flag || !slot_flag || !active_scan || !slot_of || !active_list)
+        IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "slot planning: out of device memory");
+    KL(ctx, launch_plan_slots(obj->d_chunks, n, obj->nb, active_flag, slot_flag, st));
+    KL(ctx, launch_exclusive_scan(active_flag, active_scan, n, counters + 9, st));
+    KL(ctx, launch_exclusive_scan(slot_flag, slot_of, n, counters + 10, st));
+    KL(ctx, launch_scatter_active(active_flag, active_scan, n, active_list, st));
+    if (int rc = read_words(ctx, counters, 16, words)) return rc;
+    if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
+    const uint32_t n_active = words[9], n_slots = words[10], max_depth = words[1];
+    obj->slot_capacity = n_slots;
+    obj->slots_used = n_slots;
+    obj->d_voxels = static_cast<unsigned char*>(ctx->alloc(std::max<size_t>(1, (size_t)n_slots) * SLOT_BYTES));
+    if (!obj->d_voxels) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "voxel storage (%u chunks): out of device memory", n_slots);
+    KL(ctx, launch_set_reserved_slots(obj->d_chunks, n, slot_flag, slot_of, slot_of, st));
+
+    // ---- evaluate active chunks ----
+    EvalArgs ea{};
+    ea.nodes = prog->d_nodes;
+    ea.gp = gp;
+    ea.n_active = n_active;
+    ea.active = active_list;
+    for (int d = 0; d < 3; ++d) ea.nb[d] = obj->nb[d];
+    ea.first_i = obj->first_i;
+    ea.explicit_origins = nullptr;
+    ea.instrs = ch_instrs;
+    ea.off = ch_off;
+    ea.len = ch_len;
+    ea.slot_of = slot_of;
+    ea.voxels = obj->d_voxels;
+    ea.chunks = obj->d_chunks;
+    ea.occ = counters + 2;
+    ea.raw_out = nullptr;
+    uint32_t egrid = 1;
+    if (int rc = plan_eval_stack(ctx, max_depth, tmp, n_active, ea, egrid)) return rc;
+    if (n_active) KL(ctx, launch_eval(ea, egrid, st));
+
+    // ---- cross-chunk derived state ----
+    uint32_t* convert_flag = tmp.get<uint32_t>(n);
+    if (!convert_flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "derive: out of device memory");
+    KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, st));
+    KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr, n,
+                                  persistent_grid(ctx, n, 8), st));
+
+    if (int rc = read_words(ctx, counters, 16, words)) return rc;
+    const bool any = words[2] != 0xFFFFFFFFu;
+    for (int d = 0; d < 3; ++d) {
+        obj->occ_voxels[d] = any ? words[2 + d] : 0u;
+        obj->occ_voxels[3 + d] = any ? words[5 + d] + 1u : 0u;
+    }
+    guard.o = nullptr;
+    *out = obj;
+    return IVX_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// small kernels that only the API layer needs
+namespace ivx {
+
+__global__ void k_set_reserved_slots(DevChunk* chunks, uint32_t n, const uint32_t* slot_flag, const uint32_t* slot_scan,
+                                     uint32_t* slot_of) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const uint32_t s = slot_flag[c] ? slot_scan[c] : 0xFFFFFFFFu;
+    slot_of[c] = s;
+    chunks[c].slot = s;
+}
+cudaError_t launch_set_reserved_slots(DevChunk* chunks, uint32_t n, const uint32_t* slot_flag, const uint32_t* slot_scan,
+                                      uint32_t* slot_of, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_set_reserved_slots<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, slot_flag, slot_scan, slot_of);
+    return cudaGetLastError();
+}
+
+__global__ void k_nonuniform_flags(const DevChunk* chunks, uint32_t n, uint32_t* flag) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) flag[c] = chunks[c].kind == 2 ? 1u : 0u;
+}
+cudaError_t launch_nonuniform_flags(const DevChunk* chunks, uint32_t n, uint32_t* flag, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_nonuniform_flags<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, flag);
+    return cudaGetLastError();
+}
+
+// planes → the reference's 3-byte AoS voxels, NonUniform chunks in linear chunk
+// order; chunk descriptors with data_offset = that ordinal (object.rs:574-577)
+__global__ void __launch_bounds__(256) k_pack_voxels(const DevChunk* __restrict__ chunks, uint32_t n,
+                                                     const uint32_t* __restrict__ ordinal,
+                                                     const unsigned char* __restrict__ voxels, ivx_voxel* __restrict__ out,
+                                                     ivx_chunk_desc* __restrict__ out_chunks) {
+    __shared__ uint8_t s[3 * 4096];
+    const int tid = threadIdx.x;
+    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+        const DevChunk ch = chunks[c];
+        if (tid == 0) {
+            ivx_chunk_desc d;
+            d.kind = ch.kind;
+            d.flags = ch.kind == 2 ? ch.flags : 0;
+            for (int q = 0; q < 6; ++q) d.face[q] = ch.kind == 2 ? ch.face[q] : 0;
+            d.uniform_voxel.voxel_type = ch.kind == 1 ? ch.u_type : 0;
+            d.uniform_voxel.signed_distance = ch.kind == 1 ? ch.u_sd : 0;
+            d.uniform_voxel.flags = ch.kind == 1 ? ch.u_flags : 0;
+            d._pad = 0;
+            d.data_offset = ch.kind == 2 ? ordinal[c] : 0;
+            out_chunks[c] = d;
+        }
+        if (ch.kind != 2 || out == nullptr) continue;
+        const unsigned char* slot = voxels + (size_t)ch.slot * SLOT_BYTES;
+        for (int q = 0; q < 3; ++q)
+            *reinterpret_cast<uint4*>(&s[q * 4096 + tid * 16]) = *reinterpret_cast<const uint4*>(slot + q * 4096 + tid * 16);
+        __syncthreads();
+        unsigned char* o = reinterpret_cast<unsigned char*>(out + (size_t)ordinal[c] * 4096);
+        // 12288 output bytes, 48 per thread
+        for (int b = 0; b < 48; ++b) {
+            const int byte = tid * 48 + b;
+            const int v = byte / 3, f = byte % 3;  // f: 0 type, 1 sd, 2 flags
+            o[byte] = s[(f == 0 ? PLANE_TYPE : (f == 1 ? PLANE_SD : PLANE_FLAGS)) + v];
+        }
+        __syncthreads();
+    }
+}
+cudaError_t launch_pack_voxels(const DevChunk* chunks, uint32_t n, const uint32_t* ordinal, const unsigned char* voxels,
+                               ivx_voxel* out, ivx_chunk_desc* out_chunks, uint32_t grid, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_pack_voxels<<<grid, 256, 0, st>>>(chunks, n, ordinal, voxels, out, out_chunks);
+    return cudaGetLastError();
+}
+
+__global__ void k_flag_dirty_exposed(const DevChunk* chunks, const uint8_t* dirty, uint32_t n, uint32_t* exposed_flag,
+                                     uint32_t* dirty_flag) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const bool d = dirty[c] != 0;
+    const DevChunk ch = chunks[c];
+    dirty_flag[c] = d ? 1u : 0u;
+    exposed_flag[c] = (d && ch.kind == 2 && (ch.flags & 0x3F) != 0x3F) ? 1u : 0u;
+}
+cudaError_t launch_flag_dirty_exposed(const DevChunk* chunks, const uint8_t* dirty, uint32_t n, uint32_t* exposed_flag,
+                                      uint32_t* dirty_flag, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_flag_dirty_exposed<<<(n + 255) / 256, 256, 0, st>>>(chunks, dirty, n, exposed_flag, dirty_flag);
+    return cudaGetLastError();
+}
+
+__global__ void k_count_kinds(const DevChunk* chunks, uint32_t n, uint32_t lo, uint32_t hi, uint32_t* out3) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n || c < lo || c >= hi) return;
+    atomicAdd(&out3[chunks[c].kind], 1u);
+}
+
+}  // namespace ivx
+
+namespace {
+
+// meshes the chunks flagged in `work_flag` (ascending linear order) into `m`
+int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMesh& m) {
+    free_mesh(ctx, m);
+    const uint32_t n = obj->n_chunks;
+    if (n == 0) return IVX_OK;
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t* counters = ctx->d_scratch;
+    uint32_t* scan = tmp.get<uint32_t>(n);
+    uint32_t* work = tmp.get<uint32_t>(n);
+    if (!scan || !work) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh: out of device memory");
+    KL(ctx, launch_exclusive_scan(work_flag, scan, n, counters + 16, st));
+    KL(ctx, launch_scatter_active(work_flag, scan, n, work, st));
+    uint32_t words[8];
+    if (int rc = read_words(ctx, counters + 16, 1, words)) return rc;
+    const uint32_t n_work = words[0];
+    m.n_work = n_work;
+    if (n_work == 0) return IVX_OK;
+
+    uint32_t* vcount = tmp.get<uint32_t>(n_work);
+    uint32_t* icount = tmp.get<uint32_t>(n_work);
+    uint32_t* hsub = tmp.get<uint32_t>(n_work);
+    uint32_t* voff = tmp.get<uint32_t>(n_work);
+    uint32_t* ioff = tmp.get<uint32_t>(n_work);
+    uint32_t* sord = tmp.get<uint32_t>(n_work);
+    if (!vcount || !icount || !hsub || !voff || !ioff || !sord) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh: out of device memory");
+    MeshArgs ma{};
+    ma.chunks = obj->d_chunks;
+    ma.voxels = obj->d_voxels;
+    for (int d = 0; d < 3; ++d) ma.nb[d] = obj->nb[d];
+    ma.first_i = obj->first_i;
+    ma.voxel_extent = obj->voxel_extent;
+    ma.work = work;
+    ma.n_work = n_work;
+    ma.vertex_count = vcount;
+    ma.index_count = icount;
+    ma.has_submesh = hsub;
+    const uint32_t grid = persistent_grid(ctx, n_work, 4);
+    KL(ctx, launch_mesh(false, ma, grid, st));
+    KL(ctx, launch_exclusive_scan(vcount, voff, n_work, counters + 17, st));
+    KL(ctx, launch_exclusive_scan(icount, ioff, n_work, counters + 18, st));
+    KL(ctx, launch_exclusive_scan(hsub, sord, n_work, counters + 19, st));
+    if (int rc = read_words(ctx, counters + 17, 3, words)) return rc;
+    m.n_vertices = words[0];
+    m.n_indices = words[1];
+    m.n_submeshes = words[2];
+    m.positions = static_cast<float*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_vertices) * 12));
+    m.normals = static_cast<float*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_vertices) * 12));
+    m.indices = static_cast<uint32_t*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_indices) * 4));
+    m.index_materials = static_cast<ivx_index_materials*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_indices) * 8));
+    m.submeshes = static_cast<ivx_chunk_submesh*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_submeshes) * sizeof(ivx_chunk_submesh)));
+    m.vertex_ranges = static_cast<uint32_t*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_submeshes) * 8));
+    if (!m.positions || !m.normals || !m.indices || !m.index_materials || !m.submeshes || !m.vertex_ranges)
+        IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh buffers: out of device memory");
+    ma.vertex_offset = voff;
+    ma.index_offset = ioff;
+    ma.submesh_ord = sord;
+    ma.positions = m.positions;
+    ma.normals = m.normals;
+    ma.indices = m.indices;
+    ma.index_materials = m.index_materials;
+    ma.submeshes = m.submeshes;
+    ma.vertex_ranges = m.vertex_ranges;
+    KL(ctx, launch_mesh(true, ma, grid, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return IVX_OK;
+}
+
+void fill_mesh_info(const DeviceMesh& m, ivx_mesh_info* out) {
+    out->n_vertices = m.n_vertices;
+    out->n_indices = m.n_indices;
+    out->n_submeshes = m.n_submeshes;
+    out->n_exposed_chunks = m.n_work;
+    out->d_positions = m.positions;
+    out->d_normals = m.normals;
+    out->d_index_materials = m.index_materials;
+    out->d_indices = m.indices;
+    out->d_submeshes = m.submeshes;
+    out->d_vertex_ranges = m.vertex_ranges;
+}
+
+// grows the voxel pool so that `extra` more slots fit
+int ensure_slots(ivx_ctx* ctx, ivx_object* obj, uint32_t extra) {
+    if (obj->slots_used + extra <= obj->slot_capacity) return IVX_OK;
+    const uint32_t want = std::max(obj->slots_used + extra, obj->slot_capacity + obj->slot_capacity / 2 + 64);
+    unsigned char* nv = static_cast<unsigned char*>(ctx->alloc((size_t)want * SLOT_BYTES));
+    if (!nv) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "voxel storage growth (%u chunks): out of device memory", want);
+    if (obj->slots_used)
+        CU(ctx, cudaMemcpyAsync(nv, obj->d_voxels, (size_t)obj->slots_used * SLOT_BYTES, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->release(obj->d_voxels);
+    obj->d_voxels = nv;
+    obj->slot_capacity = want;
+    return IVX_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+uint32_t ivx_abi_version(void) { return IVX_ABI_VERSION; }
+
+int ivx_create(const ivx_config* config, ivx_ctx** out_ctx) {
+    if (!config || !out_ctx) return IVX_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    if (config->abi_version != IVX_ABI_VERSION) return IVX_ERR_INVALID_ARGUMENT;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return IVX_ERR_NO_DEVICE;  // no CPU fallback
+    }
+    if (config->device < 0 || config->device >= count) return IVX_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(config->device) != cudaSuccess) return IVX_ERR_CUDA;
+    ivx_ctx* ctx = new (std::nothrow) ivx_ctx();
+    if (!ctx) return IVX_ERR_OUT_OF_MEMORY;
+    ctx->device = config->device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, config->device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (config->stream) {
+        ctx->stream = static_cast<cudaStream_t>(config->stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return IVX_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    if (cudaMallocHost(&ctx->h_pinned, 64 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess) {
+        ivx_destroy(ctx);
+        return IVX_ERR_OUT_OF_MEMORY;
+    }
+    *out_ctx = ctx;
+    return IVX_OK;
+}
+
+void ivx_destroy(ivx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->pool) cudaFree(b.ptr);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ivx_last_error(const ivx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t ivx_kernel_launch_count(const ivx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ivx_synchronize(ivx_ctx* ctx) {
+    if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IVX_OK;
+}
+
+int ivx_program_build(ivx_ctx* ctx, const ivx_sdf_node* nodes, uint32_t n_nodes, uint32_t root, ivx_program** out) {
+    if (!ctx || !out || (n_nodes && !nodes)) return IVX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    ivx_program* p = new (std::nothrow) ivx_program();
+    if (!p) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "host allocation failed");
+    std::string e = compile_program(nodes, n_nodes, root, p->host);
+    if (!e.empty()) {
+        delete p;
+        IVX_FAIL(ctx, IVX_ERR_GRAPH, "%s", e.c_str());
+    }
+    if (int rc = upload_program(ctx, p)) {
+        ivx_program_free(ctx, p);
+        return rc;
+    }
+    *out = p;
+    return IVX_OK;
+}
+
+int ivx_program_upload(ivx_ctx* ctx, const ivx_node* nodes, uint32_t n_nodes, uint32_t stack_depth,
+                       const float domain_lo[3], const float domain_hi[3], ivx_program** out) {
+    if (!ctx || !out || (n_nodes && !nodes) || !domain_lo || !domain_hi) return IVX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    for (uint32_t i = 0; i < n_nodes; ++i)
+        if (nodes[i].kind > IVX_INTERSECTION) IVX_FAIL(ctx, IVX_ERR_GRAPH, "Invalid SDF node kind %u", nodes[i].kind);
+    ivx_program* p = new (std::nothrow) ivx_program();
+    if (!p) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "host allocation failed");
+    p->host.nodes.assign(nodes, nodes + n_nodes);
+    p->host.stack_depth = stack_depth;
+    for (int d = 0; d < 3; ++d) {
+        p->host.domain_lo[d] = domain_lo[d];
+        p->host.domain_hi[d] = domain_hi[d];
+    }
+    if (int rc = upload_program(ctx, p)) {
+        ivx_program_free(ctx, p);
+        return rc;
+    }
+    *out = p;
+    return IVX_OK;
+}
+
+int ivx_program_info_get(ivx_ctx* ctx, const ivx_program* p, ivx_program_info* out) {
+    if (!ctx || !p || !out) return IVX_ERR_INVALID_ARGUMENT;
+    out->node_count = (uint32_t)p->host.nodes.size();
+    out->stack_depth = p->host.stack_depth;
+    for (int d = 0; d < 3; ++d) {
+        out->domain_lo[d] = p->host.domain_lo[d];
+        out->domain_hi[d] = p->host.domain_hi[d];
+    }
+    return IVX_OK;
+}
+
+int ivx_program_nodes(ivx_ctx* ctx, const ivx_program* p, ivx_node* out, uint32_t capacity) {
+    if (!ctx || !p || (!out && capacity)) return IVX_ERR_INVALID_ARGUMENT;
+    if (capacity < p->host.nodes.size()) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %zu nodes", p->host.nodes.size());
+    if (!p->host.nodes.empty()) std::memcpy(out, p->host.nodes.data(), p->host.nodes.size() * sizeof(ivx_node));
+    return IVX_OK;
+}
+
+void ivx_program_free(ivx_ctx* ctx, ivx_program* p) {
+    if (!ctx || !p) return;
+    ctx->release(p->d_nodes);
+    ctx->release(p->d_root);
+    ctx->release(p->d_root_meta);
+    delete p;
+}
+
+int ivx_program_eval_chunks(ivx_ctx* ctx, const ivx_program* prog, const float* origins, uint32_t n_chunks, float* out) {
+    if (!ctx || !prog || (n_chunks && (!origins || !out))) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (n_chunks == 0) return IVX_OK;
+    if (prog->host.nodes.empty()) {
+        for (size_t i = 0; i < (size_t)n_chunks * 4096; ++i) out[i] = 0.02f * 127.0f;  // atomic.rs:642-645
+        return IVX_OK;
+    }
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t* counters = ctx->d_scratch;
+    uint32_t init[2] = {0, 0};
+    CU(ctx, cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    float* d_org = tmp.get<float>((size_t)n_chunks * 3);
+    float* d_out = tmp.get<float>((size_t)n_chunks * 4096);
+    Instr* instrs = tmp.get<Instr>((size_t)n_chunks * std::max(1u, prog->root_len));
+    uint32_t* off = tmp.get<uint32_t>(n_chunks);
+    uint32_t* len = tmp.get<uint32_t>(n_chunks);
+    if (!d_org || !d_out || !instrs || !off || !len) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "eval_chunks: out of device memory");
+    std::vector<uint32_t> h(n_chunks);
+    for (uint32_t b = 0; b < n_chunks; ++b) h[b] = b * prog->root_len;
+    CU(ctx, cudaMemcpyAsync(off, h.data(), n_chunks * 4, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_org, origins, (size_t)n_chunks * 12, cudaMemcpyHostToDevice, st));
+    FoldArgs fa{};
+    fa.nodes = prog->d_nodes;
+    fa.gp.n_nodes = (uint32_t)prog->host.nodes.size();
+    fa.n_blocks = n_chunks;
+    fa.block_chunks = 1;
+    fa.explicit_origins = d_org;
+    fa.ratio = 1;
+    fa.parent_instrs = prog->d_root;
+    fa.parent_off = prog->d_root_meta;
+    fa.parent_len = prog->d_root_meta + 1;
+    fa.out_instrs = instrs;
+    fa.out_off = off;
+    fa.out_len = len;
+    fa.chunks = nullptr;
+    fa.max_depth = counters + 1;
+    fa.occ = nullptr;
+    fa.error_flag = counters;
+    KL(ctx, launch_fold(true, fa, st));
+    uint32_t words[2];
+    if (int rc = read_words(ctx, counters, 2, words)) return rc;
+    if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
+    EvalArgs ea{};
+    ea.nodes = prog->d_nodes;
+    ea.n_active = n_chunks;
+    ea.active = nullptr;
+    ea.explicit_origins = d_org;
+    ea.instrs = instrs;
+    ea.off = off;
+    ea.len = len;
+    ea.raw_out = d_out;
+    uint32_t grid = 1;
+    if (int rc = plan_eval_stack(ctx, words[1], tmp, n_chunks, ea, grid)) return rc;
+    KL(ctx, launch_eval(ea, grid, st));
+    CU(ctx, cudaMemcpyAsync(out, d_out, (size_t)n_chunks * 4096 * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return IVX_OK;
+}
+
+int ivx_object_generate(ivx_ctx* ctx, const ivx_program* program, float voxel_extent, const ivx_type_generator* tg,
+                        ivx_object** out) {
+    if (!ctx || !program || !tg || !out) return IVX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    return generate_impl(ctx, program, voxel_extent, tg, 0, 0, true, out);
+}
+
+int ivx_object_generate_slab(ivx_ctx* ctx, const ivx_program* program, float voxel_extent, const ivx_type_generator* tg,
+                             uint32_t chunk_i_begin, uint32_t chunk_i_end, ivx_object** out) {
+    if (!ctx || !program || !tg || !out) return IVX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    return generate_impl(ctx, program, voxel_extent, tg, chunk_i_begin, chunk_i_end, false, out);
+}
+
+int ivx_object_info_get(ivx_ctx* ctx, const ivx_object* obj, ivx_object_info* out) {
+    if (!ctx || !obj || !out) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    std::memset(out, 0, sizeof(*out));
+    out->voxel_extent = obj->voxel_extent;
+    for (int d = 0; d < 3; ++d) {
+        out->grid_shape[d] = obj->grid_shape[d];
+        out->chunk_counts[d] = obj->chunk_counts[d];
+    }
+    out->chunk_i_begin = obj->own_begin;
+    out->chunk_i_end = obj->own_end;
+    if (obj->n_chunks) {
+        uint32_t* c3 = ctx->d_scratch + 24;
+        CU(ctx, cudaMemsetAsync(c3, 0, 12, ctx->stream));
+        ctx->launches++;
+        k_count_kinds<<<(obj->n_chunks + 255) / 256, 256, 0, ctx->stream>>>(obj->d_chunks, obj->n_chunks, 0, obj->n_chunks, c3);
+        CU(ctx, cudaGetLastError());
+        uint32_t w[3];
+        if (int rc = read_words(ctx, c3, 3, w)) return rc;
+        out->n_void = w[0];
+        out->n_uniform = w[1];
+        out->n_non_uniform = w[2];
+    }
+    for (int d = 0; d < 3; ++d) {
+        out->occupied_voxel_ranges[2 * d] = obj->occ_voxels[d];
+        out->occupied_voxel_ranges[2 * d + 1] = obj->occ_voxels[3 + d];
+        out->occupied_chunk_ranges[2 * d] = obj->occ_voxels[d] / 16;
+        out->occupied_chunk_ranges[2 * d + 1] = (obj->occ_voxels[3 + d] + 15) / 16;
+    }
+    out->device_bytes = (uint64_t)obj->slot_capacity * SLOT_BYTES + (uint64_t)obj->n_chunks * (sizeof(DevChunk) + 1);
+    return IVX_OK;
+}
+
+int ivx_object_download(ivx_ctx* ctx, const ivx_object* obj, ivx_chunk_desc* chunks, size_t chunk_capacity,
+                        ivx_voxel* voxels, size_t voxel_capacity) {
+    if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    const uint32_t n = obj->n_chunks;
+    if (n == 0) return IVX_OK;
+    if (!chunks || chunk_capacity < n) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u chunk descriptors", n);
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t* flag = tmp.get<uint32_t>(n);
+    uint32_t* ord = tmp.get<uint32_t>(n);
+    ivx_chunk_desc* d_desc = tmp.get<ivx_chunk_desc>(n);
+    if (!flag || !ord || !d_desc) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "download: out of device memory");
+    KL(ctx, launch_nonuniform_flags(obj->d_chunks, n, flag, st));
+    KL(ctx, launch_exclusive_scan(flag, ord, n, ctx->d_scratch + 28, st));
+    uint32_t nnu;
+    if (int rc = read_words(ctx, ctx->d_scratch + 28, 1, &nnu)) return rc;
+    ivx_voxel* d_vox = nullptr;
+    if (voxels) {
+        if (voxel_capacity < (size_t)nnu * 4096) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %zu voxels", (size_t)nnu * 4096);
+        d_vox = tmp.get<ivx_voxel>(std::max<size_t>(1, (size_t)nnu * 4096));
+        if (!d_vox) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "download: out of device memory");
+    }
+    KL(ctx, launch_pack_voxels(obj->d_chunks, n, ord, obj->d_voxels, d_vox, d_desc, persistent_grid(ctx, n, 8), st));
+    CU(ctx, cudaMemcpyAsync(chunks, d_desc, (size_t)n * sizeof(ivx_chunk_desc), cudaMemcpyDeviceToHost, st));
+    if (d_vox && nnu) CU(ctx, cudaMemcpyAsync(voxels, d_vox, (size_t)nnu * 4096 * sizeof(ivx_voxel), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return IVX_OK;
+}
+
+void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
+    if (!ctx || !obj) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_mesh(ctx, obj->mesh);
+    ctx->release(obj->d_chunks);
+    ctx->release(obj->d_voxels);
+    ctx->release(obj->d_dirty);
+    delete obj;
+}
+
+int ivx_object_mesh(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
+    if (!ctx || !obj || !out) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    std::memset(out, 0, sizeof(*out));
+    if (obj->n_chunks == 0) return IVX_OK;
+    Tmp tmp(ctx);
+    uint32_t* flag = tmp.get<uint32_t>(obj->n_chunks);
+    if (!flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh: out of device memory");
+    KL(ctx, launch_exposed_flags(obj->d_chunks, obj->n_chunks, obj->nb, obj->own_begin - obj->first_i,
+                                 obj->own_end - obj->first_i, flag, ctx->stream));
+    if (int rc = mesh_impl(ctx, obj, flag, obj->mesh)) return rc;
+    fill_mesh_info(obj->mesh, out);
+    return IVX_OK;
+}
+
+int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* obj, float* positions, float* normals,
+                      ivx_index_materials* index_materials, uint32_t* indices, ivx_chunk_submesh* submeshes,
+                      uint32_t* vertex_ranges) {
+    if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    const DeviceMesh& m = obj->mesh;
+    cudaStream_t st = ctx->stream;
+    if (positions && m.n_vertices) CU(ctx, cudaMemcpyAsync(positions, m.positions, (size_t)m.n_vertices * 12, cudaMemcpyDeviceToHost, st));
+    if (normals && m.n_vertices) CU(ctx, cudaMemcpyAsync(normals, m.normals, (size_t)m.n_vertices * 12, cudaMemcpyDeviceToHost, st));
+    if (index_materials && m.n_indices) CU(ctx, cudaMemcpyAsync(index_materials, m.index_materials, (size_t)m.n_indices * 8, cudaMemcpyDeviceToHost, st));
+    if (indices && m.n_indices) CU(ctx, cudaMemcpyAsync(indices, m.indices, (size_t)m.n_indices * 4, cudaMemcpyDeviceToHost, st));
+    if (submeshes && m.n_submeshes) CU(ctx, cudaMemcpyAsync(submeshes, m.submeshes, (size_t)m.n_submeshes * sizeof(ivx_chunk_submesh), cudaMemcpyDeviceToHost, st));
+    if (vertex_ranges && m.n_submeshes) CU(ctx, cudaMemcpyAsync(vertex_ranges, m.vertex_ranges, (size_t)m.n_submeshes * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return IVX_OK;
+}
+
+int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3], float radius, float influence_radius,
+                             ivx_absorb_stats* out_stats) {
+    if (!ctx || !obj || !center) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (out_stats) std::memset(out_stats, 0, sizeof(*out_stats));
+    if (obj->first_i != 0 || obj->nb[0] != obj->chunk_counts[0])
+        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "absorption on a slab-partitioned object is not supported");
+    const uint32_t n = obj->n_chunks;
+    if (n == 0) return IVX_OK;
+    // voxel_ranges_touching_aab (intersection.rs:766-784) on the occupied voxel ranges
+    AbsorbRange r{};
+    bool empty = false;
+    for (int d = 0; d < 3; ++d) {
+        const float lo = center[d] - influence_radius, hi = center[d] + influence_radius;
+        const float fl = std::fmax(std::floor(lo), 0.0f);
+        const float ce = std::ceil(hi);
+        const uint32_t s = fl >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fl;
+        const uint32_t e = !(ce > 0.0f) ? 0u : (ce >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)ce);
+        r.v0[d] = std::max(obj->occ_voxels[d], s);
+        r.v1[d] = std::min(obj->occ_voxels[3 + d], e);
+        if (r.v0[d] >= r.v1[d]) empty = true;
+        r.c0[d] = r.v0[d] / 16;
+        r.c1[d] = (r.v1[d] + 15) / 16;
+    }
+    if (empty) return IVX_OK;
+    const uint32_t n_range = (r.c1[0] - r.c0[0]) * (r.c1[1] - r.c0[1]) * (r.c1[2] - r.c0[2]);
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t* counters = ctx->d_scratch + 32;  // [0] new slots [1..4] stats [5] new slots (boundary) [6..11] occ
+    uint32_t* need = tmp.get<uint32_t>(n_range);
+    uint32_t* ord = tmp.get<uint32_t>(n_range);
+    if (!need || !ord) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
+    {
+        uint32_t init[12] = {0, 0, 0, 0, 0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
+        CU(ctx, cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    KL(ctx, launch_absorb_plan(obj->d_chunks, obj->nb, r, need, n_range, st));
+    KL(ctx, launch_exclusive_scan(need, ord, n_range, counters, st));
+    uint32_t w[12];
+    if (int rc = read_words(ctx, counters, 1, w)) return rc;
+    if (int rc = ensure_slots(ctx, obj, w[0])) return rc;
+    AbsorbArgs aa{};
+    aa.chunks = obj->d_chunks;
+    aa.nb = make_uint3(obj->nb[0], obj->nb[1], obj->nb[2]);
+    aa.range = r;
+    aa.n_range = n_range;
+    aa.voxels = obj->d_voxels;
+    for (int d = 0; d < 3; ++d) aa.center[d] = center[d];
+    aa.radius = radius;
+    aa.influence_radius_sq = influence_radius * influence_radius;  // Sphere::radius_squared = radius.powi(2)
+    aa.first_new_slot = obj->slots_used;
+    aa.new_slot_ord = ord;
+    aa.dirty = obj->d_dirty;
+    aa.stats = counters + 1;
+    KL(ctx, launch_absorb_apply(aa, persistent_grid(ctx, n_range, 4), st));
+    obj->slots_used += w[0];
+
+    // boundary refresh over chunk range [start-1, end) (intersection.rs:391-393)
+    AbsorbRange b = r;
+    for (int d = 0; d < 3; ++d) b.c0[d] = r.c0[d] > 0 ? r.c0[d] - 1 : 0;
+    uint8_t* face_mask = tmp.get<uint8_t>(n);
+    uint32_t* convert_flag = tmp.get<uint32_t>(n);
+    uint32_t* need2 = tmp.get<uint32_t>(n);
+    uint32_t* ord2 = tmp.get<uint32_t>(n);
+    uint32_t* slot_of = tmp.get<uint32_t>(n);
+    if (!face_mask || !convert_flag || !need2 || !ord2 || !slot_of) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
+    KL(ctx, launch_absorb_face_mask(obj->nb, b, face_mask, n, st));
+    KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, face_mask, convert_flag, st));
+    KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need2, st));
+    KL(ctx, launch_exclusive_scan(need2, ord2, n, counters + 5, st));
+    if (int rc = read_words(ctx, counters, 12, w)) return rc;
+    if (int rc = ensure_slots(ctx, obj, w[5])) return rc;
+    KL(ctx, launch_assign_slots(obj->d_chunks, need2, ord2, obj->slots_used, n, slot_of, st));
+    obj->slots_used += w[5];
+    KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n,
+                                  persistent_grid(ctx, n, 8), st));
+    if (w[4]) {
+        // removed chunks → update_occupied_ranges (intersection.rs:387-389)
+        KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, counters + 6,
+                                       persistent_grid(ctx, n, 8), st));
+        uint32_t o[6];
+        if (int rc = read_words(ctx, counters + 6, 6, o)) return rc;
+        const bool any = o[0] != 0xFFFFFFFFu;
+        for (int d = 0; d < 3; ++d) {
+            obj->occ_voxels[d] = any ? o[d] : 0u;
+            obj->occ_voxels[3 + d] = any ? o[3 + d] + 1u : 0u;
+        }
+    }
+    CU(ctx, cudaStreamSynchronize(st));
+    if (out_stats) {
+        out_stats->touched_chunks = w[1];
+        out_stats->touched_voxels = w[2];
+        out_stats->emptied_voxels = w[3];
+        out_stats->removed_chunks = w[4];
+        uint32_t cnt = 0;
+        ivx_object_dirty_chunks(ctx, obj, nullptr, 0, &cnt);
+        out_stats->dirty_chunks = cnt;
+    }
+    return IVX_OK;
+}
+
+int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* obj, uint32_t* out, uint32_t capacity, uint32_t* out_count) {
+    if (!ctx || !obj || !out_count) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    *out_count = 0;
+    const uint32_t n = obj->n_chunks;
+    if (n == 0) return IVX_OK;
+    std::vector<uint8_t> h(n);
+    CU(ctx, cudaMemcpyAsync(h.data(), obj->d_dirty, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t cnt = 0;
+    for (uint32_t c = 0; c < n; ++c)
+        if (h[c]) {
+            if (out && cnt < capacity) out[cnt] = c;
+            cnt++;
+        }
+    *out_count = cnt;
+    return IVX_OK;
+}
+
+int ivx_object_remesh_dirty(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
+    if (!ctx || !obj || !out) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    std::memset(out, 0, sizeof(*out));
+    const uint32_t n = obj->n_chunks;
+    if (n == 0) return IVX_OK;
+    Tmp tmp(ctx);
+    uint32_t* exposed = tmp.get<uint32_t>(n);
+    uint32_t* dflag = tmp.get<uint32_t>(n);
+    if (!exposed || !dflag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "remesh: out of device memory");
+    KL(ctx, launch_flag_dirty_exposed(obj->d_chunks, obj->d_dirty, n, exposed, dflag, ctx->stream));
+    if (int rc = mesh_impl(ctx, obj, exposed, obj->mesh)) return rc;
+    CU(ctx, cudaMemsetAsync(obj->d_dirty, 0, n, ctx->stream));  // mark_chunk_meshes_synchronized
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    fill_mesh_info(obj->mesh, out);
+    return IVX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,769 @@
+// SDF generation kernels (sm_100a).
+//
+//   k_fold<false>  conservative program specialisation per super-block
+//   k_fold<true>   exact per-chunk specialisation: reproduces every cull /
+//                  apply decision of compute_signed_distances_for_block
+//                  (generation/sdf/atomic.rs:633-875) from the chunk AABB and
+//                  the 14 sampled voxels its predicates read (atomic.rs:1661-1797)
+//   k_eval         evaluates the specialised program over the 4096 voxels of a
+//                  chunk, quantises, classifies, assigns voxel types and
+//                  in-chunk adjacency flags, and writes the three 4 KiB planes
+//                  (generation.rs:293-371, voxel_type.rs:54-168,
+//                  object.rs:1890-1964, 2673-2756)
+//
+// The reference runs the whole post-order program on every chunk, touching a
+// 16 KiB array per node even when the node is culled. Here the decisions are
+// made first (warp per chunk, 14 lanes = 14 sampled voxels), constant
+// sub-trees are folded, dropped operands are never evaluated, and only the
+// surviving instructions are run on all voxels — with identical results.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ivx {
+
+__constant__ uint8_t c_perm[256] = {
+    151, 160, 137, 91,  90,  15,  131, 13,  201, 95,  96,  53,  194, 233, 7,   225, 140, 36,  103,
+    30,  69,  142, 8,   99,  37,  240, 21,  10,  23,  190, 6,   148, 247, 120, 234, 75,  0,   26,
+    197, 62,  94,  252, 219, 203, 117, 35,  11,  32,  57,  177, 33,  88,  237, 149, 56,  87,  174,
+    20,  125, 136, 171, 168, 68,  175, 74,  165, 71,  134, 139, 48,  27,  166, 77,  146, 158, 231,
+    83,  111, 229, 122, 60,  211, 133, 230, 220, 105, 92,  41,  55,  46,  245, 40,  244, 102, 143,
+    54,  65,  25,  63,  161, 1,   216, 80,  73,  209, 76,  132, 187, 208, 89,  18,  169, 200, 196,
+    135, 130, 116, 188, 159, 86,  164, 100, 109, 198, 173, 186, 3,   64,  52,  217, 226, 250, 124,
+    123, 5,   202, 38,  147, 118, 126, 255, 82,  85,  212, 207, 206, 59,  227, 47,  16,  58,  17,
+    182, 189, 28,  42,  223, 183, 170, 213, 119, 248, 152, 2,   44,  154, 163, 70,  221, 153, 101,
+    155, 167, 43,  172, 9,   129, 22,  39,  253, 19,  98,  108, 110, 79,  113, 224, 232, 178, 185,
+    112, 104, 218, 246, 97,  228, 251, 34,  242, 193, 238, 210, 144, 12,  191, 179, 162, 241, 81,
+    51,  145, 235, 249, 14,  239, 107, 49,  192, 214, 31,  181, 199, 106, 157, 184, 84,  204, 176,
+    115, 121, 50,  45,  127, 4,   150, 254, 138, 236, 205, 93,  222, 114, 67,  29,  24,  72,  243,
+    141, 128, 195, 78,  66,  215, 61,  156, 180};
+
+// ---------------------------------------------------------------------------
+// Noise frame of a MultifractalNoise node for one block
+// (atomic.rs:1430-1451, 1520-1537)
+struct NoiseFrame {
+    f3 o, dxn, dyn, dzn;  // origin_for_noise, d*_for_noise
+    float freq;           // unscaled_frequency
+    bool rotated;
+};
+__device__ __forceinline__ NoiseFrame make_noise_frame(const ivx_node& n, f3 block_lo) {
+    const float* M = n.transform_to_node_space;
+    f3 origin = transform_point(M, block_lo);
+    f3 dx = mk3(M[0], M[1], M[2]), dy = mk3(M[4], M[5], M[6]), dz = mk3(M[8], M[9], M[10]);
+    float inverse_scale = norm3(dx);
+    float scale = 1.0f / inverse_scale;
+    NoiseFrame f;
+    f.freq = n.p[0] * inverse_scale;
+    f.o = scale * origin;
+    f.dxn = scale * dx;
+    f.dyn = scale * dy;
+    f.dzn = scale * dz;
+    f.rotated = fabsf(dx.x * inverse_scale - 1.0f) > 1e-6f || fabsf(dy.y * inverse_scale - 1.0f) > 1e-6f;
+    return f;
+}
+// fbm_3d_offset(pos.z,1,pos.y,1,pos.x,1): simdnoise x := our z
+__device__ __forceinline__ float noise_at(const ivx_node& n, float freq, f3 pos) {
+    return fbm3(pos.z * freq, pos.y * freq, pos.x * freq, n.p[1], n.p[2], n.octaves, (int32_t)n.seed);
+}
+// Noise coordinates of voxel (i, j, k) of the block for the un-rotated block
+// call (atomic.rs:1487-1502): simdnoise walks x (our k) as start + lane for one
+// 8-wide vector then += 8, and y / z (our j / i) by repeated += 1.0.
+__device__ __forceinline__ float block_noise_x(float start, int k) {
+    return k < 8 ? start + (float)k : (start + (float)(k - 8)) + 8.0f;
+}
+__device__ __forceinline__ float accumulate_ones(float start, int n) {
+    for (int t = 0; t < n; ++t) start = start + 1.0f;
+    return start;
+}
+__device__ __forceinline__ float noise_for_voxel(const ivx_node& n, const NoiseFrame& f, int i, int j, int k) {
+    if (f.rotated) {
+        f3 pos = (f.o + (float)i * f.dxn) + (float)j * f.dyn;
+        for (int t = 0; t < k; ++t) pos = pos + f.dzn;
+        return noise_at(n, f.freq, pos);
+    }
+    float zc = accumulate_ones(f.o.x, i), yc = accumulate_ones(f.o.y, j), xc = block_noise_x(f.o.z, k);
+    return fbm3(xc * f.freq, yc * f.freq, zc * f.freq, n.p[1], n.p[2], n.octaves, (int32_t)n.seed);
+}
+
+// The 26 block test samples (atomic.rs:1683-1797): position of sample t and the
+// lane (0..13) that holds the voxel whose value the reference reads for it.
+__device__ __forceinline__ f3 test_position(int t, f3 o, f3 dx, f3 dy, f3 dz) {
+    const float s = 15.0f, h = 7.5f;
+    switch (t) {
+        case 0: return o;
+        case 1: return o + s * dx;
+        case 2: return o + s * dy;
+        case 3: return o + s * dz;
+        case 4: return o + s * (dx + dy);
+        case 5: return o + s * (dx + dz);
+        case 6: return o + s * (dy + dz);
+        case 7: return o + s * ((dx + dy) + dz);
+        case 8: return o + h * dx;
+        case 9: return (o + h * dx) + s * dy;
+        case 10: return (o + h * dx) + s * dz;
+        case 11: return (o + h * dx) + s * (dy + dz);
+        case 12: return o + h * dy;
+        case 13: return (o + h * dy) + s * dx;
+        case 14: return (o + h * dy) + s * dz;
+        case 15: return (o + h * dy) + s * (dx + dz);
+        case 16: return o + h * dz;
+        case 17: return (o + h * dz) + s * dx;
+        case 18: return (o + h * dz) + s * dy;
+        case 19: return (o + h * dz) + s * (dx + dy);
+        case 20: return (o + h * dy) + h * dz;
+        case 21: return ((o + s * dx) + h * dy) + h * dz;
+        case 22: return (o + h * dx) + h * dz;
+        case 23: return ((o + s * dy) + h * dx) + h * dz;
+        case 24: return (o + h * dx) + h * dy;
+        default: return ((o + s * dz) + h * dx) + h * dy;
+    }
+}
+__constant__ int8_t c_test_lane[26] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 2, 3, 6, 0, 1, 3, 5, 0, 1, 2, 4, 8, 9, 10, 11, 12, 13};
+// voxel (i,j,k) sampled by lane l < 14
+__constant__ int8_t c_sample_ijk[14][3] = {{0, 0, 0},   {15, 0, 0},  {0, 15, 0},  {0, 0, 15}, {15, 15, 0},
+                                           {15, 0, 15}, {0, 15, 15}, {15, 15, 15}, {0, 8, 8},  {15, 8, 8},
+                                           {8, 0, 8},   {8, 15, 8},  {8, 8, 0},    {8, 8, 15}};
+
+// ---------------------------------------------------------------------------
+constexpr int FOLD_WARPS = 4;
+constexpr int FOLD_TILE = 256;   // instructions classified per phase-1 tile
+constexpr int FOLD_MAX_DEPTH = 64;
+
+struct FoldWarpSmem {
+    uint8_t cls[FOLD_TILE];
+    uint32_t seg_start[FOLD_MAX_DEPTH];
+    float cval[FOLD_MAX_DEPTH];
+    uint8_t is_const[FOLD_MAX_DEPTH];
+    float val[FOLD_MAX_DEPTH][32];  // EXACT only: sampled values per stack slot
+};
+
+template <bool EXACT>
+__global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t block = blockIdx.x * FOLD_WARPS + warp;
+    if (block >= a.n_blocks) return;
+    FoldWarpSmem& S = *reinterpret_cast<FoldWarpSmem*>(
+        smem_raw + (size_t)warp * (EXACT ? sizeof(FoldWarpSmem) : offsetof(FoldWarpSmem, val)));
+
+    // ---- block geometry ----
+    f3 lo, hi;
+    uint32_t parent = 0;
+    uint32_t bc[3] = {0, 0, 0};
+    if (a.explicit_origins) {
+        lo = mk3(a.explicit_origins[3 * block], a.explicit_origins[3 * block + 1], a.explicit_origins[3 * block + 2]);
+        hi = lo + mk3(16.0f, 16.0f, 16.0f);
+    } else {
+        bc[2] = block % a.nb[2];
+        bc[1] = (block / a.nb[2]) % a.nb[1];
+        bc[0] = block / (a.nb[2] * a.nb[1]);
+        uint32_t px = bc[0] / a.ratio, py = bc[1] / a.ratio, pz = bc[2] / a.ratio;
+        parent = a.parent_nb[0] == 0 ? 0u : (px * a.parent_nb[1] + py) * a.parent_nb[2] + pz;
+        const float bs = (float)(a.block_chunks * 16u);
+        // chunk_origin_in_root_space = origin as f32 - shifted_grid_center (generation.rs:314-315)
+        lo = mk3((float)((bc[0] * a.block_chunks + a.first_chunk[0]) * 16u) - a.gp.shifted_center[0],
+                 (float)((bc[1] * a.block_chunks + a.first_chunk[1]) * 16u) - a.gp.shifted_center[1],
+                 (float)((bc[2] * a.block_chunks + a.first_chunk[2]) * 16u) - a.gp.shifted_center[2]);
+        hi = lo + mk3(bs, bs, bs);
+    }
+    const Instr* __restrict__ pin = a.parent_instrs + a.parent_off[parent];
+    const uint32_t plen = a.parent_len[parent];
+    Instr* __restrict__ out = a.out_instrs + a.out_off[block];
+
+    // chunks entirely beyond the grid are void without looking at the program
+    // (generation.rs:299-312)
+    if (EXACT && !a.explicit_origins) {
+        if ((bc[0] + a.first_chunk[0]) * 16u >= a.gp.grid_shape[0] ||
+            (bc[1] + a.first_chunk[1]) * 16u >= a.gp.grid_shape[1] ||
+            (bc[2] + a.first_chunk[2]) * 16u >= a.gp.grid_shape[2] || a.gp.n_nodes == 0) {
+            if (lane == 0) {
+                a.out_len[block] = 0;
+                DevChunk c{};
+                c.kind = 0;
+                c.pre = PRE_VOID;
+                a.chunks[block] = c;
+            }
+            return;
+        }
+    }
+
+    int si = 0, sj = 0, sk = 0;
+    if (EXACT) {
+        int sl = lane < 14 ? lane : 0;
+        si = c_sample_ijk[sl][0];
+        sj = c_sample_ijk[sl][1];
+        sk = c_sample_ijk[sl][2];
+    }
+
+    uint32_t olen = 0;
+    int sp = 0;
+    int max_sp = 0;
+    bool overflow = false;
+
+    for (uint32_t base = 0; base < plen; base += FOLD_TILE) {
+        const uint32_t tile_n = min((uint32_t)FOLD_TILE, plen - base);
+        // ---- phase 1: AABB classification, one instruction per lane ----
+        for (uint32_t t = lane; t < tile_n; t += 32) {
+            Instr in = pin[base + t];
+            uint32_t op = in.op_node >> 28;
+            uint8_t cls = 0;
+            if (op == OP_LEAF || op == OP_NOISE || op == OP_COMBINE) {
+                const ivx_node& n = a.nodes[in.op_node & 0x0FFFFFFFu];
+                f3 blo, bhi;
+                aabb_of_transformed(n.transform_to_node_space, lo, hi, blo, bhi);
+                if (EXACT) {
+                    if (box_lies_outside(n.domain_lo, n.domain_hi, blo, bhi))
+                        cls = 1;
+                    else if (op == OP_LEAF && sym_box_contains(leaf_interior_half_extents(n), blo, bhi))
+                        cls = 2;
+                } else {
+                    // conservative: must hold for every chunk inside this block despite f32 rounding
+                    float mx = fmaxf(fmaxf(fabsf(blo.x), fabsf(bhi.x)),
+                                     fmaxf(fmaxf(fabsf(blo.y), fabsf(bhi.y)), fmaxf(fabsf(blo.z), fabsf(bhi.z))));
+                    float eps = 1e-4f * (1.0f + mx);
+                    bool outside = (bhi.x + eps < n.domain_lo[0]) || (bhi.y + eps < n.domain_lo[1]) ||
+                                   (bhi.z + eps < n.domain_lo[2]) || (n.domain_hi[0] + eps < blo.x) ||
+                                   (n.domain_hi[1] + eps < blo.y) || (n.domain_hi[2] + eps < blo.z);
+                    if (outside) {
+                        cls = 1;
+                    } else if (op == OP_LEAF) {
+                        f3 h = leaf_interior_half_extents(n);
+                        bool inside = (blo.x - eps >= -h.x) && (blo.y - eps >= -h.y) && (blo.z - eps >= -h.z) &&
+                                      (bhi.x + eps <= h.x) && (bhi.y + eps <= h.y) && (bhi.z + eps <= h.z);
+                        if (inside) cls = 2;
+                    }
+                }
+            }
+            S.cls[t] = cls;
+        }
+        __syncwarp();
+
+        // ---- phase 2: sequential fold (warp-uniform control flow) ----
+        for (uint32_t t = 0; t < tile_n; ++t) {
+            __syncwarp();  // lane 0's stack bookkeeping of the previous step is visible to all lanes
+            const Instr in = pin[base + t];
+            const uint32_t op = in.op_node >> 28;
+            const uint32_t ni = in.op_node & 0x0FFFFFFFu;
+            const uint8_t cls = S.cls[t];
+            if (op == OP_CONST || (op == OP_LEAF && cls != 0)) {
+                float c = in.value;
+                if (op == OP_LEAF) {
+                    float m = a.nodes[ni].margin;
+                    c = cls == 1 ? m : -m;
+                }
+                if (sp >= FOLD_MAX_DEPTH) { overflow = true; break; }
+                if (lane == 0) {
+                    S.seg_start[sp] = olen;
+                    S.cval[sp] = c;
+                    S.is_const[sp] = 1;
+                    out[olen] = Instr{(uint32_t)OP_CONST << 28, c};
+                }
+                if (EXACT) S.val[sp][lane] = c;
+                olen += 1;
+                sp += 1;
+                max_sp = max(max_sp, sp);
+            } else if (op == OP_LEAF) {
+                if (sp >= FOLD_MAX_DEPTH) { overflow = true; break; }
+                if (lane == 0) {
+                    S.seg_start[sp] = olen;
+                    S.is_const[sp] = 0;
+                    out[olen] = in;
+                }
+                if (EXACT) {
+                    // update_signed_distances_for_block (atomic.rs:1601-1627) at the sampled voxel
+                    const ivx_node& n = a.nodes[ni];
+                    const float* M = n.transform_to_node_space;
+                    f3 origin = transform_point(M, lo);
+                    f3 dx = mk3(M[0], M[1], M[2]), dy = mk3(M[4], M[5], M[6]), dz = mk3(M[8], M[9], M[10]);
+                    f3 pos = (origin + (float)si * dx) + (float)sj * dy;
+                    for (int q = 0; q < sk; ++q) pos = pos + dz;
+                    S.val[sp][lane] = sd_leaf(n.kind, n.p, pos);
+                }
+                olen += 1;
+                sp += 1;
+                max_sp = max(max_sp, sp);
+            } else if (op == OP_SCALE) {
+                const float s = a.nodes[ni].p[0];
+                __syncwarp();
+                const bool tc = S.is_const[sp - 1] != 0;
+                if (tc) {
+                    float c = S.cval[sp - 1] * s;
+                    __syncwarp();
+                    if (lane == 0) {
+                        S.cval[sp - 1] = c;
+                        out[S.seg_start[sp - 1]] = Instr{(uint32_t)OP_CONST << 28, c};
+                    }
+                } else {
+                    if (lane == 0) out[olen] = in;
+                    olen += 1;
+                }
+                if (EXACT) S.val[sp - 1][lane] = S.val[sp - 1][lane] * s;
+            } else if (op == OP_NOISE) {
+                const ivx_node& n = a.nodes[ni];
+                bool apply = true;
+                if (EXACT) {
+                    NoiseFrame f = make_noise_frame(n, lo);
+                    if (cls == 1) {
+                        // all_modified_signed_distances_at_block_test_positions_pass_predicate
+                        const int tl = lane < 26 ? lane : 0;
+                        float v = __shfl_sync(0xffffffffu, S.val[sp - 1][lane], c_test_lane[tl]);
+                        f3 tp = test_position(tl, f.o, f.dxn, f.dyn, f.dzn);
+                        float mv = v + noise_at(n, f.freq, tp) * n.p[4];
+                        bool pass = mv >= n.margin;
+                        apply = !__all_sync(0xffffffffu, pass);
+                    }
+                    if (apply) {
+                        float nv = noise_for_voxel(n, f, si, sj, sk);
+                        S.val[sp - 1][lane] = S.val[sp - 1][lane] + nv * n.p[4];
+                    }
+                }
+                if (apply) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        S.is_const[sp - 1] = 0;
+                        out[olen] = in;
+                    }
+                    olen += 1;
+                }
+            } else {  // OP_COMBINE
+                const ivx_node& n = a.nodes[ni];
+                __syncwarp();
+                const int ia = sp - 2, ib = sp - 1;
+                const bool both_const = S.is_const[ia] && S.is_const[ib];
+                const float ca = S.cval[ia], cb = S.cval[ib];
+                const uint32_t seg_a = S.seg_start[ia], seg_b = S.seg_start[ib];
+                int decision;  // 0 apply, 1 skip (keep child 1), 2 undecided (conservative only)
+                if (EXACT) {
+                    float r = op_combine(n.kind, S.val[ia][lane], S.val[ib][lane], n.p[0], n.p[1]);
+                    bool pass = (lane >= 14) || (r >= n.margin);
+                    bool all_pass = __all_sync(0xffffffffu, pass);
+                    decision = (cls == 1 && all_pass) ? 1 : 0;
+                    if (decision == 0) S.val[ia][lane] = r;
+                } else {
+                    if (both_const) {
+                        bool pass = op_combine(n.kind, ca, cb, n.p[0], n.p[1]) >= n.margin;
+                        decision = !pass ? 0 : (cls == 1 ? 1 : 2);
+                    } else {
+                        decision = 2;
+                    }
+                }
+                __syncwarp();
+                if (decision == 1) {
+                    olen = seg_b;  // drop child 2's instructions
+                } else if (decision == 0 && both_const) {
+                    float c = op_combine(n.kind, ca, cb, n.p[0], n.p[1]);
+                    if (lane == 0) {
+                        S.cval[ia] = c;
+                        out[seg_a] = Instr{(uint32_t)OP_CONST << 28, c};
+                    }
+                    olen = seg_a + 1;
+                } else {
+                    if (lane == 0) {
+                        S.is_const[ia] = 0;
+                        out[olen] = in;
+                    }
+                    olen += 1;
+                }
+                sp -= 1;
+            }
+        }
+        __syncwarp();
+        if (overflow) break;
+    }
+
+    if (lane == 0) {
+        if (overflow) atomicExch(a.error_flag, 1u);
+        a.out_len[block] = olen;
+    }
+    if (!EXACT) return;
+
+    // ---- exact level: pre-classify the chunk ----
+    __syncwarp();
+    if (lane == 0) {
+        DevChunk c{};
+        c.pre = PRE_ACTIVE;
+        if (a.chunks) {
+            if (olen == 1 && S.is_const[0]) {
+                const int code = sd_encode(S.cval[0]);
+                const uint32_t ox = (bc[0] + a.first_chunk[0]) * 16u, oy = (bc[1] + a.first_chunk[1]) * 16u,
+                               oz = (bc[2] + a.first_chunk[2]) * 16u;
+                const bool full_in_grid = ox + 16u <= a.gp.grid_shape[0] && oy + 16u <= a.gp.grid_shape[1] &&
+                                          oz + 16u <= a.gp.grid_shape[2];
+                if (code > 100) {
+                    c.pre = PRE_VOID;
+                } else if (code == -128 && full_in_grid && a.gp.types.kind == 0) {
+                    c.pre = PRE_UNIFORM;
+                    c.kind = 1;
+                    c.u_type = (uint8_t)a.gp.types.same_type;
+                    c.u_sd = -128;
+                    c.u_flags = 0xFC;
+                    if (a.occ) {
+                        const uint32_t o3[3] = {ox, oy, oz};
+                        for (int d = 0; d < 3; ++d) {
+                            atomicMin(&a.occ[d], o3[d]);
+                            atomicMax(&a.occ[3 + d], o3[d] + 15u);
+                        }
+                    }
+                }
+            }
+            a.chunks[block] = c;
+        }
+        if (c.pre == PRE_ACTIVE) {
+            // stack depth the evaluator needs for this list
+            int d = 0, md = 0;
+            for (uint32_t q = 0; q < olen; ++q) {
+                uint32_t o2 = out[q].op_node >> 28;
+                if (o2 == OP_LEAF || o2 == OP_CONST) { d++; md = max(md, d); }
+                else if (o2 == OP_COMBINE) d--;
+            }
+            atomicMax(a.max_depth, (uint32_t)md);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_eval: CTA (256 threads) per active chunk; thread (i, j) owns the 16 voxels
+// of one k-column so the reference's incremental `position += dz` walk
+// (atomic.rs:1614-1626) is reproduced exactly. The operand stack lives in
+// shared memory ([level][k][thread], conflict-free); its top stays in
+// registers.
+constexpr int EVAL_THREADS = 256;
+
+__device__ __forceinline__ float* stack_level(float* smem_stack, float* spill, int level, int smem_levels) {
+    return level < smem_levels ? smem_stack + (size_t)level * 4096 : spill + (size_t)(level - smem_levels) * 4096;
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_stack = reinterpret_cast<float*>(smem_raw);
+    __shared__ __align__(16) int8_t s_sd[4096];
+    __shared__ uint32_t s_cnt[16];
+    __shared__ uint8_t s_first_type;
+
+    const int tid = threadIdx.x;
+    const int ti = tid >> 4, tj = tid & 15;
+    float* spill = a.spill ? a.spill + (size_t)blockIdx.x * a.spill_levels * 4096 : nullptr;
+
+    for (uint32_t work = blockIdx.x; work < a.n_active; work += gridDim.x) {
+        const uint32_t chunk = a.active ? a.active[work] : work;
+        const Instr* __restrict__ prog = a.instrs + a.off[chunk];
+        const uint32_t plen = a.len[chunk];
+
+        f3 lo;
+        uint32_t org[3] = {0, 0, 0};
+        if (a.explicit_origins) {
+            lo = mk3(a.explicit_origins[3 * chunk], a.explicit_origins[3 * chunk + 1], a.explicit_origins[3 * chunk + 2]);
+        } else {
+            uint32_t ck = chunk % a.nb[2], cj = (chunk / a.nb[2]) % a.nb[1], ci = chunk / (a.nb[2] * a.nb[1]);
+            org[0] = (ci + a.first_i) * 16u;
+            org[1] = cj * 16u;
+            org[2] = ck * 16u;
+            lo = mk3((float)org[0] - a.gp.shifted_center[0], (float)org[1] - a.gp.shifted_center[1],
+                     (float)org[2] - a.gp.shifted_center[2]);
+        }
+
+        float top[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) top[k] = 0.02f * 127.0f;
+        int sp = 0;
+
+        for (uint32_t pc = 0; pc < plen; ++pc) {
+            const Instr in = prog[pc];
+            const uint32_t op = in.op_node >> 28;
+            const ivx_node& n = a.nodes[in.op_node & 0x0FFFFFFFu];
+            if (op == OP_LEAF || op == OP_CONST) {
+                if (sp > 0) {
+                    float* lv = stack_level(s_stack, spill, sp - 1, a.smem_levels);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) lv[k * 256 + tid] = top[k];
+                }
+                sp++;
+                if (op == OP_CONST) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) top[k] = in.value;
+                } else {
+                    const float* M = n.transform_to_node_space;
+                    f3 origin = transform_point(M, lo);
+                    f3 dx = mk3(M[0], M[1], M[2]), dy = mk3(M[4], M[5], M[6]), dz = mk3(M[8], M[9], M[10]);
+                    f3 pos = (origin + (float)ti * dx) + (float)tj * dy;
+                    const uint32_t kind = n.kind;
+                    const float p0 = n.p[0], p1 = n.p[1], p2 = n.p[2];
+                    const float pp[3] = {p0, p1, p2};
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        top[k] = sd_leaf(kind, pp, pos);
+                        pos = pos + dz;
+                    }
+                }
+            } else if (op == OP_SCALE) {
+                const float s = n.p[0];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) top[k] = top[k] * s;
+            } else if (op == OP_NOISE) {
+                NoiseFrame f = make_noise_frame(n, lo);
+                const float ns = n.p[4];
+                const float lac = n.p[1], gain = n.p[2];
+                const uint32_t oct = n.octaves;
+                const int32_t seed = (int32_t)n.seed;
+                if (f.rotated) {
+                    f3 pos = (f.o + (float)ti * f.dxn) + (float)tj * f.dyn;
+                    for (int k = 0; k < 16; ++k) {
+                        float nv = fbm3(pos.z * f.freq, pos.y * f.freq, pos.x * f.freq, lac, gain, oct, seed);
+                        top[k] = top[k] + nv * ns;
+                        pos = pos + f.dzn;
+                    }
+                } else {
+                    const float zc = accumulate_ones(f.o.x, ti) * f.freq;
+                    const float yc = accumulate_ones(f.o.y, tj) * f.freq;
+#pragma unroll 1
+                    for (int k = 0; k < 16; ++k) {
+                        float xc = block_noise_x(f.o.z, k) * f.freq;
+                        float nv = fbm3(xc, yc, zc, lac, gain, oct, seed);
+                        top[k] = top[k] + nv * ns;
+                    }
+                }
+            } else {  // OP_COMBINE
+                const float* lv = stack_level(s_stack, spill, sp - 2, a.smem_levels);
+                const uint32_t kind = n.kind;
+                const float ks = n.p[0], qik = n.p[1];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) top[k] = op_combine(kind, lv[k * 256 + tid], top[k], ks, qik);
+                sp--;
+            }
+        }
+
+        if (a.raw_out) {
+            float* o = a.raw_out + (size_t)chunk * 4096 + tid * 16;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4)
+                *reinterpret_cast<float4*>(o + k) = make_float4(top[k], top[k + 1], top[k + 2], top[k + 3]);
+            continue;
+        }
+
+        // ---- quantise + classify (generation.rs:330-357) ----
+        if (tid < 16) s_cnt[tid] = (tid >= 6 && tid < 9) ? 0xFFFFFFFFu : 0u;
+        __syncthreads();
+        const bool col_in = (org[0] + ti < a.gp.grid_shape[0]) && (org[1] + tj < a.gp.grid_shape[1]);
+        uint32_t empty_mask = 0, void_mask = 0, m128_mask = 0;
+        int8_t codes[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            int c = 127;
+            bool in_grid = col_in && (org[2] + k < a.gp.grid_shape[2]);
+            if (in_grid) c = sd_encode(top[k]);
+            codes[k] = (int8_t)c;
+            if (c >= 0) empty_mask |= 1u << k;
+            // out-of-grid voxels do not influence is_void (generation.rs:336-340)
+            if (!in_grid || c > 100) void_mask |= 1u << k;
+            if (c == -128) m128_mask |= 1u << k;
+        }
+        {
+            uint4 pk;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                w[q] = (uint32_t)(uint8_t)codes[4 * q] | ((uint32_t)(uint8_t)codes[4 * q + 1] << 8) |
+                       ((uint32_t)(uint8_t)codes[4 * q + 2] << 16) | ((uint32_t)(uint8_t)codes[4 * q + 3] << 24);
+            *reinterpret_cast<uint4*>(&s_sd[tid * 16]) = pk;
+        }
+        const int any_nonempty = __syncthreads_or(empty_mask != 0xFFFFu);
+        const int all_void = __syncthreads_and(void_mask == 0xFFFFu);
+        const int all_m128 = __syncthreads_and(m128_mask == 0xFFFFu);
+
+        DevChunk cd = a.chunks[chunk];
+        if (all_void) {
+            if (tid == 0) {
+                cd.kind = 0;
+                cd.pre = PRE_VOID;
+                cd.flags = 0;
+                a.chunks[chunk] = cd;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- voxel types (generation.rs:359-365, voxel_type.rs) ----
+        uint8_t types[16];
+        if (!any_nonempty) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) types[k] = 255;
+        } else if (a.gp.types.kind == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) types[k] = (uint8_t)a.gp.types.same_type;
+        } else {
+            // gradient_4d_offset(0, n, o.z, 16, o.y, 16, o.x, 16): x = type axis,
+            // y / z / w = our k / j / i, each walked by repeated += 1.0
+            const float ft = a.gp.types.voxel_type_frequency, fn = a.gp.types.noise_frequency;
+            const int32_t seed = (int32_t)a.gp.types.seed;
+            const float wc = accumulate_ones(lo.x, ti) * fn;
+            const float zc = accumulate_ones(lo.y, tj) * fn;
+            float yacc = lo.z;
+            for (int k = 0; k < 16; ++k) {
+                const float yc = yacc * fn;
+                float best = 0.0f;
+                uint32_t best_t = 0;
+                for (uint32_t t = 0; t < a.gp.types.n_types; ++t) {
+                    float xc = 0.0f + (float)(t & 7u);
+                    for (uint32_t v = 0; v < (t >> 3); ++v) xc = xc + 8.0f;
+                    float nv = simplex4_t(xc * ft, yc, zc, wc, seed, c_perm);
+                    if (t == 0 || nv > best) {
+                        best = nv;
+                        best_t = t;
+                    }
+                }
+                types[k] = (uint8_t)best_t;
+                yacc = yacc + 1.0f;
+            }
+        }
+
+        // uniform ⇔ every voxel is maximally inside with the same type (object.rs:1913-1918)
+        if (all_m128) {
+            if (tid == 0) s_first_type = types[0];
+            __syncthreads();
+            bool same_cta = true;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) same_cta = same_cta && (types[k] == s_first_type);
+            const int uniform = __syncthreads_and(same_cta);
+            if (uniform) {
+                if (tid == 0) {
+                    cd.kind = 1;
+                    cd.pre = PRE_UNIFORM;
+                    cd.u_type = s_first_type;
+                    cd.u_sd = -128;
+                    cd.u_flags = 0xFC;
+                    cd.flags = 0;
+                    a.chunks[chunk] = cd;
+                    if (a.occ) {
+                        for (int d = 0; d < 3; ++d) {
+                            atomicMin(&a.occ[d], org[d]);
+                            atomicMax(&a.occ[3 + d], org[d] + 15u);
+                        }
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+        }
+
+        // ---- flags: IS_EMPTY + in-chunk adjacency (object.rs:2673-2756 on fresh voxels) ----
+        uint8_t flags[16];
+        {
+            auto nonempty_at = [&](int i, int j, int k) -> bool { return s_sd[vidx(i, j, k)] < 0; };
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                uint8_t f = 0;
+                if (codes[k] >= 0) {
+                    f = 1;  // IS_EMPTY; empty voxels carry no in-chunk adjacency bits
+                } else {
+                    if (ti > 0 && nonempty_at(ti - 1, tj, k)) f |= 1u << 2;
+                    if (tj > 0 && nonempty_at(ti, tj - 1, k)) f |= 1u << 3;
+                    if (k > 0 && codes[k - 1] < 0) f |= 1u << 4;
+                    if (ti < 15 && nonempty_at(ti + 1, tj, k)) f |= 1u << 5;
+                    if (tj < 15 && nonempty_at(ti, tj + 1, k)) f |= 1u << 6;
+                    if (k < 15 && codes[k + 1] < 0) f |= 1u << 7;
+                }
+                flags[k] = f;
+            }
+        }
+
+        // ---- face empty counts → FaceVoxelDistribution (object.rs:1920-1936, 2967-2981) ----
+        {
+            const uint32_t ne = __popc(empty_mask);
+            if (ti == 0) atomicAdd(&s_cnt[0], ne);
+            if (ti == 15) atomicAdd(&s_cnt[1], ne);
+            if (tj == 0) atomicAdd(&s_cnt[2], ne);
+            if (tj == 15) atomicAdd(&s_cnt[3], ne);
+            if (empty_mask & 1u) atomicAdd(&s_cnt[4], 1u);
+            if (empty_mask & 0x8000u) atomicAdd(&s_cnt[5], 1u);
+            // bounding range of non-empty voxels (object.rs:1187-1280)
+            const uint32_t nonempty = (~empty_mask) & 0xFFFFu;
+            if (nonempty) {
+                atomicMin(&s_cnt[6], (uint32_t)ti);
+                atomicMin(&s_cnt[7], (uint32_t)tj);
+                atomicMin(&s_cnt[8], (uint32_t)(__ffs(nonempty) - 1));
+                atomicMax(&s_cnt[9], (uint32_t)ti);
+                atomicMax(&s_cnt[10], (uint32_t)tj);
+                atomicMax(&s_cnt[11], (uint32_t)(31 - __clz(nonempty)));
+            }
+        }
+        __syncthreads();
+
+        // ---- store the three planes: 16 B per thread per plane, fully coalesced ----
+        {
+            unsigned char* slot = a.voxels + (size_t)a.slot_of[chunk] * SLOT_BYTES;
+            *reinterpret_cast<uint4*>(slot + PLANE_SD + tid * 16) = *reinterpret_cast<uint4*>(&s_sd[tid * 16]);
+            uint4 pt, pf;
+            uint32_t* wt = reinterpret_cast<uint32_t*>(&pt);
+            uint32_t* wf = reinterpret_cast<uint32_t*>(&pf);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                wt[q] = (uint32_t)types[4 * q] | ((uint32_t)types[4 * q + 1] << 8) | ((uint32_t)types[4 * q + 2] << 16) |
+                        ((uint32_t)types[4 * q + 3] << 24);
+                wf[q] = (uint32_t)flags[4 * q] | ((uint32_t)flags[4 * q + 1] << 8) | ((uint32_t)flags[4 * q + 2] << 16) |
+                        ((uint32_t)flags[4 * q + 3] << 24);
+            }
+            *reinterpret_cast<uint4*>(slot + PLANE_TYPE + tid * 16) = pt;
+            *reinterpret_cast<uint4*>(slot + PLANE_FLAGS + tid * 16) = pf;
+        }
+        if (tid == 0) {
+            cd.kind = 2;
+            cd.pre = PRE_ACTIVE;
+            cd.slot = a.slot_of[chunk];
+            if (!any_nonempty) {
+                for (int q = 0; q < 6; ++q) cd.face[q] = 0;
+                cd.flags = 1u << 6;  // HAS_ONLY_EMPTY_VOXELS
+            } else {
+                for (int q = 0; q < 6; ++q) cd.face[q] = s_cnt[q] == 256u ? 0 : (s_cnt[q] == 0u ? 1 : 2);
+                cd.flags = 0;
+                if (a.occ) {
+                    for (int d = 0; d < 3; ++d) {
+                        atomicMin(&a.occ[d], org[d] + s_cnt[6 + d]);
+                        atomicMax(&a.occ[3 + d], org[d] + s_cnt[9 + d]);
+                    }
+                }
+            }
+            a.chunks[chunk] = cd;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host launch wrappers
+size_t fold_smem_bytes(bool exact) {
+    return (size_t)FOLD_WARPS * (exact ? sizeof(FoldWarpSmem) : offsetof(FoldWarpSmem, val));
+}
+
+cudaError_t launch_fold(bool exact, const FoldArgs& a, cudaStream_t st) {
+    if (a.n_blocks == 0) return cudaSuccess;
+    const uint32_t grid = (a.n_blocks + FOLD_WARPS - 1) / FOLD_WARPS;
+    const size_t smem = fold_smem_bytes(exact);
+    if (exact) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_fold<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        k_fold<true><<<grid, FOLD_WARPS * 32, smem, st>>>(a);
+    } else {
+        k_fold<false><<<grid, FOLD_WARPS * 32, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval(const EvalArgs& a, uint32_t grid, cudaStream_t st) {
+    if (a.n_active == 0 || grid == 0) return cudaSuccess;
+    const size_t smem = (size_t)a.smem_levels * 4096 * sizeof(float);
+    cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_eval<<<grid, EVAL_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+int eval_max_blocks_per_sm(int smem_levels) {
+    int nb = 0;
+    const size_t smem = (size_t)smem_levels * 4096 * sizeof(float);
+    cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eval, EVAL_THREADS, smem);
+    return nb;
+}
+
+}  // namespace ivx

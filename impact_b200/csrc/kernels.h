@@ -1,0 +1,146 @@
+// Kernel argument blocks and host launch wrappers (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ivx_internal.h"
+
+namespace ivx {
+
+// ---- generate.cu -----------------------------------------------------------
+struct FoldArgs {
+    const ivx_node* nodes;
+    GenParams gp;
+    // this level's blocks
+    uint32_t n_blocks;
+    uint32_t nb[3];           // blocks per axis at this level
+    uint32_t block_chunks;    // block edge in chunks
+    uint32_t first_chunk[3];  // chunk coordinates (full grid) of block (0,0,0)'s first chunk
+    const float* explicit_origins;  // non-null: n_blocks x 3 chunk origins in root space, parent = 0
+    // parent level
+    uint32_t ratio;           // parent block edge / this block edge
+    uint32_t parent_nb[3];    // 0,0,0 → single parent (the root list)
+    const Instr* parent_instrs;
+    const uint32_t* parent_off;
+    const uint32_t* parent_len;
+    // outputs
+    Instr* out_instrs;
+    const uint32_t* out_off;
+    uint32_t* out_len;
+    DevChunk* chunks;         // exact level only (may be null for explicit origins)
+    uint32_t* max_depth;      // exact level only
+    uint32_t* occ;            // exact level only: min xyz, max xyz of non-empty voxels
+    uint32_t* error_flag;
+};
+cudaError_t launch_fold(bool exact, const FoldArgs& a, cudaStream_t st);
+
+struct EvalArgs {
+    const ivx_node* nodes;
+    GenParams gp;
+    uint32_t n_active;
+    const uint32_t* active;   // compacted chunk indices (null → identity)
+    uint32_t nb[3];
+    uint32_t first_i;
+    const float* explicit_origins;
+    const Instr* instrs;
+    const uint32_t* off;
+    const uint32_t* len;
+    const uint32_t* slot_of;  // per chunk
+    unsigned char* voxels;
+    DevChunk* chunks;
+    uint32_t* occ;
+    float* raw_out;           // non-null: write f32 distances instead of voxels
+    int smem_levels;
+    float* spill;
+    int spill_levels;
+};
+cudaError_t launch_eval(const EvalArgs& a, uint32_t grid, cudaStream_t st);
+int eval_max_blocks_per_sm(int smem_levels);
+
+// ---- scan.cu ----------------------------------------------------------------
+// Exclusive prefix sums over small arrays (chunk-count sized), single CTA.
+cudaError_t launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total, cudaStream_t st);
+
+cudaError_t launch_child_caps(const uint32_t* parent_len, uint32_t n_blocks, const uint32_t nb[3],
+                              const uint32_t parent_nb[3], uint32_t ratio, uint32_t* caps, cudaStream_t st);
+cudaError_t launch_plan_slots(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t* active_flag,
+                              uint32_t* slot_flag, cudaStream_t st);
+cudaError_t launch_scatter_active(const uint32_t* active_flag, const uint32_t* active_scan, uint32_t n,
+                                  uint32_t* active_list, cudaStream_t st);
+cudaError_t launch_fill_u32(uint32_t* p, uint32_t n, uint32_t v, cudaStream_t st);
+
+// ---- derive.cu ---------------------------------------------------------------
+cudaError_t launch_boundary_classify(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], const uint8_t* face_mask,
+                                     uint32_t* convert_flag, cudaStream_t st);
+cudaError_t launch_boundary_apply(DevChunk* chunks, uint32_t n, const uint32_t nb[3], const uint8_t* face_mask,
+                                  const uint32_t* convert_flag, const uint32_t* slot_of, unsigned char* voxels,
+                                  const uint32_t* work_list, uint32_t n_work, uint32_t grid, cudaStream_t st);
+
+// ---- mesh.cu -----------------------------------------------------------------
+struct MeshArgs {
+    const DevChunk* chunks;
+    const unsigned char* voxels;
+    uint32_t nb[3];
+    uint32_t first_i;
+    float voxel_extent;
+    const uint32_t* work;  // chunk indices to mesh, ascending linear order
+    uint32_t n_work;
+    // counting pass outputs / emit pass inputs (per work item)
+    uint32_t* vertex_count;
+    uint32_t* index_count;
+    uint32_t* has_submesh;
+    const uint32_t* vertex_offset;
+    const uint32_t* index_offset;
+    const uint32_t* submesh_ord;
+    // emit outputs
+    float* positions;
+    float* normals;
+    uint32_t* indices;
+    ivx_index_materials* index_materials;
+    ivx_chunk_submesh* submeshes;
+    uint32_t* vertex_ranges;
+};
+cudaError_t launch_exposed_flags(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t own_lo,
+                                 uint32_t own_hi, uint32_t* flag, cudaStream_t st);
+cudaError_t launch_mesh(bool emit, const MeshArgs& a, uint32_t grid, cudaStream_t st);
+
+// ---- modify.cu ---------------------------------------------------------------
+struct AbsorbRange {
+    uint32_t c0[3], c1[3];  // chunk range
+    uint32_t v0[3], v1[3];  // voxel range
+};
+struct AbsorbArgs {
+    DevChunk* chunks;
+    uint3 nb;
+    AbsorbRange range;
+    uint32_t n_range;
+    unsigned char* voxels;
+    float center[3];
+    float radius;
+    float influence_radius_sq;
+    uint32_t first_new_slot;
+    const uint32_t* new_slot_ord;
+    uint8_t* dirty;
+    uint32_t* stats;  // touched chunks, touched voxels, emptied voxels, removed chunks
+};
+cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], const AbsorbRange& r, uint32_t* need_slot,
+                               uint32_t n_range, cudaStream_t st);
+cudaError_t launch_absorb_apply(const AbsorbArgs& a, uint32_t grid, cudaStream_t st);
+cudaError_t launch_absorb_face_mask(const uint32_t nb[3], const AbsorbRange& b, uint8_t* face_mask, uint32_t n,
+                                    cudaStream_t st);
+cudaError_t launch_need_slot_for_convert(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t n, uint32_t* need,
+                                         cudaStream_t st);
+cudaError_t launch_assign_slots(const DevChunk* chunks, const uint32_t* need, const uint32_t* ord, uint32_t first,
+                                uint32_t n, uint32_t* slot_of, cudaStream_t st);
+cudaError_t launch_occupied_ranges(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t first_i,
+                                   const unsigned char* voxels, uint32_t* occ, uint32_t grid, cudaStream_t st);
+
+// ---- api.cu helpers ------------------------------------------------------------
+cudaError_t launch_flag_dirty_exposed(const DevChunk* chunks, const uint8_t* dirty, uint32_t n, uint32_t* exposed_flag,
+                                      uint32_t* dirty_flag, cudaStream_t st);
+cudaError_t launch_pack_voxels(const DevChunk* chunks, uint32_t n, const uint32_t* ordinal, const unsigned char* voxels,
+                               ivx_voxel* out, ivx_chunk_desc* out_chunks, uint32_t grid, cudaStream_t st);
+cudaError_t launch_nonuniform_flags(const DevChunk* chunks, uint32_t n, uint32_t* flag, cudaStream_t st);
+cudaError_t launch_set_reserved_slots(DevChunk* chunks, uint32_t n, const uint32_t* slot_flag, const uint32_t* slot_scan,
+                                      uint32_t* slot_of, cudaStream_t st);
+
+}  // namespace ivx

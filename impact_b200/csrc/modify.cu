@@ -1,0 +1,299 @@
+// Voxel modification kernels (sm_100a): sphere absorption over the touched
+// chunk range, per-chunk internal state refresh and mesh invalidation.
+//
+// Replaces
+//   VoxelObject::modify_voxels_within_sphere        (object/intersection.rs:283-394)
+//   apply_sphere_absorption's closure               (interaction/absorption.rs:823-843)
+//   VoxelAbsorbingSphere::compute_new_signed_distance (absorption.rs:170-179)
+//   Voxel::set_signed_distance                      (lib.rs:451-461)
+//   update_all_internal_state_and_determine_sparseness (object.rs:2761-2874)
+//   handle_chunk_voxels_modified                    (object/intersection.rs:539-598)
+// The cross-chunk part of the update (intersection.rs:391-393) reuses the
+// boundary kernels in derive.cu with a per-chunk face mask.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ivx {
+
+__global__ void k_absorb_plan(const DevChunk* __restrict__ chunks, uint3 nb, AbsorbRange r,
+                              uint32_t* __restrict__ need_slot, uint32_t n_range) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_range) return;
+    const uint32_t ek = r.c1[2] - r.c0[2], ej = r.c1[1] - r.c0[1];
+    const uint32_t k = r.c0[2] + t % ek, j = r.c0[1] + (t / ek) % ej, i = r.c0[0] + t / (ek * ej);
+    const DevChunk c = chunks[(i * nb.y + j) * nb.z + k];
+    need_slot[t] = (c.kind == 1 && c.slot == 0xFFFFFFFFu) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
+    __shared__ __align__(16) int8_t s_sd[4096];
+    __shared__ __align__(16) uint8_t s_fl[4096];
+    __shared__ uint32_t s_cnt[8];
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    const uint3 nb = a.nb;
+    const AbsorbRange r = a.range;
+    const uint32_t ek = r.c1[2] - r.c0[2], ej = r.c1[1] - r.c0[1];
+
+    for (uint32_t t = blockIdx.x; t < a.n_range; t += gridDim.x) {
+        const uint32_t ck = r.c0[2] + t % ek, cj = r.c0[1] + (t / ek) % ej, ci = r.c0[0] + t / (ek * ej);
+        const uint32_t cidx = (ci * nb.y + cj) * nb.z + ck;
+        DevChunk me = a.chunks[cidx];
+        if (me.kind == 0) continue;
+        unsigned char* slot;
+        if (me.kind == 1) {
+            // convert_to_non_uniform_if_uniform: every uniform chunk of the touched range (intersection.rs:318-331)
+            if (me.slot == 0xFFFFFFFFu) me.slot = a.first_new_slot + a.new_slot_ord[t];
+            me.kind = 2;
+            for (int q = 0; q < 6; ++q) me.face[q] = 1;
+            me.flags = 0x3F;
+            slot = a.voxels + (size_t)me.slot * SLOT_BYTES;
+            const uint32_t tw = (uint32_t)me.u_type * 0x01010101u;
+            *reinterpret_cast<uint4*>(slot + PLANE_TYPE + tid * 16) = make_uint4(tw, tw, tw, tw);
+            *reinterpret_cast<uint4*>(&s_sd[tid * 16]) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+            *reinterpret_cast<uint4*>(&s_fl[tid * 16]) = make_uint4(0xFCFCFCFCu, 0xFCFCFCFCu, 0xFCFCFCFCu, 0xFCFCFCFCu);
+        } else {
+            slot = a.voxels + (size_t)me.slot * SLOT_BYTES;
+            *reinterpret_cast<uint4*>(&s_sd[tid * 16]) = *reinterpret_cast<const uint4*>(slot + PLANE_SD + tid * 16);
+            *reinterpret_cast<uint4*>(&s_fl[tid * 16]) = *reinterpret_cast<const uint4*>(slot + PLANE_FLAGS + tid * 16);
+        }
+        if (tid < 8) s_cnt[tid] = 0;
+        __syncthreads();
+
+        // touched voxel ranges in this chunk (intersection.rs:336-345)
+        uint32_t v0[3], v1[3], t0[3], t1[3];
+        const uint32_t cc[3] = {ci, cj, ck};
+        for (int d = 0; d < 3; ++d) {
+            v0[d] = cc[d] * 16u;
+            v1[d] = v0[d] + 16u;
+            t0[d] = max(v0[d], r.v0[d]);
+            t1[d] = min(v1[d], r.v1[d]);
+        }
+        const uint32_t gi = v0[0] + ti, gj = v0[1] + tj;
+        uint32_t n_touched = 0, n_emptied = 0;
+        if (gi >= t0[0] && gi < t1[0] && gj >= t0[1] && gj < t1[1]) {
+            const float px = (float)gi + 0.5f, py = (float)gj + 0.5f;
+            for (uint32_t gk = t0[2]; gk < t1[2]; ++gk) {
+                const float pz = (float)gk + 0.5f;
+                // Point3::squared_distance_between(centre, voxel centre)
+                const f3 df = mk3(a.center[0] - px, a.center[1] - py, a.center[2] - pz);
+                const float d2 = dot3(df, df);
+                if (d2 < a.influence_radius_sq) {
+                    const int idx = vidx(ti, tj, (int)(gk & 15u));
+                    const bool was_empty = (s_fl[idx] & 1) != 0;
+                    const float sphere_sd = sqrtf(d2) - a.radius;
+                    const float nsd = fmaxf(sd_decode((int)s_sd[idx]), -sphere_sd);
+                    const int code = sd_encode(nsd);
+                    s_sd[idx] = (int8_t)code;
+                    if (code >= 0) {
+                        s_fl[idx] |= 1;
+                        if (!was_empty) n_emptied++;
+                    }
+                    n_touched++;
+                }
+            }
+        }
+        const int touched = __syncthreads_or(n_touched != 0);
+        if (touched) {
+            // update_all_internal_state_and_determine_sparseness as a pure function of
+            // (previous flags, emptiness): bits of empty voxels that the reference's
+            // sweep never writes keep their previous (possibly stale) value.
+            uint8_t nf[16];
+            uint32_t empty_mask = 0, void_mask = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int idx = vidx(ti, tj, k);
+                uint8_t f = s_fl[idx];
+                const bool e = (f & 1) != 0;
+                if (e) {
+                    empty_mask |= 1u << k;
+                    if ((int)s_sd[idx] > 100) void_mask |= 1u << k;
+                }
+                const int up[3] = {ti < 15 ? vidx(ti + 1, tj, k) : -1, tj < 15 ? vidx(ti, tj + 1, k) : -1,
+                                   k < 15 ? vidx(ti, tj, k + 1) : -1};
+                const int dn[3] = {ti > 0 ? vidx(ti - 1, tj, k) : -1, tj > 0 ? vidx(ti, tj - 1, k) : -1,
+                                   k > 0 ? vidx(ti, tj, k - 1) : -1};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const uint8_t ub = (uint8_t)(1u << (5 + d)), db = (uint8_t)(1u << (2 + d));
+                    if (up[d] >= 0 && !e) {
+                        if (s_fl[up[d]] & 1) f &= (uint8_t)~ub; else f |= ub;
+                    }
+                    if (dn[d] >= 0) {
+                        if (s_fl[dn[d]] & 1) f &= (uint8_t)~db;
+                        else if (!e) f |= db;
+                    }
+                }
+                nf[k] = f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s_fl[vidx(ti, tj, k)] = nf[k];
+            const uint32_t ne = __popc(empty_mask);
+            if (ti == 0) atomicAdd(&s_cnt[0], ne);
+            if (ti == 15) atomicAdd(&s_cnt[1], ne);
+            if (tj == 0) atomicAdd(&s_cnt[2], ne);
+            if (tj == 15) atomicAdd(&s_cnt[3], ne);
+            if (empty_mask & 1u) atomicAdd(&s_cnt[4], 1u);
+            if (empty_mask & 0x8000u) atomicAdd(&s_cnt[5], 1u);
+            atomicAdd(&s_cnt[6], n_touched);
+            atomicAdd(&s_cnt[7], n_emptied);
+            const int only_empty = __syncthreads_and(empty_mask == 0xFFFFu);
+            const int is_void = __syncthreads_and(void_mask == 0xFFFFu);
+            for (int q = 0; q < 6; ++q) me.face[q] = s_cnt[q] == 256u ? 0 : (s_cnt[q] == 0u ? 1 : 2);
+            if (only_empty) me.flags |= 1u << 6; else me.flags &= (uint8_t)~(1u << 6);
+            if (is_void) {
+                // the chunk is dropped; its slot is orphaned like in the reference (intersection.rs:559-562)
+                DevChunk v{};
+                v.kind = 0;
+                v.slot = 0xFFFFFFFFu;
+                me = v;
+            }
+            if (tid == 0) {
+                atomicAdd(&a.stats[0], 1u);
+                atomicAdd(&a.stats[1], s_cnt[6]);
+                atomicAdd(&a.stats[2], s_cnt[7]);
+                if (is_void) atomicAdd(&a.stats[3], 1u);
+                // invalidated meshes: this chunk and face neighbours whose border band was touched
+                a.dirty[cidx] = 1;
+                for (int d = 0; d < 3; ++d) {
+                    if (cc[d] > 0 && t0[d] - v0[d] < 2u) {
+                        uint32_t n[3] = {ci, cj, ck};
+                        n[d] -= 1;
+                        a.dirty[(n[0] * nb.y + n[1]) * nb.z + n[2]] = 1;
+                    }
+                    const uint32_t nbd = d == 0 ? nb.x : (d == 1 ? nb.y : nb.z);
+                    if (cc[d] + 1 < nbd && v1[d] - t1[d] < 2u) {
+                        uint32_t n[3] = {ci, cj, ck};
+                        n[d] += 1;
+                        a.dirty[(n[0] * nb.y + n[1]) * nb.z + n[2]] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (me.kind == 2) {
+            *reinterpret_cast<uint4*>(slot + PLANE_SD + tid * 16) = *reinterpret_cast<const uint4*>(&s_sd[tid * 16]);
+            *reinterpret_cast<uint4*>(slot + PLANE_FLAGS + tid * 16) = *reinterpret_cast<const uint4*>(&s_fl[tid * 16]);
+        }
+        if (tid == 0) a.chunks[cidx] = me;
+        __syncthreads();
+    }
+}
+
+// face mask for the boundary refresh after a modification: update_mutual_face_adjacencies
+// is called for (c, c+x), (c, c+y), (c, c+z) with c in the range `b` (intersection.rs:391-393)
+__global__ void k_absorb_face_mask(uint3 nb, AbsorbRange b, uint8_t* __restrict__ face_mask, uint32_t n) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const uint32_t k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
+    const uint32_t cc[3] = {i, j, k};
+    auto in_range = [&](uint32_t x, uint32_t y, uint32_t z) {
+        return x >= b.c0[0] && x < b.c1[0] && y >= b.c0[1] && y < b.c1[1] && z >= b.c0[2] && z < b.c1[2];
+    };
+    uint8_t m = 0;
+    if (in_range(i, j, k)) m |= (1u << 1) | (1u << 3) | (1u << 5);  // upper faces
+    for (int d = 0; d < 3; ++d) {
+        if (cc[d] == 0) continue;
+        uint32_t n3[3] = {i, j, k};
+        n3[d] -= 1;
+        if (in_range(n3[0], n3[1], n3[2])) m |= (uint8_t)(1u << (2 * d));  // lower face, pair owned by the lower chunk
+    }
+    face_mask[c] = m;
+}
+
+// slots for uniform chunks converted by the boundary refresh that have none reserved
+__global__ void k_need_slot_for_convert(const DevChunk* __restrict__ chunks, const uint32_t* __restrict__ convert_flag,
+                                        uint32_t n, uint32_t* __restrict__ need) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    need[c] = (convert_flag[c] && chunks[c].slot == 0xFFFFFFFFu) ? 1u : 0u;
+}
+__global__ void k_assign_slots(const DevChunk* __restrict__ chunks, const uint32_t* __restrict__ need,
+                               const uint32_t* __restrict__ ord, uint32_t first, uint32_t n, uint32_t* __restrict__ slot_of) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    slot_of[c] = need[c] ? first + ord[c] : chunks[c].slot;
+}
+
+// bounding range of non-empty voxels over the whole object (object.rs:1149-1280)
+__global__ void __launch_bounds__(256) k_occupied_ranges(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
+                                                         uint32_t first_i, const unsigned char* __restrict__ voxels,
+                                                         uint32_t* __restrict__ occ) {
+    __shared__ uint32_t s_mm[6];
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+        const DevChunk ch = chunks[c];
+        if (ch.kind == 0 || (ch.kind == 2 && (ch.flags & (1u << 6)))) continue;
+        const uint32_t k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
+        const uint32_t org[3] = {(i + first_i) * 16u, j * 16u, k * 16u};
+        if (ch.kind == 1) {
+            if (tid == 0)
+                for (int d = 0; d < 3; ++d) {
+                    atomicMin(&occ[d], org[d]);
+                    atomicMax(&occ[3 + d], org[d] + 15u);
+                }
+            continue;
+        }
+        if (tid < 6) s_mm[tid] = tid < 3 ? 0xFFFFFFFFu : 0u;
+        __syncthreads();
+        const uint4 w = *reinterpret_cast<const uint4*>(voxels + (size_t)ch.slot * SLOT_BYTES + PLANE_SD + tid * 16);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        uint32_t nonempty = 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if ((ws[q >> 2] >> (8 * (q & 3) + 7)) & 1u) nonempty |= 1u << q;
+        if (nonempty) {
+            atomicMin(&s_mm[0], (uint32_t)ti);
+            atomicMin(&s_mm[1], (uint32_t)tj);
+            atomicMin(&s_mm[2], (uint32_t)(__ffs(nonempty) - 1));
+            atomicMax(&s_mm[3], (uint32_t)ti);
+            atomicMax(&s_mm[4], (uint32_t)tj);
+            atomicMax(&s_mm[5], (uint32_t)(31 - __clz(nonempty)));
+        }
+        __syncthreads();
+        if (tid == 0 && s_mm[0] != 0xFFFFFFFFu)
+            for (int d = 0; d < 3; ++d) {
+                atomicMin(&occ[d], org[d] + s_mm[d]);
+                atomicMax(&occ[3 + d], org[d] + s_mm[3 + d]);
+            }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], const AbsorbRange& r, uint32_t* need_slot,
+                               uint32_t n_range, cudaStream_t st) {
+    if (n_range == 0) return cudaSuccess;
+    k_absorb_plan<<<(n_range + 255) / 256, 256, 0, st>>>(chunks, make_uint3(nb[0], nb[1], nb[2]), r, need_slot, n_range);
+    return cudaGetLastError();
+}
+cudaError_t launch_absorb_apply(const AbsorbArgs& a, uint32_t grid, cudaStream_t st) {
+    if (a.n_range == 0) return cudaSuccess;
+    k_absorb_apply<<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_absorb_face_mask(const uint32_t nb[3], const AbsorbRange& b, uint8_t* face_mask, uint32_t n,
+                                    cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_absorb_face_mask<<<(n + 255) / 256, 256, 0, st>>>(make_uint3(nb[0], nb[1], nb[2]), b, face_mask, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_need_slot_for_convert(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t n, uint32_t* need,
+                                         cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_need_slot_for_convert<<<(n + 255) / 256, 256, 0, st>>>(chunks, convert_flag, n, need);
+    return cudaGetLastError();
+}
+cudaError_t launch_assign_slots(const DevChunk* chunks, const uint32_t* need, const uint32_t* ord, uint32_t first,
+                                uint32_t n, uint32_t* slot_of, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_assign_slots<<<(n + 255) / 256, 256, 0, st>>>(chunks, need, ord, first, n, slot_of);
+    return cudaGetLastError();
+}
+cudaError_t launch_occupied_ranges(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t first_i,
+                                   const unsigned char* voxels, uint32_t* occ, uint32_t grid, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_occupied_ranges<<<grid, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), first_i, voxels, occ);
+    return cudaGetLastError();
+}
+
+}  // namespace ivx

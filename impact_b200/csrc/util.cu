@@ -1,0 +1,121 @@
+// Small bookkeeping kernels: prefix sums, list compaction, capacity planning.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ivx {
+
+// Exclusive scan of n uint32 by one 1024-thread CTA (n is chunk-count sized).
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                         uint32_t n, uint32_t* __restrict__ total) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t v = i < n ? in[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t warp_off = warp > 0 ? s_warp[warp - 1] : 0u;
+        if (i < n) out[i] = carry + warp_off + x - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + warp_off + x;
+        __syncthreads();
+    }
+    if (tid == 0 && total) *total = s_carry;
+}
+
+cudaError_t launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total, cudaStream_t st) {
+    k_exclusive_scan<<<1, 1024, 0, st>>>(in, out, n, total);
+    return cudaGetLastError();
+}
+
+// capacity of a child block's instruction list = length of its parent's list
+__global__ void k_child_caps(const uint32_t* __restrict__ parent_len, uint32_t n_blocks, uint3 nb, uint3 parent_nb,
+                             uint32_t ratio, uint32_t* __restrict__ caps) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    uint32_t bk = b % nb.z, bj = (b / nb.z) % nb.y, bi = b / (nb.z * nb.y);
+    uint32_t p = ((bi / ratio) * parent_nb.y + bj / ratio) * parent_nb.z + bk / ratio;
+    caps[b] = parent_len[p];
+}
+cudaError_t launch_child_caps(const uint32_t* parent_len, uint32_t n_blocks, const uint32_t nb[3],
+                              const uint32_t parent_nb[3], uint32_t ratio, uint32_t* caps, cudaStream_t st) {
+    if (n_blocks == 0) return cudaSuccess;
+    k_child_caps<<<(n_blocks + 255) / 256, 256, 0, st>>>(parent_len, n_blocks, make_uint3(nb[0], nb[1], nb[2]),
+                                                         make_uint3(parent_nb[0], parent_nb[1], parent_nb[2]), ratio, caps);
+    return cudaGetLastError();
+}
+
+// After the exact fold: which chunks need voxel evaluation (ACTIVE) and which
+// pre-classified uniform chunks touch a non-uniform neighbour and may have to
+// be converted to non-uniform storage later (object.rs:2118-2160).
+__global__ void k_plan_slots(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb, uint32_t* __restrict__ active_flag,
+                             uint32_t* __restrict__ slot_flag) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const uint8_t pre = chunks[c].pre;
+    uint32_t act = pre == PRE_ACTIVE ? 1u : 0u;
+    uint32_t need = act;
+    if (pre == PRE_UNIFORM) {
+        int k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
+        const int d[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+        for (int f = 0; f < 6; ++f) {
+            int ni = i + d[f][0], nj = j + d[f][1], nk = k + d[f][2];
+            bool uni = false;
+            if (ni >= 0 && nj >= 0 && nk >= 0 && ni < (int)nb.x && nj < (int)nb.y && nk < (int)nb.z)
+                uni = chunks[(ni * nb.y + nj) * nb.z + nk].pre == PRE_UNIFORM;
+            if (!uni) need = 1u;
+        }
+    }
+    active_flag[c] = act;
+    slot_flag[c] = need;
+}
+__global__ void k_scatter_active(const uint32_t* __restrict__ active_flag, const uint32_t* __restrict__ active_scan,
+                                 uint32_t n, uint32_t* __restrict__ active_list) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    if (active_flag[c]) active_list[active_scan[c]] = c;
+}
+cudaError_t launch_plan_slots(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t* active_flag,
+                              uint32_t* slot_flag, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_plan_slots<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), active_flag, slot_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter_active(const uint32_t* active_flag, const uint32_t* active_scan, uint32_t n,
+                                  uint32_t* active_list, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_scatter_active<<<(n + 255) / 256, 256, 0, st>>>(active_flag, active_scan, n, active_list);
+    return cudaGetLastError();
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t n, uint32_t v) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+cudaError_t launch_fill_u32(uint32_t* p, uint32_t n, uint32_t v, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_fill_u32<<<(n + 255) / 256, 256, 0, st>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+}  // namespace ivx

@@ -1,0 +1,240 @@
+"""Host-side mirror of the reference's voxel object API over the C ABI.
+
+Names follow the reference (engine/crates/impact_voxel/src):
+  SDFGraph.build_in             → Context.build_generator       (generation/sdf/atomic.rs:1031)
+  SDFVoxelGenerator::new        → SDFVoxelGenerator             (generation.rs:207)
+  VoxelObject::generate         → VoxelObject.generate          (object.rs:239)
+  VoxelObjectMesh::create       → VoxelObjectMesh.create        (mesh.rs:280)
+  sync_with_voxel_object        → VoxelObjectMesh.sync_with_voxel_object (mesh.rs:360)
+  apply_sphere_absorption       → VoxelObject.absorb_sphere     (interaction/absorption.rs:801)
+All compute happens in libimpact_voxel_cuda.so on the GPU; this module only
+marshals POD buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .graph import PROG_NODE_DTYPE, SDFGraph, VoxelTypeGenerator
+
+
+class Context:
+    """One `ivx_ctx`: device, stream and device-memory pool."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = L.lib()
+        cfg = L.Config(self._lib.ivx_abi_version(), device, C.c_void_p(stream) if stream else None, 0)
+        h = C.c_void_p()
+        rc = self._lib.ivx_create(C.byref(cfg), C.byref(h))
+        if rc != L.IVX_OK:
+            raise L.IvxError(rc, "ivx_create failed (a CUDA device is required; there is no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.ivx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def check(self, rc: int):
+        if rc != L.IVX_OK:
+            raise L.IvxError(rc, self._lib.ivx_last_error(self.h).decode())
+
+    @property
+    def kernel_launch_count(self) -> int:
+        return int(self._lib.ivx_kernel_launch_count(self.h))
+
+    def synchronize(self):
+        self.check(self._lib.ivx_synchronize(self.h))
+
+    def build_generator(self, graph: SDFGraph) -> "SDFGenerator":
+        """`SDFGraph::build_in` → `SDFGenerator::new_in` (atomic.rs:1031-1037, 228-493)."""
+        return SDFGenerator.from_graph(self, graph.nodes(), graph.root_node_id)
+
+
+class SDFGenerator:
+    """`SDFGenerator` (atomic.rs:33-40): the compiled post-order program, resident on the device."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+        info = L.ProgramInfo()
+        ctx.check(ctx._lib.ivx_program_info_get(ctx.h, self.h, C.byref(info)))
+        self.node_count, self.stack_depth = info.node_count, info.stack_depth
+        self.domain = (np.array(info.domain_lo[:], np.float32), np.array(info.domain_hi[:], np.float32))
+
+    @classmethod
+    def from_graph(cls, ctx: Context, nodes: np.ndarray, root: int) -> "SDFGenerator":
+        nodes = np.ascontiguousarray(nodes)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.ivx_program_build(ctx.h, L.ptr(nodes), C.c_uint32(len(nodes)), C.c_uint32(root), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_processed_nodes(cls, ctx: Context, nodes: np.ndarray, stack_depth: int, domain_lo, domain_hi):
+        nodes = np.ascontiguousarray(nodes)
+        lo = np.asarray(domain_lo, np.float32)
+        hi = np.asarray(domain_hi, np.float32)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.ivx_program_upload(ctx.h, L.ptr(nodes), C.c_uint32(len(nodes)), C.c_uint32(stack_depth),
+                                              L.ptr(lo), L.ptr(hi), C.byref(h)))
+        return cls(ctx, h)
+
+    def nodes(self) -> np.ndarray:
+        out = np.zeros(self.node_count, PROG_NODE_DTYPE)
+        self.ctx.check(self.ctx._lib.ivx_program_nodes(self.ctx.h, self.h, L.ptr(out), C.c_uint32(len(out))))
+        return out
+
+    def compute_signed_distances_for_chunks(self, chunk_origins_in_root_space) -> np.ndarray:
+        """Batched `compute_signed_distances_for_chunk` (atomic.rs:207-216) → (n, 4096) f32."""
+        org = np.ascontiguousarray(chunk_origins_in_root_space, np.float32).reshape(-1, 3)
+        out = np.zeros((len(org), 4096), np.float32)
+        self.ctx.check(self.ctx._lib.ivx_program_eval_chunks(self.ctx.h, self.h, L.ptr(org), C.c_uint32(len(org)), L.ptr(out)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx._lib.ivx_program_free(self.ctx.h, self.h)
+            self.h = None
+
+
+class SDFVoxelGenerator:
+    """`SDFVoxelGenerator` (generation.rs:70-77): voxel extent + SDF generator + voxel type generator."""
+
+    def __init__(self, voxel_extent: float, sdf_generator: SDFGenerator, voxel_type_generator: VoxelTypeGenerator):
+        assert voxel_extent > 0.0
+        self.voxel_extent = voxel_extent
+        self.sdf_generator = sdf_generator
+        self.voxel_type_generator = voxel_type_generator
+
+
+class VoxelObject:
+    """`VoxelObject` (object.rs:45-57), device resident."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+
+    @classmethod
+    def generate(cls, generator: SDFVoxelGenerator, chunk_i_range=None) -> "VoxelObject":
+        """`VoxelObject::generate` (object.rs:239-244); `chunk_i_range` = x-slab for multi-GPU."""
+        ctx = generator.sdf_generator.ctx
+        tg = generator.voxel_type_generator.pod()
+        h = C.c_void_p()
+        if chunk_i_range is None:
+            ctx.check(ctx._lib.ivx_object_generate(ctx.h, generator.sdf_generator.h, C.c_float(generator.voxel_extent),
+                                                   L.ptr(tg), C.byref(h)))
+        else:
+            ctx.check(ctx._lib.ivx_object_generate_slab(ctx.h, generator.sdf_generator.h, C.c_float(generator.voxel_extent),
+                                                        L.ptr(tg), C.c_uint32(chunk_i_range[0]),
+                                                        C.c_uint32(chunk_i_range[1]), C.byref(h)))
+        return cls(ctx, h)
+
+    def free(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx._lib.ivx_object_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        self.free()
+
+    def info(self) -> dict:
+        i = L.ObjectInfo()
+        self.ctx.check(self.ctx._lib.ivx_object_info_get(self.ctx.h, self.h, C.byref(i)))
+        return {
+            "voxel_extent": i.voxel_extent, "grid_shape": tuple(i.grid_shape[:]), "chunk_counts": tuple(i.chunk_counts[:]),
+            "chunk_i_begin": i.chunk_i_begin, "chunk_i_end": i.chunk_i_end, "n_void": i.n_void, "n_uniform": i.n_uniform,
+            "n_non_uniform": i.n_non_uniform,
+            "occupied_chunk_ranges": np.array(i.occupied_chunk_ranges[:], np.uint32).reshape(3, 2),
+            "occupied_voxel_ranges": np.array(i.occupied_voxel_ranges[:], np.uint32).reshape(3, 2),
+            "device_bytes": i.device_bytes,
+        }
+
+    def download(self, with_voxels: bool = True):
+        """→ (chunks[C], voxels[4096 * n_non_uniform]) in the reference's layout."""
+        inf = self.info()
+        n = (inf["chunk_i_end"] - inf["chunk_i_begin"]) * inf["chunk_counts"][1] * inf["chunk_counts"][2]
+        chunks = np.zeros(n, L.CHUNK_DTYPE)
+        voxels = np.zeros(inf["n_non_uniform"] * 4096 if with_voxels else 0, L.VOXEL_DTYPE)
+        self.ctx.check(self.ctx._lib.ivx_object_download(
+            self.ctx.h, self.h, L.ptr(chunks), C.c_size_t(n), L.ptr(voxels) if with_voxels else None,
+            C.c_size_t(len(voxels))))
+        return chunks, voxels
+
+    def absorb_sphere(self, center, radius: float, influence_radius: float) -> dict:
+        """`apply_sphere_absorption` (absorption.rs:801-844) in normalized voxel space."""
+        c = np.asarray(center, np.float32)
+        st = L.AbsorbStats()
+        self.ctx.check(self.ctx._lib.ivx_object_absorb_sphere(self.ctx.h, self.h, L.ptr(c), C.c_float(radius),
+                                                              C.c_float(influence_radius), C.byref(st)))
+        return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
+
+    def invalidated_mesh_chunk_indices(self) -> np.ndarray:
+        cnt = C.c_uint32()
+        self.ctx.check(self.ctx._lib.ivx_object_dirty_chunks(self.ctx.h, self.h, None, C.c_uint32(0), C.byref(cnt)))
+        out = np.zeros(max(1, cnt.value), np.uint32)
+        self.ctx.check(self.ctx._lib.ivx_object_dirty_chunks(self.ctx.h, self.h, L.ptr(out), C.c_uint32(len(out)), C.byref(cnt)))
+        return out[: cnt.value]
+
+
+class VoxelObjectMesh:
+    """`VoxelObjectMesh` (mesh.rs:50-58): SoA buffers + chunk submesh table."""
+
+    def __init__(self, obj: VoxelObject, info: L.MeshInfo):
+        self.obj = obj
+        self.n_vertices, self.n_indices, self.n_submeshes = info.n_vertices, info.n_indices, info.n_submeshes
+        self.n_exposed_chunks = info.n_exposed_chunks
+        self.device_info = info
+
+    @classmethod
+    def create(cls, obj: VoxelObject) -> "VoxelObjectMesh":
+        info = L.MeshInfo()
+        obj.ctx.check(obj.ctx._lib.ivx_object_mesh(obj.ctx.h, obj.h, C.byref(info)))
+        return cls(obj, info)
+
+    @classmethod
+    def sync_with_voxel_object(cls, obj: VoxelObject) -> "VoxelObjectMesh":
+        """Re-meshes the invalidated chunks only; returns their meshes as one compact patch."""
+        info = L.MeshInfo()
+        obj.ctx.check(obj.ctx._lib.ivx_object_remesh_dirty(obj.ctx.h, obj.h, C.byref(info)))
+        return cls(obj, info)
+
+    def download(self) -> dict:
+        pos = np.zeros((self.n_vertices, 3), np.float32)
+        nrm = np.zeros((self.n_vertices, 3), np.float32)
+        im = np.zeros(self.n_indices, L.INDEX_MATERIALS_DTYPE)
+        idx = np.zeros(self.n_indices, np.uint32)
+        sm = np.zeros(self.n_submeshes, L.SUBMESH_DTYPE)
+        vr = np.zeros((self.n_submeshes, 2), np.uint32)
+        ctx = self.obj.ctx
+        ctx.check(ctx._lib.ivx_mesh_download(ctx.h, self.obj.h, L.ptr(pos), L.ptr(nrm), L.ptr(im), L.ptr(idx), L.ptr(sm), L.ptr(vr)))
+        return {"positions": pos, "normals": nrm, "index_materials": im, "indices": idx, "submeshes": sm,
+                "vertex_ranges": vr}
+
+
+def compile_program_host(graph: SDFGraph):
+    """Host-only `SDFGraph::build_in` (no device needed): → (nodes, stack_depth, domain_lo, domain_hi).
+
+    Raises ValueError with the reference's message for cycles / missing nodes (atomic.rs:263-268).
+    """
+    lib = L.lib()
+    nodes = np.ascontiguousarray(graph.nodes())
+    count = C.c_uint32()
+    info = L.ProgramInfo()
+    err = C.create_string_buffer(256)
+    cap = max(16, 4 * len(nodes))
+    while True:
+        out = np.zeros(cap, PROG_NODE_DTYPE)
+        rc = lib.ivx_program_compile_host(L.ptr(nodes), C.c_uint32(len(nodes)), C.c_uint32(graph.root_node_id), L.ptr(out),
+                                          C.c_uint32(cap), C.byref(count), C.byref(info), err, C.c_size_t(256))
+        if rc == 5:  # IVX_ERR_CAPACITY
+            cap = count.value
+            continue
+        if rc == 2:
+            raise ValueError(err.value.decode())
+        if rc != 0:
+            raise L.IvxError(rc, "ivx_program_compile_host")
+        return (out[: count.value].copy(), info.stack_depth, np.array(info.domain_lo[:], np.float32),
+                np.array(info.domain_hi[:], np.float32))

@@ -1,0 +1,274 @@
+/*
+ * impact_voxel_cuda.h — C ABI of libimpact_voxel_cuda.so
+ *
+ * A B200 (sm_100a) implementation of the `impact_voxel` hot path of
+ * lars-frogner/Impact: compile an atomic SDF graph, generate a chunked voxel
+ * object from it, derive adjacency / obscuredness state, mesh it with Surface
+ * Nets, and re-run the same stages on dirty chunks after sphere absorption.
+ *
+ * The reference has no FFI seam around this path (it is called through Rust
+ * generics); each entry point below names the reference function it replaces.
+ * Reference paths are relative to engine/crates/impact_voxel/src/.
+ *
+ * Conventions
+ *  - every function returns an ivx_status (0 = OK) and never throws / aborts;
+ *    ivx_last_error() gives the message of the last failing call on that ctx;
+ *  - the caller owns all host memory, the library owns all device memory;
+ *  - calls are synchronous on return (work is enqueued on the ctx stream and
+ *    the stream is synchronised) unless the name ends in `_async`;
+ *  - one ivx_ctx is used from one thread at a time (the engine already holds
+ *    the voxel manager write lock around these calls).
+ *  - there is NO CPU fallback: without a CUDA device ivx_create fails.
+ */
+#ifndef IMPACT_VOXEL_CUDA_H
+#define IMPACT_VOXEL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVX_CHUNK_SIZE 16u        /* object.rs:199-210 CHUNK_SIZE */
+#define IVX_CHUNK_VOXELS 4096u
+#define IVX_ABI_VERSION 1u
+
+typedef enum ivx_status {
+    IVX_OK = 0,
+    IVX_ERR_INVALID_ARGUMENT = 1,
+    IVX_ERR_GRAPH = 2,        /* cycle / missing node / bad kind: anyhow errors of atomic.rs:263-268 */
+    IVX_ERR_CUDA = 3,
+    IVX_ERR_OUT_OF_MEMORY = 4,
+    IVX_ERR_CAPACITY = 5,     /* caller buffer too small */
+    IVX_ERR_UNSUPPORTED = 6,
+    IVX_ERR_NO_DEVICE = 7
+} ivx_status;
+
+/* SDFNode variants in declaration order (generation/sdf/atomic.rs:63-81). */
+typedef enum ivx_node_kind {
+    IVX_SPHERE = 0,
+    IVX_CAPSULE = 1,
+    IVX_BOX = 2,
+    IVX_TRANSLATION = 3,
+    IVX_ROTATION = 4,
+    IVX_SCALING = 5,
+    IVX_MULTIFRACTAL_NOISE = 6,
+    IVX_UNION = 7,
+    IVX_SUBTRACTION = 8,
+    IVX_INTERSECTION = 9
+} ivx_node_kind;
+
+/* One atomic graph node = `SDFNode` (atomic.rs:63-181) as the host would
+ * construct it with SDFNode::new_* (atomic.rs:1060-1128):
+ *   sphere       p[0]=radius
+ *   capsule      p[0]=segment_length p[1]=radius
+ *   box          p[0..3]=extents
+ *   translation  child[0], p[0..3]=translation
+ *   rotation     child[0], p[0..4]=unit quaternion (x,y,z,w)
+ *   scaling      child[0], p[0]=scaling
+ *   noise        child[0], octaves, seed, p[0]=frequency p[1]=lacunarity
+ *                p[2]=persistence p[3]=amplitude
+ *   union/subtraction/intersection  child[0], child[1], p[0]=smoothness      */
+typedef struct ivx_sdf_node {
+    uint32_t kind;
+    uint32_t child[2];
+    uint32_t octaves;
+    uint32_t seed;
+    float p[8];
+} ivx_sdf_node;
+
+/* One compiled program node = `ProcessedSDFNode` (atomic.rs:83-102) after
+ * SDFGenerator::new_in + determine_transforms_and_margins (atomic.rs:228-596).
+ *   sphere p[0]=radius | capsule p[0]=half_segment_length p[1]=radius |
+ *   box p[0..3]=half_extents | scaling p[0] | noise p[0..4] as above, p[4]=noise_scale |
+ *   combine p[0]=smoothness p[1]=0.25/smoothness                              */
+typedef struct ivx_node {
+    uint32_t kind;
+    uint32_t octaves;
+    uint32_t seed;
+    uint32_t leaf_count;
+    float p[8];
+    float transform_to_node_space[16]; /* column-major Matrix4 */
+    float domain_lo[3];                /* domain_with_margin */
+    float domain_hi[3];
+    float margin;                      /* domain_margin */
+    uint32_t _pad;
+} ivx_node;
+
+/* `Voxel` (lib.rs:60-66), repr(C), 3 bytes. */
+typedef struct ivx_voxel {
+    uint8_t voxel_type;
+    int8_t signed_distance; /* VoxelSignedDistance: trunc_sat(f32 * 50) (lib.rs:154-201) */
+    uint8_t flags;          /* VoxelFlags bits (lib.rs:75-101) */
+} ivx_voxel;
+
+/* `VoxelTypeGenerator` (generation/voxel_type.rs:9-36). */
+typedef struct ivx_type_generator {
+    uint32_t kind;       /* 0 = Same, 1 = GradientNoise */
+    uint32_t same_type;  /* Same: the voxel type */
+    uint32_t n_types;    /* GradientNoise: voxel_types.len() */
+    float noise_frequency;
+    float voxel_type_frequency;
+    uint32_t seed;
+} ivx_type_generator;
+
+/* `VoxelChunk` (object.rs:96-126) flattened. kind: 0 Void, 1 Uniform, 2 NonUniform.
+ * face[dim*2+side]: FaceVoxelDistribution 0 Empty, 1 Full, 2 Mixed.
+ * flags: VoxelChunkFlags (object.rs:158-182). */
+typedef struct ivx_chunk_desc {
+    uint8_t kind;
+    uint8_t flags;
+    uint8_t face[6];
+    ivx_voxel uniform_voxel;
+    uint8_t _pad;
+    uint32_t data_offset; /* units of 4096 voxels into the downloaded voxel array */
+} ivx_chunk_desc;
+
+/* `ChunkSubmesh` (mesh.rs:92-103). */
+typedef struct ivx_chunk_submesh {
+    uint32_t chunk_indices[3];
+    uint32_t index_offset;
+    uint32_t index_count;
+    uint32_t is_obscured_from_direction[8];
+} ivx_chunk_submesh;
+
+/* `VoxelMeshIndexMaterials` (mesh.rs:79-84). */
+typedef struct ivx_index_materials {
+    uint8_t indices[4];
+    uint8_t weights[4];
+} ivx_index_materials;
+
+typedef struct ivx_config {
+    uint32_t abi_version;  /* IVX_ABI_VERSION */
+    int32_t device;        /* CUDA device ordinal */
+    void* stream;          /* cudaStream_t to enqueue on; NULL = library-owned stream */
+    uint32_t flags;        /* reserved, 0 */
+} ivx_config;
+
+typedef struct ivx_program_info {
+    uint32_t node_count;
+    uint32_t stack_depth;  /* required_forward_stack_size */
+    float domain_lo[3];
+    float domain_hi[3];
+} ivx_program_info;
+
+typedef struct ivx_object_info {
+    float voxel_extent;
+    uint32_t grid_shape[3];
+    uint32_t chunk_counts[3];
+    uint32_t chunk_i_begin;   /* x-slab owned by this object (multi-GPU); [0, chunk_counts[0]) otherwise */
+    uint32_t chunk_i_end;
+    uint32_t n_void, n_uniform, n_non_uniform;
+    uint32_t occupied_chunk_ranges[6]; /* [dim*2 + {start,end}] */
+    uint32_t occupied_voxel_ranges[6];
+    uint64_t device_bytes;
+} ivx_object_info;
+
+typedef struct ivx_mesh_info {
+    uint32_t n_vertices;
+    uint32_t n_indices;
+    uint32_t n_submeshes;
+    uint32_t n_exposed_chunks;
+    /* device pointers, valid until the next mesh / remesh / free call on the object */
+    const float* d_positions;              /* 3 * n_vertices */
+    const float* d_normals;                /* 3 * n_vertices */
+    const ivx_index_materials* d_index_materials; /* n_indices */
+    const uint32_t* d_indices;             /* n_indices */
+    const ivx_chunk_submesh* d_submeshes;  /* n_submeshes */
+    const uint32_t* d_vertex_ranges;       /* 2 * n_submeshes */
+} ivx_mesh_info;
+
+typedef struct ivx_absorb_stats {
+    uint32_t touched_chunks;
+    uint32_t touched_voxels;
+    uint32_t emptied_voxels;
+    uint32_t removed_chunks;
+    uint32_t dirty_chunks; /* size of invalidated_mesh_chunk_indices after the call */
+} ivx_absorb_stats;
+
+typedef struct ivx_ctx ivx_ctx;
+typedef struct ivx_program ivx_program;
+typedef struct ivx_object ivx_object;
+
+/* ---- context ------------------------------------------------------------ */
+int ivx_create(const ivx_config* config, ivx_ctx** out_ctx);
+void ivx_destroy(ivx_ctx* ctx);
+const char* ivx_last_error(const ivx_ctx* ctx);
+uint32_t ivx_abi_version(void);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t ivx_kernel_launch_count(const ivx_ctx* ctx);
+int ivx_synchronize(ivx_ctx* ctx);
+
+/* ---- graph compile ------------------------------------------------------
+ * ivx_program_build  replaces SDFGraph::build_in → SDFGenerator::new_in
+ *                    (atomic.rs:1031-1037, 228-493, 495-596).
+ * ivx_program_upload takes an already compiled ProcessedSDFNode list (a Rust
+ *                    host that keeps SDFGenerator::new_in on its side). */
+int ivx_program_build(ivx_ctx* ctx, const ivx_sdf_node* nodes, uint32_t n_nodes, uint32_t root_node_id,
+                      ivx_program** out_program);
+int ivx_program_upload(ivx_ctx* ctx, const ivx_node* nodes, uint32_t n_nodes, uint32_t stack_depth,
+                       const float domain_lo[3], const float domain_hi[3], ivx_program** out_program);
+/* Host-only form of ivx_program_build (no device, no ctx): writes the compiled
+ * ProcessedSDFNode list into out_nodes (capacity in nodes; the unrolled tree can
+ * be larger than n_nodes) and returns IVX_ERR_CAPACITY with *out_count set when
+ * it does not fit. err receives the reference's error text on IVX_ERR_GRAPH. */
+int ivx_program_compile_host(const ivx_sdf_node* nodes, uint32_t n_nodes, uint32_t root_node_id,
+                             ivx_node* out_nodes, uint32_t capacity, uint32_t* out_count,
+                             ivx_program_info* out_info, char* err, size_t err_capacity);
+int ivx_program_info_get(ivx_ctx* ctx, const ivx_program* program, ivx_program_info* out);
+int ivx_program_nodes(ivx_ctx* ctx, const ivx_program* program, ivx_node* out, uint32_t capacity);
+void ivx_program_free(ivx_ctx* ctx, ivx_program* program);
+
+/* SDFGenerator::compute_signed_distances_for_chunk (atomic.rs:207-216) for a
+ * batch of chunks: origins = n_chunks x 3 chunk lower corners in root space;
+ * out = n_chunks x 4096 f32 (host). Used by the parity tests and by the
+ * meta-graph compiler's probes. */
+int ivx_program_eval_chunks(ivx_ctx* ctx, const ivx_program* program, const float* chunk_origins,
+                            uint32_t n_chunks, float* out_signed_distances);
+
+/* ---- object generation --------------------------------------------------
+ * Replaces SDFVoxelGenerator::new (generation.rs:207-258) +
+ * VoxelObject::generate / generate_in_parallel (object.rs:239-263):
+ * generate_without_derived_state, update_occupied_voxel_ranges,
+ * compute_all_derived_state (split detection excluded). */
+int ivx_object_generate(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
+                        const ivx_type_generator* type_generator, ivx_object** out_object);
+/* Multi-GPU: generate only chunk planes [chunk_i_begin, chunk_i_end) of the
+ * x-major chunk grid (the reference's thread split, object.rs:423-427) plus
+ * one halo chunk plane on each inner side. */
+int ivx_object_generate_slab(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
+                             const ivx_type_generator* type_generator, uint32_t chunk_i_begin,
+                             uint32_t chunk_i_end, ivx_object** out_object);
+int ivx_object_info_get(ivx_ctx* ctx, const ivx_object* object, ivx_object_info* out);
+/* → the Rust-side VoxelObject: chunks[C] in x-major linear order and the voxels
+ * of the NonUniform chunks, data_offset = ordinal in that order. */
+int ivx_object_download(ivx_ctx* ctx, const ivx_object* object, ivx_chunk_desc* chunks,
+                        size_t chunk_capacity, ivx_voxel* voxels, size_t voxel_capacity);
+void ivx_object_free(ivx_ctx* ctx, ivx_object* object);
+
+/* ---- meshing ------------------------------------------------------------
+ * ivx_object_mesh replaces VoxelObjectMesh::create / recreate (mesh.rs:280-354):
+ * for_each_exposed_chunk_with_sdf + compute_surface_nets_mesh + append. */
+int ivx_object_mesh(ivx_ctx* ctx, ivx_object* object, ivx_mesh_info* out);
+int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* object, float* positions, float* normals,
+                      ivx_index_materials* index_materials, uint32_t* indices,
+                      ivx_chunk_submesh* submeshes, uint32_t* vertex_ranges);
+
+/* ---- modification -------------------------------------------------------
+ * ivx_object_absorb_sphere replaces apply_sphere_absorption
+ * (interaction/absorption.rs:801-844) → modify_voxels_within_sphere
+ * (object/intersection.rs:283-394): centre / radii in normalized voxel space
+ * (voxel extent 1, grid lower corner at the origin).
+ * ivx_object_remesh_dirty replaces VoxelObjectMesh::sync_with_voxel_object
+ * (mesh.rs:360-456) for the invalidated chunk set and clears it. */
+int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* object, const float center[3], float radius,
+                             float influence_radius, ivx_absorb_stats* out_stats);
+int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* object, uint32_t* out_linear_indices,
+                            uint32_t capacity, uint32_t* out_count);
+int ivx_object_remesh_dirty(ivx_ctx* ctx, ivx_object* object, ivx_mesh_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPACT_VOXEL_CUDA_H */

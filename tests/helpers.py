@@ -1,0 +1,181 @@
+"""Shared test inputs (the reference's own benchmark graphs) and comparison helpers."""
+from __future__ import annotations
+
+import numpy as np
+
+from impact_b200.graph import SDFGraph, VoxelTypeGenerator
+
+# ---- graphs: engine/src/benchmark/benchmarks/generation.rs:24-124 and BASELINE.md §4 ----------
+
+
+def sphere_graph(radius=31.0):
+    """BASELINE config 1: `Sphere(r = 31)` → 64³ grid."""
+    g = SDFGraph()
+    g.sphere(radius)
+    return g
+
+
+def box_graph(extent=80.0):
+    g = SDFGraph()  # generate_box (generation.rs:24-38)
+    g.box([extent] * 3)
+    return g
+
+
+def sphere_union_graph(scale=1.0):
+    g = SDFGraph()  # generate_sphere_union (generation.rs:40-59)
+    s1 = g.sphere(60.0 * scale)
+    s2 = g.sphere(60.0 * scale)
+    s2 = g.translation(s2, [50.0 * scale, 0.0, 0.0])
+    g.union(s1, s2, 1.0)
+    return g
+
+
+def complex_graph(scale=1.0):
+    g = SDFGraph()  # generate_complex_object (generation.rs:61-85)
+    s = g.sphere(60.0 * scale)
+    s = g.translation(s, [50.0 * scale, 0.0, 0.0])
+    b = g.box([50.0 * scale, 60.0 * scale, 70.0 * scale])
+    b = g.scaling(b, 0.9)
+    b = g.rotation_from_axis_angle(b, [0.0, 1.0, 0.0], 10.0)
+    g.union(s, b, 1.0)
+    return g
+
+
+def noisy_sphere_graph(radius=80.0, octaves=8):
+    g = SDFGraph()  # generate_object_with_multifractal_noise (generation.rs:87-103)
+    s = g.sphere(radius)
+    g.multifractal_noise(s, octaves, 0.02, 2.0, 0.6, 4.0, 0)
+    return g
+
+
+def noisy_box_graph(extent=246.0, octaves=8):
+    """BASELINE config 2: box perturbed by 8-octave gradient noise → 256³ for extent 246."""
+    g = SDFGraph()
+    b = g.box([extent] * 3)
+    g.multifractal_noise(b, octaves, 0.02, 2.0, 0.6, 4.0, 0)
+    return g
+
+
+def csg_zoo_graph():
+    """Every node kind once: primitives, all transforms, noise under a scaling + rotation
+    (the per-voxel noise path), smooth and hard union / subtraction / intersection, a shared
+    sub-graph (DAG unrolling)."""
+    g = SDFGraph()
+    s = g.sphere(20.0)
+    c = g.capsule(24.0, 7.0)
+    c = g.rotation_from_axis_angle(c, [1.0, 0.5, 0.25], 0.7)
+    c = g.translation(c, [14.0, -3.0, 5.0])
+    u = g.union(s, c, 4.0)
+    b = g.box([18.0, 30.0, 12.0])
+    b = g.translation(b, [-12.0, 6.0, -4.0])
+    sub = g.subtraction(u, b, 2.0)
+    n = g.multifractal_noise(sub, 3, 0.05, 2.0, 0.5, 1.5, 7)
+    n = g.scaling(n, 1.3)
+    n = g.rotation_from_axis_angle(n, [0.0, 0.0, 1.0], 0.3)
+    s2 = g.sphere(26.0)
+    inter = g.intersection(n, s2, 0.0)
+    small = g.sphere(5.0)
+    t1 = g.translation(small, [0.0, 22.0, 0.0])
+    t2 = g.translation(small, [0.0, -22.0, 0.0])  # `small` shared by two parents
+    both = g.union(t1, t2, 0.0)
+    g.union(inter, both, 3.0)
+    return g
+
+
+def asteroid_like_graph(n_craters=24, radius=40.0, seed=3):
+    """A hand-built stand-in with the asteroid's structure (smooth union of a few spheres, noise,
+    smooth subtraction of a balanced union tree of rotated capsules, final noise)."""
+    rng = np.random.default_rng(seed)
+    g = SDFGraph()
+    body = g.sphere(radius)
+    for _ in range(3):
+        s = g.sphere(float(radius * rng.uniform(0.4, 0.7)))
+        s = g.translation(s, list(map(float, rng.uniform(-0.6 * radius, 0.6 * radius, 3))))
+        body = g.union(body, s, 0.25 * radius)
+    body = g.multifractal_noise(body, 1, 0.02, 2.0, 0.5, 0.1 * radius, 1)
+    craters = []
+    for _ in range(n_craters):
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        c = g.capsule(float(radius * 0.2), float(radius * rng.uniform(0.05, 0.15)))
+        c = g.rotation_from_axis_angle(c, list(map(float, rng.normal(size=3))), float(rng.uniform(0, 3.0)))
+        c = g.translation(c, list(map(float, d * radius * 0.95)))
+        craters.append(c)
+    while len(craters) > 1:  # balanced union tree (meta.rs:2390-2409)
+        nxt = []
+        for i in range(0, len(craters) - 1, 2):
+            nxt.append(g.union(craters[i], craters[i + 1], 0.05 * radius))
+        if len(craters) % 2:
+            nxt.append(craters[-1])
+        craters = nxt
+    body = g.subtraction(body, craters[0], 0.05 * radius)
+    g.multifractal_noise(body, 5, 0.02, 2.0, 0.546, 2.0, 2)
+    return g
+
+
+SAME0 = VoxelTypeGenerator.same(0)
+GRADIENT4 = VoxelTypeGenerator.gradient_noise([0, 1, 2, 3], 0.02, 1.0, 0)  # generation.rs:113-124
+
+
+# ---- comparisons ------------------------------------------------------------------------------
+
+def f32_bits_equal(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Bitwise f32 equality, except that any NaN equals any NaN (x86 and CUDA produce different payloads)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+def assert_objects_equal(gpu_chunks, gpu_voxels, orc_chunks, orc_voxels):
+    """Per-chunk parity: kind, flags, face distributions, uniform voxel, and all 4096 voxels.
+
+    data_offset is NOT compared: the reference's own value depends on traversal order
+    (object.rs:2540-2543); voxels are matched through each side's data_offset."""
+    assert len(gpu_chunks) == len(orc_chunks)
+    assert np.array_equal(gpu_chunks["kind"], orc_chunks["kind"]), "chunk kinds differ"
+    nu = orc_chunks["kind"] == 2
+    assert np.array_equal(gpu_chunks["flags"][nu], orc_chunks["flags"][nu]), "chunk flags differ"
+    assert np.array_equal(gpu_chunks["face"][nu], orc_chunks["face"][nu]), "face distributions differ"
+    un = orc_chunks["kind"] == 1
+    for f in ("uniform_type", "uniform_sd", "uniform_flags"):
+        assert np.array_equal(gpu_chunks[f][un], orc_chunks[f][un]), f"{f} differs"
+    if not nu.any():
+        return
+    gv = gpu_voxels.reshape(-1, 4096)[gpu_chunks["data_offset"][nu]]
+    ov = orc_voxels.reshape(-1, 4096)[orc_chunks["data_offset"][nu]]
+    for f in ("sd", "flags", "type"):
+        if not np.array_equal(gv[f], ov[f]):
+            bad = np.argwhere(gv[f] != ov[f])
+            c, v = bad[0]
+            cidx = np.flatnonzero(nu)[c]
+            raise AssertionError(
+                f"voxel field {f!r} differs in {len(bad)} voxels of {len(np.unique(bad[:, 0]))} chunks; first: chunk {cidx} "
+                f"voxel {v} (i,j,k={v >> 8},{(v >> 4) & 15},{v & 15}) gpu={gv[f][c, v]} oracle={ov[f][c, v]}")
+
+
+def assert_meshes_equal(gm: dict, om) -> None:
+    """Bit-exact mesh parity incl. order: positions, normals, indices, index materials, submesh table."""
+    assert len(gm["positions"]) == om.n_vertices, (len(gm["positions"]), om.n_vertices)
+    assert len(gm["indices"]) == om.n_indices, (len(gm["indices"]), om.n_indices)
+    assert len(gm["submeshes"]) == om.n_submeshes
+    assert np.array_equal(gm["indices"], om.indices), "indices differ"
+    assert f32_bits_equal(gm["positions"], om.positions).all(), "positions differ"
+    assert f32_bits_equal(gm["normals"], om.normals).all(), "normals differ"
+    assert np.array_equal(gm["index_materials"]["indices"], om.index_materials["indices"]), "index material ids differ"
+    assert np.array_equal(gm["index_materials"]["weights"], om.index_materials["weights"]), "index material weights differ"
+    for f in ("chunk_indices", "index_offset", "index_count", "obscured"):
+        assert np.array_equal(gm["submeshes"][f], om.submeshes[f]), f"submesh {f} differs"
+    assert np.array_equal(gm["vertex_ranges"], om.vertex_ranges)
+
+
+def euler_characteristic(positions: np.ndarray, indices: np.ndarray, weld=1e3):
+    """V - E + F after welding the vertices chunks duplicate along their seams; also the histogram
+    of how many triangles use each edge (closed manifold ⇒ every edge exactly twice)."""
+    key = np.round(positions.astype(np.float64) * weld).astype(np.int64)
+    _, inv = np.unique(key, axis=0, return_inverse=True)
+    tris = inv[indices.reshape(-1, 3).astype(np.int64)]
+    edges = np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]])
+    edges.sort(axis=1)
+    ue, cnt = np.unique(edges, axis=0, return_counts=True)
+    v = len(np.unique(inv))
+    return v - len(ue) + len(tris), np.bincount(cnt)
