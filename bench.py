@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — voxels/sec generated + meshed on B200 through libimpact_voxel_cuda.so.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A step = one pass of the hot path over one object: SDF generation → quantise / classify →
+derived state → Surface Nets mesh, for every chunk of the grid (for N > 1: of this rank's x-slab).
+`value` is whole-job voxels/s with the compiled SDF program already resident in HBM; `e2e` is the
+same metric through the host-buffer C ABI (graph nodes in pinned host memory → compile + upload →
+generate → mesh → object and mesh copied back to pinned host memory) inside the timed region.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "voxels_per_sec_generated_and_meshed"
+UNIT = "voxels/s"
+
+
+# ---------------------------------------------------------------------------------------------
+def make_workload(name: str):
+    """→ (graph, type generator, description). Host only."""
+    from impact_b200 import workloads as W
+
+    if name == "sphere64":
+        return W.sphere(31.0), W.same_type(0), "config 1: Sphere(r=31), Same(0)"
+    if name == "sphere202":
+        return W.sphere(100.0), W.same_type(0), "engine bench shape: Sphere(r=100), Same(0)"
+    if name == "noisybox256":
+        return W.noisy_box(246.0, 8), W.same_type(0), "config 2: Box(246^3) + 8-octave noise, Same(0)"
+    if name in ("asteroid512", "asteroid1024"):
+        hi = 512 if name == "asteroid512" else 1024
+        try:
+            from impact_b200 import meta  # meta-graph compiler (asteroid.vgen.ron)
+
+            graph = meta.asteroid_graph_scaled(hi - 16, hi)
+            desc = f"asteroid.vgen.ron compiled (seed 0), max grid dim in ({hi - 16},{hi}], GradientNoise types"
+        except ImportError:
+            s = W.scale_to_max_dim(lambda sc: W.asteroid_stand_in(sc), hi - 16, hi, hi / 256.0)
+            graph = W.asteroid_stand_in(s)
+            desc = (f"asteroid stand-in graph (same node kinds/counts as asteroid.vgen.ron; crater placement not "
+                    f"sphere-cast), max grid dim in ({hi - 16},{hi}], GradientNoise types")
+        return graph, W.gradient_noise_types(), desc
+    raise SystemExit(f"unknown workload {name!r}")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(graph, types, target_seconds: float, threads: int) -> dict:
+    """The CPU restatement of the reference (oracle/) on a bounded sample: a slab of chunk planes
+    around the object's centre, generate + derive + mesh, contiguous chunk ranges per thread
+    (the reference's own work split, object.rs:423-427)."""
+    from oracle import oracle_lib as O
+
+    gen = O.Generator(graph.nodes(), graph.root_node_id)
+    vg = O.VoxelGenerator(gen, 1.0, types)
+    planes = (vg.grid_shape[0] + 15) // 16
+    mid = planes // 2
+    plane_voxels = 16 * vg.grid_shape[1] * vg.grid_shape[2]
+
+    def run(p0, p1):
+        t0 = time.perf_counter()
+        obj = O.Object.generate_slab(vg, p0, p1, threads)
+        m = obj.mesh(threads)
+        dt = time.perf_counter() - t0
+        return dt, obj.t_generate, obj.t_derive, m.t_mesh
+
+    dt1, *_ = run(mid, mid + 1)
+    n = int(max(1, min(planes, round(target_seconds / max(dt1, 1e-6)))))
+    p0 = max(0, mid - n // 2)
+    p1 = min(planes, p0 + n)
+    dt, tg, td, tm = run(p0, p1)
+    vox = (p1 - p0) * plane_voxels
+    return {"value": vox / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"chunk planes [{p0},{p1}) of {planes} ({vox} voxels of the {vg.grid_shape} grid): "
+                      f"generate {tg:.2f}s + derive {td:.2f}s + mesh {tm:.2f}s, {threads} threads",
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    graph, types, desc = make_workload(args.workload)
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_reference(graph, types, per_step, threads)
+    vals, secs, last = [], 0.0, None
+    for _ in range(args.steps):
+        last = cpu_reference(graph, types, per_step, threads)
+        vals.append(last["value"])
+        secs += last["seconds"]
+    v = float(np.mean(vals))
+    from impact_b200 import workloads as W
+
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "grid_shape": list(W.grid_shape_of(graph))},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": last["sample"]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from impact_b200 import _lib as L
+    from impact_b200.voxel import Context, SDFVoxelGenerator, VoxelObject, VoxelObjectMesh, compile_program_host
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.Stream()
+    ctx = Context(local_rank, stream=stream.cuda_stream)  # raises without the CUDA library / a device
+
+    graph, types, desc = make_workload(args.workload)
+    nodes_host = graph.nodes()
+    gen = ctx.build_generator(graph)
+    vg = SDFVoxelGenerator(1.0, gen, types)
+    _, _, dlo, dhi = compile_program_host(graph)
+    grid_shape = [int(np.ceil(np.float32(h) - np.float32(l))) + 2 for l, h in zip(dlo, dhi)]
+    planes = (grid_shape[0] + 15) // 16
+    per = (planes + world - 1) // world
+    slab = (min(planes, rank * per), min(planes, (rank + 1) * per))
+    total_voxels = int(np.prod(grid_shape))
+    my_voxels = (min(grid_shape[0], slab[1] * 16) - min(grid_shape[0], slab[0] * 16)) * grid_shape[1] * grid_shape[2]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        obj = VoxelObject.generate(vg, slab if world > 1 else None)
+        mesh = VoxelObjectMesh.create(obj)
+        return obj, mesh
+
+    with torch.cuda.stream(stream):
+        info = None
+        for _ in range(max(3, args.warmup)):
+            obj, mesh = step_resident()
+            info = (obj.info(), mesh.n_vertices, mesh.n_indices, mesh.n_submeshes)
+            obj.free()
+
+        # ---- device-resident timing ----
+        barrier()
+        ctx.profile_enable(True)
+        ctx.profile_reset()
+        launches0 = ctx.kernel_launch_count
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms_total = 0.0
+        for _ in range(args.steps):
+            flush.fill_(1)  # evict L2 between timed iterations (outside the timed interval)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            obj, mesh = step_resident()
+            e1.record(stream)
+            e1.synchronize()
+            ms_total += e0.elapsed_time(e1)
+            obj.free()
+        clocks = sampler.stop()
+        barrier()
+        launches = ctx.kernel_launch_count - launches0
+        prof = ctx.profile_get()
+        ctx.profile_enable(False)
+
+        # ---- end to end through the host-buffer ABI ----
+        oi = info[0]
+        n_local_chunks = (slab[1] - slab[0]) * oi["chunk_counts"][1] * oi["chunk_counts"][2]
+        pin = lambda nbytes: torch.empty(max(1, nbytes), dtype=torch.uint8, pin_memory=True).numpy()
+        h_nodes = pin(nodes_host.nbytes)
+        h_nodes[:] = nodes_host.view(np.uint8).reshape(-1)
+        cap_vox = int(oi["n_non_uniform"] * 1.05) + 64
+        h_chunks = pin(n_local_chunks * 16)
+        h_vox = pin(cap_vox * 4096 * 3)
+        cap_v, cap_i, cap_s = int(info[1] * 1.05) + 64, int(info[2] * 1.05) + 64, int(info[3] * 1.05) + 64
+        h_pos, h_nrm, h_im = pin(cap_v * 12), pin(cap_v * 12), pin(cap_i * 8)
+        h_idx, h_sub, h_vr = pin(cap_i * 4), pin(cap_s * 52), pin(cap_s * 8)
+        lib = ctx._lib
+        tgp = types.pod()
+
+        def step_e2e():
+            prog = C.c_void_p()
+            ctx.check(lib.ivx_program_build(ctx.h, L.ptr(h_nodes), C.c_uint32(len(nodes_host)),
+                                            C.c_uint32(graph.root_node_id), C.byref(prog)))
+            o = C.c_void_p()
+            if world > 1:
+                ctx.check(lib.ivx_object_generate_slab(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), C.c_uint32(slab[0]),
+                                                       C.c_uint32(slab[1]), C.byref(o)))
+            else:
+                ctx.check(lib.ivx_object_generate(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), C.byref(o)))
+            mi = L.MeshInfo()
+            ctx.check(lib.ivx_object_mesh(ctx.h, o, C.byref(mi)))
+            ctx.check(lib.ivx_object_download(ctx.h, o, L.ptr(h_chunks), C.c_size_t(n_local_chunks), L.ptr(h_vox),
+                                              C.c_size_t(cap_vox * 4096)))
+            assert mi.n_vertices <= cap_v and mi.n_indices <= cap_i and mi.n_submeshes <= cap_s
+            ctx.check(lib.ivx_mesh_download(ctx.h, o, L.ptr(h_pos), L.ptr(h_nrm), L.ptr(h_im), L.ptr(h_idx),
+                                            L.ptr(h_sub), L.ptr(h_vr)))
+            d2h = n_local_chunks * 16 + oi["n_non_uniform"] * 4096 * 3 + mi.n_vertices * 24 + mi.n_indices * 12 + \
+                mi.n_submeshes * 60
+            lib.ivx_object_free(ctx.h, o)
+            lib.ivx_program_free(ctx.h, prog)
+            return d2h
+
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            d2h = step_e2e()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    t = torch.tensor([ms_total / args.steps, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # dominant kernel by device time
+        dom = max(prof, key=lambda k: prof[k][0])
+        dom_ms, dom_n = prof[dom]
+        dom_avg_s = (dom_ms / max(1, dom_n)) * 1e-3
+        # algorithmic bytes (dense definition): generation writes 3 B per grid voxel, meshing
+        # reads 2 B per grid voxel; one launch of a kernel processes this rank's whole slab
+        per_voxel = {"eval": 3.0, "fold_exact": 3.0, "fold_conservative": 3.0, "mesh_count": 2.0, "mesh_emit": 2.0,
+                     "boundary": 3.0}.get(dom, 5.0)
+        achieved = per_voxel * my_voxels / max(dom_avg_s, 1e-12) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload, {}).get(dom)
+        step_s = ms_step * 1e-3
+        out = {
+            "metric": METRIC, "value": total_voxels / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "description": desc, "grid_shape": grid_shape,
+                "chunks": int(np.prod(info[0]["chunk_counts"])), "parallelism": f"x-slab x{world}",
+                "rank0_chunks": {"void": oi["n_void"], "uniform": oi["n_uniform"], "non_uniform": oi["n_non_uniform"]},
+                "rank0_mesh": {"vertices": info[1], "indices": info[2], "submeshes": info[3]},
+                "l2": "256 MiB buffer written between timed iterations (outside the timed intervals); the voxel "
+                      "storage written per step also exceeds the 126 MB L2 for the 512^3 / 1024^3 workloads",
+                "timing": "CUDA events on the library's stream around each step, summed over K steps, max over ranks",
+            },
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "e2e": {"value": total_voxels / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(nodes_host.nbytes + 16), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms,
+                    "path": "ivx_program_build(host nodes) → ivx_object_generate → ivx_object_mesh → "
+                            "ivx_object_download + ivx_mesh_download into pinned host buffers"},
+            "roofline": {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_voxel": per_voxel, "voxels_per_launch": my_voxels,
+                         "avg_launch_ms": dom_avg_s * 1e3,
+                         "note": "dense definition (SURVEY 8d): bytes the reference's layout moves per grid voxel; "
+                                 "the kernel is FP32-bound on simplex noise, see DESIGN.md"},
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+            "whole_path_roofline_frac": (5.0 * total_voxels / step_s / 1e9) / peak,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = {k: v for k, v in cpu_reference(graph, types, 12.0, os.cpu_count() or 1).items()
+                                   if k != "seconds"}
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="asteroid1024")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,12 @@ struct ivx_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     std::vector<PoolBlock> pool;
+    // optional per-kernel timing
+    bool profiling = false;
+    struct ProfEvent { cudaEvent_t a, b; uint32_t id; };
+    std::vector<ProfEvent> prof_events;
+    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t* h_pinned = nullptr;  // 64 words of pinned scratch for counter read-back
     uint32_t* d_scratch = nullptr; // 64 words of device counters
 
@@ -134,6 +140,24 @@ namespace {
     do {                   \
         (ctx)->launches++; \
         CU(ctx, expr);     \
+    } while (0)
+
+// kernel launch with optional event timing under kernel id `kid`
+#define KLP(ctx, kid, expr)                                              \
+    do {                                                                 \
+        (ctx)->launches++;                                               \
+        ivx_ctx::ProfEvent _pe{nullptr, nullptr, (uint32_t)(kid)};       \
+        if ((ctx)->profiling) {                                          \
+            cudaEventCreate(&_pe.a);                                     \
+            cudaEventCreate(&_pe.b);                                     \
+            cudaEventRecord(_pe.a, (ctx)->stream);                       \
+        }                                                                \
+        cudaError_t _le = (expr);                                        \
+        if ((ctx)->profiling) {                                          \
+            cudaEventRecord(_pe.b, (ctx)->stream);                       \
+            (ctx)->prof_events.push_back(_pe);                           \
+        }                                                                \
+        CU(ctx, _le);                                                    \
     } while (0)
 
 struct Tmp {
@@ -351,7 +375,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     fa.max_depth = counters + 1;
     fa.occ = nullptr;
     fa.error_flag = counters;
-    KL(ctx, launch_fold(false, fa, st));
+    KLP(ctx, 0, launch_fold(false, fa, st));
 
     // ---- level 1: exact fold per chunk ----
     KL(ctx, launch_child_caps(sb_len, n, obj->nb, snb, SUPER, caps, st));
@@ -378,7 +402,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     fb.out_len = ch_len;
     fb.chunks = obj->d_chunks;
     fb.occ = counters + 2;
-    KL(ctx, launch_fold(true, fb, st));
+    KLP(ctx, 1, launch_fold(true, fb, st));
 
     // ---- slot planning ----
     uint32_t* active_flag = tmp.get<uint32_t>(n);
@@ -420,13 +444,13 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     ea.raw_out = nullptr;
     uint32_t egrid = 1;
     if (int rc = plan_eval_stack(ctx, max_depth, tmp, n_active, ea, egrid)) return rc;
-    if (n_active) KL(ctx, launch_eval(ea, egrid, st));
+    if (n_active) KLP(ctx, 2, launch_eval(ea, egrid, st));
 
     // ---- cross-chunk derived state ----
     uint32_t* convert_flag = tmp.get<uint32_t>(n);
     if (!convert_flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "derive: out of device memory");
-    KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, st));
-    KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr, n,
+    KLP(ctx, 3, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, st));
+    KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr, n,
                                   persistent_grid(ctx, n, 8), st));
 
     if (int rc = read_words(ctx, counters, 16, words)) return rc;
@@ -579,7 +603,7 @@ int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMe
     ma.index_count = icount;
     ma.has_submesh = hsub;
     const uint32_t grid = persistent_grid(ctx, n_work, 4);
-    KL(ctx, launch_mesh(false, ma, grid, st));
+    KLP(ctx, 4, launch_mesh(false, ma, grid, st));
     KL(ctx, launch_exclusive_scan(vcount, voff, n_work, counters + 17, st));
     KL(ctx, launch_exclusive_scan(icount, ioff, n_work, counters + 18, st));
     KL(ctx, launch_exclusive_scan(hsub, sord, n_work, counters + 19, st));
@@ -604,7 +628,7 @@ int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMe
     ma.index_materials = m.index_materials;
     ma.submeshes = m.submeshes;
     ma.vertex_ranges = m.vertex_ranges;
-    KL(ctx, launch_mesh(true, ma, grid, st));
+    KLP(ctx, 5, launch_mesh(true, ma, grid, st));
     CU(ctx, cudaStreamSynchronize(st));
     return IVX_OK;
 }
@@ -682,6 +706,10 @@ void ivx_destroy(ivx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& e : ctx->prof_events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
     for (auto& b : ctx->pool) cudaFree(b.ptr);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -695,6 +723,45 @@ uint64_t ivx_kernel_launch_count(const ivx_ctx* ctx) { return ctx ? ctx->launche
 int ivx_synchronize(ivx_ctx* ctx) {
     if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IVX_OK;
+}
+
+static void drain_profile(ivx_ctx* ctx) {
+    for (auto& e : ctx->prof_events) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.id < 8) {
+            ctx->prof_ms[e.id] += ms;
+            ctx->prof_launches[e.id] += 1;
+        }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    ctx->prof_events.clear();
+}
+
+int ivx_profile_enable(ivx_ctx* ctx, int enabled) {
+    if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_profile(ctx);
+    ctx->profiling = enabled != 0;
+    return IVX_OK;
+}
+int ivx_profile_reset(ivx_ctx* ctx) {
+    if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_profile(ctx);
+    for (int i = 0; i < 8; ++i) {
+        ctx->prof_ms[i] = 0;
+        ctx->prof_launches[i] = 0;
+    }
+    return IVX_OK;
+}
+int ivx_profile_get(ivx_ctx* ctx, uint32_t kernel_id, double* out_total_ms, uint64_t* out_launches) {
+    if (!ctx || kernel_id >= 8) return IVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_profile(ctx);
+    if (out_total_ms) *out_total_ms = ctx->prof_ms[kernel_id];
+    if (out_launches) *out_launches = ctx->prof_launches[kernel_id];
     return IVX_OK;
 }
 
@@ -1003,7 +1070,7 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3
     aa.new_slot_ord = ord;
     aa.dirty = obj->d_dirty;
     aa.stats = counters + 1;
-    KL(ctx, launch_absorb_apply(aa, persistent_grid(ctx, n_range, 4), st));
+    KLP(ctx, 6, launch_absorb_apply(aa, persistent_grid(ctx, n_range, 4), st));
     obj->slots_used += w[0];
 
     // boundary refresh over chunk range [start-1, end) (intersection.rs:391-393)

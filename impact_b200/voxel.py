@@ -51,6 +51,24 @@ class Context:
     def synchronize(self):
         self.check(self._lib.ivx_synchronize(self.h))
 
+    KERNEL_IDS = {"fold_conservative": 0, "fold_exact": 1, "eval": 2, "boundary": 3, "mesh_count": 4,
+                  "mesh_emit": 5, "absorb": 6, "bookkeeping": 7}
+
+    def profile_enable(self, enabled: bool = True):
+        self.check(self._lib.ivx_profile_enable(self.h, C.c_int(1 if enabled else 0)))
+
+    def profile_reset(self):
+        self.check(self._lib.ivx_profile_reset(self.h))
+
+    def profile_get(self) -> dict:
+        """→ {kernel name: (total device ms, launches)} measured with CUDA events on the ctx stream."""
+        out = {}
+        for name, kid in self.KERNEL_IDS.items():
+            ms, n = C.c_double(), C.c_uint64()
+            self.check(self._lib.ivx_profile_get(self.h, C.c_uint32(kid), C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     def build_generator(self, graph: SDFGraph) -> "SDFGenerator":
         """`SDFGraph::build_in` → `SDFGenerator::new_in` (atomic.rs:1031-1037, 228-493)."""
         return SDFGenerator.from_graph(self, graph.nodes(), graph.root_node_id)

@@ -199,6 +199,14 @@ uint32_t ivx_abi_version(void);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t ivx_kernel_launch_count(const ivx_ctx* ctx);
 int ivx_synchronize(ivx_ctx* ctx);
+/* Per-kernel device timing with CUDA events on the ctx stream (for bench.py's
+ * roofline object). kernel ids: 0 fold (conservative), 1 fold (exact), 2 eval,
+ * 3 boundary (classify+apply), 4 mesh count, 5 mesh emit, 6 absorb, 7 bookkeeping.
+ * ivx_profile_get synchronises, then returns the accumulated milliseconds and
+ * launch count of that kernel since the last reset. */
+int ivx_profile_enable(ivx_ctx* ctx, int enabled);
+int ivx_profile_reset(ivx_ctx* ctx);
+int ivx_profile_get(ivx_ctx* ctx, uint32_t kernel_id, double* out_total_ms, uint64_t* out_launches);
 
 /* ---- graph compile ------------------------------------------------------
  * ivx_program_build  replaces SDFGraph::build_in → SDFGenerator::new_in

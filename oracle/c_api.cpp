@@ -107,6 +107,21 @@ void* orc_object_generate(const void* vgp, int n_threads, double* t_gen, double*
     return obj;
 }
 
+// Bounded sample for the CPU baseline: generate + derive + mesh chunk planes [begin, end) as a slab.
+void* orc_object_generate_slab(const void* vgp, int n_threads, uint32_t plane_begin, uint32_t plane_end,
+                               double* t_gen, double* t_derive) {
+    Object* obj = new Object();
+    auto t0 = std::chrono::steady_clock::now();
+    generate_slab_without_derived_state(*(const VoxelGenerator*)vgp, *obj, n_threads, plane_begin, plane_end);
+    auto t1 = std::chrono::steady_clock::now();
+    update_occupied_voxel_ranges(*obj);
+    compute_all_derived_state(*obj);
+    auto t2 = std::chrono::steady_clock::now();
+    if (t_gen) *t_gen = std::chrono::duration<double>(t1 - t0).count();
+    if (t_derive) *t_derive = std::chrono::duration<double>(t2 - t1).count();
+    return obj;
+}
+
 // Test fixture equivalent to the reference's ManualVoxelGenerator
 // (object.rs:3387-3561): dense per-voxel sd codes + types over `shape`.
 void* orc_object_from_dense(const int8_t* sd, const uint8_t* types, const uint32_t shape[3],

@@ -214,6 +214,10 @@ struct Object {
 void generate_object(const VoxelGenerator& vg, Object& obj, int n_threads,
                      double* t_generate_s = nullptr, double* t_derive_s = nullptr);
 void generate_without_derived_state(const VoxelGenerator& vg, Object& obj, int n_threads);
+// Same, restricted to chunk planes [plane_begin, plane_end) of the x-major chunk grid (a bounded
+// sample of a large object for bench.py's cpu_baseline; the slab is treated as its own object).
+void generate_slab_without_derived_state(const VoxelGenerator& vg, Object& obj, int n_threads,
+                                         uint32_t plane_begin, uint32_t plane_end);
 void update_occupied_voxel_ranges(Object& obj);
 void update_occupied_chunk_ranges(Object& obj);
 void compute_all_derived_state(Object& obj);

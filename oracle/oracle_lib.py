@@ -51,6 +51,7 @@ def lib():
         _lib.orc_voxel_generator_create.restype = C.c_void_p
         _lib.orc_object_generate.restype = C.c_void_p
         _lib.orc_object_from_dense.restype = C.c_void_p
+        _lib.orc_object_generate_slab.restype = C.c_void_p
         _lib.orc_object_dirty.restype = C.c_uint32
         _lib.orc_mesh_create.restype = C.c_void_p
         _lib.orc_fill_brick.restype = C.c_int
@@ -157,6 +158,15 @@ class Object:
     def generate(cls, vg: VoxelGenerator, n_threads: int = 1) -> "Object":
         tg, td = C.c_double(), C.c_double()
         o = cls(lib().orc_object_generate(vg.h, C.c_int(n_threads), C.byref(tg), C.byref(td)))
+        o.t_generate, o.t_derive = tg.value, td.value
+        return o
+
+    @classmethod
+    def generate_slab(cls, vg: VoxelGenerator, plane_begin: int, plane_end: int, n_threads: int = 1) -> "Object":
+        """Chunk planes [begin, end) of the object as a stand-alone slab (bench.py's bounded CPU sample)."""
+        tg, td = C.c_double(), C.c_double()
+        o = cls(lib().orc_object_generate_slab(vg.h, C.c_int(n_threads), C.c_uint32(plane_begin), C.c_uint32(plane_end),
+                                               C.byref(tg), C.byref(td)))
         o.t_generate, o.t_derive = tg.value, td.value
         return o
 

@@ -181,9 +181,17 @@ static inline bool chunk_only_empty(const Chunk& c) {
 
 // ---- generate_voxels_for_chunks[_in_parallel] + analyze (object.rs:361-617) --
 void generate_without_derived_state(const VoxelGenerator& vg, Object& obj, int n_threads) {
+    generate_slab_without_derived_state(vg, obj, n_threads, 0, (vg.grid_shape[0] + 15) / 16);
+}
+
+void generate_slab_without_derived_state(const VoxelGenerator& vg, Object& obj, int n_threads,
+                                         uint32_t plane_begin, uint32_t plane_end) {
     obj = Object{};
     obj.voxel_extent = vg.voxel_extent;
     for (int d = 0; d < 3; ++d) obj.chunk_counts[d] = (vg.grid_shape[d] + 15) / 16;
+    if (plane_end > obj.chunk_counts[0]) plane_end = obj.chunk_counts[0];
+    if (plane_begin > plane_end) plane_begin = plane_end;
+    obj.chunk_counts[0] = plane_end - plane_begin;
     const uint32_t total = obj.chunk_counts[0] * obj.chunk_counts[1] * obj.chunk_counts[2];
     obj.chunks.assign(total, Chunk{});
     if (total == 0) return;
@@ -206,7 +214,7 @@ void generate_without_derived_state(const VoxelGenerator& vg, Object& obj, int n
             uint32_t i = ci / (obj.chunk_counts[2] * obj.chunk_counts[1]);
             uint32_t j = (ci / obj.chunk_counts[2]) % obj.chunk_counts[1];
             uint32_t k = ci % obj.chunk_counts[2];
-            uint32_t origin[3] = {i * 16, j * 16, k * 16};
+            uint32_t origin[3] = {(i + plane_begin) * 16, j * 16, k * 16};
             Sparseness sp = generate_chunk(vg, origin, buf, scratch.data(), tscratch.data());
             Chunk c = classify_generated_chunk(buf, sp);
             obj.chunks[ci] = c;
