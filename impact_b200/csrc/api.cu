@@ -375,6 +375,8 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     fa.max_depth = counters + 1;
     fa.occ = nullptr;
     fa.error_flag = counters;
+    fa.prune = 1;
+    fa.saturate = 1;
     KLP(ctx, 0, launch_fold(false, fa, st));
 
     // ---- level 1: exact fold per chunk ----
@@ -873,6 +875,8 @@ int ivx_program_eval_chunks(ivx_ctx* ctx, const ivx_program* prog, const float* 
     fa.max_depth = counters + 1;
     fa.occ = nullptr;
     fa.error_flag = counters;
+    fa.prune = 1;     // value-preserving, so the raw distances stay bit-exact
+    fa.saturate = 0;  // raw f32 distances are wanted here, not quantised codes
     KL(ctx, launch_fold(true, fa, st));
     uint32_t words[2];
     if (int rc = read_words(ctx, counters, 2, words)) return rc;

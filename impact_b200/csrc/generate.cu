@@ -132,10 +132,46 @@ struct FoldWarpSmem {
     uint8_t cls[FOLD_TILE];
     uint32_t seg_start[FOLD_MAX_DEPTH];
     float cval[FOLD_MAX_DEPTH];
+    float ilo[FOLD_MAX_DEPTH];  // rigorous value range of the slot over the whole block
+    float ihi[FOLD_MAX_DEPTH];
     uint8_t is_const[FOLD_MAX_DEPTH];
     float val[FOLD_MAX_DEPTH][32];  // EXACT only: sampled values per stack slot
 };
 
+// |simplex3| <= 1 over all gradient assignments (the 32.694… normalisation of
+// simdnoise; checked by dense sampling in tests/test_noise_bound.py), so
+// |fbm * noise_scale| <= amplitude. 0.5 % + 1e-3 absorbs f32 rounding.
+__device__ __forceinline__ float noise_bound(const ivx_node& n) { return 1.005f * fabsf(n.p[3]) + 1e-3f; }
+
+__device__ __forceinline__ float slack(float a, float b) { return 1e-3f + 2e-5f * (fabsf(a) + fabsf(b)); }
+
+// moves `len` instructions from out[src..] down to out[dst..] (dst < src), warp-cooperatively
+__device__ __forceinline__ void shift_down(Instr* out, uint32_t dst, uint32_t src, uint32_t len, int lane) {
+    for (uint32_t off = 0; off < len; off += 32) {
+        Instr v{};
+        const bool in = off + lane < len;
+        if (in) v = out[src + off + lane];
+        __syncwarp();
+        if (in) out[dst + off + lane] = v;
+        __syncwarp();
+    }
+}
+
+// Program specialisation for one block (a super-block of chunks, or one chunk).
+//
+// EXACT = true (block = one 16³ chunk): makes exactly the decisions
+// compute_signed_distances_for_block makes for this chunk — leaf fill / evaluate
+// from the chunk AABB (atomic.rs:654-668), noise / combine apply-or-skip from
+// the AABB and the 14 sampled voxels (atomic.rs:765-869) — by evaluating the
+// whole surviving program on those 14 voxels (one per lane).
+// EXACT = false (super-block): only folds what holds for EVERY chunk inside.
+//
+// On top of the reference's decisions both modes carry a rigorous value range
+// per operand (leaf SDFs are 1-Lipschitz, |noise| <= amplitude) and drop an
+// operand of a smooth combine when the other one provably decides the result
+// on every voxel of the block (|a - b| >= k ⇒ h = 0 ⇒ min/max returns one operand
+// bit-exactly). This never changes a voxel, only skips arithmetic the reference
+// spends on operands that cannot matter.
 template <bool EXACT>
 __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,7 +203,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
     }
     const Instr* __restrict__ pin = a.parent_instrs + a.parent_off[parent];
     const uint32_t plen = a.parent_len[parent];
-    Instr* __restrict__ out = a.out_instrs + a.out_off[block];
+    Instr* out = a.out_instrs + a.out_off[block];
 
     // chunks entirely beyond the grid are void without looking at the program
     // (generation.rs:299-312)
@@ -193,15 +229,17 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
         sj = c_sample_ijk[sl][1];
         sk = c_sample_ijk[sl][2];
     }
+    const bool prune = a.prune != 0;
 
     uint32_t olen = 0;
     int sp = 0;
-    int max_sp = 0;
     bool overflow = false;
 
     for (uint32_t base = 0; base < plen; base += FOLD_TILE) {
         const uint32_t tile_n = min((uint32_t)FOLD_TILE, plen - base);
         // ---- phase 1: AABB classification, one instruction per lane ----
+        // bit 0-1: 1 = block outside domain_with_margin, 2 = inside the leaf's interior box
+        // bit 2 (conservative leaf): some chunk may still be filled +margin; bit 3: ... -margin
         for (uint32_t t = lane; t < tile_n; t += 32) {
             Instr in = pin[base + t];
             uint32_t op = in.op_node >> 28;
@@ -229,7 +267,19 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                         f3 h = leaf_interior_half_extents(n);
                         bool inside = (blo.x - eps >= -h.x) && (blo.y - eps >= -h.y) && (blo.z - eps >= -h.z) &&
                                       (bhi.x + eps <= h.x) && (bhi.y + eps <= h.y) && (bhi.z + eps <= h.z);
-                        if (inside) cls = 2;
+                        if (inside) {
+                            cls = 2;
+                        } else {
+                            // which fills remain possible for some chunk of the block
+                            bool within_domain = (blo.x - eps >= n.domain_lo[0]) && (blo.y - eps >= n.domain_lo[1]) &&
+                                                 (blo.z - eps >= n.domain_lo[2]) && (bhi.x + eps <= n.domain_hi[0]) &&
+                                                 (bhi.y + eps <= n.domain_hi[1]) && (bhi.z + eps <= n.domain_hi[2]);
+                            bool misses_interior = (bhi.x + eps < -h.x) || (bhi.y + eps < -h.y) || (bhi.z + eps < -h.z) ||
+                                                   (h.x + eps < blo.x) || (h.y + eps < blo.y) || (h.z + eps < blo.z) ||
+                                                   h.x < 0.0f || h.y < 0.0f || h.z < 0.0f;
+                            if (!within_domain) cls |= 4;
+                            if (!misses_interior) cls |= 8;
+                        }
                     }
                 }
             }
@@ -244,34 +294,51 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
             const uint32_t op = in.op_node >> 28;
             const uint32_t ni = in.op_node & 0x0FFFFFFFu;
             const uint8_t cls = S.cls[t];
-            if (op == OP_CONST || (op == OP_LEAF && cls != 0)) {
+            if (op == OP_CONST || (op == OP_LEAF && (cls & 3) != 0)) {
                 float c = in.value;
                 if (op == OP_LEAF) {
                     float m = a.nodes[ni].margin;
-                    c = cls == 1 ? m : -m;
+                    c = (cls & 3) == 1 ? m : -m;
                 }
                 if (sp >= FOLD_MAX_DEPTH) { overflow = true; break; }
                 if (lane == 0) {
                     S.seg_start[sp] = olen;
                     S.cval[sp] = c;
+                    S.ilo[sp] = c;
+                    S.ihi[sp] = c;
                     S.is_const[sp] = 1;
                     out[olen] = Instr{(uint32_t)OP_CONST << 28, c};
                 }
                 if (EXACT) S.val[sp][lane] = c;
                 olen += 1;
                 sp += 1;
-                max_sp = max(max_sp, sp);
             } else if (op == OP_LEAF) {
                 if (sp >= FOLD_MAX_DEPTH) { overflow = true; break; }
+                const ivx_node& n = a.nodes[ni];
+                const float* M = n.transform_to_node_space;
+                // value range over the block: the primitive SDFs are 1-Lipschitz in node space
+                f3 blo, bhi;
+                aabb_of_transformed(M, lo, hi, blo, bhi);
+                const f3 ctr = 0.5f * (blo + bhi);
+                const float rad = norm3(0.5f * (bhi - blo));
+                const float vc = sd_leaf(n.kind, n.p, ctr);
+                const float e = 1e-3f + 1e-4f * (fabsf(vc) + rad);
+                float rlo = vc - rad - e, rhi = vc + rad + e;
+                if (!EXACT) {
+                    if (cls & 4) rhi = fmaxf(rhi, n.margin);
+                    if (cls & 8) rlo = fminf(rlo, -n.margin);
+                    if (cls & 4) rlo = fminf(rlo, n.margin);
+                    if (cls & 8) rhi = fmaxf(rhi, -n.margin);
+                }
                 if (lane == 0) {
                     S.seg_start[sp] = olen;
                     S.is_const[sp] = 0;
+                    S.ilo[sp] = rlo;
+                    S.ihi[sp] = rhi;
                     out[olen] = in;
                 }
                 if (EXACT) {
                     // update_signed_distances_for_block (atomic.rs:1601-1627) at the sampled voxel
-                    const ivx_node& n = a.nodes[ni];
-                    const float* M = n.transform_to_node_space;
                     f3 origin = transform_point(M, lo);
                     f3 dx = mk3(M[0], M[1], M[2]), dy = mk3(M[4], M[5], M[6]), dz = mk3(M[8], M[9], M[10]);
                     f3 pos = (origin + (float)si * dx) + (float)sj * dy;
@@ -280,23 +347,29 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                 }
                 olen += 1;
                 sp += 1;
-                max_sp = max(max_sp, sp);
-            } else if (op == OP_SCALE) {
-                const float s = a.nodes[ni].p[0];
-                __syncwarp();
+            } else if (op == OP_SCALE || op == OP_NEG) {
+                const float s = op == OP_NEG ? -1.0f : a.nodes[ni].p[0];
                 const bool tc = S.is_const[sp - 1] != 0;
-                if (tc) {
-                    float c = S.cval[sp - 1] * s;
-                    __syncwarp();
-                    if (lane == 0) {
+                const float c0 = S.cval[sp - 1], l0 = S.ilo[sp - 1], h0 = S.ihi[sp - 1];
+                const uint32_t seg = S.seg_start[sp - 1];
+                __syncwarp();
+                if (lane == 0) {
+                    if (tc) {
+                        const float c = op == OP_NEG ? -c0 : c0 * s;
                         S.cval[sp - 1] = c;
-                        out[S.seg_start[sp - 1]] = Instr{(uint32_t)OP_CONST << 28, c};
+                        S.ilo[sp - 1] = c;
+                        S.ihi[sp - 1] = c;
+                        out[seg] = Instr{(uint32_t)OP_CONST << 28, c};
+                    } else {
+                        const float x = l0 * s, y = h0 * s;
+                        const float e = slack(x, y);
+                        S.ilo[sp - 1] = fminf(x, y) - e;
+                        S.ihi[sp - 1] = fmaxf(x, y) + e;
+                        out[olen] = in;
                     }
-                } else {
-                    if (lane == 0) out[olen] = in;
-                    olen += 1;
                 }
-                if (EXACT) S.val[sp - 1][lane] = S.val[sp - 1][lane] * s;
+                if (!tc) olen += 1;
+                if (EXACT) S.val[sp - 1][lane] = op == OP_NEG ? -S.val[sp - 1][lane] : S.val[sp - 1][lane] * s;
             } else if (op == OP_NOISE) {
                 const ivx_node& n = a.nodes[ni];
                 bool apply = true;
@@ -317,20 +390,26 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                     }
                 }
                 if (apply) {
+                    const float l0 = S.ilo[sp - 1], h0 = S.ihi[sp - 1];
                     __syncwarp();
                     if (lane == 0) {
+                        const float A = noise_bound(n);
                         S.is_const[sp - 1] = 0;
+                        S.ilo[sp - 1] = l0 - A - slack(l0, A);
+                        S.ihi[sp - 1] = h0 + A + slack(h0, A);
                         out[olen] = in;
                     }
                     olen += 1;
                 }
             } else {  // OP_COMBINE
                 const ivx_node& n = a.nodes[ni];
-                __syncwarp();
                 const int ia = sp - 2, ib = sp - 1;
-                const bool both_const = S.is_const[ia] && S.is_const[ib];
+                const bool ac = S.is_const[ia] != 0, bcst = S.is_const[ib] != 0;
+                const bool both_const = ac && bcst;
                 const float ca = S.cval[ia], cb = S.cval[ib];
+                const float alo = S.ilo[ia], ahi = S.ihi[ia], blo2 = S.ilo[ib], bhi2 = S.ihi[ib];
                 const uint32_t seg_a = S.seg_start[ia], seg_b = S.seg_start[ib];
+                const float k = n.p[0];
                 int decision;  // 0 apply, 1 skip (keep child 1), 2 undecided (conservative only)
                 if (EXACT) {
                     float r = op_combine(n.kind, S.val[ia][lane], S.val[ib][lane], n.p[0], n.p[1]);
@@ -346,18 +425,81 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                         decision = 2;
                     }
                 }
+                // which operand provably decides the result on every voxel (if the op is applied)
+                // 1: result == a, 2: result == b, 3: result == -b
+                int keep = 0;
+                if (prune && decision != 1 && !both_const) {
+                    const float ek = k + slack(fmaxf(fabsf(alo), fabsf(ahi)), fmaxf(fabsf(blo2), fabsf(bhi2)));
+                    if (n.kind == IVX_UNION) {
+                        if (blo2 - ahi >= ek) keep = 1;
+                        else if (alo - bhi2 >= ek) keep = 2;
+                    } else if (n.kind == IVX_SUBTRACTION) {
+                        if (alo + blo2 >= ek) keep = 1;
+                        else if (ahi + bhi2 <= -ek) keep = 3;
+                    } else {
+                        if (alo - bhi2 >= ek) keep = 1;
+                        else if (blo2 - ahi >= ek) keep = 2;
+                    }
+                    if (keep >= 2 && decision != 0) keep = 0;  // "== b" only holds when the op is applied
+                }
                 __syncwarp();
-                if (decision == 1) {
-                    olen = seg_b;  // drop child 2's instructions
+                if (decision == 1 || keep == 1) {
+                    olen = seg_b;  // drop child 2's instructions; slot a is unchanged
+                } else if (keep >= 2) {
+                    const uint32_t len_b = olen - seg_b;
+                    shift_down(out, seg_a, seg_b, len_b, lane);
+                    olen = seg_a + len_b;
+                    if (lane == 0) {
+                        if (keep == 3) {
+                            if (bcst) {
+                                out[seg_a] = Instr{(uint32_t)OP_CONST << 28, -cb};
+                                S.cval[ia] = -cb;
+                                S.ilo[ia] = -cb;
+                                S.ihi[ia] = -cb;
+                            } else {
+                                out[olen] = Instr{(uint32_t)OP_NEG << 28, 0.0f};
+                                S.ilo[ia] = -bhi2;
+                                S.ihi[ia] = -blo2;
+                            }
+                        } else {
+                            S.cval[ia] = cb;
+                            S.ilo[ia] = blo2;
+                            S.ihi[ia] = bhi2;
+                        }
+                        S.is_const[ia] = bcst ? 1 : 0;
+                    }
+                    if (keep == 3 && !bcst) olen += 1;
                 } else if (decision == 0 && both_const) {
                     float c = op_combine(n.kind, ca, cb, n.p[0], n.p[1]);
                     if (lane == 0) {
                         S.cval[ia] = c;
+                        S.ilo[ia] = c;
+                        S.ihi[ia] = c;
                         out[seg_a] = Instr{(uint32_t)OP_CONST << 28, c};
                     }
                     olen = seg_a + 1;
                 } else {
                     if (lane == 0) {
+                        // value range of the applied smooth op: min/max of the operands, moved by at most k/4
+                        float rl, rh;
+                        const float q = 0.25f * k;
+                        if (n.kind == IVX_UNION) {
+                            rl = fminf(alo, blo2) - q;
+                            rh = fminf(ahi, bhi2);
+                        } else if (n.kind == IVX_SUBTRACTION) {
+                            rl = fmaxf(alo, -bhi2);
+                            rh = fmaxf(ahi, -blo2) + q;
+                        } else {
+                            rl = fmaxf(alo, blo2);
+                            rh = fmaxf(ahi, bhi2) + q;
+                        }
+                        if (decision == 2) {  // may also be skipped in some chunks: result == a there
+                            rl = fminf(rl, alo);
+                            rh = fmaxf(rh, ahi);
+                        }
+                        const float e = slack(rl, rh);
+                        S.ilo[ia] = rl - e;
+                        S.ihi[ia] = rh + e;
                         S.is_const[ia] = 0;
                         out[olen] = in;
                     }
@@ -368,6 +510,27 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
         }
         __syncwarp();
         if (overflow) break;
+    }
+    __syncwarp();
+
+    // ---- root saturation: the whole block quantises to one code (lib.rs:195-201, 240-243) ----
+    // every code > 100 ⇒ the chunks are void; every code == -128 ⇒ maximally inside everywhere
+    if (!overflow && a.saturate && sp == 1 && !S.is_const[0]) {
+        const float rl = S.ilo[0], rh = S.ihi[0];
+        float c = 0.0f;
+        bool sat = false;
+        if (rl >= 2.03f) { c = 1000.0f; sat = true; }
+        else if (rh <= -2.5601f) { c = -1000.0f; sat = true; }
+        if (sat) {
+            __syncwarp();
+            if (lane == 0) {
+                out[0] = Instr{(uint32_t)OP_CONST << 28, c};
+                S.is_const[0] = 1;
+                S.cval[0] = c;
+            }
+            olen = 1;
+            __syncwarp();
+        }
     }
 
     if (lane == 0) {
@@ -498,6 +661,9 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                 const float s = n.p[0];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) top[k] = top[k] * s;
+            } else if (op == OP_NEG) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) top[k] = -top[k];
             } else if (op == OP_NOISE) {
                 NoiseFrame f = make_noise_frame(n, lo);
                 const float ns = n.p[4];

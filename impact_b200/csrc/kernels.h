@@ -30,6 +30,8 @@ struct FoldArgs {
     uint32_t* max_depth;      // exact level only
     uint32_t* occ;            // exact level only: min xyz, max xyz of non-empty voxels
     uint32_t* error_flag;
+    uint32_t prune;           // 1: drop operands that provably cannot influence any voxel of the block
+    uint32_t saturate;        // 1: replace a program whose value range quantises to one code by a constant
 };
 cudaError_t launch_fold(bool exact, const FoldArgs& a, cudaStream_t st);
 

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import helpers as H
+from impact_b200 import workloads as W
 import invariants as INV
 from impact_b200.voxel import SDFVoxelGenerator, VoxelObject, VoxelObjectMesh
 
@@ -32,6 +33,9 @@ GRAPHS = {
     "noisy_box": (lambda: H.noisy_box_graph(38.0, 8), H.SAME0),           # BASELINE config 2, reduced
     "zoo": (H.csg_zoo_graph, H.GRADIENT4),
     "asteroid_like": (lambda: H.asteroid_like_graph(24, 40.0), H.GRADIENT4),  # BASELINE config 3 stand-in
+    # same node kinds / counts as asteroid.vgen.ron (446 leaves, depth 9) at a grid the oracle finishes in seconds
+    "asteroid_stand_in": (lambda: W.asteroid_stand_in(0.6), H.GRADIENT4),
+    "asteroid_stand_in_same": (lambda: W.asteroid_stand_in(0.45, seed=2), H.SAME0),
 }
 
 
