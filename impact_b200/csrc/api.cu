@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -257,7 +258,9 @@ uint32_t persistent_grid(ivx_ctx* ctx, uint32_t n_work, int blocks_per_sm) {
 // memory (16 KiB each), deeper levels in a global spill buffer.
 int plan_eval_stack(ivx_ctx* ctx, uint32_t max_depth, Tmp& tmp, uint32_t n_active, EvalArgs& ea, uint32_t& grid) {
     const int need = max_depth > 0 ? (int)max_depth - 1 : 0;
-    const int smem_levels = std::min(need, 12);
+    // most specialised programs need one or two operand levels; keeping the shared-memory share small
+    // lets several CTAs share an SM, the rare deeper levels go to an L2-resident spill buffer
+    const int smem_levels = std::min(need, 2);
     ea.smem_levels = smem_levels;
     ea.spill_levels = need - smem_levels;
     int bps = eval_max_blocks_per_sm(smem_levels);
@@ -335,76 +338,87 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
         CU(ctx, cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
 
-    // ---- level 0: conservative fold per super-block ----
-    uint32_t snb[3];
-    for (int d = 0; d < 3; ++d) snb[d] = (obj->nb[d] + SUPER - 1) / SUPER;
-    const uint32_t n_super = snb[0] * snb[1] * snb[2];
-    const uint32_t L0 = prog->root_len;
-    Instr* sb_instrs = tmp.get<Instr>((size_t)n_super * std::max(1u, L0));
-    uint32_t* sb_off = tmp.get<uint32_t>(n_super);
-    uint32_t* sb_len = tmp.get<uint32_t>(n_super);
-    uint32_t* caps = tmp.get<uint32_t>(n);
-    uint32_t* ch_off = tmp.get<uint32_t>(n);
-    uint32_t* ch_len = tmp.get<uint32_t>(n);
-    if (!sb_instrs || !sb_off || !sb_len || !caps || !ch_off || !ch_len)
-        IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "fold buffers: out of device memory");
+    // ---- program specialisation, coarse to fine ----
+    // Conservative folds over nested super-blocks (8³, 4³, 2³ chunks) shorten the program every chunk
+    // below them has to look at; the exact fold per chunk then makes the reference's own decisions.
+    uint32_t words[16];
+    std::vector<uint32_t> sizes;
     {
-        std::vector<uint32_t> h(n_super);
-        for (uint32_t b = 0; b < n_super; ++b) h[b] = b * L0;
-        CU(ctx, cudaMemcpyAsync(sb_off, h.data(), n_super * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CU(ctx, cudaStreamSynchronize(st));
+        const uint32_t mx = std::max(obj->nb[0], std::max(obj->nb[1], obj->nb[2]));
+        for (uint32_t sz = 8; sz >= 2; sz >>= 1)
+            if (mx >= 2 * sz) sizes.push_back(sz);
     }
     FoldArgs fa{};
     fa.nodes = prog->d_nodes;
     fa.gp = gp;
-    fa.n_blocks = n_super;
-    for (int d = 0; d < 3; ++d) fa.nb[d] = snb[d];
-    fa.block_chunks = SUPER;
     fa.first_chunk[0] = obj->first_i;
     fa.first_chunk[1] = fa.first_chunk[2] = 0;
     fa.explicit_origins = nullptr;
-    fa.ratio = 1;
-    fa.parent_nb[0] = fa.parent_nb[1] = fa.parent_nb[2] = 0;
-    fa.parent_instrs = prog->d_root;
-    fa.parent_off = prog->d_root_meta;
-    fa.parent_len = prog->d_root_meta + 1;
-    fa.out_instrs = sb_instrs;
-    fa.out_off = sb_off;
-    fa.out_len = sb_len;
     fa.chunks = nullptr;
     fa.max_depth = counters + 1;
     fa.occ = nullptr;
     fa.error_flag = counters;
     fa.prune = 1;
     fa.saturate = 1;
-    KLP(ctx, 0, launch_fold(false, fa, st));
-
-    // ---- level 1: exact fold per chunk ----
-    KL(ctx, launch_child_caps(sb_len, n, obj->nb, snb, SUPER, caps, st));
-    KL(ctx, launch_exclusive_scan(caps, ch_off, n, counters + 8, st));
-    uint32_t words[16];
-    if (int rc = read_words(ctx, counters, 16, words)) return rc;
-    if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
-    const uint32_t total_caps = words[8];
-    Instr* ch_instrs = tmp.get<Instr>(std::max<size_t>(1, total_caps));
-    if (!ch_instrs) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "chunk program arena: out of device memory");
-    FoldArgs fb = fa;
-    fb.n_blocks = n;
-    for (int d = 0; d < 3; ++d) {
-        fb.nb[d] = obj->nb[d];
-        fb.parent_nb[d] = snb[d];
+    // the "parent" of the coarsest level is the whole program
+    const Instr* par_instrs = prog->d_root;
+    const uint32_t* par_off = prog->d_root_meta;
+    const uint32_t* par_len = prog->d_root_meta + 1;
+    uint32_t par_nb[3] = {0, 0, 0};
+    uint32_t par_size = 0;
+    sizes.push_back(1);  // the exact level
+    Instr* ch_instrs = nullptr;
+    uint32_t* ch_off = nullptr;
+    uint32_t* ch_len = nullptr;
+    for (size_t li = 0; li < sizes.size(); ++li) {
+        const uint32_t sz = sizes[li];
+        const bool exact = sz == 1;
+        uint32_t lnb[3];
+        for (int d = 0; d < 3; ++d) lnb[d] = (obj->nb[d] + sz - 1) / sz;
+        const uint32_t nblk = lnb[0] * lnb[1] * lnb[2];
+        uint32_t* caps = tmp.get<uint32_t>(nblk);
+        uint32_t* off = tmp.get<uint32_t>(nblk);
+        uint32_t* len = tmp.get<uint32_t>(nblk);
+        if (!caps || !off || !len) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "fold buffers: out of device memory");
+        if (par_size == 0) {
+            KL(ctx, launch_fill_u32(caps, nblk, prog->root_len, st));
+        } else {
+            KL(ctx, launch_child_caps(par_len, nblk, lnb, par_nb, par_size / sz, caps, st));
+        }
+        KL(ctx, launch_exclusive_scan(caps, off, nblk, counters + 8, st));
+        if (int rc = read_words(ctx, counters, 16, words)) return rc;
+        if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
+        Instr* instrs = tmp.get<Instr>(std::max<size_t>(1, words[8]));
+        if (!instrs) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "program arena (%u instructions): out of device memory", words[8]);
+        fa.n_blocks = nblk;
+        for (int d = 0; d < 3; ++d) {
+            fa.nb[d] = lnb[d];
+            fa.parent_nb[d] = par_nb[d];
+        }
+        fa.block_chunks = sz;
+        fa.ratio = par_size ? par_size / sz : 1;
+        fa.parent_instrs = par_instrs;
+        fa.parent_off = par_off;
+        fa.parent_len = par_len;
+        fa.out_instrs = instrs;
+        fa.out_off = off;
+        fa.out_len = len;
+        if (exact) {
+            fa.chunks = obj->d_chunks;
+            fa.occ = counters + 2;
+        }
+        KLP(ctx, exact ? 1 : 0, launch_fold(exact, fa, st));
+        par_instrs = instrs;
+        par_off = off;
+        par_len = len;
+        for (int d = 0; d < 3; ++d) par_nb[d] = lnb[d];
+        par_size = sz;
+        if (exact) {
+            ch_instrs = instrs;
+            ch_off = off;
+            ch_len = len;
+        }
     }
-    fb.block_chunks = 1;
-    fb.ratio = SUPER;
-    fb.parent_instrs = sb_instrs;
-    fb.parent_off = sb_off;
-    fb.parent_len = sb_len;
-    fb.out_instrs = ch_instrs;
-    fb.out_off = ch_off;
-    fb.out_len = ch_len;
-    fb.chunks = obj->d_chunks;
-    fb.occ = counters + 2;
-    KLP(ctx, 1, launch_fold(true, fb, st));
 
     // ---- slot planning ----
     uint32_t* active_flag = tmp.get<uint32_t>(n);
@@ -421,6 +435,17 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     if (int rc = read_words(ctx, counters, 16, words)) return rc;
     if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
     const uint32_t n_active = words[9], n_slots = words[10], max_depth = words[1];
+    if (std::getenv("IVX_DEBUG")) {
+        std::vector<uint32_t> hc(n), hact(n);
+        cudaMemcpy(hc.data(), ch_len, n * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hact.data(), active_flag, n * 4, cudaMemcpyDeviceToHost);
+        uint64_t sc = 0, sact = 0, mx = 0;
+        for (uint32_t c = 0; c < n; ++c)
+            if (hact[c]) { sc += hc[c]; sact++; mx = std::max<uint64_t>(mx, hc[c]); }
+        std::fprintf(stderr, "[ivx] root_len %u | chunks %u parent arena %u | active %llu mean_len %.1f max %llu | max_depth %u slots %u\n",
+                     prog->root_len, n, words[8], (unsigned long long)sact, sact ? (double)sc / sact : 0.0,
+                     (unsigned long long)mx, max_depth, n_slots);
+    }
     obj->slot_capacity = n_slots;
     obj->slots_used = n_slots;
     obj->d_voxels = static_cast<unsigned char*>(ctx->alloc(std::max<size_t>(1, (size_t)n_slots) * SLOT_BYTES));
@@ -444,6 +469,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     ea.chunks = obj->d_chunks;
     ea.occ = counters + 2;
     ea.raw_out = nullptr;
+    ea.saturate_final_noise = 1;
     uint32_t egrid = 1;
     if (int rc = plan_eval_stack(ctx, max_depth, tmp, n_active, ea, egrid)) return rc;
     if (n_active) KLP(ctx, 2, launch_eval(ea, egrid, st));

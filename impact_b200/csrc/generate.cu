@@ -157,6 +157,41 @@ __device__ __forceinline__ void shift_down(Instr* out, uint32_t dst, uint32_t sr
     }
 }
 
+// Evaluates out[begin, end) — the specialised program of one operand — at voxel (si, sj, sk) of the
+// block. Pruning is value-preserving, so this is exactly the value the reference holds for that voxel
+// at this point of its sweep. `stk` is this lane's column of the warp's shared value stack.
+__device__ float eval_segment_at_voxel(const ivx_node* __restrict__ nodes, const Instr* seg, uint32_t begin, uint32_t end,
+                                       f3 lo, int si, int sj, int sk, float* stk /* stride 32 */) {
+    int sp = 0;
+    for (uint32_t q = begin; q < end; ++q) {
+        const Instr in = seg[q];
+        const uint32_t op = in.op_node >> 28;
+        const ivx_node& n = nodes[in.op_node & 0x0FFFFFFFu];
+        if (op == OP_CONST) {
+            stk[32 * sp++] = in.value;
+        } else if (op == OP_LEAF) {
+            const float* M = n.transform_to_node_space;
+            f3 origin = transform_point(M, lo);
+            f3 dx = mk3(M[0], M[1], M[2]), dy = mk3(M[4], M[5], M[6]), dz = mk3(M[8], M[9], M[10]);
+            f3 pos = (origin + (float)si * dx) + (float)sj * dy;
+            for (int t = 0; t < sk; ++t) pos = pos + dz;
+            stk[32 * sp++] = sd_leaf(n.kind, n.p, pos);
+        } else if (op == OP_SCALE) {
+            stk[32 * (sp - 1)] = stk[32 * (sp - 1)] * n.p[0];
+        } else if (op == OP_NEG) {
+            stk[32 * (sp - 1)] = -stk[32 * (sp - 1)];
+        } else if (op == OP_NOISE) {
+            NoiseFrame f = make_noise_frame(n, lo);
+            stk[32 * (sp - 1)] = stk[32 * (sp - 1)] + noise_for_voxel(n, f, si, sj, sk) * n.p[4];
+        } else {
+            const float r = op_combine(n.kind, stk[32 * (sp - 2)], stk[32 * (sp - 1)], n.p[0], n.p[1]);
+            sp -= 1;
+            stk[32 * (sp - 1)] = r;
+        }
+    }
+    return stk[0];
+}
+
 // Program specialisation for one block (a super-block of chunks, or one chunk).
 //
 // EXACT = true (block = one 16³ chunk): makes exactly the decisions
@@ -263,7 +298,14 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                                    (n.domain_hi[1] + eps < blo.y) || (n.domain_hi[2] + eps < blo.z);
                     if (outside) {
                         cls = 1;
-                    } else if (op == OP_LEAF) {
+                    } else if (op != OP_LEAF) {
+                        // a noise / combine can only be skipped by chunks lying outside its domain; if the whole
+                        // block sits inside the domain box every chunk applies it
+                        bool within_domain = (blo.x - eps >= n.domain_lo[0]) && (blo.y - eps >= n.domain_lo[1]) &&
+                                             (blo.z - eps >= n.domain_lo[2]) && (bhi.x + eps <= n.domain_hi[0]) &&
+                                             (bhi.y + eps <= n.domain_hi[1]) && (bhi.z + eps <= n.domain_hi[2]);
+                        if (!within_domain) cls |= 4;
+                    } else {
                         f3 h = leaf_interior_half_extents(n);
                         bool inside = (blo.x - eps >= -h.x) && (blo.y - eps >= -h.y) && (blo.z - eps >= -h.z) &&
                                       (bhi.x + eps <= h.x) && (bhi.y + eps <= h.y) && (bhi.z + eps <= h.z);
@@ -309,7 +351,6 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                     S.is_const[sp] = 1;
                     out[olen] = Instr{(uint32_t)OP_CONST << 28, c};
                 }
-                if (EXACT) S.val[sp][lane] = c;
                 olen += 1;
                 sp += 1;
             } else if (op == OP_LEAF) {
@@ -337,14 +378,6 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                     S.ihi[sp] = rhi;
                     out[olen] = in;
                 }
-                if (EXACT) {
-                    // update_signed_distances_for_block (atomic.rs:1601-1627) at the sampled voxel
-                    f3 origin = transform_point(M, lo);
-                    f3 dx = mk3(M[0], M[1], M[2]), dy = mk3(M[4], M[5], M[6]), dz = mk3(M[8], M[9], M[10]);
-                    f3 pos = (origin + (float)si * dx) + (float)sj * dy;
-                    for (int q = 0; q < sk; ++q) pos = pos + dz;
-                    S.val[sp][lane] = sd_leaf(n.kind, n.p, pos);
-                }
                 olen += 1;
                 sp += 1;
             } else if (op == OP_SCALE || op == OP_NEG) {
@@ -369,25 +402,21 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                     }
                 }
                 if (!tc) olen += 1;
-                if (EXACT) S.val[sp - 1][lane] = op == OP_NEG ? -S.val[sp - 1][lane] : S.val[sp - 1][lane] * s;
             } else if (op == OP_NOISE) {
                 const ivx_node& n = a.nodes[ni];
                 bool apply = true;
-                if (EXACT) {
+                if (EXACT && cls == 1) {
+                    // all_modified_signed_distances_at_block_test_positions_pass_predicate (atomic.rs:1510-1572):
+                    // the operand's value at the 14 sampled voxels, then the 26 test positions
                     NoiseFrame f = make_noise_frame(n, lo);
-                    if (cls == 1) {
-                        // all_modified_signed_distances_at_block_test_positions_pass_predicate
-                        const int tl = lane < 26 ? lane : 0;
-                        float v = __shfl_sync(0xffffffffu, S.val[sp - 1][lane], c_test_lane[tl]);
-                        f3 tp = test_position(tl, f.o, f.dxn, f.dyn, f.dzn);
-                        float mv = v + noise_at(n, f.freq, tp) * n.p[4];
-                        bool pass = mv >= n.margin;
-                        apply = !__all_sync(0xffffffffu, pass);
-                    }
-                    if (apply) {
-                        float nv = noise_for_voxel(n, f, si, sj, sk);
-                        S.val[sp - 1][lane] = S.val[sp - 1][lane] + nv * n.p[4];
-                    }
+                    const float cv = eval_segment_at_voxel(a.nodes, out, S.seg_start[sp - 1], olen, lo, si, sj, sk,
+                                                           &S.val[0][lane]);
+                    const int tl = lane < 26 ? lane : 0;
+                    float v = __shfl_sync(0xffffffffu, cv, c_test_lane[tl]);
+                    f3 tp = test_position(tl, f.o, f.dxn, f.dyn, f.dzn);
+                    float mv = v + noise_at(n, f.freq, tp) * n.p[4];
+                    bool pass = mv >= n.margin;
+                    apply = !__all_sync(0xffffffffu, pass);
                 }
                 if (apply) {
                     const float l0 = S.ilo[sp - 1], h0 = S.ihi[sp - 1];
@@ -412,13 +441,20 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                 const float k = n.p[0];
                 int decision;  // 0 apply, 1 skip (keep child 1), 2 undecided (conservative only)
                 if (EXACT) {
-                    float r = op_combine(n.kind, S.val[ia][lane], S.val[ib][lane], n.p[0], n.p[1]);
-                    bool pass = (lane >= 14) || (r >= n.margin);
-                    bool all_pass = __all_sync(0xffffffffu, pass);
-                    decision = (cls == 1 && all_pass) ? 1 : 0;
-                    if (decision == 0) S.val[ia][lane] = r;
+                    decision = 0;
+                    if (cls == 1) {
+                        // all_block_test_positions_pass_predicate (atomic.rs:796-806): both operands at the
+                        // 14 sampled voxels (one per lane)
+                        const float va = eval_segment_at_voxel(a.nodes, out, seg_a, seg_b, lo, si, sj, sk, &S.val[0][lane]);
+                        const float vb = eval_segment_at_voxel(a.nodes, out, seg_b, olen, lo, si, sj, sk, &S.val[0][lane]);
+                        const float r = op_combine(n.kind, va, vb, n.p[0], n.p[1]);
+                        const bool pass = (lane >= 14) || (r >= n.margin);
+                        if (__all_sync(0xffffffffu, pass)) decision = 1;
+                    }
                 } else {
-                    if (both_const) {
+                    if ((cls & 5) == 0) {
+                        decision = 0;  // no chunk of the block lies outside the node's domain: always applied
+                    } else if (both_const) {
                         bool pass = op_combine(n.kind, ca, cb, n.p[0], n.p[1]) >= n.margin;
                         decision = !pass ? 0 : (cls == 1 ? 1 : 2);
                     } else {
@@ -601,6 +637,11 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
     __shared__ __align__(16) int8_t s_sd[4096];
     __shared__ uint32_t s_cnt[16];
     __shared__ uint8_t s_first_type;
+    // permutation table of the 4-D simplex noise: thread-divergent byte gathers are serialised by
+    // the constant cache, shared memory serves them at bank-conflict cost only
+    __shared__ uint8_t s_perm[256];
+    if (threadIdx.x < 256) s_perm[threadIdx.x] = c_perm[threadIdx.x];
+    __syncthreads();
 
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tj = tid & 15;
@@ -666,6 +707,11 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                 for (int k = 0; k < 16; ++k) top[k] = -top[k];
             } else if (op == OP_NOISE) {
                 NoiseFrame f = make_noise_frame(n, lo);
+                // Last instruction of a voxel (not raw) evaluation: a voxel whose value cannot leave the
+                // saturated code range whatever the noise adds (|noise * scale| <= A) is stored as 127 / -128
+                // without evaluating the noise (lib.rs:195-201); decided per voxel, skipped per warp.
+                const bool final_sat = (pc + 1 == plen) && a.raw_out == nullptr && a.saturate_final_noise;
+                const float A = 1.005f * fabsf(n.p[3]) + 1e-3f;
                 const float ns = n.p[4];
                 const float lac = n.p[1], gain = n.p[2];
                 const uint32_t oct = n.octaves;
@@ -673,8 +719,16 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                 if (f.rotated) {
                     f3 pos = (f.o + (float)ti * f.dxn) + (float)tj * f.dyn;
                     for (int k = 0; k < 16; ++k) {
-                        float nv = fbm3(pos.z * f.freq, pos.y * f.freq, pos.x * f.freq, lac, gain, oct, seed);
-                        top[k] = top[k] + nv * ns;
+                        const float v = top[k];
+                        bool need = true;
+                        if (final_sat) {
+                            if (v - A >= 2.5401f) { need = false; top[k] = 1000.0f; }
+                            else if (v + A <= -2.5601f) { need = false; top[k] = -1000.0f; }
+                        }
+                        if (need) {
+                            float nv = fbm3(pos.z * f.freq, pos.y * f.freq, pos.x * f.freq, lac, gain, oct, seed);
+                            top[k] = v + nv * ns;
+                        }
                         pos = pos + f.dzn;
                     }
                 } else {
@@ -682,9 +736,18 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                     const float yc = accumulate_ones(f.o.y, tj) * f.freq;
 #pragma unroll 1
                     for (int k = 0; k < 16; ++k) {
-                        float xc = block_noise_x(f.o.z, k) * f.freq;
-                        float nv = fbm3(xc, yc, zc, lac, gain, oct, seed);
-                        top[k] = top[k] + nv * ns;
+                        const float v = top[k];
+                        bool need = true;
+                        if (final_sat) {
+                            if (v - A >= 2.5401f) { need = false; top[k] = 1000.0f; }
+                            else if (v + A <= -2.5601f) { need = false; top[k] = -1000.0f; }
+                            if (!__any_sync(0xffffffffu, need)) continue;
+                        }
+                        if (need) {
+                            float xc = block_noise_x(f.o.z, k) * f.freq;
+                            float nv = fbm3(xc, yc, zc, lac, gain, oct, seed);
+                            top[k] = v + nv * ns;
+                        }
                     }
                 }
             } else {  // OP_COMBINE
@@ -770,7 +833,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                 for (uint32_t t = 0; t < a.gp.types.n_types; ++t) {
                     float xc = 0.0f + (float)(t & 7u);
                     for (uint32_t v = 0; v < (t >> 3); ++v) xc = xc + 8.0f;
-                    float nv = simplex4_t(xc * ft, yc, zc, wc, seed, c_perm);
+                    float nv = simplex4_t(xc * ft, yc, zc, wc, seed, s_perm);
                     if (t == 0 || nv > best) {
                         best = nv;
                         best_t = t;

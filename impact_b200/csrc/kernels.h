@@ -51,6 +51,7 @@ struct EvalArgs {
     DevChunk* chunks;
     uint32_t* occ;
     float* raw_out;           // non-null: write f32 distances instead of voxels
+    int saturate_final_noise; // 1: skip a final noise term where it cannot change the stored code
     int smem_levels;
     float* spill;
     int spill_levels;
