@@ -44,17 +44,18 @@ def make_workload(name: str):
         return W.noisy_box(246.0, 8), W.same_type(0), "config 2: Box(246^3) + 8-octave noise, Same(0)"
     if name in ("asteroid512", "asteroid1024"):
         hi = 512 if name == "asteroid512" else 1024
-        try:
-            from impact_b200 import meta  # meta-graph compiler (asteroid.vgen.ron)
+        from impact_b200 import meta  # meta-graph compiler; bench graphs cached under impact_b200/data/
 
-            graph = meta.asteroid_graph_scaled(hi - 16, hi)
-            desc = f"asteroid.vgen.ron compiled (seed 0), max grid dim in ({hi - 16},{hi}], GradientNoise types"
-        except ImportError:
-            s = W.scale_to_max_dim(lambda sc: W.asteroid_stand_in(sc), hi - 16, hi, hi / 256.0)
-            graph = W.asteroid_stand_in(s)
-            desc = (f"asteroid stand-in graph (same node kinds/counts as asteroid.vgen.ron; crater placement not "
-                    f"sphere-cast), max grid dim in ({hi - 16},{hi}], GradientNoise types")
+        graph = meta.asteroid_graph_scaled(hi - 16, hi)
+        desc = (f"engine/benches/data/asteroid.vgen.ron compiled with seed 0, scale_factor tuned so the largest grid "
+                f"dimension is in ({hi - 16},{hi}]; GradientNoise(4 types, 0.02, 1.0, seed 0)")
         return graph, W.gradient_noise_types(), desc
+    if name in ("standin512", "standin1024"):
+        hi = 512 if name == "standin512" else 1024
+        s = W.scale_to_max_dim(lambda sc: W.asteroid_stand_in(sc), hi - 16, hi, hi / 256.0)
+        desc = (f"stress graph: 5 spheres + 440 rotated capsules in balanced smooth-union trees (the node mix of "
+                f"asteroid.vgen.ron with every crater placed), max grid dim in ({hi - 16},{hi}], GradientNoise types")
+        return W.asteroid_stand_in(s), W.gradient_noise_types(), desc
     raise SystemExit(f"unknown workload {name!r}")
 
 

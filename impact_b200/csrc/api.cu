@@ -924,6 +924,26 @@ int ivx_program_eval_chunks(ivx_ctx* ctx, const ivx_program* prog, const float* 
     return IVX_OK;
 }
 
+int ivx_program_eval_blocks(ivx_ctx* ctx, const ivx_program* prog, const float* origins, uint32_t n_blocks, uint32_t size,
+                            float* out) {
+    if (!ctx || !prog || (n_blocks && (!origins || !out))) return IVX_ERR_INVALID_ARGUMENT;
+    if (size != 1 && size != 2) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "block size must be 1 or 2");
+    cudaSetDevice(ctx->device);
+    if (n_blocks == 0) return IVX_OK;
+    if (prog->host.stack_depth > 64) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    const size_t count = (size_t)n_blocks * size * size * size;
+    float* d_org = tmp.get<float>((size_t)n_blocks * 3);
+    float* d_out = tmp.get<float>(count);
+    if (!d_org || !d_out) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "eval_blocks: out of device memory");
+    CU(ctx, cudaMemcpyAsync(d_org, origins, (size_t)n_blocks * 12, cudaMemcpyHostToDevice, st));
+    KL(ctx, launch_eval_blocks(prog->d_nodes, (uint32_t)prog->host.nodes.size(), d_org, n_blocks, (int)size, d_out, st));
+    CU(ctx, cudaMemcpyAsync(out, d_out, count * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return IVX_OK;
+}
+
 int ivx_object_generate(ivx_ctx* ctx, const ivx_program* program, float voxel_extent, const ivx_type_generator* tg,
                         ivx_object** out) {
     if (!ctx || !program || !tg || !out) return IVX_ERR_INVALID_ARGUMENT;

@@ -957,6 +957,67 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// k_eval_blocks: compute_signed_distances_for_block_preserving_gradients<SIZE, SIZE³>
+// (atomic.rs:877-998) for many small blocks (SIZE = 1 or 2): the whole program, no culling, one thread
+// per voxel with its operand stack in local memory. Used by the meta-graph compiler's surface probes
+// (meta.rs:2705-2748), batched over all instances of a node.
+__global__ void k_eval_blocks(const ivx_node* __restrict__ nodes, uint32_t n_nodes, const float* __restrict__ origins,
+                              uint32_t n_blocks, int size, float* __restrict__ out) {
+    const uint32_t count = (uint32_t)(size * size * size);
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_blocks * count) return;
+    const uint32_t b = gid / count, v = gid % count;
+    const int i = (int)(v / (uint32_t)(size * size)), j = (int)((v / (uint32_t)size) % (uint32_t)size), k = (int)(v % (uint32_t)size);
+    const f3 lo = mk3(origins[3 * b], origins[3 * b + 1], origins[3 * b + 2]);
+    float stk[FOLD_MAX_DEPTH];
+    int sp = 0;
+    if (n_nodes == 0) {
+        out[gid] = 0.02f * 127.0f;
+        return;
+    }
+    for (uint32_t q = 0; q < n_nodes; ++q) {
+        const ivx_node& n = nodes[q];
+        if (n.kind <= IVX_BOX) {
+            const float* M = n.transform_to_node_space;
+            f3 origin = transform_point(M, lo);
+            f3 dx = mk3(M[0], M[1], M[2]), dy = mk3(M[4], M[5], M[6]), dz = mk3(M[8], M[9], M[10]);
+            f3 pos = (origin + (float)i * dx) + (float)j * dy;
+            for (int t = 0; t < k; ++t) pos = pos + dz;
+            if (sp < FOLD_MAX_DEPTH) stk[sp] = sd_leaf(n.kind, n.p, pos);
+            sp++;
+        } else if (n.kind == IVX_SCALING) {
+            stk[sp - 1] = stk[sp - 1] * n.p[0];
+        } else if (n.kind == IVX_MULTIFRACTAL_NOISE) {
+            NoiseFrame f = make_noise_frame(n, lo);
+            float nv;
+            if (f.rotated) {
+                f3 pos = (f.o + (float)i * f.dxn) + (float)j * f.dyn;
+                for (int t = 0; t < k; ++t) pos = pos + f.dzn;
+                nv = noise_at(n, f.freq, pos);
+            } else {
+                // block call with SIZE < 8: x = start + lane, y / z by repeated += 1.0
+                const float zc = accumulate_ones(f.o.x, i), yc = accumulate_ones(f.o.y, j), xc = f.o.z + (float)k;
+                nv = fbm3(xc * f.freq, yc * f.freq, zc * f.freq, n.p[1], n.p[2], n.octaves, (int32_t)n.seed);
+            }
+            stk[sp - 1] = stk[sp - 1] + nv * n.p[4];
+        } else if (n.kind >= IVX_UNION) {
+            const float r = op_combine(n.kind, stk[sp - 2], stk[sp - 1], n.p[0], n.p[1]);
+            sp -= 1;
+            stk[sp - 1] = r;
+        }
+    }
+    out[gid] = stk[0];
+}
+
+cudaError_t launch_eval_blocks(const ivx_node* nodes, uint32_t n_nodes, const float* origins, uint32_t n_blocks, int size,
+                               float* out, cudaStream_t st) {
+    const uint32_t total = n_blocks * (uint32_t)(size * size * size);
+    if (total == 0) return cudaSuccess;
+    k_eval_blocks<<<(total + 127) / 128, 128, 0, st>>>(nodes, n_nodes, origins, n_blocks, size, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // host launch wrappers
 size_t fold_smem_bytes(bool exact) {
     return (size_t)FOLD_WARPS * (exact ? sizeof(FoldWarpSmem) : offsetof(FoldWarpSmem, val));

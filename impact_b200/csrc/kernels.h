@@ -58,6 +58,8 @@ struct EvalArgs {
 };
 cudaError_t launch_eval(const EvalArgs& a, uint32_t grid, cudaStream_t st);
 int eval_max_blocks_per_sm(int smem_levels);
+cudaError_t launch_eval_blocks(const ivx_node* nodes, uint32_t n_nodes, const float* origins, uint32_t n_blocks, int size,
+                               float* out, cudaStream_t st);
 
 // ---- scan.cu ----------------------------------------------------------------
 // Exclusive prefix sums over small arrays (chunk-count sized), single CTA.

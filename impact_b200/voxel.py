@@ -113,6 +113,15 @@ class SDFGenerator:
         self.ctx.check(self.ctx._lib.ivx_program_eval_chunks(self.ctx.h, self.h, L.ptr(org), C.c_uint32(len(org)), L.ptr(out)))
         return out
 
+    def compute_signed_distances_for_blocks_preserving_gradients(self, block_origins, size: int) -> np.ndarray:
+        """Batched `compute_signed_distances_for_block_preserving_gradients::<SIZE, _>` (atomic.rs:877-998),
+        SIZE in {1, 2} → (n, SIZE**3) f32; the meta compiler's surface probes."""
+        org = np.ascontiguousarray(block_origins, np.float32).reshape(-1, 3)
+        out = np.zeros((len(org), size ** 3), np.float32)
+        self.ctx.check(self.ctx._lib.ivx_program_eval_blocks(self.ctx.h, self.h, L.ptr(org), C.c_uint32(len(org)),
+                                                             C.c_uint32(size), L.ptr(out)))
+        return out
+
     def __del__(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx._lib.ivx_program_free(self.ctx.h, self.h)

@@ -235,6 +235,13 @@ void ivx_program_free(ivx_ctx* ctx, ivx_program* program);
 int ivx_program_eval_chunks(ivx_ctx* ctx, const ivx_program* program, const float* chunk_origins,
                             uint32_t n_chunks, float* out_signed_distances);
 
+/* SDFGenerator::compute_signed_distances_for_block_preserving_gradients<SIZE, SIZE^3>
+ * (atomic.rs:877-998; no culling) for a batch of small blocks, SIZE = 1 or 2: origins = n_blocks x 3 block
+ * lower corners in root space, out = n_blocks x SIZE^3 f32 (host). These are the probes the meta-graph compiler's
+ * sphere-cast / closest-point / gradient nodes issue (meta.rs:2705-2748), batched over instances. */
+int ivx_program_eval_blocks(ivx_ctx* ctx, const ivx_program* program, const float* block_origins,
+                            uint32_t n_blocks, uint32_t size, float* out_signed_distances);
+
 /* ---- object generation --------------------------------------------------
  * Replaces SDFVoxelGenerator::new (generation.rs:207-258) +
  * VoxelObject::generate / generate_in_parallel (object.rs:239-263):
