@@ -195,8 +195,11 @@ def run_gpu(args):
     _, _, dlo, dhi = compile_program_host(graph)
     grid_shape = [int(np.ceil(np.float32(h) - np.float32(l))) + 2 for l, h in zip(dlo, dhi)]
     planes = (grid_shape[0] + 15) // 16
-    per = (planes + world - 1) // world
-    slab = (min(planes, rank * per), min(planes, (rank + 1) * per))
+    from impact_b200 import distributed as D
+
+    ranges = D.slab_ranges(planes, world)
+    slab = ranges[rank]
+    dev = torch.device("cuda", local_rank)
     total_voxels = int(np.prod(grid_shape))
     my_voxels = (min(grid_shape[0], slab[1] * 16) - min(grid_shape[0], slab[0] * 16)) * grid_shape[1] * grid_shape[2]
 
@@ -208,9 +211,20 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def step_resident():
-        obj = VoxelObject.generate(vg, slab if world > 1 else None)
+        if world == 1:
+            obj = VoxelObject.generate(vg)
+            return obj, VoxelObjectMesh.create(obj)
+        # x-slab per rank → halo planes over NCCL → derived state → mesh → mesh gathered on rank 0
+        obj = VoxelObject.generate(vg, slab)
+        halo_stats.update(D.exchange_halos_and_finalize(obj, ranges, rank, dev))
         mesh = VoxelObjectMesh.create(obj)
+        merged = D.gather_mesh(D.device_mesh_tensors(mesh, dev), rank, world, dev)
+        if merged is not None:
+            halo_stats["merged_vertices"] = int(merged["positions"].shape[0])
+            halo_stats["merged_indices"] = int(merged["indices"].shape[0])
         return obj, mesh
+
+    halo_stats = {}
 
     with torch.cuda.stream(stream):
         info = None
@@ -265,6 +279,9 @@ def run_gpu(args):
             if world > 1:
                 ctx.check(lib.ivx_object_generate_slab(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), C.c_uint32(slab[0]),
                                                        C.c_uint32(slab[1]), C.byref(o)))
+                view = VoxelObject(ctx, o)
+                D.exchange_halos_and_finalize(view, ranges, rank, dev)
+                view.h = None  # `o` is freed below
             else:
                 ctx.check(lib.ivx_object_generate(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), C.byref(o)))
             mi = L.MeshInfo()
@@ -319,6 +336,7 @@ def run_gpu(args):
             "config": {
                 "workload": args.workload, "description": desc, "grid_shape": grid_shape,
                 "chunks": int(np.prod(info[0]["chunk_counts"])), "parallelism": f"x-slab x{world}",
+                "slab_planes": [list(r) for r in ranges], "rank0_exchange": halo_stats,
                 "rank0_chunks": {"void": oi["n_void"], "uniform": oi["n_uniform"], "non_uniform": oi["n_non_uniform"]},
                 "rank0_mesh": {"vertices": info[1], "indices": info[2], "submeshes": info[3]},
                 "l2": "256 MiB buffer written between timed iterations (outside the timed intervals); the voxel "
@@ -331,7 +349,10 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(nodes_host.nbytes + 16), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms,
                     "path": "ivx_program_build(host nodes) → ivx_object_generate → ivx_object_mesh → "
-                            "ivx_object_download + ivx_mesh_download into pinned host buffers"},
+                            "ivx_object_download + ivx_mesh_download into pinned host buffers" if world == 1 else
+                            "per rank: ivx_program_build(host nodes) → ivx_object_generate_slab → halo exchange (NCCL) → "
+                            "ivx_object_slab_finalize → ivx_object_mesh → ivx_object_download + ivx_mesh_download of "
+                            "the rank's slab into pinned host buffers; d2h bytes are rank 0's"},
             "roofline": {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": per_voxel, "voxels_per_launch": my_voxels,

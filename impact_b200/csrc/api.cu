@@ -114,6 +114,11 @@ struct ivx_object {
     uint32_t occ_voxels[6] = {0, 0, 0, 0, 0, 0};  // lo xyz, hi xyz (exclusive)
     uint32_t n_void = 0, n_uniform = 0, n_non_uniform = 0;
     DeviceMesh mesh;
+    // slab protocol (multi-GPU): derived state is pending until the halo planes are imported
+    bool derive_pending = false;
+    uint32_t* d_slot_of = nullptr;       // slot reserved for each chunk (conversion target), 0xFFFFFFFF = none
+    uint32_t* d_convert_flag = nullptr;  // result of ivx_object_slab_classify
+    bool halo_present[2] = {false, false};
 };
 
 namespace {
@@ -214,8 +219,6 @@ void derive_grid(const HostProgram& p, uint32_t grid_shape[3], float shifted_cen
     }
 }
 
-constexpr uint32_t SUPER = 4;  // super-block edge in chunks for the conservative fold
-
 int upload_program(ivx_ctx* ctx, ivx_program* prog) {
     const auto& nodes = prog->host.nodes;
     std::vector<Instr> root;
@@ -311,10 +314,15 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
         obj->grid_shape[d] = gp.grid_shape[d];
         obj->chunk_counts[d] = gp.chunk_counts[d];
     }
-    obj->first_i = i_begin;
+    // a slab keeps one extra chunk plane per inner side for the neighbouring rank's boundary plane
+    const uint32_t halo_lo = (!whole && i_end > i_begin && i_begin > 0) ? 1u : 0u;
+    const uint32_t halo_hi = (!whole && i_end > i_begin && i_end < gp.chunk_counts[0]) ? 1u : 0u;
+    obj->halo_present[0] = halo_lo != 0;
+    obj->halo_present[1] = halo_hi != 0;
+    obj->first_i = i_begin - halo_lo;
     obj->own_begin = i_begin;
     obj->own_end = i_end;
-    obj->nb[0] = i_end - i_begin;
+    obj->nb[0] = (i_end - i_begin) + halo_lo + halo_hi;
     obj->nb[1] = gp.chunk_counts[1];
     obj->nb[2] = gp.chunk_counts[2];
     const uint32_t n = obj->nb[0] * obj->nb[1] * obj->nb[2];
@@ -360,6 +368,8 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     fa.error_flag = counters;
     fa.prune = 1;
     fa.saturate = 1;
+    fa.own_lo = halo_lo;
+    fa.own_hi = obj->nb[0] - halo_hi;
     // the "parent" of the coarsest level is the whole program
     const Instr* par_instrs = prog->d_root;
     const uint32_t* par_off = prog->d_root_meta;
@@ -424,7 +434,8 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     uint32_t* active_flag = tmp.get<uint32_t>(n);
     uint32_t* slot_flag = tmp.get<uint32_t>(n);
     uint32_t* active_scan = tmp.get<uint32_t>(n);
-    uint32_t* slot_of = tmp.get<uint32_t>(n);
+    uint32_t* slot_of = whole ? tmp.get<uint32_t>(n) : static_cast<uint32_t*>(ctx->alloc((size_t)n * 4));
+    if (!whole) obj->d_slot_of = slot_of;
     uint32_t* active_list = tmp.get<uint32_t>(n);
     if (!active_flag || !slot_flag || !active_scan || !slot_of || !active_list)
         IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "slot planning: out of device memory");
@@ -446,10 +457,12 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
                      prog->root_len, n, words[8], (unsigned long long)sact, sact ? (double)sc / sact : 0.0,
                      (unsigned long long)mx, max_depth, n_slots);
     }
-    obj->slot_capacity = n_slots;
+    // halo planes get their slots up front so that importing them never moves the pool
+    obj->slot_capacity = n_slots + (halo_lo + halo_hi) * obj->nb[1] * obj->nb[2];
     obj->slots_used = n_slots;
-    obj->d_voxels = static_cast<unsigned char*>(ctx->alloc(std::max<size_t>(1, (size_t)n_slots) * SLOT_BYTES));
-    if (!obj->d_voxels) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "voxel storage (%u chunks): out of device memory", n_slots);
+    obj->d_voxels = static_cast<unsigned char*>(ctx->alloc(std::max<size_t>(1, (size_t)obj->slot_capacity) * SLOT_BYTES));
+    if (!obj->d_voxels)
+        IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "voxel storage (%u chunks): out of device memory", obj->slot_capacity);
     KL(ctx, launch_set_reserved_slots(obj->d_chunks, n, slot_flag, slot_of, slot_of, st));
 
     // ---- evaluate active chunks ----
@@ -475,11 +488,16 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     if (n_active) KLP(ctx, 2, launch_eval(ea, egrid, st));
 
     // ---- cross-chunk derived state ----
-    uint32_t* convert_flag = tmp.get<uint32_t>(n);
-    if (!convert_flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "derive: out of device memory");
-    KLP(ctx, 3, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, st));
-    KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr, n,
-                                  persistent_grid(ctx, n, 8), st));
+    if (whole) {
+        uint32_t* convert_flag = tmp.get<uint32_t>(n);
+        if (!convert_flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "derive: out of device memory");
+        KLP(ctx, 3, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, 0, obj->nb[0], st));
+        KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr,
+                                          n, 0, obj->nb[0], persistent_grid(ctx, n, 8), st));
+    } else {
+        // a slab waits for its halo planes: ivx_object_halo_* → ivx_object_slab_classify → ivx_object_slab_finalize
+        obj->derive_pending = true;
+    }
 
     if (int rc = read_words(ctx, counters, 16, words)) return rc;
     const bool any = words[2] != 0xFFFFFFFFu;
@@ -960,6 +978,121 @@ int ivx_object_generate_slab(ivx_ctx* ctx, const ivx_program* program, float vox
     return generate_impl(ctx, program, voxel_extent, tg, chunk_i_begin, chunk_i_end, false, out);
 }
 
+// ---- slab protocol (multi-GPU) ------------------------------------------------
+namespace {
+struct HaloPlane {
+    uint32_t plane_chunks, own_first, halo_first;
+};
+// side 0 = towards lower chunk-i, side 1 = towards higher
+bool halo_plane(const ivx_object* obj, int side, HaloPlane& hp) {
+    if (side < 0 || side > 1 || !obj->halo_present[side]) return false;
+    hp.plane_chunks = obj->nb[1] * obj->nb[2];
+    const uint32_t lo = obj->own_begin - obj->first_i, hi = obj->own_end - obj->first_i;  // local own planes [lo, hi)
+    hp.own_first = (side == 0 ? lo : hi - 1) * hp.plane_chunks;
+    hp.halo_first = (side == 0 ? lo - 1 : hi) * hp.plane_chunks;
+    return true;
+}
+}  // namespace
+
+int ivx_object_halo_capacity(ivx_ctx* ctx, const ivx_object* obj, size_t* out_bytes) {
+    if (!ctx || !obj || !out_bytes) return IVX_ERR_INVALID_ARGUMENT;
+    *out_bytes = (size_t)obj->nb[1] * obj->nb[2] * (sizeof(DevChunk) + SLOT_BYTES);
+    return IVX_OK;
+}
+
+int ivx_object_halo_export(ivx_ctx* ctx, const ivx_object* obj, int side, void* d_buf, size_t capacity, size_t* out_bytes) {
+    if (!ctx || !obj || !d_buf || !out_bytes) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    HaloPlane hp;
+    if (!halo_plane(obj, side, hp)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object has no neighbour slab on side %d", side);
+    Tmp tmp(ctx);
+    uint32_t* flag = tmp.get<uint32_t>(hp.plane_chunks);
+    uint32_t* ord = tmp.get<uint32_t>(hp.plane_chunks);
+    if (!flag || !ord) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "halo export: out of device memory");
+    KL(ctx, launch_halo_flags(obj->d_chunks, hp.own_first, hp.plane_chunks, flag, ctx->stream));
+    KL(ctx, launch_exclusive_scan(flag, ord, hp.plane_chunks, ctx->d_scratch + 29, ctx->stream));
+    uint32_t nnu;
+    if (int rc = read_words(ctx, ctx->d_scratch + 29, 1, &nnu)) return rc;
+    const size_t bytes = (size_t)hp.plane_chunks * sizeof(DevChunk) + (size_t)nnu * SLOT_BYTES;
+    if (capacity < bytes) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "halo export needs %zu bytes, buffer has %zu", bytes, capacity);
+    KL(ctx, launch_halo_pack(obj->d_chunks, hp.own_first, hp.plane_chunks, ord, obj->d_voxels,
+                             static_cast<unsigned char*>(d_buf), ctx->stream));
+    *out_bytes = bytes;
+    return IVX_OK;
+}
+
+int ivx_object_halo_import(ivx_ctx* ctx, ivx_object* obj, int side, const void* d_buf, size_t bytes) {
+    if (!ctx || !obj || !d_buf) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    HaloPlane hp;
+    if (!halo_plane(obj, side, hp)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object has no neighbour slab on side %d", side);
+    if (!obj->derive_pending) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "halo import after ivx_object_slab_finalize");
+    const size_t head = (size_t)hp.plane_chunks * sizeof(DevChunk);
+    if (bytes < head || (bytes - head) % SLOT_BYTES != 0)
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "halo buffer of %zu bytes does not hold a plane of %u chunks", bytes, hp.plane_chunks);
+    const uint32_t nnu = (uint32_t)((bytes - head) / SLOT_BYTES);
+    if (nnu > hp.plane_chunks) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "halo buffer holds more chunks than a plane");
+    if (int rc = ensure_slots(ctx, obj, nnu)) return rc;
+    KL(ctx, launch_halo_unpack(obj->d_chunks, hp.halo_first, hp.plane_chunks, obj->slots_used, obj->d_voxels,
+                               static_cast<const unsigned char*>(d_buf), ctx->stream));
+    obj->slots_used += nnu;
+    return IVX_OK;
+}
+
+int ivx_object_slab_classify(ivx_ctx* ctx, ivx_object* obj) {
+    if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (!obj->derive_pending) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object is not a slab with pending derived state");
+    if (obj->n_chunks == 0) return IVX_OK;
+    if (!obj->d_convert_flag) obj->d_convert_flag = static_cast<uint32_t*>(ctx->alloc((size_t)obj->n_chunks * 4));
+    if (!obj->d_convert_flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "derive: out of device memory");
+    KLP(ctx, 3, launch_boundary_classify(obj->d_chunks, obj->n_chunks, obj->nb, nullptr, obj->d_convert_flag,
+                                         obj->own_begin - obj->first_i, obj->own_end - obj->first_i, ctx->stream));
+    return IVX_OK;
+}
+
+int ivx_object_halo_kinds_export(ivx_ctx* ctx, const ivx_object* obj, int side, void* d_buf, size_t capacity) {
+    if (!ctx || !obj || !d_buf) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    HaloPlane hp;
+    if (!halo_plane(obj, side, hp)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object has no neighbour slab on side %d", side);
+    if (!obj->d_convert_flag) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "call ivx_object_slab_classify first");
+    if (capacity < hp.plane_chunks) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "kinds export needs %u bytes", hp.plane_chunks);
+    KL(ctx, launch_halo_kinds_pack(obj->d_chunks, obj->d_convert_flag, hp.own_first, hp.plane_chunks,
+                                   static_cast<uint8_t*>(d_buf), ctx->stream));
+    return IVX_OK;
+}
+
+int ivx_object_halo_kinds_import(ivx_ctx* ctx, ivx_object* obj, int side, const void* d_buf, size_t bytes) {
+    if (!ctx || !obj || !d_buf) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    HaloPlane hp;
+    if (!halo_plane(obj, side, hp)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object has no neighbour slab on side %d", side);
+    if (bytes < hp.plane_chunks) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "kinds buffer needs %u bytes", hp.plane_chunks);
+    KL(ctx, launch_halo_kinds_unpack(obj->d_chunks, hp.halo_first, hp.plane_chunks, static_cast<const uint8_t*>(d_buf),
+                                     ctx->stream));
+    return IVX_OK;
+}
+
+int ivx_object_slab_finalize(ivx_ctx* ctx, ivx_object* obj) {
+    if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (!obj->derive_pending) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object is not a slab with pending derived state");
+    if (obj->n_chunks) {
+        if (!obj->d_convert_flag)
+            if (int rc = ivx_object_slab_classify(ctx, obj)) return rc;
+        KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, obj->n_chunks, obj->nb, nullptr, obj->d_convert_flag, obj->d_slot_of,
+                                          obj->d_voxels, nullptr, obj->n_chunks, obj->own_begin - obj->first_i,
+                                          obj->own_end - obj->first_i, persistent_grid(ctx, obj->n_chunks, 8), ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->release(obj->d_slot_of);
+    ctx->release(obj->d_convert_flag);
+    obj->d_slot_of = obj->d_convert_flag = nullptr;
+    obj->derive_pending = false;
+    return IVX_OK;
+}
+
 int ivx_object_info_get(ivx_ctx* ctx, const ivx_object* obj, ivx_object_info* out) {
     if (!ctx || !obj || !out) return IVX_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
@@ -975,7 +1108,9 @@ int ivx_object_info_get(ivx_ctx* ctx, const ivx_object* obj, ivx_object_info* ou
         uint32_t* c3 = ctx->d_scratch + 24;
         CU(ctx, cudaMemsetAsync(c3, 0, 12, ctx->stream));
         ctx->launches++;
-        k_count_kinds<<<(obj->n_chunks + 255) / 256, 256, 0, ctx->stream>>>(obj->d_chunks, obj->n_chunks, 0, obj->n_chunks, c3);
+        const uint32_t plane = obj->nb[1] * obj->nb[2];
+        k_count_kinds<<<(obj->n_chunks + 255) / 256, 256, 0, ctx->stream>>>(
+            obj->d_chunks, obj->n_chunks, (obj->own_begin - obj->first_i) * plane, (obj->own_end - obj->first_i) * plane, c3);
         CU(ctx, cudaGetLastError());
         uint32_t w[3];
         if (int rc = read_words(ctx, c3, 3, w)) return rc;
@@ -997,7 +1132,10 @@ int ivx_object_download(ivx_ctx* ctx, const ivx_object* obj, ivx_chunk_desc* chu
                         ivx_voxel* voxels, size_t voxel_capacity) {
     if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
-    const uint32_t n = obj->n_chunks;
+    // a slab downloads its own planes; halo planes belong to the neighbouring ranks
+    const uint32_t plane = obj->nb[1] * obj->nb[2];
+    const uint32_t n = (obj->own_end - obj->own_begin) * plane;
+    const DevChunk* own_chunks = obj->d_chunks + (size_t)(obj->own_begin - obj->first_i) * plane;
     if (n == 0) return IVX_OK;
     if (!chunks || chunk_capacity < n) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u chunk descriptors", n);
     Tmp tmp(ctx);
@@ -1006,7 +1144,7 @@ int ivx_object_download(ivx_ctx* ctx, const ivx_object* obj, ivx_chunk_desc* chu
     uint32_t* ord = tmp.get<uint32_t>(n);
     ivx_chunk_desc* d_desc = tmp.get<ivx_chunk_desc>(n);
     if (!flag || !ord || !d_desc) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "download: out of device memory");
-    KL(ctx, launch_nonuniform_flags(obj->d_chunks, n, flag, st));
+    KL(ctx, launch_nonuniform_flags(own_chunks, n, flag, st));
     KL(ctx, launch_exclusive_scan(flag, ord, n, ctx->d_scratch + 28, st));
     uint32_t nnu;
     if (int rc = read_words(ctx, ctx->d_scratch + 28, 1, &nnu)) return rc;
@@ -1016,7 +1154,7 @@ int ivx_object_download(ivx_ctx* ctx, const ivx_object* obj, ivx_chunk_desc* chu
         d_vox = tmp.get<ivx_voxel>(std::max<size_t>(1, (size_t)nnu * 4096));
         if (!d_vox) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "download: out of device memory");
     }
-    KL(ctx, launch_pack_voxels(obj->d_chunks, n, ord, obj->d_voxels, d_vox, d_desc, persistent_grid(ctx, n, 8), st));
+    KL(ctx, launch_pack_voxels(own_chunks, n, ord, obj->d_voxels, d_vox, d_desc, persistent_grid(ctx, n, 8), st));
     CU(ctx, cudaMemcpyAsync(chunks, d_desc, (size_t)n * sizeof(ivx_chunk_desc), cudaMemcpyDeviceToHost, st));
     if (d_vox && nnu) CU(ctx, cudaMemcpyAsync(voxels, d_vox, (size_t)nnu * 4096 * sizeof(ivx_voxel), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
@@ -1031,6 +1169,8 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     ctx->release(obj->d_chunks);
     ctx->release(obj->d_voxels);
     ctx->release(obj->d_dirty);
+    ctx->release(obj->d_slot_of);
+    ctx->release(obj->d_convert_flag);
     delete obj;
 }
 
@@ -1039,6 +1179,8 @@ int ivx_object_mesh(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
     cudaSetDevice(ctx->device);
     std::memset(out, 0, sizeof(*out));
     if (obj->n_chunks == 0) return IVX_OK;
+    if (obj->derive_pending)
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "slab object: call ivx_object_slab_finalize before meshing");
     Tmp tmp(ctx);
     uint32_t* flag = tmp.get<uint32_t>(obj->n_chunks);
     if (!flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh: out of device memory");
@@ -1133,7 +1275,7 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3
     uint32_t* slot_of = tmp.get<uint32_t>(n);
     if (!face_mask || !convert_flag || !need2 || !ord2 || !slot_of) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
     KL(ctx, launch_absorb_face_mask(obj->nb, b, face_mask, n, st));
-    KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, face_mask, convert_flag, st));
+    KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, face_mask, convert_flag, 0, obj->nb[0], st));
     KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need2, st));
     KL(ctx, launch_exclusive_scan(need2, ord2, n, counters + 5, st));
     if (int rc = read_words(ctx, counters, 12, w)) return rc;
@@ -1141,7 +1283,7 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3
     KL(ctx, launch_assign_slots(obj->d_chunks, need2, ord2, obj->slots_used, n, slot_of, st));
     obj->slots_used += w[5];
     KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n,
-                                  persistent_grid(ctx, n, 8), st));
+                                  0, obj->nb[0], persistent_grid(ctx, n, 8), st));
     if (w[4]) {
         // removed chunks → update_occupied_ranges (intersection.rs:387-389)
         KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, counters + 6,

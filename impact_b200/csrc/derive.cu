@@ -51,12 +51,14 @@ __device__ __forceinline__ Neighbour neighbour_of(const DevChunk* __restrict__ c
 
 // face bit: bit (dim, side) of a 6-bit mask, index dim*2+side
 __global__ void k_boundary_classify(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
-                                    const uint8_t* __restrict__ face_mask, uint32_t* __restrict__ convert_flag) {
+                                    const uint8_t* __restrict__ face_mask, uint32_t* __restrict__ convert_flag,
+                                    uint32_t own_lo, uint32_t own_hi) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     uint32_t conv = 0;
     const DevChunk me = chunks[c];
-    if (me.kind == 1) {
+    const uint32_t plane = c / (nb.z * nb.y);
+    if (me.kind == 1 && plane >= own_lo && plane < own_hi) {
         const int k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
         const uint8_t mask = face_mask ? face_mask[c] : 0x3F;
         for (int f = 0; f < 6; ++f) {
@@ -74,14 +76,16 @@ __global__ void __launch_bounds__(256) k_boundary_apply(DevChunk* __restrict__ c
                                                          const uint32_t* __restrict__ convert_flag,
                                                          const uint32_t* __restrict__ slot_of,
                                                          unsigned char* __restrict__ voxels,
-                                                         const uint32_t* __restrict__ work_list, uint32_t n_work) {
+                                                         const uint32_t* __restrict__ work_list, uint32_t n_work,
+                                                         uint32_t own_lo, uint32_t own_hi) {
     __shared__ __align__(16) uint8_t s_flags[4096];
     const int tid = threadIdx.x;
     for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
         const uint32_t c = work_list ? work_list[w] : w;
         DevChunk me = chunks[c];
         const bool converting = convert_flag[c] != 0;
-        if (me.kind != 2 && !converting) continue;  // uniform across the CTA
+        const uint32_t plane = c / (nb.z * nb.y);
+        if ((me.kind != 2 && !converting) || plane < own_lo || plane >= own_hi) continue;  // uniform across the CTA
         const uint8_t mask = face_mask ? face_mask[c] : 0x3F;
         const int ck = c % nb.z, cj = (c / nb.z) % nb.y, ci = c / (nb.z * nb.y);
         unsigned char* slot;
@@ -147,18 +151,19 @@ __global__ void __launch_bounds__(256) k_boundary_apply(DevChunk* __restrict__ c
 }
 
 cudaError_t launch_boundary_classify(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], const uint8_t* face_mask,
-                                     uint32_t* convert_flag, cudaStream_t st) {
+                                     uint32_t* convert_flag, uint32_t own_lo, uint32_t own_hi, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     k_boundary_classify<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), face_mask,
-                                                         convert_flag);
+                                                         convert_flag, own_lo, own_hi);
     return cudaGetLastError();
 }
 cudaError_t launch_boundary_apply(DevChunk* chunks, uint32_t n, const uint32_t nb[3], const uint8_t* face_mask,
                                   const uint32_t* convert_flag, const uint32_t* slot_of, unsigned char* voxels,
-                                  const uint32_t* work_list, uint32_t n_work, uint32_t grid, cudaStream_t st) {
+                                  const uint32_t* work_list, uint32_t n_work, uint32_t own_lo, uint32_t own_hi,
+                                  uint32_t grid, cudaStream_t st) {
     if (n_work == 0) return cudaSuccess;
     k_boundary_apply<<<grid, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), face_mask, convert_flag, slot_of,
-                                           voxels, work_list, n_work);
+                                           voxels, work_list, n_work, own_lo, own_hi);
     return cudaGetLastError();
 }
 

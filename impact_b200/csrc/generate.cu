@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
     if (EXACT && !a.explicit_origins) {
         if ((bc[0] + a.first_chunk[0]) * 16u >= a.gp.grid_shape[0] ||
             (bc[1] + a.first_chunk[1]) * 16u >= a.gp.grid_shape[1] ||
-            (bc[2] + a.first_chunk[2]) * 16u >= a.gp.grid_shape[2] || a.gp.n_nodes == 0) {
+            (bc[2] + a.first_chunk[2]) * 16u >= a.gp.grid_shape[2] || a.gp.n_nodes == 0 || bc[0] < a.own_lo ||
+            bc[0] >= a.own_hi) {
             if (lane == 0) {
                 a.out_len[block] = 0;
                 DevChunk c{};

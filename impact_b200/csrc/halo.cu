@@ -1,0 +1,112 @@
+// Slab-boundary exchange support (multi-GPU, sm_100a).
+//
+// The object is partitioned into x-slabs of chunk planes, one per rank (the reference's own thread
+// split of the x-major linear chunk index, engine/crates/impact_voxel/src/object.rs:423-427).
+// Generation needs no exchange. Derived state and meshing of a rank's outer chunk planes read the
+// neighbouring rank's boundary plane: the 1-voxel brick padding (object/sdf.rs:35, 410-428), the face
+// adjacency / obscuredness rules (object.rs:1682-1704) and, for the "+x neighbour is non-uniform"
+// quad-ownership rule (object/sdf/surface_nets.rs:252-261), that plane's final chunk kinds.
+// These kernels pack a boundary plane into one contiguous buffer (chunk descriptors, then the 12 KiB
+// slots of its non-uniform chunks in plane order) for NCCL send/recv, and unpack it into the halo
+// plane on the receiving side.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ivx {
+
+// one thread per chunk of the plane: non-uniform flag (for the scan that orders the payload)
+__global__ void k_halo_flags(const DevChunk* __restrict__ chunks, uint32_t plane_first, uint32_t plane_chunks,
+                             uint32_t* __restrict__ flag) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= plane_chunks) return;
+    flag[t] = chunks[plane_first + t].kind == 2 ? 1u : 0u;
+}
+
+// CTA per chunk of the plane: descriptor (slot := payload ordinal) + the three planes of its slot
+__global__ void __launch_bounds__(256) k_halo_pack(const DevChunk* __restrict__ chunks, uint32_t plane_first,
+                                                   uint32_t plane_chunks, const uint32_t* __restrict__ ordinal,
+                                                   const unsigned char* __restrict__ voxels, unsigned char* __restrict__ dst) {
+    const uint32_t t = blockIdx.x;
+    if (t >= plane_chunks) return;
+    DevChunk c = chunks[plane_first + t];
+    DevChunk* out_desc = reinterpret_cast<DevChunk*>(dst);
+    unsigned char* payload = dst + (size_t)plane_chunks * sizeof(DevChunk);
+    if (c.kind == 2) {
+        const uint4* src = reinterpret_cast<const uint4*>(voxels + (size_t)c.slot * SLOT_BYTES);
+        uint4* d = reinterpret_cast<uint4*>(payload + (size_t)ordinal[t] * SLOT_BYTES);
+        for (int q = threadIdx.x; q < (int)(SLOT_BYTES / 16); q += blockDim.x) d[q] = src[q];
+    }
+    if (threadIdx.x == 0) {
+        c.slot = c.kind == 2 ? ordinal[t] : 0xFFFFFFFFu;
+        out_desc[t] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_halo_unpack(DevChunk* __restrict__ chunks, uint32_t plane_first,
+                                                     uint32_t plane_chunks, uint32_t first_slot,
+                                                     unsigned char* __restrict__ voxels, const unsigned char* __restrict__ src) {
+    const uint32_t t = blockIdx.x;
+    if (t >= plane_chunks) return;
+    const DevChunk* in_desc = reinterpret_cast<const DevChunk*>(src);
+    const unsigned char* payload = src + (size_t)plane_chunks * sizeof(DevChunk);
+    DevChunk c = in_desc[t];
+    if (c.kind == 2) {
+        const uint32_t slot = first_slot + c.slot;
+        const uint4* s = reinterpret_cast<const uint4*>(payload + (size_t)c.slot * SLOT_BYTES);
+        uint4* d = reinterpret_cast<uint4*>(voxels + (size_t)slot * SLOT_BYTES);
+        for (int q = threadIdx.x; q < (int)(SLOT_BYTES / 16); q += blockDim.x) d[q] = s[q];
+        c.slot = slot;
+    }
+    if (threadIdx.x == 0) {
+        c.pre = PRE_ACTIVE;
+        chunks[plane_first + t] = c;
+    }
+}
+
+// second exchange: whether each chunk of the boundary plane ends up non-uniform (after conversion)
+__global__ void k_halo_kinds_pack(const DevChunk* __restrict__ chunks, const uint32_t* __restrict__ convert_flag,
+                                  uint32_t plane_first, uint32_t plane_chunks, uint8_t* __restrict__ dst) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= plane_chunks) return;
+    const DevChunk c = chunks[plane_first + t];
+    dst[t] = (c.kind == 2 || (c.kind == 1 && convert_flag[plane_first + t])) ? 1 : 0;
+}
+__global__ void k_halo_kinds_unpack(DevChunk* __restrict__ chunks, uint32_t plane_first, uint32_t plane_chunks,
+                                    const uint8_t* __restrict__ src) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= plane_chunks) return;
+    if (src[t] && chunks[plane_first + t].kind == 1) chunks[plane_first + t].pre = PRE_CONVERTED_HALO;
+}
+
+cudaError_t launch_halo_flags(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t* flag,
+                              cudaStream_t st) {
+    if (plane_chunks == 0) return cudaSuccess;
+    k_halo_flags<<<(plane_chunks + 255) / 256, 256, 0, st>>>(chunks, plane_first, plane_chunks, flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_halo_pack(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, const uint32_t* ordinal,
+                             const unsigned char* voxels, unsigned char* dst, cudaStream_t st) {
+    if (plane_chunks == 0) return cudaSuccess;
+    k_halo_pack<<<plane_chunks, 256, 0, st>>>(chunks, plane_first, plane_chunks, ordinal, voxels, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_halo_unpack(DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t first_slot,
+                               unsigned char* voxels, const unsigned char* src, cudaStream_t st) {
+    if (plane_chunks == 0) return cudaSuccess;
+    k_halo_unpack<<<plane_chunks, 256, 0, st>>>(chunks, plane_first, plane_chunks, first_slot, voxels, src);
+    return cudaGetLastError();
+}
+cudaError_t launch_halo_kinds_pack(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t plane_first,
+                                   uint32_t plane_chunks, uint8_t* dst, cudaStream_t st) {
+    if (plane_chunks == 0) return cudaSuccess;
+    k_halo_kinds_pack<<<(plane_chunks + 255) / 256, 256, 0, st>>>(chunks, convert_flag, plane_first, plane_chunks, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_halo_kinds_unpack(DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, const uint8_t* src,
+                                     cudaStream_t st) {
+    if (plane_chunks == 0) return cudaSuccess;
+    k_halo_kinds_unpack<<<(plane_chunks + 255) / 256, 256, 0, st>>>(chunks, plane_first, plane_chunks, src);
+    return cudaGetLastError();
+}
+
+}  // namespace ivx

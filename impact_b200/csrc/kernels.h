@@ -32,6 +32,7 @@ struct FoldArgs {
     uint32_t* error_flag;
     uint32_t prune;           // 1: drop operands that provably cannot influence any voxel of the block
     uint32_t saturate;        // 1: replace a program whose value range quantises to one code by a constant
+    uint32_t own_lo, own_hi;  // exact level: local chunk planes [own_lo, own_hi) are generated, the rest are halo planes
 };
 cudaError_t launch_fold(bool exact, const FoldArgs& a, cudaStream_t st);
 
@@ -74,11 +75,26 @@ cudaError_t launch_scatter_active(const uint32_t* active_flag, const uint32_t* a
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t n, uint32_t v, cudaStream_t st);
 
 // ---- derive.cu ---------------------------------------------------------------
+// own_lo / own_hi: only chunks of local planes [own_lo, own_hi) are classified / updated (halo planes belong to
+// the neighbour rank)
 cudaError_t launch_boundary_classify(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], const uint8_t* face_mask,
-                                     uint32_t* convert_flag, cudaStream_t st);
+                                     uint32_t* convert_flag, uint32_t own_lo, uint32_t own_hi, cudaStream_t st);
 cudaError_t launch_boundary_apply(DevChunk* chunks, uint32_t n, const uint32_t nb[3], const uint8_t* face_mask,
                                   const uint32_t* convert_flag, const uint32_t* slot_of, unsigned char* voxels,
-                                  const uint32_t* work_list, uint32_t n_work, uint32_t grid, cudaStream_t st);
+                                  const uint32_t* work_list, uint32_t n_work, uint32_t own_lo, uint32_t own_hi,
+                                  uint32_t grid, cudaStream_t st);
+
+// ---- halo.cu -----------------------------------------------------------------
+cudaError_t launch_halo_flags(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t* flag,
+                              cudaStream_t st);
+cudaError_t launch_halo_pack(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, const uint32_t* ordinal,
+                             const unsigned char* voxels, unsigned char* dst, cudaStream_t st);
+cudaError_t launch_halo_unpack(DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t first_slot,
+                               unsigned char* voxels, const unsigned char* src, cudaStream_t st);
+cudaError_t launch_halo_kinds_pack(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t plane_first,
+                                   uint32_t plane_chunks, uint8_t* dst, cudaStream_t st);
+cudaError_t launch_halo_kinds_unpack(DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, const uint8_t* src,
+                                     cudaStream_t st);
 
 // ---- mesh.cu -----------------------------------------------------------------
 struct MeshArgs {

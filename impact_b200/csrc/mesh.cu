@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(MESH_THREADS) k_mesh(MeshArgs a) {
             n[tid] += 1;
             uint32_t up = 0;
             if (n[0] < (int)a.nb[0] && n[1] < (int)a.nb[1] && n[2] < (int)a.nb[2])
-                up = a.chunks[(n[0] * a.nb[1] + n[1]) * a.nb[2] + n[2]].kind == 2 ? 1u : 0u;
+            {
+                const DevChunk nc = a.chunks[(n[0] * a.nb[1] + n[1]) * a.nb[2] + n[2]];
+                up = (nc.kind == 2 || (nc.kind == 1 && nc.pre == PRE_CONVERTED_HALO)) ? 1u : 0u;
+            }
             s_adj_up[tid] = up;
         }
         for (int cell = tid; cell < 5832; cell += MESH_THREADS) {

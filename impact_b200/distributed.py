@@ -1,0 +1,236 @@
+"""Multi-GPU orchestration of the voxel hot path: one process per GPU, x-slabs of chunk planes.
+
+The reference parallelises generation over contiguous ranges of the x-major linear chunk index
+(`VoxelObject::generate_without_derived_state_in_parallel`, object.rs:402-470) and meshing over exposed
+chunks (mesh.rs:286-354). The same partition maps onto GPUs as slabs of whole chunk planes:
+
+  * generation needs no communication;
+  * derived state and Surface Nets read one chunk plane of the neighbouring slab (the 1-voxel brick padding,
+    object/sdf.rs:35, and the face rules, object.rs:1682-1704) → ONE point-to-point halo exchange with each
+    neighbour (NCCL send/recv over NVLink), plus one byte per chunk of the upper neighbour's final chunk kinds
+    (quad ownership, surface_nets.rs:252-261);
+  * the per-slab meshes are concatenated on one rank in slab order, which IS the reference's order (chunks
+    are meshed in linear chunk order), with vertex / index offsets rebased.
+
+There is no other collective on the data path. `torch.distributed` is plumbing only: the functions take any
+initialised process group (NCCL on the GPUs, gloo in the CPU tests) and objects exposing the slab protocol
+of `impact_b200.voxel.VoxelObject` (raw-pointer methods), so the host logic is testable without a GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slab_ranges(n_planes: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous chunk-plane ranges per rank: ceil split, like the reference's per-thread split of the
+    linear chunk index (object.rs:423-427). Trailing ranks may be empty when n_planes < world."""
+    per = (n_planes + world - 1) // world if world > 0 else 0
+    return [(min(n_planes, r * per), min(n_planes, (r + 1) * per)) for r in range(world)]
+
+
+def slab_neighbours(ranges: list[tuple[int, int]], rank: int) -> tuple[int | None, int | None]:
+    """Ranks owning the planes just below / above `rank`'s slab (empty slabs are skipped)."""
+    b, e = ranges[rank]
+    if b == e:
+        return None, None
+    lo = next((r for r in range(rank - 1, -1, -1) if ranges[r][0] < ranges[r][1]), None)
+    hi = next((r for r in range(rank + 1, len(ranges)) if ranges[r][0] < ranges[r][1]), None)
+    return lo, hi
+
+
+def _p2p(ops, group):
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def exchange_halos_and_finalize(obj, ranges, rank: int, device, group=None) -> dict:
+    """Runs the slab protocol of include/impact_voxel_cuda.h for this rank's slab object.
+
+    → {"halo_bytes_sent": …, "halo_bytes_received": …}
+    """
+    lo, hi = slab_neighbours(ranges, rank)
+    stats = {"halo_bytes_sent": 0, "halo_bytes_received": 0}
+    if ranges[rank][0] == ranges[rank][1]:
+        return stats
+    peers = [(0, lo), (1, hi)]
+    cap = obj.halo_capacity()
+
+    # exchange A: boundary planes. Sizes first (the payload holds only the non-uniform chunks of the plane).
+    out_buf, out_len, in_len = {}, {}, {}
+    ops = []
+    for side, peer in peers:
+        if peer is None:
+            continue
+        buf = torch.empty(cap, dtype=torch.uint8, device=device)
+        n = obj.halo_export(side, buf.data_ptr(), cap)
+        out_buf[side] = buf[:n]
+        out_len[side] = torch.tensor([n], dtype=torch.int64, device=device)
+        in_len[side] = torch.zeros(1, dtype=torch.int64, device=device)
+        ops.append(dist.P2POp(dist.isend, out_len[side], peer, group))
+        ops.append(dist.P2POp(dist.irecv, in_len[side], peer, group))
+    _p2p(ops, group)
+    in_buf = {}
+    ops = []
+    for side, peer in peers:
+        if peer is None:
+            continue
+        n_in = int(in_len[side].item())
+        in_buf[side] = torch.empty(n_in, dtype=torch.uint8, device=device)
+        ops.append(dist.P2POp(dist.isend, out_buf[side], peer, group))
+        ops.append(dist.P2POp(dist.irecv, in_buf[side], peer, group))
+        stats["halo_bytes_sent"] += int(out_buf[side].numel())
+        stats["halo_bytes_received"] += n_in
+    _p2p(ops, group)
+    for side, buf in in_buf.items():
+        obj.halo_import(side, buf.data_ptr(), int(buf.numel()))
+
+    obj.slab_classify()
+
+    # exchange B: final non-uniform flags of my lowest plane → the rank below (its +x neighbour chunks)
+    plane = obj.plane_chunks()
+    ops = []
+    k_out = k_in = None
+    if lo is not None:
+        k_out = torch.empty(plane, dtype=torch.uint8, device=device)
+        obj.halo_kinds_export(0, k_out.data_ptr(), plane)
+        ops.append(dist.P2POp(dist.isend, k_out, lo, group))
+        stats["halo_bytes_sent"] += plane
+    if hi is not None:
+        k_in = torch.empty(plane, dtype=torch.uint8, device=device)
+        ops.append(dist.P2POp(dist.irecv, k_in, hi, group))
+        stats["halo_bytes_received"] += plane
+    _p2p(ops, group)
+    if k_in is not None:
+        obj.halo_kinds_import(1, k_in.data_ptr(), plane)
+    obj.slab_finalize()
+    return stats
+
+
+# ---- mesh gather -------------------------------------------------------------------------------------------
+MESH_FIELDS = (  # name, trailing shape, torch dtype, "count" key
+    ("positions", (3,), torch.float32, "v"),
+    ("normals", (3,), torch.float32, "v"),
+    ("indices", (), torch.int32, "i"),
+    ("index_materials", (8,), torch.uint8, "i"),
+    ("submeshes", (13,), torch.int32, "s"),
+    ("vertex_ranges", (2,), torch.int32, "s"),
+)
+_SUBMESH_INDEX_OFFSET_COL = 3  # ivx_chunk_submesh.index_offset (include/impact_voxel_cuda.h)
+
+
+class _DeviceArray:
+    """Zero-copy view of a device buffer owned by the library (ivx_mesh_info.d_*) for torch.as_tensor."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def device_mesh_tensors(mesh, device) -> dict:
+    """Wraps the device buffers of a `VoxelObjectMesh` as torch tensors (no copy)."""
+    info = mesh.device_info
+    nv, ni, ns = mesh.n_vertices, mesh.n_indices, mesh.n_submeshes
+
+    def wrap(ptr, shape, typestr, dtype):
+        n = int(np.prod(shape))
+        if n == 0 or not ptr:
+            return torch.empty(shape, dtype=dtype, device=device)
+        return torch.as_tensor(_DeviceArray(ptr, shape, typestr), device=device)
+
+    return {
+        "positions": wrap(info.d_positions, (nv, 3), "<f4", torch.float32),
+        "normals": wrap(info.d_normals, (nv, 3), "<f4", torch.float32),
+        "indices": wrap(info.d_indices, (ni,), "<i4", torch.int32),
+        "index_materials": wrap(info.d_index_materials, (ni, 8), "|u1", torch.uint8),
+        "submeshes": wrap(info.d_submeshes, (ns, 13), "<i4", torch.int32),
+        "vertex_ranges": wrap(info.d_vertex_ranges, (ns, 2), "<i4", torch.int32),
+    }
+
+
+def host_mesh_tensors(mesh: dict) -> dict:
+    """The dict returned by `VoxelObjectMesh.download()` / the oracle as CPU tensors in the gather layout."""
+    return {
+        "positions": torch.from_numpy(np.ascontiguousarray(mesh["positions"], np.float32).reshape(-1, 3)),
+        "normals": torch.from_numpy(np.ascontiguousarray(mesh["normals"], np.float32).reshape(-1, 3)),
+        "indices": torch.from_numpy(np.ascontiguousarray(mesh["indices"]).view(np.int32).reshape(-1)),
+        "index_materials": torch.from_numpy(np.ascontiguousarray(mesh["index_materials"]).view(np.uint8).reshape(-1, 8)),
+        "submeshes": torch.from_numpy(np.ascontiguousarray(mesh["submeshes"]).view(np.int32).reshape(-1, 13)),
+        "vertex_ranges": torch.from_numpy(np.ascontiguousarray(mesh["vertex_ranges"]).view(np.int32).reshape(-1, 2)),
+    }
+
+
+def gather_mesh(parts: dict, rank: int, world: int, device, dst: int = 0, group=None):
+    """Concatenates the per-slab meshes on `dst` in slab (= linear chunk) order (mesh.rs:286-354).
+
+    `parts`: this rank's tensors in the MESH_FIELDS layout. Indices are rebased by the vertex count of the
+    lower slabs, submesh index offsets by their index count, vertex ranges by their vertex count.
+    → the merged dict on `dst`, None elsewhere.
+    """
+    counts = torch.tensor([parts["positions"].shape[0], parts["indices"].shape[0], parts["submeshes"].shape[0]],
+                          dtype=torch.int64, device=device)
+    all_counts = [torch.zeros(3, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    table = torch.stack(all_counts).cpu().numpy()  # [world, 3]
+    key_col = {"v": 0, "i": 1, "s": 2}
+    if rank != dst:
+        ops = [dist.P2POp(dist.isend, parts[name].contiguous(), dst, group)
+               for name, _, _, key in MESH_FIELDS if table[rank, key_col[key]] > 0]
+        _p2p(ops, group)
+        return None
+    totals = table.sum(axis=0)
+    starts = np.concatenate([np.zeros((1, 3), np.int64), np.cumsum(table, axis=0)[:-1]])
+    merged = {name: torch.empty((int(totals[key_col[key]]),) + shape, dtype=dtype, device=device)
+              for name, shape, dtype, key in MESH_FIELDS}
+    ops = []
+    for r in range(world):
+        for name, _, _, key in MESH_FIELDS:
+            n, s = int(table[r, key_col[key]]), int(starts[r, key_col[key]])
+            if n == 0:
+                continue
+            if r == rank:
+                merged[name][s:s + n].copy_(parts[name])
+            else:
+                ops.append(dist.P2POp(dist.irecv, merged[name][s:s + n], r, group))
+    _p2p(ops, group)
+    _rebase(merged, table, starts)
+    return merged
+
+
+def _rebase(merged: dict, table: np.ndarray, starts: np.ndarray) -> None:
+    """Part r's indices / submesh index offsets / vertex ranges become offsets into the merged buffers."""
+    for r in range(len(table)):
+        v0, i0, s0 = (int(x) for x in starts[r])
+        nv, ni, ns = (int(x) for x in table[r])
+        if v0 and ni:
+            merged["indices"][i0:i0 + ni] += v0
+        if ns:
+            if i0:
+                merged["submeshes"][s0:s0 + ns, _SUBMESH_INDEX_OFFSET_COL] += i0
+            if v0:
+                merged["vertex_ranges"][s0:s0 + ns] += v0
+
+
+def concat_meshes(parts_list: list[dict]) -> dict:
+    """Single-process form of `gather_mesh` (several slabs held by one process)."""
+    table = np.array([[p["positions"].shape[0], p["indices"].shape[0], p["submeshes"].shape[0]] for p in parts_list],
+                     np.int64).reshape(-1, 3)
+    starts = np.concatenate([np.zeros((1, 3), np.int64), np.cumsum(table, axis=0)[:-1]])
+    merged = {name: torch.cat([p[name].reshape((-1,) + shape) for p in parts_list]).clone()
+              for name, shape, _, _ in MESH_FIELDS}
+    _rebase(merged, table, starts)
+    return merged
+
+
+def merged_mesh_to_numpy(merged: dict) -> dict:
+    """→ the `VoxelObjectMesh.download()` layout (structured dtypes) for comparisons."""
+    from . import _lib as L
+
+    g = {k: v.cpu().numpy() for k, v in merged.items()}
+    return {
+        "positions": g["positions"], "normals": g["normals"], "indices": g["indices"].view(np.uint32),
+        "index_materials": np.ascontiguousarray(g["index_materials"]).view(L.INDEX_MATERIALS_DTYPE).reshape(-1),
+        "submeshes": np.ascontiguousarray(g["submeshes"]).view(L.SUBMESH_DTYPE).reshape(-1),
+        "vertex_ranges": g["vertex_ranges"].view(np.uint32),
+    }

@@ -146,7 +146,11 @@ class VoxelObject:
 
     @classmethod
     def generate(cls, generator: SDFVoxelGenerator, chunk_i_range=None) -> "VoxelObject":
-        """`VoxelObject::generate` (object.rs:239-244); `chunk_i_range` = x-slab for multi-GPU."""
+        """`VoxelObject::generate` (object.rs:239-244).
+
+        `chunk_i_range` = this rank's x-slab of chunk planes (multi-GPU): the object's cross-chunk derived state
+        then stays pending until `impact_b200.distributed.exchange_halos_and_finalize` (or the slab protocol
+        calls below) has run."""
         ctx = generator.sdf_generator.ctx
         tg = generator.voxel_type_generator.pod()
         h = C.c_void_p()
@@ -189,6 +193,41 @@ class VoxelObject:
             self.ctx.h, self.h, L.ptr(chunks), C.c_size_t(n), L.ptr(voxels) if with_voxels else None,
             C.c_size_t(len(voxels))))
         return chunks, voxels
+
+    # ---- slab protocol (multi-GPU; include/impact_voxel_cuda.h "slab protocol") ----
+    # Buffers are raw DEVICE pointers (int); impact_b200.distributed wraps them in torch tensors for NCCL.
+    def plane_chunks(self) -> int:
+        cc = self.info()["chunk_counts"]
+        return int(cc[1]) * int(cc[2])
+
+    def halo_capacity(self) -> int:
+        n = C.c_size_t()
+        self.ctx.check(self.ctx._lib.ivx_object_halo_capacity(self.ctx.h, self.h, C.byref(n)))
+        return n.value
+
+    def halo_export(self, side: int, device_ptr: int, capacity: int) -> int:
+        n = C.c_size_t()
+        self.ctx.check(self.ctx._lib.ivx_object_halo_export(self.ctx.h, self.h, C.c_int(side), C.c_void_p(device_ptr),
+                                                            C.c_size_t(capacity), C.byref(n)))
+        return n.value
+
+    def halo_import(self, side: int, device_ptr: int, nbytes: int) -> None:
+        self.ctx.check(self.ctx._lib.ivx_object_halo_import(self.ctx.h, self.h, C.c_int(side), C.c_void_p(device_ptr),
+                                                            C.c_size_t(nbytes)))
+
+    def slab_classify(self) -> None:
+        self.ctx.check(self.ctx._lib.ivx_object_slab_classify(self.ctx.h, self.h))
+
+    def halo_kinds_export(self, side: int, device_ptr: int, capacity: int) -> None:
+        self.ctx.check(self.ctx._lib.ivx_object_halo_kinds_export(self.ctx.h, self.h, C.c_int(side), C.c_void_p(device_ptr),
+                                                                  C.c_size_t(capacity)))
+
+    def halo_kinds_import(self, side: int, device_ptr: int, nbytes: int) -> None:
+        self.ctx.check(self.ctx._lib.ivx_object_halo_kinds_import(self.ctx.h, self.h, C.c_int(side), C.c_void_p(device_ptr),
+                                                                  C.c_size_t(nbytes)))
+
+    def slab_finalize(self) -> None:
+        self.ctx.check(self.ctx._lib.ivx_object_slab_finalize(self.ctx.h, self.h))
 
     def absorb_sphere(self, center, radius: float, influence_radius: float) -> dict:
         """`apply_sphere_absorption` (absorption.rs:801-844) in normalized voxel space."""

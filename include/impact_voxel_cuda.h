@@ -250,11 +250,39 @@ int ivx_program_eval_blocks(ivx_ctx* ctx, const ivx_program* program, const floa
 int ivx_object_generate(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
                         const ivx_type_generator* type_generator, ivx_object** out_object);
 /* Multi-GPU: generate only chunk planes [chunk_i_begin, chunk_i_end) of the
- * x-major chunk grid (the reference's thread split, object.rs:423-427) plus
- * one halo chunk plane on each inner side. */
+ * x-major chunk grid (the reference's thread split of the linear chunk index,
+ * object.rs:423-427). The object also reserves one halo chunk plane on each
+ * side that has a neighbouring slab; its cross-chunk derived state
+ * (object.rs:1659-1785) stays pending until the slab protocol below has run:
+ *
+ *   every rank:  generate_slab
+ *   exchange A:  halo_export(side) → send → neighbour's halo_import(1 - side)
+ *   every rank:  slab_classify           (which uniform chunks convert)
+ *   exchange B:  halo_kinds_export(0) → send → lower neighbour's halo_kinds_import(1)
+ *   every rank:  slab_finalize           (adjacency bits, obscuredness)
+ *
+ * after which ivx_object_mesh / ivx_object_download act on the owned planes
+ * and give exactly the rows of the whole object. Exchange B carries the one
+ * bit per chunk that the quad-ownership rule of Surface Nets reads from the +x
+ * neighbour chunk (object/sdf/surface_nets.rs:252-261). Buffers are DEVICE
+ * pointers (send them with NCCL or a peer copy); their layout is private to
+ * this library version. side: 0 = lower chunk-i, 1 = higher. */
 int ivx_object_generate_slab(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
                              const ivx_type_generator* type_generator, uint32_t chunk_i_begin,
                              uint32_t chunk_i_end, ivx_object** out_object);
+/* upper bound of a halo_export in bytes (a whole plane of non-uniform chunks) */
+int ivx_object_halo_capacity(ivx_ctx* ctx, const ivx_object* object, size_t* out_bytes);
+int ivx_object_halo_export(ivx_ctx* ctx, const ivx_object* object, int side, void* device_buffer,
+                           size_t capacity, size_t* out_bytes);
+int ivx_object_halo_import(ivx_ctx* ctx, ivx_object* object, int side, const void* device_buffer,
+                           size_t bytes);
+int ivx_object_slab_classify(ivx_ctx* ctx, ivx_object* object);
+/* one byte per chunk of a plane (chunk_counts[1] * chunk_counts[2] bytes) */
+int ivx_object_halo_kinds_export(ivx_ctx* ctx, const ivx_object* object, int side, void* device_buffer,
+                                 size_t capacity);
+int ivx_object_halo_kinds_import(ivx_ctx* ctx, ivx_object* object, int side, const void* device_buffer,
+                                 size_t bytes);
+int ivx_object_slab_finalize(ivx_ctx* ctx, ivx_object* object);
 int ivx_object_info_get(ivx_ctx* ctx, const ivx_object* object, ivx_object_info* out);
 /* → the Rust-side VoxelObject: chunks[C] in x-major linear order and the voxels
  * of the NonUniform chunks, data_offset = ordinal in that order. */
