@@ -22,86 +22,102 @@ namespace ivx {
 
 constexpr int MESH_THREADS = 256;
 constexpr int N_CUBES = 17 * 17 * 17;
+constexpr int CUBES_PER_THREAD = (N_CUBES + MESH_THREADS - 1) / MESH_THREADS;  // 20
 
+// SurfaceNetsVertexMaterials (surface_nets.rs:440-451) packed into registers: byte q of `idx` / `wgt` is
+// indices[q] / weights[q]; indices[7] holds the material count.
 struct VertexMaterials {
-    uint8_t indices[8];
-    uint8_t weights[8];
+    uint64_t idx, wgt;
 };
 
+__device__ __forceinline__ uint32_t byte_of(uint64_t v, int q) { return (uint32_t)(v >> (8 * q)) & 0xFFu; }
+
 // SurfaceNetsVertexMaterials::compute + sort_descending (surface_nets.rs:453-538)
-__device__ __forceinline__ VertexMaterials vertex_materials(uint32_t neg_mask, const uint8_t* mat) {
-    VertexMaterials m;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) m.indices[q] = m.weights[q] = 0;
+__device__ __noinline__ VertexMaterials vertex_materials(uint32_t neg_mask, const uint8_t* s_type, int lin) {
+    uint64_t idx = 0, wgt = 0;
     int count = 0;
+#pragma unroll
     for (int c = 0; c < 8; ++c) {
         if ((neg_mask >> c) & 1u) {
+            const uint32_t m = s_type[lin + ((c >> 2) & 1) * 324 + ((c >> 1) & 1) * 18 + (c & 1)];
             int found = -1;
-            for (int q = 0; q < count; ++q)
-                if (m.indices[q] == mat[c] && found < 0) found = q;
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+                if (q < count && found < 0 && byte_of(idx, q) == m) found = q;
             if (found < 0) {
-                m.indices[count] = mat[c];
-                m.weights[count] = 1;
+                idx |= (uint64_t)m << (8 * count);
+                wgt |= 1ull << (8 * count);
                 count++;
             } else {
-                m.weights[found] += 1;
+                wgt += 1ull << (8 * found);
             }
         }
     }
-    m.indices[7] = (uint8_t)count;
+    idx |= (uint64_t)count << 56;
     const int NET[17][2] = {{0, 6}, {1, 5}, {2, 4}, {0, 3}, {1, 2}, {4, 5}, {0, 1}, {2, 3}, {4, 6},
                             {5, 6}, {1, 4}, {3, 5}, {1, 2}, {3, 4}, {5, 6}, {2, 3}, {4, 5}};
 #pragma unroll
     for (int s = 0; s < 17; ++s) {
         const int i = NET[s][0], j = NET[s][1];
-        if (m.weights[i] < m.weights[j]) {
-            uint8_t t = m.indices[i]; m.indices[i] = m.indices[j]; m.indices[j] = t;
-            t = m.weights[i]; m.weights[i] = m.weights[j]; m.weights[j] = t;
+        const uint32_t wi = byte_of(wgt, i), wj = byte_of(wgt, j);
+        if (wi < wj) {
+            const uint64_t xw = (uint64_t)(wi ^ wj);
+            wgt ^= (xw << (8 * i)) | (xw << (8 * j));
+            const uint64_t xi = (uint64_t)(byte_of(idx, i) ^ byte_of(idx, j));
+            idx ^= (xi << (8 * i)) | (xi << (8 * j));
         }
     }
-    return m;
+    return VertexMaterials{idx, wgt};
 }
 
-// calculate_index_materials_for_triangle (surface_nets.rs:556-637)
-__device__ __forceinline__ void triangle_index_materials(const VertexMaterials* const vm[3], ivx_index_materials out[3]) {
-    if (vm[0]->indices[7] == 1 && vm[1]->indices[7] == 1 && vm[2]->indices[7] == 1) {
-        const uint8_t index = vm[0]->indices[0];
-        if (vm[1]->indices[0] == index && vm[2]->indices[0] == index) {
-            ivx_index_materials im = {{index, 0, 0, 0}, {1, 0, 0, 0}};
-            out[0] = out[1] = out[2] = im;
+// calculate_index_materials_for_triangle (surface_nets.rs:556-637); out = indices[4] | weights[4] << 32
+__device__ __noinline__ void triangle_index_materials(const VertexMaterials vm[3], uint64_t out[3]) {
+    const uint32_t cnt[3] = {byte_of(vm[0].idx, 7), byte_of(vm[1].idx, 7), byte_of(vm[2].idx, 7)};
+    if (cnt[0] == 1 && cnt[1] == 1 && cnt[2] == 1) {
+        const uint32_t index = byte_of(vm[0].idx, 0);
+        if (byte_of(vm[1].idx, 0) == index && byte_of(vm[2].idx, 0) == index) {
+            out[0] = out[1] = out[2] = (uint64_t)index | (1ull << 32);
             return;
         }
     }
-    uint8_t top[4] = {0, 0, 0, 0};
+    uint32_t top = 0;  // 4 packed bytes
     int n_top = 0;
     int off[3] = {0, 0, 0};
     for (int t = 0; t < 4; ++t) {
-        uint8_t w[3];
-        for (int i = 0; i < 3; ++i) w[i] = vm[i]->weights[off[i]];
+        uint32_t w[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) w[i] = byte_of(vm[i].wgt, off[i]);
         const int mx = (w[0] >= w[1]) ? ((w[0] >= w[2]) ? 0 : 2) : ((w[1] >= w[2]) ? 1 : 2);
-        if (w[mx] == 0) break;
-        top[t] = vm[mx]->indices[off[mx]];
+        const uint32_t wmx = mx == 0 ? w[0] : (mx == 1 ? w[1] : w[2]);
+        if (wmx == 0) break;
+        const uint64_t imx = mx == 0 ? vm[0].idx : (mx == 1 ? vm[1].idx : vm[2].idx);
+        const int omx = mx == 0 ? off[0] : (mx == 1 ? off[1] : off[2]);
+        top |= byte_of(imx, omx) << (8 * t);
         n_top++;
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
             for (;;) {
-                if (off[i] >= (int)vm[i]->indices[7]) break;
-                const uint8_t cand = vm[i]->indices[off[i]];
+                if (off[i] >= (int)cnt[i]) break;
+                const uint32_t cand = byte_of(vm[i].idx, off[i]);
                 bool is_top = false;
-                for (int q = 0; q < n_top; ++q) is_top = is_top || (top[q] == cand);
+                for (int q = 0; q < n_top; ++q) is_top = is_top || (((top >> (8 * q)) & 0xFFu) == cand);
                 if (!is_top) break;
                 off[i]++;
             }
         }
     }
+#pragma unroll
     for (int v = 0; v < 3; ++v) {
-        ivx_index_materials im = {{top[0], top[1], top[2], top[3]}, {0, 0, 0, 0}};
-        for (int i = 0; i < n_top; ++i)
-            for (int j = 0; j < (int)vm[v]->indices[7]; ++j)
-                if (vm[v]->indices[j] == top[i]) {
-                    im.weights[i] = vm[v]->weights[j];
+        uint32_t weights = 0;
+        for (int i = 0; i < n_top; ++i) {
+            const uint32_t want = (top >> (8 * i)) & 0xFFu;
+            for (int j = 0; j < (int)cnt[v]; ++j)
+                if (byte_of(vm[v].idx, j) == want) {
+                    weights |= byte_of(vm[v].wgt, j) << (8 * i);
                     break;
                 }
-        out[v] = im;
+        }
+        out[v] = (uint64_t)top | ((uint64_t)weights << 32);
     }
 }
 
@@ -132,11 +148,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(MESH_THREADS) k_mesh(MeshArgs a) {
+__global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
     __shared__ __align__(16) int8_t s_sd[5832];
     __shared__ __align__(16) uint8_t s_type[5832];
     __shared__ uint16_t s_l2v[EMIT ? 5832 : 1];
     __shared__ uint16_t s_surf[N_CUBES];
+    __shared__ uint8_t s_vmat[EMIT ? N_CUBES : 1];
     __shared__ uint32_t s_warp[MESH_THREADS / 32];
     __shared__ uint32_t s_adj_up[3];
 
@@ -193,73 +210,113 @@ __global__ void __launch_bounds__(MESH_THREADS) k_mesh(MeshArgs a) {
         const bool skip_emit = EMIT && a.index_count[w] == 0u;  // empty mesh: nothing is appended (mesh.rs:319-321)
 
         // ---- vertex pass: estimate_surface_nets_surface (surface_nets.rs:152-244) ----
+        // 1) compact the surface cubes in cube order (i → j → k), which is the reference's vertex order:
+        //    each thread owns CUBES_PER_THREAD consecutive cubes, one block scan places them
         uint32_t n_vertices = 0;
-        for (int base = 0; base < N_CUBES; base += MESH_THREADS) {
-            const int q = base + tid;
-            uint32_t neg = 0;
-            int lin = 0, i = 0, j = 0, k = 0;
-            if (q < N_CUBES) {
-                i = q / 289;
-                j = (q / 17) % 17;
-                k = q % 17;
-                lin = bidx(i, j, k);
+        {
+            const int q0 = tid * CUBES_PER_THREAD;
+            int i = q0 / 289, j = (q0 / 17) % 17, k = q0 % 17;
+            const int i0 = i, j0 = j, k0 = k;
+            uint32_t smask = 0;
+#pragma unroll 4
+            for (int u = 0; u < CUBES_PER_THREAD; ++u) {
+                if (q0 + u < N_CUBES) {
+                    const int lin = bidx(i, j, k);
+                    uint32_t neg = 0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) neg |= (s_sd[lin + corner_off(c)] < 0 ? 1u : 0u) << c;
-            }
-            const bool surf = q < N_CUBES && neg != 0u && neg != 0xFFu;
-            uint32_t tile_total;
-            const uint32_t pre = block_exclusive_scan(surf ? 1u : 0u, s_warp, tile_total);
-            if (surf) {
-                const uint32_t v = n_vertices + pre;
-                s_surf[v] = (uint16_t)lin;
-                if (EMIT && !skip_emit) {
-                    s_l2v[lin] = (uint16_t)v;
-                    float d[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) d[c] = sd_decode((int)s_sd[lin + corner_off(c)]);
-                    // centroid_of_edge_intersections (surface_nets.rs:384-418)
-                    const int E[12][2] = {{0, 1}, {0, 2}, {0, 4}, {1, 3}, {1, 5}, {2, 3},
-                                          {2, 6}, {3, 7}, {4, 5}, {4, 6}, {5, 7}, {6, 7}};
-                    int count = 0;
-                    f3 sum = mk3(0.0f, 0.0f, 0.0f);
-#pragma unroll
-                    for (int e = 0; e < 12; ++e) {
-                        const int c1 = E[e][0], c2 = E[e][1];
-                        if (((neg >> c1) ^ (neg >> c2)) & 1u) {
-                            count++;
-                            const float interp1 = d[c1] / (d[c1] - d[c2]);
-                            const float interp2 = 1.0f - interp1;
-                            f3 p1 = mk3((float)((c1 >> 2) & 1), (float)((c1 >> 1) & 1), (float)(c1 & 1));
-                            f3 p2 = mk3((float)((c2 >> 2) & 1), (float)((c2 >> 1) & 1), (float)(c2 & 1));
-                            sum = sum + (interp2 * p1 + interp1 * p2);
-                        }
+                    for (int c = 0; c < 8; ++c) neg |= (s_sd[lin + corner_off(c)] < 0 ? 1u : 0u) << c;
+                    if (neg != 0u && neg != 0xFFu) smask |= 1u << u;
+                }
+                if (++k == 17) {
+                    k = 0;
+                    if (++j == 17) {
+                        j = 0;
+                        ++i;
                     }
-                    const float fc = (float)count;
-                    const f3 o = mk3(sum.x / fc, sum.y / fc, sum.z / fc);
-                    // compute_sdf_gradient_from_corner_samples (object/sdf.rs:603-633)
-                    const f3 r = mk3(1.0f - o.x, 1.0f - o.y, 1.0f - o.z);
-                    const f3 d00 = mk3(d[4] - d[0], d[2] - d[0], d[1] - d[0]);
-                    const f3 d01 = mk3(d[5] - d[1], d[6] - d[4], d[3] - d[2]);
-                    const f3 d10 = mk3(d[6] - d[2], d[3] - d[1], d[5] - d[4]);
-                    const f3 d11 = mk3(d[7] - d[3], d[7] - d[5], d[7] - d[6]);
-                    // rev.yzx * rev.zxy * d00 + rev.yzx * o.zxy * d01 + o.yzx * rev.zxy * d10 + o.yzx * o.zxy * d11
-                    f3 g;
-                    g.x = (((r.y * r.z) * d00.x + (r.y * o.z) * d01.x) + (o.y * r.z) * d10.x) + (o.y * o.z) * d11.x;
-                    g.y = (((r.z * r.x) * d00.y + (r.z * o.x) * d01.y) + (o.z * r.x) * d10.y) + (o.z * o.x) * d11.y;
-                    g.z = (((r.x * r.y) * d00.z + (r.x * o.y) * d01.z) + (o.x * r.y) * d10.z) + (o.x * o.y) * d11.z;
-                    const float len = norm3(g);
-                    const f3 nrm = mk3(g.x / len, g.y / len, g.z / len);
-                    const f3 pos = mk3(extent * (o.x + (float)i) + offset.x, extent * (o.y + (float)j) + offset.y,
-                                       extent * (o.z + (float)k) + offset.z);
-                    float* P = a.positions + 3 * (size_t)(voff + v);
-                    float* N = a.normals + 3 * (size_t)(voff + v);
-                    P[0] = pos.x; P[1] = pos.y; P[2] = pos.z;
-                    N[0] = nrm.x; N[1] = nrm.y; N[2] = nrm.z;
                 }
             }
-            n_vertices += tile_total;
+            uint32_t v = block_exclusive_scan(__popc(smask), s_warp, n_vertices);
+            i = i0, j = j0, k = k0;
+            for (int u = 0; u < CUBES_PER_THREAD && smask; ++u) {
+                if ((smask >> u) & 1u) {
+                    const int lin = bidx(i, j, k);
+                    s_surf[v] = (uint16_t)lin;
+                    if (EMIT) s_l2v[lin] = (uint16_t)v;
+                    ++v;
+                }
+                if (++k == 17) {
+                    k = 0;
+                    if (++j == 17) {
+                        j = 0;
+                        ++i;
+                    }
+                }
+            }
         }
         __syncthreads();
+
+        // 2) one thread per surface vertex (dense lanes): position, normal, material summary
+        if (EMIT && !skip_emit) {
+            for (uint32_t v = tid; v < n_vertices; v += MESH_THREADS) {
+                const int lin = s_surf[v];
+                const int i = lin / 324, j = (lin / 18) % 18, k = lin % 18;
+                float d[8];
+                uint32_t neg = 0;
+                uint32_t mat_first = 256u;
+                bool single = true;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int code = (int)s_sd[lin + corner_off(c)];
+                    d[c] = sd_decode(code);
+                    if (code < 0) {
+                        neg |= 1u << c;
+                        const uint32_t m = s_type[lin + corner_off(c)];
+                        if (mat_first == 256u) mat_first = m;
+                        single = single && (m == mat_first);
+                    }
+                }
+                s_vmat[v] = single ? (uint8_t)mat_first : (uint8_t)255;  // 255 = several materials (types are < 255)
+                // centroid_of_edge_intersections (surface_nets.rs:384-418)
+                const int E[12][2] = {{0, 1}, {0, 2}, {0, 4}, {1, 3}, {1, 5}, {2, 3},
+                                      {2, 6}, {3, 7}, {4, 5}, {4, 6}, {5, 7}, {6, 7}};
+                int count = 0;
+                f3 sum = mk3(0.0f, 0.0f, 0.0f);
+#pragma unroll
+                for (int e = 0; e < 12; ++e) {
+                    const int c1 = E[e][0], c2 = E[e][1];
+                    if (((neg >> c1) ^ (neg >> c2)) & 1u) {
+                        count++;
+                        const float interp1 = d[c1] / (d[c1] - d[c2]);
+                        const float interp2 = 1.0f - interp1;
+                        f3 p1 = mk3((float)((c1 >> 2) & 1), (float)((c1 >> 1) & 1), (float)(c1 & 1));
+                        f3 p2 = mk3((float)((c2 >> 2) & 1), (float)((c2 >> 1) & 1), (float)(c2 & 1));
+                        sum = sum + (interp2 * p1 + interp1 * p2);
+                    }
+                }
+                const float fc = (float)count;
+                const f3 o = mk3(sum.x / fc, sum.y / fc, sum.z / fc);
+                // compute_sdf_gradient_from_corner_samples (object/sdf.rs:603-633)
+                const f3 r = mk3(1.0f - o.x, 1.0f - o.y, 1.0f - o.z);
+                const f3 d00 = mk3(d[4] - d[0], d[2] - d[0], d[1] - d[0]);
+                const f3 d01 = mk3(d[5] - d[1], d[6] - d[4], d[3] - d[2]);
+                const f3 d10 = mk3(d[6] - d[2], d[3] - d[1], d[5] - d[4]);
+                const f3 d11 = mk3(d[7] - d[3], d[7] - d[5], d[7] - d[6]);
+                // rev.yzx * rev.zxy * d00 + rev.yzx * o.zxy * d01 + o.yzx * rev.zxy * d10 + o.yzx * o.zxy * d11
+                f3 g;
+                g.x = (((r.y * r.z) * d00.x + (r.y * o.z) * d01.x) + (o.y * r.z) * d10.x) + (o.y * o.z) * d11.x;
+                g.y = (((r.z * r.x) * d00.y + (r.z * o.x) * d01.y) + (o.z * r.x) * d10.y) + (o.z * o.x) * d11.y;
+                g.z = (((r.x * r.y) * d00.z + (r.x * o.y) * d01.z) + (o.x * r.y) * d10.z) + (o.x * o.y) * d11.z;
+                const float len = norm3(g);
+                const f3 nrm = mk3(g.x / len, g.y / len, g.z / len);
+                const f3 pos = mk3(extent * (o.x + (float)i) + offset.x, extent * (o.y + (float)j) + offset.y,
+                                   extent * (o.z + (float)k) + offset.z);
+                float* P = a.positions + 3 * (size_t)(voff + v);
+                float* N = a.normals + 3 * (size_t)(voff + v);
+                P[0] = pos.x; P[1] = pos.y; P[2] = pos.z;
+                N[0] = nrm.x; N[1] = nrm.y; N[2] = nrm.z;
+            }
+            __syncthreads();
+        }
 
         // ---- quad pass: make_all_surface_nets_quads (surface_nets.rs:251-381) ----
         const int up0 = 17 - (int)s_adj_up[0], up1 = 17 - (int)s_adj_up[1], up2 = 17 - (int)s_adj_up[2];
@@ -280,49 +337,64 @@ __global__ void __launch_bounds__(MESH_THREADS) k_mesh(MeshArgs a) {
             const uint32_t pre = block_exclusive_scan(__popc(qmask), s_warp, tile_total);
             if (EMIT && !skip_emit && qmask) {
                 uint32_t qi = n_quads + pre;
-                const bool n1 = s_sd[lin] < 0;
-#pragma unroll
+                // d1 negative, d2 positive → negative_face = false (surface_nets.rs:345-349)
+                const bool negative_face = !(s_sd[lin] < 0);
+#pragma unroll 1
                 for (int ax = 0; ax < 3; ++ax) {
                     if (!((qmask >> ax) & 1u)) continue;
                     const int axb = ax == 0 ? 18 : (ax == 1 ? 1 : 324);
                     const int axc = ax == 0 ? 1 : (ax == 1 ? 324 : 18);
-                    // d1 negative, d2 positive → negative_face = false (surface_nets.rs:345-349)
-                    const bool negative_face = !n1;
                     const int cl[4] = {lin, lin - axb, lin - axc, lin - axb - axc};
                     uint32_t vid[4];
                     f3 p[4];
-                    VertexMaterials vm[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         vid[c] = s_l2v[cl[c]];
                         const float* P = a.positions + 3 * (size_t)(voff + vid[c]);
                         p[c] = mk3(P[0], P[1], P[2]);
-                        uint32_t neg = 0;
-                        uint8_t mat[8];
-#pragma unroll
-                        for (int cc = 0; cc < 8; ++cc) {
-                            neg |= (s_sd[cl[c] + corner_off(cc)] < 0 ? 1u : 0u) << cc;
-                            mat[cc] = s_type[cl[c] + corner_off(cc)];
-                        }
-                        vm[c] = vertex_materials(neg, mat);
                     }
-                    int order[6];
-                    if (norm3(p[0] - p[3]) < norm3(p[1] - p[2])) {
-                        if (negative_face) { order[0]=0; order[1]=3; order[2]=1; order[3]=0; order[4]=2; order[5]=3; }
-                        else               { order[0]=0; order[1]=1; order[2]=3; order[3]=0; order[4]=3; order[5]=2; }
-                    } else if (negative_face) { order[0]=1; order[1]=2; order[2]=3; order[3]=1; order[4]=0; order[5]=2; }
-                    else                      { order[0]=1; order[1]=3; order[2]=2; order[3]=1; order[4]=2; order[5]=0; }
+                    // triangle corner → quad corner, 3 bits each: [t0c0 t0c1 t0c2 t1c0 t1c1 t1c2]
+                    uint32_t order;
+                    if (norm3(p[0] - p[3]) < norm3(p[1] - p[2]))
+                        order = negative_face ? (0u | 3u << 3 | 1u << 6 | 0u << 9 | 2u << 12 | 3u << 15)
+                                              : (0u | 1u << 3 | 3u << 6 | 0u << 9 | 3u << 12 | 2u << 15);
+                    else
+                        order = negative_face ? (1u | 2u << 3 | 3u << 6 | 1u << 9 | 0u << 12 | 2u << 15)
+                                              : (1u | 3u << 3 | 2u << 6 | 1u << 9 | 2u << 12 | 0u << 15);
                     uint32_t* I = a.indices + (size_t)ioff + 6 * (size_t)qi;
-                    ivx_index_materials* IM = a.index_materials + (size_t)ioff + 6 * (size_t)qi;
+                    uint64_t* IM = reinterpret_cast<uint64_t*>(a.index_materials + (size_t)ioff + 6 * (size_t)qi);
 #pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const VertexMaterials* tv[3] = {&vm[order[3 * t]], &vm[order[3 * t + 1]], &vm[order[3 * t + 2]]};
-                        ivx_index_materials im[3];
-                        triangle_index_materials(tv, im);
+                    for (int c = 0; c < 6; ++c) {
+                        const uint32_t sel = (order >> (3 * c)) & 3u;
+                        I[c] = voff + (sel == 0 ? vid[0] : (sel == 1 ? vid[1] : (sel == 2 ? vid[2] : vid[3])));
+                    }
+                    const uint32_t m0 = s_vmat[vid[0]], m1 = s_vmat[vid[1]], m2 = s_vmat[vid[2]], m3 = s_vmat[vid[3]];
+                    if (m0 != 255u && m0 == m1 && m0 == m2 && m0 == m3) {
+                        // every vertex has the one material: {index, 0, 0, 0} / {1, 0, 0, 0} (surface_nets.rs:563-577)
+                        const uint64_t im = (uint64_t)m0 | (1ull << 32);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            I[3 * t + c] = voff + vid[order[3 * t + c]];
-                            IM[3 * t + c] = im[c];
+                        for (int c = 0; c < 6; ++c) IM[c] = im;
+                    } else {
+                        VertexMaterials vm[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t neg = 0;
+#pragma unroll
+                            for (int cc = 0; cc < 8; ++cc) neg |= (s_sd[cl[c] + corner_off(cc)] < 0 ? 1u : 0u) << cc;
+                            vm[c] = vertex_materials(neg, s_type, cl[c]);
+                        }
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            VertexMaterials tv[3];
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const uint32_t sel = (order >> (3 * (3 * t + c))) & 3u;
+                                tv[c] = sel == 0 ? vm[0] : (sel == 1 ? vm[1] : (sel == 2 ? vm[2] : vm[3]));
+                            }
+                            uint64_t im[3];
+                            triangle_index_materials(tv, im);
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) IM[3 * t + c] = im[c];
                         }
                     }
                     qi++;
