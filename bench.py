@@ -31,6 +31,15 @@ METRIC = "voxels_per_sec_generated_and_meshed"
 UNIT = "voxels/s"
 
 
+_JSON_OUT = None
+
+
+def emit(obj: dict):
+    f = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
 # ---------------------------------------------------------------------------------------------
 def make_workload(name: str):
     """→ (graph, type generator, description). Host only."""
@@ -167,7 +176,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": last["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -320,7 +329,7 @@ def run_gpu(args):
         dom_avg_s = (dom_ms / max(1, dom_n)) * 1e-3
         # algorithmic bytes (dense definition): generation writes 3 B per grid voxel, meshing
         # reads 2 B per grid voxel; one launch of a kernel processes this rank's whole slab
-        per_voxel = {"eval": 3.0, "fold_exact": 3.0, "fold_conservative": 3.0, "mesh_count": 2.0, "mesh_emit": 2.0,
+        per_voxel = {"eval": 3.0, "types": 3.0, "fold_exact": 3.0, "fold_conservative": 3.0, "mesh_count": 2.0, "mesh_emit": 2.0,
                      "boundary": 3.0}.get(dom, 5.0)
         achieved = per_voxel * my_voxels / max(dom_avg_s, 1e-12) / 1e9
         traffic = None
@@ -365,7 +374,7 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = {k: v for k, v in cpu_reference(graph, types, 12.0, os.cpu_count() or 1).items()
                                    if k != "seconds"}
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -380,6 +389,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 while the bench runs
+    # (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) is sent to stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

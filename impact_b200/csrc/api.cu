@@ -486,6 +486,19 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     uint32_t egrid = 1;
     if (int rc = plan_eval_stack(ctx, max_depth, tmp, n_active, ea, egrid)) return rc;
     if (n_active) KLP(ctx, 2, launch_eval(ea, egrid, st));
+    if (n_active) {
+        TypesArgs ta{};
+        ta.gp = gp;
+        ta.n_active = n_active;
+        ta.active = active_list;
+        for (int d = 0; d < 3; ++d) ta.nb[d] = obj->nb[d];
+        ta.first_i = obj->first_i;
+        ta.slot_of = slot_of;
+        ta.voxels = obj->d_voxels;
+        ta.chunks = obj->d_chunks;
+        ta.occ = counters + 2;
+        KLP(ctx, 7, launch_types(ta, persistent_grid(ctx, n_active, std::max(1, types_max_blocks_per_sm())), st));
+    }
 
     // ---- cross-chunk derived state ----
     if (whole) {

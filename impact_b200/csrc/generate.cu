@@ -21,21 +21,6 @@
 
 namespace ivx {
 
-__constant__ uint8_t c_perm[256] = {
-    151, 160, 137, 91,  90,  15,  131, 13,  201, 95,  96,  53,  194, 233, 7,   225, 140, 36,  103,
-    30,  69,  142, 8,   99,  37,  240, 21,  10,  23,  190, 6,   148, 247, 120, 234, 75,  0,   26,
-    197, 62,  94,  252, 219, 203, 117, 35,  11,  32,  57,  177, 33,  88,  237, 149, 56,  87,  174,
-    20,  125, 136, 171, 168, 68,  175, 74,  165, 71,  134, 139, 48,  27,  166, 77,  146, 158, 231,
-    83,  111, 229, 122, 60,  211, 133, 230, 220, 105, 92,  41,  55,  46,  245, 40,  244, 102, 143,
-    54,  65,  25,  63,  161, 1,   216, 80,  73,  209, 76,  132, 187, 208, 89,  18,  169, 200, 196,
-    135, 130, 116, 188, 159, 86,  164, 100, 109, 198, 173, 186, 3,   64,  52,  217, 226, 250, 124,
-    123, 5,   202, 38,  147, 118, 126, 255, 82,  85,  212, 207, 206, 59,  227, 47,  16,  58,  17,
-    182, 189, 28,  42,  223, 183, 170, 213, 119, 248, 152, 2,   44,  154, 163, 70,  221, 153, 101,
-    155, 167, 43,  172, 9,   129, 22,  39,  253, 19,  98,  108, 110, 79,  113, 224, 232, 178, 185,
-    112, 104, 218, 246, 97,  228, 251, 34,  242, 193, 238, 210, 144, 12,  191, 179, 162, 241, 81,
-    51,  145, 235, 249, 14,  239, 107, 49,  192, 214, 31,  181, 199, 106, 157, 184, 84,  204, 176,
-    115, 121, 50,  45,  127, 4,   150, 254, 138, 236, 205, 93,  222, 114, 67,  29,  24,  72,  243,
-    141, 128, 195, 78,  66,  215, 61,  156, 180};
 
 // ---------------------------------------------------------------------------
 // Noise frame of a MultifractalNoise node for one block
@@ -69,10 +54,6 @@ __device__ __forceinline__ float noise_at(const ivx_node& n, float freq, f3 pos)
 // 8-wide vector then += 8, and y / z (our j / i) by repeated += 1.0.
 __device__ __forceinline__ float block_noise_x(float start, int k) {
     return k < 8 ? start + (float)k : (start + (float)(k - 8)) + 8.0f;
-}
-__device__ __forceinline__ float accumulate_ones(float start, int n) {
-    for (int t = 0; t < n; ++t) start = start + 1.0f;
-    return start;
 }
 __device__ __forceinline__ float noise_for_voxel(const ivx_node& n, const NoiseFrame& f, int i, int j, int k) {
     if (f.rotated) {
@@ -635,15 +616,6 @@ __device__ __forceinline__ float* stack_level(float* smem_stack, float* spill, i
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_stack = reinterpret_cast<float*>(smem_raw);
-    __shared__ __align__(16) int8_t s_sd[4096];
-    __shared__ uint32_t s_cnt[16];
-    __shared__ uint8_t s_first_type;
-    // permutation table of the 4-D simplex noise: thread-divergent byte gathers are serialised by
-    // the constant cache, shared memory serves them at bank-conflict cost only
-    __shared__ uint8_t s_perm[256];
-    if (threadIdx.x < 256) s_perm[threadIdx.x] = c_perm[threadIdx.x];
-    __syncthreads();
-
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tj = tid & 15;
     float* spill = a.spill ? a.spill + (size_t)blockIdx.x * a.spill_levels * 4096 : nullptr;
@@ -770,190 +742,38 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
         }
 
         // ---- quantise + classify (generation.rs:330-357) ----
-        if (tid < 16) s_cnt[tid] = (tid >= 6 && tid < 9) ? 0xFFFFFFFFu : 0u;
-        __syncthreads();
         const bool col_in = (org[0] + ti < a.gp.grid_shape[0]) && (org[1] + tj < a.gp.grid_shape[1]);
-        uint32_t empty_mask = 0, void_mask = 0, m128_mask = 0;
-        int8_t codes[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            int c = 127;
-            bool in_grid = col_in && (org[2] + k < a.gp.grid_shape[2]);
-            if (in_grid) c = sd_encode(top[k]);
-            codes[k] = (int8_t)c;
-            if (c >= 0) empty_mask |= 1u << k;
-            // out-of-grid voxels do not influence is_void (generation.rs:336-340)
-            if (!in_grid || c > 100) void_mask |= 1u << k;
-            if (c == -128) m128_mask |= 1u << k;
-        }
+        uint32_t void_mask = 0;
+        uint4 pk;
         {
-            uint4 pk;
             uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                w[q] = (uint32_t)(uint8_t)codes[4 * q] | ((uint32_t)(uint8_t)codes[4 * q + 1] << 8) |
-                       ((uint32_t)(uint8_t)codes[4 * q + 2] << 16) | ((uint32_t)(uint8_t)codes[4 * q + 3] << 24);
-            *reinterpret_cast<uint4*>(&s_sd[tid * 16]) = pk;
+            for (int q = 0; q < 4; ++q) w[q] = 0u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                int c = 127;
+                const bool in_grid = col_in && (org[2] + k < a.gp.grid_shape[2]);
+                if (in_grid) c = sd_encode(top[k]);
+                // out-of-grid voxels do not influence is_void (generation.rs:336-340)
+                if (!in_grid || c > 100) void_mask |= 1u << k;
+                w[k >> 2] |= (uint32_t)(uint8_t)(int8_t)c << (8 * (k & 3));
+            }
         }
-        const int any_nonempty = __syncthreads_or(empty_mask != 0xFFFFu);
         const int all_void = __syncthreads_and(void_mask == 0xFFFFu);
-        const int all_m128 = __syncthreads_and(m128_mask == 0xFFFFu);
 
-        DevChunk cd = a.chunks[chunk];
         if (all_void) {
             if (tid == 0) {
+                DevChunk cd = a.chunks[chunk];
                 cd.kind = 0;
                 cd.pre = PRE_VOID;
                 cd.flags = 0;
                 a.chunks[chunk] = cd;
             }
-            __syncthreads();
-            continue;
-        }
-
-        // ---- voxel types (generation.rs:359-365, voxel_type.rs) ----
-        uint8_t types[16];
-        if (!any_nonempty) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) types[k] = 255;
-        } else if (a.gp.types.kind == 0) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) types[k] = (uint8_t)a.gp.types.same_type;
         } else {
-            // gradient_4d_offset(0, n, o.z, 16, o.y, 16, o.x, 16): x = type axis,
-            // y / z / w = our k / j / i, each walked by repeated += 1.0
-            const float ft = a.gp.types.voxel_type_frequency, fn = a.gp.types.noise_frequency;
-            const int32_t seed = (int32_t)a.gp.types.seed;
-            const float wc = accumulate_ones(lo.x, ti) * fn;
-            const float zc = accumulate_ones(lo.y, tj) * fn;
-            float yacc = lo.z;
-            for (int k = 0; k < 16; ++k) {
-                const float yc = yacc * fn;
-                float best = 0.0f;
-                uint32_t best_t = 0;
-                for (uint32_t t = 0; t < a.gp.types.n_types; ++t) {
-                    float xc = 0.0f + (float)(t & 7u);
-                    for (uint32_t v = 0; v < (t >> 3); ++v) xc = xc + 8.0f;
-                    float nv = simplex4_t(xc * ft, yc, zc, wc, seed, s_perm);
-                    if (t == 0 || nv > best) {
-                        best = nv;
-                        best_t = t;
-                    }
-                }
-                types[k] = (uint8_t)best_t;
-                yacc = yacc + 1.0f;
-            }
-        }
-
-        // uniform ⇔ every voxel is maximally inside with the same type (object.rs:1913-1918)
-        if (all_m128) {
-            if (tid == 0) s_first_type = types[0];
-            __syncthreads();
-            bool same_cta = true;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) same_cta = same_cta && (types[k] == s_first_type);
-            const int uniform = __syncthreads_and(same_cta);
-            if (uniform) {
-                if (tid == 0) {
-                    cd.kind = 1;
-                    cd.pre = PRE_UNIFORM;
-                    cd.u_type = s_first_type;
-                    cd.u_sd = -128;
-                    cd.u_flags = 0xFC;
-                    cd.flags = 0;
-                    a.chunks[chunk] = cd;
-                    if (a.occ) {
-                        for (int d = 0; d < 3; ++d) {
-                            atomicMin(&a.occ[d], org[d]);
-                            atomicMax(&a.occ[3 + d], org[d] + 15u);
-                        }
-                    }
-                }
-                __syncthreads();
-                continue;
-            }
-        }
-
-        // ---- flags: IS_EMPTY + in-chunk adjacency (object.rs:2673-2756 on fresh voxels) ----
-        uint8_t flags[16];
-        {
-            auto nonempty_at = [&](int i, int j, int k) -> bool { return s_sd[vidx(i, j, k)] < 0; };
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                uint8_t f = 0;
-                if (codes[k] >= 0) {
-                    f = 1;  // IS_EMPTY; empty voxels carry no in-chunk adjacency bits
-                } else {
-                    if (ti > 0 && nonempty_at(ti - 1, tj, k)) f |= 1u << 2;
-                    if (tj > 0 && nonempty_at(ti, tj - 1, k)) f |= 1u << 3;
-                    if (k > 0 && codes[k - 1] < 0) f |= 1u << 4;
-                    if (ti < 15 && nonempty_at(ti + 1, tj, k)) f |= 1u << 5;
-                    if (tj < 15 && nonempty_at(ti, tj + 1, k)) f |= 1u << 6;
-                    if (k < 15 && codes[k + 1] < 0) f |= 1u << 7;
-                }
-                flags[k] = f;
-            }
-        }
-
-        // ---- face empty counts → FaceVoxelDistribution (object.rs:1920-1936, 2967-2981) ----
-        {
-            const uint32_t ne = __popc(empty_mask);
-            if (ti == 0) atomicAdd(&s_cnt[0], ne);
-            if (ti == 15) atomicAdd(&s_cnt[1], ne);
-            if (tj == 0) atomicAdd(&s_cnt[2], ne);
-            if (tj == 15) atomicAdd(&s_cnt[3], ne);
-            if (empty_mask & 1u) atomicAdd(&s_cnt[4], 1u);
-            if (empty_mask & 0x8000u) atomicAdd(&s_cnt[5], 1u);
-            // bounding range of non-empty voxels (object.rs:1187-1280)
-            const uint32_t nonempty = (~empty_mask) & 0xFFFFu;
-            if (nonempty) {
-                atomicMin(&s_cnt[6], (uint32_t)ti);
-                atomicMin(&s_cnt[7], (uint32_t)tj);
-                atomicMin(&s_cnt[8], (uint32_t)(__ffs(nonempty) - 1));
-                atomicMax(&s_cnt[9], (uint32_t)ti);
-                atomicMax(&s_cnt[10], (uint32_t)tj);
-                atomicMax(&s_cnt[11], (uint32_t)(31 - __clz(nonempty)));
-            }
-        }
-        __syncthreads();
-
-        // ---- store the three planes: 16 B per thread per plane, fully coalesced ----
-        {
+            // the chunk stays PRE_ACTIVE: k_types assigns voxel types, flags and the chunk descriptor
             unsigned char* slot = a.voxels + (size_t)a.slot_of[chunk] * SLOT_BYTES;
-            *reinterpret_cast<uint4*>(slot + PLANE_SD + tid * 16) = *reinterpret_cast<uint4*>(&s_sd[tid * 16]);
-            uint4 pt, pf;
-            uint32_t* wt = reinterpret_cast<uint32_t*>(&pt);
-            uint32_t* wf = reinterpret_cast<uint32_t*>(&pf);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                wt[q] = (uint32_t)types[4 * q] | ((uint32_t)types[4 * q + 1] << 8) | ((uint32_t)types[4 * q + 2] << 16) |
-                        ((uint32_t)types[4 * q + 3] << 24);
-                wf[q] = (uint32_t)flags[4 * q] | ((uint32_t)flags[4 * q + 1] << 8) | ((uint32_t)flags[4 * q + 2] << 16) |
-                        ((uint32_t)flags[4 * q + 3] << 24);
-            }
-            *reinterpret_cast<uint4*>(slot + PLANE_TYPE + tid * 16) = pt;
-            *reinterpret_cast<uint4*>(slot + PLANE_FLAGS + tid * 16) = pf;
+            *reinterpret_cast<uint4*>(slot + PLANE_SD + tid * 16) = pk;
         }
-        if (tid == 0) {
-            cd.kind = 2;
-            cd.pre = PRE_ACTIVE;
-            cd.slot = a.slot_of[chunk];
-            if (!any_nonempty) {
-                for (int q = 0; q < 6; ++q) cd.face[q] = 0;
-                cd.flags = 1u << 6;  // HAS_ONLY_EMPTY_VOXELS
-            } else {
-                for (int q = 0; q < 6; ++q) cd.face[q] = s_cnt[q] == 256u ? 0 : (s_cnt[q] == 0u ? 1 : 2);
-                cd.flags = 0;
-                if (a.occ) {
-                    for (int d = 0; d < 3; ++d) {
-                        atomicMin(&a.occ[d], org[d] + s_cnt[6 + d]);
-                        atomicMax(&a.occ[3 + d], org[d] + s_cnt[9 + d]);
-                    }
-                }
-            }
-            a.chunks[chunk] = cd;
-        }
-        __syncthreads();
     }
 }
 

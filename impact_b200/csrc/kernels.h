@@ -62,6 +62,21 @@ int eval_max_blocks_per_sm(int smem_levels);
 cudaError_t launch_eval_blocks(const ivx_node* nodes, uint32_t n_nodes, const float* origins, uint32_t n_blocks, int size,
                                float* out, cudaStream_t st);
 
+// ---- types.cu ----------------------------------------------------------------
+struct TypesArgs {
+    GenParams gp;
+    uint32_t n_active;
+    const uint32_t* active;   // compacted chunk indices (null → identity)
+    uint32_t nb[3];
+    uint32_t first_i;
+    const uint32_t* slot_of;  // per chunk
+    unsigned char* voxels;
+    DevChunk* chunks;
+    uint32_t* occ;
+};
+cudaError_t launch_types(const TypesArgs& a, uint32_t grid, cudaStream_t st);
+int types_max_blocks_per_sm();
+
 // ---- scan.cu ----------------------------------------------------------------
 // Exclusive prefix sums over small arrays (chunk-count sized), single CTA.
 cudaError_t launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total, cudaStream_t st);

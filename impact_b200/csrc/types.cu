@@ -1,0 +1,475 @@
+// Voxel types and per-voxel derived flags (sm_100a).
+//
+//   k_types  second half of chunk generation, for every chunk k_eval left non-void:
+//            voxel types (generation.rs:359-365, voxel_type.rs:54-168), uniform detection
+//            (object.rs:1913-1918), IS_EMPTY + in-chunk adjacency flags (object.rs:2673-2756),
+//            face distributions (object.rs:1920-1936, 2967-2981), occupied ranges
+//            (object.rs:1187-1280); writes the type and flag planes.
+//
+// GradientNoise types are the arg-max over `n_types` evaluations of simdnoise's 4-D simplex noise
+// per voxel — for a 1024³ asteroid that is ~10⁹ evaluations and the largest single cost of the whole
+// path. The per-voxel arithmetic cannot be shared between voxels without changing rounding, but the
+// *lattice* part can: a 16³ chunk at the usual frequencies touches only a few simplex cells, so the
+// permutation-table hash chain (4 dependent byte gathers per corner, 5 corners per evaluation) and the
+// gradient selection it feeds are hoisted into a per-chunk table of gradient vectors, one float4 in
+// {-1, 0, +1}⁴ per lattice point. A corner's gradient dot product then is
+//     g.x·x + (g.y·y + (g.z·z + g.w·w))
+// which reproduces simdnoise's `a + (b + c)` of sign-selected components exactly: multiplying by ±1 is
+// exact, and the one zero term only ever adds ±0. Differences are confined to the sign of an exact
+// zero, which no comparison downstream can see (the result only feeds `noise > max_noise`).
+// Corner ranks are computed as small floats so that almost all of the work runs on the FMA pipe
+// (FADD / FMUL / FFMA / IMAD) instead of the half-rate ALU pipe (ISETP / SEL / LOP3).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ivx {
+
+constexpr int TYPES_THREADS = 256;
+constexpr int TAB_CAP = 1024;        // gradient-table entries (float4) per batch of types
+constexpr int MAX_TYPES = 255;
+constexpr float CELL_LIMIT = 4096.0f;  // |cell index| < 2^12 and strides <= 2^9: every integer-valued f32 term stays below 2^22
+constexpr float MAGIC = 12582912.0f;      // 1.5 * 2^23: (small integer + MAGIC) keeps the integer in the low mantissa bits
+constexpr uint32_t MAGIC_BITS = 0x4B400000u;
+
+struct TypeTab {   // per-type constants of the table walk
+    float x;       // noise x coordinate of this type (already multiplied by voxel_type_frequency)
+    float base;    // MAGIC - entry index of the first lattice cell
+    float sa, sb, sc;  // strides of axes 0..2 in entries (axis 3 has stride 1)
+    float s4;      // sa + sb + sc + 1: entry step to the far corner
+    uint32_t addr; // shared-memory byte address of entry 0, minus 16 * MAGIC_BITS
+};
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// simdnoise simplex_4d (see common.cuh simplex4_t for the direct restatement) with the gradient of
+// each corner read from the chunk's lattice table.
+__device__ __forceinline__ float simplex4_tab(float x, float y, float z, float w, const TypeTab& T) {
+    const float F4 = 0.309016994f, G4 = 0.138196601f;
+    const float G24 = 2.0f * 0.138196601f, G34 = 3.0f * 0.138196601f, G44 = 4.0f * 0.138196601f;
+    const float s = F4 * (x + (y + (z + w)));
+    const float ips = floorf(x + s), jps = floorf(y + s), kps = floorf(z + s), lps = floorf(w + s);
+    // (float)(i + (j + (k + l))): the cell indices are small integers, so the f32 sum is exact
+    const float t = (ips + (jps + (kps + lps))) * G4;
+    const float x0 = x - (ips - t), y0 = y - (jps - t), z0 = z - (kps - t), w0 = w - (lps - t);
+
+    // ranks (how many of the other coordinates each one exceeds), as exact small floats
+    const float pxy = x0 > y0 ? 1.0f : 0.0f, pxz = x0 > z0 ? 1.0f : 0.0f, pxw = x0 > w0 ? 1.0f : 0.0f;
+    const float pyz = y0 > z0 ? 1.0f : 0.0f, pyw = y0 > w0 ? 1.0f : 0.0f, pzw = z0 > w0 ? 1.0f : 0.0f;
+    const float rx = (pxy + pxz) + pxw;
+    const float ry = ((1.0f - pxy) + pyz) + pyw;
+    const float rz = ((2.0f - pxz) - pyz) + pzw;
+    const float rw = ((6.0f - rx) - ry) - rz;
+    // corner c steps along the axes whose rank exceeds 3 - c (compares run on the ALU pipe, which
+    // this kernel leaves mostly idle)
+    const float i1 = rx > 2.5f ? 1.0f : 0.0f, j1 = ry > 2.5f ? 1.0f : 0.0f, k1 = rz > 2.5f ? 1.0f : 0.0f,
+                l1 = rw > 2.5f ? 1.0f : 0.0f;
+    const float i2 = rx > 1.5f ? 1.0f : 0.0f, j2 = ry > 1.5f ? 1.0f : 0.0f, k2 = rz > 1.5f ? 1.0f : 0.0f,
+                l2 = rw > 1.5f ? 1.0f : 0.0f;
+    const float i3 = fminf(rx, 1.0f), j3 = fminf(ry, 1.0f), k3 = fminf(rz, 1.0f), l3 = fminf(rw, 1.0f);
+
+    // table addresses: entry = ((a·Db + b)·Dc + c)·Dd + d relative to the first cell, accumulated on top
+    // of MAGIC so that the integer sits in the low mantissa bits (T.base = MAGIC - first cell's entry; all
+    // terms are integers below 2^22, so every FMA is exact); one IMAD turns the bits into an address
+    const float e0 = __fmaf_rn(ips, T.sa, __fmaf_rn(jps, T.sb, __fmaf_rn(kps, T.sc, lps + T.base)));
+    const float e1 = __fmaf_rn(i1, T.sa, __fmaf_rn(j1, T.sb, __fmaf_rn(k1, T.sc, l1 + e0)));
+    const float e2 = __fmaf_rn(i2, T.sa, __fmaf_rn(j2, T.sb, __fmaf_rn(k2, T.sc, l2 + e0)));
+    const float e3 = __fmaf_rn(i3, T.sa, __fmaf_rn(j3, T.sb, __fmaf_rn(k3, T.sc, l3 + e0)));
+    const float e4 = e0 + T.s4;
+    const float4 g0 = lds128(__float_as_uint(e0) * 16u + T.addr);
+    const float4 g1 = lds128(__float_as_uint(e1) * 16u + T.addr);
+    const float4 g2 = lds128(__float_as_uint(e2) * 16u + T.addr);
+    const float4 g3 = lds128(__float_as_uint(e3) * 16u + T.addr);
+    const float4 g4 = lds128(__float_as_uint(e4) * 16u + T.addr);
+
+    const float x1 = (x0 - i1) + G4, y1 = (y0 - j1) + G4, z1 = (z0 - k1) + G4, w1 = (w0 - l1) + G4;
+    const float x2 = (x0 - i2) + G24, y2 = (y0 - j2) + G24, z2 = (z0 - k2) + G24, w2 = (w0 - l2) + G24;
+    const float x3 = (x0 - i3) + G34, y3 = (y0 - j3) + G34, z3 = (z0 - k3) + G34, w3 = (w0 - l3) + G34;
+    const float x4 = (x0 - 1.0f) + G44, y4 = (y0 - 1.0f) + G44, z4 = (z0 - 1.0f) + G44, w4 = (w0 - 1.0f) + G44;
+
+    float t0 = (((0.5f - x0 * x0) - y0 * y0) - z0 * z0) - w0 * w0;
+    float t1 = (((0.5f - x1 * x1) - y1 * y1) - z1 * z1) - w1 * w1;
+    float t2 = (((0.5f - x2 * x2) - y2 * y2) - z2 * z2) - w2 * w2;
+    float t3 = (((0.5f - x3 * x3) - y3 * y3) - z3 * z3) - w3 * w3;
+    float t4 = (((0.5f - x4 * x4) - y4 * y4) - z4 * z4) - w4 * w4;
+    // a corner with t < 0 contributes 0: clamping t first makes its term ±0 instead
+    t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); t2 = fmaxf(t2, 0.0f); t3 = fmaxf(t3, 0.0f); t4 = fmaxf(t4, 0.0f);
+    float q0 = t0 * t0, q1 = t1 * t1, q2 = t2 * t2, q3 = t3 * t3, q4 = t4 * t4;
+    q0 = q0 * q0; q1 = q1 * q1; q2 = q2 * q2; q3 = q3 * q3; q4 = q4 * q4;
+    const float n0 = q0 * (g0.x * x0 + (g0.y * y0 + (g0.z * z0 + g0.w * w0)));
+    const float n1 = q1 * (g1.x * x1 + (g1.y * y1 + (g1.z * z1 + g1.w * w1)));
+    const float n2 = q2 * (g2.x * x2 + (g2.y * y2 + (g2.z * z2 + g2.w * w2)));
+    const float n3 = q3 * (g3.x * x3 + (g3.y * y3 + (g3.z * z3 + g3.w * w3)));
+    const float n4 = q4 * (g4.x * x4 + (g4.y * y4 + (g4.z * z4 + g4.w * w4)));
+    return (n0 + (n1 + (n2 + (n3 + n4)))) * 62.77772078955791f;
+}
+
+// the lattice cell of a noise-space point, exactly as simplex4 computes it
+__device__ __forceinline__ void simplex4_cell(float x, float y, float z, float w, float c[4]) {
+    const float F4 = 0.309016994f;
+    const float s = F4 * (x + (y + (z + w)));
+    c[0] = floorf(x + s);
+    c[1] = floorf(y + s);
+    c[2] = floorf(z + s);
+    c[3] = floorf(w + s);
+}
+
+// simdnoise grad4 (common.cuh) as a vector: grad = g · (x, y, z, t)
+__device__ __forceinline__ float4 grad4_vector(int32_t h) {
+    const float sa = (h & 1) ? -1.0f : 1.0f, sb = (h & 2) ? -1.0f : 1.0f, sc = (h & 4) ? -1.0f : 1.0f;
+    if (h < 8) return make_float4(sa, sb, sc, 0.0f);    // (x, y, z)
+    if (h < 16) return make_float4(sa, sb, 0.0f, sc);   // (x, y, t)
+    if (h < 24) return make_float4(sa, 0.0f, sb, sc);   // (x, z, t)
+    return make_float4(0.0f, sa, sb, sc);               // (y, z, t)
+}
+
+// x coordinate of type t: simdnoise walks x as start + lane inside one 8-wide vector, then += 8
+__device__ __forceinline__ float type_axis_coordinate(uint32_t t) {
+    float xc = 0.0f + (float)(t & 7u);
+    for (uint32_t v = 0; v < (t >> 3); ++v) xc = xc + 8.0f;
+    return xc;
+}
+
+struct TypesSmem {
+    float4 tab[TAB_CAP];
+    float best[16 * TYPES_THREADS];     // [k][thread]
+    uint8_t best_t[16 * TYPES_THREADS];
+    int8_t sd[4096];
+    int cmin[MAX_TYPES + 1][4];
+    int cmax[MAX_TYPES + 1][4];
+    uint16_t tab_off[MAX_TYPES + 1];    // entry offset of the type's table inside its batch
+    uint8_t new_batch[MAX_TYPES + 1];
+    uint8_t perm[256];
+    uint32_t cnt[16];
+    int fallback;
+    uint8_t first_type;
+};
+
+__global__ void __launch_bounds__(TYPES_THREADS) k_types(TypesArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TypesSmem& S = *reinterpret_cast<TypesSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int ti = tid >> 4, tj = tid & 15;
+    S.perm[tid] = c_perm[tid];
+    __syncthreads();
+    const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(&S.tab[0]);
+    const uint32_t n_types = a.gp.types.n_types;
+
+    for (uint32_t work = blockIdx.x; work < a.n_active; work += gridDim.x) {
+        const uint32_t chunk = a.active ? a.active[work] : work;
+        DevChunk cd = a.chunks[chunk];
+        if (cd.pre != PRE_ACTIVE) continue;  // k_eval found the chunk void (block-uniform branch)
+        const uint32_t slot = a.slot_of[chunk];
+        unsigned char* slot_ptr = a.voxels + (size_t)slot * SLOT_BYTES;
+
+        uint32_t org[3];
+        {
+            const uint32_t ck = chunk % a.nb[2], cj = (chunk / a.nb[2]) % a.nb[1], ci = chunk / (a.nb[2] * a.nb[1]);
+            org[0] = (ci + a.first_i) * 16u;
+            org[1] = cj * 16u;
+            org[2] = ck * 16u;
+        }
+        const f3 lo = mk3((float)org[0] - a.gp.shifted_center[0], (float)org[1] - a.gp.shifted_center[1],
+                          (float)org[2] - a.gp.shifted_center[2]);
+
+        // ---- the chunk's signed-distance codes (written by k_eval) ----
+        const uint4 pk = *reinterpret_cast<const uint4*>(slot_ptr + PLANE_SD + tid * 16);
+        *reinterpret_cast<uint4*>(&S.sd[tid * 16]) = pk;
+        int8_t codes[16];
+        {
+            const uint32_t* wv = reinterpret_cast<const uint32_t*>(&pk);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) codes[k] = (int8_t)((wv[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+        }
+        uint32_t empty_mask = 0, m128_mask = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (codes[k] >= 0) empty_mask |= 1u << k;
+            if (codes[k] == -128) m128_mask |= 1u << k;
+        }
+        if (tid < 16) S.cnt[tid] = (tid >= 6 && tid < 9) ? 0xFFFFFFFFu : 0u;
+        const int any_nonempty = __syncthreads_or(empty_mask != 0xFFFFu);
+        const int all_m128 = __syncthreads_and(m128_mask == 0xFFFFu);
+
+        // ---- voxel types (generation.rs:359-365, voxel_type.rs) ----
+        uint8_t types[16];
+        if (!any_nonempty) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) types[k] = 255;
+        } else if (a.gp.types.kind == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) types[k] = (uint8_t)a.gp.types.same_type;
+        } else {
+            // gradient_4d_offset(0, n, o.z, 16, o.y, 16, o.x, 16): x = type axis,
+            // y / z / w = our k / j / i, each walked by repeated += 1.0
+            const float ft = a.gp.types.voxel_type_frequency, fn = a.gp.types.noise_frequency;
+            const int32_t seed = (int32_t)a.gp.types.seed;
+            const float wc = accumulate_ones(lo.x, ti) * fn;
+            const float zc = accumulate_ones(lo.y, tj) * fn;
+
+            // ---- lattice cells touched by the chunk, per type: the cell of a voxel is monotone in each
+            // voxel index (every step of the computation is a monotone f32 operation), so the 8 corner
+            // voxels bound it ----
+            for (uint32_t q = tid; q < n_types * 4u; q += TYPES_THREADS) {
+                S.cmin[q >> 2][q & 3] = INT_MAX;
+                S.cmax[q >> 2][q & 3] = INT_MIN;
+            }
+            if (tid == 0) S.fallback = 0;
+            __syncthreads();
+            for (uint32_t q = tid; q < n_types * 8u; q += TYPES_THREADS) {
+                const uint32_t t = q >> 3, cv = q & 7u;
+                const float x = type_axis_coordinate(t) * ft;
+                const float w = accumulate_ones(lo.x, (cv & 4u) ? 15 : 0) * fn;
+                const float z = accumulate_ones(lo.y, (cv & 2u) ? 15 : 0) * fn;
+                const float y = accumulate_ones(lo.z, (cv & 1u) ? 15 : 0) * fn;
+                float c[4];
+                simplex4_cell(x, y, z, w, c);
+                bool ok = true;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) ok = ok && (fabsf(c[d]) < CELL_LIMIT);  // false for NaN too
+                if (!ok) {
+                    S.fallback = 1;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        atomicMin(&S.cmin[t][d], (int)c[d]);
+                        atomicMax(&S.cmax[t][d], (int)c[d]);
+                    }
+                }
+            }
+            __syncthreads();
+            // batches of types whose tables fit TAB_CAP together (sequential, n_types <= 255)
+            if (tid == 0 && !S.fallback) {
+                uint32_t run = 0;
+                for (uint32_t t = 0; t < n_types; ++t) {
+                    uint64_t e = 1;
+                    for (int d = 0; d < 4; ++d) e *= (uint64_t)((int64_t)S.cmax[t][d] - S.cmin[t][d] + 2);
+                    if (e > (uint64_t)TAB_CAP) {
+                        S.fallback = 1;
+                        break;
+                    }
+                    const bool nb = (t == 0) || (run + (uint32_t)e > (uint32_t)TAB_CAP);
+                    if (nb) run = 0;
+                    S.new_batch[t] = nb ? 1 : 0;
+                    S.tab_off[t] = (uint16_t)run;
+                    run += (uint32_t)e;
+                }
+            }
+            __syncthreads();
+
+            if (S.fallback) {
+                // cells too spread out (very high frequencies) or out of the exact-integer range:
+                // direct evaluation with the permutation table, as in common.cuh
+                float yacc = lo.z;
+                for (int k = 0; k < 16; ++k) {
+                    const float yc = yacc * fn;
+                    float best = 0.0f;
+                    uint32_t best_t = 0;
+                    for (uint32_t t = 0; t < n_types; ++t) {
+                        const float nv = simplex4_t(type_axis_coordinate(t) * ft, yc, zc, wc, seed, S.perm);
+                        if (t == 0 || nv > best) {
+                            best = nv;
+                            best_t = t;
+                        }
+                    }
+                    types[k] = (uint8_t)best_t;
+                    yacc = yacc + 1.0f;
+                }
+            } else {
+                uint32_t t0 = 0;
+                while (t0 < n_types) {
+                    uint32_t t1 = t0 + 1;
+                    while (t1 < n_types && !S.new_batch[t1]) ++t1;
+                    // ---- gradient table of the batch ----
+                    {
+                        uint32_t n_entries = S.tab_off[t1 - 1];
+                        {
+                            uint32_t e = 1;
+                            for (int d = 0; d < 4; ++d) e *= (uint32_t)(S.cmax[t1 - 1][d] - S.cmin[t1 - 1][d] + 2);
+                            n_entries += e;
+                        }
+                        uint32_t t = t0;
+                        for (uint32_t e = tid; e < n_entries; e += TYPES_THREADS) {
+                            while (t + 1 < t1 && e >= S.tab_off[t + 1]) ++t;
+                            uint32_t r = e - S.tab_off[t];
+                            const uint32_t Dd = (uint32_t)(S.cmax[t][3] - S.cmin[t][3] + 2);
+                            const uint32_t Dc = (uint32_t)(S.cmax[t][2] - S.cmin[t][2] + 2);
+                            const uint32_t Db = (uint32_t)(S.cmax[t][1] - S.cmin[t][1] + 2);
+                            const uint32_t d3 = r % Dd; r /= Dd;
+                            const uint32_t d2 = r % Dc; r /= Dc;
+                            const uint32_t d1 = r % Db; r /= Db;
+                            const uint32_t d0 = r;
+                            const int32_t I = S.cmin[t][0] + (int32_t)d0, J = S.cmin[t][1] + (int32_t)d1,
+                                          K = S.cmin[t][2] + (int32_t)d2, L = S.cmin[t][3] + (int32_t)d3;
+                            int32_t g = S.perm[L & 255];
+                            g = S.perm[((K & 255) + g) & 255];
+                            g = S.perm[((J & 255) + g) & 255];
+                            g = S.perm[((I & 255) + g) & 255];
+                            S.tab[e] = grad4_vector((seed ^ g) & 31);
+                        }
+                    }
+                    __syncthreads();
+                    // ---- evaluate the batch's types over this thread's k-column ----
+                    for (uint32_t t = t0; t < t1; ++t) {
+                        TypeTab T;
+                        T.x = type_axis_coordinate(t) * ft;
+                        const uint32_t Dd = (uint32_t)(S.cmax[t][3] - S.cmin[t][3] + 2);
+                        const uint32_t Dc = (uint32_t)(S.cmax[t][2] - S.cmin[t][2] + 2);
+                        const uint32_t Db = (uint32_t)(S.cmax[t][1] - S.cmin[t][1] + 2);
+                        T.sc = (float)Dd;
+                        T.sb = (float)(Dd * Dc);
+                        T.sa = (float)(Dd * Dc * Db);
+                        T.s4 = (float)(Dd * Dc * Db + Dd * Dc + Dd + 1u);
+                        T.base = MAGIC - (((float)S.cmin[t][0] * T.sa + (float)S.cmin[t][1] * T.sb) +
+                                          ((float)S.cmin[t][2] * T.sc + (float)S.cmin[t][3]));
+                        T.addr = tab_base + (uint32_t)S.tab_off[t] * 16u - MAGIC_BITS * 16u;
+                        float yacc = lo.z;
+#pragma unroll 2
+                        for (int k = 0; k < 16; ++k) {
+                            const float nv = simplex4_tab(T.x, yacc * fn, zc, wc, T);
+                            const int bi = k * TYPES_THREADS + tid;
+                            if (t == 0 || nv > S.best[bi]) {
+                                S.best[bi] = nv;
+                                S.best_t[bi] = (uint8_t)t;
+                            }
+                            yacc = yacc + 1.0f;
+                        }
+                    }
+                    __syncthreads();  // the table is rebuilt by the next batch
+                    t0 = t1;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) types[k] = S.best_t[k * TYPES_THREADS + tid];
+            }
+        }
+
+        // uniform ⇔ every voxel is maximally inside with the same type (object.rs:1913-1918)
+        if (all_m128) {
+            if (tid == 0) S.first_type = types[0];
+            __syncthreads();
+            bool same_cta = true;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) same_cta = same_cta && (types[k] == S.first_type);
+            const int uniform = __syncthreads_and(same_cta);
+            if (uniform) {
+                if (tid == 0) {
+                    cd.kind = 1;
+                    cd.pre = PRE_UNIFORM;
+                    cd.u_type = S.first_type;
+                    cd.u_sd = -128;
+                    cd.u_flags = 0xFC;
+                    cd.flags = 0;
+                    a.chunks[chunk] = cd;
+                    if (a.occ) {
+                        for (int d = 0; d < 3; ++d) {
+                            atomicMin(&a.occ[d], org[d]);
+                            atomicMax(&a.occ[3 + d], org[d] + 15u);
+                        }
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+        }
+
+        // ---- flags: IS_EMPTY + in-chunk adjacency (object.rs:2673-2756 on fresh voxels) ----
+        uint8_t flags[16];
+        {
+            auto nonempty_at = [&](int i, int j, int k) -> bool { return S.sd[vidx(i, j, k)] < 0; };
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                uint8_t f = 0;
+                if (codes[k] >= 0) {
+                    f = 1;  // IS_EMPTY; empty voxels carry no in-chunk adjacency bits
+                } else {
+                    if (ti > 0 && nonempty_at(ti - 1, tj, k)) f |= 1u << 2;
+                    if (tj > 0 && nonempty_at(ti, tj - 1, k)) f |= 1u << 3;
+                    if (k > 0 && codes[k - 1] < 0) f |= 1u << 4;
+                    if (ti < 15 && nonempty_at(ti + 1, tj, k)) f |= 1u << 5;
+                    if (tj < 15 && nonempty_at(ti, tj + 1, k)) f |= 1u << 6;
+                    if (k < 15 && codes[k + 1] < 0) f |= 1u << 7;
+                }
+                flags[k] = f;
+            }
+        }
+
+        // ---- face empty counts → FaceVoxelDistribution (object.rs:1920-1936, 2967-2981) ----
+        {
+            const uint32_t ne = __popc(empty_mask);
+            if (ti == 0) atomicAdd(&S.cnt[0], ne);
+            if (ti == 15) atomicAdd(&S.cnt[1], ne);
+            if (tj == 0) atomicAdd(&S.cnt[2], ne);
+            if (tj == 15) atomicAdd(&S.cnt[3], ne);
+            if (empty_mask & 1u) atomicAdd(&S.cnt[4], 1u);
+            if (empty_mask & 0x8000u) atomicAdd(&S.cnt[5], 1u);
+            // bounding range of non-empty voxels (object.rs:1187-1280)
+            const uint32_t nonempty = (~empty_mask) & 0xFFFFu;
+            if (nonempty) {
+                atomicMin(&S.cnt[6], (uint32_t)ti);
+                atomicMin(&S.cnt[7], (uint32_t)tj);
+                atomicMin(&S.cnt[8], (uint32_t)(__ffs(nonempty) - 1));
+                atomicMax(&S.cnt[9], (uint32_t)ti);
+                atomicMax(&S.cnt[10], (uint32_t)tj);
+                atomicMax(&S.cnt[11], (uint32_t)(31 - __clz(nonempty)));
+            }
+        }
+        __syncthreads();
+
+        // ---- store the type and flag planes: 16 B per thread per plane, fully coalesced ----
+        {
+            uint4 pt, pf;
+            uint32_t* wt = reinterpret_cast<uint32_t*>(&pt);
+            uint32_t* wf = reinterpret_cast<uint32_t*>(&pf);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                wt[q] = (uint32_t)types[4 * q] | ((uint32_t)types[4 * q + 1] << 8) | ((uint32_t)types[4 * q + 2] << 16) |
+                        ((uint32_t)types[4 * q + 3] << 24);
+                wf[q] = (uint32_t)flags[4 * q] | ((uint32_t)flags[4 * q + 1] << 8) | ((uint32_t)flags[4 * q + 2] << 16) |
+                        ((uint32_t)flags[4 * q + 3] << 24);
+            }
+            *reinterpret_cast<uint4*>(slot_ptr + PLANE_TYPE + tid * 16) = pt;
+            *reinterpret_cast<uint4*>(slot_ptr + PLANE_FLAGS + tid * 16) = pf;
+        }
+        if (tid == 0) {
+            cd.kind = 2;
+            cd.pre = PRE_ACTIVE;
+            cd.slot = slot;
+            if (!any_nonempty) {
+                for (int q = 0; q < 6; ++q) cd.face[q] = 0;
+                cd.flags = 1u << 6;  // HAS_ONLY_EMPTY_VOXELS
+            } else {
+                for (int q = 0; q < 6; ++q) cd.face[q] = S.cnt[q] == 256u ? 0 : (S.cnt[q] == 0u ? 1 : 2);
+                cd.flags = 0;
+                if (a.occ) {
+                    for (int d = 0; d < 3; ++d) {
+                        atomicMin(&a.occ[d], org[d] + S.cnt[6 + d]);
+                        atomicMax(&a.occ[3 + d], org[d] + S.cnt[9 + d]);
+                    }
+                }
+            }
+            a.chunks[chunk] = cd;
+        }
+        __syncthreads();
+    }
+}
+
+size_t types_smem_bytes() { return sizeof(TypesSmem); }
+
+int types_max_blocks_per_sm() {
+    int nb = 0;
+    cudaFuncSetAttribute(k_types, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TypesSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_types, TYPES_THREADS, sizeof(TypesSmem));
+    return nb;
+}
+
+cudaError_t launch_types(const TypesArgs& a, uint32_t grid, cudaStream_t st) {
+    if (a.n_active == 0 || grid == 0) return cudaSuccess;
+    cudaFuncSetAttribute(k_types, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TypesSmem));
+    k_types<<<grid, TYPES_THREADS, sizeof(TypesSmem), st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace ivx

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Runs on the GPU box (via gpurun): GPU parity tests, then a short bench; summaries go to gpurun_out/<tag>_*.
+tag=${1:-check}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${tag}_gputests.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+tail -8 gpurun_out/${tag}_gputests.log
+python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${tag}_bench.json"))
+    print("ms/step", d["ms_per_step"], "e2e ms", d["e2e"]["ms_per_step"])
+    print(d["kernel_ms_per_step"])
+except Exception as e:
+    print("bench failed:", e)
+PY
+tail -5 gpurun_out/${tag}_bench.err
