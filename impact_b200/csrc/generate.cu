@@ -16,6 +16,8 @@
 // made first (warp per chunk, 14 lanes = 14 sampled voxels), constant
 // sub-trees are folded, dropped operands are never evaluated, and only the
 // surviving instructions are run on all voxels — with identical results.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -616,6 +618,8 @@ __device__ __forceinline__ float* stack_level(float* smem_stack, float* spill, i
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_stack = reinterpret_cast<float*>(smem_raw);
+    __shared__ float s_coord[48];
+    __shared__ uint32_t s_wsum[EVAL_THREADS / 32];
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tj = tid & 15;
     float* spill = a.spill ? a.spill + (size_t)blockIdx.x * a.spill_levels * 4096 : nullptr;
@@ -689,7 +693,94 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                 const float lac = n.p[1], gain = n.p[2];
                 const uint32_t oct = n.octaves;
                 const int32_t seed = (int32_t)n.seed;
-                if (f.rotated) {
+                if (final_sat && !f.rotated) {
+                    // ---- compacted, octave-by-octave evaluation ----
+                    // After octaves 0..o the remaining ones can move the result by at most
+                    // |noise_scale| * sum_{i>o} gain^i (|simplex3| <= 1), so a voxel whose partial value is further
+                    // than that beyond the saturated code range is finished. The surviving voxels of the whole
+                    // chunk are compacted into a dense list each octave, so that lanes do not idle beside a few
+                    // unfinished neighbours. The arithmetic of a surviving voxel is fbm3's, operation for operation.
+                    float* res = s_stack;                                            // [k][thread] partial fBm sums
+                    uint16_t* list = reinterpret_cast<uint16_t*>(s_stack + 4096);    // voxel indices still needed
+                    const uint32_t n_oct = max(oct & 0xFFu, 1u);
+                    float total = 1.0f;  // sum of the octave amplitudes
+                    {
+                        float am = 1.0f;
+                        for (uint32_t o = 1; o < n_oct; ++o) {
+                            am = am * gain;
+                            total = total + am;
+                        }
+                    }
+                    uint32_t mask = 0xFFFFu;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float v = top[k];
+                        if (v - A >= 2.5401f) { top[k] = 1000.0f; mask &= ~(1u << k); }
+                        else if (v + A <= -2.5601f) { top[k] = -1000.0f; mask &= ~(1u << k); }
+                    }
+                    __syncthreads();  // stack levels are free: this is the last instruction (sp == 1)
+                    if (tid < 16) {
+                        s_coord[tid] = block_noise_x(f.o.z, tid) * f.freq;            // simdnoise x = our k
+                        s_coord[16 + tid] = accumulate_ones(f.o.y, tid) * f.freq;     // y = our j
+                        s_coord[32 + tid] = accumulate_ones(f.o.x, tid) * f.freq;     // z = our i
+                    }
+                    float amp = 1.0f, done = 0.0f;
+                    for (uint32_t o = 0; o < n_oct; ++o) {
+                        if (o > 0) {
+                            amp = amp * gain;
+                            if (tid < 48) s_coord[tid] = s_coord[tid] * lac;
+                            const float R = fabsf(ns) * (total - done) * 1.005f + (1e-3f + 1e-5f * fabsf(ns) * total);
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                if (mask & (1u << k)) {
+                                    const float c = top[k] + res[k * 256 + tid] * ns;
+                                    if (c - R >= 2.5401f) { top[k] = 1000.0f; mask &= ~(1u << k); }
+                                    else if (c + R <= -2.5601f) { top[k] = -1000.0f; mask &= ~(1u << k); }
+                                }
+                            }
+                        }
+                        // CTA-wide compaction of the surviving voxels
+                        const uint32_t cnt = __popc(mask);
+                        uint32_t incl = cnt;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                            if ((tid & 31) >= d) incl += y;
+                        }
+                        if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+                        __syncthreads();
+                        uint32_t base = 0, n_list = 0;
+#pragma unroll
+                        for (int w = 0; w < EVAL_THREADS / 32; ++w) {
+                            const uint32_t ws = s_wsum[w];
+                            if (w < (tid >> 5)) base += ws;
+                            n_list += ws;
+                        }
+                        if (n_list == 0) break;  // CTA-uniform
+                        {
+                            uint32_t pos = base + incl - cnt, m = mask;
+                            while (m) {
+                                const int k = __ffs(m) - 1;
+                                m &= m - 1;
+                                list[pos++] = (uint16_t)(tid * 16 + k);
+                            }
+                        }
+                        __syncthreads();
+                        for (uint32_t it = tid; it < n_list; it += EVAL_THREADS) {
+                            const uint32_t idx = list[it];
+                            const float sx = s_coord[idx & 15u], sy = s_coord[16 + ((idx >> 4) & 15u)],
+                                        sz = s_coord[32 + (idx >> 8)];
+                            const float sv = simplex3(sx, sy, sz, seed);
+                            float* r = &res[(idx & 15u) * 256 + (idx >> 4)];
+                            *r = o == 0 ? sv : sv * amp + *r;
+                        }
+                        done = done + amp;
+                        __syncthreads();
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (mask & (1u << k)) top[k] = top[k] + res[k * 256 + tid] * ns;
+                } else if (f.rotated) {
                     f3 pos = (f.o + (float)ti * f.dxn) + (float)tj * f.dyn;
                     for (int k = 0; k < 16; ++k) {
                         const float v = top[k];
@@ -709,18 +800,9 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                     const float yc = accumulate_ones(f.o.y, tj) * f.freq;
 #pragma unroll 1
                     for (int k = 0; k < 16; ++k) {
-                        const float v = top[k];
-                        bool need = true;
-                        if (final_sat) {
-                            if (v - A >= 2.5401f) { need = false; top[k] = 1000.0f; }
-                            else if (v + A <= -2.5601f) { need = false; top[k] = -1000.0f; }
-                            if (!__any_sync(0xffffffffu, need)) continue;
-                        }
-                        if (need) {
-                            float xc = block_noise_x(f.o.z, k) * f.freq;
-                            float nv = fbm3(xc, yc, zc, lac, gain, oct, seed);
-                            top[k] = v + nv * ns;
-                        }
+                        float xc = block_noise_x(f.o.z, k) * f.freq;
+                        float nv = fbm3(xc, yc, zc, lac, gain, oct, seed);
+                        top[k] = top[k] + nv * ns;
                     }
                 }
             } else {  // OP_COMBINE
@@ -861,9 +943,15 @@ cudaError_t launch_fold(bool exact, const FoldArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// shared memory of k_eval: the operand stack levels; at least 24 KiB because the compacted final-noise path
+// reuses the (then empty) stack area for its partial sums and its voxel list
+static size_t eval_smem_bytes(int smem_levels) {
+    return std::max<size_t>((size_t)smem_levels * 4096 * sizeof(float), 24576);
+}
+
 cudaError_t launch_eval(const EvalArgs& a, uint32_t grid, cudaStream_t st) {
     if (a.n_active == 0 || grid == 0) return cudaSuccess;
-    const size_t smem = (size_t)a.smem_levels * 4096 * sizeof(float);
+    const size_t smem = eval_smem_bytes(a.smem_levels);
     cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_eval<<<grid, EVAL_THREADS, smem, st>>>(a);
     return cudaGetLastError();
@@ -871,7 +959,7 @@ cudaError_t launch_eval(const EvalArgs& a, uint32_t grid, cudaStream_t st) {
 
 int eval_max_blocks_per_sm(int smem_levels) {
     int nb = 0;
-    const size_t smem = (size_t)smem_levels * 4096 * sizeof(float);
+    const size_t smem = eval_smem_bytes(smem_levels);
     cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eval, EVAL_THREADS, smem);
     return nb;

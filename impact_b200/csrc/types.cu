@@ -99,11 +99,13 @@ __device__ __forceinline__ float simplex4_tab(float x, float y, float z, float w
     t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); t2 = fmaxf(t2, 0.0f); t3 = fmaxf(t3, 0.0f); t4 = fmaxf(t4, 0.0f);
     float q0 = t0 * t0, q1 = t1 * t1, q2 = t2 * t2, q3 = t3 * t3, q4 = t4 * t4;
     q0 = q0 * q0; q1 = q1 * q1; q2 = q2 * q2; q3 = q3 * q3; q4 = q4 * q4;
-    const float n0 = q0 * (g0.x * x0 + (g0.y * y0 + (g0.z * z0 + g0.w * w0)));
-    const float n1 = q1 * (g1.x * x1 + (g1.y * y1 + (g1.z * z1 + g1.w * w1)));
-    const float n2 = q2 * (g2.x * x2 + (g2.y * y2 + (g2.z * z2 + g2.w * w2)));
-    const float n3 = q3 * (g3.x * x3 + (g3.y * y3 + (g3.z * z3 + g3.w * w3)));
-    const float n4 = q4 * (g4.x * x4 + (g4.y * y4 + (g4.z * z4 + g4.w * w4)));
+    // products with a gradient component in {-1, 0, +1} are exact, so each FMA rounds exactly once, like
+    // the separate multiply and add it replaces
+    const float n0 = q0 * __fmaf_rn(g0.x, x0, __fmaf_rn(g0.y, y0, __fmaf_rn(g0.z, z0, g0.w * w0)));
+    const float n1 = q1 * __fmaf_rn(g1.x, x1, __fmaf_rn(g1.y, y1, __fmaf_rn(g1.z, z1, g1.w * w1)));
+    const float n2 = q2 * __fmaf_rn(g2.x, x2, __fmaf_rn(g2.y, y2, __fmaf_rn(g2.z, z2, g2.w * w2)));
+    const float n3 = q3 * __fmaf_rn(g3.x, x3, __fmaf_rn(g3.y, y3, __fmaf_rn(g3.z, z3, g3.w * w3)));
+    const float n4 = q4 * __fmaf_rn(g4.x, x4, __fmaf_rn(g4.y, y4, __fmaf_rn(g4.z, z4, g4.w * w4)));
     return (n0 + (n1 + (n2 + (n3 + n4)))) * 62.77772078955791f;
 }
 
@@ -148,7 +150,7 @@ struct TypesSmem {
     uint8_t first_type;
 };
 
-__global__ void __launch_bounds__(TYPES_THREADS) k_types(TypesArgs a) {
+__global__ void __launch_bounds__(TYPES_THREADS, 3) k_types(TypesArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TypesSmem& S = *reinterpret_cast<TypesSmem*>(smem_raw);
     const int tid = threadIdx.x;
