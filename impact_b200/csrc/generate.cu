@@ -126,6 +126,158 @@ struct FoldWarpSmem {
 // |fbm * noise_scale| <= amplitude. 0.5 % + 1e-3 absorbs f32 rounding.
 __device__ __forceinline__ float noise_bound(const ivx_node& n) { return 1.005f * fabsf(n.p[3]) + 1e-3f; }
 
+// ---------------------------------------------------------------------------
+// Rigorous range of the noise over a block (warp-cooperative; every lane calls).
+//
+// simplex3(p) = 32.694 * sum over the 4 corners Q of p's simplex of t^4 (g_Q . d), d = p - Q, t = max(0.6 - |d|^2, 0).
+// For a box B of noise-space points, every lattice point Q that can reach B (t > 0 somewhere in B) is
+// enumerated, its own gradient is taken from the same hash simplex3 uses, and t^4 (g . d) is bounded over
+// d in B - Q with interval arithmetic. A lattice point is a corner for some points of B and not for
+// others, so each term enters as [min(lo, 0), max(hi, 0)]. The sum of those intervals contains simplex3(p)
+// for every p in B. At the usual frequencies a block touches one or two simplex cells, and the range is a
+// small fraction of [-1, 1]; when the box spans too many cells the octave falls back to [-1, 1].
+constexpr int NOISE_RANGE_MAX_POINTS = 1024;
+constexpr float NOISE_RANGE_MAX_EXTENT = 0.75f;
+
+__device__ __forceinline__ void simplex3_range(float blo[3], float bhi[3], int32_t seed, int lane, float& out_lo,
+                                               float& out_hi) {
+    out_lo = -1.0f;
+    out_hi = 1.0f;
+    const float R = 0.7747f;  // sqrt(0.6) rounded up: beyond this distance t = 0
+    const float G3 = 1.0f / 6.0f;
+    float elo[3], ehi[3];
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        elo[c] = blo[c] - R;
+        ehi[c] = bhi[c] + R;
+        ok = ok && (fabsf(elo[c]) < 1.0e6f) && (fabsf(ehi[c]) < 1.0e6f) && (blo[c] <= bhi[c]);
+    }
+    if (!ok) return;  // also taken for NaN
+    // a box wider than this spans several simplex cells: the bound is no better than [-1, 1]
+    if (fmaxf(bhi[0] - blo[0], fmaxf(bhi[1] - blo[1], bhi[2] - blo[2])) > NOISE_RANGE_MAX_EXTENT) return;
+    // Lattice points by planes S = I + J + K: the unskewed position is P = (I, J, K) - S/6, so
+    // S = 2 (P.x + P.y + P.z), and on a plane I - S/6 and J - S/6 must lie in the box's x / y range.
+    const float sum_lo = (elo[0] + elo[1]) + elo[2], sum_hi = (ehi[0] + ehi[1]) + ehi[2];
+    const int s0 = (int)floorf(2.0f * sum_lo) - 1;
+    const int ns = (int)ceilf(2.0f * sum_hi) + 1 - s0 + 1;
+    const int na = (int)ceilf(ehi[0] - elo[0]) + 2, nb = (int)ceilf(ehi[1] - elo[1]) + 2;
+    const int total = ns * na * nb;
+    if (total > NOISE_RANGE_MAX_POINTS) return;
+    float acc_lo = 0.0f, acc_hi = 0.0f;
+    for (int q = lane; q < total; q += 32) {
+        const int S = s0 + q / (na * nb);
+        const float sg = (float)S * G3;
+        const int I = (int)floorf(elo[0] + sg) + (q / nb) % na, J = (int)floorf(elo[1] + sg) + q % nb;
+        const int K = S - I - J;
+        const float g = G3 * (float)(I + J + K);
+        const float P[3] = {(float)I - g, (float)J - g, (float)K - g};
+        float dlo[3], dhi[3], minsq = 0.0f, maxsq = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float e = 4e-6f * (1.0f + fabsf(P[c]) + fabsf(blo[c]) + fabsf(bhi[c]));
+            dlo[c] = (blo[c] - P[c]) - e;
+            dhi[c] = (bhi[c] - P[c]) + e;
+            const float a2 = dlo[c] * dlo[c], b2 = dhi[c] * dhi[c];
+            maxsq += fmaxf(a2, b2);
+            minsq += (dlo[c] <= 0.0f && dhi[c] >= 0.0f) ? 0.0f : fminf(a2, b2);
+        }
+        const float thi = fmaxf(0.6f - minsq * 0.99999f, 0.0f) * 1.00001f;
+        if (thi <= 0.0f) continue;
+        const float tlo = fmaxf(0.6f - maxsq * 1.00001f, 0.0f) * 0.99999f;
+        // the lattice point's gradient: grad3d_dot of common.cuh
+        uint32_t h = ((uint32_t)I * 1619u) ^ (uint32_t)seed;
+        h = ((uint32_t)J * 31337u) ^ h;
+        h = ((uint32_t)K * 6791u) ^ h;
+        h = ((h * h) * 60493u) * h;
+        h = (uint32_t)((int32_t)h >> 13) ^ h;
+        const uint32_t h13 = h & 13u;
+        const int ua = (h13 < 8u) ? 0 : 1;
+        const int va = (h13 < 2u) ? 1 : ((h13 == 12u) ? 0 : 2);
+        float ulo = dlo[ua], uhi = dhi[ua], vlo = dlo[va], vhi = dhi[va];
+        if (h & 1u) { const float t = ulo; ulo = -uhi; uhi = -t; }
+        if (h & 2u) { const float t = vlo; vlo = -vhi; vhi = -t; }
+        const float glo = ulo + vlo, ghi = uhi + vhi;
+        float t4lo = tlo * tlo, t4hi = thi * thi;
+        t4lo = t4lo * t4lo * 0.9999f;
+        t4hi = t4hi * t4hi * 1.0001f;
+        const float clo = fminf(fminf(t4lo * glo, t4hi * glo), 0.0f);
+        const float chi = fmaxf(fmaxf(t4lo * ghi, t4hi * ghi), 0.0f);
+        acc_lo += clo;
+        acc_hi += chi;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        acc_lo += __shfl_xor_sync(0xffffffffu, acc_lo, d);
+        acc_hi += __shfl_xor_sync(0xffffffffu, acc_hi, d);
+    }
+    const float S = 32.69428253173828125f * 1.0001f;
+    out_lo = fmaxf(acc_lo * S - 1e-5f, -1.0f);
+    out_hi = fminf(acc_hi * S + 1e-5f, 1.0f);
+    if (!(out_lo <= out_hi)) {  // cannot happen; stay safe
+        out_lo = -1.0f;
+        out_hi = 1.0f;
+    }
+}
+
+// Range of `fbm * noise_scale` (the term a MultifractalNoise node adds, atomic.rs:1423-1507) over the voxels
+// of the block [lo, lo + bs)^3 in root space. Always within [-A, A], A = noise_bound(n).
+__device__ __forceinline__ void noise_term_range(const ivx_node& n, f3 lo, float bs, int lane, float& out_lo,
+                                                 float& out_hi) {
+    const float A = 1.005f * fabsf(n.p[3]) + 1e-3f;
+    out_lo = -A;
+    out_hi = A;
+    const NoiseFrame f = make_noise_frame(n, lo);
+    // positions walked by the block: o + i dxn + j dyn + k dzn, 0 <= i, j, k <= bs - 1 (voxel samples)
+    const float o3[3] = {f.o.x, f.o.y, f.o.z};
+    const float dx3[3] = {f.dxn.x, f.dxn.y, f.dxn.z}, dy3[3] = {f.dyn.x, f.dyn.y, f.dyn.z},
+                dz3[3] = {f.dzn.x, f.dzn.y, f.dzn.z};
+    float blo[3], bhi[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = bs * dx3[c], b = bs * dy3[c], d = bs * dz3[c];
+        float l = o3[c] + (fminf(a, 0.0f) + fminf(b, 0.0f) + fminf(d, 0.0f));
+        float h = o3[c] + (fmaxf(a, 0.0f) + fmaxf(b, 0.0f) + fmaxf(d, 0.0f));
+        // f32 rounding of the incremental position walks
+        const float e = 1e-5f * (fabsf(l) + fabsf(h) + bs) + 1e-4f;
+        l = (l - e) * f.freq;
+        h = (h + e) * f.freq;
+        // simdnoise x, y, z = our z, y, x
+        blo[2 - c] = fminf(l, h);
+        bhi[2 - c] = fmaxf(l, h);
+    }
+    const float lac = n.p[1], gain = n.p[2];
+    const uint32_t n_oct = max(n.octaves & 0xFFu, 1u);
+    float amp = 1.0f, sum_lo = 0.0f, sum_hi = 0.0f, sum_abs = 0.0f;
+    for (uint32_t o = 0; o < n_oct; ++o) {
+        if (o > 0) {
+            amp = amp * gain;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float l = blo[c] * lac, h = bhi[c] * lac;
+                const float e = 1e-6f * (fabsf(l) + fabsf(h));
+                blo[c] = fminf(l, h) - e;
+                bhi[c] = fmaxf(l, h) + e;
+            }
+        }
+        float slo, shi;
+        simplex3_range(blo, bhi, (int32_t)n.seed, lane, slo, shi);
+        const float x = amp * slo, y = amp * shi;
+        sum_lo += fminf(x, y);
+        sum_hi += fmaxf(x, y);
+        sum_abs += fabsf(amp);
+    }
+    const float ns = n.p[4];
+    const float x = sum_lo * ns, y = sum_hi * ns;
+    const float e = 1e-5f * sum_abs * fabsf(ns) + 1e-4f;
+    out_lo = fmaxf(fminf(x, y) - e, -A);
+    out_hi = fminf(fmaxf(x, y) + e, A);
+    if (!(out_lo <= out_hi)) {
+        out_lo = -A;
+        out_hi = A;
+    }
+}
+
 __device__ __forceinline__ float slack(float a, float b) { return 1e-3f + 2e-5f * (fabsf(a) + fabsf(b)); }
 
 // moves `len` instructions from out[src..] down to out[dst..] (dst < src), warp-cooperatively
@@ -404,12 +556,13 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                 }
                 if (apply) {
                     const float l0 = S.ilo[sp - 1], h0 = S.ihi[sp - 1];
+                    float nlo, nhi;  // range of the added term over the block
+                    noise_term_range(n, lo, hi.x - lo.x, lane, nlo, nhi);
                     __syncwarp();
                     if (lane == 0) {
-                        const float A = noise_bound(n);
                         S.is_const[sp - 1] = 0;
-                        S.ilo[sp - 1] = l0 - A - slack(l0, A);
-                        S.ihi[sp - 1] = h0 + A + slack(h0, A);
+                        S.ilo[sp - 1] = (l0 + nlo) - slack(l0, nlo);
+                        S.ihi[sp - 1] = (h0 + nhi) + slack(h0, nhi);
                         out[olen] = in;
                     }
                     olen += 1;
