@@ -330,6 +330,42 @@ void orc_absorb_sphere(void* op, const float center[3], float radius, float infl
     absorb_sphere(*(Object*)op, v3(center[0], center[1], center[2]), radius, influence_radius, stats);
 }
 
+// ---- connected regions ----
+// Runs the whole detection on the object's current state. info (u32 x 24): n_regions, has_two, two[0], two[1],
+// smallest, overflow, n_region_entries, n_label_bytes, then per candidate region 8 words: chunk_count,
+// non_uniform_chunk_count, chunk_min[3], chunk_max[3].
+void* orc_split_detect(void* op, uint32_t* info) {
+    auto* sd = new SplitDetection();
+    resolve_connected_regions(*(Object*)op, *sd);
+    info[0] = sd->n_regions;
+    info[1] = sd->has_two ? 1u : 0u;
+    info[2] = sd->two[0];
+    info[3] = sd->two[1];
+    info[4] = sd->smallest;
+    info[5] = sd->overflow ? 1u : 0u;
+    info[6] = (uint32_t)sd->region_root.size();
+    info[7] = (uint32_t)sd->voxel_labels.size();
+    for (int q = 0; q < 2; ++q) {
+        uint32_t* o = info + 8 + 8 * q;
+        o[0] = sd->stats[q].chunk_count;
+        o[1] = sd->stats[q].non_uniform_chunk_count;
+        for (int d = 0; d < 3; ++d) {
+            o[2 + d] = sd->stats[q].chunk_min[d];
+            o[5 + d] = sd->stats[q].chunk_max[d];
+        }
+    }
+    return sd;
+}
+// per_chunk: n_chunks x {u16 region_count, u16 boundary_region_count, u32 first_region}
+void orc_split_copy(void* sp, uint8_t* voxel_labels, void* per_chunk, uint32_t* region_roots) {
+    auto* sd = (SplitDetection*)sp;
+    if (voxel_labels) std::memcpy(voxel_labels, sd->voxel_labels.data(), sd->voxel_labels.size());
+    if (per_chunk) std::memcpy(per_chunk, sd->per_chunk.data(), sd->per_chunk.size() * sizeof(ChunkRegions));
+    if (region_roots) std::memcpy(region_roots, sd->region_root.data(), sd->region_root.size() * 4);
+}
+void orc_split_free(void* sp) { delete (SplitDetection*)sp; }
+uint32_t orc_count_regions_brute_force(void* op) { return count_regions_brute_force(*(Object*)op); }
+
 float orc_simplex3(float x, float y, float z, int32_t seed) { return simplex3(x, y, z, seed); }
 float orc_fbm3(float x, float y, float z, float lac, float gain, uint32_t oct, int32_t seed) {
     return fbm3(x, y, z, lac, gain, oct, seed);

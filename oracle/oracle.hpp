@@ -291,4 +291,31 @@ struct AbsorbStats {
 void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius,
                    AbsorbStats* stats);
 
+// --- connected regions (object/split_detection.rs, object/extraction.rs:121-281) ---
+struct ChunkRegions {
+    uint16_t region_count;           // local regions in the chunk (uniform chunk: 1)
+    uint16_t boundary_region_count;  // of which touch the chunk boundary (labelled first)
+    uint32_t first_region;           // index of the chunk's region 0 in the per-region arrays
+};
+struct RegionStats {
+    uint32_t chunk_count, non_uniform_chunk_count;
+    uint32_t chunk_min[3], chunk_max[3];
+};
+struct SplitDetection {
+    std::vector<uint8_t> voxel_labels;  // 4096 per non-uniform chunk, data_offset order; 255 = empty
+    std::vector<ChunkRegions> per_chunk;
+    std::vector<uint32_t> region_parent;  // GlobalRegionLabel = chunk_idx << 8 | region_idx
+    std::vector<uint32_t> region_root;    // resolved representative of every local region
+    uint32_t n_regions = 0;               // count_regions
+    bool has_two = false;                 // find_two_disconnected_regions
+    uint32_t two[2] = {0, 0};
+    RegionStats stats[2];
+    uint32_t smallest = 0;                // which of `two` extract_smallest_region would extract
+    bool overflow = false;                // more regions / connections than the reference's fixed capacities
+};
+bool local_regions_for_chunk(const Voxel* voxels, bool only_empty, uint8_t* labels, uint16_t* boundary_region_count,
+                             uint16_t* region_count);
+void resolve_connected_regions(const Object& obj, SplitDetection& sd);
+uint32_t count_regions_brute_force(const Object& obj);
+
 }  // namespace orc

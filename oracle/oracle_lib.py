@@ -251,6 +251,31 @@ class Object:
         return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
                 "removed_chunks": int(st[3])}
 
+    REGIONS_DTYPE = np.dtype([("region_count", "<u2"), ("boundary_region_count", "<u2"), ("first_region", "<u4")])
+
+    def split_detection(self) -> dict:
+        """Connected regions of the object's current state (split_detection.rs): local labels per voxel,
+        region counts per chunk, the resolved root of every local region, count_regions,
+        find_two_disconnected_regions and the region extract_smallest_region would pick."""
+        info = np.zeros(24, np.uint32)
+        lib().orc_split_detect.restype = C.c_void_p
+        h = C.c_void_p(lib().orc_split_detect(self.h, _p(info)))
+        labels = np.zeros(int(info[7]), np.uint8)
+        per_chunk = np.zeros(len(self.chunks()), self.REGIONS_DTYPE)
+        roots = np.zeros(int(info[6]), np.uint32)
+        lib().orc_split_copy(h, _p(labels), _p(per_chunk), _p(roots))
+        lib().orc_split_free(h)
+        cand = [{"chunk_count": int(info[8 + 8 * q]), "non_uniform_chunk_count": int(info[9 + 8 * q]),
+                 "chunk_min": info[10 + 8 * q: 13 + 8 * q].copy(), "chunk_max": info[13 + 8 * q: 16 + 8 * q].copy()}
+                for q in range(2)]
+        return {"n_regions": int(info[0]), "has_two": bool(info[1]), "two": (int(info[2]), int(info[3])),
+                "smallest": int(info[4]), "overflow": bool(info[5]), "voxel_labels": labels, "per_chunk": per_chunk,
+                "region_roots": roots, "candidates": cand}
+
+    def count_regions_brute_force(self) -> int:
+        lib().orc_count_regions_brute_force.restype = C.c_uint32
+        return int(lib().orc_count_regions_brute_force(self.h))
+
 
 class Mesh:
     """VoxelObjectMesh (mesh.rs:50-58)."""

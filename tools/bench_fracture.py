@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""BASELINE config 5: repeated spherical absorption on the 1024^3 asteroid with dirty-chunk remesh.
+
+    python tools/bench_fracture.py [--workload asteroid1024] [--steps 32] [--cpu-steps 4]
+
+Geometry of the reference's `update_mesh` bench (engine/src/benchmark/benchmarks/voxel_object.rs:343-362):
+an absorbing sphere of radius 0.15 R starts on the bounding sphere along the (1,1,1) diagonal and moves
+inward by one absorber radius per step; after each step the invalidated chunks are re-meshed
+(`sync_with_voxel_object`) and, every step, connected regions are re-resolved when the library offers it.
+Prints one JSON line (per-step device times from CUDA events inside the library, host wall time per step,
+dirty chunks / touched voxels per step) and, with --cpu-steps > 0, the CPU restatement (oracle/) timed on
+the same first steps after generating the same object on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def absorber_path(shape, steps):
+    R = 0.5 * float(max(shape))
+    radius = np.float32(0.15 * R)
+    start = (0.5 * np.asarray(shape, np.float64) - R / np.sqrt(3.0)).astype(np.float32)
+    d = np.float32(1.0 / np.sqrt(3.0))
+    return [(start + np.float32(s) * radius * d).astype(np.float32) for s in range(steps)], float(radius)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="asteroid1024")
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--cpu-steps", type=int, default=0)
+    ap.add_argument("--split", action="store_true", help="also resolve connected regions after every step")
+    args = ap.parse_args()
+
+    import bench
+    from impact_b200.voxel import Context, SDFVoxelGenerator, VoxelObject, VoxelObjectMesh
+
+    graph, types, desc = bench.make_workload(args.workload)
+    ctx = Context(0)
+    gen = ctx.build_generator(graph)
+    obj = VoxelObject.generate(SDFVoxelGenerator(1.0, gen, types))
+    info = obj.info()
+    shape = info["grid_shape"]
+    VoxelObjectMesh.create(obj)
+    centers, radius = absorber_path(shape, args.steps)
+    influence = radius + 2.0  # absorption.rs:170-179: influence radius = radius + 2 voxel extents
+
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    per_step = []
+    launches0 = ctx.kernel_launch_count
+    t_all = time.perf_counter()
+    for c in centers:
+        t0 = time.perf_counter()
+        st = obj.absorb_sphere(c, radius, influence)
+        n_dirty = len(obj.invalidated_mesh_chunk_indices())
+        t1 = time.perf_counter()
+        patch = VoxelObjectMesh.sync_with_voxel_object(obj)
+        ctx.synchronize()
+        t2 = time.perf_counter()
+        regions = None
+        if args.split and hasattr(obj, "count_regions"):
+            regions = obj.count_regions()
+        t3 = time.perf_counter()
+        per_step.append({"absorb_ms": 1e3 * (t1 - t0), "remesh_ms": 1e3 * (t2 - t1), "split_ms": 1e3 * (t3 - t2),
+                         "touched_chunks": st["touched_chunks"], "touched_voxels": st["touched_voxels"],
+                         "emptied_voxels": st["emptied_voxels"], "dirty_chunks": n_dirty,
+                         "remeshed_submeshes": patch.n_submeshes, "patch_vertices": patch.n_vertices,
+                         "regions": regions})
+    wall = time.perf_counter() - t_all
+    prof = ctx.profile_get()
+    launches = ctx.kernel_launch_count - launches0
+    mean = lambda k: float(np.mean([s[k] for s in per_step]))
+    touched = sum(s["touched_voxels"] for s in per_step)
+    out = {
+        "metric": "fracture_step_ms", "workload": args.workload, "description": desc, "grid_shape": list(shape),
+        "steps": args.steps, "absorber_radius_voxels": radius,
+        "ms_per_step": 1e3 * wall / args.steps, "absorb_ms": mean("absorb_ms"), "remesh_ms": mean("remesh_ms"),
+        "split_ms": mean("split_ms") if args.split else None,
+        "dirty_chunks_per_step": mean("dirty_chunks"), "touched_chunks_per_step": mean("touched_chunks"),
+        "touched_voxels_per_step": mean("touched_voxels"), "emptied_voxels_total": sum(s["emptied_voxels"] for s in per_step),
+        "touched_voxels_per_s": touched / wall,
+        # modification moves 6 B per voxel of the touched chunks (3 read + 3 written), SURVEY 8d
+        "absorb_kernel_ms_per_step": prof["absorb"][0] / max(1, args.steps),
+        "absorb_kernel_gbs": (6.0 * 4096 * sum(s["touched_chunks"] for s in per_step)) / max(prof["absorb"][0] * 1e-3, 1e-12) / 1e9,
+        "mesh_kernel_ms_per_step": (prof["mesh_count"][0] + prof["mesh_emit"][0]) / max(1, args.steps),
+        "gpu_launches": int(launches), "timing": "host wall clock around synchronous C-ABI calls; kernel times from CUDA events",
+        "last_step": per_step[-1],
+    }
+
+    if args.cpu_steps > 0:
+        from oracle import oracle_lib as O
+
+        threads = os.cpu_count() or 1
+        ogen = O.Generator(graph.nodes(), graph.root_node_id)
+        t0 = time.perf_counter()
+        oobj = O.Object.generate(O.VoxelGenerator(ogen, 1.0, types), threads)
+        oobj.mesh(threads)
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        n_dirty = 0
+        for c in centers[: args.cpu_steps]:
+            oobj.absorb_sphere(c, radius, influence)
+            dirty = oobj.dirty()
+            n_dirty += len(dirty)
+            cc = oobj.info()["chunk_counts"]
+            for lin in dirty:
+                oobj.mesh_chunk(int(lin // (cc[1] * cc[2])), int((lin // cc[2]) % cc[1]), int(lin % cc[2]))
+            oobj.clear_dirty()
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"kind": "port", "cores": 1, "steps": args.cpu_steps, "ms_per_step": 1e3 * dt / args.cpu_steps,
+                               "generate_and_mesh_s": t_gen, "generate_threads": threads,
+                               "note": "oracle absorb + per-chunk remesh of the dirty set, single thread (the "
+                                       "reference's absorb / sync_with_voxel_object are single-threaded too)"}
+    print(json.dumps(out), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
