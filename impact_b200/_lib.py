@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_slab_finalize", "ivx_object_info_get",
     "ivx_object_download", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_object_absorb_sphere",
     "ivx_object_dirty_chunks", "ivx_object_remesh_dirty",
+    "ivx_object_resolve_connected_regions", "ivx_object_split_detection_download",
 ]
 
 
@@ -60,6 +61,18 @@ class AbsorbStats(C.Structure):
                 ("removed_chunks", C.c_uint32), ("dirty_chunks", C.c_uint32)]
 
 
+class RegionCandidate(C.Structure):
+    _fields_ = [("label", C.c_uint32), ("chunk_count", C.c_uint32), ("non_uniform_chunk_count", C.c_uint32),
+                ("chunk_min", C.c_uint32 * 3), ("chunk_max", C.c_uint32 * 3)]
+
+
+class SplitInfo(C.Structure):
+    _fields_ = [("n_regions", C.c_uint32), ("has_two", C.c_uint32), ("candidates", RegionCandidate * 2),
+                ("smallest", C.c_uint32), ("n_local_regions", C.c_uint32), ("n_connections", C.c_uint32),
+                ("device_ms", C.c_float), ("host_ms", C.c_float)]
+
+
+CHUNK_REGIONS_DTYPE = np.dtype([("region_count", "<u2"), ("boundary_region_count", "<u2"), ("first_region", "<u4")])
 VOXEL_DTYPE = np.dtype([("type", "u1"), ("sd", "i1"), ("flags", "u1")])
 CHUNK_DTYPE = np.dtype(
     [("kind", "u1"), ("flags", "u1"), ("face", "u1", (6,)), ("uniform_type", "u1"), ("uniform_sd", "i1"),

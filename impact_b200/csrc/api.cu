@@ -10,176 +10,11 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
-#include "kernels.h"
+#include "api_internal.cuh"
 
 using namespace ivx;
 
-// ---------------------------------------------------------------------------
-struct PoolBlock {
-    void* ptr;
-    size_t size;
-    bool used;
-};
-
-struct ivx_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    std::string err;
-    uint64_t launches = 0;
-    int sm_count = 148;
-    std::vector<PoolBlock> pool;
-    // optional per-kernel timing
-    bool profiling = false;
-    struct ProfEvent { cudaEvent_t a, b; uint32_t id; };
-    std::vector<ProfEvent> prof_events;
-    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t* h_pinned = nullptr;  // 64 words of pinned scratch for counter read-back
-    uint32_t* d_scratch = nullptr; // 64 words of device counters
-
-    void* alloc(size_t bytes) {
-        if (bytes == 0) bytes = 16;
-        bytes = (bytes + 255) & ~(size_t)255;
-        int best = -1;
-        for (int i = 0; i < (int)pool.size(); ++i)
-            if (!pool[i].used && pool[i].size >= bytes && pool[i].size <= bytes * 2 + (1 << 20) &&
-                (best < 0 || pool[i].size < pool[best].size))
-                best = i;
-        if (best >= 0) {
-            pool[best].used = true;
-            return pool[best].ptr;
-        }
-        void* p = nullptr;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) {
-            cudaGetLastError();
-            // release cached blocks and retry once
-            for (auto it = pool.begin(); it != pool.end();) {
-                if (!it->used) {
-                    cudaFree(it->ptr);
-                    it = pool.erase(it);
-                } else {
-                    ++it;
-                }
-            }
-            if (cudaMalloc(&p, bytes) != cudaSuccess) {
-                cudaGetLastError();
-                return nullptr;
-            }
-        }
-        pool.push_back({p, bytes, true});
-        return p;
-    }
-    void release(void* p) {
-        if (!p) return;
-        for (auto& b : pool)
-            if (b.ptr == p) {
-                b.used = false;
-                return;
-            }
-    }
-};
-
-struct ivx_program {
-    HostProgram host;
-    ivx_node* d_nodes = nullptr;
-    Instr* d_root = nullptr;     // the whole program as an instruction list
-    uint32_t root_len = 0;
-    uint32_t* d_root_meta = nullptr;  // [0] = offset (0), [1] = length
-};
-
-struct DeviceMesh {
-    uint32_t n_vertices = 0, n_indices = 0, n_submeshes = 0, n_work = 0;
-    float* positions = nullptr;
-    float* normals = nullptr;
-    uint32_t* indices = nullptr;
-    ivx_index_materials* index_materials = nullptr;
-    ivx_chunk_submesh* submeshes = nullptr;
-    uint32_t* vertex_ranges = nullptr;
-};
-
-struct ivx_object {
-    float voxel_extent = 1.0f;
-    uint32_t grid_shape[3] = {0, 0, 0};
-    uint32_t chunk_counts[3] = {0, 0, 0};  // full grid
-    uint32_t nb[3] = {0, 0, 0};            // locally stored chunk planes (slab)
-    uint32_t first_i = 0;                  // global chunk-i of local plane 0
-    uint32_t own_begin = 0, own_end = 0;   // owned planes, global chunk-i
-    uint32_t n_chunks = 0;
-    DevChunk* d_chunks = nullptr;
-    unsigned char* d_voxels = nullptr;
-    uint32_t slot_capacity = 0, slots_used = 0;
-    uint8_t* d_dirty = nullptr;
-    uint32_t occ_voxels[6] = {0, 0, 0, 0, 0, 0};  // lo xyz, hi xyz (exclusive)
-    uint32_t n_void = 0, n_uniform = 0, n_non_uniform = 0;
-    DeviceMesh mesh;
-    // slab protocol (multi-GPU): derived state is pending until the halo planes are imported
-    bool derive_pending = false;
-    uint32_t* d_slot_of = nullptr;       // slot reserved for each chunk (conversion target), 0xFFFFFFFF = none
-    uint32_t* d_convert_flag = nullptr;  // result of ivx_object_slab_classify
-    bool halo_present[2] = {false, false};
-};
-
 namespace {
-
-#define IVX_FAIL(ctx, code, ...)                              \
-    do {                                                      \
-        char _b[512];                                         \
-        std::snprintf(_b, sizeof(_b), __VA_ARGS__);           \
-        (ctx)->err = _b;                                      \
-        return (code);                                        \
-    } while (0)
-
-#define CU(ctx, expr)                                                                               \
-    do {                                                                                            \
-        cudaError_t _e = (expr);                                                                    \
-        if (_e != cudaSuccess) {                                                                    \
-            cudaGetLastError();                                                                     \
-            IVX_FAIL(ctx, _e == cudaErrorMemoryAllocation ? IVX_ERR_OUT_OF_MEMORY : IVX_ERR_CUDA,   \
-                     "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);   \
-        }                                                                                           \
-    } while (0)
-
-// kernel launch through a launch_* wrapper: counts the launch
-#define KL(ctx, expr)      \
-    do {                   \
-        (ctx)->launches++; \
-        CU(ctx, expr);     \
-    } while (0)
-
-// kernel launch with optional event timing under kernel id `kid`
-#define KLP(ctx, kid, expr)                                              \
-    do {                                                                 \
-        (ctx)->launches++;                                               \
-        ivx_ctx::ProfEvent _pe{nullptr, nullptr, (uint32_t)(kid)};       \
-        if ((ctx)->profiling) {                                          \
-            cudaEventCreate(&_pe.a);                                     \
-            cudaEventCreate(&_pe.b);                                     \
-            cudaEventRecord(_pe.a, (ctx)->stream);                       \
-        }                                                                \
-        cudaError_t _le = (expr);                                        \
-        if ((ctx)->profiling) {                                          \
-            cudaEventRecord(_pe.b, (ctx)->stream);                       \
-            (ctx)->prof_events.push_back(_pe);                           \
-        }                                                                \
-        CU(ctx, _le);                                                    \
-    } while (0)
-
-struct Tmp {
-    ivx_ctx* ctx;
-    std::vector<void*> ptrs;
-    explicit Tmp(ivx_ctx* c) : ctx(c) {}
-    ~Tmp() {
-        for (void* p : ptrs) ctx->release(p);
-    }
-    template <typename T>
-    T* get(size_t count) {
-        void* p = ctx->alloc(count * sizeof(T));
-        if (p) ptrs.push_back(p);
-        return static_cast<T*>(p);
-    }
-};
 
 int read_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t n, uint32_t* out) {
     CU(ctx, cudaMemcpyAsync(ctx->h_pinned, d_src, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -276,6 +111,13 @@ int plan_eval_stack(ivx_ctx* ctx, uint32_t max_depth, Tmp& tmp, uint32_t n_activ
     }
     return IVX_OK;
 }
+
+}  // namespace
+
+int ivx_read_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t n, uint32_t* out) { return read_words(ctx, d_src, n, out); }
+uint32_t ivx_persistent_grid(ivx_ctx* ctx, uint32_t n_work, int blocks_per_sm) { return persistent_grid(ctx, n_work, blocks_per_sm); }
+
+namespace {
 
 int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, const ivx_type_generator* tg,
                   uint32_t i_begin, uint32_t i_end, bool whole, ivx_object** out) {
@@ -1184,6 +1026,7 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     ctx->release(obj->d_dirty);
     ctx->release(obj->d_slot_of);
     ctx->release(obj->d_convert_flag);
+    ctx->release(obj->d_labels);
     delete obj;
 }
 

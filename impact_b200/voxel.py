@@ -237,6 +237,34 @@ class VoxelObject:
                                                               C.c_float(influence_radius), C.byref(st)))
         return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
 
+    def resolve_connected_regions(self, download: bool = False) -> dict:
+        """`update_local_connected_regions_for_all_chunks` + `resolve_connected_regions_between_all_chunks` +
+        `count_regions` / `find_two_disconnected_regions` (split_detection.rs:193-488) and the region
+        `extract_smallest_region_with_property_transferrer` would pick (extraction.rs:121-281)."""
+        si = L.SplitInfo()
+        self.ctx.check(self.ctx._lib.ivx_object_resolve_connected_regions(self.ctx.h, self.h, C.byref(si)))
+        cand = [{"label": int(c.label), "chunk_count": int(c.chunk_count),
+                 "non_uniform_chunk_count": int(c.non_uniform_chunk_count),
+                 "chunk_min": np.array(c.chunk_min[:], np.uint32), "chunk_max": np.array(c.chunk_max[:], np.uint32)}
+                for c in si.candidates]
+        out = {"n_regions": int(si.n_regions), "has_two": bool(si.has_two), "two": (cand[0]["label"], cand[1]["label"]),
+               "smallest": int(si.smallest), "candidates": cand, "n_local_regions": int(si.n_local_regions),
+               "n_connections": int(si.n_connections), "device_ms": float(si.device_ms), "host_ms": float(si.host_ms)}
+        if download:
+            inf = self.info()
+            n = int(np.prod(inf["chunk_counts"]))
+            labels = np.zeros(inf["n_non_uniform"] * 4096, np.uint8)
+            per_chunk = np.zeros(n, L.CHUNK_REGIONS_DTYPE)
+            roots = np.zeros(max(1, si.n_local_regions), np.uint32)
+            self.ctx.check(self.ctx._lib.ivx_object_split_detection_download(
+                self.ctx.h, self.h, L.ptr(labels), C.c_size_t(len(labels)), L.ptr(per_chunk), C.c_size_t(n), L.ptr(roots),
+                C.c_size_t(len(roots))))
+            out.update(voxel_labels=labels, per_chunk=per_chunk, region_roots=roots[: si.n_local_regions])
+        return out
+
+    def count_regions(self) -> int:
+        return self.resolve_connected_regions()["n_regions"]
+
     def invalidated_mesh_chunk_indices(self) -> np.ndarray:
         cnt = C.c_uint32()
         self.ctx.check(self.ctx._lib.ivx_object_dirty_chunks(self.ctx.h, self.h, None, C.c_uint32(0), C.byref(cnt)))

@@ -311,6 +311,51 @@ int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* object, uint32_t* ou
                             uint32_t capacity, uint32_t* out_count);
 int ivx_object_remesh_dirty(ivx_ctx* ctx, ivx_object* object, ivx_mesh_info* out);
 
+/* ---- connected regions ("split detection") -------------------------------
+ * ivx_object_resolve_connected_regions replaces, on the object's current state,
+ *   update_local_connected_regions_for_all_chunks  (object/split_detection.rs:305-317, 662-893)
+ *   the connection updates of update_mutual_face_adjacencies (split_detection.rs:1046-1326, 1424-1463)
+ *   resolve_connected_regions_between_all_chunks   (split_detection.rs:323-488)
+ *   count_regions / find_two_disconnected_regions  (split_detection.rs:193-301)
+ *   and the choice made by extract_smallest_region_with_property_transferrer
+ *   (object/extraction.rs:121-281: fewest non-uniform chunks, then fewest chunks).
+ * Local labels follow the reference's numbering (boundary regions first, in its face traversal order), and
+ * the global pass visits chunks and regions in its order, so the representative (root) region of every
+ * global region — hence `candidates[].label` — is the reference's. Whole objects only (a multi-GPU slab
+ * object gathers on one rank first). Returns IVX_ERR_UNSUPPORTED for chunks with more local
+ * regions or adjacent-region connections than the reference's fixed capacities (its asserts / overwrites,
+ * split_detection.rs:798, 835, 1519-1546).
+ * GlobalRegionLabel = linear chunk index << 8 | local region index (split_detection.rs:1550-1571). */
+typedef struct ivx_region_candidate {
+    uint32_t label;                   /* root GlobalRegionLabel */
+    uint32_t chunk_count;             /* non-void chunks containing voxels of the region */
+    uint32_t non_uniform_chunk_count;
+    uint32_t chunk_min[3], chunk_max[3]; /* inclusive chunk index range */
+} ivx_region_candidate;
+typedef struct ivx_split_info {
+    uint32_t n_regions;               /* count_regions */
+    uint32_t has_two;                 /* find_two_disconnected_regions().is_some() */
+    ivx_region_candidate candidates[2];
+    uint32_t smallest;                /* index into candidates of the region an extraction would split off */
+    uint32_t n_local_regions;         /* total local regions (entries of region_roots) */
+    uint32_t n_connections;           /* distinct cross-chunk region connections found */
+    float device_ms;                  /* device time of the labelling + connection kernels */
+    float host_ms;                    /* host time of the chunk-level union-find */
+} ivx_split_info;
+typedef struct ivx_chunk_regions {
+    uint16_t region_count;            /* NonUniformChunkSplitDetectionData (split_detection.rs:77-84); uniform: 1 */
+    uint16_t boundary_region_count;
+    uint32_t first_region;            /* index of the chunk's region 0 in region_roots */
+} ivx_chunk_regions;
+int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* object, ivx_split_info* out);
+/* Results of the last resolve: per-voxel LocalRegionLabels (4096 per NonUniform chunk in linear chunk
+ * order like ivx_object_download; 255 = empty), per-chunk region counts, and the resolved root
+ * GlobalRegionLabel of every local region. Any pointer may be NULL. */
+int ivx_object_split_detection_download(ivx_ctx* ctx, const ivx_object* object, uint8_t* voxel_labels,
+                                        size_t label_capacity, ivx_chunk_regions* per_chunk,
+                                        size_t chunk_capacity, uint32_t* region_roots,
+                                        size_t region_capacity);
+
 #ifdef __cplusplus
 }
 #endif
