@@ -69,7 +69,7 @@ class RegionCandidate(C.Structure):
 class SplitInfo(C.Structure):
     _fields_ = [("n_regions", C.c_uint32), ("has_two", C.c_uint32), ("candidates", RegionCandidate * 2),
                 ("smallest", C.c_uint32), ("n_local_regions", C.c_uint32), ("n_connections", C.c_uint32),
-                ("device_ms", C.c_float), ("host_ms", C.c_float)]
+                ("n_relabelled_chunks", C.c_uint32), ("device_ms", C.c_float), ("host_ms", C.c_float)]
 
 
 CHUNK_REGIONS_DTYPE = np.dtype([("region_count", "<u2"), ("boundary_region_count", "<u2"), ("first_region", "<u4")])

@@ -1027,6 +1027,8 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     ctx->release(obj->d_slot_of);
     ctx->release(obj->d_convert_flag);
     ctx->release(obj->d_labels);
+    ctx->release(obj->d_regions);
+    ctx->release(obj->d_label_stale);
     delete obj;
 }
 
@@ -1140,6 +1142,15 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3
     obj->slots_used += w[5];
     KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n,
                                   0, obj->nb[0], persistent_grid(ctx, n, 8), st));
+    {
+        // region labels of the touched chunks and of any neighbour converted to non-uniform are stale (split.cu)
+        uint32_t lo3[3], hi3[3];
+        for (int d = 0; d < 3; ++d) {
+            lo3[d] = b.c0[d];
+            hi3[d] = r.c1[d] + 1;
+        }
+        KL(ctx, launch_mark_box(obj->d_label_stale, obj->nb, lo3, hi3, 1, st));
+    }
     if (w[4]) {
         // removed chunks → update_occupied_ranges (intersection.rs:387-389)
         KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, counters + 6,

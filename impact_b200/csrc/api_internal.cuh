@@ -123,6 +123,8 @@ struct ivx_object {
     // connected regions (split.cu): device labels per slot, host results of the last resolve
     uint8_t* d_labels = nullptr;
     uint32_t label_slots = 0;
+    uint32_t* d_regions = nullptr;      // per chunk: kind << 16 | boundary_region_count << 8 | region_count
+    uint8_t* d_label_stale = nullptr;   // per chunk: modified since its labels were computed
     std::vector<uint32_t> h_chunk_regions;  // per chunk: kind << 16 | boundary_region_count << 8 | region_count
     std::vector<uint32_t> h_first_region;
     std::vector<uint32_t> h_region_roots;

@@ -170,6 +170,11 @@ cudaError_t launch_assign_slots(const DevChunk* chunks, const uint32_t* need, co
 cudaError_t launch_occupied_ranges(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t first_i,
                                    const unsigned char* voxels, uint32_t* occ, uint32_t grid, cudaStream_t st);
 
+// ---- split.cu ------------------------------------------------------------------
+// sets arr[chunk] = value for the chunks of the box [lo, hi) (clamped to the grid); no-op when arr is null
+cudaError_t launch_mark_box(uint8_t* arr, const uint32_t nb[3], const uint32_t lo[3], const uint32_t hi[3], uint8_t value,
+                            cudaStream_t st);
+
 // ---- api.cu helpers ------------------------------------------------------------
 cudaError_t launch_flag_dirty_exposed(const DevChunk* chunks, const uint8_t* dirty, uint32_t n, uint32_t* exposed_flag,
                                       uint32_t* dirty_flag, cudaStream_t st);

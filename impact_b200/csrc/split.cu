@@ -14,11 +14,12 @@
 // the local label numbering, which in turn depends on which voxel the reference's union-find leaves as the
 // root of each local region ("the current voxel's root absorbs the roots of its upper neighbours", visited in
 // linear voxel order). That is a property of the visiting order, not of the component structure, so a parallel
-// labelling cannot reproduce it. One lane per chunk therefore replays the reference's exact sequence on
-// shared-memory state (8 KiB parents + 4 KiB flags + 4 KiB labels, ~14 chunks in flight per SM), while the
-// embarrassingly parallel parts (loading, the two trivial cases "all voxels present" / "none present", the final
-// label propagation, the stores) use the whole warp. The global pass works on ~10^5 regions and stays on the
-// host, as in the reference.
+// generic parallel labelling cannot reproduce it. One warp per chunk therefore replays the reference's sequence
+// on shared-memory state (8 KiB parents + 4 KiB flags + 4 KiB labels, ~13 chunks in flight per SM), parallel
+// only where the order provably does not matter: all merges of one k-run go under the same root, the
+// boundary traversal is taken 32 positions at a time with the earliest lane winning a contested root, and
+// label numbers are ballot prefix counts. The global pass works on ~10^5 regions and stays on the host, as
+// in the reference.
 #include <chrono>
 
 #include "api_internal.cuh"
@@ -27,13 +28,41 @@ namespace ivx {
 
 constexpr uint32_t LABEL_EMPTY = 255u;
 
+// Labels are a pure function of a chunk's own voxel flags, so only chunks modified since the last resolve
+// (stale != 0) are re-labelled; the others keep their labels and counts.
 __global__ void k_init_regions(const DevChunk* __restrict__ chunks, uint32_t n, uint32_t* __restrict__ regions,
-                               uint32_t* __restrict__ nu_flag) {
+                               uint8_t* __restrict__ stale, uint32_t* __restrict__ work_flag) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const uint32_t kind = chunks[c].kind;
-    regions[c] = kind == 1u ? ((1u << 16) | (1u << 8) | 1u) : (kind << 16);
-    nu_flag[c] = kind == 2u ? 1u : 0u;
+    const bool relabel = kind == 2u && stale[c] != 0;
+    if (kind != 2u) regions[c] = kind == 1u ? ((1u << 16) | (1u << 8) | 1u) : 0u;
+    work_flag[c] = relabel ? 1u : 0u;
+    stale[c] = 0;
+}
+
+__global__ void k_mark_box(uint8_t* __restrict__ arr, uint3 nb, uint3 lo, uint3 hi, uint8_t value) {
+    const uint32_t ext_y = hi.y - lo.y, ext_z = hi.z - lo.z;
+    const uint32_t total = (hi.x - lo.x) * ext_y * ext_z;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const uint32_t k = lo.z + t % ext_z, j = lo.y + (t / ext_z) % ext_y, i = lo.x + t / (ext_z * ext_y);
+    arr[(i * nb.y + j) * nb.z + k] = value;
+}
+
+cudaError_t launch_mark_box(uint8_t* arr, const uint32_t nb[3], const uint32_t lo[3], const uint32_t hi[3], uint8_t value,
+                            cudaStream_t st) {
+    if (!arr) return cudaSuccess;
+    uint32_t h[3], l[3];
+    for (int d = 0; d < 3; ++d) {
+        l[d] = std::min(lo[d], nb[d]);
+        h[d] = std::min(hi[d], nb[d]);
+        if (l[d] >= h[d]) return cudaSuccess;
+    }
+    const uint32_t total = (h[0] - l[0]) * (h[1] - l[1]) * (h[2] - l[2]);
+    k_mark_box<<<(total + 255) / 256, 256, 0, st>>>(arr, make_uint3(nb[0], nb[1], nb[2]), make_uint3(l[0], l[1], l[2]),
+                                                    make_uint3(h[0], h[1], h[2]), value);
+    return cudaGetLastError();
 }
 
 __device__ __forceinline__ uint32_t find_root_compress(uint16_t* par, uint32_t idx) {
@@ -83,75 +112,107 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
         }
         for (int idx = lane; idx < 4096; idx += 32) s_par[idx] = (uint16_t)idx;
         __syncwarp();
-        if (lane == 0) {
-            // ---- union pass (split_detection.rs:701-744): linear voxel order, upper neighbours only ----
-            for (uint32_t idx = 0; idx < 4096u; ++idx) {
-                const uint32_t f = s_flags[idx];
-                if (f & 1u) continue;
-                if ((f & 0xE0u) == 0u) continue;  // no upper neighbour inside the chunk: nothing to merge
-                const uint32_t root = find_root_compress(s_par, idx);
-                const uint32_t i = idx >> 8, j = (idx >> 4) & 15u, k = idx & 15u;
-                if (i < 15u && (f & (1u << 5))) {
-                    const uint32_t r = find_root_compress(s_par, idx + 256u);
-                    if (r != root) s_par[r] = (uint16_t)root;
+        // ---- union pass (split_detection.rs:701-744) ----
+        // The reference visits the voxels in linear order; the visited voxel's root absorbs the roots of its
+        // upper x / y / z neighbours. Along a k-run of linked voxels every voxel therefore ends up under the
+        // root the run's FIRST voxel had when it was visited, and so do all upper neighbours of the run — in
+        // whatever order those merges happen. One run per step: lane 0 finds the run's root, then the lanes of
+        // the run's voxels merge their upper neighbours' sets under it concurrently (racing writes all store
+        // the same root; path compression only ever stores an ancestor).
+        for (uint32_t row = 0; row < 256u; ++row) {
+            const uint32_t f = lane < 16 ? (uint32_t)s_flags[row * 16u + lane] : 1u;
+            const uint32_t present = __ballot_sync(0xffffffffu, (f & 1u) == 0u) & 0xFFFFu;
+            if (present == 0u) continue;
+            // voxel k is linked to k + 1 when it is present and carries HAS_ADJACENT_Z_UP
+            const uint32_t link = __ballot_sync(0xffffffffu, (f & 1u) == 0u && (f & 0x80u) != 0u && lane < 15) & 0x7FFFu;
+            const uint32_t i = row >> 4, j = row & 15u;
+            uint32_t todo = present;
+            while (todo) {
+                const uint32_t k0 = (uint32_t)__ffs(todo) - 1u;
+                // the run [k0, k1]: extend while linked
+                uint32_t k1 = k0;
+                while (k1 < 15u && ((link >> k1) & 1u) && ((present >> (k1 + 1u)) & 1u)) ++k1;
+                const uint32_t run = ((2u << k1) - 1u) & ~((1u << k0) - 1u);
+                todo &= ~run;
+                uint32_t root = 0;
+                if (lane == 0) root = find_root_compress(s_par, row * 16u + k0);
+                root = __shfl_sync(0xffffffffu, root, 0);
+                __syncwarp();
+                if ((run >> lane) & 1u) {
+                    const uint32_t idx = row * 16u + (uint32_t)lane;
+                    if (i < 15u && (f & (1u << 5))) {
+                        const uint32_t r = find_root_compress(s_par, idx + 256u);
+                        if (r != root) s_par[r] = (uint16_t)root;
+                    }
+                    if (j < 15u && (f & (1u << 6))) {
+                        const uint32_t r = find_root_compress(s_par, idx + 16u);
+                        if (r != root) s_par[r] = (uint16_t)root;
+                    }
+                    if ((link >> lane) & 1u) {
+                        const uint32_t r = find_root_compress(s_par, idx + 1u);
+                        if (r != root) s_par[r] = (uint16_t)root;
+                    }
                 }
-                if (j < 15u && (f & (1u << 6))) {
-                    const uint32_t r = find_root_compress(s_par, idx + 16u);
-                    if (r != root) s_par[r] = (uint16_t)root;
-                }
-                if (k < 15u && (f & (1u << 7))) {
-                    const uint32_t r = find_root_compress(s_par, idx + 1u);
-                    if (r != root) s_par[r] = (uint16_t)root;
-                }
+                __syncwarp();
             }
-            // ---- representative voxels of boundary regions, in the reference's face order (:760-796) ----
-            uint32_t current = 0;
-            auto visit = [&](uint32_t i, uint32_t j, uint32_t k) {
-                const uint32_t idx = (i << 8) | (j << 4) | k;
-                if (s_flags[idx] & 1u) {
-                    s_lab[idx] = (uint8_t)LABEL_EMPTY;
-                    return;
-                }
-                const uint32_t set_id = find_root_compress(s_par, idx);
-                bool take = set_id == idx;
-                if (!take) {
-                    const uint32_t si = set_id >> 8, sj = (set_id >> 4) & 15u, sk = set_id & 15u;
-                    if (si > 0u && si < 15u && sj > 0u && sj < 15u && sk > 0u && sk < 15u) {
-                        s_par[set_id] = (uint16_t)idx;  // make_voxel_root
-                        s_par[idx] = (uint16_t)idx;
-                        take = true;
-                    }
-                }
-                if (take) {
-                    s_lab[idx] = (uint8_t)current;
-                    current = min(current + 1u, 255u);
-                }
-            };
-            for (uint32_t s = 0; s < 2; ++s)
-                for (uint32_t j = 0; j < 16; ++j)
-                    for (uint32_t k = 0; k < 16; ++k) visit(s ? 15u : 0u, j, k);
-            for (uint32_t s = 0; s < 2; ++s)
-                for (uint32_t i = 1; i < 15; ++i)
-                    for (uint32_t k = 0; k < 16; ++k) visit(i, s ? 15u : 0u, k);
-            for (uint32_t s = 0; s < 2; ++s)
-                for (uint32_t i = 1; i < 15; ++i)
-                    for (uint32_t j = 1; j < 15; ++j) visit(i, j, s ? 15u : 0u);
-            const uint32_t boundary = current;
-            // ---- interior-only regions (:803-822) ----
-            for (uint32_t i = 1; i < 15; ++i)
-                for (uint32_t j = 1; j < 15; ++j)
-                    for (uint32_t k = 1; k < 15; ++k) {
-                        const uint32_t idx = (i << 8) | (j << 4) | k;
-                        if (s_par[idx] != idx) continue;
-                        if (!(s_flags[idx] & 1u)) {
-                            s_lab[idx] = (uint8_t)current;
-                            current = min(current + 1u, 255u);
-                        } else {
-                            s_lab[idx] = (uint8_t)LABEL_EMPTY;
-                        }
-                    }
-            s_counts[0] = boundary;
-            s_counts[1] = current;
+        }
+        // ---- representative voxels of boundary regions, in the reference's face order (:760-796) ----
+        // 32 boundary voxels of the traversal per step. A region is labelled where its root voxel is visited
+        // if the root lies on the boundary, else at its first visited boundary voxel, which then becomes the
+        // root (make_voxel_root); labels count these events in traversal order.
+        uint32_t current = 0;
+        for (uint32_t base = 0; base < 1352u; base += 32u) {
+            const uint32_t pos = base + (uint32_t)lane;
+            uint32_t idx = 0xFFFFu;
+            if (pos < 512u) {
+                idx = ((pos < 256u ? 0u : 15u) << 8) | (pos & 255u);
+            } else if (pos < 960u) {
+                const uint32_t p = pos < 736u ? pos - 512u : pos - 736u;
+                idx = ((1u + (p >> 4)) << 8) | ((pos < 736u ? 0u : 15u) << 4) | (p & 15u);
+            } else if (pos < 1352u) {
+                const uint32_t p = pos < 1156u ? pos - 960u : pos - 1156u;
+                idx = ((1u + p / 14u) << 8) | ((1u + p % 14u) << 4) | (pos < 1156u ? 0u : 15u);
+            }
+            const bool valid = idx != 0xFFFFu;
+            const bool present = valid && (s_flags[idx] & 1u) == 0u;
+            uint32_t set_id = 0xFFFFFFFFu;
+            if (present) set_id = find_root_compress(s_par, idx);
+            __syncwarp();
+            bool interior_root = false;
+            if (present && set_id != idx) {
+                const uint32_t si = set_id >> 8, sj = (set_id >> 4) & 15u, sk = set_id & 15u;
+                interior_root = si > 0u && si < 15u && sj > 0u && sj < 15u && sk > 0u && sk < 15u;
+            }
+            // among the lanes that hit the same interior root, the earliest position takes it over
+            const uint32_t peers = __match_any_sync(0xffffffffu, interior_root ? set_id : (0x10000u | (uint32_t)lane));
+            bool event = present && set_id == idx;
+            if (interior_root && (uint32_t)(__ffs(peers) - 1) == (uint32_t)lane) {
+                s_par[set_id] = (uint16_t)idx;  // make_voxel_root
+                s_par[idx] = (uint16_t)idx;
+                event = true;
+            }
+            const uint32_t events = __ballot_sync(0xffffffffu, event);
+            if (event) s_lab[idx] = (uint8_t)min(current + __popc(events & ((1u << lane) - 1u)), 255u);
+            else if (valid && !present) s_lab[idx] = (uint8_t)LABEL_EMPTY;
+            current += __popc(events);
+            __syncwarp();
+        }
+        const uint32_t boundary = current;
+        // ---- interior-only regions: interior root voxels in linear order (:803-822) ----
+        for (uint32_t base = 0; base < 4096u; base += 32u) {
+            const uint32_t idx = base + (uint32_t)lane;
+            const uint32_t vi = idx >> 8, vj = (idx >> 4) & 15u, vk = idx & 15u;
+            const bool interior = vi > 0u && vi < 15u && vj > 0u && vj < 15u && vk > 0u && vk < 15u;
+            const bool is_root = interior && s_par[idx] == idx;
+            const bool event = is_root && (s_flags[idx] & 1u) == 0u;
+            const uint32_t events = __ballot_sync(0xffffffffu, event);
+            if (event) s_lab[idx] = (uint8_t)min(current + __popc(events & ((1u << lane) - 1u)), 255u);
+            else if (is_root) s_lab[idx] = (uint8_t)LABEL_EMPTY;
+            current += __popc(events);
+        }
+        if (lane == 0) {
+            s_counts[0] = min(boundary, 255u);
+            s_counts[1] = min(current, 255u);
             // the reference asserts boundary < 255 and total < 255 (:798, :835)
             if (boundary >= 255u || current >= 255u) atomicExch(error_flag, 1u);
         }
@@ -308,8 +369,15 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
             IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "region labels (%u chunks): out of device memory", obj->slot_capacity);
         }
         obj->label_slots = obj->slot_capacity;
+        if (obj->d_label_stale) CU(ctx, cudaMemsetAsync(obj->d_label_stale, 1, n, st));  // the new buffer holds no labels
     }
-    uint32_t* regions = tmp.get<uint32_t>(n);
+    if (!obj->d_regions) {
+        obj->d_regions = static_cast<uint32_t*>(ctx->alloc((size_t)n * 4));
+        obj->d_label_stale = static_cast<uint8_t*>(ctx->alloc(n));
+        if (!obj->d_regions || !obj->d_label_stale) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "split detection: out of device memory");
+        CU(ctx, cudaMemsetAsync(obj->d_label_stale, 1, n, st));  // nothing labelled yet
+    }
+    uint32_t* regions = obj->d_regions;
     uint32_t* flag = tmp.get<uint32_t>(n);
     uint32_t* scan = tmp.get<uint32_t>(n);
     uint32_t* work = tmp.get<uint32_t>(n);
@@ -322,7 +390,7 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
     cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
     ctx->launches++;
-    k_init_regions<<<(n + 255) / 256, 256, 0, st>>>(obj->d_chunks, n, regions, flag);
+    k_init_regions<<<(n + 255) / 256, 256, 0, st>>>(obj->d_chunks, n, regions, obj->d_label_stale, flag);
     CU(ctx, cudaGetLastError());
     KL(ctx, launch_exclusive_scan(flag, scan, n, counters, st));
     KL(ctx, launch_scatter_active(flag, scan, n, work, st));
@@ -451,6 +519,7 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
     out->has_two = n_regions >= 2 ? 1u : 0u;
     out->n_local_regions = total;
     out->n_connections = n_records;
+    out->n_relabelled_chunks = n_work;
     if (out->has_two) {
         for (int q = 0; q < 2; ++q) {
             out->candidates[q].label = two[q];

@@ -249,7 +249,8 @@ class VoxelObject:
                 for c in si.candidates]
         out = {"n_regions": int(si.n_regions), "has_two": bool(si.has_two), "two": (cand[0]["label"], cand[1]["label"]),
                "smallest": int(si.smallest), "candidates": cand, "n_local_regions": int(si.n_local_regions),
-               "n_connections": int(si.n_connections), "device_ms": float(si.device_ms), "host_ms": float(si.host_ms)}
+               "n_connections": int(si.n_connections),
+               "n_relabelled_chunks": int(si.n_relabelled_chunks), "device_ms": float(si.device_ms), "host_ms": float(si.host_ms)}
         if download:
             inf = self.info()
             n = int(np.prod(inf["chunk_counts"]))

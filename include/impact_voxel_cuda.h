@@ -339,6 +339,7 @@ typedef struct ivx_split_info {
     uint32_t smallest;                /* index into candidates of the region an extraction would split off */
     uint32_t n_local_regions;         /* total local regions (entries of region_roots) */
     uint32_t n_connections;           /* distinct cross-chunk region connections found */
+    uint32_t n_relabelled_chunks;     /* chunks whose local labels were recomputed (modified since the last resolve) */
     float device_ms;                  /* device time of the labelling + connection kernels */
     float host_ms;                    /* host time of the chunk-level union-find */
 } ivx_split_info;
