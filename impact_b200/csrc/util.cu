@@ -4,7 +4,9 @@
 
 namespace ivx {
 
-// Exclusive scan of n uint32 by one 1024-thread CTA (n is chunk-count sized).
+// Exclusive scan of n uint32 by one 1024-thread CTA (n is chunk-count sized): 8 consecutive elements per thread
+// and step (two 16-byte loads / stores), so a 2 x 10^5 element array takes 25 steps.
+constexpr int SCAN_PER_THREAD = 8;
 __global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
                                                          uint32_t n, uint32_t* __restrict__ total) {
     __shared__ uint32_t s_warp[32];
@@ -12,10 +14,25 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + tid;
-        const uint32_t v = i < n ? in[i] : 0u;
-        uint32_t x = v;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    for (uint32_t base = 0; base < n; base += 1024u * SCAN_PER_THREAD) {
+        const uint32_t i0 = base + (uint32_t)tid * SCAN_PER_THREAD;
+        uint32_t v[SCAN_PER_THREAD];
+        if (aligned && i0 + SCAN_PER_THREAD <= n) {
+            const uint4 a = *reinterpret_cast<const uint4*>(in + i0), b = *reinterpret_cast<const uint4*>(in + i0 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < SCAN_PER_THREAD; ++q) v[q] = i0 + q < n ? in[i0 + q] : 0u;
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < SCAN_PER_THREAD; ++q) {
+            const uint32_t t = v[q];
+            v[q] = sum;  // exclusive within the thread
+            sum += t;
+        }
+        uint32_t x = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -34,10 +51,17 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restr
         }
         __syncthreads();
         const uint32_t carry = s_carry;
-        const uint32_t warp_off = warp > 0 ? s_warp[warp - 1] : 0u;
-        if (i < n) out[i] = carry + warp_off + x - v;
+        const uint32_t off = carry + (warp > 0 ? s_warp[warp - 1] : 0u) + x - sum;
+        if (aligned && i0 + SCAN_PER_THREAD <= n) {
+            *reinterpret_cast<uint4*>(out + i0) = make_uint4(off + v[0], off + v[1], off + v[2], off + v[3]);
+            *reinterpret_cast<uint4*>(out + i0 + 4) = make_uint4(off + v[4], off + v[5], off + v[6], off + v[7]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < SCAN_PER_THREAD; ++q)
+                if (i0 + q < n) out[i0 + q] = off + v[q];
+        }
         __syncthreads();
-        if (tid == 1023) s_carry = carry + warp_off + x;
+        if (tid == 1023) s_carry = off + sum;
         __syncthreads();
     }
     if (tid == 0 && total) *total = s_carry;
