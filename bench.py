@@ -224,16 +224,24 @@ def run_gpu(args):
             obj = VoxelObject.generate(vg)
             return obj, VoxelObjectMesh.create(obj)
         # x-slab per rank → halo planes over NCCL → derived state → mesh → mesh gathered on rank 0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record(stream)
         obj = VoxelObject.generate(vg, slab)
+        ev[1].record(stream)
         halo_stats.update(D.exchange_halos_and_finalize(obj, ranges, rank, dev))
+        ev[2].record(stream)
         mesh = VoxelObjectMesh.create(obj)
+        ev[3].record(stream)
         merged = D.gather_mesh(D.device_mesh_tensors(mesh, dev), rank, world, dev)
+        ev[4].record(stream)
+        phase_events.append(ev)
         if merged is not None:
             halo_stats["merged_vertices"] = int(merged["positions"].shape[0])
             halo_stats["merged_indices"] = int(merged["indices"].shape[0])
         return obj, mesh
 
     halo_stats = {}
+    phase_events = []  # multi-GPU: (generate, halo exchange + derive, mesh, gather) per step
 
     with torch.cuda.stream(stream):
         info = None
@@ -261,6 +269,11 @@ def run_gpu(args):
             obj.free()
         clocks = sampler.stop()
         barrier()
+        if phase_events:
+            last = phase_events[-args.steps:]
+            names = ("generate_slab", "halo_exchange_and_derive", "mesh", "gather_mesh")
+            halo_stats["rank0_phase_ms"] = {n: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in last]))
+                                            for i, n in enumerate(names)}
         launches = ctx.kernel_launch_count - launches0
         prof = ctx.profile_get()
         ctx.profile_enable(False)
@@ -327,10 +340,11 @@ def run_gpu(args):
         dom = max(prof, key=lambda k: prof[k][0])
         dom_ms, dom_n = prof[dom]
         dom_avg_s = (dom_ms / max(1, dom_n)) * 1e-3
-        # algorithmic bytes (dense definition): generation writes 3 B per grid voxel, meshing
-        # reads 2 B per grid voxel; one launch of a kernel processes this rank's whole slab
-        per_voxel = {"eval": 3.0, "types": 3.0, "fold_exact": 3.0, "fold_conservative": 3.0, "mesh_count": 2.0, "mesh_emit": 2.0,
-                     "boundary": 3.0}.get(dom, 5.0)
+        # algorithmic bytes (dense definition): generation leaves 3 B per grid voxel (k_eval writes the
+        # 1-byte signed-distance code; k_types reads it and writes the type and flag bytes), meshing reads 2 B per
+        # grid voxel; one launch of a kernel processes this rank's whole slab
+        per_voxel = {"eval": 1.0, "types": 3.0, "fold_exact": 3.0, "fold_conservative": 3.0, "mesh_count": 2.0,
+                     "mesh_emit": 2.0, "boundary": 3.0}.get(dom, 5.0)
         achieved = per_voxel * my_voxels / max(dom_avg_s, 1e-12) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
@@ -367,7 +381,8 @@ def run_gpu(args):
                          "algorithmic_bytes_per_voxel": per_voxel, "voxels_per_launch": my_voxels,
                          "avg_launch_ms": dom_avg_s * 1e3,
                          "note": "dense definition (SURVEY 8d): bytes the reference's layout moves per grid voxel; "
-                                 "the kernel is FP32-bound on simplex noise, see DESIGN.md"},
+                                 "the kernel is instruction-issue bound on simplex noise (ncu: issue slots 82-86 % busy, DRAM 1 %), "
+                                 "see DESIGN.md §4 and profiles/"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
             "whole_path_roofline_frac": (5.0 * total_voxels / step_s / 1e9) / peak,
         }
