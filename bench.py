@@ -206,7 +206,13 @@ def run_gpu(args):
     planes = (grid_shape[0] + 15) // 16
     from impact_b200 import distributed as D
 
-    ranges = D.slab_ranges(planes, world)
+    from impact_b200.voxel import plane_work
+
+    def partition():
+        """x-slabs of equal estimated work (ivx_program_plane_work; deterministic, so all ranks agree)."""
+        return D.slab_ranges_weighted(plane_work(vg), world) if world > 1 else [(0, planes)]
+
+    ranges = partition()
     slab = ranges[rank]
     dev = torch.device("cuda", local_rank)
     total_voxels = int(np.prod(grid_shape))
@@ -226,9 +232,10 @@ def run_gpu(args):
         # x-slab per rank → halo planes over NCCL → derived state → mesh → mesh gathered on rank 0
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record(stream)
-        obj = VoxelObject.generate(vg, slab)
+        step_ranges = partition()  # part of the job: every step re-derives the balanced partition
+        obj = VoxelObject.generate(vg, step_ranges[rank])
         ev[1].record(stream)
-        halo_stats.update(D.exchange_halos_and_finalize(obj, ranges, rank, dev))
+        halo_stats.update(D.exchange_halos_and_finalize(obj, step_ranges, rank, dev))
         ev[2].record(stream)
         mesh = VoxelObjectMesh.create(obj)
         ev[3].record(stream)
@@ -299,10 +306,15 @@ def run_gpu(args):
                                             C.c_uint32(graph.root_node_id), C.byref(prog)))
             o = C.c_void_p()
             if world > 1:
-                ctx.check(lib.ivx_object_generate_slab(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), C.c_uint32(slab[0]),
-                                                       C.c_uint32(slab[1]), C.byref(o)))
+                pw = np.zeros(planes, np.uint32)
+                npl = C.c_uint32()
+                ctx.check(lib.ivx_program_plane_work(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), L.ptr(pw), C.c_uint32(planes),
+                                                     C.byref(npl)))
+                rr = D.slab_ranges_weighted(pw, world)
+                ctx.check(lib.ivx_object_generate_slab(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), C.c_uint32(rr[rank][0]),
+                                                       C.c_uint32(rr[rank][1]), C.byref(o)))
                 view = VoxelObject(ctx, o)
-                D.exchange_halos_and_finalize(view, ranges, rank, dev)
+                D.exchange_halos_and_finalize(view, rr, rank, dev)
                 view.h = None  # `o` is freed below
             else:
                 ctx.check(lib.ivx_object_generate(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), C.byref(o)))
@@ -358,7 +370,7 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic",
             "config": {
                 "workload": args.workload, "description": desc, "grid_shape": grid_shape,
-                "chunks": int(np.prod(info[0]["chunk_counts"])), "parallelism": f"x-slab x{world}",
+                "chunks": int(np.prod(info[0]["chunk_counts"])), "parallelism": f"x-slab x{world}" + (" (work-balanced plane ranges)" if world > 1 else ""),
                 "slab_planes": [list(r) for r in ranges], "rank0_exchange": halo_stats,
                 "rank0_chunks": {"void": oi["n_void"], "uniform": oi["n_uniform"], "non_uniform": oi["n_non_uniform"]},
                 "rank0_mesh": {"vertices": info[1], "indices": info[2], "submeshes": info[3]},

@@ -30,6 +30,29 @@ def slab_ranges(n_planes: int, world: int) -> list[tuple[int, int]]:
     return [(min(n_planes, r * per), min(n_planes, (r + 1) * per)) for r in range(world)]
 
 
+def slab_ranges_weighted(work, world: int) -> list[tuple[int, int]]:
+    """Contiguous chunk-plane ranges per rank with (nearly) equal summed `work` (one non-negative number per
+    plane, e.g. `impact_b200.voxel.plane_work`): the r-th cut goes where the running sum is closest to r / world
+    of the total. Deterministic in `work`; ranks must pass identical arrays. Falls back to `slab_ranges` for
+    all-zero work."""
+    w = np.asarray(work, np.float64)
+    n = len(w)
+    total = float(w.sum())
+    if world <= 0 or n == 0 or not total > 0.0:
+        return slab_ranges(n, world)
+    prefix = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        i = int(np.searchsorted(prefix, target))
+        i = min(max(i, 1), n)
+        if abs(prefix[i - 1] - target) <= abs(prefix[i] - target):
+            i -= 1
+        cuts.append(min(n, max(cuts[-1], i)))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def slab_neighbours(ranges: list[tuple[int, int]], rank: int) -> tuple[int | None, int | None]:
     """Ranks owning the planes just below / above `rank`'s slab (empty slabs are skipped)."""
     b, e = ranges[rank]

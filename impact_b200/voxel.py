@@ -138,6 +138,19 @@ class SDFVoxelGenerator:
         self.voxel_type_generator = voxel_type_generator
 
 
+def plane_work(generator: SDFVoxelGenerator) -> np.ndarray:
+    """Estimated generation work per chunk plane (ivx_program_plane_work) for `distributed.slab_ranges_weighted`."""
+    ctx = generator.sdf_generator.ctx
+    tg = generator.voxel_type_generator.pod()
+    n = C.c_uint32()
+    ctx.check(ctx._lib.ivx_program_plane_work(ctx.h, generator.sdf_generator.h, C.c_float(generator.voxel_extent), L.ptr(tg),
+                                              None, C.c_uint32(0), C.byref(n)))
+    out = np.zeros(max(1, n.value), np.uint32)
+    ctx.check(ctx._lib.ivx_program_plane_work(ctx.h, generator.sdf_generator.h, C.c_float(generator.voxel_extent), L.ptr(tg),
+                                              L.ptr(out), C.c_uint32(len(out)), C.byref(n)))
+    return out[: n.value]
+
+
 class VoxelObject:
     """`VoxelObject` (object.rs:45-57), device resident."""
 

@@ -270,6 +270,13 @@ int ivx_object_generate(ivx_ctx* ctx, const ivx_program* program, float voxel_ex
 int ivx_object_generate_slab(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
                              const ivx_type_generator* type_generator, uint32_t chunk_i_begin,
                              uint32_t chunk_i_end, ivx_object** out_object);
+/* Work estimate per chunk plane of the x-major chunk grid (arbitrary integer units), for partitioning the
+ * planes into slabs of equal work instead of equal thickness: the conservative program-specialisation levels of
+ * generation run over the whole grid and classify 2^3-chunk blocks as void / inside / undecided. Deterministic, so
+ * every rank that calls it derives the same partition. out_work may be NULL to query *out_planes only. */
+int ivx_program_plane_work(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
+                           const ivx_type_generator* type_generator, uint32_t* out_work, uint32_t capacity,
+                           uint32_t* out_planes);
 /* upper bound of a halo_export in bytes (a whole plane of non-uniform chunks) */
 int ivx_object_halo_capacity(ivx_ctx* ctx, const ivx_object* object, size_t* out_bytes);
 int ivx_object_halo_export(ivx_ctx* ctx, const ivx_object* object, int side, void* device_buffer,

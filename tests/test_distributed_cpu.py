@@ -18,6 +18,23 @@ import helpers as H
 from impact_b200 import distributed as D
 
 
+def test_weighted_slab_ranges_balance_the_work():
+    rng = np.random.default_rng(0)
+    for planes in (1, 7, 60, 64):
+        for world in (1, 2, 3, 8):
+            w = rng.integers(0, 100, planes)
+            r = D.slab_ranges_weighted(w, world)
+            assert len(r) == world and r[0][0] == 0 and r[-1][1] == planes
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1)) and all(a <= b for a, b in r)
+    # an ellipsoid-like profile: the equal-thickness split leaves the end ranks idle, the weighted one does not
+    x = np.linspace(-1, 1, 60)
+    w = np.maximum(1.0 - x * x, 0.0) * 1000 + 1
+    sums = [w[a:b].sum() for a, b in D.slab_ranges_weighted(w, 8)]
+    even = [w[a:b].sum() for a, b in D.slab_ranges(60, 8)]
+    assert max(sums) < 1.25 * w.sum() / 8 < max(even)
+    assert D.slab_ranges_weighted(np.zeros(10), 4) == D.slab_ranges(10, 4)
+
+
 def test_slab_ranges_cover_the_planes_without_overlap():
     for planes in (0, 1, 5, 60, 64):
         for world in (1, 2, 3, 8):

@@ -173,3 +173,23 @@ def test_slabs_over_nccl_equal_the_whole_object(name):
         p.join(timeout=120)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_plane_work_estimate_tracks_the_object(ctx):
+    """ivx_program_plane_work: deterministic, one entry per chunk plane, zero-ish outside the object and largest
+    through its middle; the weighted partition of an off-centre object differs from the equal-thickness one."""
+    from impact_b200.voxel import plane_work
+    from impact_b200.graph import SDFGraph
+
+    g = SDFGraph()
+    a = g.sphere(60.0)
+    b = g.translation(g.sphere(12.0), [150.0, 0.0, 0.0])
+    g.union(a, b, 1.0)
+    vg = SDFVoxelGenerator(1.0, ctx.build_generator(g), H.GRADIENT4)
+    w = plane_work(vg)
+    w2 = plane_work(vg)
+    obj = VoxelObject.generate(vg)
+    assert len(w) == obj.info()["chunk_counts"][0] and np.array_equal(w, w2)
+    assert w[: len(w) // 3].sum() > 3 * w[2 * len(w) // 3:].sum()  # the big sphere sits at low x
+    r = D.slab_ranges_weighted(w, 4)
+    assert r != D.slab_ranges(len(w), 4) and r[0][0] == 0 and r[-1][1] == len(w)
