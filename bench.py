@@ -279,8 +279,11 @@ def run_gpu(args):
         if phase_events:
             last = phase_events[-args.steps:]
             names = ("generate_slab", "halo_exchange_and_derive", "mesh", "gather_mesh")
-            halo_stats["rank0_phase_ms"] = {n: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in last]))
-                                            for i, n in enumerate(names)}
+            mine = torch.tensor([float(np.mean([e[i].elapsed_time(e[i + 1]) for e in last])) for i in range(4)],
+                                dtype=torch.float64, device="cuda")
+            allp = [torch.zeros(4, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(allp, mine)
+            halo_stats["phase_ms_per_rank"] = {n: [round(float(t[i]), 3) for t in allp] for i, n in enumerate(names)}
         launches = ctx.kernel_launch_count - launches0
         prof = ctx.profile_get()
         ctx.profile_enable(False)
