@@ -497,7 +497,12 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                 f3 blo, bhi;
                 aabb_of_transformed(M, lo, hi, blo, bhi);
                 const f3 ctr = 0.5f * (blo + bhi);
-                const float rad = norm3(0.5f * (bhi - blo));
+                // The node transform is a similarity (translations, rotations, uniform scalings: atomic.rs:495-596),
+                // so every sample of the block lies within scale * half-diagonal of the block centre's image —
+                // tighter than the diagonal of the rotated block's axis-aligned box for rotated leaves.
+                const float m_scale = fmaxf(norm3(mk3(M[0], M[1], M[2])), fmaxf(norm3(mk3(M[4], M[5], M[6])), norm3(mk3(M[8], M[9], M[10]))));
+                const float rad = fminf(norm3(0.5f * (bhi - blo)),
+                                        m_scale * (0.8660254f * (hi.x - lo.x)) * 1.00001f + 1e-4f);
                 const float vc = sd_leaf(n.kind, n.p, ctr);
                 const float e = 1e-3f + 1e-4f * (fabsf(vc) + rad);
                 float rlo = vc - rad - e, rhi = vc + rad + e;
