@@ -669,17 +669,31 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k_fold(FoldArgs a) {
                     olen = seg_a + 1;
                 } else {
                     if (lane == 0) {
-                        // value range of the applied smooth op: min/max of the operands, moved by at most k/4
-                        float rl, rh;
-                        const float q = 0.25f * k;
+                        // value range of the applied smooth op: min / max of the operands moved by h^2 / (4k),
+                        // h = max(k - |u - v|, 0) (generation/sdf.rs:89-102). Over the block |u - v| lies in
+                        // [dmin, dmax] (from the operand ranges), so the shift lies in
+                        // [(k - dmax)^2 / 4k, (k - dmin)^2 / 4k] — far tighter than [0, k/4] once the operands
+                        // are known to differ, which matters with the asteroid's k of 100 voxels.
+                        float rl, rh, ulo, uhi, vlo, vhi;
+                        if (n.kind == IVX_UNION) { ulo = alo; uhi = ahi; vlo = blo2; vhi = bhi2; }
+                        else if (n.kind == IVX_SUBTRACTION) { ulo = -ahi; uhi = -alo; vlo = blo2; vhi = bhi2; }
+                        else { ulo = -ahi; uhi = -alo; vlo = -bhi2; vhi = -blo2; }
+                        float q = 0.0f, qmin = 0.0f;
+                        if (k > 0.0f) {
+                            const float dmin = fmaxf(0.0f, fmaxf(ulo - vhi, vlo - uhi));
+                            const float dmax = fmaxf(uhi - vlo, vhi - ulo);
+                            const float hmax = fmaxf(k - dmin, 0.0f), hmin = fmaxf(k - dmax, 0.0f);
+                            q = fminf((hmax * hmax) * (0.25f / k) * 1.0001f + 1e-5f, 0.25f * k);
+                            qmin = fmaxf((hmin * hmin) * (0.25f / k) * 0.9999f - 1e-5f, 0.0f);
+                        }
                         if (n.kind == IVX_UNION) {
                             rl = fminf(alo, blo2) - q;
-                            rh = fminf(ahi, bhi2);
+                            rh = fminf(ahi, bhi2) - qmin;
                         } else if (n.kind == IVX_SUBTRACTION) {
-                            rl = fmaxf(alo, -bhi2);
+                            rl = fmaxf(alo, -bhi2) + qmin;
                             rh = fmaxf(ahi, -blo2) + q;
                         } else {
-                            rl = fmaxf(alo, blo2);
+                            rl = fmaxf(alo, blo2) + qmin;
                             rh = fmaxf(ahi, bhi2) + q;
                         }
                         if (decision == 2) {  // may also be skipped in some chunks: result == a there
