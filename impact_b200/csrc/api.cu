@@ -975,7 +975,7 @@ bool halo_plane(const ivx_object* obj, int side, HaloPlane& hp) {
 
 int ivx_object_halo_capacity(ivx_ctx* ctx, const ivx_object* obj, size_t* out_bytes) {
     if (!ctx || !obj || !out_bytes) return IVX_ERR_INVALID_ARGUMENT;
-    *out_bytes = (size_t)obj->nb[1] * obj->nb[2] * (sizeof(DevChunk) + SLOT_BYTES);
+    *out_bytes = halo_message_bytes(obj->nb[1] * obj->nb[2]);
     return IVX_OK;
 }
 
@@ -984,17 +984,10 @@ int ivx_object_halo_export(ivx_ctx* ctx, const ivx_object* obj, int side, void* 
     cudaSetDevice(ctx->device);
     HaloPlane hp;
     if (!halo_plane(obj, side, hp)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object has no neighbour slab on side %d", side);
-    Tmp tmp(ctx);
-    uint32_t* flag = tmp.get<uint32_t>(hp.plane_chunks);
-    uint32_t* ord = tmp.get<uint32_t>(hp.plane_chunks);
-    if (!flag || !ord) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "halo export: out of device memory");
-    KL(ctx, launch_halo_flags(obj->d_chunks, hp.own_first, hp.plane_chunks, flag, ctx->stream));
-    KL(ctx, launch_exclusive_scan(flag, ord, hp.plane_chunks, ctx->d_scratch + 29, ctx->stream));
-    uint32_t nnu;
-    if (int rc = read_words(ctx, ctx->d_scratch + 29, 1, &nnu)) return rc;
-    const size_t bytes = (size_t)hp.plane_chunks * sizeof(DevChunk) + (size_t)nnu * SLOT_BYTES;
+    const size_t bytes = halo_message_bytes(hp.plane_chunks);
     if (capacity < bytes) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "halo export needs %zu bytes, buffer has %zu", bytes, capacity);
-    KL(ctx, launch_halo_pack(obj->d_chunks, hp.own_first, hp.plane_chunks, ord, obj->d_voxels,
+    // the layer of the boundary plane that touches the neighbour: i = 0 of my lowest plane, i = 15 of my highest
+    KL(ctx, launch_halo_pack(obj->d_chunks, hp.own_first, hp.plane_chunks, side == 0 ? 0u : 15u, obj->d_voxels,
                              static_cast<unsigned char*>(d_buf), ctx->stream));
     *out_bytes = bytes;
     return IVX_OK;
@@ -1006,15 +999,15 @@ int ivx_object_halo_import(ivx_ctx* ctx, ivx_object* obj, int side, const void* 
     HaloPlane hp;
     if (!halo_plane(obj, side, hp)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object has no neighbour slab on side %d", side);
     if (!obj->derive_pending) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "halo import after ivx_object_slab_finalize");
-    const size_t head = (size_t)hp.plane_chunks * sizeof(DevChunk);
-    if (bytes < head || (bytes - head) % SLOT_BYTES != 0)
-        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "halo buffer of %zu bytes does not hold a plane of %u chunks", bytes, hp.plane_chunks);
-    const uint32_t nnu = (uint32_t)((bytes - head) / SLOT_BYTES);
-    if (nnu > hp.plane_chunks) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "halo buffer holds more chunks than a plane");
-    if (int rc = ensure_slots(ctx, obj, nnu)) return rc;
-    KL(ctx, launch_halo_unpack(obj->d_chunks, hp.halo_first, hp.plane_chunks, obj->slots_used, obj->d_voxels,
-                               static_cast<const unsigned char*>(d_buf), ctx->stream));
-    obj->slots_used += nnu;
+    if (bytes != halo_message_bytes(hp.plane_chunks))
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "halo buffer of %zu bytes does not hold a plane of %u chunks (%zu bytes)", bytes,
+                 hp.plane_chunks, halo_message_bytes(hp.plane_chunks));
+    // one slot per chunk of the plane was reserved at generation, so importing never moves the pool
+    if (int rc = ensure_slots(ctx, obj, hp.plane_chunks)) return rc;
+    // my lower halo plane holds the neighbour's highest plane (its layer i = 15), my upper one its layer i = 0
+    KL(ctx, launch_halo_unpack(obj->d_chunks, hp.halo_first, hp.plane_chunks, obj->slots_used, side == 0 ? 15u : 0u,
+                               obj->d_voxels, static_cast<const unsigned char*>(d_buf), ctx->stream));
+    obj->slots_used += hp.plane_chunks;
     return IVX_OK;
 }
 

@@ -6,58 +6,57 @@
 // neighbouring rank's boundary plane: the 1-voxel brick padding (object/sdf.rs:35, 410-428), the face
 // adjacency / obscuredness rules (object.rs:1682-1704) and, for the "+x neighbour is non-uniform"
 // quad-ownership rule (object/sdf/surface_nets.rs:252-261), that plane's final chunk kinds.
-// These kernels pack a boundary plane into one contiguous buffer (chunk descriptors, then the 12 KiB
-// slots of its non-uniform chunks in plane order) for NCCL send/recv, and unpack it into the halo
-// plane on the receiving side.
+// These kernels pack a boundary plane into one contiguous fixed-size buffer (chunk descriptors, then one
+// 768-byte voxel layer per chunk) for NCCL send/recv, and unpack it into the halo plane on the receiving side.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace ivx {
 
-// one thread per chunk of the plane: non-uniform flag (for the scan that orders the payload)
-__global__ void k_halo_flags(const DevChunk* __restrict__ chunks, uint32_t plane_first, uint32_t plane_chunks,
-                             uint32_t* __restrict__ flag) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= plane_chunks) return;
-    flag[t] = chunks[plane_first + t].kind == 2 ? 1u : 0u;
-}
+// Per non-uniform chunk only the voxel layer that touches the neighbouring slab travels: 256 voxels x 3 planes =
+// 768 bytes at a fixed position (chunk t of the plane at head + t * 768), so a message has a fixed size known to
+// both sides and needs no size handshake.
+constexpr uint32_t HALO_LAYER_BYTES = 3u * 256u;
 
-// CTA per chunk of the plane: descriptor (slot := payload ordinal) + the three planes of its slot
-__global__ void __launch_bounds__(256) k_halo_pack(const DevChunk* __restrict__ chunks, uint32_t plane_first,
-                                                   uint32_t plane_chunks, const uint32_t* __restrict__ ordinal,
-                                                   const unsigned char* __restrict__ voxels, unsigned char* __restrict__ dst) {
+// CTA per chunk of the plane: descriptor + the layer `layer_i` (i = 0 or 15) of its three planes
+__global__ void __launch_bounds__(64) k_halo_pack(const DevChunk* __restrict__ chunks, uint32_t plane_first,
+                                                  uint32_t plane_chunks, uint32_t layer_i,
+                                                  const unsigned char* __restrict__ voxels, unsigned char* __restrict__ dst) {
     const uint32_t t = blockIdx.x;
     if (t >= plane_chunks) return;
     DevChunk c = chunks[plane_first + t];
     DevChunk* out_desc = reinterpret_cast<DevChunk*>(dst);
-    unsigned char* payload = dst + (size_t)plane_chunks * sizeof(DevChunk);
-    if (c.kind == 2) {
-        const uint4* src = reinterpret_cast<const uint4*>(voxels + (size_t)c.slot * SLOT_BYTES);
-        uint4* d = reinterpret_cast<uint4*>(payload + (size_t)ordinal[t] * SLOT_BYTES);
-        for (int q = threadIdx.x; q < (int)(SLOT_BYTES / 16); q += blockDim.x) d[q] = src[q];
+    unsigned char* payload = dst + (size_t)plane_chunks * sizeof(DevChunk) + (size_t)t * HALO_LAYER_BYTES;
+    const uint32_t q = threadIdx.x;  // 48 x 16 bytes
+    if (q < 48u) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c.kind == 2)
+            v = *reinterpret_cast<const uint4*>(voxels + (size_t)c.slot * SLOT_BYTES + (q >> 4) * 4096u + layer_i * 256u + (q & 15u) * 16u);
+        *reinterpret_cast<uint4*>(payload + q * 16u) = v;
     }
-    if (threadIdx.x == 0) {
-        c.slot = c.kind == 2 ? ordinal[t] : 0xFFFFFFFFu;
+    if (q == 0) {
+        c.slot = c.kind == 2 ? t : 0xFFFFFFFFu;
         out_desc[t] = c;
     }
 }
 
-__global__ void __launch_bounds__(256) k_halo_unpack(DevChunk* __restrict__ chunks, uint32_t plane_first,
-                                                     uint32_t plane_chunks, uint32_t first_slot,
-                                                     unsigned char* __restrict__ voxels, const unsigned char* __restrict__ src) {
+__global__ void __launch_bounds__(64) k_halo_unpack(DevChunk* __restrict__ chunks, uint32_t plane_first,
+                                                    uint32_t plane_chunks, uint32_t first_slot, uint32_t layer_i,
+                                                    unsigned char* __restrict__ voxels, const unsigned char* __restrict__ src) {
     const uint32_t t = blockIdx.x;
     if (t >= plane_chunks) return;
     const DevChunk* in_desc = reinterpret_cast<const DevChunk*>(src);
-    const unsigned char* payload = src + (size_t)plane_chunks * sizeof(DevChunk);
+    const unsigned char* payload = src + (size_t)plane_chunks * sizeof(DevChunk) + (size_t)t * HALO_LAYER_BYTES;
     DevChunk c = in_desc[t];
+    const uint32_t q = threadIdx.x;
     if (c.kind == 2) {
-        const uint32_t slot = first_slot + c.slot;
-        const uint4* s = reinterpret_cast<const uint4*>(payload + (size_t)c.slot * SLOT_BYTES);
-        uint4* d = reinterpret_cast<uint4*>(voxels + (size_t)slot * SLOT_BYTES);
-        for (int q = threadIdx.x; q < (int)(SLOT_BYTES / 16); q += blockDim.x) d[q] = s[q];
+        const uint32_t slot = first_slot + t;
+        if (q < 48u)
+            *reinterpret_cast<uint4*>(voxels + (size_t)slot * SLOT_BYTES + (q >> 4) * 4096u + layer_i * 256u + (q & 15u) * 16u) =
+                *reinterpret_cast<const uint4*>(payload + q * 16u);
         c.slot = slot;
     }
-    if (threadIdx.x == 0) {
+    if (q == 0) {
         c.pre = PRE_ACTIVE;
         chunks[plane_first + t] = c;
     }
@@ -78,22 +77,18 @@ __global__ void k_halo_kinds_unpack(DevChunk* __restrict__ chunks, uint32_t plan
     if (src[t] && chunks[plane_first + t].kind == 1) chunks[plane_first + t].pre = PRE_CONVERTED_HALO;
 }
 
-cudaError_t launch_halo_flags(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t* flag,
-                              cudaStream_t st) {
-    if (plane_chunks == 0) return cudaSuccess;
-    k_halo_flags<<<(plane_chunks + 255) / 256, 256, 0, st>>>(chunks, plane_first, plane_chunks, flag);
-    return cudaGetLastError();
-}
-cudaError_t launch_halo_pack(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, const uint32_t* ordinal,
+size_t halo_message_bytes(uint32_t plane_chunks) { return (size_t)plane_chunks * (sizeof(DevChunk) + HALO_LAYER_BYTES); }
+
+cudaError_t launch_halo_pack(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t layer_i,
                              const unsigned char* voxels, unsigned char* dst, cudaStream_t st) {
     if (plane_chunks == 0) return cudaSuccess;
-    k_halo_pack<<<plane_chunks, 256, 0, st>>>(chunks, plane_first, plane_chunks, ordinal, voxels, dst);
+    k_halo_pack<<<plane_chunks, 64, 0, st>>>(chunks, plane_first, plane_chunks, layer_i, voxels, dst);
     return cudaGetLastError();
 }
 cudaError_t launch_halo_unpack(DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t first_slot,
-                               unsigned char* voxels, const unsigned char* src, cudaStream_t st) {
+                               uint32_t layer_i, unsigned char* voxels, const unsigned char* src, cudaStream_t st) {
     if (plane_chunks == 0) return cudaSuccess;
-    k_halo_unpack<<<plane_chunks, 256, 0, st>>>(chunks, plane_first, plane_chunks, first_slot, voxels, src);
+    k_halo_unpack<<<plane_chunks, 64, 0, st>>>(chunks, plane_first, plane_chunks, first_slot, layer_i, voxels, src);
     return cudaGetLastError();
 }
 cudaError_t launch_halo_kinds_pack(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t plane_first,

@@ -100,12 +100,11 @@ cudaError_t launch_boundary_apply(DevChunk* chunks, uint32_t n, const uint32_t n
                                   uint32_t grid, cudaStream_t st);
 
 // ---- halo.cu -----------------------------------------------------------------
-cudaError_t launch_halo_flags(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t* flag,
-                              cudaStream_t st);
-cudaError_t launch_halo_pack(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, const uint32_t* ordinal,
+size_t halo_message_bytes(uint32_t plane_chunks);
+cudaError_t launch_halo_pack(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t layer_i,
                              const unsigned char* voxels, unsigned char* dst, cudaStream_t st);
 cudaError_t launch_halo_unpack(DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t first_slot,
-                               unsigned char* voxels, const unsigned char* src, cudaStream_t st);
+                               uint32_t layer_i, unsigned char* voxels, const unsigned char* src, cudaStream_t st);
 cudaError_t launch_halo_kinds_pack(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t plane_first,
                                    uint32_t plane_chunks, uint8_t* dst, cudaStream_t st);
 cudaError_t launch_halo_kinds_unpack(DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, const uint8_t* src,

@@ -7,7 +7,7 @@ chunks (mesh.rs:286-354). The same partition maps onto GPUs as slabs of whole ch
   * generation needs no communication;
   * derived state and Surface Nets read one chunk plane of the neighbouring slab (the 1-voxel brick padding,
     object/sdf.rs:35, and the face rules, object.rs:1682-1704) → ONE point-to-point halo exchange with each
-    neighbour (NCCL send/recv over NVLink), plus one byte per chunk of the upper neighbour's final chunk kinds
+    neighbour (NCCL send/recv over NVLink; only the touching voxel layer of each chunk travels), plus one byte per chunk of the upper neighbour's final chunk kinds
     (quad ownership, surface_nets.rs:252-261);
   * the per-slab meshes are concatenated on one rank in slab order, which IS the reference's order (chunks
     are meshed in linear chunk order), with vertex / index offsets rebased.
@@ -81,34 +81,24 @@ def exchange_halos_and_finalize(obj, ranges, rank: int, device, group=None) -> d
     peers = [(0, lo), (1, hi)]
     cap = obj.halo_capacity()
 
-    # exchange A: boundary planes. Sizes first (the payload holds only the non-uniform chunks of the plane).
-    out_buf, out_len, in_len = {}, {}, {}
+    # exchange A: boundary planes. A message has a fixed size (chunk descriptors + one 768-byte voxel layer per
+    # chunk of the plane), so both directions of both neighbours go out in ONE batch with no size handshake.
+    out_buf, in_buf = {}, {}
     ops = []
     for side, peer in peers:
         if peer is None:
             continue
-        buf = torch.empty(cap, dtype=torch.uint8, device=device)
-        n = obj.halo_export(side, buf.data_ptr(), cap)
-        out_buf[side] = buf[:n]
-        out_len[side] = torch.tensor([n], dtype=torch.int64, device=device)
-        in_len[side] = torch.zeros(1, dtype=torch.int64, device=device)
-        ops.append(dist.P2POp(dist.isend, out_len[side], peer, group))
-        ops.append(dist.P2POp(dist.irecv, in_len[side], peer, group))
-    _p2p(ops, group)
-    in_buf = {}
-    ops = []
-    for side, peer in peers:
-        if peer is None:
-            continue
-        n_in = int(in_len[side].item())
-        in_buf[side] = torch.empty(n_in, dtype=torch.uint8, device=device)
+        out_buf[side] = torch.empty(cap, dtype=torch.uint8, device=device)
+        n = obj.halo_export(side, out_buf[side].data_ptr(), cap)
+        assert n == cap, "halo messages have the fixed size ivx_object_halo_capacity reports"
+        in_buf[side] = torch.empty(cap, dtype=torch.uint8, device=device)
         ops.append(dist.P2POp(dist.isend, out_buf[side], peer, group))
         ops.append(dist.P2POp(dist.irecv, in_buf[side], peer, group))
-        stats["halo_bytes_sent"] += int(out_buf[side].numel())
-        stats["halo_bytes_received"] += n_in
+        stats["halo_bytes_sent"] += cap
+        stats["halo_bytes_received"] += cap
     _p2p(ops, group)
     for side, buf in in_buf.items():
-        obj.halo_import(side, buf.data_ptr(), int(buf.numel()))
+        obj.halo_import(side, buf.data_ptr(), cap)
 
     obj.slab_classify()
 

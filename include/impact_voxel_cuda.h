@@ -277,7 +277,9 @@ int ivx_object_generate_slab(ivx_ctx* ctx, const ivx_program* program, float vox
 int ivx_program_plane_work(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
                            const ivx_type_generator* type_generator, uint32_t* out_work, uint32_t capacity,
                            uint32_t* out_planes);
-/* upper bound of a halo_export in bytes (a whole plane of non-uniform chunks) */
+/* exact size of every halo message of this object in bytes: chunk descriptors of one plane + the one voxel layer
+ * per chunk that touches the neighbouring slab (768 bytes); fixed, so sender and receiver need no size handshake.
+ * halo_export writes exactly this many bytes (*out_bytes), halo_import expects exactly this many. */
 int ivx_object_halo_capacity(ivx_ctx* ctx, const ivx_object* object, size_t* out_bytes);
 int ivx_object_halo_export(ivx_ctx* ctx, const ivx_object* object, int side, void* device_buffer,
                            size_t capacity, size_t* out_bytes);

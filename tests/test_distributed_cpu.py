@@ -69,16 +69,15 @@ class RecordingSlab:
         return 4096
 
     def halo_export(self, side, ptr, cap):
-        n = 100 + 17 * self.rank + 5 * side  # payload size differs per (rank, side)
-        assert cap >= n
-        self._view(ptr, n)[:] = (self.rank * 2 + side) & 0xFF
+        assert cap == self.halo_capacity()  # fixed-size messages: no size handshake
+        self._view(ptr, cap)[:] = (self.rank * 2 + side) & 0xFF
         self.log.append(("export", side))
-        return n
+        return cap
 
     def halo_import(self, side, ptr, nbytes):
         peer = self.lo if side == 0 else self.hi
         assert peer is not None
-        assert nbytes == 100 + 17 * peer + 5 * (1 - side)
+        assert nbytes == self.halo_capacity()
         assert (self._view(ptr, nbytes) == ((peer * 2 + (1 - side)) & 0xFF)).all()
         self.log.append(("import", side))
 
@@ -139,7 +138,7 @@ def _worker(rank, world, port, planes, q):
             want += [("kinds_import", 1)] if hi is not None else []
             want += [("finalize",)]
         assert slab.log == want, (slab.log, want)
-        assert stats["halo_bytes_sent"] == sum(100 + 17 * rank + 5 * s for s, p in ((0, lo), (1, hi)) if p is not None) + (
+        assert stats["halo_bytes_sent"] == sum(slab.halo_capacity() for s, p in ((0, lo), (1, hi)) if p is not None) + (
             slab.PLANE if lo is not None else 0)
 
         # mesh gather against the oracle
