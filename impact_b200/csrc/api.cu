@@ -339,6 +339,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
         ta.voxels = obj->d_voxels;
         ta.chunks = obj->d_chunks;
         ta.occ = counters + 2;
+        ta.neg_zero = -0.0f;
         KLP(ctx, 7, launch_types(ta, persistent_grid(ctx, n_active, std::max(1, types_max_blocks_per_sm())), st));
     }
 

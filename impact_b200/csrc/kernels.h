@@ -73,6 +73,7 @@ struct TypesArgs {
     unsigned char* voxels;
     DevChunk* chunks;
     uint32_t* occ;
+    float neg_zero;           // -0.0f, deliberately a run-time value (see simplex4_tab2 in types.cu)
 };
 cudaError_t launch_types(const TypesArgs& a, uint32_t grid, cudaStream_t st);
 int types_max_blocks_per_sm();

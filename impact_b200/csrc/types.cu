@@ -109,6 +109,91 @@ __device__ __forceinline__ float simplex4_tab(float x, float y, float z, float w
     return (n0 + (n1 + (n2 + (n3 + n4)))) * 62.77772078955791f;
 }
 
+// ---- two voxels per thread on the packed f32x2 pipe -------------------------------------------------
+// sm_100a issues FADD2 / FFMA2 (two independent, individually rounded f32 operations per lane) at the
+// scalar FP32 rate per *operation* but half the rate per *instruction*; k_types is bound by issue
+// slots, not by the FMA pipe (tools/microbench/f32x2.cu, profiles/README.md), so the same arithmetic
+// on (k, k+1) voxel pairs needs ~1/3 fewer slots. Every packed operation rounds exactly like the scalar
+// one it replaces. ptxas 12.9 contracts `mul.rn.f32x2` followed by `add.rn.f32x2` into FFMA2 even
+// under --fmad=false, which would change results; packed products therefore go through FFMA2 with an
+// addend of -0.0 that is only known at run time (x·y + (-0) == RN(x·y) for every x·y, signed zeros
+// included), so there is no multiply for ptxas to contract.
+typedef float2 f2;
+__device__ __forceinline__ f2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz) { return __ffma2_rn(a, b, nz); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 gt2(f2 a, f2 b) { return make_float2(a.x > b.x ? 1.0f : 0.0f, a.y > b.y ? 1.0f : 0.0f); }
+__device__ __forceinline__ f2 gtc2(f2 a, float c) { return make_float2(a.x > c ? 1.0f : 0.0f, a.y > c ? 1.0f : 0.0f); }
+__device__ __forceinline__ f2 floor2(f2 a) { return make_float2(floorf(a.x), floorf(a.y)); }
+__device__ __forceinline__ f2 min2c(f2 a, float c) { return make_float2(fminf(a.x, c), fminf(a.y, c)); }
+__device__ __forceinline__ f2 max2c(f2 a, float c) { return make_float2(fmaxf(a.x, c), fmaxf(a.y, c)); }
+// entry address of a MAGIC-biased entry number. Inline PTX on purpose: nvcc 12.9 drops the `* 16` for the
+// low half of a float2 returned by the f32x2 builtins when this is written in C++.
+__device__ __forceinline__ float4 tab_load(float e, uint32_t addr) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(r) : "r"(__float_as_uint(e)), "r"(addr));
+    return lds128(r);
+}
+__device__ __forceinline__ float gdot(const float4 g, float x, float y, float z, float w) {
+    return __fmaf_rn(g.x, x, __fmaf_rn(g.y, y, __fmaf_rn(g.z, z, g.w * w)));
+}
+
+// simplex4_tab for the voxel pair (y.x, y.y); x, z, w are the same for both. Operation for operation
+// the scalar function above.
+__device__ __forceinline__ f2 simplex4_tab2(f2 x, f2 y, f2 z, f2 w, f2 zw, const TypeTab& T, f2 nz) {
+    const float F4 = 0.309016994f, G4 = 0.138196601f;
+    const float G24 = 2.0f * 0.138196601f, G34 = 3.0f * 0.138196601f, G44 = 4.0f * 0.138196601f;
+    const f2 s = mul2(bc2(F4), add2(x, add2(y, zw)), nz);
+    const f2 ips = floor2(add2(x, s)), jps = floor2(add2(y, s)), kps = floor2(add2(z, s)), lps = floor2(add2(w, s));
+    const f2 t = mul2(add2(ips, add2(jps, add2(kps, lps))), bc2(G4), nz);
+    const f2 x0 = sub2(x, sub2(ips, t)), y0 = sub2(y, sub2(jps, t)), z0 = sub2(z, sub2(kps, t)), w0 = sub2(w, sub2(lps, t));
+
+    const f2 pxy = gt2(x0, y0), pxz = gt2(x0, z0), pxw = gt2(x0, w0);
+    const f2 pyz = gt2(y0, z0), pyw = gt2(y0, w0), pzw = gt2(z0, w0);
+    const f2 rx = add2(add2(pxy, pxz), pxw);
+    const f2 ry = add2(add2(sub2(bc2(1.0f), pxy), pyz), pyw);
+    const f2 rz = add2(sub2(sub2(bc2(2.0f), pxz), pyz), pzw);
+    const f2 rw = sub2(sub2(sub2(bc2(6.0f), rx), ry), rz);
+    const f2 i1 = gtc2(rx, 2.5f), j1 = gtc2(ry, 2.5f), k1 = gtc2(rz, 2.5f), l1 = gtc2(rw, 2.5f);
+    const f2 i2 = gtc2(rx, 1.5f), j2 = gtc2(ry, 1.5f), k2 = gtc2(rz, 1.5f), l2 = gtc2(rw, 1.5f);
+    const f2 i3 = min2c(rx, 1.0f), j3 = min2c(ry, 1.0f), k3 = min2c(rz, 1.0f), l3 = min2c(rw, 1.0f);
+
+    const f2 sa = bc2(T.sa), sb = bc2(T.sb), sc = bc2(T.sc);
+    const f2 e0 = fma2(ips, sa, fma2(jps, sb, fma2(kps, sc, add2(lps, bc2(T.base)))));
+    const f2 e1 = fma2(i1, sa, fma2(j1, sb, fma2(k1, sc, add2(l1, e0))));
+    const f2 e2 = fma2(i2, sa, fma2(j2, sb, fma2(k2, sc, add2(l2, e0))));
+    const f2 e3 = fma2(i3, sa, fma2(j3, sb, fma2(k3, sc, add2(l3, e0))));
+    const f2 e4 = add2(e0, bc2(T.s4));
+    const float4 g0a = tab_load(e0.x, T.addr), g0b = tab_load(e0.y, T.addr);
+    const float4 g1a = tab_load(e1.x, T.addr), g1b = tab_load(e1.y, T.addr);
+    const float4 g2a = tab_load(e2.x, T.addr), g2b = tab_load(e2.y, T.addr);
+    const float4 g3a = tab_load(e3.x, T.addr), g3b = tab_load(e3.y, T.addr);
+    const float4 g4a = tab_load(e4.x, T.addr), g4b = tab_load(e4.y, T.addr);
+
+    const f2 c1 = bc2(G4), c2 = bc2(G24), c3 = bc2(G34), c4 = bc2(G44), one = bc2(1.0f), half = bc2(0.5f);
+    const f2 x1 = add2(sub2(x0, i1), c1), y1 = add2(sub2(y0, j1), c1), z1 = add2(sub2(z0, k1), c1), w1 = add2(sub2(w0, l1), c1);
+    const f2 x2 = add2(sub2(x0, i2), c2), y2 = add2(sub2(y0, j2), c2), z2 = add2(sub2(z0, k2), c2), w2 = add2(sub2(w0, l2), c2);
+    const f2 x3 = add2(sub2(x0, i3), c3), y3 = add2(sub2(y0, j3), c3), z3 = add2(sub2(z0, k3), c3), w3 = add2(sub2(w0, l3), c3);
+    const f2 x4 = add2(sub2(x0, one), c4), y4 = add2(sub2(y0, one), c4), z4 = add2(sub2(z0, one), c4), w4 = add2(sub2(w0, one), c4);
+
+#define IVX_T2(X, Y, Z, W) \
+    sub2(sub2(sub2(sub2(half, mul2(X, X, nz)), mul2(Y, Y, nz)), mul2(Z, Z, nz)), mul2(W, W, nz))
+    f2 t0 = IVX_T2(x0, y0, z0, w0), t1 = IVX_T2(x1, y1, z1, w1), t2 = IVX_T2(x2, y2, z2, w2),
+       t3 = IVX_T2(x3, y3, z3, w3), t4 = IVX_T2(x4, y4, z4, w4);
+#undef IVX_T2
+    t0 = max2c(t0, 0.0f); t1 = max2c(t1, 0.0f); t2 = max2c(t2, 0.0f); t3 = max2c(t3, 0.0f); t4 = max2c(t4, 0.0f);
+    f2 q0 = mul2(t0, t0, nz), q1 = mul2(t1, t1, nz), q2 = mul2(t2, t2, nz), q3 = mul2(t3, t3, nz), q4 = mul2(t4, t4, nz);
+    q0 = mul2(q0, q0, nz); q1 = mul2(q1, q1, nz); q2 = mul2(q2, q2, nz); q3 = mul2(q3, q3, nz); q4 = mul2(q4, q4, nz);
+    const f2 n0 = mul2(q0, make_float2(gdot(g0a, x0.x, y0.x, z0.x, w0.x), gdot(g0b, x0.y, y0.y, z0.y, w0.y)), nz);
+    const f2 n1 = mul2(q1, make_float2(gdot(g1a, x1.x, y1.x, z1.x, w1.x), gdot(g1b, x1.y, y1.y, z1.y, w1.y)), nz);
+    const f2 n2 = mul2(q2, make_float2(gdot(g2a, x2.x, y2.x, z2.x, w2.x), gdot(g2b, x2.y, y2.y, z2.y, w2.y)), nz);
+    const f2 n3 = mul2(q3, make_float2(gdot(g3a, x3.x, y3.x, z3.x, w3.x), gdot(g3b, x3.y, y3.y, z3.y, w3.y)), nz);
+    const f2 n4 = mul2(q4, make_float2(gdot(g4a, x4.x, y4.x, z4.x, w4.x), gdot(g4b, x4.y, y4.y, z4.y, w4.y)), nz);
+    return mul2(add2(n0, add2(n1, add2(n2, add2(n3, n4)))), bc2(62.77772078955791f), nz);
+}
+
 // the lattice cell of a noise-space point, exactly as simplex4 computes it
 __device__ __forceinline__ void simplex4_cell(float x, float y, float z, float w, float c[4]) {
     const float F4 = 0.309016994f;
@@ -211,6 +296,7 @@ __global__ void __launch_bounds__(TYPES_THREADS, 3) k_types(TypesArgs a) {
             const int32_t seed = (int32_t)a.gp.types.seed;
             const float wc = accumulate_ones(lo.x, ti) * fn;
             const float zc = accumulate_ones(lo.y, tj) * fn;
+            const f2 nz = bc2(a.neg_zero), Z2 = bc2(zc), W2 = bc2(wc), ZW2 = bc2(zc + wc);
 
             // ---- lattice cells touched by the chunk, per type: the cell of a voxel is monotone in each
             // voxel index (every step of the computation is a monotone f32 operation), so the 8 corner
@@ -328,16 +414,22 @@ __global__ void __launch_bounds__(TYPES_THREADS, 3) k_types(TypesArgs a) {
                         T.base = MAGIC - (((float)S.cmin[t][0] * T.sa + (float)S.cmin[t][1] * T.sb) +
                                           ((float)S.cmin[t][2] * T.sc + (float)S.cmin[t][3]));
                         T.addr = tab_base + (uint32_t)S.tab_off[t] * 16u - MAGIC_BITS * 16u;
+                        const f2 X2 = bc2(T.x);
                         float yacc = lo.z;
-#pragma unroll 2
-                        for (int k = 0; k < 16; ++k) {
-                            const float nv = simplex4_tab(T.x, yacc * fn, zc, wc, T);
+#pragma unroll 1
+                        for (int k = 0; k < 16; k += 2) {
+                            const float yacc1 = yacc + 1.0f;
+                            const f2 nv = simplex4_tab2(X2, make_float2(yacc * fn, yacc1 * fn), Z2, W2, ZW2, T, nz);
                             const int bi = k * TYPES_THREADS + tid;
-                            if (t == 0 || nv > S.best[bi]) {
-                                S.best[bi] = nv;
+                            if (t == 0 || nv.x > S.best[bi]) {
+                                S.best[bi] = nv.x;
                                 S.best_t[bi] = (uint8_t)t;
                             }
-                            yacc = yacc + 1.0f;
+                            if (t == 0 || nv.y > S.best[bi + TYPES_THREADS]) {
+                                S.best[bi + TYPES_THREADS] = nv.y;
+                                S.best_t[bi + TYPES_THREADS] = (uint8_t)t;
+                            }
+                            yacc = yacc1 + 1.0f;
                         }
                     }
                     __syncthreads();  // the table is rebuilt by the next batch
