@@ -1184,9 +1184,45 @@ int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* obj, float* positions, flo
     return IVX_OK;
 }
 
+static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats);
+
 int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3], float radius, float influence_radius,
                              ivx_absorb_stats* out_stats) {
     if (!ctx || !obj || !center) return IVX_ERR_INVALID_ARGUMENT;
+    if (!(radius >= 0.0f) || !(influence_radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;  // Sphere::new asserts
+    ivx::AbsorbShape s{};
+    s.capsule = 0;
+    for (int d = 0; d < 3; ++d) s.center[d] = center[d];
+    s.radius = radius;
+    s.influence_radius = influence_radius;
+    s.influence_radius_sq = influence_radius * influence_radius;  // Sphere::radius_squared = radius.powi(2)
+    return absorb_impl(ctx, obj, s, out_stats);
+}
+
+int ivx_object_absorb_capsule(ivx_ctx* ctx, ivx_object* obj, const float segment_start[3], const float segment_vector[3],
+                              float radius, float influence_radius, ivx_absorb_stats* out_stats) {
+    if (!ctx || !obj || !segment_start || !segment_vector) return IVX_ERR_INVALID_ARGUMENT;
+    if (!(radius >= 0.0f) || !(influence_radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;  // Capsule::new asserts
+    ivx::AbsorbShape s{};
+    s.capsule = 1;
+    for (int d = 0; d < 3; ++d) {
+        s.center[d] = segment_start[d];
+        s.seg[d] = segment_vector[d];
+    }
+    // Capsule::create_point_containment_tester (capsule.rs:168-181)
+    const float len2 = (s.seg[0] * s.seg[0] + s.seg[1] * s.seg[1]) + s.seg[2] * s.seg[2];
+    for (int d = 0; d < 3; ++d) s.seg_over_len2[d] = len2 > 1e-8f ? s.seg[d] / len2 : 0.0f;
+    s.radius = radius;
+    s.influence_radius = influence_radius;
+    s.influence_radius_sq = influence_radius * influence_radius;
+    return absorb_impl(ctx, obj, s, out_stats);
+}
+
+}  // extern "C"
+
+static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats) {
+    using namespace ivx;
+    const float influence_radius = shape.influence_radius;
     cudaSetDevice(ctx->device);
     if (out_stats) std::memset(out_stats, 0, sizeof(*out_stats));
     if (obj->first_i != 0 || obj->nb[0] != obj->chunk_counts[0])
@@ -1197,7 +1233,13 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3
     AbsorbRange r{};
     bool empty = false;
     for (int d = 0; d < 3; ++d) {
-        const float lo = center[d] - influence_radius, hi = center[d] + influence_radius;
+        // Sphere::compute_aabb / Capsule::compute_aabb (the union of the two end spheres' boxes)
+        float lo = shape.center[d] - influence_radius, hi = shape.center[d] + influence_radius;
+        if (shape.capsule) {
+            const float e = shape.center[d] + shape.seg[d];
+            lo = std::fmin(lo, e - influence_radius);
+            hi = std::fmax(hi, e + influence_radius);
+        }
         const float fl = std::fmax(std::floor(lo), 0.0f);
         const float ce = std::ceil(hi);
         const uint32_t s = fl >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fl;
@@ -1220,7 +1262,7 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3
         uint32_t init[12] = {0, 0, 0, 0, 0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
         CU(ctx, cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
-    KL(ctx, launch_absorb_plan(obj->d_chunks, obj->nb, r, need, n_range, st));
+    KL(ctx, launch_absorb_plan(obj->d_chunks, obj->nb, r, shape, need, n_range, st));
     KL(ctx, launch_exclusive_scan(need, ord, n_range, counters, st));
     uint32_t w[12];
     if (int rc = read_words(ctx, counters, 1, w)) return rc;
@@ -1231,9 +1273,7 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3
     aa.range = r;
     aa.n_range = n_range;
     aa.voxels = obj->d_voxels;
-    for (int d = 0; d < 3; ++d) aa.center[d] = center[d];
-    aa.radius = radius;
-    aa.influence_radius_sq = influence_radius * influence_radius;  // Sphere::radius_squared = radius.powi(2)
+    aa.shape = shape;
     aa.first_new_slot = obj->slots_used;
     aa.new_slot_ord = ord;
     aa.dirty = obj->d_dirty;
@@ -1293,6 +1333,8 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3
     }
     return IVX_OK;
 }
+
+extern "C" {
 
 int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* obj, uint32_t* out, uint32_t capacity, uint32_t* out_count) {
     if (!ctx || !obj || !out_count) return IVX_ERR_INVALID_ARGUMENT;

@@ -144,22 +144,30 @@ struct AbsorbRange {
     uint32_t c0[3], c1[3];  // chunk range
     uint32_t v0[3], v1[3];  // voxel range
 };
+// the absorbing shape in normalized voxel space: a sphere, or a capsule (segment start, segment vector)
+struct AbsorbShape {
+    int capsule;               // 0 sphere, 1 capsule
+    float center[3];           // sphere centre / capsule segment start
+    float seg[3];              // capsule segment vector
+    float seg_over_len2[3];    // CapsulePointContainmentTester (capsule.rs:168-181)
+    float radius;              // absorbing radius
+    float influence_radius;    // radius of the shape whose voxels are visited
+    float influence_radius_sq;
+};
 struct AbsorbArgs {
     DevChunk* chunks;
     uint3 nb;
     AbsorbRange range;
     uint32_t n_range;
     unsigned char* voxels;
-    float center[3];
-    float radius;
-    float influence_radius_sq;
+    AbsorbShape shape;
     uint32_t first_new_slot;
     const uint32_t* new_slot_ord;
     uint8_t* dirty;
     uint32_t* stats;  // touched chunks, touched voxels, emptied voxels, removed chunks
 };
-cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], const AbsorbRange& r, uint32_t* need_slot,
-                               uint32_t n_range, cudaStream_t st);
+cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], const AbsorbRange& r, const AbsorbShape& shape,
+                               uint32_t* need_slot, uint32_t n_range, cudaStream_t st);
 cudaError_t launch_absorb_apply(const AbsorbArgs& a, uint32_t grid, cudaStream_t st);
 cudaError_t launch_absorb_face_mask(const uint32_t nb[3], const AbsorbRange& b, uint8_t* face_mask, uint32_t n,
                                     cudaStream_t st);

@@ -3,6 +3,9 @@
 //
 // Replaces
 //   VoxelObject::modify_voxels_within_sphere        (object/intersection.rs:283-394)
+//   VoxelObject::modify_voxels_within_capsule       (object/intersection.rs:417-537)
+//   Capsule::trim_segment_outside_aab, CapsulePointContainmentTester (impact_geometry/src/capsule.rs:144-250)
+//   apply_capsule_absorption's closure              (interaction/absorption.rs:869-888)
 //   apply_sphere_absorption's closure               (interaction/absorption.rs:823-843)
 //   VoxelAbsorbingSphere::compute_new_signed_distance (absorption.rs:170-179)
 //   Voxel::set_signed_distance                      (lib.rs:451-461)
@@ -15,14 +18,66 @@
 
 namespace ivx {
 
-__global__ void k_absorb_plan(const DevChunk* __restrict__ chunks, uint3 nb, AbsorbRange r,
+// `x as usize` of a non-negative float, saturating (32-bit indices are plenty: grids are < 2^16 voxels wide)
+__device__ __forceinline__ uint32_t sat_u32(float v) {
+    return !(v > 0.0f) ? 0u : (v >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)v);
+}
+
+// The voxel range of chunk `cc` the modification visits, [t0, t1) per axis; false if the chunk is skipped before
+// anything happens to it.
+//   sphere:  the object-level touched range clipped to the chunk (intersection.rs:336-345)
+//   capsule: the capsule is first trimmed to the chunk's box expanded by the radius
+//            (Capsule::trim_segment_outside_aab → AxisAlignedBox::find_contained_subsegment); the range is the
+//            trimmed capsule's AABB clipped to the chunk (voxel_ranges_touching_aab), intersection.rs:445-461
+__device__ __forceinline__ bool touched_range_in_chunk(const AbsorbShape& s, const AbsorbRange& r, const uint32_t cc[3],
+                                                       uint32_t t0[3], uint32_t t1[3]) {
+    if (!s.capsule) {
+        for (int d = 0; d < 3; ++d) {
+            t0[d] = max(cc[d] * 16u, r.v0[d]);
+            t1[d] = min(cc[d] * 16u + 16u, r.v1[d]);
+        }
+        return true;
+    }
+    const float R = s.influence_radius;
+    float t_min = 0.0f, t_max = 1.0f;
+    for (int d = 0; d < 3; ++d) {
+        const float lo = (float)(cc[d] * 16u) - R, hi = (float)((cc[d] + 1u) * 16u) + R;
+        const float v = s.seg[d], o = s.center[d];
+        if (fabsf(v) > 1e-8f) {
+            const float recip = 1.0f / v;
+            const float a = (lo - o) * recip, b = (hi - o) * recip;
+            const float t_entry = a < b ? a : b, t_exit = a < b ? b : a;
+            t_min = fmaxf(t_min, t_entry);
+            t_max = fminf(t_max, t_exit);
+        } else if (o < lo || o > hi) {
+            return false;
+        }
+    }
+    if (!(t_min <= t_max)) return false;
+    bool any = true;
+    for (int d = 0; d < 3; ++d) {
+        const float a = s.center[d] + s.seg[d] * t_min;     // trimmed segment start
+        const float b = a + s.seg[d] * (t_max - t_min);     // ... and end
+        const float lo = fminf(a - R, b - R), hi = fmaxf(a + R, b + R);  // Capsule::compute_aabb
+        t0[d] = max(cc[d] * 16u, sat_u32(fmaxf(floorf(lo), 0.0f)));
+        t1[d] = min(cc[d] * 16u + 16u, sat_u32(ceilf(hi)));
+        if (t0[d] >= t1[d]) any = false;
+    }
+    return any;
+}
+
+__global__ void k_absorb_plan(const DevChunk* __restrict__ chunks, uint3 nb, AbsorbRange r, AbsorbShape shape,
                               uint32_t* __restrict__ need_slot, uint32_t n_range) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_range) return;
     const uint32_t ek = r.c1[2] - r.c0[2], ej = r.c1[1] - r.c0[1];
     const uint32_t k = r.c0[2] + t % ek, j = r.c0[1] + (t / ek) % ej, i = r.c0[0] + t / (ek * ej);
     const DevChunk c = chunks[(i * nb.y + j) * nb.z + k];
-    need_slot[t] = (c.kind == 1 && c.slot == 0xFFFFFFFFu) ? 1u : 0u;
+    const uint32_t cc[3] = {i, j, k};
+    uint32_t t0[3], t1[3];
+    // only chunks the modification reaches are converted to non-uniform
+    const bool reached = touched_range_in_chunk(shape, r, cc, t0, t1);
+    need_slot[t] = (reached && c.kind == 1 && c.slot == 0xFFFFFFFFu) ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
@@ -38,6 +93,13 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
         const uint32_t ck = r.c0[2] + t % ek, cj = r.c0[1] + (t / ek) % ej, ci = r.c0[0] + t / (ek * ej);
         const uint32_t cidx = (ci * nb.y + cj) * nb.z + ck;
         DevChunk me = a.chunks[cidx];
+        const uint32_t cc[3] = {ci, cj, ck};
+        uint32_t v0[3], v1[3], t0[3], t1[3];
+        for (int d = 0; d < 3; ++d) {
+            v0[d] = cc[d] * 16u;
+            v1[d] = v0[d] + 16u;
+        }
+        if (!touched_range_in_chunk(a.shape, r, cc, t0, t1)) continue;  // block-uniform
         if (me.kind == 0) continue;
         unsigned char* slot;
         if (me.kind == 1) {
@@ -59,28 +121,36 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
         if (tid < 8) s_cnt[tid] = 0;
         __syncthreads();
 
-        // touched voxel ranges in this chunk (intersection.rs:336-345)
-        uint32_t v0[3], v1[3], t0[3], t1[3];
-        const uint32_t cc[3] = {ci, cj, ck};
-        for (int d = 0; d < 3; ++d) {
-            v0[d] = cc[d] * 16u;
-            v1[d] = v0[d] + 16u;
-            t0[d] = max(v0[d], r.v0[d]);
-            t1[d] = min(v1[d], r.v1[d]);
-        }
         const uint32_t gi = v0[0] + ti, gj = v0[1] + tj;
         uint32_t n_touched = 0, n_emptied = 0;
         if (gi >= t0[0] && gi < t1[0] && gj >= t0[1] && gj < t1[1]) {
             const float px = (float)gi + 0.5f, py = (float)gj + 0.5f;
             for (uint32_t gk = t0[2]; gk < t1[2]; ++gk) {
                 const float pz = (float)gk + 0.5f;
-                // Point3::squared_distance_between(centre, voxel centre)
-                const f3 df = mk3(a.center[0] - px, a.center[1] - py, a.center[2] - pz);
-                const float d2 = dot3(df, df);
-                if (d2 < a.influence_radius_sq) {
+                float d2;
+                bool inside;
+                if (a.shape.capsule) {
+                    // shortest_squared_distance_from_point_to_segment_if_contained (capsule.rs:225-250): boundary included
+                    const f3 c0 = mk3(a.shape.center[0], a.shape.center[1], a.shape.center[2]);
+                    const f3 sv = mk3(a.shape.seg[0], a.shape.seg[1], a.shape.seg[2]);
+                    const f3 sp = mk3(px, py, pz) - c0;
+                    float t = dot3(sp, mk3(a.shape.seg_over_len2[0], a.shape.seg_over_len2[1], a.shape.seg_over_len2[2]));
+                    if (t < 0.0f) t = 0.0f;
+                    if (t > 1.0f) t = 1.0f;
+                    const f3 closest = mk3(c0.x + sv.x * t, c0.y + sv.y * t, c0.z + sv.z * t);
+                    const f3 df = mk3(px, py, pz) - closest;
+                    d2 = dot3(df, df);
+                    inside = d2 <= a.shape.influence_radius_sq;
+                } else {
+                    // Point3::squared_distance_between(centre, voxel centre); strictly inside
+                    const f3 df = mk3(a.shape.center[0] - px, a.shape.center[1] - py, a.shape.center[2] - pz);
+                    d2 = dot3(df, df);
+                    inside = d2 < a.shape.influence_radius_sq;
+                }
+                if (inside) {
                     const int idx = vidx(ti, tj, (int)(gk & 15u));
                     const bool was_empty = (s_fl[idx] & 1) != 0;
-                    const float sphere_sd = sqrtf(d2) - a.radius;
+                    const float sphere_sd = sqrtf(d2) - a.shape.radius;
                     const float nsd = fmaxf(sd_decode((int)s_sd[idx]), -sphere_sd);
                     const int code = sd_encode(nsd);
                     s_sd[idx] = (int8_t)code;
@@ -260,10 +330,10 @@ __global__ void __launch_bounds__(256) k_occupied_ranges(const DevChunk* __restr
     }
 }
 
-cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], const AbsorbRange& r, uint32_t* need_slot,
-                               uint32_t n_range, cudaStream_t st) {
+cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], const AbsorbRange& r, const AbsorbShape& shape,
+                               uint32_t* need_slot, uint32_t n_range, cudaStream_t st) {
     if (n_range == 0) return cudaSuccess;
-    k_absorb_plan<<<(n_range + 255) / 256, 256, 0, st>>>(chunks, make_uint3(nb[0], nb[1], nb[2]), r, need_slot, n_range);
+    k_absorb_plan<<<(n_range + 255) / 256, 256, 0, st>>>(chunks, make_uint3(nb[0], nb[1], nb[2]), r, shape, need_slot, n_range);
     return cudaGetLastError();
 }
 cudaError_t launch_absorb_apply(const AbsorbArgs& a, uint32_t grid, cudaStream_t st) {

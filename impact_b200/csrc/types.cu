@@ -25,6 +25,9 @@
 namespace ivx {
 
 constexpr int TYPES_THREADS = 256;
+#ifndef IVX_TYPES_CTAS
+#define IVX_TYPES_CTAS 3   // resident CTAs per SM the register budget is set for
+#endif
 constexpr int TAB_CAP = 1024;        // gradient-table entries (float4) per batch of types
 constexpr int MAX_TYPES = 255;
 constexpr float CELL_LIMIT = 4096.0f;  // |cell index| < 2^12 and strides <= 2^9: every integer-valued f32 term stays below 2^22
@@ -235,7 +238,7 @@ struct TypesSmem {
     uint8_t first_type;
 };
 
-__global__ void __launch_bounds__(TYPES_THREADS, 3) k_types(TypesArgs a) {
+__global__ void __launch_bounds__(TYPES_THREADS, IVX_TYPES_CTAS) k_types(TypesArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TypesSmem& S = *reinterpret_cast<TypesSmem*>(smem_raw);
     const int tid = threadIdx.x;

@@ -7,6 +7,7 @@ Names follow the reference (engine/crates/impact_voxel/src):
   VoxelObjectMesh::create       → VoxelObjectMesh.create        (mesh.rs:280)
   sync_with_voxel_object        → VoxelObjectMesh.sync_with_voxel_object (mesh.rs:360)
   apply_sphere_absorption       → VoxelObject.absorb_sphere     (interaction/absorption.rs:801)
+  apply_capsule_absorption      → VoxelObject.absorb_capsule    (interaction/absorption.rs:846)
 All compute happens in libimpact_voxel_cuda.so on the GPU; this module only
 marshals POD buffers.
 """
@@ -248,6 +249,14 @@ class VoxelObject:
         st = L.AbsorbStats()
         self.ctx.check(self.ctx._lib.ivx_object_absorb_sphere(self.ctx.h, self.h, L.ptr(c), C.c_float(radius),
                                                               C.c_float(influence_radius), C.byref(st)))
+        return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
+
+    def absorb_capsule(self, segment_start, segment_vector, radius: float, influence_radius: float) -> dict:
+        """`apply_capsule_absorption` (absorption.rs:846-889) in normalized voxel space."""
+        a, v = np.asarray(segment_start, np.float32), np.asarray(segment_vector, np.float32)
+        st = L.AbsorbStats()
+        self.ctx.check(self.ctx._lib.ivx_object_absorb_capsule(self.ctx.h, self.h, L.ptr(a), L.ptr(v), C.c_float(radius),
+                                                               C.c_float(influence_radius), C.byref(st)))
         return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
 
     def resolve_connected_regions(self, download: bool = False) -> dict:

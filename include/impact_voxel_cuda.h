@@ -316,6 +316,14 @@ int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* object, float* positions, 
  * (mesh.rs:360-456) for the invalidated chunk set and clears it. */
 int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* object, const float center[3], float radius,
                              float influence_radius, ivx_absorb_stats* out_stats);
+/* ivx_object_absorb_capsule replaces apply_capsule_absorption (interaction/absorption.rs:846-889) →
+ * modify_voxels_within_capsule (object/intersection.rs:417-537): the influence capsule is given by its segment start
+ * and segment vector (Capsule::new, impact_geometry/src/capsule.rs:61) and `influence_radius`; voxels whose centre
+ * lies within or on it get max(sd, -(distance_to_segment - radius)). Negative radii return
+ * IVX_ERR_INVALID_ARGUMENT (the reference asserts). */
+int ivx_object_absorb_capsule(ivx_ctx* ctx, ivx_object* object, const float segment_start[3],
+                              const float segment_vector[3], float radius, float influence_radius,
+                              ivx_absorb_stats* out_stats);
 int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* object, uint32_t* out_linear_indices,
                             uint32_t capacity, uint32_t* out_count);
 int ivx_object_remesh_dirty(ivx_ctx* ctx, ivx_object* object, ivx_mesh_info* out);

@@ -330,6 +330,12 @@ void orc_absorb_sphere(void* op, const float center[3], float radius, float infl
     absorb_sphere(*(Object*)op, v3(center[0], center[1], center[2]), radius, influence_radius, stats);
 }
 
+void orc_absorb_capsule(void* op, const float start[3], const float vec[3], float radius, float influence_radius,
+                        AbsorbStats* stats) {
+    absorb_capsule(*(Object*)op, v3(start[0], start[1], start[2]), v3(vec[0], vec[1], vec[2]), radius,
+                   influence_radius, stats);
+}
+
 // ---- connected regions ----
 // Runs the whole detection on the object's current state. info (u32 x 24): n_regions, has_two, two[0], two[1],
 // smallest, overflow, n_region_entries, n_label_bytes, then per candidate region 8 words: chunk_count,

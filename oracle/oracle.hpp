@@ -290,6 +290,9 @@ struct AbsorbStats {
 // (centre, influence_radius) and absorbing radius, all in normalized voxel space.
 void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius,
                    AbsorbStats* stats);
+// apply_capsule_absorption likewise: influence capsule (segment start, segment vector, influence_radius)
+void absorb_capsule(Object& obj, V3 segment_start, V3 segment_vector, float radius, float influence_radius,
+                    AbsorbStats* stats);
 
 // --- connected regions (object/split_detection.rs, object/extraction.rs:121-281) ---
 struct ChunkRegions {

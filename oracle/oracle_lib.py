@@ -251,6 +251,14 @@ class Object:
         return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
                 "removed_chunks": int(st[3])}
 
+    def absorb_capsule(self, segment_start, segment_vector, radius: float, influence_radius: float):
+        """apply_capsule_absorption (absorption.rs:846-889) with the influence capsule given in voxel space."""
+        a, v = np.asarray(segment_start, np.float32), np.asarray(segment_vector, np.float32)
+        st = np.zeros(4, np.uint32)
+        lib().orc_absorb_capsule(self.h, _p(a), _p(v), C.c_float(radius), C.c_float(influence_radius), _p(st))
+        return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
+                "removed_chunks": int(st[3])}
+
     REGIONS_DTYPE = np.dtype([("region_count", "<u2"), ("boundary_region_count", "<u2"), ("first_region", "<u4")])
 
     def split_detection(self) -> dict:

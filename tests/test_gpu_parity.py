@@ -169,6 +169,39 @@ def test_absorption_and_dirty_remesh_are_bit_exact(ctx, oracle, name, types):
     H.assert_meshes_equal(VoxelObjectMesh.create(obj_gpu).download(), obj_cpu.mesh(4))
 
 
+@pytest.mark.parametrize("name,types", [("sphere", H.SAME0), ("asteroid_like", H.GRADIENT4)])
+def test_capsule_absorption_is_bit_exact(ctx, oracle, name, types):
+    # apply_capsule_absorption (absorption.rs:846-889) → modify_voxels_within_capsule (intersection.rs:417-537):
+    # slanted, axis-aligned, zero-length, grazing and missing capsules; uniform interior chunks get converted
+    g = H.sphere_graph(40.0) if name == "sphere" else H.asteroid_like_graph(16, 36.0)
+    _, _, _, obj_gpu, obj_cpu = _both(ctx, oracle, g, types)
+    cc = obj_cpu.info()["chunk_counts"]
+    shape = (np.array(cc) * 16).astype(np.float32)
+    f = np.float32
+    mid = f(0.5) * shape
+    capsules = [
+        (mid - f([30.5, 8.25, 3.0]), f([61.0, 16.5, 6.0]), f(5.0)),      # slanted, through the centre
+        (f([mid[0], 2.3, mid[2]]), f([0.0, shape[1] - 4.0, 0.0]), f(3.5)),  # axis aligned (zero components)
+        (mid + f([9.1, -7.7, 11.3]), f([0.0, 0.0, 0.0]), f(6.0)),        # zero-length segment
+        (f([-6.0, mid[1], mid[2]]), f([14.0, 3.0, -2.0]), f(4.0)),       # enters from outside the grid
+        (f([-50.0, -50.0, -50.0]), f([10.0, 0.0, 0.0]), f(4.0)),         # misses the object
+        (mid - f([3.0, 40.0, 1.0]), f([5.5, 80.0, 2.5]), f(9.0)),        # thick, crosses everything again
+    ]
+    for step, (a, v, radius) in enumerate(capsules):
+        st_c = obj_cpu.absorb_capsule(a, v, float(radius), float(radius + f(2.0)))
+        st_g = obj_gpu.absorb_capsule(a, v, float(radius), float(radius + f(2.0)))
+        for k in ("touched_chunks", "touched_voxels", "emptied_voxels", "removed_chunks"):
+            assert st_g[k] == st_c[k], (step, k, st_g, st_c)
+        gch, gvx = obj_gpu.download()
+        H.assert_objects_equal(gch, gvx, obj_cpu.chunks(), obj_cpu.voxels())
+        assert np.array_equal(obj_gpu.info()["occupied_voxel_ranges"], obj_cpu.info()["occupied_voxel_ranges"])
+        assert np.array_equal(np.sort(obj_gpu.invalidated_mesh_chunk_indices()), np.sort(obj_cpu.dirty())), step
+    assert st_c["touched_voxels"] > 0
+    H.assert_meshes_equal(VoxelObjectMesh.create(obj_gpu).download(), obj_cpu.mesh(4))
+    with pytest.raises(Exception):
+        obj_gpu.absorb_capsule(mid, f([1, 0, 0]), -1.0, 1.0)
+
+
 def test_full_size_sphere_properties(ctx):
     # engine bench shape: Sphere(r = 100) → 202³ (benchmarks/voxel_object.rs:650-660); no oracle here,
     # only size-independent properties: reference invariants + closed manifold + radius

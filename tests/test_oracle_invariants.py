@@ -126,6 +126,54 @@ def test_sphere_modification_touches_exactly_the_brute_force_voxel_set(oracle):
     assert before.shape[0] <= obj.voxels().shape[0]
 
 
+def test_capsule_modification_touches_exactly_the_brute_force_voxel_set(oracle):
+    # intersection.rs:955-982 (fuzz_test_obtaining_voxels_within_capsule): voxels visited == voxels whose centre lies
+    # within or on the capsule (CapsulePointContainmentTester, capsule.rs:225-250), restricted to the occupied ranges
+    _, obj = _gen(oracle, H.sphere_graph(23.3))
+    info = obj.info()
+    occ = info["occupied_voxel_ranges"].astype(np.int64)
+    ch_before = obj.chunks().copy()
+    f = np.float32
+    start, vec, radius = f([4.3, 30.1, 9.7]), f([37.0, -11.5, 21.25]), f(6.5)
+    st = obj.absorb_capsule(start, vec, float(radius - f(2.0)), float(radius))
+    # whole chunks of the touched chunk range are visited: the per-chunk voxel range comes from the capsule trimmed
+    # to the chunk, not from the occupied voxel ranges (intersection.rs:445-461), so empty voxels beyond the occupied
+    # ranges are visited too (the reference's fuzz test only counts non-empty ones)
+    end = start + vec
+    lo = np.maximum(np.floor(np.minimum(start, end) - radius), 0).astype(np.int64)
+    hi = np.ceil(np.maximum(start, end) + radius).astype(np.int64)
+    tlo, thi = np.maximum(occ[:, 0], lo), np.minimum(occ[:, 1], hi)
+    assert np.all(tlo < thi)
+    clo, chi = tlo // 16, (thi + 15) // 16
+    idx = np.stack(np.meshgrid(*[np.arange(clo[d] * 16, chi[d] * 16) for d in range(3)], indexing="ij"), -1).reshape(-1, 3)
+    p = idx.astype(np.float32) + f(0.5)
+    len2 = (vec[0] * vec[0] + vec[1] * vec[1]) + vec[2] * vec[2]
+    vol = vec / len2
+    sp = p - start
+    t = np.clip((sp[:, 0] * vol[0] + sp[:, 1] * vol[1]) + sp[:, 2] * vol[2], f(0.0), f(1.0)).astype(np.float32)
+    d = p - (start + vec * t[:, None])
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    inside = d2 <= radius * radius
+    cc = info["chunk_counts"]
+    cidx = ((idx[:, 0] // 16) * cc[1] + idx[:, 1] // 16) * cc[2] + idx[:, 2] // 16
+    not_void = ch_before["kind"][cidx] != 0
+    assert st["touched_voxels"] == int((inside & not_void).sum())
+    assert st["touched_voxels"] > 0 and st["emptied_voxels"] > 0
+    _check_all(oracle, obj)
+    # a capsule with a zero-length segment visits the voxels of the sphere, boundary included
+    _, obj2 = _gen(oracle, H.sphere_graph(23.3))
+    st2 = obj2.absorb_capsule(f([30.2, 24.9, 11.3]), f([0, 0, 0]), 7.5, 9.5)
+    _, obj3 = _gen(oracle, H.sphere_graph(23.3))
+    st3 = obj3.absorb_sphere(f([30.2, 24.9, 11.3]), 7.5, 9.5)
+    assert st2["touched_voxels"] >= st3["touched_voxels"] > 0
+    _check_all(oracle, obj2)
+    # a capsule that misses the object leaves it untouched
+    _, obj4 = _gen(oracle, H.sphere_graph(23.3))
+    v0 = obj4.voxels().copy()
+    st4 = obj4.absorb_capsule(f([-40, -40, -40]), f([5, 0, 0]), 3.0, 5.0)
+    assert st4["touched_voxels"] == 0 and np.array_equal(v0, obj4.voxels()) and len(obj4.dirty()) == 0
+
+
 def test_repeated_absorption_keeps_invariants_and_remesh_is_consistent(oracle):
     _, obj = _gen(oracle, H.sphere_graph(23.3))
     for step in range(4):
