@@ -309,6 +309,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
 
     // ---- evaluate active chunks ----
     EvalArgs ea{};
+    ea.neg_zero = -0.0f;
     ea.nodes = prog->d_nodes;
     ea.gp = gp;
     ea.n_active = n_active;
@@ -782,6 +783,7 @@ int ivx_program_eval_chunks(ivx_ctx* ctx, const ivx_program* prog, const float* 
     if (int rc = read_words(ctx, counters, 2, words)) return rc;
     if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
     EvalArgs ea{};
+    ea.neg_zero = -0.0f;
     ea.nodes = prog->d_nodes;
     ea.n_active = n_chunks;
     ea.active = nullptr;

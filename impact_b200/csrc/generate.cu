@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "packed.cuh"
 #include "kernels.h"
 
 namespace ivx {
@@ -805,6 +806,159 @@ __device__ __noinline__ float fbm3_call(float x, float y, float z, float lacunar
     return result;
 }
 
+// ---- 3-D simplex noise from a per-chunk lattice table, two voxels per thread --------------------------
+// simplex3 (common.cuh) spends more than half of its instructions on the per-corner gradient: the integer hash,
+// the selection of two of (x, y, z) and their sign flips, all on the half-rate ALU pipe. The hash depends only on
+// the lattice point, and one octave of a 16³ chunk touches few lattice points, so the compacted final-noise path
+// builds a table of gradient vectors g ∈ {-1, 0, +1}³ per (chunk, octave) and evaluates a corner's gradient as
+// fma(g.x, x, fma(g.y, y, g.z·z)): products with ±1 / 0 are exact and exactly one component is 0, so the result
+// is RN(±u ± v), simdnoise's `xor_sign(u) + xor_sign(v)` up to the sign of an exact zero (which cannot reach a
+// stored voxel code). The rest of the arithmetic runs on voxel pairs with packed FADD2 / FFMA2 (packed.cuh),
+// operation for operation simplex3's.
+constexpr int TAB3_CAP = 1536;           // float4 entries
+constexpr float CELL3_LIMIT = 1024.0f;   // |cell| < 2^10, strides < 2^11: every integer-valued f32 term stays below 2^22
+
+struct Tab3 {
+    float base;   // MAGIC - entry of the first lattice cell
+    float sa, sb; // entry strides of the x and y cell axes (z has stride 1)
+    float s3;     // sa + sb + 1
+    uint32_t addr;  // shared-memory byte address of entry 0, minus 16 * MAGIC_BITS
+};
+
+// gradient vector of lattice point (I, J, K): grad3d_dot's hash and selection (common.cuh)
+__device__ __forceinline__ float4 grad3_vector(int32_t seed, int32_t I, int32_t J, int32_t K) {
+    uint32_t hash = ((uint32_t)I * 1619u) ^ (uint32_t)seed;
+    hash = ((uint32_t)J * 31337u) ^ hash;
+    hash = ((uint32_t)K * 6791u) ^ hash;
+    hash = ((hash * hash) * 60493u) * hash;
+    hash = (uint32_t)((int32_t)hash >> 13) ^ hash;
+    const uint32_t h13 = hash & 13u;
+    const float su = (hash & 1u) ? -1.0f : 1.0f, sv = (hash & 2u) ? -1.0f : 1.0f;
+    float4 g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (h13 < 8u) g.x = su; else g.y = su;        // u = x or y
+    if (h13 < 2u) g.y = sv;                         // v = y
+    else if (h13 == 12u) g.x = sv;                  // v = x (u is y here)
+    else g.z = sv;                                  // v = z
+    return g;
+}
+
+__device__ __forceinline__ float gdot3(const float4 g, float x, float y, float z) {
+    return __fmaf_rn(g.x, x, __fmaf_rn(g.y, y, g.z * z));
+}
+
+__device__ __forceinline__ f2 simplex3_tab2(f2 x, f2 y, f2 z, const Tab3& T, f2 nz) {
+    const float F3 = 1.0f / 3.0f, G3 = 1.0f / 6.0f, G33 = 3.0f / 6.0f - 1.0f;
+    const f2 f = mul2(bc2(F3), add2(add2(x, y), z), nz);
+    const f2 xf = floor2(add2(x, f)), yf = floor2(add2(y, f)), zf = floor2(add2(z, f));
+    const f2 g = mul2(bc2(G3), add2(add2(xf, yf), zf), nz);
+    const f2 x0 = sub2(x, sub2(xf, g)), y0 = sub2(y, sub2(yf, g)), z0 = sub2(z, sub2(zf, g));
+    // corner steps as exact 0 / 1 floats: a = [x0 >= y0], b = [y0 >= z0], c = [x0 >= z0]
+    const f2 a = make_float2(x0.x >= y0.x ? 1.0f : 0.0f, x0.y >= y0.y ? 1.0f : 0.0f);
+    const f2 b = make_float2(y0.x >= z0.x ? 1.0f : 0.0f, y0.y >= z0.y ? 1.0f : 0.0f);
+    const f2 c = make_float2(x0.x >= z0.x ? 1.0f : 0.0f, x0.y >= z0.y ? 1.0f : 0.0f);
+    const f2 one = bc2(1.0f);
+    const f2 na = sub2(one, a), nb = sub2(one, b), nc = sub2(one, c);
+    const f2 i1 = mul2(a, c, nz), j1 = mul2(na, b, nz), k1 = mul2(nc, nb, nz);                 // and
+    const f2 i2 = sub2(add2(a, c), i1), j2 = sub2(add2(na, b), j1), k2 = sub2(one, mul2(c, b, nz));  // or / nand
+
+    const f2 sa = bc2(T.sa), sb = bc2(T.sb);
+    const f2 e0 = fma2(xf, sa, fma2(yf, sb, add2(zf, bc2(T.base))));
+    const f2 e1 = fma2(i1, sa, fma2(j1, sb, add2(k1, e0)));
+    const f2 e2 = fma2(i2, sa, fma2(j2, sb, add2(k2, e0)));
+    const f2 e3 = add2(e0, bc2(T.s3));
+    const float4 g0a = tab_load(e0.x, T.addr), g0b = tab_load(e0.y, T.addr);
+    const float4 g1a = tab_load(e1.x, T.addr), g1b = tab_load(e1.y, T.addr);
+    const float4 g2a = tab_load(e2.x, T.addr), g2b = tab_load(e2.y, T.addr);
+    const float4 g3a = tab_load(e3.x, T.addr), g3b = tab_load(e3.y, T.addr);
+
+    const f2 cG3 = bc2(G3), cF3 = bc2(F3), cG33 = bc2(G33), c06 = bc2(0.6f);
+    const f2 x1 = add2(sub2(x0, i1), cG3), y1 = add2(sub2(y0, j1), cG3), z1 = add2(sub2(z0, k1), cG3);
+    const f2 x2 = add2(sub2(x0, i2), cF3), y2 = add2(sub2(y0, j2), cF3), z2 = add2(sub2(z0, k2), cF3);
+    const f2 x3 = add2(x0, cG33), y3 = add2(y0, cG33), z3 = add2(z0, cG33);
+#define IVX_T3(X, Y, Z) sub2(sub2(sub2(c06, mul2(X, X, nz)), mul2(Y, Y, nz)), mul2(Z, Z, nz))
+    f2 t0 = IVX_T3(x0, y0, z0), t1 = IVX_T3(x1, y1, z1), t2 = IVX_T3(x2, y2, z2), t3 = IVX_T3(x3, y3, z3);
+#undef IVX_T3
+    // (t >= 0) ? t : 0, NaN → 0
+    t0 = max2c(t0, 0.0f); t1 = max2c(t1, 0.0f); t2 = max2c(t2, 0.0f); t3 = max2c(t3, 0.0f);
+    t0 = mul2(t0, t0, nz); t1 = mul2(t1, t1, nz); t2 = mul2(t2, t2, nz); t3 = mul2(t3, t3, nz);
+    t0 = mul2(t0, t0, nz); t1 = mul2(t1, t1, nz); t2 = mul2(t2, t2, nz); t3 = mul2(t3, t3, nz);
+    const f2 v0 = mul2(t0, make_float2(gdot3(g0a, x0.x, y0.x, z0.x), gdot3(g0b, x0.y, y0.y, z0.y)), nz);
+    const f2 v1 = mul2(t1, make_float2(gdot3(g1a, x1.x, y1.x, z1.x), gdot3(g1b, x1.y, y1.y, z1.y)), nz);
+    const f2 v2 = mul2(t2, make_float2(gdot3(g2a, x2.x, y2.x, z2.x), gdot3(g2b, x2.y, y2.y, z2.y)), nz);
+    const f2 v3 = mul2(t3, make_float2(gdot3(g3a, x3.x, y3.x, z3.x), gdot3(g3b, x3.y, y3.y, z3.y)), nz);
+    const f2 p1 = add2(v3, v2);
+    const f2 p2 = add2(p1, v1);
+    return mul2(add2(p2, v0), bc2(32.69428253173828125f), nz);
+}
+
+// One octave of a whole k-column (16 voxels of thread (i, j)) as 8 voxel pairs. Out of line on purpose: k_eval keeps
+// its column of 16 distances live across the noise node; the call boundary parks them once per octave instead of
+// raising the kernel's register count (a resident CTA per SM).
+__device__ __noinline__ void noise_column_tab(float* acc, const float* coord, int ti, int tj, Tab3 T, float amp,
+                                              bool first_octave, float neg_zero) {
+    __builtin_assume(__isShared(coord));
+    const f2 nz = bc2(neg_zero);
+    const f2 y = bc2(coord[16 + tj]), z = bc2(coord[32 + ti]);
+#pragma unroll 1
+    for (int k = 0; k < 16; k += 2) {
+        const f2 sv = simplex3_tab2(make_float2(coord[k], coord[k + 1]), y, z, T, nz);
+        acc[k] = first_octave ? sv.x : sv.x * amp + acc[k];
+        acc[k + 1] = first_octave ? sv.y : sv.y * amp + acc[k + 1];
+    }
+}
+
+// Lattice cells one octave of the chunk touches, from the noise coordinates of its 8 corner voxels (coord[0..15] x,
+// [16..31] y, [32..47] z): the cell is monotone in each coordinate (every step of simplex3's cell computation is a
+// monotone f32 operation) and each coordinate is monotone in its voxel index, so the corners bound it. Called by
+// warp 0; lane 0 writes min[3], max[3] and the usable flag to `cell`.
+__device__ __forceinline__ void lattice3_bounds(const float* coord, int lane, int* cell) {
+    const float F3 = 1.0f / 3.0f;
+    const float cx = coord[(lane & 1) ? 15 : 0], cy = coord[16 + ((lane & 2) ? 15 : 0)], cz = coord[32 + ((lane & 4) ? 15 : 0)];
+    const float ff = F3 * ((cx + cy) + cz);
+    const float c3[3] = {floorf(cx + ff), floorf(cy + ff), floorf(cz + ff)};
+    int ok = 1, lo3[3], hi3[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) ok &= (fabsf(c3[d]) < CELL3_LIMIT) ? 1 : 0;  // false for NaN too
+#pragma unroll
+    for (int d = 0; d < 3; ++d) lo3[d] = hi3[d] = ok ? (int)c3[d] : 0;
+#pragma unroll
+    for (int sh = 1; sh < 8; sh <<= 1) {
+        ok &= __shfl_xor_sync(0xffffffffu, ok, sh);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            lo3[d] = min(lo3[d], __shfl_xor_sync(0xffffffffu, lo3[d], sh));
+            hi3[d] = max(hi3[d], __shfl_xor_sync(0xffffffffu, hi3[d], sh));
+        }
+    }
+    if (lane == 0) {
+        const int64_t entries = ok ? (int64_t)(hi3[0] - lo3[0] + 2) * (hi3[1] - lo3[1] + 2) * (hi3[2] - lo3[2] + 2) : 0;
+        cell[6] = (ok && entries <= TAB3_CAP) ? 1 : 0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            cell[d] = lo3[d];
+            cell[3 + d] = hi3[d];
+        }
+    }
+}
+
+// fills the gradient table for the cell bounds in `cell` (all threads) and returns its addressing constants
+__device__ __forceinline__ Tab3 lattice3_build(const int* cell, float4* tab, int32_t seed, int tid) {
+    const int cx0 = cell[0], cy0 = cell[1], cz0 = cell[2];
+    const uint32_t Dy = (uint32_t)(cell[4] - cy0 + 2), Dz = (uint32_t)(cell[5] - cz0 + 2);
+    const uint32_t entries = (uint32_t)(cell[3] - cx0 + 2) * Dy * Dz;
+    for (uint32_t e = tid; e < entries; e += 256u) {
+        const uint32_t dz_ = e % Dz, dy_ = (e / Dz) % Dy, dx_ = e / (Dz * Dy);
+        tab[e] = grad3_vector(seed, cx0 + (int)dx_, cy0 + (int)dy_, cz0 + (int)dz_);
+    }
+    Tab3 T;
+    T.sa = (float)(Dy * Dz);
+    T.sb = (float)Dz;
+    T.s3 = (float)(Dy * Dz + Dz + 1u);
+    T.base = MAGIC - (((float)cx0 * T.sa + (float)cy0 * T.sb) + (float)cz0);
+    T.addr = (uint32_t)__cvta_generic_to_shared(tab) - MAGIC_BITS * 16u;
+    return T;
+}
+
 // ---------------------------------------------------------------------------
 // k_eval: CTA (256 threads) per active chunk; thread (i, j) owns the 16 voxels
 // of one k-column so the reference's incremental `position += dz` walk
@@ -817,11 +971,13 @@ __device__ __forceinline__ float* stack_level(float* smem_stack, float* spill, i
     return level < smem_levels ? smem_stack + (size_t)level * 4096 : spill + (size_t)(level - smem_levels) * 4096;
 }
 
-__global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
+__global__ void __launch_bounds__(EVAL_THREADS, 3) k_eval(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_stack = reinterpret_cast<float*>(smem_raw);
     __shared__ float s_coord[48];
     __shared__ uint32_t s_wsum[EVAL_THREADS / 32];
+    __shared__ __align__(16) float4 s_tab3[TAB3_CAP];  // lattice gradient table of the current (chunk, octave)
+    __shared__ int s_cell[8];                          // cell bounds min[3], max[3], usable flag
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tj = tid & 15;
     float* spill = a.spill ? a.spill + (size_t)blockIdx.x * a.spill_levels * 4096 : nullptr;
@@ -984,6 +1140,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                             }
                         }
                         __syncthreads();
+                        // (~300 surviving voxels per chunk and octave on the asteroid: one evaluation per thread, so the
+                        // lattice table of the generic path below does not pay here)
                         for (uint32_t it = tid; it < n_list; it += EVAL_THREADS) {
                             const uint32_t idx = list[it];
                             const float sx = s_coord[idx & 15u], sy = s_coord[16 + ((idx >> 4) & 15u)],
@@ -1014,14 +1172,41 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(EvalArgs a) {
                         pos = pos + f.dzn;
                     }
                 } else {
-                    const float zc = accumulate_ones(f.o.x, ti) * f.freq;
-                    const float yc = accumulate_ones(f.o.y, tj) * f.freq;
-#pragma unroll 1
-                    for (int k = 0; k < 16; ++k) {
-                        float xc = block_noise_x(f.o.z, k) * f.freq;
-                        float nv = fbm3_call(xc, yc, zc, lac, gain, oct, seed);
-                        top[k] = top[k] + nv * ns;
+                    // ---- the whole chunk, octave by octave: fbm3 (common.cuh) with the octave loop outermost, so that
+                    // one lattice gradient table serves all 4096 evaluations of an octave ----
+                    const uint32_t n_oct = max(oct & 0xFFu, 1u);
+                    __syncthreads();  // s_coord / s_tab3 may still be read by the previous noise node
+                    if (tid < 16) {
+                        s_coord[tid] = block_noise_x(f.o.z, tid) * f.freq;            // simdnoise x = our k
+                        s_coord[16 + tid] = accumulate_ones(f.o.y, tid) * f.freq;     // y = our j
+                        s_coord[32 + tid] = accumulate_ones(f.o.x, tid) * f.freq;     // z = our i
                     }
+                    float acc[16];
+                    float amp = 1.0f;
+                    for (uint32_t o = 0; o < n_oct; ++o) {
+                        if (o > 0) {
+                            amp = amp * gain;
+                            if (tid < 48) s_coord[tid] = s_coord[tid] * lac;
+                        }
+                        __syncthreads();
+                        if (tid < 32) lattice3_bounds(s_coord, tid, s_cell);
+                        __syncthreads();
+                        if (s_cell[6]) {
+                            const Tab3 T = lattice3_build(s_cell, s_tab3, seed, tid);
+                            __syncthreads();
+                            noise_column_tab(acc, s_coord, ti, tj, T, amp, o == 0, a.neg_zero);
+                        } else {
+                            const float yc = s_coord[16 + tj], zc = s_coord[32 + ti];
+#pragma unroll 1
+                            for (int k = 0; k < 16; ++k) {
+                                const float sv = simplex3_call(s_coord[k], yc, zc, seed);
+                                acc[k] = o == 0 ? sv : sv * amp + acc[k];
+                            }
+                        }
+                        __syncthreads();  // before the coordinates and the table are overwritten
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) top[k] = top[k] + acc[k] * ns;
                 }
             } else {  // OP_COMBINE
                 const float* lv = stack_level(s_stack, spill, sp - 2, a.smem_levels);

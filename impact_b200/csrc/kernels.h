@@ -56,6 +56,7 @@ struct EvalArgs {
     int smem_levels;
     float* spill;
     int spill_levels;
+    float neg_zero;           // -0.0f, deliberately a run-time value (packed.cuh)
 };
 cudaError_t launch_eval(const EvalArgs& a, uint32_t grid, cudaStream_t st);
 int eval_max_blocks_per_sm(int smem_levels);

@@ -20,6 +20,7 @@
 // Corner ranks are computed as small floats so that almost all of the work runs on the FMA pipe
 // (FADD / FMUL / FFMA / IMAD) instead of the half-rate ALU pipe (ISETP / SEL / LOP3).
 #include "common.cuh"
+#include "packed.cuh"
 #include "kernels.h"
 
 namespace ivx {
@@ -31,8 +32,6 @@ constexpr int TYPES_THREADS = 256;
 constexpr int TAB_CAP = 1024;        // gradient-table entries (float4) per batch of types
 constexpr int MAX_TYPES = 255;
 constexpr float CELL_LIMIT = 4096.0f;  // |cell index| < 2^12 and strides <= 2^9: every integer-valued f32 term stays below 2^22
-constexpr float MAGIC = 12582912.0f;      // 1.5 * 2^23: (small integer + MAGIC) keeps the integer in the low mantissa bits
-constexpr uint32_t MAGIC_BITS = 0x4B400000u;
 
 struct TypeTab {   // per-type constants of the table walk
     float x;       // noise x coordinate of this type (already multiplied by voxel_type_frequency)
@@ -42,11 +41,6 @@ struct TypeTab {   // per-type constants of the table walk
     uint32_t addr; // shared-memory byte address of entry 0, minus 16 * MAGIC_BITS
 };
 
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
 
 // simdnoise simplex_4d (see common.cuh simplex4_t for the direct restatement) with the gradient of
 // each corner read from the chunk's lattice table.
@@ -110,37 +104,6 @@ __device__ __forceinline__ float simplex4_tab(float x, float y, float z, float w
     const float n3 = q3 * __fmaf_rn(g3.x, x3, __fmaf_rn(g3.y, y3, __fmaf_rn(g3.z, z3, g3.w * w3)));
     const float n4 = q4 * __fmaf_rn(g4.x, x4, __fmaf_rn(g4.y, y4, __fmaf_rn(g4.z, z4, g4.w * w4)));
     return (n0 + (n1 + (n2 + (n3 + n4)))) * 62.77772078955791f;
-}
-
-// ---- two voxels per thread on the packed f32x2 pipe -------------------------------------------------
-// sm_100a issues FADD2 / FFMA2 (two independent, individually rounded f32 operations per lane) at the
-// scalar FP32 rate per *operation* but half the rate per *instruction*; k_types is bound by issue
-// slots, not by the FMA pipe (tools/microbench/f32x2.cu, profiles/README.md), so the same arithmetic
-// on (k, k+1) voxel pairs needs ~1/3 fewer slots. Every packed operation rounds exactly like the scalar
-// one it replaces. ptxas 12.9 contracts `mul.rn.f32x2` followed by `add.rn.f32x2` into FFMA2 even
-// under --fmad=false, which would change results; packed products therefore go through FFMA2 with an
-// addend of -0.0 that is only known at run time (x·y + (-0) == RN(x·y) for every x·y, signed zeros
-// included), so there is no multiply for ptxas to contract.
-typedef float2 f2;
-__device__ __forceinline__ f2 bc2(float a) { return make_float2(a, a); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz) { return __ffma2_rn(a, b, nz); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ f2 gt2(f2 a, f2 b) { return make_float2(a.x > b.x ? 1.0f : 0.0f, a.y > b.y ? 1.0f : 0.0f); }
-__device__ __forceinline__ f2 gtc2(f2 a, float c) { return make_float2(a.x > c ? 1.0f : 0.0f, a.y > c ? 1.0f : 0.0f); }
-__device__ __forceinline__ f2 floor2(f2 a) { return make_float2(floorf(a.x), floorf(a.y)); }
-__device__ __forceinline__ f2 min2c(f2 a, float c) { return make_float2(fminf(a.x, c), fminf(a.y, c)); }
-__device__ __forceinline__ f2 max2c(f2 a, float c) { return make_float2(fmaxf(a.x, c), fmaxf(a.y, c)); }
-// entry address of a MAGIC-biased entry number. Inline PTX on purpose: nvcc 12.9 drops the `* 16` for the
-// low half of a float2 returned by the f32x2 builtins when this is written in C++.
-__device__ __forceinline__ float4 tab_load(float e, uint32_t addr) {
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(r) : "r"(__float_as_uint(e)), "r"(addr));
-    return lds128(r);
-}
-__device__ __forceinline__ float gdot(const float4 g, float x, float y, float z, float w) {
-    return __fmaf_rn(g.x, x, __fmaf_rn(g.y, y, __fmaf_rn(g.z, z, g.w * w)));
 }
 
 // simplex4_tab for the voxel pair (y.x, y.y); x, z, w are the same for both. Operation for operation
