@@ -22,6 +22,7 @@ namespace ivx {
 
 constexpr int MESH_THREADS = 256;
 constexpr int N_CUBES = 17 * 17 * 17;
+constexpr int MQ_CAP = 384;  // queued multi-material quads per tile of 256 vertices; the rest are handled in place
 constexpr int CUBES_PER_THREAD = (N_CUBES + MESH_THREADS - 1) / MESH_THREADS;  // 20
 
 // SurfaceNetsVertexMaterials (surface_nets.rs:440-451) packed into registers: byte q of `idx` / `wgt` is
@@ -147,17 +148,51 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return woff + x - v;
 }
 
+// index materials of the two triangles of a quad whose corner vertices carry several materials
+// (calculate_all_index_materials, surface_nets.rs:540-637, slow path)
+__device__ __forceinline__ void emit_quad_materials(const uint32_t vid[4], uint32_t order, const uint16_t* s_surf,
+                                                    const uint32_t* s_neg, const uint8_t* s_type, uint64_t* IM) {
+    VertexMaterials vm[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int l = s_surf[vid[c]];
+        const int r = (l / 324) * 18 + (l / 18) % 18, k = l % 18;
+        const uint32_t neg = ((s_neg[r] >> k) & 3u) | (((s_neg[r + 1] >> k) & 3u) << 2) |
+                             (((s_neg[r + 18] >> k) & 3u) << 4) | (((s_neg[r + 19] >> k) & 3u) << 6);
+        vm[c] = vertex_materials(neg, s_type, l);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        VertexMaterials tv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t sel = (order >> (3 * (3 * t + c))) & 3u;
+            tv[c] = sel == 0 ? vm[0] : (sel == 1 ? vm[1] : (sel == 2 ? vm[2] : vm[3]));
+        }
+        uint64_t im[3];
+        triangle_index_materials(tv, im);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) IM[3 * t + c] = im[c];
+    }
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
     __shared__ __align__(16) int8_t s_sd[5832];
     __shared__ __align__(16) uint8_t s_type[5832];
-    __shared__ uint16_t s_l2v[EMIT ? 5832 : 1];
+    __shared__ __align__(4) uint16_t s_l2v[EMIT ? 5832 : 2];
+    __shared__ uint32_t s_neg[324];
+    // multi-material quads of one tile of 256 vertices (<= 3 each): index position | corner order << 14, vertex ids
+    __shared__ uint32_t s_mq_head[EMIT ? MQ_CAP : 1];
+    __shared__ ushort4 s_mq_vid[EMIT ? MQ_CAP : 1];
+    __shared__ uint32_t s_mq_count;
     __shared__ uint16_t s_surf[N_CUBES];
     __shared__ uint8_t s_vmat[EMIT ? N_CUBES : 1];
     __shared__ uint32_t s_warp[MESH_THREADS / 32];
     __shared__ uint32_t s_adj_up[3];
 
     const int tid = threadIdx.x;
+    if (tid == 0) s_mq_count = 0;
     for (uint32_t w = blockIdx.x; w < a.n_work; w += gridDim.x) {
         const uint32_t chunk = a.work[w];
         const uint32_t ck = chunk % a.nb[2], cj = (chunk / a.nb[2]) % a.nb[1], ci = chunk / (a.nb[2] * a.nb[1]);
@@ -174,8 +209,40 @@ __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
             }
             s_adj_up[tid] = up;
         }
-        for (int cell = tid; cell < 5832; cell += MESH_THREADS) {
-            const int bi = cell / 324, bj = (cell / 18) % 18, bk = cell % 18;
+        // interior 16³: the chunk's own planes, one 16-byte row (i, j, 0..15) per thread and plane
+        {
+            const DevChunk me = a.chunks[chunk];  // NonUniform by construction of the work list
+            const unsigned char* slot = a.voxels + (size_t)me.slot * SLOT_BYTES;
+            const uint4 wsd = *reinterpret_cast<const uint4*>(slot + PLANE_SD + tid * 16);
+            const uint4 wty = *reinterpret_cast<const uint4*>(slot + PLANE_TYPE + tid * 16);
+            const uint32_t ws[4] = {wsd.x, wsd.y, wsd.z, wsd.w}, wt[4] = {wty.x, wty.y, wty.z, wty.w};
+            const int row = bidx((tid >> 4) + 1, (tid & 15) + 1, 1);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                s_sd[row + k] = (int8_t)((ws[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+                s_type[row + k] = (uint8_t)((wt[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+            }
+        }
+        // the 1-voxel halo (1736 cells) from the up to 26 neighbours (object/sdf.rs:410-508): the two i planes, then
+        // the two j planes without their i borders, then the two k planes without their i and j borders
+        for (int h = tid; h < 1736; h += MESH_THREADS) {
+            int bi, bj, bk;
+            if (h < 648) {
+                bi = (h / 324) * 17;
+                bj = (h % 324) / 18;
+                bk = h % 18;
+            } else if (h < 1224) {
+                const int r = (h - 648) % 288;
+                bi = 1 + r / 18;
+                bj = ((h - 648) / 288) * 17;
+                bk = r % 18;
+            } else {
+                const int r = (h - 1224) % 256;
+                bi = 1 + (r >> 4);
+                bj = 1 + (r & 15);
+                bk = ((h - 1224) / 256) * 17;
+            }
+            const int cell = bidx(bi, bj, bk);
             const int gi = (int)ci * 16 + bi - 1, gj = (int)cj * 16 + bj - 1, gk = (int)ck * 16 + bk - 1;
             int8_t sd = 127;
             uint8_t ty = 255;
@@ -196,7 +263,16 @@ __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
             }
             s_sd[cell] = sd;
             s_type[cell] = ty;
-            if (EMIT) s_l2v[cell] = 0xFFFF;
+        }
+        if (EMIT)
+            for (int cell = tid; cell < 5832 / 2; cell += MESH_THREADS) reinterpret_cast<uint32_t*>(s_l2v)[cell] = 0xFFFFFFFFu;
+        __syncthreads();
+        // sign bits per brick row (i, j): bit k = cell (i, j, k) is negative
+        for (int r = tid; r < 324; r += MESH_THREADS) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int k = 0; k < 18; ++k) m |= (s_sd[r * 18 + k] < 0 ? 1u : 0u) << k;
+            s_neg[r] = m;
         }
         __syncthreads();
 
@@ -221,10 +297,10 @@ __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
 #pragma unroll 4
             for (int u = 0; u < CUBES_PER_THREAD; ++u) {
                 if (q0 + u < N_CUBES) {
-                    const int lin = bidx(i, j, k);
-                    uint32_t neg = 0;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) neg |= (s_sd[lin + corner_off(c)] < 0 ? 1u : 0u) << c;
+                    // the cube's 8 corner signs: bits k, k+1 of the four rows (i, j), (i, j+1), (i+1, j), (i+1, j+1)
+                    const int r = i * 18 + j;
+                    const uint32_t neg = ((s_neg[r] >> k) & 3u) | (((s_neg[r + 1] >> k) & 3u) << 2) |
+                                         (((s_neg[r + 18] >> k) & 3u) << 4) | (((s_neg[r + 19] >> k) & 3u) << 6);
                     if (neg != 0u && neg != 0xFFu) smask |= 1u << u;
                 }
                 if (++k == 17) {
@@ -375,32 +451,34 @@ __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
 #pragma unroll
                         for (int c = 0; c < 6; ++c) IM[c] = im;
                     } else {
-                        VertexMaterials vm[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint32_t neg = 0;
-#pragma unroll
-                            for (int cc = 0; cc < 8; ++cc) neg |= (s_sd[cl[c] + corner_off(cc)] < 0 ? 1u : 0u) << cc;
-                            vm[c] = vertex_materials(neg, s_type, cl[c]);
-                        }
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            VertexMaterials tv[3];
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const uint32_t sel = (order >> (3 * (3 * t + c))) & 3u;
-                                tv[c] = sel == 0 ? vm[0] : (sel == 1 ? vm[1] : (sel == 2 ? vm[2] : vm[3]));
-                            }
-                            uint64_t im[3];
-                            triangle_index_materials(tv, im);
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) IM[3 * t + c] = im[c];
+                        // several materials meet here: queued, and worked off below by dense lanes instead of by the
+                        // few lanes of this warp that happen to sit on a material boundary
+                        const uint32_t e = atomicAdd(&s_mq_count, 1u);
+                        if (e < MQ_CAP) {
+                            s_mq_head[e] = qi | (order << 14);
+                            s_mq_vid[e] = make_ushort4((unsigned short)vid[0], (unsigned short)vid[1], (unsigned short)vid[2],
+                                                       (unsigned short)vid[3]);
+                        } else {
+                            emit_quad_materials(vid, order, s_surf, s_neg, s_type, IM);  // queue full: in place
                         }
                     }
                     qi++;
                 }
             }
             n_quads += tile_total;
+            if (EMIT && !skip_emit) {
+                __syncthreads();
+                const uint32_t n_mq = min(s_mq_count, (uint32_t)MQ_CAP);
+                for (uint32_t e = tid; e < n_mq; e += MESH_THREADS) {
+                    const uint32_t head = s_mq_head[e];
+                    const ushort4 v4 = s_mq_vid[e];
+                    const uint32_t vid[4] = {v4.x, v4.y, v4.z, v4.w};
+                    emit_quad_materials(vid, head >> 14, s_surf, s_neg, s_type,
+                                        reinterpret_cast<uint64_t*>(a.index_materials + (size_t)ioff + 6 * (size_t)(head & 0x3FFFu)));
+                }
+                __syncthreads();
+                if (tid == 0) s_mq_count = 0;
+            }
         }
 
         if (!EMIT) {

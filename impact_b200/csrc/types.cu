@@ -26,6 +26,10 @@
 namespace ivx {
 
 constexpr int TYPES_THREADS = 256;
+#ifndef IVX_TYPES_UNROLL
+#define IVX_TYPES_UNROLL 1
+#endif
+constexpr int TYPES_UNROLL = IVX_TYPES_UNROLL;  // voxel pairs in flight per thread
 #ifndef IVX_TYPES_CTAS
 #define IVX_TYPES_CTAS 3   // resident CTAs per SM the register budget is set for
 #endif
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(TYPES_THREADS, IVX_TYPES_CTAS) k_types(TypesAr
                         T.addr = tab_base + (uint32_t)S.tab_off[t] * 16u - MAGIC_BITS * 16u;
                         const f2 X2 = bc2(T.x);
                         float yacc = lo.z;
-#pragma unroll 1
+#pragma unroll TYPES_UNROLL
                         for (int k = 0; k < 16; k += 2) {
                             const float yacc1 = yacc + 1.0f;
                             const f2 nv = simplex4_tab2(X2, make_float2(yacc * fn, yacc1 * fn), Z2, W2, ZW2, T, nz);

@@ -82,6 +82,24 @@ def csg_zoo_graph():
     return g
 
 
+def mid_noise_graph():
+    """Multi-octave noise in the middle of the program (not the last node, not rotated): the evaluator's
+    whole-chunk, octave-by-octave path. Lacunarity 3 makes the last octaves touch more lattice cells per chunk than
+    the gradient table holds, so both the table and the direct evaluation run; the translated copy sits far from the
+    noise origin (large cell indices)."""
+    g = SDFGraph()
+    s = g.sphere(26.0)
+    n = g.multifractal_noise(s, 4, 0.11, 3.0, 0.55, 3.0, 11)
+    n = g.translation(n, [7.5, -3.25, 2.0])
+    b = g.box([30.0, 12.0, 44.0])
+    u = g.union(n, b, 2.5)
+    s2 = g.sphere(9.0)
+    n2 = g.multifractal_noise(s2, 2, 0.7, 2.0, 0.5, 1.0, 3)
+    n2 = g.translation(n2, [-31.0, 20.0, -18.0])
+    g.union(u, n2, 0.0)
+    return g
+
+
 def asteroid_like_graph(n_craters=24, radius=40.0, seed=3):
     """A hand-built stand-in with the asteroid's structure (smooth union of a few spheres, noise,
     smooth subtraction of a balanced union tree of rotated capsules, final noise)."""

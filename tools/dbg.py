@@ -11,3 +11,6 @@ gen = ctx.build_generator(g)
 print("program nodes", gen.node_count, "depth", gen.stack_depth)
 obj = VoxelObject.generate(SDFVoxelGenerator(1.0, gen, t))
 print(obj.info())
+if len(sys.argv) > 2 and sys.argv[2] == "mesh":
+    m = VoxelObjectMesh.create(obj)
+    print("mesh", m.info if hasattr(m, "info") else "")
