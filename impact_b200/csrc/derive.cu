@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) k_boundary_apply(DevChunk* __restrict__ c
                                                          const uint32_t* __restrict__ work_list, uint32_t n_work,
                                                          uint32_t own_lo, uint32_t own_hi) {
     __shared__ __align__(16) uint8_t s_flags[4096];
+    __shared__ Neighbour s_nb[6];
     const int tid = threadIdx.x;
     for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
         const uint32_t c = work_list ? work_list[w] : w;
@@ -105,12 +106,37 @@ __global__ void __launch_bounds__(256) k_boundary_apply(DevChunk* __restrict__ c
             slot = voxels + (size_t)me.slot * SLOT_BYTES;
             *reinterpret_cast<uint4*>(&s_flags[tid * 16]) = *reinterpret_cast<const uint4*>(slot + PLANE_FLAGS + tid * 16);
         }
+        // the six neighbours' descriptors in one round trip
+        if (tid < 6) s_nb[tid] = neighbour_of(chunks, nb, ci, cj, ck, tid >> 1, tid & 1, convert_flag);
         __syncthreads();
         uint8_t cflags = me.flags;
+        // this thread's face voxel per face, and for faces against a Mixed neighbour face the adjacent voxel's
+        // emptiness, all fetched before any of them is used (independent loads instead of six dependent ones)
+        int fidx[6];
+        uint32_t adj_empty = 0, mixed = 0;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+            const int dim = f >> 1, side = f & 1;
+            const int b = tid >> 4, cc = tid & 15, p = side ? 15 : 0;
+            int v[3];
+            v[dim] = p;
+            v[dim == 0 ? 1 : 0] = b;
+            v[dim == 2 ? 1 : 2] = cc;
+            fidx[f] = vidx(v[0], v[1], v[2]);
+            const Neighbour nbh = s_nb[f];
+            if (((mask >> f) & 1) && me.face[f] != 0 && nbh.kind == 2 && nbh.face == 2 && !(s_flags[fidx[f]] & 1)) {
+                int a3[3] = {v[0], v[1], v[2]};
+                a3[dim] = side ? 0 : 15;
+                const unsigned char* nslot = voxels + (size_t)nbh.slot * SLOT_BYTES;
+                mixed |= 1u << f;
+                if (nslot[PLANE_FLAGS + vidx(a3[0], a3[1], a3[2])] & 1) adj_empty |= 1u << f;
+            }
+        }
+#pragma unroll
         for (int f = 0; f < 6; ++f) {
             if (!((mask >> f) & 1)) continue;
             const int dim = f >> 1, side = f & 1;
-            const Neighbour nbh = neighbour_of(chunks, nb, ci, cj, ck, dim, side, convert_flag);
+            const Neighbour nbh = s_nb[f];
             const uint8_t own = me.face[f];
             // obscuredness
             const uint8_t obit = (uint8_t)(1u << (side == 0 ? dim : 3 + dim));
@@ -118,25 +144,13 @@ __global__ void __launch_bounds__(256) k_boundary_apply(DevChunk* __restrict__ c
             if (obscured) cflags |= obit; else cflags &= (uint8_t)~obit;
             if (own != 0) {
                 const uint8_t abit = (uint8_t)(1u << ((side == 0 ? 2 : 5) + dim));
-                // face voxel handled by this thread: the two other dims ascending
-                const int b = tid >> 4, cc = tid & 15, p = side ? 15 : 0;
-                int v[3];
-                v[dim] = p;
-                v[dim == 0 ? 1 : 0] = b;
-                v[dim == 2 ? 1 : 2] = cc;
-                const int idx = vidx(v[0], v[1], v[2]);
+                const int idx = fidx[f];
                 if (nbh.kind == 0 || (nbh.kind == 2 && nbh.face == 0)) {
                     s_flags[idx] &= (uint8_t)~abit;
                 } else if (nbh.kind == 1 || nbh.face == 1) {
                     s_flags[idx] |= abit;
-                } else {
-                    if (!(s_flags[idx] & 1)) {
-                        int a[3] = {v[0], v[1], v[2]};
-                        a[dim] = side ? 0 : 15;
-                        const unsigned char* nslot = voxels + (size_t)nbh.slot * SLOT_BYTES;
-                        const bool adj_empty = (nslot[PLANE_FLAGS + vidx(a[0], a[1], a[2])] & 1) != 0;
-                        if (adj_empty) s_flags[idx] &= (uint8_t)~abit; else s_flags[idx] |= abit;
-                    }
+                } else if ((mixed >> f) & 1u) {
+                    if ((adj_empty >> f) & 1u) s_flags[idx] &= (uint8_t)~abit; else s_flags[idx] |= abit;
                 }
             }
             __syncthreads();  // edge / corner voxels sit on several faces
