@@ -119,8 +119,17 @@ uint32_t ivx_persistent_grid(ivx_ctx* ctx, uint32_t n_work, int blocks_per_sm) {
 
 namespace {
 
+// host destination of a streamed generation (ivx_object_generate_streamed)
+struct StreamOut {
+    ivx_chunk_desc* h_chunks;
+    size_t chunk_capacity;
+    ivx_voxel* h_voxels;
+    size_t voxel_capacity;   // voxels
+    uint64_t n_non_uniform;  // out
+};
+
 int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, const ivx_type_generator* tg,
-                  uint32_t i_begin, uint32_t i_end, bool whole, ivx_object** out) {
+                  uint32_t i_begin, uint32_t i_end, bool whole, ivx_object** out, StreamOut* so = nullptr) {
     if (!(voxel_extent > 0.0f)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "voxel_extent must be > 0");
     if (tg->kind > 1) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "unknown voxel type generator kind %u", tg->kind);
     if (tg->kind == 1 && (tg->n_types == 0 || tg->n_types > 255))
@@ -328,32 +337,117 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     ea.saturate_final_noise = 1;
     uint32_t egrid = 1;
     if (int rc = plan_eval_stack(ctx, max_depth, tmp, n_active, ea, egrid)) return rc;
-    if (n_active) KLP(ctx, 2, launch_eval(ea, egrid, st));
-    if (n_active) {
-        TypesArgs ta{};
-        ta.gp = gp;
-        ta.n_active = n_active;
-        ta.active = active_list;
-        for (int d = 0; d < 3; ++d) ta.nb[d] = obj->nb[d];
-        ta.first_i = obj->first_i;
-        ta.slot_of = slot_of;
-        ta.voxels = obj->d_voxels;
-        ta.chunks = obj->d_chunks;
-        ta.occ = counters + 2;
-        ta.neg_zero = -0.0f;
-        KLP(ctx, 7, launch_types(ta, persistent_grid(ctx, n_active, std::max(1, types_max_blocks_per_sm())), st));
-    }
+    TypesArgs ta{};
+    ta.gp = gp;
+    for (int d = 0; d < 3; ++d) ta.nb[d] = obj->nb[d];
+    ta.first_i = obj->first_i;
+    ta.slot_of = slot_of;
+    ta.voxels = obj->d_voxels;
+    ta.chunks = obj->d_chunks;
+    ta.occ = counters + 2;
+    ta.neg_zero = -0.0f;
+    const int types_bps = std::max(1, types_max_blocks_per_sm());
 
-    // ---- cross-chunk derived state ----
+    // A streamed generation (ivx_object_generate_streamed) cuts the chunk planes into parts: each part is evaluated,
+    // typed, gets its cross-chunk state as soon as the next plane is typed, is packed to the reference's voxel layout
+    // and handed to the copy stream, so the device→host transfer of part p runs under the arithmetic of parts > p.
+    // The ordinary generation is the one-part case without the pack / copy tail.
+    const uint32_t plane = obj->nb[1] * obj->nb[2];
+    const uint32_t P = (so && whole) ? std::min<uint32_t>(8u, std::max<uint32_t>(1u, obj->nb[0] / 4u)) : 1u;
+    std::vector<uint32_t> xb(P + 1), ab(P + 1);
+    for (uint32_t q = 0; q <= P; ++q) xb[q] = (uint32_t)((uint64_t)q * obj->nb[0] / P);
+    ab[0] = 0;
+    ab[P] = n_active;
+    if (P > 1) {
+        // active_scan[c] = number of active chunks before chunk c
+        for (uint32_t q = 1; q < P; ++q)
+            CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 32 + q, active_scan + (size_t)xb[q] * plane, 4, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        for (uint32_t q = 1; q < P; ++q) ab[q] = ctx->h_pinned[32 + q];
+    }
+    uint32_t* convert_flag = nullptr;
     if (whole) {
-        uint32_t* convert_flag = tmp.get<uint32_t>(n);
+        convert_flag = tmp.get<uint32_t>(n);
         if (!convert_flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "derive: out of device memory");
-        KLP(ctx, 3, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, 0, obj->nb[0], st));
-        KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr,
-                                          n, 0, obj->nb[0], persistent_grid(ctx, n, 8), st));
     } else {
         // a slab waits for its halo planes: ivx_object_halo_* → ivx_object_slab_classify → ivx_object_slab_finalize
         obj->derive_pending = true;
+    }
+    uint32_t* pk_flag = nullptr;
+    uint32_t* pk_ord = nullptr;
+    uint32_t* part_counts = counters + 44;  // [P] NonUniform chunks per packed plane range
+    std::vector<cudaEvent_t> part_done;
+    std::vector<uint32_t> part_lo(P), part_hi(P);
+    if (so) {
+        if (so->chunk_capacity < n) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u chunk descriptors", n);
+        obj->d_stage_voxels = static_cast<ivx_voxel*>(ctx->alloc(std::max<size_t>(1, (size_t)n_slots) * 12288));
+        obj->d_stage_chunks = static_cast<ivx_chunk_desc*>(ctx->alloc((size_t)n * sizeof(ivx_chunk_desc)));
+        pk_flag = tmp.get<uint32_t>(n);
+        pk_ord = tmp.get<uint32_t>(n);
+        if (!obj->d_stage_voxels || !obj->d_stage_chunks || !pk_flag || !pk_ord)
+            IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "streamed generation: out of device memory");
+        CU(ctx, cudaMemsetAsync(part_counts, 0, 16 * sizeof(uint32_t), st));
+        part_done.resize(P);
+        for (auto& e : part_done) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    for (uint32_t q = 0; q < P; ++q) {
+        const uint32_t cnt = ab[q + 1] - ab[q];
+        if (cnt) {
+            ea.active = active_list + ab[q];
+            ea.n_active = cnt;
+            KLP(ctx, 2, launch_eval(ea, std::min(egrid, cnt), st));
+            ta.active = active_list + ab[q];
+            ta.n_active = cnt;
+            KLP(ctx, 7, launch_types(ta, persistent_grid(ctx, cnt, types_bps), st));
+        }
+        // ---- cross-chunk derived state of the planes whose six neighbours are typed ----
+        const uint32_t lo = q == 0 ? 0u : xb[q] - 1u, hi = q + 1 == P ? obj->nb[0] : xb[q + 1] - 1u;
+        part_lo[q] = lo;
+        part_hi[q] = std::max(lo, hi);
+        if (whole && hi > lo) {
+            KLP(ctx, 3, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, lo, hi, st));
+            KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr,
+                                              n, lo, hi, persistent_grid(ctx, n, 8), st));
+        }
+        if (so) {
+            if (hi > lo) {
+                const uint32_t c0 = lo * plane, nc = (hi - lo) * plane;
+                KL(ctx, launch_nonuniform_flags(obj->d_chunks + c0, nc, pk_flag, st));
+                KL(ctx, launch_exclusive_scan(pk_flag, pk_ord, nc, part_counts + q, st));
+                KL(ctx, launch_pack_voxels(obj->d_chunks + c0, nc, pk_ord, part_counts, q, obj->d_voxels, obj->d_stage_voxels,
+                                           obj->d_stage_chunks + c0, persistent_grid(ctx, nc, 8), st));
+                CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 40 + q, part_counts + q, 4, cudaMemcpyDeviceToHost, st));
+            }
+            CU(ctx, cudaEventRecord(part_done[q], st));
+        }
+    }
+    if (so) {
+        // the host follows the parts as they finish and queues their transfers; the compute stream never waits
+        uint64_t base = 0;
+        int rc = IVX_OK;
+        for (uint32_t q = 0; q < P; ++q) {
+            cudaError_t e = cudaEventSynchronize(part_done[q]);
+            if (e == cudaSuccess && part_hi[q] > part_lo[q] && rc == IVX_OK) {
+                const uint64_t cnt = ctx->h_pinned[40 + q];
+                const size_t c0 = (size_t)part_lo[q] * plane, nc = (size_t)(part_hi[q] - part_lo[q]) * plane;
+                if ((base + cnt) * 4096 > so->voxel_capacity) {
+                    rc = IVX_ERR_CAPACITY;
+                } else {
+                    e = cudaMemcpyAsync(so->h_chunks + c0, obj->d_stage_chunks + c0, nc * sizeof(ivx_chunk_desc),
+                                        cudaMemcpyDeviceToHost, ctx->copy_stream);
+                    if (e == cudaSuccess && cnt)
+                        e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(so->h_voxels) + base * 12288,
+                                            reinterpret_cast<unsigned char*>(obj->d_stage_voxels) + base * 12288, cnt * 12288,
+                                            cudaMemcpyDeviceToHost, ctx->copy_stream);
+                    base += cnt;
+                }
+            }
+            if (e != cudaSuccess && rc == IVX_OK) rc = IVX_ERR_CUDA;
+        }
+        for (auto& e : part_done) cudaEventDestroy(e);
+        if (rc == IVX_ERR_CAPACITY) IVX_FAIL(ctx, rc, "streamed generation: voxel buffer too small");
+        if (rc != IVX_OK) IVX_FAIL(ctx, rc, "streamed generation: %s", cudaGetErrorString(cudaGetLastError()));
+        so->n_non_uniform = base;
     }
 
     if (int rc = read_words(ctx, counters, 16, words)) return rc;
@@ -399,15 +493,21 @@ cudaError_t launch_nonuniform_flags(const DevChunk* chunks, uint32_t n, uint32_t
 }
 
 // planes → the reference's 3-byte AoS voxels, NonUniform chunks in linear chunk
-// order; chunk descriptors with data_offset = that ordinal (object.rs:574-577)
+// order; chunk descriptors with data_offset = that ordinal (object.rs:574-577).
+// `ordinal` counts NonUniform chunks inside this call's chunk range; `part_counts[0..part)` are the counts of
+// the ranges packed before it (streamed generation), so the global ordinal is their sum + ordinal[c].
 __global__ void __launch_bounds__(256) k_pack_voxels(const DevChunk* __restrict__ chunks, uint32_t n,
                                                      const uint32_t* __restrict__ ordinal,
+                                                     const uint32_t* __restrict__ part_counts, uint32_t part,
                                                      const unsigned char* __restrict__ voxels, ivx_voxel* __restrict__ out,
                                                      ivx_chunk_desc* __restrict__ out_chunks) {
-    __shared__ uint8_t s[3 * 4096];
+    __shared__ __align__(16) uint32_t s_out[3 * 1024];  // one chunk of interleaved voxels
     const int tid = threadIdx.x;
+    uint32_t base = 0;
+    for (uint32_t q = 0; q < part; ++q) base += part_counts[q];
     for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
         const DevChunk ch = chunks[c];
+        const uint32_t ord = ch.kind == 2 ? base + ordinal[c] : 0u;
         if (tid == 0) {
             ivx_chunk_desc d;
             d.kind = ch.kind;
@@ -417,28 +517,43 @@ __global__ void __launch_bounds__(256) k_pack_voxels(const DevChunk* __restrict_
             d.uniform_voxel.signed_distance = ch.kind == 1 ? ch.u_sd : 0;
             d.uniform_voxel.flags = ch.kind == 1 ? ch.u_flags : 0;
             d._pad = 0;
-            d.data_offset = ch.kind == 2 ? ordinal[c] : 0;
+            d.data_offset = ord;
             out_chunks[c] = d;
         }
         if (ch.kind != 2 || out == nullptr) continue;
         const unsigned char* slot = voxels + (size_t)ch.slot * SLOT_BYTES;
-        for (int q = 0; q < 3; ++q)
-            *reinterpret_cast<uint4*>(&s[q * 4096 + tid * 16]) = *reinterpret_cast<const uint4*>(slot + q * 4096 + tid * 16);
-        __syncthreads();
-        unsigned char* o = reinterpret_cast<unsigned char*>(out + (size_t)ordinal[c] * 4096);
-        // 12288 output bytes, 48 per thread
-        for (int b = 0; b < 48; ++b) {
-            const int byte = tid * 48 + b;
-            const int v = byte / 3, f = byte % 3;  // f: 0 type, 1 sd, 2 flags
-            o[byte] = s[(f == 0 ? PLANE_TYPE : (f == 1 ? PLANE_SD : PLANE_FLAGS)) + v];
+        // this thread's 16 voxels: one 16-byte row of each plane → 48 interleaved bytes {type, sd, flags}
+        const uint4 wt = *reinterpret_cast<const uint4*>(slot + PLANE_TYPE + tid * 16);
+        const uint4 wd = *reinterpret_cast<const uint4*>(slot + PLANE_SD + tid * 16);
+        const uint4 wf = *reinterpret_cast<const uint4*>(slot + PLANE_FLAGS + tid * 16);
+        const uint32_t pt[4] = {wt.x, wt.y, wt.z, wt.w}, pd[4] = {wd.x, wd.y, wd.z, wd.w}, pf[4] = {wf.x, wf.y, wf.z, wf.w};
+        uint32_t w12[12];
+#pragma unroll
+        for (int w = 0; w < 12; ++w) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = 4 * w + j, v = b / 3, f = b % 3;
+                const uint32_t src = f == 0 ? pt[v >> 2] : (f == 1 ? pd[v >> 2] : pf[v >> 2]);
+                acc |= ((src >> (8 * (v & 3))) & 0xFFu) << (8 * j);
+            }
+            w12[w] = acc;
         }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            *reinterpret_cast<uint4*>(&s_out[tid * 12 + 4 * q]) = make_uint4(w12[4 * q], w12[4 * q + 1], w12[4 * q + 2], w12[4 * q + 3]);
+        __syncthreads();
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(out) + (size_t)ord * 12288);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) o[q * 256 + tid] = *reinterpret_cast<const uint4*>(&s_out[(q * 256 + tid) * 4]);
         __syncthreads();
     }
 }
-cudaError_t launch_pack_voxels(const DevChunk* chunks, uint32_t n, const uint32_t* ordinal, const unsigned char* voxels,
-                               ivx_voxel* out, ivx_chunk_desc* out_chunks, uint32_t grid, cudaStream_t st) {
+cudaError_t launch_pack_voxels(const DevChunk* chunks, uint32_t n, const uint32_t* ordinal, const uint32_t* part_counts,
+                               uint32_t part, const unsigned char* voxels, ivx_voxel* out, ivx_chunk_desc* out_chunks,
+                               uint32_t grid, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_pack_voxels<<<grid, 256, 0, st>>>(chunks, n, ordinal, voxels, out, out_chunks);
+    k_pack_voxels<<<grid, 256, 0, st>>>(chunks, n, ordinal, part_counts, part, voxels, out, out_chunks);
     return cudaGetLastError();
 }
 
@@ -596,6 +711,11 @@ int ivx_create(const ivx_config* config, ivx_ctx** out_ctx) {
         }
         ctx->own_stream = true;
     }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        ctx->copy_stream = nullptr;
+        ivx_destroy(ctx);
+        return IVX_ERR_CUDA;
+    }
     if (cudaMallocHost(&ctx->h_pinned, 64 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess) {
         ivx_destroy(ctx);
@@ -609,6 +729,10 @@ void ivx_destroy(ivx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     for (auto& e : ctx->prof_events) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -626,6 +750,7 @@ uint64_t ivx_kernel_launch_count(const ivx_ctx* ctx) { return ctx ? ctx->launche
 int ivx_synchronize(ivx_ctx* ctx) {
     if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return IVX_OK;
 }
 
@@ -826,6 +951,19 @@ int ivx_object_generate(ivx_ctx* ctx, const ivx_program* program, float voxel_ex
     *out = nullptr;
     cudaSetDevice(ctx->device);
     return generate_impl(ctx, program, voxel_extent, tg, 0, 0, true, out);
+}
+
+int ivx_object_generate_streamed(ivx_ctx* ctx, const ivx_program* program, float voxel_extent, const ivx_type_generator* tg,
+                                 ivx_chunk_desc* host_chunks, size_t chunk_capacity, ivx_voxel* host_voxels,
+                                 size_t voxel_capacity, ivx_object** out, uint64_t* out_non_uniform_chunks) {
+    if (!ctx || !program || !tg || !out || !host_chunks || !host_voxels) return IVX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (out_non_uniform_chunks) *out_non_uniform_chunks = 0;
+    cudaSetDevice(ctx->device);
+    StreamOut so{host_chunks, chunk_capacity, host_voxels, voxel_capacity, 0};
+    const int rc = generate_impl(ctx, program, voxel_extent, tg, 0, 0, true, out, &so);
+    if (rc == IVX_OK && out_non_uniform_chunks) *out_non_uniform_chunks = so.n_non_uniform;
+    return rc;
 }
 
 // Work estimate per chunk plane for a balanced slab partition: the conservative fold levels of generate_impl
@@ -1129,7 +1267,7 @@ int ivx_object_download(ivx_ctx* ctx, const ivx_object* obj, ivx_chunk_desc* chu
         d_vox = tmp.get<ivx_voxel>(std::max<size_t>(1, (size_t)nnu * 4096));
         if (!d_vox) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "download: out of device memory");
     }
-    KL(ctx, launch_pack_voxels(own_chunks, n, ord, obj->d_voxels, d_vox, d_desc, persistent_grid(ctx, n, 8), st));
+    KL(ctx, launch_pack_voxels(own_chunks, n, ord, nullptr, 0, obj->d_voxels, d_vox, d_desc, persistent_grid(ctx, n, 8), st));
     CU(ctx, cudaMemcpyAsync(chunks, d_desc, (size_t)n * sizeof(ivx_chunk_desc), cudaMemcpyDeviceToHost, st));
     if (d_vox && nnu) CU(ctx, cudaMemcpyAsync(voxels, d_vox, (size_t)nnu * 4096 * sizeof(ivx_voxel), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
@@ -1140,7 +1278,10 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     if (!ctx || !obj) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
     free_mesh(ctx, obj->mesh);
+    ctx->release(obj->d_stage_voxels);
+    ctx->release(obj->d_stage_chunks);
     ctx->release(obj->d_chunks);
     ctx->release(obj->d_voxels);
     ctx->release(obj->d_dirty);

@@ -27,6 +27,7 @@ struct ivx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // device→host copies of streamed generation, beside the compute stream
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -129,6 +130,9 @@ struct ivx_object {
     std::vector<uint32_t> h_first_region;
     std::vector<uint32_t> h_region_roots;
     bool split_valid = false;
+    // streamed generation: packed voxels / descriptors staged for the copy stream
+    ivx_voxel* d_stage_voxels = nullptr;
+    ivx_chunk_desc* d_stage_chunks = nullptr;
 };
 
 #define IVX_FAIL(ctx, code, ...)                              \

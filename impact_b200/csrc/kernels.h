@@ -187,8 +187,9 @@ cudaError_t launch_mark_box(uint8_t* arr, const uint32_t nb[3], const uint32_t l
 // ---- api.cu helpers ------------------------------------------------------------
 cudaError_t launch_flag_dirty_exposed(const DevChunk* chunks, const uint8_t* dirty, uint32_t n, uint32_t* exposed_flag,
                                       uint32_t* dirty_flag, cudaStream_t st);
-cudaError_t launch_pack_voxels(const DevChunk* chunks, uint32_t n, const uint32_t* ordinal, const unsigned char* voxels,
-                               ivx_voxel* out, ivx_chunk_desc* out_chunks, uint32_t grid, cudaStream_t st);
+cudaError_t launch_pack_voxels(const DevChunk* chunks, uint32_t n, const uint32_t* ordinal, const uint32_t* part_counts,
+                               uint32_t part, const unsigned char* voxels, ivx_voxel* out, ivx_chunk_desc* out_chunks,
+                               uint32_t grid, cudaStream_t st);
 cudaError_t launch_nonuniform_flags(const DevChunk* chunks, uint32_t n, uint32_t* flag, cudaStream_t st);
 cudaError_t launch_set_reserved_slots(DevChunk* chunks, uint32_t n, const uint32_t* slot_flag, const uint32_t* slot_scan,
                                       uint32_t* slot_of, cudaStream_t st);

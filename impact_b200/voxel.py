@@ -177,6 +177,21 @@ class VoxelObject:
                                                         C.c_uint32(chunk_i_range[1]), C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def generate_streamed(cls, generator: SDFVoxelGenerator, host_chunks: np.ndarray, host_voxels: np.ndarray):
+        """`VoxelObject::generate` straight into host buffers (`ivx_object_generate_streamed`): the download of
+        finished chunk planes overlaps the generation of the following ones. Returns (object, n_non_uniform); the
+        buffers are complete after `ctx.synchronize()`."""
+        ctx = generator.sdf_generator.ctx
+        tg = generator.voxel_type_generator.pod()
+        h = C.c_void_p()
+        nnu = C.c_uint64()
+        ctx.check(ctx._lib.ivx_object_generate_streamed(
+            ctx.h, generator.sdf_generator.h, C.c_float(generator.voxel_extent), L.ptr(tg), L.ptr(host_chunks),
+            C.c_size_t(host_chunks.nbytes // 16), L.ptr(host_voxels), C.c_size_t(host_voxels.nbytes // 3), C.byref(h),
+            C.byref(nnu)))
+        return cls(ctx, h), int(nnu.value)
+
     def free(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx._lib.ivx_object_free(self.ctx.h, self.h)

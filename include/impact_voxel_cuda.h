@@ -249,6 +249,18 @@ int ivx_program_eval_blocks(ivx_ctx* ctx, const ivx_program* program, const floa
  * compute_all_derived_state (split detection excluded). */
 int ivx_object_generate(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
                         const ivx_type_generator* type_generator, ivx_object** out_object);
+/* ivx_object_generate followed by ivx_object_download, overlapped: the chunk planes are generated in parts and each
+ * finished part is packed to the reference's layout (`Voxel` AoS, `data_offset` = ordinal among NonUniform chunks,
+ * object.rs:574-577) and copied to the host buffers on a second stream while the next parts are still being
+ * computed. `host_chunks` needs room for every chunk of the grid, `host_voxels` for 4096 voxels per NonUniform chunk
+ * (IVX_ERR_CAPACITY otherwise); page-locked buffers are needed for the copies to overlap. The call returns when the
+ * object is complete on the device; the host buffers are complete after ivx_synchronize (or ivx_object_free), so a
+ * following ivx_object_mesh runs under the tail of the transfer. */
+int ivx_object_generate_streamed(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
+                                 const ivx_type_generator* types, ivx_chunk_desc* host_chunks, size_t chunk_capacity,
+                                 ivx_voxel* host_voxels, size_t voxel_capacity, ivx_object** out_object,
+                                 uint64_t* out_non_uniform_chunks);
+
 /* Multi-GPU: generate only chunk planes [chunk_i_begin, chunk_i_end) of the
  * x-major chunk grid (the reference's thread split of the linear chunk index,
  * object.rs:423-427). The object also reserves one halo chunk plane on each

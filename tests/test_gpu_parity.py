@@ -203,6 +203,45 @@ def test_capsule_absorption_is_bit_exact(ctx, oracle, name, types):
         obj_gpu.absorb_capsule(mid, f([1, 0, 0]), -1.0, 1.0)
 
 
+@pytest.mark.parametrize("name", ["sphere_big_interior", "asteroid_like", "asteroid_stand_in", "box_types"])
+def test_streamed_generation_fills_host_buffers_like_generate_plus_download(ctx, name):
+    # ivx_object_generate_streamed: planes generated in parts, each part's cross-chunk state, packing and copy
+    # overlapped with the next parts; the result must be the bytes of generate → download, and the object left on
+    # the device must mesh identically
+    import torch
+    from impact_b200 import _lib as L
+    make, types = GRAPHS[name]
+    vg = SDFVoxelGenerator(1.0, ctx.build_generator(make()), types)
+    ref = VoxelObject.generate(vg)
+    rch, rvx = ref.download()
+    n_chunks = len(rch)
+    h_chunks = torch.empty(n_chunks * 16, dtype=torch.uint8, pin_memory=True).numpy()
+    h_vox = torch.empty(max(1, len(rvx)) * 3 + 4096 * 3, dtype=torch.uint8, pin_memory=True).numpy()
+    h_chunks[:] = 0xAB
+    h_vox[:] = 0xCD
+    obj, nnu = VoxelObject.generate_streamed(vg, h_chunks, h_vox)
+    ctx.synchronize()
+    assert nnu * 4096 == len(rvx)
+    assert np.array_equal(h_chunks.view(L.CHUNK_DTYPE), rch)
+    assert np.array_equal(h_vox[: len(rvx) * 3].view(L.VOXEL_DTYPE), rvx)
+    assert (h_vox[len(rvx) * 3:] == 0xCD).all()  # nothing written past the end
+    gch, gvx = obj.download()
+    assert np.array_equal(gch, rch) and np.array_equal(gvx, rvx)
+    ia, ib = obj.info(), ref.info()
+    for k in ib:
+        if k != "device_bytes":
+            assert np.array_equal(ia[k], ib[k]), k
+    ma, mb = VoxelObjectMesh.create(obj).download(), VoxelObjectMesh.create(ref).download()
+    for k in ma:
+        assert np.array_equal(np.asarray(ma[k]).view(np.uint8), np.asarray(mb[k]).view(np.uint8)), k
+    # too small a voxel buffer is reported, not overrun
+    if len(rvx):
+        small = torch.empty(4096 * 3, dtype=torch.uint8, pin_memory=True).numpy()
+        with pytest.raises(Exception):
+            VoxelObject.generate_streamed(vg, h_chunks, small)
+        ctx.synchronize()
+
+
 def test_full_size_sphere_properties(ctx):
     # engine bench shape: Sphere(r = 100) → 202³ (benchmarks/voxel_object.rs:650-660); no oracle here,
     # only size-independent properties: reference invariants + closed manifold + radius
