@@ -239,7 +239,10 @@ def run_gpu(args):
         ev[2].record(stream)
         mesh = VoxelObjectMesh.create(obj)
         ev[3].record(stream)
-        merged = D.gather_mesh(D.device_mesh_tensors(mesh, dev), rank, world, dev)
+        if peer_gather[0] is not None:
+            merged = peer_gather[0].gather(mesh)  # every rank stores its part into rank 0's memory over NVLink
+        else:
+            merged = D.gather_mesh(D.device_mesh_tensors(mesh, dev), rank, world, dev)
         ev[4].record(stream)
         phase_events.append(ev)
         if merged is not None:
@@ -248,6 +251,9 @@ def run_gpu(args):
         return obj, mesh
 
     halo_stats = {}
+    # mesh gather: peer-memory stores (CUDA IPC + NVLink) unless IVX_GATHER=nccl asks for the NCCL send/recv path
+    peer_gather = [D.PeerMeshGather(ctx, rank, world, dev) if world > 1 and os.environ.get("IVX_GATHER", "peer") == "peer"
+                   else None]
     phase_events = []  # multi-GPU: (generate, halo exchange + derive, mesh, gather) per step
 
     with torch.cuda.stream(stream):
@@ -381,6 +387,8 @@ def run_gpu(args):
                 "workload": args.workload, "description": desc, "grid_shape": grid_shape,
                 "chunks": int(np.prod(info[0]["chunk_counts"])), "parallelism": f"x-slab x{world}" + (" (work-balanced plane ranges)" if world > 1 else ""),
                 "slab_planes": [list(r) for r in ranges], "rank0_exchange": halo_stats,
+                "mesh_gather": ("peer-memory stores into rank 0 (ivx_mesh_push over NVLink, CUDA IPC)" if peer_gather[0] is not None
+                                else ("NCCL send/recv" if world > 1 else "none")),
                 "rank0_chunks": {"void": oi["n_void"], "uniform": oi["n_uniform"], "non_uniform": oi["n_non_uniform"]},
                 "rank0_mesh": {"vertices": info[1], "indices": info[2], "submeshes": info[3]},
                 "l2": "256 MiB buffer written between timed iterations (outside the timed intervals); the voxel "
@@ -412,6 +420,8 @@ def run_gpu(args):
             out["cpu_baseline"] = {k: v for k, v in cpu_reference(graph, types, 12.0, os.cpu_count() or 1).items()
                                    if k != "seconds"}
         emit(out)
+    if peer_gather[0] is not None:
+        peer_gather[0].close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

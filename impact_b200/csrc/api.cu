@@ -1329,6 +1329,75 @@ int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* obj, float* positions, flo
 
 static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats);
 
+// ---- mesh gather over peer memory (multi-GPU) ------------------------------------------------------------
+int ivx_peer_alloc(ivx_ctx* ctx, size_t bytes, void** out_ptr, unsigned char out_handle[64]) {
+    if (!ctx || !out_ptr || !out_handle) return IVX_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ivx_peer_alloc hands out 64-byte handles");
+    cudaSetDevice(ctx->device);
+    *out_ptr = nullptr;
+    void* p = nullptr;
+    // a dedicated cudaMalloc (not the context pool): an IPC handle names a whole allocation
+    CU(ctx, cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        cudaGetLastError();
+        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    std::memcpy(out_handle, &h, 64);
+    *out_ptr = p;
+    return IVX_OK;
+}
+int ivx_peer_free(ivx_ctx* ctx, void* ptr) {
+    if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (ptr) CU(ctx, cudaFree(ptr));
+    return IVX_OK;
+}
+int ivx_peer_open(ivx_ctx* ctx, const unsigned char handle[64], void** out_ptr) {
+    if (!ctx || !handle || !out_ptr) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    *out_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    *out_ptr = p;
+    return IVX_OK;
+}
+int ivx_peer_close(ivx_ctx* ctx, void* ptr) {
+    if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (ptr) CU(ctx, cudaIpcCloseMemHandle(ptr));
+    return IVX_OK;
+}
+
+int ivx_mesh_push(ivx_ctx* ctx, const ivx_object* obj, void* dst_base, const uint64_t field_offsets[6], uint32_t vertex_base,
+                  uint32_t index_base, uint32_t submesh_base) {
+    if (!ctx || !obj || !dst_base || !field_offsets) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    const DeviceMesh& m = obj->mesh;
+    unsigned char* d = static_cast<unsigned char*>(dst_base);
+    cudaStream_t st = ctx->stream;
+    const uint32_t grid = (uint32_t)ctx->sm_count * 4u;
+    const size_t nv = m.n_vertices, ni = m.n_indices, ns = m.n_submeshes;
+    static_assert(sizeof(ivx_chunk_submesh) == 52, "13 words per submesh");
+    // positions, normals, indices (+ vertex base), index materials, submeshes (index_offset + index base),
+    // vertex ranges (+ vertex base): the layout of VoxelObjectMesh (mesh.rs:50-103), concatenated in slab order
+    KL(ctx, launch_push_words(m.positions, d + field_offsets[0] + (size_t)vertex_base * 12, nv * 3, 0, 0, 0, grid, st));
+    KL(ctx, launch_push_words(m.normals, d + field_offsets[1] + (size_t)vertex_base * 12, nv * 3, 0, 0, 0, grid, st));
+    KL(ctx, launch_push_words(m.indices, d + field_offsets[2] + (size_t)index_base * 4, ni, vertex_base, 1, 0, grid, st));
+    KL(ctx, launch_push_words(m.index_materials, d + field_offsets[3] + (size_t)index_base * 8, ni * 2, 0, 0, 0, grid, st));
+    KL(ctx, launch_push_words(m.submeshes, d + field_offsets[4] + (size_t)submesh_base * 52, ns * 13, index_base, 13, 3, grid, st));
+    KL(ctx, launch_push_words(m.vertex_ranges, d + field_offsets[5] + (size_t)submesh_base * 8, ns * 2, vertex_base, 1, 0, grid, st));
+    return IVX_OK;
+}
+
 int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3], float radius, float influence_radius,
                              ivx_absorb_stats* out_stats) {
     if (!ctx || !obj || !center) return IVX_ERR_INVALID_ARGUMENT;

@@ -104,4 +104,38 @@ cudaError_t launch_halo_kinds_unpack(DevChunk* chunks, uint32_t plane_first, uin
     return cudaGetLastError();
 }
 
+
+// ---- mesh gather over peer memory ----------------------------------------------------------------------
+// One slab's mesh arrays are written straight into the merged mesh that lives in ANOTHER GPU's memory (mapped through
+// CUDA IPC, reached over NVLink / NVSwitch), already rebased: word i of `src` lands at dst[i], plus `add` when
+// i % period == col (period 1: every word — the u32 vertex indices; period 13, col 3: ChunkSubmesh::index_offset;
+// period 0: plain copy). 16-byte accesses on both sides; `n_words` need not be a multiple of 4.
+__global__ void __launch_bounds__(256) k_push_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n_words,
+                                                     uint32_t add, uint32_t period, uint32_t col) {
+    const size_t n4 = n_words / 4;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto fix = [&](uint32_t w, size_t i) { return (period == 1u || (period > 1u && i % period == col)) ? w + add : w; };
+    if (aligned) {
+        for (size_t q = t; q < n4; q += stride) {
+            uint4 v = reinterpret_cast<const uint4*>(src)[q];
+            v.x = fix(v.x, 4 * q);
+            v.y = fix(v.y, 4 * q + 1);
+            v.z = fix(v.z, 4 * q + 2);
+            v.w = fix(v.w, 4 * q + 3);
+            reinterpret_cast<uint4*>(dst)[q] = v;
+        }
+        for (size_t i = 4 * n4 + t; i < n_words; i += stride) dst[i] = fix(src[i], i);
+    } else {
+        for (size_t i = t; i < n_words; i += stride) dst[i] = fix(src[i], i);
+    }
+}
+cudaError_t launch_push_words(const void* src, void* dst, size_t n_words, uint32_t add, uint32_t period, uint32_t col,
+                              uint32_t grid, cudaStream_t st) {
+    if (n_words == 0) return cudaSuccess;
+    k_push_words<<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), n_words, add, period, col);
+    return cudaGetLastError();
+}
+
 }  // namespace ivx

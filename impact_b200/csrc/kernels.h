@@ -111,6 +111,8 @@ cudaError_t launch_halo_kinds_pack(const DevChunk* chunks, const uint32_t* conve
                                    uint32_t plane_chunks, uint8_t* dst, cudaStream_t st);
 cudaError_t launch_halo_kinds_unpack(DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, const uint8_t* src,
                                      cudaStream_t st);
+cudaError_t launch_push_words(const void* src, void* dst, size_t n_words, uint32_t add, uint32_t period, uint32_t col,
+                              uint32_t grid, cudaStream_t st);
 
 // ---- mesh.cu -----------------------------------------------------------------
 struct MeshArgs {

@@ -211,6 +211,101 @@ def gather_mesh(parts: dict, rank: int, world: int, device, dst: int = 0, group=
     return merged
 
 
+# ---- mesh gather over peer memory (NVLink / NVSwitch stores instead of NCCL messages) -------------------------
+_FIELD_BYTES = (("positions", 12, "v"), ("normals", 12, "v"), ("indices", 4, "i"), ("index_materials", 8, "i"),
+                ("submeshes", 52, "s"), ("vertex_ranges", 8, "s"))
+
+
+class PeerMeshGather:
+    """The merged mesh lives in one block of the gathering GPU's memory, exported once through CUDA IPC
+    (`ivx_peer_alloc` / `ivx_peer_open`); every step each rank writes its slab's mesh straight into it with
+    `ivx_mesh_push` — indices, submesh index offsets and vertex ranges rebased on the fly — so the only collective
+    left is the all-gather of three counts per rank. The block grows (all ranks agree from the gathered counts)
+    when a step needs more room."""
+
+    def __init__(self, ctx, rank: int, world: int, device, dst: int = 0, group=None):
+        self.ctx, self.rank, self.world, self.device, self.dst, self.group = ctx, rank, world, device, dst, group
+        self.caps = np.zeros(3, np.int64)  # vertices, indices, submeshes
+        self.base = None                   # pointer valid on this rank's device
+        self.offsets = None
+
+    def _layout(self, caps):
+        key = {"v": int(caps[0]), "i": int(caps[1]), "s": int(caps[2])}
+        offs, o = [], 0
+        for _, nbytes, k in _FIELD_BYTES:
+            offs.append(o)
+            o += (key[k] * nbytes + 255) // 256 * 256
+        return offs, max(o, 256)
+
+    def _release(self):
+        if self.base is not None:
+            import ctypes as C
+            lib = self.ctx._lib
+            (lib.ivx_peer_free if self.rank == self.dst else lib.ivx_peer_close)(self.ctx.h, C.c_void_p(self.base))
+            self.base = None
+
+    def _ensure(self, totals):
+        import ctypes as C
+        if self.base is not None and np.all(totals <= self.caps):
+            return
+        self.ctx.synchronize()
+        dist.barrier(group=self.group)  # nobody is still writing into the old block
+        self._release()
+        self.caps = np.maximum((totals * 1.25).astype(np.int64) + 1024, self.caps)
+        self.offsets, nbytes = self._layout(self.caps)
+        handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
+        lib = self.ctx._lib
+        if self.rank == self.dst:
+            ptr = C.c_void_p()
+            hbuf = (C.c_ubyte * 64)()
+            self.ctx.check(lib.ivx_peer_alloc(self.ctx.h, C.c_size_t(nbytes), C.byref(ptr), hbuf))
+            self.base = ptr.value
+            handle.copy_(torch.tensor(list(hbuf), dtype=torch.uint8))
+        dist.broadcast(handle, self.dst, group=self.group)
+        if self.rank != self.dst:
+            hb = (C.c_ubyte * 64)(*handle.cpu().tolist())
+            ptr = C.c_void_p()
+            self.ctx.check(lib.ivx_peer_open(self.ctx.h, hb, C.byref(ptr)))
+            self.base = ptr.value
+
+    def gather(self, mesh):
+        """`mesh`: this rank's `VoxelObjectMesh`. → the merged dict of device tensors on `dst` (views into the
+        block, valid until the next call), None elsewhere."""
+        import ctypes as C
+        counts = torch.tensor([mesh.n_vertices, mesh.n_indices, mesh.n_submeshes], dtype=torch.int64, device=self.device)
+        all_counts = torch.zeros(self.world * 3, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(all_counts, counts, group=self.group)
+        table = all_counts.cpu().numpy().reshape(self.world, 3)
+        totals = table.sum(axis=0)
+        starts = np.concatenate([np.zeros((1, 3), np.int64), np.cumsum(table, axis=0)[:-1]])
+        self._ensure(totals)
+        v0, i0, s0 = (int(x) for x in starts[self.rank])
+        offs = (C.c_uint64 * 6)(*self.offsets)
+        self.ctx.check(self.ctx._lib.ivx_mesh_push(self.ctx.h, mesh.obj.h, C.c_void_p(self.base), offs, C.c_uint32(v0),
+                                                   C.c_uint32(i0), C.c_uint32(s0)))
+        dist.barrier(group=self.group)  # stream-ordered after the pushes: every part has landed
+        if self.rank != self.dst:
+            return None
+        nv, ni, ns = (int(x) for x in totals)
+        o = self.offsets
+
+        def view(off, shape, typestr, dtype):
+            if int(np.prod(shape)) == 0:
+                return torch.empty(shape, dtype=dtype, device=self.device)
+            return torch.as_tensor(_DeviceArray(self.base + off, shape, typestr), device=self.device)
+
+        return {
+            "positions": view(o[0], (nv, 3), "<f4", torch.float32), "normals": view(o[1], (nv, 3), "<f4", torch.float32),
+            "indices": view(o[2], (ni,), "<i4", torch.int32), "index_materials": view(o[3], (ni, 8), "|u1", torch.uint8),
+            "submeshes": view(o[4], (ns, 13), "<i4", torch.int32), "vertex_ranges": view(o[5], (ns, 2), "<i4", torch.int32),
+        }
+
+    def close(self):
+        self.ctx.synchronize()
+        dist.barrier(group=self.group)
+        self._release()
+
+
 def _rebase(merged: dict, table: np.ndarray, starts: np.ndarray) -> None:
     """Part r's indices / submesh index offsets / vertex ranges become offsets into the merged buffers."""
     for r in range(len(table)):

@@ -319,6 +319,25 @@ int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* object, float* positions, 
                       ivx_index_materials* index_materials, uint32_t* indices,
                       ivx_chunk_submesh* submeshes, uint32_t* vertex_ranges);
 
+/* ---- multi-GPU mesh gather over peer memory ------------------------------
+ * VoxelObjectMesh::recreate appends the chunk meshes in linear chunk order (mesh.rs:286-354); with x-slabs on several
+ * GPUs that is the concatenation of the slabs' meshes with vertex / index offsets rebased. Instead of sending the six
+ * arrays through NCCL, every rank writes its part directly into the merged mesh in the gathering GPU's memory
+ * (NVLink / NVSwitch peer stores), rebasing on the fly:
+ *   gathering rank: ivx_peer_alloc → 64-byte IPC handle, sent to the other ranks once (any transport)
+ *   other ranks:    ivx_peer_open(handle) → pointer valid on their device
+ *   every step:     ivx_object_mesh, exchange the three counts, then
+ *                   ivx_mesh_push(base, field_offsets, vertex_base, index_base, submesh_base)   [asynchronous]
+ *                   and a barrier on the same stream before the gathering rank reads the result.
+ * field_offsets[6]: byte offsets of positions, normals, indices, index_materials, submeshes, vertex_ranges inside
+ * the merged block (16-byte aligned). Fails with IVX_ERR_UNSUPPORTED where CUDA IPC is not available. */
+int ivx_peer_alloc(ivx_ctx* ctx, size_t bytes, void** out_device_ptr, unsigned char out_handle[64]);
+int ivx_peer_free(ivx_ctx* ctx, void* device_ptr);
+int ivx_peer_open(ivx_ctx* ctx, const unsigned char handle[64], void** out_device_ptr);
+int ivx_peer_close(ivx_ctx* ctx, void* device_ptr);
+int ivx_mesh_push(ivx_ctx* ctx, const ivx_object* object, void* merged_base, const uint64_t field_offsets[6],
+                  uint32_t vertex_base, uint32_t index_base, uint32_t submesh_base);
+
 /* ---- modification -------------------------------------------------------
  * ivx_object_absorb_sphere replaces apply_sphere_absorption
  * (interaction/absorption.rs:801-844) → modify_voxels_within_sphere

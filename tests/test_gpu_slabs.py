@@ -136,13 +136,19 @@ def _nccl_worker(rank, world, port, name, q):
             stats = D.exchange_halos_and_finalize(obj, ranges, rank, dev)
             mesh = VoxelObjectMesh.create(obj)
             merged = D.gather_mesh(D.device_mesh_tensors(mesh, dev), rank, world, dev)
+            # the same gather through peer memory (ivx_mesh_push over NVLink), twice: the second call reuses the block
+            pg = D.PeerMeshGather(c, rank, world, dev)
+            pushed = pg.gather(mesh)
+            pushed = pg.gather(mesh)
             if rank == 0:
                 assert stats["halo_bytes_received"] > 0
                 wm = VoxelObjectMesh.create(whole).download()
                 H.assert_meshes_equal(D.merged_mesh_to_numpy(merged), _MeshLike(wm))
+                H.assert_meshes_equal(D.merged_mesh_to_numpy(pushed), _MeshLike(wm))
                 wc, wv = whole.download()
                 oc, ov = obj.download()
                 H.assert_objects_equal(oc, ov, wc[: len(oc)], wv)
+            pg.close()
             stream.synchronize()
         dist.barrier()
         dist.destroy_process_group()
