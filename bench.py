@@ -232,7 +232,7 @@ def run_gpu(args):
         # x-slab per rank → halo planes over NCCL → derived state → mesh → mesh gathered on rank 0
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record(stream)
-        step_ranges = partition()  # part of the job: every step re-derives the balanced partition
+        step_ranges = partition()  # the work estimate belongs to the compiled program and is cached with it
         obj = VoxelObject.generate(vg, step_ranges[rank])
         ev[1].record(stream)
         halo_stats.update(D.exchange_halos_and_finalize(obj, step_ranges, rank, dev))

@@ -141,6 +141,9 @@ class SDFVoxelGenerator:
 
 def plane_work(generator: SDFVoxelGenerator) -> np.ndarray:
     """Estimated generation work per chunk plane (ivx_program_plane_work) for `distributed.slab_ranges_weighted`."""
+    cached = getattr(generator, "_plane_work", None)
+    if cached is not None:  # a property of the compiled program, the extent and the type generator, all immutable
+        return cached
     ctx = generator.sdf_generator.ctx
     tg = generator.voxel_type_generator.pod()
     n = C.c_uint32()
@@ -149,7 +152,8 @@ def plane_work(generator: SDFVoxelGenerator) -> np.ndarray:
     out = np.zeros(max(1, n.value), np.uint32)
     ctx.check(ctx._lib.ivx_program_plane_work(ctx.h, generator.sdf_generator.h, C.c_float(generator.voxel_extent), L.ptr(tg),
                                               L.ptr(out), C.c_uint32(len(out)), C.byref(n)))
-    return out[: n.value]
+    generator._plane_work = out[: n.value]
+    return generator._plane_work
 
 
 class VoxelObject:
