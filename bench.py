@@ -411,8 +411,8 @@ def run_gpu(args):
                          "algorithmic_bytes_per_voxel": per_voxel, "voxels_per_launch": my_voxels,
                          "avg_launch_ms": dom_avg_s * 1e3,
                          "note": "dense definition (SURVEY 8d): bytes the reference's layout moves per grid voxel; "
-                                 "the kernel is instruction-issue bound on simplex noise (ncu: issue slots 82-86 % busy, DRAM 1 %), "
-                                 "see DESIGN.md §4 and profiles/"},
+                                 "the kernel is bound by the FP32 pipe / instruction issue on simplex noise (ncu: FMA pipe 65 %, issue slots "
+                                 "64 % busy, DRAM 1 %), see DESIGN.md §4 and profiles/"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
             "whole_path_roofline_frac": (5.0 * total_voxels / step_s / 1e9) / peak,
         }

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(256) k_boundary_apply(DevChunk* __restrict__ c
                 if (nslot[PLANE_FLAGS + vidx(a3[0], a3[1], a3[2])] & 1) adj_empty |= 1u << f;
             }
         }
+        __syncthreads();  // every IS_EMPTY read above precedes the first byte update below
 #pragma unroll
         for (int f = 0; f < 6; ++f) {
             if (!((mask >> f) & 1)) continue;
