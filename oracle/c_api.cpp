@@ -370,6 +370,22 @@ void orc_split_copy(void* sp, uint8_t* voxel_labels, void* per_chunk, uint32_t* 
     if (region_roots) std::memcpy(region_roots, sd->region_root.data(), sd->region_root.size() * 4);
 }
 void orc_split_free(void* sp) { delete (SplitDetection*)sp; }
+
+// ---- region extraction ----
+// info (u32 x 8): found_two, extracted, discarded, single_chunk, region_label, origin_offset_in_parent[3].
+// Returns the extracted object (caller frees with orc_object_free) or null.
+void* orc_extract_any_disconnected_region(void* op, uint32_t* info) {
+    Extraction ex;
+    extract_any_disconnected_region(*(Object*)op, ex);
+    info[0] = ex.found_two;
+    info[1] = ex.extracted;
+    info[2] = ex.discarded;
+    info[3] = ex.single_chunk;
+    info[4] = ex.region_label;
+    for (int d = 0; d < 3; ++d) info[5 + d] = ex.origin_offset_in_parent[d];
+    if (!ex.extracted) return nullptr;
+    return new Object(std::move(ex.object));
+}
 uint32_t orc_count_regions_brute_force(void* op) { return count_regions_brute_force(*(Object*)op); }
 
 float orc_simplex3(float x, float y, float z, int32_t seed) { return simplex3(x, y, z, seed); }

@@ -316,6 +316,21 @@ struct SplitDetection {
     uint32_t smallest = 0;                // which of `two` extract_smallest_region would extract
     bool overflow = false;                // more regions / connections than the reference's fixed capacities
 };
+// --- region extraction (object/extraction.rs) ---
+struct Extraction {
+    bool found_two = false;     // find_two_disconnected_regions found something to extract
+    bool extracted = false;     // ExtractionResult::Extracted
+    bool discarded = false;     // fewer than NON_EMPTY_VOXEL_THRESHOLD non-empty voxels: removed from the parent, dropped
+    bool single_chunk = false;  // re-packed into one chunk (create_extracted_voxel_object_in_single_chunk_if_possible)
+    uint32_t region_label = 0;
+    uint32_t origin_offset_in_parent[3] = {0, 0, 0};  // voxels
+    Object object;
+};
+// extract_any_disconnected_region: both objects end with their derived state up to date (connected regions are
+// resolved again on demand by resolve_connected_regions).
+void extract_any_disconnected_region(Object& obj, Extraction& out);
+void update_all_chunk_boundary_adjacencies(Object& obj);
+
 bool local_regions_for_chunk(const Voxel* voxels, bool only_empty, uint8_t* labels, uint16_t* boundary_region_count,
                              uint16_t* region_count);
 void resolve_connected_regions(const Object& obj, SplitDetection& sd);

@@ -259,6 +259,17 @@ class Object:
         return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
                 "removed_chunks": int(st[3])}
 
+    def extract_any_disconnected_region(self):
+        """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113): → (info, extracted Object or None).
+        This object is modified in place (the region's voxels leave it)."""
+        info = np.zeros(8, np.uint32)
+        lib().orc_extract_any_disconnected_region.restype = C.c_void_p
+        h = lib().orc_extract_any_disconnected_region(self.h, _p(info))
+        d = {"found_two": bool(info[0]), "extracted": bool(info[1]), "discarded": bool(info[2]),
+             "single_chunk": bool(info[3]), "region_label": int(info[4]),
+             "origin_offset_in_parent": tuple(int(x) for x in info[5:8])}
+        return d, (Object(h) if h else None)
+
     REGIONS_DTYPE = np.dtype([("region_count", "<u2"), ("boundary_region_count", "<u2"), ("first_region", "<u4")])
 
     def split_detection(self) -> dict:

@@ -601,7 +601,7 @@ void update_upper_boundary_adjacencies_in_ranges(Object& obj, const uint32_t r[3
             }
 }
 
-static void update_all_chunk_boundary_adjacencies(Object& obj) {
+void update_all_chunk_boundary_adjacencies(Object& obj) {
     uint32_t r[3][2] = {{0, obj.chunk_counts[0]}, {0, obj.chunk_counts[1]}, {0, obj.chunk_counts[2]}};
     update_upper_boundary_adjacencies_in_ranges(obj, r);
     for (uint32_t j = 0; j < obj.chunk_counts[1]; ++j)
