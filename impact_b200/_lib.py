@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_slab_finalize", "ivx_object_info_get",
     "ivx_object_download", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_peer_alloc", "ivx_peer_free", "ivx_peer_open", "ivx_peer_close", "ivx_mesh_push", "ivx_object_absorb_sphere", "ivx_object_absorb_capsule",
     "ivx_object_dirty_chunks", "ivx_object_remesh_dirty",
-    "ivx_object_resolve_connected_regions", "ivx_object_split_detection_download",
+    "ivx_object_resolve_connected_regions", "ivx_object_split_detection_download", "ivx_object_extract_disconnected_region",
 ]
 
 
@@ -54,6 +54,13 @@ class MeshInfo(C.Structure):
                 ("n_exposed_chunks", C.c_uint32), ("d_positions", C.c_void_p), ("d_normals", C.c_void_p),
                 ("d_index_materials", C.c_void_p), ("d_indices", C.c_void_p), ("d_submeshes", C.c_void_p),
                 ("d_vertex_ranges", C.c_void_p)]
+
+
+class ExtractionInfo(C.Structure):
+    _fields_ = [("n_regions_before", C.c_uint32), ("found_two", C.c_uint32), ("extracted", C.c_uint32),
+                ("discarded", C.c_uint32), ("single_chunk", C.c_uint32), ("region_label", C.c_uint32),
+                ("region_chunks", C.c_uint32), ("moved_non_empty_voxels", C.c_uint32),
+                ("origin_offset_in_parent", C.c_uint32 * 3)]
 
 
 class AbsorbStats(C.Structure):

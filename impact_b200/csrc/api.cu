@@ -1546,7 +1546,241 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     return IVX_OK;
 }
 
+// ---- disconnected-region extraction (object/extraction.rs) -------------------------------------------------
+namespace {
+
+// update_all_chunk_boundary_adjacencies (`range` null) or update_upper_boundary_adjacencies_for_chunks_in_ranges over
+// the chunk range [c0, c1) of `range` (object.rs:1659-1785): conversions get slots, then adjacency bits / obscuredness
+int refresh_boundaries(ivx_ctx* ctx, ivx_object* obj, const AbsorbRange* range) {
+    const uint32_t n = obj->n_chunks;
+    if (n == 0) return IVX_OK;
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t* counters = ctx->d_scratch + 32;
+    uint8_t* face_mask = range ? tmp.get<uint8_t>(n) : nullptr;
+    uint32_t* convert_flag = tmp.get<uint32_t>(n);
+    uint32_t* need = tmp.get<uint32_t>(n);
+    uint32_t* ord = tmp.get<uint32_t>(n);
+    uint32_t* slot_of = tmp.get<uint32_t>(n);
+    if ((range && !face_mask) || !convert_flag || !need || !ord || !slot_of)
+        IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "boundary refresh: out of device memory");
+    if (range) KL(ctx, launch_absorb_face_mask(obj->nb, *range, face_mask, n, st));
+    KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, face_mask, convert_flag, 0, obj->nb[0], st));
+    KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need, st));
+    KL(ctx, launch_exclusive_scan(need, ord, n, counters + 5, st));
+    uint32_t w;
+    if (int rc = read_words(ctx, counters + 5, 1, &w)) return rc;
+    if (int rc = ensure_slots(ctx, obj, w)) return rc;
+    KL(ctx, launch_assign_slots(obj->d_chunks, need, ord, obj->slots_used, n, slot_of, st));
+    obj->slots_used += w;
+    KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n, 0,
+                                  obj->nb[0], persistent_grid(ctx, n, 8), st));
+    if (obj->d_label_stale) {
+        // a neighbour converted to non-uniform has no labels yet
+        uint32_t lo3[3] = {0, 0, 0}, hi3[3] = {obj->nb[0], obj->nb[1], obj->nb[2]};
+        if (range)
+            for (int d = 0; d < 3; ++d) {
+                lo3[d] = range->c0[d];
+                hi3[d] = std::min(obj->nb[d], range->c1[d] + 1);
+            }
+        KL(ctx, launch_mark_box(obj->d_label_stale, obj->nb, lo3, hi3, 1, st));
+    }
+    return IVX_OK;
+}
+
+// update_occupied_ranges (object.rs:1149-1280)
+int refresh_occupied_ranges(ivx_ctx* ctx, ivx_object* obj) {
+    const uint32_t n = obj->n_chunks;
+    uint32_t* occ = ctx->d_scratch + 38;
+    const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
+    CU(ctx, cudaMemcpyAsync(occ, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, occ, persistent_grid(ctx, n, 8),
+                                   ctx->stream));
+    uint32_t o[6];
+    if (int rc = read_words(ctx, occ, 6, o)) return rc;
+    const bool any = o[0] != 0xFFFFFFFFu;
+    for (int d = 0; d < 3; ++d) {
+        obj->occ_voxels[d] = any ? o[d] : 0u;
+        obj->occ_voxels[3 + d] = any ? o[3 + d] + 1u : 0u;
+    }
+    return IVX_OK;
+}
+
+// a fresh whole object of `nb` chunks with room for `slots` stored chunks
+int new_plain_object(ivx_ctx* ctx, float voxel_extent, const uint32_t nb[3], uint32_t slots, ivx_object** out) {
+    ivx_object* o = new (std::nothrow) ivx_object();
+    if (!o) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "host allocation failed");
+    o->voxel_extent = voxel_extent;
+    for (int d = 0; d < 3; ++d) {
+        o->grid_shape[d] = nb[d] * 16u;
+        o->chunk_counts[d] = o->nb[d] = nb[d];
+    }
+    o->first_i = 0;
+    o->own_begin = 0;
+    o->own_end = nb[0];
+    o->n_chunks = nb[0] * nb[1] * nb[2];
+    o->slot_capacity = std::max(1u, slots);
+    o->slots_used = 0;
+    o->d_chunks = static_cast<DevChunk*>(ctx->alloc((size_t)o->n_chunks * sizeof(DevChunk)));
+    o->d_dirty = static_cast<uint8_t*>(ctx->alloc(o->n_chunks));
+    o->d_voxels = static_cast<unsigned char*>(ctx->alloc((size_t)o->slot_capacity * SLOT_BYTES));
+    if (!o->d_chunks || !o->d_dirty || !o->d_voxels) {
+        ivx_object_free(ctx, o);
+        IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "extracted object: out of device memory");
+    }
+    cudaMemsetAsync(o->d_dirty, 0, o->n_chunks, ctx->stream);
+    *out = o;
+    return IVX_OK;
+}
+
+}  // namespace
+
 extern "C" {
+
+int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* obj, ivx_extraction_info* info, ivx_object** out_extracted) {
+    if (!ctx || !obj || !info || !out_extracted) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    std::memset(info, 0, sizeof(*info));
+    *out_extracted = nullptr;
+    // find_two_disconnected_regions on freshly resolved regions (labels of unmodified chunks are reused)
+    ivx_split_info si;
+    if (int rc = ivx_object_resolve_connected_regions(ctx, obj, &si)) return rc;
+    info->n_regions_before = si.n_regions;
+    if (!si.has_two) return IVX_OK;
+    info->found_two = 1;
+    const ivx_region_candidate& cand = si.candidates[si.smallest];
+    const uint32_t R = cand.label;
+    info->region_label = R;
+    uint32_t r0[3], nbE[3];
+    for (int d = 0; d < 3; ++d) {
+        r0[d] = cand.chunk_min[d];
+        nbE[d] = cand.chunk_max[d] + 1 - r0[d];
+        info->origin_offset_in_parent[d] = r0[d] * 16u;
+    }
+    const uint32_t nE = nbE[0] * nbE[1] * nbE[2];
+    const std::vector<uint32_t>&creg = obj->h_chunk_regions, &first = obj->h_first_region, &roots = obj->h_region_roots;
+
+    // ---- the region's chunks inside its bounding box, in linear order (extraction.rs:137-245, 339-349) ----
+    std::vector<uint8_t> mode(nE, 0), is_r(roots.size());
+    std::vector<uint32_t> src_index(nE, 0xFFFFFFFFu), first_region(nE, 0), dst_slot(nE, 0xFFFFFFFFu);
+    for (size_t q = 0; q < roots.size(); ++q) is_r[q] = roots[q] == R ? 1 : 0;
+    uint32_t n_uniform = 0, n_non_uniform = 0, e = 0;
+    for (uint32_t i = 0; i < nbE[0]; ++i)
+        for (uint32_t j = 0; j < nbE[1]; ++j)
+            for (uint32_t k = 0; k < nbE[2]; ++k, ++e) {
+                const uint32_t c = ((r0[0] + i) * obj->nb[1] + (r0[1] + j)) * obj->nb[2] + (r0[2] + k);
+                const uint32_t rc = creg[c] & 255u, kind = creg[c] >> 16;
+                bool in_region = false, mixed = false;
+                for (uint32_t r = 0; r < rc; ++r) {
+                    if (is_r[first[c] + r]) in_region = true; else mixed = true;
+                }
+                if (!in_region || kind == 0u) continue;
+                src_index[e] = c;
+                first_region[e] = first[c];
+                if (kind == 1u) {
+                    mode[e] = 1;
+                    n_uniform++;
+                } else {
+                    mode[e] = mixed ? 3 : 2;
+                    dst_slot[e] = n_non_uniform++;
+                }
+            }
+    info->region_chunks = n_uniform + n_non_uniform;
+
+    ivx_object* ext = nullptr;
+    // uniform chunks may be converted by the cross-chunk pass of the extracted object: room for them too
+    if (int rc = new_plain_object(ctx, obj->voxel_extent, nbE, n_non_uniform + n_uniform, &ext)) return rc;
+    struct Guard {
+        ivx_ctx* c;
+        ivx_object* o;
+        ~Guard() {
+            if (o) ivx_object_free(c, o);
+        }
+    } guard{ctx, ext};
+    ext->slots_used = n_non_uniform;
+
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint8_t* d_mode = tmp.get<uint8_t>(nE);
+    uint32_t* d_src = tmp.get<uint32_t>(nE);
+    uint32_t* d_first = tmp.get<uint32_t>(nE);
+    uint32_t* d_slot = tmp.get<uint32_t>(nE);
+    uint8_t* d_is_r = tmp.get<uint8_t>(std::max<size_t>(1, is_r.size()));
+    uint32_t* d_count = ctx->d_scratch + 44;
+    if (!d_mode || !d_src || !d_first || !d_slot || !d_is_r) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "extraction: out of device memory");
+    CU(ctx, cudaMemcpyAsync(d_mode, mode.data(), nE, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_src, src_index.data(), (size_t)nE * 4, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_first, first_region.data(), (size_t)nE * 4, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_slot, dst_slot.data(), (size_t)nE * 4, cudaMemcpyHostToDevice, st));
+    if (!is_r.empty()) CU(ctx, cudaMemcpyAsync(d_is_r, is_r.data(), is_r.size(), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemsetAsync(d_count, 0, 4, st));
+    ExtractArgs xa{};
+    xa.src_chunks = obj->d_chunks;
+    xa.src_voxels = obj->d_voxels;
+    xa.src_labels = obj->d_labels;
+    xa.src_dirty = obj->d_dirty;
+    xa.src_label_stale = obj->d_label_stale;
+    xa.n_ext = nE;
+    xa.mode = d_mode;
+    xa.src_index = d_src;
+    xa.first_region = d_first;
+    xa.dst_slot = d_slot;
+    xa.region_is_r = d_is_r;
+    xa.dst_chunks = ext->d_chunks;
+    xa.dst_voxels = ext->d_voxels;
+    xa.non_empty_count = d_count;
+    KL(ctx, launch_extract_chunks(xa, persistent_grid(ctx, nE, 4), st));
+    CU(ctx, cudaStreamSynchronize(st));  // the host staging vectors go out of scope below
+    obj->split_valid = false;
+
+    // ---- the object the region left (extraction.rs:556-575) ----
+    if (int rc = refresh_occupied_ranges(ctx, obj)) return rc;
+    AbsorbRange b{};
+    for (int d = 0; d < 3; ++d) {
+        b.c0[d] = r0[d] > 0 ? r0[d] - 1 : 0;
+        b.c1[d] = r0[d] + nbE[d];
+    }
+    if (int rc = refresh_boundaries(ctx, obj, &b)) return rc;
+
+    // ---- complete_extracted_voxel_object (extraction.rs:1902-1973) ----
+    uint32_t moved;
+    if (int rc = read_words(ctx, d_count, 1, &moved)) return rc;
+    info->moved_non_empty_voxels = moved;
+    if (n_uniform == 0 && moved < 8u) {  // NON_EMPTY_VOXEL_THRESHOLD (object.rs:203): dropped
+        info->discarded = 1;
+        return IVX_OK;  // guard frees the extracted object
+    }
+    if (nbE[0] <= 2 && nbE[1] <= 2 && nbE[2] <= 2 && n_uniform == 0 && nE > 1) {
+        if (int rc = refresh_occupied_ranges(ctx, ext)) return rc;  // determine_occupied_voxel_ranges
+        const uint32_t* ov = ext->occ_voxels;
+        if (ov[3] - ov[0] <= 14u && ov[4] - ov[1] <= 14u && ov[5] - ov[2] <= 14u) {
+            uint32_t org[3], one3[3] = {1, 1, 1};
+            for (int d = 0; d < 3; ++d) org[d] = ov[d] > 0 ? ov[d] - 1 : 0;  // room for one empty boundary layer
+            ivx_object* one = nullptr;
+            if (int rc = new_plain_object(ctx, obj->voxel_extent, one3, 1, &one)) return rc;
+            one->slots_used = 1;
+            cudaError_t le = launch_repack_single(ext->d_chunks, ext->nb, ext->d_voxels, org, ov, ov + 3, one->d_chunks, one->d_voxels, st);
+            ctx->launches++;
+            if (le != cudaSuccess) {
+                ivx_object_free(ctx, one);
+                IVX_FAIL(ctx, IVX_ERR_CUDA, "repack: %s", cudaGetErrorString(le));
+            }
+            for (int d = 0; d < 3; ++d) info->origin_offset_in_parent[d] += org[d];
+            ivx_object_free(ctx, ext);
+            ext = one;
+            guard.o = one;
+            info->single_chunk = 1;
+        }
+    }
+    // derived state of the extracted object from scratch (extraction.rs:585-597)
+    if (int rc = refresh_boundaries(ctx, ext, nullptr)) return rc;
+    if (int rc = refresh_occupied_ranges(ctx, ext)) return rc;
+    CU(ctx, cudaStreamSynchronize(st));
+    info->extracted = 1;
+    guard.o = nullptr;
+    *out_extracted = ext;
+    return IVX_OK;
+}
 
 int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* obj, uint32_t* out, uint32_t capacity, uint32_t* out_count) {
     if (!ctx || !obj || !out_count) return IVX_ERR_INVALID_ARGUMENT;

@@ -101,6 +101,30 @@ cudaError_t launch_boundary_apply(DevChunk* chunks, uint32_t n, const uint32_t n
                                   const uint32_t* work_list, uint32_t n_work, uint32_t own_lo, uint32_t own_hi,
                                   uint32_t grid, cudaStream_t st);
 
+// ---- extract.cu --------------------------------------------------------------
+struct ExtractArgs {
+    // the object the region leaves
+    DevChunk* src_chunks;
+    unsigned char* src_voxels;
+    const uint8_t* src_labels;   // LocalRegionLabel per voxel, per slot (split.cu)
+    uint8_t* src_dirty;
+    uint8_t* src_label_stale;    // may be null
+    // per chunk of the extracted object's chunk grid
+    uint32_t n_ext;
+    const uint8_t* mode;         // 0 padding, 1 Uniform, 2 NonUniform moved whole, 3 NonUniform shared with other regions
+    const uint32_t* src_index;   // linear chunk index in the source object
+    const uint32_t* first_region;  // index of the source chunk's region 0 in region_is_r
+    const uint32_t* dst_slot;    // slot of NonUniform chunks in the extracted object
+    const uint8_t* region_is_r;  // per local region of the source: 1 = part of the extracted global region
+    DevChunk* dst_chunks;
+    unsigned char* dst_voxels;
+    uint32_t* non_empty_count;   // non-empty voxels that moved
+};
+cudaError_t launch_extract_chunks(const ExtractArgs& a, uint32_t grid, cudaStream_t st);
+cudaError_t launch_repack_single(const DevChunk* chunks, const uint32_t nb[3], const unsigned char* voxels, const uint32_t org[3],
+                                 const uint32_t occ_lo[3], const uint32_t occ_hi[3], DevChunk* out_chunk, unsigned char* out_slot,
+                                 cudaStream_t st);
+
 // ---- halo.cu -----------------------------------------------------------------
 size_t halo_message_bytes(uint32_t plane_chunks);
 cudaError_t launch_halo_pack(const DevChunk* chunks, uint32_t plane_first, uint32_t plane_chunks, uint32_t layer_i,

@@ -278,6 +278,16 @@ class VoxelObject:
                                                                C.c_float(influence_radius), C.byref(st)))
         return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
 
+    def extract_any_disconnected_region(self):
+        """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113) → (info dict, extracted VoxelObject or
+        None). This object is modified in place."""
+        info = L.ExtractionInfo()
+        h = C.c_void_p()
+        self.ctx.check(self.ctx._lib.ivx_object_extract_disconnected_region(self.ctx.h, self.h, C.byref(info), C.byref(h)))
+        d = {f: getattr(info, f) for f, _ in L.ExtractionInfo._fields_ if f != "origin_offset_in_parent"}
+        d["origin_offset_in_parent"] = tuple(info.origin_offset_in_parent[:])
+        return d, (VoxelObject(self.ctx, h) if h.value else None)
+
     def resolve_connected_regions(self, download: bool = False) -> dict:
         """`update_local_connected_regions_for_all_chunks` + `resolve_connected_regions_between_all_chunks` +
         `count_regions` / `find_two_disconnected_regions` (split_detection.rs:193-488) and the region

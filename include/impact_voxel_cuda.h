@@ -405,6 +405,31 @@ int ivx_object_split_detection_download(ivx_ctx* ctx, const ivx_object* object, 
                                         size_t chunk_capacity, uint32_t* region_roots,
                                         size_t region_capacity);
 
+/* ---- disconnected-region extraction --------------------------------------
+ * ivx_object_extract_disconnected_region replaces VoxelObject::extract_any_disconnected_region
+ * (object/extraction.rs:78-113 → extract_smallest_region… :121-281 → extract_disconnected_region :297-600 →
+ * complete_extracted_voxel_object :1902-2187): connected regions are resolved, and if there are at least two, the
+ * smaller of the first two found (fewest NonUniform chunks, then fewest chunks) leaves `object` as a new object whose
+ * chunk grid is the bounding box of the region's chunks. Chunks holding only that region move whole, chunks shared with
+ * other regions are split voxel by voxel (empty voxels are copied to both sides). A fragment with fewer than 8
+ * non-empty voxels and no uniform chunk is dropped (`discarded`); one of at most 2 x 2 x 2 chunks whose voxels span at
+ * most 14 per axis is re-packed into a single chunk. Both objects leave with their derived state (adjacencies,
+ * obscuredness, occupied ranges) up to date; `object`'s chunks that lost voxels are marked for re-meshing
+ * (ivx_object_remesh_dirty). Inertial-property transfer (PropertyTransferrer) stays with the host. */
+typedef struct ivx_extraction_info {
+    uint32_t n_regions_before;          /* count_regions of `object` */
+    uint32_t found_two;                 /* find_two_disconnected_regions().is_some() */
+    uint32_t extracted;                 /* ExtractionResult::Extracted */
+    uint32_t discarded;                 /* removed from `object` but too small to keep (NotExtracted) */
+    uint32_t single_chunk;              /* re-packed into one chunk */
+    uint32_t region_label;              /* GlobalRegionLabel of the extracted region */
+    uint32_t region_chunks;             /* chunks of `object` the region touched */
+    uint32_t moved_non_empty_voxels;    /* non-empty voxels that left through NonUniform chunks */
+    uint32_t origin_offset_in_parent[3];/* ExtractedVoxelObject::origin_offset_in_parent, voxels */
+} ivx_extraction_info;
+int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* object, ivx_extraction_info* out_info,
+                                           ivx_object** out_extracted);
+
 #ifdef __cplusplus
 }
 #endif
