@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--workload", default="asteroid1024")
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=0)
-    ap.add_argument("--split", action="store_true", help="also resolve connected regions after every step")
+    ap.add_argument("--split", action="store_true", help="also resolve connected regions and split off disconnected ones after every step")
     args = ap.parse_args()
 
     import bench
@@ -57,6 +57,7 @@ def main():
     ctx.profile_enable(True)
     ctx.profile_reset()
     per_step = []
+    fragments = []  # extracted objects stay alive, like the entities the engine spawns for them
     launches0 = ctx.kernel_launch_count
     t_all = time.perf_counter()
     for c in centers:
@@ -68,10 +69,28 @@ def main():
         ctx.synchronize()
         t2 = time.perf_counter()
         regions = None
-        if args.split and hasattr(obj, "count_regions"):
-            regions = obj.count_regions()
+        n_extracted = n_discarded = 0
+        if args.split:
+            # handle_voxel_object_after_removing_voxels: resolve, then split off disconnected regions while there
+            # are any (every extraction re-resolves); the fragments' meshes are created like any new object's
+            while True:
+                xi, frag = obj.extract_any_disconnected_region()
+                if regions is None:
+                    regions = xi["n_regions_before"]
+                if not xi["found_two"]:
+                    break
+                if xi["extracted"]:
+                    n_extracted += 1
+                    VoxelObjectMesh.create(frag)
+                    fragments.append(frag)
+                else:
+                    n_discarded += 1
+            if n_extracted or n_discarded:
+                VoxelObjectMesh.sync_with_voxel_object(obj)
+            ctx.synchronize()
         t3 = time.perf_counter()
         per_step.append({"absorb_ms": 1e3 * (t1 - t0), "remesh_ms": 1e3 * (t2 - t1), "split_ms": 1e3 * (t3 - t2),
+                         "extracted": n_extracted, "discarded": n_discarded,
                          "touched_chunks": st["touched_chunks"], "touched_voxels": st["touched_voxels"],
                          "emptied_voxels": st["emptied_voxels"], "dirty_chunks": n_dirty,
                          "remeshed_submeshes": patch.n_submeshes, "patch_vertices": patch.n_vertices,
@@ -86,6 +105,8 @@ def main():
         "steps": args.steps, "absorber_radius_voxels": radius,
         "ms_per_step": 1e3 * wall / args.steps, "absorb_ms": mean("absorb_ms"), "remesh_ms": mean("remesh_ms"),
         "split_ms": mean("split_ms") if args.split else None,
+        "fragments_extracted": sum(s["extracted"] for s in per_step), "fragments_dropped": sum(s["discarded"] for s in per_step),
+        "split_note": "resolve connected regions + extract_any_disconnected_region until one region is left + mesh the fragments",
         "dirty_chunks_per_step": mean("dirty_chunks"), "touched_chunks_per_step": mean("touched_chunks"),
         "touched_voxels_per_step": mean("touched_voxels"), "emptied_voxels_total": sum(s["emptied_voxels"] for s in per_step),
         "touched_voxels_per_s": touched / wall,
