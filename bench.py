@@ -379,6 +379,15 @@ def run_gpu(args):
             with open(tp) as f:
                 traffic = json.load(f).get(args.workload, {}).get(dom)
         step_s = ms_step * 1e-3
+        fp32_pipe = None
+        if types.kind == 1 and prof.get("types", (0.0, 0))[1]:
+            evals = int(oi["n_non_uniform"]) * 4096 * int(types.n_types)
+            t_types = prof["types"][0] / args.steps * 1e-3
+            peak_ops = 148 * 128 * float(clocks.get("sm_mhz") or 1965.0) * 1e6
+            fp32_pipe = {"kernel": "k_types", "evaluations_per_step": evals, "f32_ops_per_evaluation": 163,
+                         "achieved_tops": evals * 163 / max(t_types, 1e-12) / 1e12, "peak_tops": peak_ops / 1e12,
+                         "frac": evals * 163 / max(t_types, 1e-12) / peak_ops,
+                         "note": "approximate: evaluations = this rank's NonUniform chunks x 4096 x voxel types"}
         out = {
             "metric": METRIC, "value": total_voxels / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -414,6 +423,10 @@ def run_gpu(args):
                                  "the kernel is bound by the FP32 pipe / instruction issue on simplex noise (ncu: FMA pipe 65 %, issue slots "
                                  "64 % busy, DRAM 1 %), see DESIGN.md §4 and profiles/"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+            # what actually bounds the dominant kernel: 163 f32 instructions-worth of arithmetic per 4-D simplex evaluation
+            # (SASS count, FMA = 1; profiles/README.md) on every voxel of every NonUniform chunk and every voxel type,
+            # against the FP32 pipes' 128 lanes x SMs x clock
+            "fp32_pipe": fp32_pipe,
             "whole_path_roofline_frac": (5.0 * total_voxels / step_s / 1e9) / peak,
         }
         if world == 1 and not args.no_cpu_baseline:

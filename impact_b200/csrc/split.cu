@@ -433,7 +433,9 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
 
     std::vector<uint32_t>& creg = obj->h_chunk_regions;
     creg.resize(n);
-    std::vector<uint2> recs(n_records);
+    // host scratch keeps its capacity across calls (a resolve per modification step: no page faults on MBs of vectors)
+    static thread_local std::vector<uint2> recs;
+    recs.resize(n_records);
     CU(ctx, cudaMemcpyAsync(creg.data(), regions, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (n_records) CU(ctx, cudaMemcpyAsync(recs.data(), records, (size_t)n_records * sizeof(uint2), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
@@ -448,21 +450,22 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
         total += creg[c] & 255u;
     }
     first[n] = total;
-    std::vector<uint32_t> parent(total);
+    static thread_local std::vector<uint32_t> parent, deg, start, adj, fill;
+    parent.resize(total);
     for (uint32_t c = 0; c < n; ++c)
         for (uint32_t r = 0; r < (creg[c] & 255u); ++r) parent[first[c] + r] = (c << 8) | r;
     // adjacency in CSR form, both directions
     const uint32_t stride[3] = {obj->nb[1] * obj->nb[2], obj->nb[2], 1u};
-    std::vector<uint32_t> deg(total + 1, 0);
+    deg.assign(total + 1, 0);
     for (const uint2& r : recs) {
         const uint32_t c = r.x, d = r.y >> 16, la = (r.y >> 8) & 255u, lb = r.y & 255u, cu = c + stride[d];
         deg[first[c] + la]++;
         deg[first[cu] + lb]++;
     }
-    std::vector<uint32_t> start(total + 1, 0);
+    start.assign(total + 1, 0);
     for (uint32_t i = 0; i < total; ++i) start[i + 1] = start[i] + deg[i];
-    std::vector<uint32_t> adj(start[total]);
-    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+    adj.resize(start[total]);
+    fill.assign(start.begin(), start.end() - 1);
     for (const uint2& r : recs) {
         const uint32_t c = r.x, d = r.y >> 16, la = (r.y >> 8) & 255u, lb = r.y & 255u, cu = c + stride[d];
         adj[fill[first[c] + la]++] = (cu << 8) | lb;
