@@ -309,7 +309,11 @@ def run_gpu(args):
         lib = ctx._lib
         tgp = types.pod()
 
+        trace = os.environ.get("IVX_E2E_TRACE")
+
         def step_e2e():
+            tt = [time.perf_counter()]
+            mark = (lambda: tt.append(time.perf_counter())) if trace else (lambda: None)
             prog = C.c_void_p()
             ctx.check(lib.ivx_program_build(ctx.h, L.ptr(h_nodes), C.c_uint32(len(nodes_host)),
                                             C.c_uint32(graph.root_node_id), C.byref(prog)))
@@ -331,8 +335,10 @@ def run_gpu(args):
                 ctx.check(lib.ivx_object_generate_streamed(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), L.ptr(h_chunks),
                                                            C.c_size_t(n_local_chunks), L.ptr(h_vox),
                                                            C.c_size_t(cap_vox * 4096), C.byref(o), C.byref(nnu)))
+            mark()
             mi = L.MeshInfo()
             ctx.check(lib.ivx_object_mesh(ctx.h, o, C.byref(mi)))
+            mark()
             if world > 1:
                 ctx.check(lib.ivx_object_download(ctx.h, o, L.ptr(h_chunks), C.c_size_t(n_local_chunks), L.ptr(h_vox),
                                                   C.c_size_t(cap_vox * 4096)))
@@ -341,9 +347,15 @@ def run_gpu(args):
                                             L.ptr(h_sub), L.ptr(h_vr)))
             d2h = n_local_chunks * 16 + oi["n_non_uniform"] * 4096 * 3 + mi.n_vertices * 24 + mi.n_indices * 12 + \
                 mi.n_submeshes * 60
+            mark()
             ctx.check(lib.ivx_synchronize(ctx.h))  # both streams: the host buffers are complete
+            mark()
             lib.ivx_object_free(ctx.h, o)
             lib.ivx_program_free(ctx.h, prog)
+            mark()
+            if trace:
+                print("e2e phases ms (build+generate, mesh, mesh download, synchronize, free):",
+                      [round(1e3 * (b - a), 2) for a, b in zip(tt, tt[1:])], file=sys.stderr)
             return d2h
 
         step_e2e()

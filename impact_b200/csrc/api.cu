@@ -16,8 +16,20 @@ using namespace ivx;
 
 namespace {
 
+// device words → mapped pinned host words, by a kernel: a device→host memcpy on the compute stream would queue on
+// the copy engine behind the bulk transfers of a streamed generation and stall every kernel after it
+__global__ void k_store_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n) {
+    if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+cudaError_t store_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t host_word, uint32_t n) {
+    k_store_words<<<1, 64, 0, ctx->stream>>>(d_src, ctx->h_pinned_dev + host_word, n);
+    return cudaGetLastError();
+}
+
 int read_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t n, uint32_t* out) {
-    CU(ctx, cudaMemcpyAsync(ctx->h_pinned, d_src, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n > 32) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "read_words: at most 32 words");
+    CU(ctx, store_words(ctx, d_src, 0, n));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     std::memcpy(out, ctx->h_pinned, n * sizeof(uint32_t));
     return IVX_OK;
@@ -119,6 +131,9 @@ uint32_t ivx_persistent_grid(ivx_ctx* ctx, uint32_t n_work, int blocks_per_sm) {
 
 namespace {
 
+#ifndef IVX_STREAM_PARTS
+#define IVX_STREAM_PARTS 16u  // at most this many parts of at least 3 chunk planes
+#endif
 // host destination of a streamed generation (ivx_object_generate_streamed)
 struct StreamOut {
     ivx_chunk_desc* h_chunks;
@@ -353,7 +368,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     // and handed to the copy stream, so the device→host transfer of part p runs under the arithmetic of parts > p.
     // The ordinary generation is the one-part case without the pack / copy tail.
     const uint32_t plane = obj->nb[1] * obj->nb[2];
-    const uint32_t P = (so && whole) ? std::min<uint32_t>(8u, std::max<uint32_t>(1u, obj->nb[0] / 4u)) : 1u;
+    const uint32_t P = (so && whole) ? std::min<uint32_t>(IVX_STREAM_PARTS, std::max<uint32_t>(1u, obj->nb[0] / 3u)) : 1u;
     std::vector<uint32_t> xb(P + 1), ab(P + 1);
     for (uint32_t q = 0; q <= P; ++q) xb[q] = (uint32_t)((uint64_t)q * obj->nb[0] / P);
     ab[0] = 0;
@@ -361,7 +376,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     if (P > 1) {
         // active_scan[c] = number of active chunks before chunk c
         for (uint32_t q = 1; q < P; ++q)
-            CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 32 + q, active_scan + (size_t)xb[q] * plane, 4, cudaMemcpyDeviceToHost, st));
+            CU(ctx, store_words(ctx, active_scan + (size_t)xb[q] * plane, 32 + q, 1));
         CU(ctx, cudaStreamSynchronize(st));
         for (uint32_t q = 1; q < P; ++q) ab[q] = ctx->h_pinned[32 + q];
     }
@@ -390,36 +405,67 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
         part_done.resize(P);
         for (auto& e : part_done) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    // Streamed: the evaluation of all parts runs ahead on the compute stream while typing, cross-chunk state and
+    // packing of each evaluated part follow on a second, higher-priority compute stream, so the tail of one kernel
+    // is filled by the CTAs of the other instead of idling eight times.
+    cudaStream_t st2 = so ? ctx->aux_stream : st;
+    std::vector<cudaEvent_t> evaluated;
+    if (so) {
+        evaluated.resize(P);
+        for (auto& e : evaluated) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     for (uint32_t q = 0; q < P; ++q) {
         const uint32_t cnt = ab[q + 1] - ab[q];
         if (cnt) {
             ea.active = active_list + ab[q];
             ea.n_active = cnt;
             KLP(ctx, 2, launch_eval(ea, std::min(egrid, cnt), st));
+        }
+        if (so) CU(ctx, cudaEventRecord(evaluated[q], st));
+    }
+    for (uint32_t q = 0; q < P; ++q) {
+        const uint32_t cnt = ab[q + 1] - ab[q];
+        if (so) CU(ctx, cudaStreamWaitEvent(st2, evaluated[q], 0));
+        if (cnt) {
             ta.active = active_list + ab[q];
             ta.n_active = cnt;
-            KLP(ctx, 7, launch_types(ta, persistent_grid(ctx, cnt, types_bps), st));
+            if (so) {
+                KL(ctx, launch_types(ta, persistent_grid(ctx, cnt, types_bps), st2));
+            } else {
+                KLP(ctx, 7, launch_types(ta, persistent_grid(ctx, cnt, types_bps), st2));
+            }
         }
         // ---- cross-chunk derived state of the planes whose six neighbours are typed ----
         const uint32_t lo = q == 0 ? 0u : xb[q] - 1u, hi = q + 1 == P ? obj->nb[0] : xb[q + 1] - 1u;
         part_lo[q] = lo;
         part_hi[q] = std::max(lo, hi);
         if (whole && hi > lo) {
-            KLP(ctx, 3, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, lo, hi, st));
-            KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr,
-                                              n, lo, hi, persistent_grid(ctx, n, 8), st));
+            if (so) {
+                KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, lo, hi, st2));
+                KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr,
+                                              n, lo, hi, persistent_grid(ctx, n, 8), st2));
+            } else {
+                KLP(ctx, 3, launch_boundary_classify(obj->d_chunks, n, obj->nb, nullptr, convert_flag, lo, hi, st2));
+                KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, n, obj->nb, nullptr, convert_flag, slot_of, obj->d_voxels, nullptr,
+                                                  n, lo, hi, persistent_grid(ctx, n, 8), st2));
+            }
         }
         if (so) {
             if (hi > lo) {
                 const uint32_t c0 = lo * plane, nc = (hi - lo) * plane;
-                KL(ctx, launch_nonuniform_flags(obj->d_chunks + c0, nc, pk_flag, st));
-                KL(ctx, launch_exclusive_scan(pk_flag, pk_ord, nc, part_counts + q, st));
+                KL(ctx, launch_nonuniform_flags(obj->d_chunks + c0, nc, pk_flag, st2));
+                KL(ctx, launch_exclusive_scan(pk_flag, pk_ord, nc, part_counts + q, st2));
                 KL(ctx, launch_pack_voxels(obj->d_chunks + c0, nc, pk_ord, part_counts, q, obj->d_voxels, obj->d_stage_voxels,
-                                           obj->d_stage_chunks + c0, persistent_grid(ctx, nc, 8), st));
-                CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 40 + q, part_counts + q, 4, cudaMemcpyDeviceToHost, st));
+                                           obj->d_stage_chunks + c0, persistent_grid(ctx, nc, 8), st2));
+                k_store_words<<<1, 64, 0, st2>>>(part_counts + q, ctx->h_pinned_dev + 40 + q, 1);
+                CU(ctx, cudaGetLastError());
             }
-            CU(ctx, cudaEventRecord(part_done[q], st));
+            CU(ctx, cudaEventRecord(part_done[q], st2));
         }
+    }
+    if (so) {
+        CU(ctx, cudaStreamWaitEvent(st, part_done[P - 1], 0));  // later work on the compute stream sees the finished object
+        for (auto& e : evaluated) cudaEventDestroy(e);
     }
     if (so) {
         // the host follows the parts as they finish and queues their transfers; the compute stream never waits
@@ -711,12 +757,17 @@ int ivx_create(const ivx_config* config, ivx_ctx** out_ctx) {
         }
         ctx->own_stream = true;
     }
-    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        ctx->copy_stream = nullptr;
-        ivx_destroy(ctx);
-        return IVX_ERR_CUDA;
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+            ivx_destroy(ctx);
+            return IVX_ERR_CUDA;
+        }
     }
-    if (cudaMallocHost(&ctx->h_pinned, 64 * sizeof(uint32_t)) != cudaSuccess ||
+    if (cudaHostAlloc(&ctx->h_pinned, 64 * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&ctx->h_pinned_dev, ctx->h_pinned, 0) != cudaSuccess ||
         cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess) {
         ivx_destroy(ctx);
         return IVX_ERR_OUT_OF_MEMORY;
@@ -732,6 +783,10 @@ void ivx_destroy(ivx_ctx* ctx) {
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
+    }
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
     }
     for (auto& e : ctx->prof_events) {
         cudaEventDestroy(e.a);
@@ -750,6 +805,7 @@ uint64_t ivx_kernel_launch_count(const ivx_ctx* ctx) { return ctx ? ctx->launche
 int ivx_synchronize(ivx_ctx* ctx) {
     if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->aux_stream));
     CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return IVX_OK;
 }

@@ -28,6 +28,8 @@ struct ivx_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;  // device→host copies of streamed generation, beside the compute stream
+    cudaStream_t aux_stream = nullptr;   // second compute stream of streamed generation (typing / packing of part p
+                                         // under the evaluation of part p + 1)
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -39,6 +41,8 @@ struct ivx_ctx {
     double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t* h_pinned = nullptr;  // 64 words of pinned scratch for counter read-back
+    uint32_t* h_pinned_dev = nullptr;  // the same words as the device sees them (mapped): counters are stored by a
+                                       // kernel, not by the copy engine, which may be busy with a bulk transfer
     uint32_t* d_scratch = nullptr; // 64 words of device counters
 
     void* alloc(size_t bytes) {

@@ -22,6 +22,8 @@
 // Faces not selected by `face_mask` are left untouched, which is how the
 // modification path restricts the update to the touched chunk range
 // (object/intersection.rs:391-393).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -71,18 +73,18 @@ __global__ void k_boundary_classify(const DevChunk* __restrict__ chunks, uint32_
     convert_flag[c] = conv;
 }
 
-__global__ void __launch_bounds__(256) k_boundary_apply(DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
+__global__ void __launch_bounds__(256, 8) k_boundary_apply(DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
                                                          const uint8_t* __restrict__ face_mask,
                                                          const uint32_t* __restrict__ convert_flag,
                                                          const uint32_t* __restrict__ slot_of,
                                                          unsigned char* __restrict__ voxels,
                                                          const uint32_t* __restrict__ work_list, uint32_t n_work,
-                                                         uint32_t own_lo, uint32_t own_hi) {
+                                                         uint32_t work_first, uint32_t own_lo, uint32_t own_hi) {
     __shared__ __align__(16) uint8_t s_flags[4096];
     __shared__ Neighbour s_nb[6];
     const int tid = threadIdx.x;
     for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const uint32_t c = work_list ? work_list[w] : w;
+        const uint32_t c = work_list ? work_list[w] : w + work_first;
         DevChunk me = chunks[c];
         const bool converting = convert_flag[c] != 0;
         const uint32_t plane = c / (nb.z * nb.y);
@@ -177,8 +179,18 @@ cudaError_t launch_boundary_apply(DevChunk* chunks, uint32_t n, const uint32_t n
                                   const uint32_t* work_list, uint32_t n_work, uint32_t own_lo, uint32_t own_hi,
                                   uint32_t grid, cudaStream_t st) {
     if (n_work == 0) return cudaSuccess;
+    uint32_t work_first = 0;
+    if (!work_list) {
+        // without a work list only the chunks of planes [own_lo, own_hi) can have work: walk just those
+        const uint32_t plane = nb[1] * nb[2];
+        const uint32_t lo = std::min(own_lo, nb[0]), hi = std::min(own_hi, nb[0]);
+        if (hi <= lo) return cudaSuccess;
+        work_first = lo * plane;
+        n_work = std::min(n_work, (hi - lo) * plane);
+        grid = std::max(1u, std::min(grid, n_work));
+    }
     k_boundary_apply<<<grid, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), face_mask, convert_flag, slot_of,
-                                           voxels, work_list, n_work, own_lo, own_hi);
+                                           voxels, work_list, n_work, work_first, own_lo, own_hi);
     return cudaGetLastError();
 }
 

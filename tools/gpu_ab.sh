@@ -10,7 +10,7 @@ for v in "$@"; do
 import json
 try:
     d = json.load(open("gpurun_out/${tag}_${v}_bench.json"))
-    print("$v", "ms/step", round(d["ms_per_step"],3), {k: round(x,3) for k,x in d["kernel_ms_per_step"].items()})
+    print("$v", "ms/step", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["ms_per_step"],2), {k: round(x,3) for k,x in d["kernel_ms_per_step"].items()})
 except Exception as e:
     print("$v bench failed:", e)
 PY
