@@ -408,7 +408,8 @@ def run_gpu(args):
                 "workload": args.workload, "description": desc, "grid_shape": grid_shape,
                 "chunks": int(np.prod(info[0]["chunk_counts"])), "parallelism": f"x-slab x{world}" + (" (work-balanced plane ranges)" if world > 1 else ""),
                 "slab_planes": [list(r) for r in ranges], "rank0_exchange": halo_stats,
-                "mesh_gather": ("peer-memory stores into rank 0 (ivx_mesh_push over NVLink, CUDA IPC)" if peer_gather[0] is not None
+                "mesh_gather": ("peer-memory stores into rank 0 (ivx_mesh_push over NVLink, CUDA IPC)"
+                                if peer_gather[0] is not None and peer_gather[0].available
                                 else ("NCCL send/recv" if world > 1 else "none")),
                 "rank0_chunks": {"void": oi["n_void"], "uniform": oi["n_uniform"], "non_uniform": oi["n_non_uniform"]},
                 "rank0_mesh": {"vertices": info[1], "indices": info[2], "submeshes": info[3]},

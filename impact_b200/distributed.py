@@ -228,6 +228,7 @@ class PeerMeshGather:
         self.caps = np.zeros(3, np.int64)  # vertices, indices, submeshes
         self.base = None                   # pointer valid on this rank's device
         self.offsets = None
+        self.available = True              # False once CUDA IPC turned out not to work on some rank
 
     def _layout(self, caps):
         key = {"v": int(caps[0]), "i": int(caps[1]), "s": int(caps[2])}
@@ -255,18 +256,30 @@ class PeerMeshGather:
         self.offsets, nbytes = self._layout(self.caps)
         handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
         lib = self.ctx._lib
+        ok = 1
         if self.rank == self.dst:
             ptr = C.c_void_p()
             hbuf = (C.c_ubyte * 64)()
-            self.ctx.check(lib.ivx_peer_alloc(self.ctx.h, C.c_size_t(nbytes), C.byref(ptr), hbuf))
-            self.base = ptr.value
-            handle.copy_(torch.tensor(list(hbuf), dtype=torch.uint8))
+            if lib.ivx_peer_alloc(self.ctx.h, C.c_size_t(nbytes), C.byref(ptr), hbuf) == 0:
+                self.base = ptr.value
+                handle.copy_(torch.tensor(list(hbuf), dtype=torch.uint8))
+            else:
+                ok = 0
         dist.broadcast(handle, self.dst, group=self.group)
         if self.rank != self.dst:
             hb = (C.c_ubyte * 64)(*handle.cpu().tolist())
             ptr = C.c_void_p()
-            self.ctx.check(lib.ivx_peer_open(self.ctx.h, hb, C.byref(ptr)))
-            self.base = ptr.value
+            if lib.ivx_peer_open(self.ctx.h, hb, C.byref(ptr)) == 0:
+                self.base = ptr.value
+            else:
+                ok = 0
+        # CUDA IPC can be unavailable (container / driver settings): all ranks agree, and the caller falls back to the
+        # NCCL send/recv gather
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self._release()
+            self.available = False
 
     def gather(self, mesh):
         """`mesh`: this rank's `VoxelObjectMesh`. → the merged dict of device tensors on `dst` (views into the
@@ -278,7 +291,10 @@ class PeerMeshGather:
         table = all_counts.cpu().numpy().reshape(self.world, 3)
         totals = table.sum(axis=0)
         starts = np.concatenate([np.zeros((1, 3), np.int64), np.cumsum(table, axis=0)[:-1]])
-        self._ensure(totals)
+        if self.available:
+            self._ensure(totals)
+        if not self.available:
+            return gather_mesh(device_mesh_tensors(mesh, self.device), self.rank, self.world, self.device, self.dst, self.group)
         v0, i0, s0 = (int(x) for x in starts[self.rank])
         offs = (C.c_uint64 * 6)(*self.offsets)
         self.ctx.check(self.ctx._lib.ivx_mesh_push(self.ctx.h, mesh.obj.h, C.c_void_p(self.base), offs, C.c_uint32(v0),
