@@ -179,7 +179,7 @@ __device__ __forceinline__ void emit_quad_materials(const uint32_t vid[4], uint3
 template <bool EMIT>
 __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
     __shared__ __align__(16) int8_t s_sd[5832];
-    __shared__ __align__(16) uint8_t s_type[5832];
+    __shared__ __align__(16) uint8_t s_type[EMIT ? 5832 : 16];
     __shared__ __align__(4) uint16_t s_l2v[EMIT ? 5832 : 2];
     __shared__ uint32_t s_neg[324];
     // multi-material quads of one tile of 256 vertices (<= 3 each): index position | corner order << 14, vertex ids
@@ -214,13 +214,15 @@ __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
             const DevChunk me = a.chunks[chunk];  // NonUniform by construction of the work list
             const unsigned char* slot = a.voxels + (size_t)me.slot * SLOT_BYTES;
             const uint4 wsd = *reinterpret_cast<const uint4*>(slot + PLANE_SD + tid * 16);
-            const uint4 wty = *reinterpret_cast<const uint4*>(slot + PLANE_TYPE + tid * 16);
-            const uint32_t ws[4] = {wsd.x, wsd.y, wsd.z, wsd.w}, wt[4] = {wty.x, wty.y, wty.z, wty.w};
+            const uint32_t ws[4] = {wsd.x, wsd.y, wsd.z, wsd.w};
             const int row = bidx((tid >> 4) + 1, (tid & 15) + 1, 1);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                s_sd[row + k] = (int8_t)((ws[k >> 2] >> (8 * (k & 3))) & 0xFFu);
-                s_type[row + k] = (uint8_t)((wt[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+            for (int k = 0; k < 16; ++k) s_sd[row + k] = (int8_t)((ws[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+            if (EMIT) {  // the counting pass only needs signs
+                const uint4 wty = *reinterpret_cast<const uint4*>(slot + PLANE_TYPE + tid * 16);
+                const uint32_t wt[4] = {wty.x, wty.y, wty.z, wty.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) s_type[row + k] = (uint8_t)((wt[k >> 2] >> (8 * (k & 3))) & 0xFFu);
             }
         }
         // the 1-voxel halo (1736 cells) from the up to 26 neighbours (object/sdf.rs:410-508): the two i planes, then
@@ -257,12 +259,12 @@ __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
                         const unsigned char* slot = a.voxels + (size_t)nc.slot * SLOT_BYTES;
                         const int v = vidx(gi & 15, gj & 15, gk & 15);
                         sd = (int8_t)slot[PLANE_SD + v];
-                        ty = slot[PLANE_TYPE + v];
+                        if (EMIT) ty = slot[PLANE_TYPE + v];
                     }
                 }
             }
             s_sd[cell] = sd;
-            s_type[cell] = ty;
+            if (EMIT) s_type[cell] = ty;
         }
         if (EMIT)
             for (int cell = tid; cell < 5832 / 2; cell += MESH_THREADS) reinterpret_cast<uint32_t*>(s_l2v)[cell] = 0xFFFFFFFFu;
