@@ -147,6 +147,161 @@ def load_vgen_ron(path):
 
 
 # ------------------------------------------------------------------------------------------------
+# the editor's `*.graph.ron` (apps/voxel_generator/src/editor/meta/io.rs:15-70): nodes with positional parameters and
+# links, turned into the same meta nodes by the editor's own rules (build.rs:53-100, node_kind.rs `build` of every kind)
+
+_SAMPLING = ("OnlyOnce", "PerInstance")            # "Only once", "Per instance" / "Per SDF" (meta.rs:2272-2280)
+_COMPOSITION = ("Post", "Pre")                      # node_kind.rs:446
+_ROTATION = ("Identity", "RadialOutwards", "RadialInwards")  # node_kind.rs:956
+_ANCHOR = ("Origin", "ShapeBoundaryAtOrigin")       # node_kind.rs:1036
+# kind → (child field names in slot order, [(field, how)]): how = "dist" (distributed → ParamSpec), "num" (UInt / Float
+# value) or a tuple of enum variant names indexed by the stored variant number
+EDITOR_NODE_KINDS = {
+    "Points": ((), [("count", "num")]),
+    "Spheres": ((), [("radius", "dist"), ("center_x", "dist"), ("center_y", "dist"), ("center_z", "dist"), ("count", "num"),
+                     ("seed", "num"), ("sampling", _SAMPLING)]),
+    "Capsules": ((), [("segment_length", "dist"), ("radius", "dist"), ("center_x", "dist"), ("center_y", "dist"),
+                      ("center_z", "dist"), ("count", "num"), ("seed", "num"), ("sampling", _SAMPLING)]),
+    "Boxes": ((), [("extent_x", "dist"), ("extent_y", "dist"), ("extent_z", "dist"), ("center_x", "dist"), ("center_y", "dist"),
+                   ("center_z", "dist"), ("count", "num"), ("seed", "num"), ("sampling", _SAMPLING)]),
+    "Translation": (("child_id",), [("composition", _COMPOSITION), ("translation_x", "dist"), ("translation_y", "dist"),
+                                    ("translation_z", "dist"), ("seed", "num"), ("sampling", _SAMPLING)]),
+    "Rotation": (("child_id",), [("composition", _COMPOSITION), ("tilt_angle", "dist"), ("turn_angle", "dist"),
+                                 ("roll_angle", "dist"), ("seed", "num"), ("sampling", _SAMPLING)]),
+    "Scaling": (("child_id",), [("composition", _COMPOSITION), ("scaling", "dist"), ("seed", "num"), ("sampling", _SAMPLING)]),
+    "Similarity": (("child_id",), [("composition", _COMPOSITION), ("scale", "dist"), ("tilt_angle", "dist"), ("turn_angle", "dist"),
+                                   ("roll_angle", "dist"), ("translation_x", "dist"), ("translation_y", "dist"),
+                                   ("translation_z", "dist"), ("seed", "num"), ("sampling", _SAMPLING)]),
+    "StratifiedGridTransforms": (("child_id",), [("shape_x", "dist"), ("shape_y", "dist"), ("shape_z", "dist"),
+                                                 ("cell_extent_x", "dist"), ("cell_extent_y", "dist"), ("cell_extent_z", "dist"),
+                                                 ("jitter_fraction", "dist"), ("seed", "num")]),
+    "SphereSurfaceTransforms": (("child_id",), [("radius", "dist"), ("jitter_fraction", "dist"), ("rotation", _ROTATION),
+                                                ("seed", "num")]),
+    "ClosestTranslationToSurface": (("surface_sdf_id", "subject_id"), []),
+    "RayTranslationToSurface": (("surface_sdf_id", "subject_id"), [("anchor", _ANCHOR)]),
+    "RotationToGradient": (("gradient_sdf_id", "subject_id"), []),
+    "StochasticSelection": (("child_id",), [("min_pick_count", "num"), ("max_pick_count", "num"), ("pick_probability", "num"),
+                                            ("seed", "num")]),
+    "SDFInstantiation": (("child_id",), []),
+    "TransformApplication": (("sdf_id", "instance_id"), []),
+    "MultifractalNoiseSDFModifier": (("child_id",), [("octaves", "dist"), ("frequency", "dist"), ("lacunarity", "dist"),
+                                                     ("persistence", "dist"), ("amplitude", "dist"), ("seed", "num"),
+                                                     ("sampling", _SAMPLING)]),
+    "SDFUnion": (("child_1_id", "child_2_id"), [("smoothness", "num")]),
+    "SDFSubtraction": (("child_1_id", "child_2_id"), [("smoothness", "num")]),
+    "SDFIntersection": (("child_1_id", "child_2_id"), [("smoothness", "num")]),
+    "SDFGroupUnion": (("child_id",), [("smoothness", "num")]),
+}
+
+
+def _payload(t):
+    """`Tag(x)` → x (the parser keeps a single positional field as the value or as a one-element list)."""
+    return t.fields[0] if isinstance(t.fields, list) else t.fields
+
+
+_EDITOR_DISCRETE = {"shape_x", "shape_y", "shape_z", "octaves"}  # DiscreteParamSpec fields (meta.rs)
+
+
+def _editor_source(src, discrete=False):
+    """`ValueSource` → `ContValueSource` / `DiscreteValueSource` (param.rs:883-905; `fixed as u32` for discrete ones)."""
+    if src["variant"].tag == "Fixed":
+        return Tagged("Fixed", int(max(src["fixed"], 0.0)) if discrete else src["fixed"])
+    fp = src["from_param"]
+    lin = fp["mapping"]["linear"]
+    return Tagged("FromParam", {"idx": int(fp["param_idx"]),
+                                "mapping": Tagged("Linear", {"offset": lin["offset"], "scale": lin["scale"]})})
+
+
+def _editor_spec(dist, discrete=False):
+    """`ParamDistribution` → `ContParamSpec` / `DiscreteParamSpec` (param.rs:751-785)."""
+    v = dist["variant"].tag
+    some = _payload  # Some((…))
+    if v == "Constant":
+        return Tagged("Constant", _editor_source(dist["constant"], discrete))
+    if v == "Uniform":
+        u = some(dist["uniform"])
+        return Tagged("Uniform", {"min": _editor_source(u["min"], discrete), "max": _editor_source(u["max"], discrete)})
+    if discrete:
+        raise ValueError(f"distribution {v} is not available for discrete parameters")
+    if v == "UniformCosAngle":
+        u = some(dist["uniform_cos_angle"])
+        return Tagged("UniformCosAngle", {"min_angle": _editor_source(u["min_angle"]), "max_angle": _editor_source(u["max_angle"])})
+    if v == "PowerLaw":
+        u = some(dist["power_law"])
+        return Tagged("PowerLaw", {"min": _editor_source(u["min"]), "max": _editor_source(u["max"]),
+                                   "exponent": _editor_source(u["exponent"])})
+    raise ValueError(f"unknown distribution variant {v}")
+
+
+def load_graph_ron(path):
+    """The voxel generator editor's `*.graph.ron` → (meta nodes, voxel_extent, scale_factor, seed).
+
+    Restates `build_meta_graph` (apps/voxel_generator/src/editor/meta/build.rs:53-100): the graph below the Output node
+    (id 0; its parameters are voxel extent, scale factor and seed, node_kind.rs `get_properties_from_output_node`) is
+    walked depth first, first child first, and every node is added after its children, so meta node ids are post-order
+    positions and the root is the last node. Raises ValueError for a graph without output or with an unattached slot
+    (`build_meta_graph` returns None there)."""
+    with open(path) as f:
+        return graph_ron_nodes(f.read())
+
+
+def graph_ron_nodes(text):
+    """`load_graph_ron` on the file's text."""
+    doc = parse_ron(text)
+    by_id = {int(n["id"]): n for n in doc["nodes"]}
+    out = by_id.get(0)
+    if out is None or out["kind"].tag != "Output":
+        raise ValueError("graph has no Output node")
+    p = out["params"]
+    voxel_extent, scale_factor, seed = float(_payload(p[0])), float(_payload(p[1])), int(_payload(p[2]))
+
+    def link(l):
+        if l.tag != "Some":
+            raise ValueError("unattached child slot")
+        return int(_payload(l)["to_node"])
+
+    root = link(out["links_to_children"][0])
+    id_map, nodes = {}, []
+    stack = [("visit", root)]
+    while stack:
+        op, nid = stack.pop()
+        node = by_id[nid]
+        if op == "visit":
+            if nid in id_map:
+                continue
+            stack.append(("build", nid))
+            for l in reversed(node["links_to_children"]):
+                stack.append(("visit", link(l)))
+            continue
+        if nid in id_map:
+            continue
+        kind = node["kind"].tag
+        child_names, params = EDITOR_NODE_KINDS[kind]
+        if len(node["params"]) != len(params):
+            raise ValueError(f"{kind} node {nid}: expected {len(params)} parameters, found {len(node['params'])}")
+        fields = {}
+        for name, l in zip(child_names, node["links_to_children"]):
+            fields[name] = id_map[link(l)]
+        for (name, how), val in zip(params, node["params"]):
+            if how == "dist":
+                fields[name] = _editor_spec(_payload(val), name in _EDITOR_DISCRETE)
+            elif how == "num":
+                fields[name] = _payload(val)
+            else:
+                fields[name] = Tagged(how[int(_payload(val))], None)
+        id_map[nid] = len(nodes)
+        nodes.append(Tagged(kind, fields))
+    return nodes, voxel_extent, scale_factor, seed
+
+
+def compile_graph_file(path, ctx=None):
+    """`build_sdf_graph` (build.rs:102-128): the editor file compiled with its own scale factor and seed →
+    (atomic SDFGraph, voxel_extent)."""
+    nodes, voxel_extent, scale_factor, seed = load_graph_ron(path)
+    return MetaCompiler(nodes, scale_factor, seed, ctx).build(), voxel_extent
+
+
+# ------------------------------------------------------------------------------------------------
 # randomness: splitmix (impact_math/src/random/splitmix.rs) + fastrand wyrand (restated, see header)
 
 def splitmix(state):

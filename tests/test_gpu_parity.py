@@ -33,6 +33,9 @@ GRAPHS = {
     "noisy_box": (lambda: H.noisy_box_graph(38.0, 8), H.SAME0),           # BASELINE config 2, reduced
     "zoo": (H.csg_zoo_graph, H.GRADIENT4),
     "mid_noise": (H.mid_noise_graph, H.SAME0),
+    # an editor file (tests/golden/mini.graph.ron) through the .graph.ron loader and the meta-graph compiler
+    "editor_mini": (lambda: __import__("impact_b200.meta", fromlist=["x"]).compile_graph_file(
+        __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "mini.graph.ron"))[0], H.GRADIENT4),
     "asteroid_like": (lambda: H.asteroid_like_graph(24, 40.0), H.GRADIENT4),  # BASELINE config 3 stand-in
     # same node kinds / counts as asteroid.vgen.ron (446 leaves, depth 9) at a grid the oracle finishes in seconds
     "asteroid_stand_in": (lambda: W.asteroid_stand_in(0.6), H.GRADIENT4),

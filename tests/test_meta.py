@@ -37,6 +37,50 @@ def test_ron_reader_handles_the_generator_format():
     assert nodes[0]["sampling"].tag == "PerInstance" and nodes[1]["child_id"] == 0
 
 
+REF_GRAPH_RON = "/root/reference/apps/voxel_generator/examples/asteroid.graph.ron"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GRAPH_RON), reason="reference tree not present on this machine")
+def test_editor_graph_file_gives_the_same_meta_nodes_as_the_generator_file():
+    # apps/voxel_generator/examples/asteroid.graph.ron is the editor's copy of engine/benches/data/asteroid.vgen.ron:
+    # loading it through the editor's build rules must give the identical meta graph, node for node, in the same order
+    nodes, voxel_extent, scale_factor, seed = M.load_graph_ron(REF_GRAPH_RON)
+    assert (voxel_extent, scale_factor, seed) == (0.25, 1.0, 346)
+    assert _norm(nodes) == _norm(M.load_vgen_ron(REF_RON))
+
+
+def test_editor_graph_reader_follows_the_editors_build_rules():
+    # tests/golden/mini.graph.ron: post-order ids, a child shared by two parents added once, enum variants by index,
+    # discrete `fixed as u32`, FromParam sources, every distribution variant
+    with open(os.path.join(os.path.dirname(__file__), "golden", "mini.graph.ron")) as f:
+        nodes, voxel_extent, scale_factor, seed = M.graph_ron_nodes(f.read())
+    assert (voxel_extent, scale_factor, seed) == (0.5, 2.0, 7)
+    assert [n.tag for n in nodes] == ["Spheres", "SDFInstantiation", "SDFGroupUnion", "Scaling", "SDFInstantiation",
+                                      "SDFGroupUnion", "SDFUnion", "MultifractalNoiseSDFModifier"]
+    sph, inst1, gu1, scal, inst2, gu2, uni, noise = nodes
+    assert (gu1["child_id"], gu1["smoothness"], gu2["child_id"], gu2["smoothness"]) == (1, 0.0, 4, 0.25)
+    assert sph["count"] == 1 and sph["seed"] == 3 and sph["sampling"].tag == "OnlyOnce"
+    assert sph["radius"].tag == "Constant" and sph["radius"].fields.fields == 12.0
+    assert sph["center_z"].tag == "UniformCosAngle" and sph["center_z"]["max_angle"].fields == 20.0
+    assert inst1["child_id"] == 0 and scal["child_id"] == 0 and inst2["child_id"] == 3
+    assert scal["composition"].tag == "Pre" and scal["sampling"].tag == "OnlyOnce" and scal["seed"] == 11
+    assert scal["scaling"].tag == "PowerLaw" and scal["scaling"]["exponent"].fields == 2.5
+    assert (uni["child_1_id"], uni["child_2_id"], uni["smoothness"]) == (2, 5, 1.5)
+    assert noise["child_id"] == 6 and noise["sampling"].tag == "PerInstance"
+    assert noise["octaves"].fields.fields == 3 and isinstance(noise["octaves"].fields.fields, int)
+    amp = noise["amplitude"].fields
+    assert amp.tag == "FromParam" and amp["idx"] == 1 and amp["mapping"]["offset"] == 1.0 and amp["mapping"]["scale"] == 100.0
+    assert noise["frequency"].tag == "Uniform" and noise["frequency"]["min"].fields == 0.01
+    with pytest.raises(ValueError):
+        M.graph_ron_nodes("(kind: Subgraph(root_node_id: 1), nodes: [], collapsed_nodes: [])")
+    # and the file compiles to an atomic graph with the editor's own scale factor and seed (build.rs:102-128)
+    g, ve = M.compile_graph_file(os.path.join(os.path.dirname(__file__), "golden", "mini.graph.ron"))
+    kinds = [int(k) for k in g.nodes()["kind"]]
+    assert ve == 0.5 and len(g) >= 4 and g.root_node_id == len(g) - 1
+    from impact_b200 import workloads as W
+    assert all(20 < d < 160 for d in W.grid_shape_of(g)), W.grid_shape_of(g)
+
+
 def test_parameter_evaluation_order_is_topological_fifo():
     # params.rs:266-330: parameters without dependencies first (index order), dependents as they become ready
     node = M.asteroid_meta_nodes()[7]  # Capsules: segment_length and center_y depend on radius (idx 1)
