@@ -243,6 +243,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     uint32_t par_nb[3] = {0, 0, 0};
     uint32_t par_size = 0;
     sizes.push_back(1);  // the exact level
+    uint64_t arena_bound = 0;  // host-side upper bound of the previous level's arena, in instructions
     Instr* ch_instrs = nullptr;
     uint32_t* ch_off = nullptr;
     uint32_t* ch_len = nullptr;
@@ -262,10 +263,26 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
             KL(ctx, launch_child_caps(par_len, nblk, lnb, par_nb, par_size / sz, caps, st));
         }
         KL(ctx, launch_exclusive_scan(caps, off, nblk, counters + 8, st));
-        if (int rc = read_words(ctx, counters, 16, words)) return rc;
-        if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
-        Instr* instrs = tmp.get<Instr>(std::max<size_t>(1, words[8]));
-        if (!instrs) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "program arena (%u instructions): out of device memory", words[8]);
+        // The arena of this level holds sum(caps) instructions. That sum is only known on the device; a host-side
+        // bound (every block's cap is at most the root program's length, and at most its parent's share of the parent
+        // arena) avoids a host round trip per level as long as it stays small next to HBM — the arena is scratch.
+        uint64_t bound = (uint64_t)nblk * prog->root_len;
+        if (par_size != 0) {
+            const uint64_t r = par_size / sz;
+            bound = std::min(bound, arena_bound * r * r * r);
+        }
+        arena_bound = bound;
+        size_t arena_instrs;
+        if (bound * sizeof(Instr) <= ((size_t)1 << 30)) {
+            arena_instrs = (size_t)bound;
+        } else {
+            if (int rc = read_words(ctx, counters, 16, words)) return rc;
+            if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
+            arena_instrs = words[8];
+            arena_bound = words[8];
+        }
+        Instr* instrs = tmp.get<Instr>(std::max<size_t>(1, arena_instrs));
+        if (!instrs) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "program arena (%zu instructions): out of device memory", arena_instrs);
         fa.n_blocks = nblk;
         for (int d = 0; d < 3; ++d) {
             fa.nb[d] = lnb[d];
