@@ -249,18 +249,26 @@ def graph_ron_nodes(text):
     """`load_graph_ron` on the file's text."""
     doc = parse_ron(text)
     by_id = {int(n["id"]): n for n in doc["nodes"]}
-    out = by_id.get(0)
-    if out is None or out["kind"].tag != "Output":
-        raise ValueError("graph has no Output node")
-    p = out["params"]
-    voxel_extent, scale_factor, seed = float(_payload(p[0])), float(_payload(p[1])), int(_payload(p[2]))
 
     def link(l):
         if l.tag != "Some":
             raise ValueError("unattached child slot")
         return int(_payload(l)["to_node"])
 
-    root = link(out["links_to_children"][0])
+    if doc["kind"].tag == "Subgraph":
+        # a `*.subgraph.ron` fragment (io.rs:31-39): no Output node; its root is named by the file and the output
+        # properties take the editor's defaults for a new Output node (node_kind.rs:101-104, 1727-1770)
+        root = int(doc["kind"]["root_node_id"])
+        if root not in by_id:
+            raise ValueError("subgraph root node is missing")
+        voxel_extent, scale_factor, seed = 0.25, 0.25, 0
+    else:
+        out = by_id.get(0)
+        if out is None or out["kind"].tag != "Output":
+            raise ValueError("graph has no Output node")
+        p = out["params"]
+        voxel_extent, scale_factor, seed = float(_payload(p[0])), float(_payload(p[1])), int(_payload(p[2]))
+        root = link(out["links_to_children"][0])
     id_map, nodes = {}, []
     stack = [("visit", root)]
     while stack:
