@@ -49,6 +49,19 @@ def test_editor_graph_file_gives_the_same_meta_nodes_as_the_generator_file():
     assert _norm(nodes) == _norm(M.load_vgen_ron(REF_RON))
 
 
+@pytest.mark.skipif(not os.path.exists(REF_GRAPH_RON), reason="reference tree not present on this machine")
+def test_editor_subgraph_fragments():
+    # *.subgraph.ron (io.rs:31-39): asteroid_base is the first seven nodes of the asteroid graph; the crater fragments
+    # have an open input (the surface they are cast onto) and cannot be built on their own
+    ex = os.path.dirname(REF_GRAPH_RON)
+    base, *_ = M.load_graph_ron(os.path.join(ex, "asteroid_base.subgraph.ron"))
+    full, *_ = M.load_graph_ron(REF_GRAPH_RON)
+    assert _norm(base) == _norm(full[:7])
+    for name in ("big_craters", "medium_craters", "small_craters"):
+        with pytest.raises(ValueError, match="unattached"):
+            M.load_graph_ron(os.path.join(ex, f"{name}.subgraph.ron"))
+
+
 def test_editor_graph_reader_follows_the_editors_build_rules():
     # tests/golden/mini.graph.ron: post-order ids, a child shared by two parents added once, enum variants by index,
     # discrete `fixed as u32`, FromParam sources, every distribution variant
