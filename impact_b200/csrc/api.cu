@@ -1351,6 +1351,7 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     if (!ctx || !obj) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->aux_stream);
     cudaStreamSynchronize(ctx->copy_stream);
     free_mesh(ctx, obj->mesh);
     ctx->release(obj->d_stage_voxels);
