@@ -709,7 +709,14 @@ int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMe
     ma.index_materials = m.index_materials;
     ma.submeshes = m.submeshes;
     ma.vertex_ranges = m.vertex_ranges;
+    // room to record every quad as multi-material (scratch; the usual share is a few per cent)
+    ma.mq_capacity = m.n_indices / 6u;
+    ma.mq_entries = tmp.get<uint4>(std::max<size_t>(1, (size_t)ma.mq_capacity * 3));
+    ma.mq_count = counters + 20;
+    if (!ma.mq_entries) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh: out of device memory");
+    CU(ctx, cudaMemsetAsync(ma.mq_count, 0, 4, st));
     KLP(ctx, 5, launch_mesh(true, ma, grid, st));
+    KLP(ctx, 5, launch_mesh_materials(ma.mq_entries, ma.mq_count, ma.mq_capacity, m.index_materials, st));
     CU(ctx, cudaStreamSynchronize(st));
     return IVX_OK;
 }

@@ -161,7 +161,14 @@ struct MeshArgs {
     ivx_index_materials* index_materials;
     ivx_chunk_submesh* submeshes;
     uint32_t* vertex_ranges;
+    // quads whose four vertices do not share one material are recorded here by the emit pass and finished by
+    // k_mesh_materials (one thread per quad) instead of by a few lanes of the emit kernel
+    uint4* mq_entries;      // 3 x uint4 per quad
+    uint32_t* mq_count;
+    uint32_t mq_capacity;   // quads; beyond it the emit kernel finishes the quad in place
 };
+cudaError_t launch_mesh_materials(const uint4* entries, const uint32_t* count, uint32_t capacity,
+                                  ivx_index_materials* index_materials, cudaStream_t st);
 cudaError_t launch_exposed_flags(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t own_lo,
                                  uint32_t own_hi, uint32_t* flag, cudaStream_t st);
 cudaError_t launch_mesh(bool emit, const MeshArgs& a, uint32_t grid, cudaStream_t st);

@@ -22,7 +22,6 @@ namespace ivx {
 
 constexpr int MESH_THREADS = 256;
 constexpr int N_CUBES = 17 * 17 * 17;
-constexpr int MQ_CAP = 384;  // queued multi-material quads per tile of 256 vertices; the rest are handled in place
 constexpr int CUBES_PER_THREAD = (N_CUBES + MESH_THREADS - 1) / MESH_THREADS;  // 20
 
 // SurfaceNetsVertexMaterials (surface_nets.rs:440-451) packed into registers: byte q of `idx` / `wgt` is
@@ -34,13 +33,14 @@ struct VertexMaterials {
 __device__ __forceinline__ uint32_t byte_of(uint64_t v, int q) { return (uint32_t)(v >> (8 * q)) & 0xFFu; }
 
 // SurfaceNetsVertexMaterials::compute + sort_descending (surface_nets.rs:453-538)
-__device__ __noinline__ VertexMaterials vertex_materials(uint32_t neg_mask, const uint8_t* s_type, int lin) {
+// `types`: byte c = voxel type at cube corner c (CUBE_CORNERS order, surface_nets.rs:639-648)
+__device__ __noinline__ VertexMaterials vertex_materials(uint32_t neg_mask, uint64_t types) {
     uint64_t idx = 0, wgt = 0;
     int count = 0;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         if ((neg_mask >> c) & 1u) {
-            const uint32_t m = s_type[lin + ((c >> 2) & 1) * 324 + ((c >> 1) & 1) * 18 + (c & 1)];
+            const uint32_t m = (uint32_t)(types >> (8 * c)) & 0xFFu;
             int found = -1;
 #pragma unroll
             for (int q = 0; q < 7; ++q)
@@ -148,19 +148,23 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return woff + x - v;
 }
 
+// what the material merge needs of one surface vertex: the signs and voxel types of its cube's 8 corners
+__device__ __forceinline__ void vertex_corner_data(int lin, const uint32_t* s_neg, const uint8_t* s_type, uint32_t& neg,
+                                                   uint64_t& types) {
+    const int r = (lin / 324) * 18 + (lin / 18) % 18, k = lin % 18;
+    neg = ((s_neg[r] >> k) & 3u) | (((s_neg[r + 1] >> k) & 3u) << 2) | (((s_neg[r + 18] >> k) & 3u) << 4) |
+          (((s_neg[r + 19] >> k) & 3u) << 6);
+    types = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) types |= (uint64_t)s_type[lin + corner_off(c)] << (8 * c);
+}
+
 // index materials of the two triangles of a quad whose corner vertices carry several materials
 // (calculate_all_index_materials, surface_nets.rs:540-637, slow path)
-__device__ __forceinline__ void emit_quad_materials(const uint32_t vid[4], uint32_t order, const uint16_t* s_surf,
-                                                    const uint32_t* s_neg, const uint8_t* s_type, uint64_t* IM) {
+__device__ __forceinline__ void emit_quad_materials(const uint32_t neg[4], const uint64_t types[4], uint32_t order, uint64_t* IM) {
     VertexMaterials vm[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int l = s_surf[vid[c]];
-        const int r = (l / 324) * 18 + (l / 18) % 18, k = l % 18;
-        const uint32_t neg = ((s_neg[r] >> k) & 3u) | (((s_neg[r + 1] >> k) & 3u) << 2) |
-                             (((s_neg[r + 18] >> k) & 3u) << 4) | (((s_neg[r + 19] >> k) & 3u) << 6);
-        vm[c] = vertex_materials(neg, s_type, l);
-    }
+    for (int c = 0; c < 4; ++c) vm[c] = vertex_materials(neg[c], types[c]);
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         VertexMaterials tv[3];
@@ -176,23 +180,32 @@ __device__ __forceinline__ void emit_quad_materials(const uint32_t vid[4], uint3
     }
 }
 
+// One thread per recorded multi-material quad. Entry layout (3 x uint4): types of the four vertices' cube corners
+// (4 x u64), then {first index of the quad in the object's index buffer, corner order | neg masks, -, -}.
+__global__ void __launch_bounds__(128) k_mesh_materials(const uint4* __restrict__ entries, const uint32_t* __restrict__ count,
+                                                         uint32_t capacity, ivx_index_materials* __restrict__ index_materials) {
+    const uint32_t n = min(*count, capacity);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint4 a = entries[3 * (size_t)e], b = entries[3 * (size_t)e + 1], c = entries[3 * (size_t)e + 2];
+        const uint64_t types[4] = {(uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
+                                   (uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32)};
+        const uint32_t neg[4] = {c.z & 0xFFu, (c.z >> 8) & 0xFFu, (c.z >> 16) & 0xFFu, c.z >> 24};
+        emit_quad_materials(neg, types, c.y, reinterpret_cast<uint64_t*>(index_materials + c.x));
+    }
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
     __shared__ __align__(16) int8_t s_sd[5832];
     __shared__ __align__(16) uint8_t s_type[EMIT ? 5832 : 16];
     __shared__ __align__(4) uint16_t s_l2v[EMIT ? 5832 : 2];
     __shared__ uint32_t s_neg[324];
-    // multi-material quads of one tile of 256 vertices (<= 3 each): index position | corner order << 14, vertex ids
-    __shared__ uint32_t s_mq_head[EMIT ? MQ_CAP : 1];
-    __shared__ ushort4 s_mq_vid[EMIT ? MQ_CAP : 1];
-    __shared__ uint32_t s_mq_count;
     __shared__ uint16_t s_surf[N_CUBES];
     __shared__ uint8_t s_vmat[EMIT ? N_CUBES : 1];
     __shared__ uint32_t s_warp[MESH_THREADS / 32];
     __shared__ uint32_t s_adj_up[3];
 
     const int tid = threadIdx.x;
-    if (tid == 0) s_mq_count = 0;
     for (uint32_t w = blockIdx.x; w < a.n_work; w += gridDim.x) {
         const uint32_t chunk = a.work[w];
         const uint32_t ck = chunk % a.nb[2], cj = (chunk / a.nb[2]) % a.nb[1], ci = chunk / (a.nb[2] * a.nb[1]);
@@ -453,34 +466,26 @@ __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
 #pragma unroll
                         for (int c = 0; c < 6; ++c) IM[c] = im;
                     } else {
-                        // several materials meet here: queued, and worked off below by dense lanes instead of by the
-                        // few lanes of this warp that happen to sit on a material boundary
-                        const uint32_t e = atomicAdd(&s_mq_count, 1u);
-                        if (e < MQ_CAP) {
-                            s_mq_head[e] = qi | (order << 14);
-                            s_mq_vid[e] = make_ushort4((unsigned short)vid[0], (unsigned short)vid[1], (unsigned short)vid[2],
-                                                       (unsigned short)vid[3]);
+                        // several materials meet here: the quad is recorded and finished by k_mesh_materials with one
+                        // thread per quad, instead of by the few lanes of this warp that sit on a material boundary
+                        uint32_t neg4[4];
+                        uint64_t types4[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) vertex_corner_data(cl[c], s_neg, s_type, neg4[c], types4[c]);
+                        const uint32_t e = atomicAdd(a.mq_count, 1u);
+                        if (e < a.mq_capacity) {
+                            uint4* dst = a.mq_entries + 3 * (size_t)e;
+                            dst[0] = make_uint4((uint32_t)types4[0], (uint32_t)(types4[0] >> 32), (uint32_t)types4[1], (uint32_t)(types4[1] >> 32));
+                            dst[1] = make_uint4((uint32_t)types4[2], (uint32_t)(types4[2] >> 32), (uint32_t)types4[3], (uint32_t)(types4[3] >> 32));
+                            dst[2] = make_uint4(ioff + 6u * qi, order, neg4[0] | (neg4[1] << 8) | (neg4[2] << 16) | (neg4[3] << 24), 0u);
                         } else {
-                            emit_quad_materials(vid, order, s_surf, s_neg, s_type, IM);  // queue full: in place
+                            emit_quad_materials(neg4, types4, order, IM);  // no room: in place
                         }
                     }
                     qi++;
                 }
             }
             n_quads += tile_total;
-            if (EMIT && !skip_emit) {
-                __syncthreads();
-                const uint32_t n_mq = min(s_mq_count, (uint32_t)MQ_CAP);
-                for (uint32_t e = tid; e < n_mq; e += MESH_THREADS) {
-                    const uint32_t head = s_mq_head[e];
-                    const ushort4 v4 = s_mq_vid[e];
-                    const uint32_t vid[4] = {v4.x, v4.y, v4.z, v4.w};
-                    emit_quad_materials(vid, head >> 14, s_surf, s_neg, s_type,
-                                        reinterpret_cast<uint64_t*>(a.index_materials + (size_t)ioff + 6 * (size_t)(head & 0x3FFFu)));
-                }
-                __syncthreads();
-                if (tid == 0) s_mq_count = 0;
-            }
         }
 
         if (!EMIT) {
@@ -530,6 +535,14 @@ cudaError_t launch_exposed_flags(const DevChunk* chunks, uint32_t n, const uint3
                                  uint32_t own_hi, uint32_t* flag, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     k_exposed_flags<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), own_lo, own_hi, flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh_materials(const uint4* entries, const uint32_t* count, uint32_t capacity,
+                                  ivx_index_materials* index_materials, cudaStream_t st) {
+    if (capacity == 0) return cudaSuccess;
+    // the count lives on the device: a fixed grid-stride launch (the bulk of the surface has one material)
+    k_mesh_materials<<<148 * 4, 128, 0, st>>>(entries, count, capacity, index_materials);
     return cudaGetLastError();
 }
 
