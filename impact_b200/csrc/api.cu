@@ -134,6 +134,24 @@ namespace {
 #ifndef IVX_STREAM_PARTS
 #define IVX_STREAM_PARTS 16u  // at most this many parts of at least 3 chunk planes
 #endif
+// events that are destroyed on every exit path
+struct EventList {
+    std::vector<cudaEvent_t> ev;
+    ~EventList() {
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+    cudaError_t create(size_t n) {
+        ev.assign(n, nullptr);
+        for (auto& e : ev) {
+            cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            if (rc != cudaSuccess) return rc;
+        }
+        return cudaSuccess;
+    }
+    cudaEvent_t operator[](size_t i) const { return ev[i]; }
+};
+
 // host destination of a streamed generation (ivx_object_generate_streamed)
 struct StreamOut {
     ivx_chunk_desc* h_chunks;
@@ -408,7 +426,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     uint32_t* pk_flag = nullptr;
     uint32_t* pk_ord = nullptr;
     uint32_t* part_counts = counters + 44;  // [P] NonUniform chunks per packed plane range
-    std::vector<cudaEvent_t> part_done;
+    EventList part_done;
     std::vector<uint32_t> part_lo(P), part_hi(P);
     if (so) {
         if (so->chunk_capacity < n) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u chunk descriptors", n);
@@ -419,17 +437,15 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
         if (!obj->d_stage_voxels || !obj->d_stage_chunks || !pk_flag || !pk_ord)
             IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "streamed generation: out of device memory");
         CU(ctx, cudaMemsetAsync(part_counts, 0, 16 * sizeof(uint32_t), st));
-        part_done.resize(P);
-        for (auto& e : part_done) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(ctx, part_done.create(P));
     }
     // Streamed: the evaluation of all parts runs ahead on the compute stream while typing, cross-chunk state and
     // packing of each evaluated part follow on a second, higher-priority compute stream, so the tail of one kernel
     // is filled by the CTAs of the other instead of idling eight times.
     cudaStream_t st2 = so ? ctx->aux_stream : st;
-    std::vector<cudaEvent_t> evaluated;
+    EventList evaluated;
     if (so) {
-        evaluated.resize(P);
-        for (auto& e : evaluated) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(ctx, evaluated.create(P));
     }
     for (uint32_t q = 0; q < P; ++q) {
         const uint32_t cnt = ab[q + 1] - ab[q];
@@ -482,7 +498,6 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     }
     if (so) {
         CU(ctx, cudaStreamWaitEvent(st, part_done[P - 1], 0));  // later work on the compute stream sees the finished object
-        for (auto& e : evaluated) cudaEventDestroy(e);
     }
     if (so) {
         // the host follows the parts as they finish and queues their transfers; the compute stream never waits
@@ -507,7 +522,6 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
             }
             if (e != cudaSuccess && rc == IVX_OK) rc = IVX_ERR_CUDA;
         }
-        for (auto& e : part_done) cudaEventDestroy(e);
         if (rc == IVX_ERR_CAPACITY) IVX_FAIL(ctx, rc, "streamed generation: voxel buffer too small");
         if (rc != IVX_OK) IVX_FAIL(ctx, rc, "streamed generation: %s", cudaGetErrorString(cudaGetLastError()));
         so->n_non_uniform = base;
