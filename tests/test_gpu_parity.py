@@ -8,6 +8,7 @@ import pytest
 import helpers as H
 from impact_b200 import workloads as W
 import invariants as INV
+from impact_b200.graph import VoxelTypeGenerator
 from impact_b200.voxel import SDFVoxelGenerator, VoxelObject, VoxelObjectMesh
 
 pytestmark = pytest.mark.gpu
@@ -83,6 +84,26 @@ def test_generated_object_and_mesh_are_bit_exact(ctx, oracle, name):
     INV.validate_occupied_voxel_ranges(gch, gvx, gi["chunk_counts"], gi["occupied_voxel_ranges"])
     mesh = VoxelObjectMesh.create(obj_gpu)
     H.assert_meshes_equal(mesh.download(), obj_cpu.mesh(4))
+
+
+@pytest.mark.parametrize("label,types", [
+    ("one_type", VoxelTypeGenerator.gradient_noise([5], 0.02, 1.0, 0)),
+    ("nine_types_seeded", VoxelTypeGenerator.gradient_noise(list(range(9)), 0.031, 0.37, 12345)),
+    # 70 types: their lattice tables do not fit one batch; type coordinates beyond the first 8-wide vector
+    ("seventy_types", VoxelTypeGenerator.gradient_noise(list(range(70)), 0.02, 1.0, 3)),
+    # noise cells much smaller than a chunk: the gradient table does not fit, the direct evaluation runs
+    ("high_frequency", VoxelTypeGenerator.gradient_noise([0, 1, 2, 3, 4], 0.9, 1.0, 1)),
+    ("medium_frequency", VoxelTypeGenerator.gradient_noise([0, 1, 2], 0.21, 2.5, 7)),
+])
+def test_voxel_type_generators_are_bit_exact(ctx, oracle, label, types):
+    # voxel_type.rs:54-168: every path of k_types (one batch, several batches, direct evaluation)
+    g = H.sphere_graph(21.0)
+    _, _, _, obj_gpu, obj_cpu = _both(ctx, oracle, g, types)
+    gch, gvx = obj_gpu.download()
+    H.assert_objects_equal(gch, gvx, obj_cpu.chunks(), obj_cpu.voxels())
+    if label != "one_type":
+        assert len(np.unique(gvx["type"][(gvx["flags"] & 1) == 0])) > 1
+    H.assert_meshes_equal(VoxelObjectMesh.create(obj_gpu).download(), obj_cpu.mesh(4))
 
 
 def test_voxel_extent_scales_positions_only(ctx, oracle):
