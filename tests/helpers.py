@@ -197,3 +197,48 @@ def euler_characteristic(positions: np.ndarray, indices: np.ndarray, weld=1e3):
     ue, cnt = np.unique(edges, axis=0, return_counts=True)
     v = len(np.unique(inv))
     return v - len(ue) + len(tris), np.bincount(cnt)
+
+
+# ---- canonical digests (tests/golden/object_digests.json) ----------------------------------------------
+
+def object_digest(chunks, voxels) -> str:
+    """sha256 over a canonical serialisation of a voxel object: chunk kinds, flags / face distributions of NonUniform
+    chunks, uniform voxels of Uniform chunks, and the voxels of the NonUniform chunks in linear chunk order (the
+    reference's own data_offset depends on traversal order, so it is not hashed)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    kind = np.ascontiguousarray(chunks["kind"], np.uint8)
+    h.update(kind.tobytes())
+    nu, un = kind == 2, kind == 1
+    h.update(np.ascontiguousarray(chunks["flags"][nu], np.uint8).tobytes())
+    h.update(np.ascontiguousarray(chunks["face"][nu], np.uint8).tobytes())
+    for f in ("uniform_type", "uniform_sd", "uniform_flags"):
+        h.update(np.ascontiguousarray(chunks[f][un]).tobytes())
+    if nu.any():
+        v = voxels.reshape(-1, 4096)[chunks["data_offset"][nu]]
+        for f in ("type", "sd", "flags"):
+            h.update(np.ascontiguousarray(v[f]).tobytes())
+    return h.hexdigest()
+
+
+def mesh_digest(positions, normals, indices, index_materials, submeshes, vertex_ranges) -> str:
+    """sha256 over the mesh buffers in the reference's order (f32 as bits)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for a in (np.ascontiguousarray(positions, np.float32), np.ascontiguousarray(normals, np.float32),
+              np.ascontiguousarray(indices, np.uint32), np.ascontiguousarray(index_materials),
+              np.ascontiguousarray(submeshes), np.ascontiguousarray(vertex_ranges, np.uint32)):
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+GOLDEN_OBJECTS = {
+    "sphere64": (lambda: sphere_graph(31.0), "SAME0"),
+    "zoo": (csg_zoo_graph, "GRADIENT4"),
+    "asteroid_like": (lambda: asteroid_like_graph(24, 40.0), "GRADIENT4"),
+    "mid_noise": (mid_noise_graph, "SAME0"),
+    "noisy_box": (lambda: noisy_box_graph(38.0, 8), "SAME0"),
+}
+

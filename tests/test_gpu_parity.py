@@ -106,6 +106,25 @@ def test_voxel_type_generators_are_bit_exact(ctx, oracle, label, types):
     H.assert_meshes_equal(VoxelObjectMesh.create(obj_gpu).download(), obj_cpu.mesh(4))
 
 
+@pytest.mark.parametrize("name", sorted(H.GOLDEN_OBJECTS))
+def test_cuda_objects_match_the_committed_digests(ctx, name):
+    # the same committed fixtures the oracle is frozen by (tests/golden/object_digests.json), without the oracle in
+    # the loop: chunk table, every voxel, and the mesh buffers in the reference's order
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "object_digests.json")) as f:
+        want = json.load(f)[name]
+    make, types_name = H.GOLDEN_OBJECTS[name]
+    obj = VoxelObject.generate(SDFVoxelGenerator(1.0, ctx.build_generator(make()), getattr(H, types_name)))
+    assert list(obj.info()["chunk_counts"]) == want["chunk_counts"]
+    assert H.object_digest(*obj.download()) == want["object"]
+    m = VoxelObjectMesh.create(obj).download()
+    assert (len(m["positions"]), len(m["indices"])) == (want["vertices"], want["indices"])
+    assert H.mesh_digest(m["positions"], m["normals"], m["indices"], m["index_materials"], m["submeshes"],
+                         m["vertex_ranges"]) == want["mesh"]
+
+
 def test_voxel_extent_scales_positions_only(ctx, oracle):
     _, _, _, obj_gpu, obj_cpu = _both(ctx, oracle, H.complex_graph(0.4), H.SAME0, extent=0.25)
     gch, gvx = obj_gpu.download()
