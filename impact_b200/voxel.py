@@ -278,6 +278,24 @@ class VoxelObject:
                                                                C.c_float(influence_radius), C.byref(st)))
         return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
 
+    def inertial_moments(self, voxel_type_densities, initial=None, per_chunk: bool = False):
+        """`compute_inertial_property_moments_for_object` (object/inertia.rs:754-789) → 10 f32: mass, moments[3],
+        moments_of_inertia[3], products_of_inertia[3] about the grid origin, bit for bit the reference's sums.
+        `initial` continues another slab's sums (multi-GPU); `per_chunk` also returns the (n_owned_chunks, 10) terms."""
+        dens = np.ascontiguousarray(voxel_type_densities, np.float32)
+        out = np.zeros(10, np.float32)
+        init = None if initial is None else np.ascontiguousarray(initial, np.float32)
+        assert init is None or init.shape == (10,)
+        pc = None
+        if per_chunk:
+            inf = self.info()
+            n = (inf["chunk_i_end"] - inf["chunk_i_begin"]) * inf["chunk_counts"][1] * inf["chunk_counts"][2]
+            pc = np.zeros((n, 10), np.float32)
+        self.ctx.check(self.ctx._lib.ivx_object_inertial_moments(
+            self.ctx.h, self.h, L.ptr(dens), C.c_uint32(len(dens)), L.ptr(init) if init is not None else None,
+            L.ptr(out), L.ptr(pc) if per_chunk else None, C.c_size_t(len(pc) if per_chunk else 0)))
+        return (out, pc) if per_chunk else out
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113) → (info dict, extracted VoxelObject or
         None). This object is modified in place."""

@@ -430,6 +430,31 @@ typedef struct ivx_extraction_info {
 int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* object, ivx_extraction_info* out_info,
                                            ivx_object** out_extracted);
 
+/* ---- inertial properties ----------------------------------------------------
+ * `VoxelObjectInertialPropertyManager` (object/inertia.rs:19-25): mass, moments (m x, m y, m z), moments of inertia
+ * (diagonal of the inertia tensor) and products of inertia (m x y, m y z, m z x) integrated over the non-empty voxels
+ * with respect to the origin of the voxel grid.
+ * ivx_object_inertial_moments replaces VoxelObjectInertialPropertyManager::initialized_from (inertia.rs:125-137 →
+ * compute_inertial_property_moments_for_object :754-789, compute_moments_for_non_uniform_chunk :629-706,
+ * compute_moments_for_uniform_chunk :710-752) and returns the same f32 bits: the additions are made in the reference's
+ * order (voxels i → j → k inside a chunk, chunk terms in linear chunk order).
+ *   voxel_type_densities[n_densities]  mass density per voxel type (a non-empty voxel whose type has none is
+ *                                      IVX_ERR_INVALID_ARGUMENT; the reference panics on the slice index)
+ *   initial            NULL, or the sums to continue from: a slab object (multi-GPU) sums only its own chunk planes, so
+ *                      passing rank r-1's result to rank r reproduces the whole object's chain exactly
+ *   per_chunk_terms    NULL, or room for ten floats per owned chunk in linear chunk order (zero for void chunks)
+ * The derived quantities (centre of mass, inertia tensor about it: derive_inertial_properties, inertia.rs:160-167)
+ * are a handful of host flops on these ten numbers and stay with the host. */
+typedef struct ivx_inertial_moments {
+    float mass;
+    float moments[3];
+    float moments_of_inertia[3];
+    float products_of_inertia[3];
+} ivx_inertial_moments;
+int ivx_object_inertial_moments(ivx_ctx* ctx, const ivx_object* object, const float* voxel_type_densities,
+                                uint32_t n_densities, const ivx_inertial_moments* initial, ivx_inertial_moments* out,
+                                float* per_chunk_terms, size_t per_chunk_capacity);
+
 #ifdef __cplusplus
 }
 #endif

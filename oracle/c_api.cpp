@@ -336,6 +336,40 @@ void orc_absorb_capsule(void* op, const float start[3], const float vec[3], floa
                    influence_radius, stats);
 }
 
+// ---- inertial properties (object/inertia.rs); moments = 10 f32: mass, moments[3], moments_of_inertia[3], products[3] ----
+static_assert(sizeof(InertialMoments) == 40, "InertialMoments is 10 packed floats");
+void orc_moments_for_voxel(float e, const float* densities, const uint32_t ijk[3], uint8_t type, float out[10]) {
+    moments_for_voxel(e, e * e, (e * e) * e, densities, ijk, type, *(InertialMoments*)out);
+}
+void orc_moments_for_non_uniform_chunk(float e, const Voxel* voxels, const float* densities, const uint32_t cc[3],
+                                       float out[10]) {
+    moments_for_non_uniform_chunk(e, voxels, densities, cc, *(InertialMoments*)out);
+}
+void orc_moments_for_uniform_chunk(float e, const float* densities, uint8_t type, const uint32_t cc[3], float out[10]) {
+    moments_for_uniform_chunk(e, densities, type, cc, *(InertialMoments*)out);
+}
+// per_chunk: NULL or 10 floats per chunk of the grid (zero for chunks that contribute nothing)
+void orc_object_inertial_moments(const void* op, const float* densities, float out[10], float* per_chunk) {
+    const Object& o = *(const Object*)op;
+    if (per_chunk) std::memset(per_chunk, 0, o.chunks.size() * sizeof(InertialMoments));
+    inertial_moments_for_object(o, densities, *(InertialMoments*)out, (InertialMoments*)per_chunk);
+}
+// absorption with the inertial-property updater attached (apply_*_absorption, absorption.rs:801-889)
+void orc_absorb_sphere_inertial(void* op, const float center[3], float radius, float influence_radius,
+                                AbsorbStats* stats, const float* densities, float moments[10]) {
+    Object& o = *(Object*)op;
+    InertialUpdater upd((InertialMoments*)moments, o.voxel_extent, densities);
+    absorb_sphere(o, v3(center[0], center[1], center[2]), radius, influence_radius, stats, &upd);
+}
+void orc_absorb_capsule_inertial(void* op, const float start[3], const float vec[3], float radius,
+                                 float influence_radius, AbsorbStats* stats, const float* densities,
+                                 float moments[10]) {
+    Object& o = *(Object*)op;
+    InertialUpdater upd((InertialMoments*)moments, o.voxel_extent, densities);
+    absorb_capsule(o, v3(start[0], start[1], start[2]), v3(vec[0], vec[1], vec[2]), radius, influence_radius, stats,
+                   &upd);
+}
+
 // ---- connected regions ----
 // Runs the whole detection on the object's current state. info (u32 x 24): n_regions, has_two, two[0], two[1],
 // smallest, overflow, n_region_entries, n_label_bytes, then per candidate region 8 words: chunk_count,

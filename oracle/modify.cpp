@@ -84,7 +84,7 @@ bool trim_capsule(const Shape& s, const uint32_t cc[3], V3& t_start, V3& t_vec) 
     return true;
 }
 
-void absorb_shape(Object& obj, const Shape& shape, AbsorbStats* stats) {
+void absorb_shape(Object& obj, const Shape& shape, AbsorbStats* stats, InertialUpdater* updater) {
     AbsorbStats st{0, 0, 0, 0};
     const V3 center = shape.start;
     const float radius = shape.radius, influence_radius = shape.influence_radius;
@@ -185,7 +185,15 @@ void absorb_shape(Object& obj, const Shape& shape, AbsorbStats* stats) {
                                 vx.sd = sd_encode(nsd);
                                 if (!(vx.sd < 0)) {
                                     vx.flags |= FLAG_EMPTY;
-                                    if (!was_empty) st.emptied_voxels++;
+                                    if (!was_empty) {
+                                        st.emptied_voxels++;
+                                        // the closure's callback (absorption.rs:836-840): remove_voxel with the
+                                        // object voxel indices and the voxel's (unchanged) type
+                                        if (updater) {
+                                            const uint32_t ijk[3] = {i, j, k};
+                                            updater->remove_voxel(ijk, vx.type);
+                                        }
+                                    }
                                 }
                                 st.touched_voxels++;
                                 touched = true;
@@ -229,13 +237,14 @@ void absorb_shape(Object& obj, const Shape& shape, AbsorbStats* stats) {
 
 }  // namespace
 
-void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius, AbsorbStats* stats) {
-    absorb_shape(obj, Shape{false, center, v3(0.0f, 0.0f, 0.0f), radius, influence_radius}, stats);
+void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius, AbsorbStats* stats,
+                   InertialUpdater* updater) {
+    absorb_shape(obj, Shape{false, center, v3(0.0f, 0.0f, 0.0f), radius, influence_radius}, stats, updater);
 }
 
 void absorb_capsule(Object& obj, V3 segment_start, V3 segment_vector, float radius, float influence_radius,
-                    AbsorbStats* stats) {
-    absorb_shape(obj, Shape{true, segment_start, segment_vector, radius, influence_radius}, stats);
+                    AbsorbStats* stats, InertialUpdater* updater) {
+    absorb_shape(obj, Shape{true, segment_start, segment_vector, radius, influence_radius}, stats, updater);
 }
 
 }  // namespace orc

@@ -9,6 +9,7 @@
 //   object/sdf/surface_nets.rs, mesh.rs)
 //   sphere absorption + dirty-chunk bookkeeping (object/intersection.rs,
 //   interaction/absorption.rs)
+//   inertial moments of an object and their incremental update (object/inertia.rs)
 // Paths are relative to /root/reference/engine/crates/impact_voxel/src/.
 //
 // PARITY PINNING: the reference is Rust and cannot be built or run here (no
@@ -279,6 +280,35 @@ void mesh_object(const Object& obj, Mesh& mesh, int n_threads = 1);
 bool mesh_chunk(const Object& obj, uint32_t ci, uint32_t cj, uint32_t ck, ChunkMesh& cm,
                 uint8_t* chunk_flags);
 
+// --- inertial properties (object/inertia.rs) ----------------------------------
+// VoxelObjectInertialPropertyManager (inertia.rs:19-25): mass, moments (m x), moments of inertia, products of inertia,
+// all with respect to the origin of the voxel grid.
+struct InertialMoments {
+    float mass = 0.0f;
+    float moments[3] = {0, 0, 0};
+    float moi[3] = {0, 0, 0};
+    float poi[3] = {0, 0, 0};
+};
+void moments_for_voxel(float e, float e2, float e3, const float* densities, const uint32_t ijk[3], uint8_t type,
+                       InertialMoments& out);
+void moments_for_non_uniform_chunk(float e, const Voxel* voxels, const float* densities, const uint32_t cc[3],
+                                   InertialMoments& out);
+void moments_for_uniform_chunk(float e, const float* densities, uint8_t type, const uint32_t cc[3],
+                               InertialMoments& out);
+// initialized_from (inertia.rs:125-137); per_chunk (optional, one per chunk of the grid) receives the chunk terms
+void inertial_moments_for_object(const Object& obj, const float* densities, InertialMoments& out,
+                                 InertialMoments* per_chunk);
+// VoxelObjectInertialPropertyUpdater (inertia.rs:27-35, 174-189, 374-395)
+struct InertialUpdater {
+    InertialMoments* parent;
+    const float* densities;
+    float e, e2, e3;
+    uint64_t removed = 0;
+    InertialUpdater(InertialMoments* p, float voxel_extent, const float* dens)
+        : parent(p), densities(dens), e(voxel_extent), e2(voxel_extent * voxel_extent), e3(e2 * voxel_extent) {}
+    void remove_voxel(const uint32_t ijk[3], uint8_t type);
+};
+
 // --- modification (object/intersection.rs, interaction/absorption.rs) --------
 struct AbsorbStats {
     uint32_t touched_chunks;
@@ -289,10 +319,10 @@ struct AbsorbStats {
 // apply_sphere_absorption restricted to the voxel-object side: influence sphere
 // (centre, influence_radius) and absorbing radius, all in normalized voxel space.
 void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius,
-                   AbsorbStats* stats);
+                   AbsorbStats* stats, InertialUpdater* updater = nullptr);
 // apply_capsule_absorption likewise: influence capsule (segment start, segment vector, influence_radius)
 void absorb_capsule(Object& obj, V3 segment_start, V3 segment_vector, float radius, float influence_radius,
-                    AbsorbStats* stats);
+                    AbsorbStats* stats, InertialUpdater* updater = nullptr);
 
 // --- connected regions (object/split_detection.rs, object/extraction.rs:121-281) ---
 struct ChunkRegions {

@@ -259,6 +259,38 @@ class Object:
         return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
                 "removed_chunks": int(st[3])}
 
+    def inertial_moments(self, densities, per_chunk: bool = False):
+        """VoxelObjectInertialPropertyManager::initialized_from (inertia.rs:125-137) → 10 f32: mass, moments[3],
+        moments_of_inertia[3], products_of_inertia[3] (and the per-chunk terms, one row per chunk of the grid)."""
+        dens = _densities(densities)
+        out = np.zeros(10, np.float32)
+        pc = np.zeros((len(self.chunks()), 10), np.float32) if per_chunk else None
+        lib().orc_object_inertial_moments(self.h, _p(dens), _p(out), _p(pc) if per_chunk else None)
+        return (out, pc) if per_chunk else out
+
+    def absorb_sphere_inertial(self, center, radius: float, influence_radius: float, densities, moments):
+        """apply_sphere_absorption with its VoxelObjectInertialPropertyUpdater (absorption.rs:801-844): `moments`
+        (10 f32) is updated in place, voxel by voxel in the reference's visiting order."""
+        center = np.asarray(center, np.float32)
+        dens = _densities(densities)
+        assert moments.dtype == np.float32 and moments.shape == (10,)
+        st = np.zeros(4, np.uint32)
+        lib().orc_absorb_sphere_inertial(self.h, _p(center), C.c_float(radius), C.c_float(influence_radius), _p(st),
+                                         _p(dens), _p(moments))
+        return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
+                "removed_chunks": int(st[3])}
+
+    def absorb_capsule_inertial(self, segment_start, segment_vector, radius: float, influence_radius: float, densities,
+                                moments):
+        a, v = np.asarray(segment_start, np.float32), np.asarray(segment_vector, np.float32)
+        dens = _densities(densities)
+        assert moments.dtype == np.float32 and moments.shape == (10,)
+        st = np.zeros(4, np.uint32)
+        lib().orc_absorb_capsule_inertial(self.h, _p(a), _p(v), C.c_float(radius), C.c_float(influence_radius), _p(st),
+                                          _p(dens), _p(moments))
+        return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
+                "removed_chunks": int(st[3])}
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113): → (info, extracted Object or None).
         This object is modified in place (the region's voxels leave it)."""
@@ -334,6 +366,39 @@ def index_materials(vms):
     out = np.zeros(24, np.uint8)
     lib().orc_index_materials(_p(buf), _p(out))
     return [(out[8 * v: 8 * v + 4].copy(), out[8 * v + 4: 8 * v + 8].copy()) for v in range(3)]
+
+
+def _densities(densities) -> np.ndarray:
+    """voxel_type_densities padded to 256 entries so that any u8 type indexes it (the reference would panic)."""
+    d = np.zeros(256, np.float32)
+    d[: len(densities)] = np.asarray(densities, np.float32)
+    return d
+
+
+def moments_for_voxel(voxel_extent: float, densities, ijk, voxel_type: int) -> np.ndarray:
+    """compute_moments_for_voxel (inertia.rs:591-625)."""
+    out = np.zeros(10, np.float32)
+    lib().orc_moments_for_voxel(C.c_float(voxel_extent), _p(_densities(densities)), _p(np.asarray(ijk, np.uint32)),
+                                C.c_uint8(voxel_type), _p(out))
+    return out
+
+
+def moments_for_non_uniform_chunk(voxel_extent: float, voxels: np.ndarray, densities, chunk_indices) -> np.ndarray:
+    """compute_moments_for_non_uniform_chunk (inertia.rs:629-706); voxels: 4096 x VOXEL_DTYPE."""
+    assert voxels.dtype == VOXEL_DTYPE and len(voxels) == 4096
+    out = np.zeros(10, np.float32)
+    lib().orc_moments_for_non_uniform_chunk(C.c_float(voxel_extent), _p(np.ascontiguousarray(voxels)),
+                                            _p(_densities(densities)), _p(np.asarray(chunk_indices, np.uint32)),
+                                            _p(out))
+    return out
+
+
+def moments_for_uniform_chunk(voxel_extent: float, densities, voxel_type: int, chunk_indices) -> np.ndarray:
+    """compute_moments_for_uniform_chunk (inertia.rs:710-752)."""
+    out = np.zeros(10, np.float32)
+    lib().orc_moments_for_uniform_chunk(C.c_float(voxel_extent), _p(_densities(densities)), C.c_uint8(voxel_type),
+                                        _p(np.asarray(chunk_indices, np.uint32)), _p(out))
+    return out
 
 
 def sd_encode(v: float) -> int:
