@@ -851,7 +851,7 @@ int ivx_synchronize(ivx_ctx* ctx) {
 static void drain_profile(ivx_ctx* ctx) {
     for (auto& e : ctx->prof_events) {
         float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.id < 8) {
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.id < 12) {
             ctx->prof_ms[e.id] += ms;
             ctx->prof_launches[e.id] += 1;
         }
@@ -872,14 +872,14 @@ int ivx_profile_reset(ivx_ctx* ctx) {
     if (!ctx) return IVX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     drain_profile(ctx);
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 12; ++i) {
         ctx->prof_ms[i] = 0;
         ctx->prof_launches[i] = 0;
     }
     return IVX_OK;
 }
 int ivx_profile_get(ivx_ctx* ctx, uint32_t kernel_id, double* out_total_ms, uint64_t* out_launches) {
-    if (!ctx || kernel_id >= 8) return IVX_ERR_INVALID_ARGUMENT;
+    if (!ctx || kernel_id >= 12) return IVX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     drain_profile(ctx);
     if (out_total_ms) *out_total_ms = ctx->prof_ms[kernel_id];

@@ -38,8 +38,8 @@ struct ivx_ctx {
     bool profiling = false;
     struct ProfEvent { cudaEvent_t a, b; uint32_t id; };
     std::vector<ProfEvent> prof_events;
-    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double prof_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t prof_launches[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t* h_pinned = nullptr;  // 64 words of pinned scratch for counter read-back
     uint32_t* h_pinned_dev = nullptr;  // the same words as the device sees them (mapped): counters are stored by a
                                        // kernel, not by the copy engine, which may be busy with a bulk transfer

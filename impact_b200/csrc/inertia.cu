@@ -10,15 +10,19 @@
 // The reference's result is a chain of f32 additions in a fixed order (voxels i → j → k inside a chunk, chunks
 // i → j → k over the occupied range), and f32 addition does not reassociate. To return the same bits, the order
 // is kept and the parallelism is taken across chains instead of inside them:
-//   k_moments_classify     one thread per chunk: closed form for uniform chunks, zero for void ones, non-uniform
-//                          chunks appended to a work list;
+//   k_moments_flags + scan every non-void chunk gets a row, rows in linear chunk order (void chunks add nothing to the
+//                          reference's sums: they get no row);
+//   k_moments_classify     one thread per chunk: closed form for uniform chunks, non-uniform chunks appended to a
+//                          work list;
 //   k_moments_non_uniform  one thread per non-uniform chunk walks its 4096 voxels in the reference's order with
 //                          its ten accumulators in registers (the 2 B/voxel it reads are the kernel's HBM
 //                          traffic; ~10^5 independent chains on a 1024^3 object fill the machine);
-//   k_moments_sum          the chunk terms are added in linear chunk order by ten lanes of one warp, one lane per
-//                          component, from shared-memory tiles the rest of the block stages ahead of them. A
-//                          void chunk contributes +0.0, which leaves a partial sum that is not -0.0 unchanged —
-//                          and the partial sums start at +0.0 and can only become -0.0 by adding two -0.0.
+//   k_moments_sum          the rows are added in order by ten lanes of one warp, one lane per component, from
+//                          shared-memory tiles the rest of the block stages ahead of them. The tail of the last tile
+//                          is padded with +0.0, which leaves a partial sum that is not -0.0 unchanged — and the
+//                          partial sums start at +0.0 (or the caller's values) and only become -0.0 by adding two -0.0;
+//                          a caller-provided -0.0 start is kept by not touching the padding at all (the loop stops at
+//                          the row count).
 #include "api_internal.cuh"
 
 namespace ivx {
@@ -35,10 +39,16 @@ struct MomentsArgs {
     uint32_t c_begin, c_end;  // local linear chunk range that is summed (the owned planes)
     float e;            // voxel extent
     uint32_t n_densities;
-    float* part;        // 10 floats per chunk of [c_begin, c_end)
+    float* part;        // 10 floats per non-void chunk of [c_begin, c_end), in linear chunk order
+    const uint32_t* row;  // per chunk of [c_begin, c_end): its row in `part` (exclusive scan of the non-void flags)
     uint32_t* list;     // non-uniform chunks (local linear index)
-    uint32_t* counters; // [0] list length, [1] error: a non-empty voxel type without a density
+    uint32_t* counters; // [0] list length, [1] error: a non-empty voxel type without a density, [2] rows
 };
+
+__global__ void k_moments_flags(const DevChunk* __restrict__ chunks, uint32_t c_begin, uint32_t n, uint32_t* __restrict__ flag) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) flag[t] = chunks[c_begin + t].kind != 0 ? 1u : 0u;
+}
 
 // compute_moments_for_uniform_chunk (inertia.rs:710-752)
 __device__ __forceinline__ void uniform_chunk_moments(float e, float density, const uint32_t cc[3], float out[10]) {
@@ -88,14 +98,13 @@ __global__ void __launch_bounds__(256) k_moments_classify(MomentsArgs a, const _
         a.list[base + __popc(m & ((1u << lane) - 1u))] = c;
         return;
     }
-    float out[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    if (ch.kind == 1) {
-        const uint32_t k = c % a.nb.z, j = (c / a.nb.z) % a.nb.y, i = c / (a.nb.z * a.nb.y) + a.first_i;
-        const uint32_t cc[3] = {i, j, k};
-        if (ch.u_type >= a.n_densities) atomicOr(&a.counters[1], 1u);
-        uniform_chunk_moments(a.e, dens.v[ch.u_type], cc, out);
-    }
-    float* p = a.part + (size_t)(c - a.c_begin) * 10;
+    if (ch.kind != 1) return;
+    float out[10];
+    const uint32_t k = c % a.nb.z, j = (c / a.nb.z) % a.nb.y, i = c / (a.nb.z * a.nb.y) + a.first_i;
+    const uint32_t cc[3] = {i, j, k};
+    if (ch.u_type >= a.n_densities) atomicOr(&a.counters[1], 1u);
+    uniform_chunk_moments(a.e, dens.v[ch.u_type], cc, out);
+    float* p = a.part + (size_t)a.row[c - a.c_begin] * 10;
 #pragma unroll
     for (int q = 0; q < 10; ++q) p[q] = out[q];
 }
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(64) k_moments_non_uniform(MomentsArgs a, const
     if (bad) atomicOr(&a.counters[1], 1u);
     const float e2 = e * e, e3 = e2 * e;
     const float fm = 0.5f * e2, fi = (1.0f / 3.0f) * e2, fp = 0.25f * e;
-    float* p = a.part + (size_t)(c - a.c_begin) * 10;
+    float* p = a.part + (size_t)a.row[c - a.c_begin] * 10;
     p[0] = mass * e3;
     p[1] = m0 * fm;
     p[2] = m1 * fm;
@@ -196,19 +205,22 @@ __global__ void __launch_bounds__(64) k_moments_non_uniform(MomentsArgs a, const
 }
 
 // compute_inertial_property_moments_for_object's outer loop (inertia.rs:769-787): `*mass += chunk_mass` … in linear
-// chunk order. One block: warps 1.. stage the next tile of chunk terms in shared memory while lanes 0-9 of warp 0
-// each extend one component's chain over the current tile.
-constexpr int SUM_TILE = 512;  // chunks per tile: 20 KiB, two tiles in flight
-__global__ void __launch_bounds__(256) k_moments_sum(const float* __restrict__ part, uint32_t n_chunks, const float* initial,
-                                                     float* __restrict__ out) {
+// chunk order. One block: warps 1.. stage the next tile of rows in shared memory while lanes 0-9 of warp 0 each extend
+// one component's chain over the current tile.
+constexpr int SUM_TILE = 512;  // rows per tile: 20 KiB, two tiles in flight
+__global__ void __launch_bounds__(256) k_moments_sum(const float* __restrict__ part, const uint32_t* __restrict__ n_rows_ptr,
+                                                     const float* initial, float* __restrict__ out) {
     __shared__ __align__(16) float s_tile[2][SUM_TILE * 10];
     const int tid = threadIdx.x;
-    const uint32_t n_words = n_chunks * 10u;
-    const uint32_t n_tiles = (n_chunks + SUM_TILE - 1) / SUM_TILE;
+    const uint32_t n_rows = *n_rows_ptr;
+    const uint32_t n_vec = (n_rows * 10u + 3u) / 4u;  // the rows as float4 (the buffer is padded to a multiple of 16 bytes)
+    const uint32_t n_tiles = (n_rows + SUM_TILE - 1) / SUM_TILE;
+    const float4* part4 = reinterpret_cast<const float4*>(part);
     auto stage = [&](uint32_t tile, int first_thread, int n_threads) {
-        const uint32_t w0 = tile * (SUM_TILE * 10u);
-        for (uint32_t w = (uint32_t)(tid - first_thread); w < SUM_TILE * 10u; w += (uint32_t)n_threads)
-            s_tile[tile & 1][w] = (w0 + w < n_words) ? part[w0 + w] : 0.0f;
+        const uint32_t v0 = tile * (SUM_TILE * 10u / 4u);
+        float4* dst = reinterpret_cast<float4*>(s_tile[tile & 1]);
+        for (uint32_t v = (uint32_t)(tid - first_thread); v < SUM_TILE * 10u / 4u; v += (uint32_t)n_threads)
+            if (v0 + v < n_vec) dst[v] = part4[v0 + v];
     };
     if (n_tiles) stage(0, 0, 256);
     __syncthreads();
@@ -218,12 +230,26 @@ __global__ void __launch_bounds__(256) k_moments_sum(const float* __restrict__ p
             if (t + 1 < n_tiles) stage(t + 1, 32, 224);
         } else if (tid < 10) {
             const float* s = s_tile[t & 1] + tid;
-#pragma unroll 16
-            for (int q = 0; q < SUM_TILE; ++q) acc += s[q * 10];
+            const int rows = (int)min((uint32_t)SUM_TILE, n_rows - t * SUM_TILE);
+            if (rows == SUM_TILE) {
+#pragma unroll 32
+                for (int q = 0; q < SUM_TILE; ++q) acc += s[q * 10];
+            } else {
+                for (int q = 0; q < rows; ++q) acc += s[q * 10];
+            }
         }
         __syncthreads();
     }
     if (tid < 10) out[tid] = acc;
+}
+
+// the rows spread back over all chunks (void chunks: zero) for callers that ask for the per-chunk terms
+__global__ void k_moments_scatter(const DevChunk* __restrict__ chunks, uint32_t c_begin, uint32_t n, const uint32_t* __restrict__ row,
+                                  const float* __restrict__ part, float* __restrict__ dense) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 10u) return;
+    const uint32_t c = t / 10u, q = t % 10u;
+    dense[t] = chunks[c_begin + c].kind != 0 ? part[(size_t)row[c] * 10 + q] : 0.0f;
 }
 
 }  // namespace ivx
@@ -264,23 +290,36 @@ int ivx_object_inertial_moments(ivx_ctx* ctx, const ivx_object* obj, const float
     a.c_end = c_end;
     a.e = obj->voxel_extent;
     a.n_densities = n_densities;
-    a.part = tmp.get<float>((size_t)n * 10);
+    a.part = tmp.get<float>((size_t)n * 10 + 4);
     a.list = tmp.get<uint32_t>(n);
+    uint32_t* flag = tmp.get<uint32_t>(n);
+    uint32_t* row = tmp.get<uint32_t>(n);
+    a.row = row;
     float* d_io = tmp.get<float>(32);  // [0..10) initial, [16..26) result
     a.counters = ctx->d_scratch + 48;
-    if (!a.part || !a.list || !d_io) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "inertial moments: out of device memory");
-    CU(ctx, cudaMemsetAsync(a.counters, 0, 8, st));
+    if (!a.part || !a.list || !flag || !row || !d_io) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "inertial moments: out of device memory");
+    CU(ctx, cudaMemsetAsync(a.counters, 0, 12, st));
     CU(ctx, cudaMemcpyAsync(d_io, &start, sizeof(start), cudaMemcpyHostToDevice, st));
-    ctx->launches += 3;
-    k_moments_classify<<<(n + 255) / 256, 256, 0, st>>>(a, dens);
-    CU(ctx, cudaGetLastError());
+    auto prepare = [&]() -> cudaError_t {
+        k_moments_flags<<<(n + 255) / 256, 256, 0, st>>>(a.chunks, c_begin, n, flag);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = launch_exclusive_scan(flag, row, n, a.counters + 2, st);
+        if (e != cudaSuccess) return e;
+        k_moments_classify<<<(n + 255) / 256, 256, 0, st>>>(a, dens);
+        return cudaGetLastError();
+    };
+    ctx->launches += 2;
+    KLP(ctx, 8, prepare());
     // sized for the case that every chunk is non-uniform; threads beyond the list length leave at once
-    k_moments_non_uniform<<<(n + 63) / 64, 64, 0, st>>>(a, dens);
-    CU(ctx, cudaGetLastError());
-    k_moments_sum<<<1, 256, 0, st>>>(a.part, n, d_io, d_io + 16);
-    CU(ctx, cudaGetLastError());
-    if (per_chunk_terms)
-        CU(ctx, cudaMemcpyAsync(per_chunk_terms, a.part, (size_t)n * 40, cudaMemcpyDeviceToHost, st));
+    KLP(ctx, 9, (k_moments_non_uniform<<<(n + 63) / 64, 64, 0, st>>>(a, dens), cudaGetLastError()));
+    KLP(ctx, 10, (k_moments_sum<<<1, 256, 0, st>>>(a.part, a.counters + 2, d_io, d_io + 16), cudaGetLastError()));
+    if (per_chunk_terms) {
+        float* dense = tmp.get<float>((size_t)n * 10);
+        if (!dense) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "inertial moments: out of device memory");
+        KL(ctx, (k_moments_scatter<<<(n * 10 + 255) / 256, 256, 0, st>>>(a.chunks, c_begin, n, row, a.part, dense), cudaGetLastError()));
+        CU(ctx, cudaMemcpyAsync(per_chunk_terms, dense, (size_t)n * 40, cudaMemcpyDeviceToHost, st));
+    }
     uint32_t w[12];
     CU(ctx, cudaMemcpyAsync(d_io + 26, a.counters, 8, cudaMemcpyDeviceToDevice, st));
     if (int rc = ivx_read_words(ctx, reinterpret_cast<const uint32_t*>(d_io + 16), 12, w)) return rc;

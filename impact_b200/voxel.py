@@ -53,7 +53,7 @@ class Context:
         self.check(self._lib.ivx_synchronize(self.h))
 
     KERNEL_IDS = {"fold_conservative": 0, "fold_exact": 1, "eval": 2, "boundary": 3, "mesh_count": 4,
-                  "mesh_emit": 5, "absorb": 6, "types": 7}
+                  "mesh_emit": 5, "absorb": 6, "types": 7, "moments_rows": 8, "moments_non_uniform": 9, "moments_sum": 10}
 
     def profile_enable(self, enabled: bool = True):
         self.check(self._lib.ivx_profile_enable(self.h, C.c_int(1 if enabled else 0)))

@@ -201,7 +201,8 @@ uint64_t ivx_kernel_launch_count(const ivx_ctx* ctx);
 int ivx_synchronize(ivx_ctx* ctx);
 /* Per-kernel device timing with CUDA events on the ctx stream (for bench.py's
  * roofline object). kernel ids: 0 fold (conservative), 1 fold (exact), 2 eval,
- * 3 boundary (classify+apply), 4 mesh count, 5 mesh emit, 6 absorb, 7 voxel types + flags (k_types).
+ * 3 boundary (classify+apply), 4 mesh count, 5 mesh emit, 6 absorb, 7 voxel types + flags (k_types),
+ * 8 inertial moments: rows + uniform chunks, 9 inertial moments: non-uniform chunks, 10 inertial moments: ordered sum.
  * ivx_profile_get synchronises, then returns the accumulated milliseconds and
  * launch count of that kernel since the last reset. */
 int ivx_profile_enable(ivx_ctx* ctx, int enabled);

@@ -131,7 +131,10 @@ def test_full_size_ball_has_a_balls_inertial_properties(ctx):
     r, e, rho = 500.0, 0.1, 2.5
     obj = VoxelObject.generate(SDFVoxelGenerator(e, ctx.build_generator(H.sphere_graph(r)), H.SAME0))
     inf = obj.info()
-    assert inf["n_uniform"] > 90000 and inf["n_non_uniform"] > 8000
+    # chunks inside the sphere's inscribed cube are filled with -margin = -2.54 → code -127, not -128: they are stored
+    # NonUniform like in the reference (atomic.rs:663-668, object.rs:1913-1918); only the shell between the cube and
+    # the surface is Uniform
+    assert inf["n_uniform"] > 60000 and inf["n_non_uniform"] > 50000
     m = I.VoxelObjectInertialPropertyManager.initialized_from(obj, [rho])
     props = m.derive_inertial_properties()
     R = r * e

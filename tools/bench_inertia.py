@@ -35,6 +35,13 @@ def main():
         m2 = obj.inertial_moments(dens)
         ts.append((time.perf_counter() - t0) * 1e3)
     assert np.array_equal(m.view(np.uint32), m2.view(np.uint32)), "not deterministic"
+    # per-kernel device times (CUDA events inside the library, separate passes so the events do not sit in `ts`)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    for _ in range(args.reps):
+        obj.inertial_moments(dens)
+    prof = {k: round(v[0] / args.reps, 4) for k, v in ctx.profile_get().items() if k.startswith("moments")}
+    ctx.profile_enable(False)
     n_chunks = int(np.prod(inf["chunk_counts"]))
     ms = float(np.median(ts))
     # algorithmic bytes: 2 B (type + flags) per voxel of every non-uniform chunk + 16 B descriptor per chunk
@@ -42,7 +49,7 @@ def main():
     print(json.dumps({"workload": args.workload, "grid_shape": list(inf["grid_shape"]), "chunks": n_chunks,
                       "non_uniform": inf["n_non_uniform"], "uniform": inf["n_uniform"], "ms_median": ms,
                       "ms_min": float(min(ts)), "algorithmic_GB": bytes_alg / 1e9,
-                      "GBps": bytes_alg / ms / 1e6, "moments": [float(x) for x in m]}))
+                      "GBps": bytes_alg / ms / 1e6, "kernel_ms": prof, "moments": [float(x) for x in m]}))
 
 
 if __name__ == "__main__":
