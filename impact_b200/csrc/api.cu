@@ -1422,7 +1422,8 @@ int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* obj, float* positions, flo
     return IVX_OK;
 }
 
-static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats);
+static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats,
+                       const InertialUpdate* upd = nullptr);
 
 // ---- mesh gather over peer memory (multi-GPU) ------------------------------------------------------------
 int ivx_peer_alloc(ivx_ctx* ctx, size_t bytes, void** out_ptr, unsigned char out_handle[64]) {
@@ -1493,23 +1494,17 @@ int ivx_mesh_push(ivx_ctx* ctx, const ivx_object* obj, void* dst_base, const uin
     return IVX_OK;
 }
 
-int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3], float radius, float influence_radius,
-                             ivx_absorb_stats* out_stats) {
-    if (!ctx || !obj || !center) return IVX_ERR_INVALID_ARGUMENT;
-    if (!(radius >= 0.0f) || !(influence_radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;  // Sphere::new asserts
+static ivx::AbsorbShape sphere_shape(const float center[3], float radius, float influence_radius) {
     ivx::AbsorbShape s{};
     s.capsule = 0;
     for (int d = 0; d < 3; ++d) s.center[d] = center[d];
     s.radius = radius;
     s.influence_radius = influence_radius;
     s.influence_radius_sq = influence_radius * influence_radius;  // Sphere::radius_squared = radius.powi(2)
-    return absorb_impl(ctx, obj, s, out_stats);
+    return s;
 }
-
-int ivx_object_absorb_capsule(ivx_ctx* ctx, ivx_object* obj, const float segment_start[3], const float segment_vector[3],
-                              float radius, float influence_radius, ivx_absorb_stats* out_stats) {
-    if (!ctx || !obj || !segment_start || !segment_vector) return IVX_ERR_INVALID_ARGUMENT;
-    if (!(radius >= 0.0f) || !(influence_radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;  // Capsule::new asserts
+static ivx::AbsorbShape capsule_shape(const float segment_start[3], const float segment_vector[3], float radius,
+                                      float influence_radius) {
     ivx::AbsorbShape s{};
     s.capsule = 1;
     for (int d = 0; d < 3; ++d) {
@@ -1522,12 +1517,49 @@ int ivx_object_absorb_capsule(ivx_ctx* ctx, ivx_object* obj, const float segment
     s.radius = radius;
     s.influence_radius = influence_radius;
     s.influence_radius_sq = influence_radius * influence_radius;
-    return absorb_impl(ctx, obj, s, out_stats);
+    return s;
+}
+
+int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* obj, const float center[3], float radius, float influence_radius,
+                             ivx_absorb_stats* out_stats) {
+    if (!ctx || !obj || !center) return IVX_ERR_INVALID_ARGUMENT;
+    if (!(radius >= 0.0f) || !(influence_radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;  // Sphere::new asserts
+    return absorb_impl(ctx, obj, sphere_shape(center, radius, influence_radius), out_stats);
+}
+
+int ivx_object_absorb_sphere_inertial(ivx_ctx* ctx, ivx_object* obj, const float center[3], float radius,
+                                      float influence_radius, const float* voxel_type_densities, uint32_t n_densities,
+                                      ivx_inertial_moments* inout_moments, ivx_absorb_stats* out_stats) {
+    if (!ctx || !obj || !center || !inout_moments || (!voxel_type_densities && n_densities) || n_densities > 256)
+        return IVX_ERR_INVALID_ARGUMENT;
+    if (!(radius >= 0.0f) || !(influence_radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;
+    const InertialUpdate upd{voxel_type_densities, n_densities, inout_moments};
+    return absorb_impl(ctx, obj, sphere_shape(center, radius, influence_radius), out_stats, &upd);
+}
+
+int ivx_object_absorb_capsule_inertial(ivx_ctx* ctx, ivx_object* obj, const float segment_start[3],
+                                       const float segment_vector[3], float radius, float influence_radius,
+                                       const float* voxel_type_densities, uint32_t n_densities,
+                                       ivx_inertial_moments* inout_moments, ivx_absorb_stats* out_stats) {
+    if (!ctx || !obj || !segment_start || !segment_vector || !inout_moments || (!voxel_type_densities && n_densities) ||
+        n_densities > 256)
+        return IVX_ERR_INVALID_ARGUMENT;
+    if (!(radius >= 0.0f) || !(influence_radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;
+    const InertialUpdate upd{voxel_type_densities, n_densities, inout_moments};
+    return absorb_impl(ctx, obj, capsule_shape(segment_start, segment_vector, radius, influence_radius), out_stats, &upd);
+}
+
+int ivx_object_absorb_capsule(ivx_ctx* ctx, ivx_object* obj, const float segment_start[3], const float segment_vector[3],
+                              float radius, float influence_radius, ivx_absorb_stats* out_stats) {
+    if (!ctx || !obj || !segment_start || !segment_vector) return IVX_ERR_INVALID_ARGUMENT;
+    if (!(radius >= 0.0f) || !(influence_radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;  // Capsule::new asserts
+    return absorb_impl(ctx, obj, capsule_shape(segment_start, segment_vector, radius, influence_radius), out_stats);
 }
 
 }  // extern "C"
 
-static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats) {
+static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats,
+                       const InertialUpdate* upd) {
     using namespace ivx;
     const float influence_radius = shape.influence_radius;
     cudaSetDevice(ctx->device);
@@ -1585,8 +1617,16 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     aa.new_slot_ord = ord;
     aa.dirty = obj->d_dirty;
     aa.stats = counters + 1;
+    if (upd) {
+        aa.removed_cols = tmp.get<uint16_t>((size_t)n_range * 256);
+        aa.removed_info = tmp.get<uint32_t>((size_t)n_range * 2);
+        if (!aa.removed_cols || !aa.removed_info) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
+        CU(ctx, cudaMemsetAsync(aa.removed_info, 0, (size_t)n_range * 8, st));  // chunks the kernel skips removed nothing
+    }
     KLP(ctx, 6, launch_absorb_apply(aa, persistent_grid(ctx, n_range, 4), st));
     obj->slots_used += w[0];
+    if (upd)
+        if (int rc = ivx_apply_removed_voxels(ctx, obj, r, n_range, aa.removed_info, aa.removed_cols, *upd)) return rc;
 
     // boundary refresh over chunk range [start-1, end) (intersection.rs:391-393)
     AbsorbRange b = r;

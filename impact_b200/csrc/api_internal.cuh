@@ -198,6 +198,16 @@ struct Tmp {
 };
 
 
+// inertia.cu: VoxelObjectInertialPropertyUpdater::remove_voxel (object/inertia.rs:374-395) for every voxel an absorption
+// emptied, applied to `inout` in the reference's visiting order
+struct InertialUpdate {
+    const float* densities;
+    uint32_t n_densities;
+    ivx_inertial_moments* inout;
+};
+int ivx_apply_removed_voxels(ivx_ctx* ctx, const ivx_object* obj, const AbsorbRange& r, uint32_t n_range,
+                             const uint32_t* removed_info, const uint16_t* removed_cols, const InertialUpdate& upd);
+
 // api.cu
 int ivx_read_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t n, uint32_t* out);
 uint32_t ivx_persistent_grid(ivx_ctx* ctx, uint32_t n_work, int blocks_per_sm);

@@ -5,7 +5,8 @@
 //   VoxelObjectInertialPropertyManager::initialized_from       (object/inertia.rs:125-137)
 //   compute_inertial_property_moments_for_object               (object/inertia.rs:754-789)
 //   compute_moments_for_non_uniform_chunk / _uniform_chunk     (object/inertia.rs:629-752)
-//   compute_moments_for_voxel (the absorption updater's term)  (object/inertia.rs:591-625)
+//   VoxelObjectInertialPropertyUpdater::remove_voxel → compute_moments_for_voxel, for the voxels an absorption
+//   empties (ivx_apply_removed_voxels, called by ivx_object_absorb_*_inertial)  (object/inertia.rs:374-395, 591-625)
 //
 // The reference's result is a chain of f32 additions in a fixed order (voxels i → j → k inside a chunk, chunks
 // i → j → k over the occupied range), and f32 addition does not reassociate. To return the same bits, the order
@@ -252,7 +253,116 @@ __global__ void k_moments_scatter(const DevChunk* __restrict__ chunks, uint32_t 
     dense[t] = chunks[c_begin + c].kind != 0 ? part[(size_t)row[c] * 10 + q] : 0.0f;
 }
 
+// ---- incremental update: the voxels an absorption emptied ------------------------------------------------------
+// compute_moments_for_voxel (inertia.rs:591-625), negated: `parent.mass -= voxel_mass` is `parent.mass + (-voxel_mass)`
+__device__ __forceinline__ void negated_voxel_moments(float e, float e2, float e3, float density, const uint32_t ijk[3],
+                                                      float* __restrict__ out) {
+    float h2[3], h3[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float lo = e * (float)ijk[d];
+        const float hi = lo + e;
+        const float lo2 = lo * lo, hi2 = hi * hi;
+        const float lo3 = lo2 * lo, hi3 = hi2 * hi;
+        h2[d] = hi2 - lo2;
+        h3[d] = hi3 - lo3;
+    }
+    const float fm = (0.5f * e2) * density;
+    const float fi = ((1.0f / 3.0f) * e2) * density;
+    const float fp = (0.25f * e) * density;
+    out[0] = -(e3 * density);
+    out[1] = -(fm * h2[0]);
+    out[2] = -(fm * h2[1]);
+    out[3] = -(fm * h2[2]);
+    out[4] = -(fi * (h3[1] + h3[2]));
+    out[5] = -(fi * (h3[0] + h3[2]));
+    out[6] = -(fi * (h3[0] + h3[1]));
+    out[7] = -(fp * (h2[0] * h2[1]));
+    out[8] = -(fp * (h2[1] * h2[2]));
+    out[9] = -(fp * (h2[2] * h2[0]));
+}
+
+__global__ void k_removed_counts(const uint32_t* __restrict__ info, uint32_t n_range, uint32_t* __restrict__ count) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_range) count[t] = info[2 * t];
+}
+
+// One block per chunk of the touched range: the emptied voxels' negated terms, one row each, in the order the
+// reference's closure was called (chunks of the range i → j → k = the range index, voxels i → j → k inside a chunk).
+__global__ void __launch_bounds__(256) k_removed_terms(AbsorbRange r, const uint32_t* __restrict__ info,
+                                                       const uint16_t* __restrict__ cols, const uint32_t* __restrict__ first_row,
+                                                       const unsigned char* __restrict__ voxels, float e, uint32_t n_densities,
+                                                       const __grid_constant__ Densities dens, float* __restrict__ rows,
+                                                       uint32_t* __restrict__ error) {
+    __shared__ uint32_t s_warp[8];
+    const uint32_t t = blockIdx.x;
+    if (info[2 * t] == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bits = cols[(size_t)t * 256 + tid];
+    const uint32_t mine = __popc(bits);
+    // exclusive scan of the column counts over the block (column order = voxel order)
+    uint32_t x = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    uint32_t before = x - mine;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (!mine) return;
+    const uint32_t ek = r.c1[2] - r.c0[2], ej = r.c1[1] - r.c0[1];
+    const uint32_t ck = r.c0[2] + t % ek, cj = r.c0[1] + (t / ek) % ej, ci = r.c0[0] + t / (ek * ej);
+    const unsigned char* types = voxels + (size_t)info[2 * t + 1] * SLOT_BYTES + PLANE_TYPE + tid * 16;
+    const float e2 = e * e, e3 = e2 * e;
+    float* out = rows + ((size_t)first_row[t] + before) * 10;
+    for (uint32_t b = bits; b; b &= b - 1) {
+        const uint32_t k = (uint32_t)__ffs(b) - 1u;
+        const uint32_t ty = types[k];
+        if (ty >= n_densities) atomicOr(error, 1u);
+        const uint32_t ijk[3] = {ci * 16u + (uint32_t)(tid >> 4), cj * 16u + (uint32_t)(tid & 15), ck * 16u + k};
+        negated_voxel_moments(e, e2, e3, dens.v[ty], ijk, out);
+        out += 10;
+    }
+}
+
 }  // namespace ivx
+
+int ivx_apply_removed_voxels(ivx_ctx* ctx, const ivx_object* obj, const AbsorbRange& r, uint32_t n_range,
+                             const uint32_t* removed_info, const uint16_t* removed_cols, const InertialUpdate& upd) {
+    if (n_range == 0) return IVX_OK;
+    Densities dens{};
+    for (uint32_t q = 0; q < upd.n_densities; ++q) dens.v[q] = upd.densities[q];
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t* count = tmp.get<uint32_t>(n_range);
+    uint32_t* first_row = tmp.get<uint32_t>(n_range);
+    float* d_io = tmp.get<float>(32);  // [0..10) the sums before, [16..26) after, [26] rows, [27] error
+    uint32_t* counters = ctx->d_scratch + 48;  // [0] rows [1] error
+    if (!count || !first_row || !d_io) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "inertial update: out of device memory");
+    CU(ctx, cudaMemsetAsync(counters, 0, 8, st));
+    CU(ctx, cudaMemcpyAsync(d_io, upd.inout, sizeof(ivx_inertial_moments), cudaMemcpyHostToDevice, st));
+    KL(ctx, (k_removed_counts<<<(n_range + 255) / 256, 256, 0, st>>>(removed_info, n_range, count), cudaGetLastError()));
+    KL(ctx, launch_exclusive_scan(count, first_row, n_range, counters, st));
+    uint32_t n_rows = 0;
+    if (int rc = ivx_read_words(ctx, counters, 1, &n_rows)) return rc;
+    if (n_rows == 0) return IVX_OK;
+    float* rows = tmp.get<float>((size_t)n_rows * 10 + 4);
+    if (!rows) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "inertial update: out of device memory");
+    KL(ctx, (k_removed_terms<<<n_range, 256, 0, st>>>(r, removed_info, removed_cols, first_row, obj->d_voxels, obj->voxel_extent,
+                                                      upd.n_densities, dens, rows, counters + 1),
+             cudaGetLastError()));
+    KLP(ctx, 10, (k_moments_sum<<<1, 256, 0, st>>>(rows, counters, d_io, d_io + 16), cudaGetLastError()));
+    CU(ctx, cudaMemcpyAsync(d_io + 26, counters, 8, cudaMemcpyDeviceToDevice, st));
+    uint32_t w[12];
+    if (int rc = ivx_read_words(ctx, reinterpret_cast<const uint32_t*>(d_io + 16), 12, w)) return rc;
+    if (w[11])
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT,
+                 "inertial update: an emptied voxel has a type without a density (%u densities given)", upd.n_densities);
+    std::memcpy(upd.inout, w, sizeof(ivx_inertial_moments));
+    return IVX_OK;
+}
 
 extern "C" {
 

@@ -199,6 +199,10 @@ struct AbsorbArgs {
     const uint32_t* new_slot_ord;
     uint8_t* dirty;
     uint32_t* stats;  // touched chunks, touched voxels, emptied voxels, removed chunks
+    // inertial-property update (null unless asked for): which voxels went from non-empty to empty, per chunk of the
+    // range in its visiting order — 256 columns x 16 bits — and {count, voxel slot} per chunk
+    uint16_t* removed_cols;
+    uint32_t* removed_info;
 };
 cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], const AbsorbRange& r, const AbsorbShape& shape,
                                uint32_t* need_slot, uint32_t n_range, cudaStream_t st);

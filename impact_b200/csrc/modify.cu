@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
         __syncthreads();
 
         const uint32_t gi = v0[0] + ti, gj = v0[1] + tj;
-        uint32_t n_touched = 0, n_emptied = 0;
+        uint32_t n_touched = 0, n_emptied = 0, removed_bits = 0;
         if (gi >= t0[0] && gi < t1[0] && gj >= t0[1] && gj < t1[1]) {
             const float px = (float)gi + 0.5f, py = (float)gj + 0.5f;
             for (uint32_t gk = t0[2]; gk < t1[2]; ++gk) {
@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
                     s_sd[idx] = (int8_t)code;
                     if (code >= 0) {
                         s_fl[idx] |= 1;
-                        if (!was_empty) n_emptied++;
+                        if (!was_empty) {
+                            n_emptied++;
+                            removed_bits |= 1u << (gk & 15u);  // the closure's remove_voxel callback (absorption.rs:836-840)
+                        }
                     }
                     n_touched++;
                 }
@@ -211,6 +214,13 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
             const int is_void = __syncthreads_and(void_mask == 0xFFFFu);
             for (int q = 0; q < 6; ++q) me.face[q] = s_cnt[q] == 256u ? 0 : (s_cnt[q] == 0u ? 1 : 2);
             if (only_empty) me.flags |= 1u << 6; else me.flags &= (uint8_t)~(1u << 6);
+            if (a.removed_cols) {
+                a.removed_cols[(size_t)t * 256 + tid] = (uint16_t)removed_bits;
+                if (tid == 0) {
+                    a.removed_info[2 * t] = s_cnt[7];
+                    a.removed_info[2 * t + 1] = me.slot;  // still valid for reading the types if the chunk is dropped below
+                }
+            }
             if (is_void) {
                 // the chunk is dropped; its slot is orphaned like in the reference (intersection.rs:559-562)
                 DevChunk v{};

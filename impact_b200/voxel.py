@@ -296,6 +296,31 @@ class VoxelObject:
             L.ptr(out), L.ptr(pc) if per_chunk else None, C.c_size_t(len(pc) if per_chunk else 0)))
         return (out, pc) if per_chunk else out
 
+    def absorb_sphere_inertial(self, center, radius: float, influence_radius: float, voxel_type_densities,
+                               moments: np.ndarray) -> dict:
+        """`apply_sphere_absorption` with its `VoxelObjectInertialPropertyUpdater` (absorption.rs:801-844): `moments`
+        (10 f32, e.g. `VoxelObjectInertialPropertyManager.m`) is updated in place, bit for bit like the reference."""
+        c = np.asarray(center, np.float32)
+        dens = np.ascontiguousarray(voxel_type_densities, np.float32)
+        assert moments.dtype == np.float32 and moments.shape == (10,) and moments.flags.c_contiguous
+        st = L.AbsorbStats()
+        self.ctx.check(self.ctx._lib.ivx_object_absorb_sphere_inertial(
+            self.ctx.h, self.h, L.ptr(c), C.c_float(radius), C.c_float(influence_radius), L.ptr(dens),
+            C.c_uint32(len(dens)), L.ptr(moments), C.byref(st)))
+        return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
+
+    def absorb_capsule_inertial(self, segment_start, segment_vector, radius: float, influence_radius: float,
+                                voxel_type_densities, moments: np.ndarray) -> dict:
+        """`apply_capsule_absorption` with its inertial-property updater (absorption.rs:846-889)."""
+        a, v = np.asarray(segment_start, np.float32), np.asarray(segment_vector, np.float32)
+        dens = np.ascontiguousarray(voxel_type_densities, np.float32)
+        assert moments.dtype == np.float32 and moments.shape == (10,) and moments.flags.c_contiguous
+        st = L.AbsorbStats()
+        self.ctx.check(self.ctx._lib.ivx_object_absorb_capsule_inertial(
+            self.ctx.h, self.h, L.ptr(a), L.ptr(v), C.c_float(radius), C.c_float(influence_radius), L.ptr(dens),
+            C.c_uint32(len(dens)), L.ptr(moments), C.byref(st)))
+        return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113) → (info dict, extracted VoxelObject or
         None). This object is modified in place."""

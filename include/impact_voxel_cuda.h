@@ -455,6 +455,21 @@ typedef struct ivx_inertial_moments {
 int ivx_object_inertial_moments(ivx_ctx* ctx, const ivx_object* object, const float* voxel_type_densities,
                                 uint32_t n_densities, const ivx_inertial_moments* initial, ivx_inertial_moments* out,
                                 float* per_chunk_terms, size_t per_chunk_capacity);
+/* ivx_object_absorb_sphere / _capsule with the reference's VoxelObjectInertialPropertyUpdater attached
+ * (apply_sphere_absorption / apply_capsule_absorption, interaction/absorption.rs:801-889: the closure calls
+ * remove_voxel(object_voxel_indices, voxel_type) for every voxel that goes from non-empty to empty, object/inertia.rs:
+ * 374-395 → compute_moments_for_voxel :591-625). `inout_moments` leaves with the same f32 bits as the reference's
+ * manager: the emptied voxels' terms are computed in parallel, then subtracted one after the other in the order the
+ * reference visits them (chunks of the touched range i → j → k, voxels i → j → k inside a chunk). If an emptied voxel's
+ * type has no density the call fails with IVX_ERR_INVALID_ARGUMENT after the voxels were modified (the reference
+ * panics at the same point); `inout_moments` is then left untouched. */
+int ivx_object_absorb_sphere_inertial(ivx_ctx* ctx, ivx_object* object, const float center[3], float radius,
+                                      float influence_radius, const float* voxel_type_densities, uint32_t n_densities,
+                                      ivx_inertial_moments* inout_moments, ivx_absorb_stats* out_stats);
+int ivx_object_absorb_capsule_inertial(ivx_ctx* ctx, ivx_object* object, const float segment_start[3],
+                                       const float segment_vector[3], float radius, float influence_radius,
+                                       const float* voxel_type_densities, uint32_t n_densities,
+                                       ivx_inertial_moments* inout_moments, ivx_absorb_stats* out_stats);
 
 #ifdef __cplusplus
 }

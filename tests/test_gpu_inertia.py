@@ -74,6 +74,50 @@ def test_inertial_moments_follow_absorption(ctx, oracle):
     _assert_same_moments(obj_gpu, obj_cpu, DENS4, "capsule")
 
 
+@pytest.mark.parametrize("name,types,dens,extent", [("sphere", H.SAME0, [0.5], 1.0), ("asteroid_like", H.GRADIENT4, DENS4, 0.25)])
+def test_absorption_updates_the_moments_bit_for_bit(ctx, oracle, name, types, dens, extent):
+    # apply_sphere_absorption / apply_capsule_absorption with the VoxelObjectInertialPropertyUpdater attached
+    # (absorption.rs:801-889): the manager's ten sums after every call, against the oracle's voxel-by-voxel chain
+    g = H.sphere_graph(40.0) if name == "sphere" else H.asteroid_like_graph(16, 36.0)
+    obj_gpu, obj_cpu = _both(ctx, oracle, g, types, extent)
+    f = np.float32
+    shape = (np.array(obj_cpu.info()["chunk_counts"]) * 16).astype(np.float32)
+    mid = f(0.5) * shape
+    m_cpu = obj_cpu.inertial_moments(dens).copy()
+    m_gpu = obj_gpu.inertial_moments(dens).copy()
+    assert H.f32_bits_equal(m_cpu, m_gpu).all()
+    R = f(0.5) * shape.max()
+    radius = f(0.15) * R
+    start = (mid - R / f(np.sqrt(3.0))).astype(np.float32)
+    removed = 0
+    for step in range(5):  # BASELINE config 5 geometry: the absorber marches inward along the diagonal
+        c = (start + f(step) * radius * f(0.6)).astype(np.float32)
+        st_c = obj_cpu.absorb_sphere_inertial(c, float(radius), float(radius + f(2.0)), dens, m_cpu)
+        st_g = obj_gpu.absorb_sphere_inertial(c, float(radius), float(radius + f(2.0)), dens, m_gpu)
+        for k in ("touched_chunks", "touched_voxels", "emptied_voxels", "removed_chunks"):
+            assert st_g[k] == st_c[k], (step, k, st_g, st_c)
+        removed += st_c["emptied_voxels"]
+        assert H.f32_bits_equal(m_gpu, m_cpu).all(), (step, m_gpu, m_cpu)
+    capsules = [
+        (mid - f([30.5, 8.25, 3.0]), f([61.0, 16.5, 6.0]), f(5.0)),      # slanted, through the centre
+        (mid + f([9.1, -7.7, 11.3]), f([0.0, 0.0, 0.0]), f(6.0)),        # zero-length segment
+        (f([-50.0, -50.0, -50.0]), f([10.0, 0.0, 0.0]), f(4.0)),         # misses the object: nothing changes
+        (mid - f([3.0, 40.0, 1.0]), f([5.5, 80.0, 2.5]), f(9.0)),        # thick, crosses everything again
+    ]
+    for step, (a, v, rad) in enumerate(capsules):
+        st_c = obj_cpu.absorb_capsule_inertial(a, v, float(rad), float(rad + f(2.0)), dens, m_cpu)
+        st_g = obj_gpu.absorb_capsule_inertial(a, v, float(rad), float(rad + f(2.0)), dens, m_gpu)
+        assert st_g["emptied_voxels"] == st_c["emptied_voxels"]
+        removed += st_c["emptied_voxels"]
+        assert H.f32_bits_equal(m_gpu, m_cpu).all(), ("capsule", step, m_gpu, m_cpu)
+    assert removed > 20000
+    # the voxels themselves went through the same path as without the updater
+    H.assert_objects_equal(*obj_gpu.download(), obj_cpu.chunks(), obj_cpu.voxels())
+    # and the incremental sums stay within the reference's validate_for_object tolerance of the from-scratch ones
+    scratch = _assert_same_moments(obj_gpu, obj_cpu, dens, "after absorption")
+    assert np.all(np.abs(scratch - m_gpu) <= 1e-3 * np.maximum(np.abs(scratch), 1.0))
+
+
 def test_inertial_moments_of_a_split_off_fragment(ctx, oracle):
     # extract_any_disconnected_region (extraction.rs:78-113): both parts' sums from scratch, and the bookkeeping the
     # reference's PropertyTransferrer does incrementally (inertia.rs:397-470) holds between them
@@ -122,6 +166,11 @@ def test_missing_density_is_an_error(ctx):
     with pytest.raises(Exception, match="density"):
         obj.inertial_moments([1.0, 2.0])
     assert obj.inertial_moments([1.0, 2.0, 3.0, 4.0])[0] > 0
+    m = obj.inertial_moments([1.0, 2.0, 3.0, 4.0]).copy()
+    keep = m.copy()
+    with pytest.raises(Exception, match="density"):
+        obj.absorb_sphere_inertial([24.0, 24.0, 24.0], 6.0, 8.0, np.zeros(0, np.float32), m)
+    assert np.array_equal(m, keep)
     empty = VoxelObject.generate(SDFVoxelGenerator(1.0, ctx.build_generator(H.SDFGraph()), H.SAME0))
     assert not empty.inertial_moments([1.0]).any()
 
