@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=0)
     ap.add_argument("--split", action="store_true", help="also resolve connected regions and split off disconnected ones after every step")
+    ap.add_argument("--inertial", action="store_true",
+                    help="attach the inertial-property updater to every absorption (ivx_object_absorb_sphere_inertial)")
     args = ap.parse_args()
 
     import bench
@@ -54,6 +56,10 @@ def main():
     centers, radius = absorber_path(shape, args.steps)
     influence = radius + 2.0  # absorption.rs:170-179: influence radius = radius + 2 voxel extents
 
+    densities = np.float32([1.0, 2.7, 0.3, 5.5])
+    moments = obj.inertial_moments(densities).copy() if args.inertial else None
+    moments_start = None if moments is None else moments.copy()
+
     ctx.profile_enable(True)
     ctx.profile_reset()
     per_step = []
@@ -62,7 +68,10 @@ def main():
     t_all = time.perf_counter()
     for c in centers:
         t0 = time.perf_counter()
-        st = obj.absorb_sphere(c, radius, influence)
+        if args.inertial:
+            st = obj.absorb_sphere_inertial(c, radius, influence, densities, moments)
+        else:
+            st = obj.absorb_sphere(c, radius, influence)
         n_dirty = len(obj.invalidated_mesh_chunk_indices())
         t1 = time.perf_counter()
         patch = VoxelObjectMesh.sync_with_voxel_object(obj)
@@ -117,6 +126,16 @@ def main():
         "gpu_launches": int(launches), "timing": "host wall clock around synchronous C-ABI calls; kernel times from CUDA events",
         "last_step": per_step[-1],
     }
+    if args.inertial:
+        scratch = obj.inertial_moments(densities)
+        out["inertial"] = {
+            "note": "VoxelObjectInertialPropertyUpdater attached to every absorption (bit-exact ordered subtraction); "
+                    "absorb_ms includes it",
+            "ordered_sum_kernel_ms_per_step": prof["moments_sum"][0] / max(1, args.steps),
+            "mass_before": float(moments_start[0]), "mass_after_incremental": float(moments[0]),
+            "mass_after_from_scratch": float(scratch[0]),
+            "max_rel_dev_incremental_vs_scratch": float(np.max(np.abs(moments - scratch) / np.maximum(np.abs(scratch), 1e-30))),
+        }
 
     if args.cpu_steps > 0:
         from oracle import oracle_lib as O
