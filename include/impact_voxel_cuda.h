@@ -416,7 +416,8 @@ int ivx_object_split_detection_download(ivx_ctx* ctx, const ivx_object* object, 
  * non-empty voxels and no uniform chunk is dropped (`discarded`); one of at most 2 x 2 x 2 chunks whose voxels span at
  * most 14 per axis is re-packed into a single chunk. Both objects leave with their derived state (adjacencies,
  * obscuredness, occupied ranges) up to date; `object`'s chunks that lost voxels are marked for re-meshing
- * (ivx_object_remesh_dirty). Inertial-property transfer (PropertyTransferrer) stays with the host. */
+ * (ivx_object_remesh_dirty). The PropertyTransferrer's bookkeeping is replaced by ivx_object_inertial_moments on both
+ * objects after the call. */
 typedef struct ivx_extraction_info {
     uint32_t n_regions_before;          /* count_regions of `object` */
     uint32_t found_two;                 /* find_two_disconnected_regions().is_some() */
