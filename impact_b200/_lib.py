@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_download", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_peer_alloc", "ivx_peer_free", "ivx_peer_open", "ivx_peer_close", "ivx_mesh_push", "ivx_object_absorb_sphere", "ivx_object_absorb_capsule",
     "ivx_object_dirty_chunks", "ivx_object_remesh_dirty",
     "ivx_object_resolve_connected_regions", "ivx_object_split_detection_download", "ivx_object_extract_disconnected_region",
-    "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",
+    "ivx_object_from_generated_chunks", "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",
 ]
 
 

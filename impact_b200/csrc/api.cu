@@ -1772,6 +1772,74 @@ int new_plain_object(ivx_ctx* ctx, float voxel_extent, const uint32_t nb[3], uin
 
 extern "C" {
 
+int ivx_object_from_generated_chunks(ivx_ctx* ctx, float voxel_extent, const uint32_t grid_shape[3], const ivx_voxel* voxels,
+                                     const uint8_t* sparseness, ivx_object** out_object) {
+    if (!ctx || !grid_shape || !out_object) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    *out_object = nullptr;
+    if (!(voxel_extent > 0.0f)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "voxel_extent must be positive");
+    uint32_t cc[3];
+    uint64_t n64 = 1;
+    for (int d = 0; d < 3; ++d) {
+        cc[d] = (grid_shape[d] + 15u) / 16u;
+        n64 *= cc[d];
+    }
+    if (n64 > 0x7FFFFFFFull / 10) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "grid too large");
+    const uint32_t n = (uint32_t)n64;
+    if (n && (!voxels || !sparseness)) return IVX_ERR_INVALID_ARGUMENT;
+    uint32_t stored_bound = 0;
+    for (uint32_t c = 0; c < n; ++c) stored_bound += (sparseness[c] & 2u) ? 0u : 1u;
+    ivx_object* o = nullptr;
+    if (int rc = new_plain_object(ctx, voxel_extent, cc, stored_bound, &o)) return rc;
+    for (int d = 0; d < 3; ++d) o->grid_shape[d] = grid_shape[d];
+    if (n == 0) {
+        *out_object = o;
+        return IVX_OK;
+    }
+    auto fail = [&](int rc) {
+        ivx_object_free(ctx, o);
+        return rc;
+    };
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    unsigned char* d_src = tmp.get<unsigned char>((size_t)n * SLOT_BYTES);
+    uint8_t* d_sp = tmp.get<uint8_t>(n);
+    uint32_t* counter = ctx->d_scratch + 50;
+    if (!d_src || !d_sp) {
+        ctx->err = "ingest: out of device memory";
+        return fail(IVX_ERR_OUT_OF_MEMORY);
+    }
+    static_assert(sizeof(ivx_voxel) == 3, "Voxel is three bytes");
+    cudaError_t e = cudaMemcpyAsync(d_src, voxels, (size_t)n * SLOT_BYTES, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sp, sparseness, n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, 8, st);
+    if (e == cudaSuccess) {
+        ctx->launches++;
+        e = launch_ingest_chunks(d_src, d_sp, n, o->d_chunks, o->d_voxels, counter, persistent_grid(ctx, n, 4), st);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = std::string("ingest failed: ") + cudaGetErrorString(e);
+        return fail(IVX_ERR_CUDA);
+    }
+    uint32_t used[2] = {0, 0};
+    if (int rc = read_words(ctx, counter, 2, used)) return fail(rc);
+    if (used[1]) {
+        ctx->err = "ingest: a voxel's EMPTY flag disagrees with the sign of its signed distance (Voxel invariant, lib.rs:300-348)";
+        return fail(IVX_ERR_INVALID_ARGUMENT);
+    }
+    o->slots_used = used[0];
+    // update_occupied_voxel_ranges, then compute_all_derived_state's cross-chunk pass (object.rs:239-263, 1659-1785)
+    if (int rc = refresh_occupied_ranges(ctx, o)) return fail(rc);
+    if (int rc = refresh_boundaries(ctx, o, nullptr)) return fail(rc);
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        ctx->err = "ingest: stream synchronisation failed";
+        return fail(IVX_ERR_CUDA);
+    }
+    *out_object = o;
+    return IVX_OK;
+}
+
 int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* obj, ivx_extraction_info* info, ivx_object** out_extracted) {
     if (!ctx || !obj || !info || !out_extracted) return IVX_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);

@@ -233,6 +233,90 @@ __global__ void __launch_bounds__(256) k_repack_single(const DevChunk* __restric
     }
 }
 
+// ---- ingest of host-generated chunks -------------------------------------------------------------------------
+// VoxelChunk::create_for_generated_voxels (object.rs:1890-1964) + update_internal_adjacencies (object.rs:2673-2756) for
+// chunks a host-side ChunkedVoxelGenerator produced (generation.rs:41-67): one CTA per chunk reads the chunk's 4096
+// `Voxel`s (AoS, 48 contiguous bytes per (i, j) column), classifies it and stores NonUniform chunks as planes.
+// sparseness: bit 0 has_only_empty_voxels, bit 1 is_void — the generator's own answer, taken as given like the reference
+__global__ void __launch_bounds__(256) k_ingest_chunks(const unsigned char* __restrict__ src, const uint8_t* __restrict__ sparseness,
+                                                       uint32_t n, DevChunk* __restrict__ chunks, unsigned char* __restrict__ voxels,
+                                                       uint32_t* __restrict__ slot_counter) {
+    __shared__ __align__(16) uint8_t s_fl[4096];
+    __shared__ uint32_t s_cnt[8];
+    __shared__ uint32_t s_first, s_slot;
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+        const uint32_t sp = sparseness[c];
+        DevChunk me{};
+        me.slot = 0xFFFFFFFFu;
+        if (sp & 2u) {  // Void
+            if (tid == 0) chunks[c] = me;
+            continue;
+        }
+        const uint4* p = reinterpret_cast<const uint4*>(src + (size_t)c * SLOT_BYTES + (size_t)tid * 48);
+        const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        const uint32_t w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+        uint8_t ty[16], sd[16], fl[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int b = 3 * k;  // Voxel { voxel_type, signed_distance, flags } (lib.rs:60-66)
+            ty[k] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+            sd[k] = (uint8_t)(w[(b + 1) >> 2] >> (8 * ((b + 1) & 3)));
+            fl[k] = (uint8_t)(w[(b + 2) >> 2] >> (8 * ((b + 2) & 3)));
+        }
+        *reinterpret_cast<uint4*>(&s_fl[tid * 16]) = pack16(fl);
+        if (tid < 8) s_cnt[tid] = 0;
+        if (tid == 0) s_first = (uint32_t)ty[0] | ((uint32_t)fl[0] << 8);
+        __syncthreads();
+        const uint32_t first = s_first;
+        bool same = true, valid = true;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            same = same && ty[k] == (uint8_t)first && fl[k] == (uint8_t)(first >> 8) && sd[k] == 0x80u;
+            // the `Voxel` constructors' invariant (lib.rs:300-348, 451-461): EMPTY ⇔ the distance code is not negative;
+            // the occupied ranges and the mesher read emptiness from the sign
+            valid = valid && ((fl[k] & 1u) != 0) == ((sd[k] & 0x80u) == 0);
+        }
+        if (!valid) atomicOr(slot_counter + 1, 1u);
+        const int uniform = __syncthreads_and(same) && !(sp & 1u);
+        if (uniform) {
+            // stored as one voxel that assumes full adjacency; fixed later if a neighbour disagrees (object.rs:1940-1952)
+            me.kind = 1;
+            me.u_type = (uint8_t)first;
+            me.u_sd = (int8_t)-128;
+            me.u_flags = (uint8_t)(first >> 8) | 0xFCu;
+            if (tid == 0) chunks[c] = me;
+            __syncthreads();
+            continue;
+        }
+        uint8_t nf[16];
+        const uint32_t empty_mask = refresh_column_flags(s_fl, ti, tj, nf);
+        count_face_empties(empty_mask, ti, tj, s_cnt);
+        if (tid == 0) s_slot = atomicAdd(slot_counter, 1u);
+        __syncthreads();
+        me.kind = 2;
+        me.slot = s_slot;
+        if (sp & 1u) {
+            me.flags = 1u << 6;  // HAS_ONLY_EMPTY_VOXELS, all faces Empty
+            for (int q = 0; q < 6; ++q) me.face[q] = 0;
+        } else {
+            for (int q = 0; q < 6; ++q) me.face[q] = s_cnt[q] == 256u ? 0 : (s_cnt[q] == 0u ? 1 : 2);
+        }
+        unsigned char* slot = voxels + (size_t)me.slot * SLOT_BYTES;
+        *reinterpret_cast<uint4*>(slot + PLANE_SD + tid * 16) = pack16(sd);
+        *reinterpret_cast<uint4*>(slot + PLANE_TYPE + tid * 16) = pack16(ty);
+        *reinterpret_cast<uint4*>(slot + PLANE_FLAGS + tid * 16) = pack16(nf);
+        if (tid == 0) chunks[c] = me;
+        __syncthreads();
+    }
+}
+cudaError_t launch_ingest_chunks(const unsigned char* src, const uint8_t* sparseness, uint32_t n, DevChunk* chunks,
+                                 unsigned char* voxels, uint32_t* slot_counter, uint32_t grid, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_ingest_chunks<<<grid, 256, 0, st>>>(src, sparseness, n, chunks, voxels, slot_counter);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_extract_chunks(const ExtractArgs& a, uint32_t grid, cudaStream_t st) {
     if (a.n_ext == 0) return cudaSuccess;
     k_extract_chunks<<<grid, 256, 0, st>>>(a);

@@ -121,6 +121,8 @@ struct ExtractArgs {
     uint32_t* non_empty_count;   // non-empty voxels that moved
 };
 cudaError_t launch_extract_chunks(const ExtractArgs& a, uint32_t grid, cudaStream_t st);
+cudaError_t launch_ingest_chunks(const unsigned char* src, const uint8_t* sparseness, uint32_t n, DevChunk* chunks,
+                                 unsigned char* voxels, uint32_t* slot_counter, uint32_t grid, cudaStream_t st);
 cudaError_t launch_repack_single(const DevChunk* chunks, const uint32_t nb[3], const unsigned char* voxels, const uint32_t org[3],
                                  const uint32_t occ_lo[3], const uint32_t occ_hi[3], DevChunk* out_chunk, unsigned char* out_slot,
                                  cudaStream_t st);

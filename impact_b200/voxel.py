@@ -196,6 +196,22 @@ class VoxelObject:
             C.byref(nnu)))
         return cls(ctx, h), int(nnu.value)
 
+    @classmethod
+    def from_generated_chunks(cls, ctx: Context, voxel_extent: float, grid_shape, voxels: np.ndarray,
+                              sparseness: np.ndarray) -> "VoxelObject":
+        """`VoxelObject::generate` for a host-side `ChunkedVoxelGenerator` given as data (object.rs:361-404):
+        `voxels` = (n_chunks, 4096) `Voxel`s in linear chunk order, `sparseness` = per chunk bit 0
+        has_only_empty_voxels, bit 1 is_void. Classification and all derived state are computed on the device."""
+        gs = np.asarray(grid_shape, np.uint32)
+        voxels = np.ascontiguousarray(voxels, L.VOXEL_DTYPE)
+        sparseness = np.ascontiguousarray(sparseness, np.uint8)
+        n = int(np.prod((gs + 15) // 16))
+        assert voxels.size == n * 4096 and sparseness.size == n
+        h = C.c_void_p()
+        ctx.check(ctx._lib.ivx_object_from_generated_chunks(ctx.h, C.c_float(voxel_extent), L.ptr(gs), L.ptr(voxels),
+                                                            L.ptr(sparseness), C.byref(h)))
+        return cls(ctx, h)
+
     def free(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx._lib.ivx_object_free(self.ctx.h, self.h)

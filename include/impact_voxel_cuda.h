@@ -262,6 +262,20 @@ int ivx_object_generate_streamed(ivx_ctx* ctx, const ivx_program* program, float
                                  ivx_voxel* host_voxels, size_t voxel_capacity, ivx_object** out_object,
                                  uint64_t* out_non_uniform_chunks);
 
+/* VoxelObject::generate (object.rs:239-244 → generate_voxels_for_chunks :361-404) for a host-side
+ * `ChunkedVoxelGenerator` (generation.rs:41-67) — any generator other than the SDF one, e.g. the reference's
+ * OffsetBoxVoxelGenerator / ManualVoxelGenerator fixtures (object.rs:3387-3561) or voxels loaded from elsewhere: the host
+ * calls its generator's generate_chunk for every chunk of the grid and hands over what it returned,
+ *   voxels      4096 `Voxel`s per chunk, chunks in x-major linear order, voxels in the order i*256 + j*16 + k
+ *   sparseness  one byte per chunk: bit 0 ChunkSparseness::has_only_empty_voxels, bit 1 ::is_void
+ * and the device does the rest of generate(): VoxelChunk::create_for_generated_voxels (object.rs:1890-1964),
+ * update_occupied_voxel_ranges and compute_all_derived_state. chunk_counts = ceil(grid_shape / 16). The result is an
+ * ordinary object (mesh, absorb, connected regions, extraction, inertial moments, download). Voxels of non-void chunks
+ * must satisfy the invariant of the reference's `Voxel` constructors (EMPTY flag ⇔ signed-distance code >= 0, lib.rs:
+ * 300-348); IVX_ERR_INVALID_ARGUMENT otherwise. */
+int ivx_object_from_generated_chunks(ivx_ctx* ctx, float voxel_extent, const uint32_t grid_shape[3],
+                                     const ivx_voxel* voxels, const uint8_t* sparseness, ivx_object** out_object);
+
 /* Multi-GPU: generate only chunk planes [chunk_i_begin, chunk_i_end) of the
  * x-major chunk grid (the reference's thread split of the linear chunk index,
  * object.rs:423-427). The object also reserves one halo chunk plane on each

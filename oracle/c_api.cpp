@@ -207,6 +207,19 @@ void* orc_object_from_dense(const int8_t* sd, const uint8_t* types, const uint32
     return objp;
 }
 
+// VoxelObject::generate for a ChunkedVoxelGenerator given as data (the reference's test fixtures OffsetBoxVoxelGenerator /
+// ManualVoxelGenerator, object.rs:3387-3561, or any other): raw chunks → classification → occupied ranges → derived state
+void* orc_object_from_generated_chunks(const Voxel* voxels, const uint8_t* sparseness, const uint32_t grid_shape[3],
+                                       float voxel_extent, int derive) {
+    Object* o = new Object();
+    object_from_generated_chunks(voxels, sparseness, grid_shape, voxel_extent, *o);
+    if (derive) {
+        update_occupied_voxel_ranges(*o);
+        compute_all_derived_state(*o);
+    }
+    return o;
+}
+
 void orc_object_info(const void* op, uint32_t chunk_counts[3], uint64_t* n_voxels, uint32_t occ_chunks[6],
                      uint32_t occ_voxels[6]) {
     const Object* obj = (const Object*)op;

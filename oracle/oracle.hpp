@@ -220,6 +220,10 @@ void generate_without_derived_state(const VoxelGenerator& vg, Object& obj, int n
 void generate_slab_without_derived_state(const VoxelGenerator& vg, Object& obj, int n_threads,
                                          uint32_t plane_begin, uint32_t plane_end);
 void update_occupied_voxel_ranges(Object& obj);
+// generate_without_derived_state for a generator whose chunks are given as data (sparseness: bit 0 has_only_empty_voxels,
+// bit 1 is_void per chunk)
+void object_from_generated_chunks(const Voxel* voxels, const uint8_t* sparseness, const uint32_t grid_shape[3],
+                                  float voxel_extent, Object& obj);
 void update_occupied_chunk_ranges(Object& obj);
 void compute_all_derived_state(Object& obj);
 void update_internal_adjacencies(Voxel* chunk_voxels);

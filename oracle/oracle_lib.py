@@ -177,6 +177,19 @@ class Object:
         shape = np.asarray(sd.shape, np.uint32)
         return cls(lib().orc_object_from_dense(_p(sd), _p(types), _p(shape), C.c_float(voxel_extent)))
 
+    @classmethod
+    def from_generated_chunks(cls, voxels: np.ndarray, sparseness: np.ndarray, grid_shape, voxel_extent: float = 1.0,
+                              derive: bool = True) -> "Object":
+        """`VoxelObject::generate` (derive=True) / `generate_without_derived_state` for a `ChunkedVoxelGenerator` given
+        as data: `voxels` = (n_chunks, 4096) VOXEL_DTYPE in linear chunk order, `sparseness` = per chunk bit 0
+        has_only_empty_voxels, bit 1 is_void (generation.rs:41-67, object.rs:361-404)."""
+        voxels = np.ascontiguousarray(voxels, VOXEL_DTYPE)
+        sparseness = np.ascontiguousarray(sparseness, np.uint8)
+        gs = np.asarray(grid_shape, np.uint32)
+        lib().orc_object_from_generated_chunks.restype = C.c_void_p
+        return cls(lib().orc_object_from_generated_chunks(_p(voxels), _p(sparseness), _p(gs), C.c_float(voxel_extent),
+                                                          C.c_int(1 if derive else 0)))
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_object_free(self.h)

@@ -179,6 +179,54 @@ static inline bool chunk_only_empty(const Chunk& c) {
     return c.kind == CK_VOID || (c.kind == CK_NONUNIFORM && (c.flags & CF_ONLY_EMPTY));
 }
 
+// analyze_and_initialize_chunks (object.rs:560-617): data offsets in chunk order, chunk-granular occupied ranges
+static void analyze_and_initialize_chunks(Object& obj) {
+    const uint32_t total = (uint32_t)obj.chunks.size();
+    uint32_t nu = 0;
+    uint32_t lo[3] = {UINT32_MAX, UINT32_MAX, UINT32_MAX}, hi[3] = {0, 0, 0};
+    bool any = false;
+    for (uint32_t ci = 0; ci < total; ++ci) {
+        Chunk& c = obj.chunks[ci];
+        if (c.kind == CK_NONUNIFORM) c.data_offset = nu++;
+        if (!chunk_only_empty(c)) {
+            uint32_t ijk[3] = {ci / (obj.chunk_counts[2] * obj.chunk_counts[1]),
+                               (ci / obj.chunk_counts[2]) % obj.chunk_counts[1],
+                               ci % obj.chunk_counts[2]};
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = std::min(lo[d], ijk[d]);
+                hi[d] = std::max(hi[d], ijk[d] + 1);
+            }
+            any = true;
+        }
+    }
+    for (int d = 0; d < 3; ++d) {
+        obj.occ_chunks[d][0] = any ? lo[d] : 0;
+        obj.occ_chunks[d][1] = any ? hi[d] : 0;
+        obj.occ_voxels[d][0] = obj.occ_chunks[d][0] * 16;
+        obj.occ_voxels[d][1] = obj.occ_chunks[d][1] * 16;
+    }
+}
+
+// VoxelObject::generate_without_derived_state (object.rs:307-359 → generate_voxels_for_chunks :361-404) for any
+// ChunkedVoxelGenerator whose output is given as data: 4096 voxels and the ChunkSparseness per chunk, linear chunk order
+void object_from_generated_chunks(const Voxel* voxels, const uint8_t* sparseness, const uint32_t grid_shape[3],
+                                  float voxel_extent, Object& obj) {
+    obj = Object{};
+    obj.voxel_extent = voxel_extent;
+    for (int d = 0; d < 3; ++d) obj.chunk_counts[d] = (grid_shape[d] + 15) / 16;
+    const uint32_t total = obj.chunk_counts[0] * obj.chunk_counts[1] * obj.chunk_counts[2];
+    obj.chunks.assign(total, Chunk{});
+    if (total == 0) return;
+    for (uint32_t ci = 0; ci < total; ++ci) {
+        const Voxel* buf = voxels + (size_t)ci * CHUNK_VOXELS;
+        const Sparseness sp{(sparseness[ci] & 1) != 0, (sparseness[ci] & 2) != 0};
+        const Chunk c = classify_generated_chunk(buf, sp);
+        obj.chunks[ci] = c;
+        if (c.kind == CK_NONUNIFORM) obj.voxels.insert(obj.voxels.end(), buf, buf + CHUNK_VOXELS);
+    }
+    analyze_and_initialize_chunks(obj);
+}
+
 // ---- generate_voxels_for_chunks[_in_parallel] + analyze (object.rs:361-617) --
 void generate_without_derived_state(const VoxelGenerator& vg, Object& obj, int n_threads) {
     generate_slab_without_derived_state(vg, obj, n_threads, 0, (vg.grid_shape[0] + 15) / 16);
@@ -234,33 +282,9 @@ void generate_slab_without_derived_state(const VoxelGenerator& vg, Object& obj, 
     obj.voxels.reserve(nv);
     for (auto& p : parts) obj.voxels.insert(obj.voxels.end(), p.voxels.begin(), p.voxels.end());
 
-    // analyze_and_initialize_chunks
-    uint32_t nu = 0;
-    uint32_t lo[3] = {UINT32_MAX, UINT32_MAX, UINT32_MAX}, hi[3] = {0, 0, 0};
-    bool any = false;
-    for (uint32_t ci = 0; ci < total; ++ci) {
-        Chunk& c = obj.chunks[ci];
-        if (c.kind == CK_NONUNIFORM) c.data_offset = nu++;
-        if (!chunk_only_empty(c)) {
-            uint32_t ijk[3] = {ci / (obj.chunk_counts[2] * obj.chunk_counts[1]),
-                               (ci / obj.chunk_counts[2]) % obj.chunk_counts[1],
-                               ci % obj.chunk_counts[2]};
-            for (int d = 0; d < 3; ++d) {
-                lo[d] = std::min(lo[d], ijk[d]);
-                hi[d] = std::max(hi[d], ijk[d] + 1);
-            }
-            any = true;
-        }
-    }
-    for (int d = 0; d < 3; ++d) {
-        obj.occ_chunks[d][0] = any ? lo[d] : 0;
-        obj.occ_chunks[d][1] = any ? hi[d] : 0;
-        obj.occ_voxels[d][0] = obj.occ_chunks[d][0] * 16;
-        obj.occ_voxels[d][1] = obj.occ_chunks[d][1] * 16;
-    }
+    analyze_and_initialize_chunks(obj);
 }
 
-// ---- occupied ranges (object.rs:1149-1280) ----------------------------------
 void update_occupied_chunk_ranges(Object& obj) {
     uint32_t lo[3] = {UINT32_MAX, UINT32_MAX, UINT32_MAX}, hi[3] = {0, 0, 0};
     bool any = false;

@@ -242,3 +242,90 @@ GOLDEN_OBJECTS = {
     "noisy_box": (lambda: noisy_box_graph(38.0, 8), "SAME0"),
 }
 
+
+
+# ---- the reference's fake generators (object.rs:3387-3561) as data -------------------------------------
+
+INSIDE = (0, -128, 0)      # Voxel::maximally_inside(VoxelType::default())
+OUTSIDE = (255, 127, 1)    # Voxel::maximally_outside()
+
+
+def _chunks_from_dense(types, sd, flags, grid_shape):
+    """Cuts dense (type, sd, flags) grids padded to whole chunks into the per-chunk arrays a ChunkedVoxelGenerator
+    returns: (n_chunks, 4096) voxels in linear chunk order + a ChunkSparseness byte per chunk computed the way the
+    reference's fixtures do (has_only_empty_voxels: no non-empty voxel; is_void: every voxel maximally outside)."""
+    from impact_b200._lib import VOXEL_DTYPE
+
+    cc = [(int(s) + 15) // 16 for s in grid_shape]
+    n = cc[0] * cc[1] * cc[2]
+    vox = np.zeros((n, 4096), VOXEL_DTYPE)
+    sp = np.zeros(n, np.uint8)
+    for c in range(n):
+        i, j, k = c // (cc[1] * cc[2]), (c // cc[2]) % cc[1], c % cc[2]
+        sl = (slice(16 * i, 16 * i + 16), slice(16 * j, 16 * j + 16), slice(16 * k, 16 * k + 16))
+        vox[c]["type"] = types[sl].reshape(-1)
+        vox[c]["sd"] = sd[sl].reshape(-1)
+        vox[c]["flags"] = flags[sl].reshape(-1)
+        only_empty = bool(((flags[sl] & 1) != 0).all())
+        is_void = bool((sd[sl] == 127).all())
+        sp[c] = (1 if only_empty else 0) | (2 if is_void else 0)
+    return vox, sp
+
+
+def offset_box_chunks(shape, offset=(0, 0, 0), voxel=INSIDE):
+    """`OffsetBoxVoxelGenerator::new(shape, offset, voxel)` → (voxels, sparseness, grid_shape)."""
+    grid = [int(o) + int(s) for o, s in zip(offset, shape)]
+    cc = [(g + 15) // 16 for g in grid]
+    full = tuple(16 * c for c in cc)
+    ty = np.full(full, OUTSIDE[0], np.uint8)
+    sd = np.full(full, OUTSIDE[1], np.int8)
+    fl = np.full(full, OUTSIDE[2], np.uint8)
+    sl = tuple(slice(int(o), int(o) + int(s)) for o, s in zip(offset, shape))
+    ty[sl], sd[sl], fl[sl] = voxel
+    return (*_chunks_from_dense(ty, sd, fl, grid), grid)
+
+
+def manual_chunks(cells, offset=(0, 0, 0)):
+    """`ManualVoxelGenerator::<N>::with_offset(cells, offset)`: non-zero cells are maximally inside voxels."""
+    cells = np.asarray(cells, np.uint8)
+    grid = [int(o) + cells.shape[d] for d, o in enumerate(offset)]
+    cc = [(g + 15) // 16 for g in grid]
+    full = tuple(16 * c for c in cc)
+    ty = np.full(full, OUTSIDE[0], np.uint8)
+    sd = np.full(full, OUTSIDE[1], np.int8)
+    fl = np.full(full, OUTSIDE[2], np.uint8)
+    sl = tuple(slice(int(o), int(o) + cells.shape[d]) for d, o in enumerate(offset))
+    solid = cells != 0
+    ty[sl] = np.where(solid, INSIDE[0], OUTSIDE[0])
+    sd[sl] = np.where(solid, INSIDE[1], OUTSIDE[1])
+    fl[sl] = np.where(solid, INSIDE[2], OUTSIDE[2])
+    return (*_chunks_from_dense(ty, sd, fl, grid), grid)
+
+
+def random_voxel_chunks(shape, seed, n_types=4, fill=0.5, blobs=True):
+    """A fuzz generator: random signed-distance codes (negative = non-empty, the `Voxel` invariant), random types, with
+    whole-chunk regions forced solid / void so that Uniform and Void chunks and their conversions occur."""
+    rng = np.random.default_rng(seed)
+    cc = [(int(s) + 15) // 16 for s in shape]
+    full = tuple(16 * c for c in cc)
+    if blobs:
+        # smooth random field → connected blobs with noisy distance codes
+        coarse = rng.normal(size=tuple(c * 2 + 1 for c in cc))
+        from scipy.ndimage import zoom
+        field = zoom(coarse, [f / s for f, s in zip(full, coarse.shape)], order=1)
+        field = field + 0.35 * rng.normal(size=full) + (0.5 - fill)
+    else:
+        field = rng.normal(size=full) + (0.5 - fill) * 2.0
+    sd = np.clip(np.round(field * 60.0), -128, 127).astype(np.int8)
+    ty = rng.integers(0, n_types, full).astype(np.uint8)
+    # a solid block of whole chunks (Uniform candidates) and a void block
+    if cc[0] >= 3:
+        sd[16:32, 0:32, 0:32] = -128
+        ty[16:32, 0:32, 0:32] = 1
+    sd[-16:, -16:, :] = 127
+    inside = np.zeros(full, bool)
+    inside[tuple(slice(0, int(s)) for s in shape)] = True
+    sd[~inside] = 127
+    fl = np.where(sd >= 0, 1, 0).astype(np.uint8)
+    ty = np.where(sd == 127, 255, ty).astype(np.uint8)
+    return (*_chunks_from_dense(ty, sd, fl, shape), list(map(int, shape)))
