@@ -67,7 +67,7 @@ def test_empty_grid_and_invalid_voxels(ctx):
     g = VoxelObject.from_generated_chunks(ctx, 0.25, grid, vox, sp)
     assert g.info()["chunk_counts"] == (0, 0, 0) and VoxelObjectMesh.create(g).n_vertices == 0
     vox, sp, grid = H.offset_box_chunks([5, 5, 5])
-    vox[0]["flags"][7] = 1  # EMPTY flag on a voxel with a negative distance: not a `Voxel` any constructor makes
+    vox[0]["flags"][0] = 1  # EMPTY flag on a voxel with a negative distance: not a `Voxel` any constructor makes
     with pytest.raises(Exception, match="EMPTY"):
         VoxelObject.from_generated_chunks(ctx, 0.25, grid, vox, sp)
     with pytest.raises(Exception):
