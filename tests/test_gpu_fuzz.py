@@ -1,0 +1,121 @@
+"""Seeded fuzz parity on the GPU. The reference's fuzz targets (impact_voxel/fuzz/fuzz_targets/*.rs, generators in
+generation.rs:374-527) draw one random primitive — sphere, capsule or box of size up to 200 with a fractional part —
+a random voxel extent and a random voxel type generator, then assert the structural invariants. Here the same
+distribution (the reference's own MAX_SIZE of 200) and random composite graphs over every node kind are generated
+by the CUDA path and compared with the oracle bit for bit: per-chunk signed distances, the voxel object, the mesh; the
+invariants are asserted on the GPU output as well."""
+import numpy as np
+import pytest
+
+import helpers as H
+import invariants as INV
+from impact_b200.graph import SDFGraph, VoxelTypeGenerator
+from impact_b200.voxel import SDFVoxelGenerator, VoxelObject, VoxelObjectMesh
+
+pytestmark = pytest.mark.gpu
+
+
+def _size(rng, lo, hi):
+    return float(rng.integers(lo, hi + 1)) + float(np.float32(rng.random()))  # clamp(1, MAX) as f32 + norm_f32
+
+
+def random_primitive(g: SDFGraph, rng, max_size):
+    kind = int(rng.integers(0, 3))
+    if kind == 0:
+        return g.sphere(_size(rng, 1, max_size // 2 - 1))
+    if kind == 1:
+        return g.capsule(_size(rng, 1, max_size // 2 - 1), _size(rng, 1, max_size // 3))
+    return g.box([_size(rng, 1, max_size - 1) for _ in range(3)])
+
+
+def random_types(rng):
+    if rng.random() < 0.4:
+        return VoxelTypeGenerator.same(int(rng.integers(0, 200)))
+    n = int(rng.integers(1, 9))
+    return VoxelTypeGenerator.gradient_noise(list(range(n)), float(rng.uniform(0.005, 0.2)), float(rng.uniform(0.1, 3.0)),
+                                             int(rng.integers(0, 1000)))
+
+
+def random_graph(g: SDFGraph, rng, depth, size):
+    """A random tree over all ten node kinds; shared sub-graphs now and then (DAG unrolling)."""
+    r = rng.random()
+    if depth == 0 or r < 0.2:
+        node = random_primitive(g, rng, size)
+    elif r < 0.55:
+        a = random_graph(g, rng, depth - 1, size)
+        b = a if rng.random() < 0.1 else random_graph(g, rng, depth - 1, max(6, size // 2))
+        if rng.random() < 0.8:
+            b = g.translation(b, [float(x) for x in rng.uniform(-0.4 * size, 0.4 * size, 3)])
+        k = float(rng.choice([0.0, 0.0, 0.5, 2.0, 6.0]))
+        node = [g.union, g.subtraction, g.intersection][int(rng.integers(0, 3))](a, b, k)
+    elif r < 0.7:
+        node = g.multifractal_noise(random_graph(g, rng, depth - 1, size), int(rng.integers(1, 5)),
+                                    float(rng.uniform(0.02, 0.3)), float(rng.choice([2.0, 2.5, 3.0])),
+                                    float(rng.uniform(0.3, 0.7)), float(rng.uniform(0.3, 4.0)), int(rng.integers(0, 100)))
+    elif r < 0.8:
+        node = g.scaling(random_graph(g, rng, depth - 1, size), float(rng.uniform(0.6, 1.6)))
+    elif r < 0.9:
+        node = g.rotation_from_axis_angle(random_graph(g, rng, depth - 1, size), [float(x) for x in rng.normal(size=3)],
+                                          float(rng.uniform(0, 6.28)))
+    else:
+        node = g.translation(random_graph(g, rng, depth - 1, size), [float(x) for x in rng.uniform(-8, 8, 3)])
+    return node
+
+
+def _compare(ctx, oracle, g, types, extent):
+    gen_gpu = ctx.build_generator(g)
+    gen_cpu = oracle.Generator(g.nodes(), g.root_node_id)
+    vg = oracle.VoxelGenerator(gen_cpu, extent, types)
+    if max(vg.grid_shape) > 260 or min(vg.grid_shape) == 0:
+        pytest.skip(f"grid {vg.grid_shape} outside the size the oracle finishes quickly")
+    cc = [(s + 15) // 16 for s in vg.grid_shape]
+    origins = np.array([[i, j, k] for i in range(cc[0]) for j in range(cc[1]) for k in range(cc[2])], np.float32) * 16
+    if len(origins) > 48:
+        origins = origins[np.random.default_rng(0).choice(len(origins), 48, replace=False)]
+    lo = origins - vg.shifted_center
+    got = gen_gpu.compute_signed_distances_for_chunks(lo)
+    for row, o in zip(got, lo):
+        want, _ = gen_cpu.eval_chunk(o)
+        assert H.f32_bits_equal(row, want).all(), f"signed distances differ in the chunk at {o}"
+    obj_cpu = oracle.Object.generate(vg, 4)
+    obj_gpu = VoxelObject.generate(SDFVoxelGenerator(extent, gen_gpu, types))
+    ch, vx = obj_gpu.download()
+    H.assert_objects_equal(ch, vx, obj_cpu.chunks(), obj_cpu.voxels())
+    info = obj_gpu.info()
+    assert np.array_equal(info["occupied_voxel_ranges"], obj_cpu.info()["occupied_voxel_ranges"])
+    H.assert_meshes_equal(VoxelObjectMesh.create(obj_gpu).download(), obj_cpu.mesh(4))
+    INV.validate_adjacencies(ch, vx, info["chunk_counts"])
+    INV.validate_chunk_obscuredness(ch, info["chunk_counts"])
+    INV.validate_occupied_voxel_ranges(ch, vx, info["chunk_counts"], info["occupied_voxel_ranges"])
+    return obj_gpu, obj_cpu
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_single_primitives_like_the_reference_fuzzer(ctx, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    g = SDFGraph()
+    random_primitive(g, rng, 200 if seed % 3 else 14)  # every third case: objects of a chunk or less
+    extent = float(np.float32(10.0 * max(rng.random(), 1e-6)))
+    obj_gpu, obj_cpu = _compare(ctx, oracle, g, random_types(rng), extent)
+    # absorbing_voxels_within_sphere / _capsule targets: a random absorber, then the same checks
+    shape = np.array(obj_cpu.info()["chunk_counts"]) * 16.0
+    c = (shape * rng.uniform(0.2, 0.8, 3)).astype(np.float32)
+    r = float(rng.uniform(1.0, 0.3 * shape.max()))
+    assert obj_gpu.absorb_sphere(c, r, r + 2.0)["emptied_voxels"] == obj_cpu.absorb_sphere(c, r, r + 2.0)["emptied_voxels"]
+    v = (shape * rng.uniform(-0.5, 0.5, 3)).astype(np.float32)
+    obj_gpu.absorb_capsule(c, v, 0.5 * r, 0.5 * r + 2.0)
+    obj_cpu.absorb_capsule(c, v, 0.5 * r, 0.5 * r + 2.0)
+    ch, vx = obj_gpu.download()
+    H.assert_objects_equal(ch, vx, obj_cpu.chunks(), obj_cpu.voxels())
+    cc = obj_gpu.info()["chunk_counts"]
+    INV.validate_adjacencies(ch, vx, cc)
+    INV.validate_occupied_voxel_ranges(ch, vx, cc, obj_gpu.info()["occupied_voxel_ranges"])
+    H.assert_meshes_equal(VoxelObjectMesh.create(obj_gpu).download(), obj_cpu.mesh(4))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_composite_graphs_are_bit_exact(ctx, oracle, seed):
+    rng = np.random.default_rng(2000 + seed)
+    g = SDFGraph()
+    random_graph(g, rng, int(rng.integers(2, 6)), int(rng.integers(20, 90)))
+    _compare(ctx, oracle, g, random_types(rng), 1.0)
