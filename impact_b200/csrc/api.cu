@@ -1422,8 +1422,13 @@ int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* obj, float* positions, flo
     return IVX_OK;
 }
 
+// voxel ranges given by the caller instead of derived from a shape (modify_voxels_within_ranges), with the closure's inputs
+struct ExplicitRanges {
+    uint32_t v0[3], v1[3];
+    ivx::MutualArgs mutual;
+};
 static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats,
-                       const InertialUpdate* upd = nullptr);
+                       const InertialUpdate* upd = nullptr, const ExplicitRanges* er = nullptr);
 
 // ---- mesh gather over peer memory (multi-GPU) ------------------------------------------------------------
 int ivx_peer_alloc(ivx_ctx* ctx, size_t bytes, void** out_ptr, unsigned char out_handle[64]) {
@@ -1549,6 +1554,79 @@ int ivx_object_absorb_capsule_inertial(ivx_ctx* ctx, ivx_object* obj, const floa
     return absorb_impl(ctx, obj, capsule_shape(segment_start, segment_vector, radius, influence_radius), out_stats, &upd);
 }
 
+int ivx_objects_absorb_mutually(ivx_ctx* ctx, ivx_object* a, ivx_object* b, const ivx_isometry* transform_from_b_to_a,
+                                float smoothness, const uint32_t ranges_in_a[6], const uint32_t ranges_in_b[6],
+                                const float* voxel_type_densities, uint32_t n_densities, ivx_inertial_moments* inout_a,
+                                ivx_inertial_moments* inout_b, ivx_absorb_stats* stats_a, ivx_absorb_stats* stats_b) {
+    if (!ctx || !a || !b || a == b || !transform_from_b_to_a || !ranges_in_a || !ranges_in_b) return IVX_ERR_INVALID_ARGUMENT;
+    const bool inertial = inout_a || inout_b;
+    if (inertial && (!inout_a || !inout_b || (!voxel_type_densities && n_densities) || n_densities > 256))
+        return IVX_ERR_INVALID_ARGUMENT;
+    if (!(smoothness >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (stats_a) std::memset(stats_a, 0, sizeof(*stats_a));
+    if (stats_b) std::memset(stats_b, 0, sizeof(*stats_b));
+    if (b->first_i != 0 || b->nb[0] != b->chunk_counts[0] || a->first_i != 0 || a->nb[0] != a->chunk_counts[0])
+        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "mutual absorption on a slab-partitioned object is not supported");
+    const float ea = a->voxel_extent, eb = b->voxel_extent;
+    const float inv_ea = 1.0f / ea, inv_eb = 1.0f / eb;  // inverse_voxel_extent = voxel_extent.recip() (object.rs:348)
+    const float b_dist_to_a = eb * inv_ea, a_dist_to_b = ea * inv_eb;
+    // the snapshot of A's signed distances: the intersection ranges padded by ceil(b_dist_to_a) voxels (absorption.rs:927-944)
+    const float pad_f = std::ceil(b_dist_to_a);
+    const uint32_t pad = !(pad_f > 0.0f) ? 0u : (pad_f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)pad_f);
+    ExplicitRanges ra{}, rb{};
+    uint64_t n_snap = 1;
+    for (int d = 0; d < 3; ++d) {
+        const uint32_t dim_a = a->chunk_counts[d] * 16u;
+        if (ranges_in_a[2 * d + 1] > dim_a || ranges_in_b[2 * d + 1] > b->chunk_counts[d] * 16u)
+            IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "intersection voxel range beyond the grid");
+        ra.v0[d] = ranges_in_a[2 * d] > pad ? ranges_in_a[2 * d] - pad : 0u;
+        ra.v1[d] = (uint32_t)std::min<uint64_t>((uint64_t)ranges_in_a[2 * d + 1] + pad, dim_a);
+        rb.v0[d] = ranges_in_b[2 * d];
+        rb.v1[d] = ranges_in_b[2 * d + 1];
+        n_snap *= ra.v1[d] > ra.v0[d] ? ra.v1[d] - ra.v0[d] : 0u;
+    }
+    Tmp tmp(ctx);
+    float* snapshot = tmp.get<float>((size_t)std::max<uint64_t>(n_snap, 1));
+    if (!snapshot) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mutual absorption: out of device memory for the snapshot");
+    {
+        const float max_f32 = 127.0f * 0.02f;  // VoxelSignedDistance::MAX_F32
+        uint32_t bits;
+        std::memcpy(&bits, &max_f32, 4);
+        if (n_snap) KL(ctx, launch_fill_u32(reinterpret_cast<uint32_t*>(snapshot), (uint32_t)n_snap, bits, ctx->stream));
+    }
+    ivx::MutualArgs m{};
+    for (int q = 0; q < 4; ++q) m.q[q] = transform_from_b_to_a->rotation[q];
+    for (int d = 0; d < 3; ++d) {
+        m.t[d] = transform_from_b_to_a->translation[d];
+        m.s0[d] = ra.v0[d];
+        m.s1[d] = ra.v1[d];
+        m.o_nb[d] = b->nb[d];
+    }
+    m.smoothness = smoothness;
+    m.qik = 0.25f / smoothness;
+    m.snapshot = snapshot;
+    m.o_chunks = b->d_chunks;
+    m.o_voxels = b->d_voxels;
+    ivx::AbsorbShape shape{};
+    // object A: every voxel of the padded ranges that is not maximally outside samples B's signed distance field
+    m.extent = ea;
+    m.inv_extent_other = inv_eb;
+    m.dist_scale = b_dist_to_a;
+    ra.mutual = m;
+    shape.capsule = 2;
+    const InertialUpdate ua{voxel_type_densities, n_densities, inout_a}, ub{voxel_type_densities, n_densities, inout_b};
+    if (n_snap > 0xFFFFFFFFull) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "snapshot of more than 2^32 voxels");
+    if (int rc = absorb_impl(ctx, a, shape, stats_a, inertial ? &ua : nullptr, &ra)) return rc;
+    // object B: samples A's snapshot
+    m.extent = eb;
+    m.inv_extent_other = inv_ea;
+    m.dist_scale = a_dist_to_b;
+    rb.mutual = m;
+    shape.capsule = 3;
+    return absorb_impl(ctx, b, shape, stats_b, inertial ? &ub : nullptr, &rb);
+}
+
 int ivx_object_absorb_capsule(ivx_ctx* ctx, ivx_object* obj, const float segment_start[3], const float segment_vector[3],
                               float radius, float influence_radius, ivx_absorb_stats* out_stats) {
     if (!ctx || !obj || !segment_start || !segment_vector) return IVX_ERR_INVALID_ARGUMENT;
@@ -1559,7 +1637,7 @@ int ivx_object_absorb_capsule(ivx_ctx* ctx, ivx_object* obj, const float segment
 }  // extern "C"
 
 static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& shape, ivx_absorb_stats* out_stats,
-                       const InertialUpdate* upd) {
+                       const InertialUpdate* upd, const ExplicitRanges* er) {
     using namespace ivx;
     const float influence_radius = shape.influence_radius;
     cudaSetDevice(ctx->device);
@@ -1571,7 +1649,16 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     // voxel_ranges_touching_aab (intersection.rs:766-784) on the occupied voxel ranges
     AbsorbRange r{};
     bool empty = false;
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; er && d < 3; ++d) {
+        // modify_voxels_within_ranges (intersection.rs:167-261): the ranges as given, chunk ranges encompassing them
+        if (er->v1[d] > obj->chunk_counts[d] * 16u) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "voxel range beyond the grid");
+        r.v0[d] = er->v0[d];
+        r.v1[d] = er->v1[d];
+        if (r.v0[d] >= r.v1[d]) empty = true;
+        r.c0[d] = r.v0[d] / 16;
+        r.c1[d] = (r.v1[d] + 15) / 16;
+    }
+    for (int d = 0; !er && d < 3; ++d) {
         // Sphere::compute_aabb / Capsule::compute_aabb (the union of the two end spheres' boxes)
         float lo = shape.center[d] - influence_radius, hi = shape.center[d] + influence_radius;
         if (shape.capsule) {
@@ -1617,6 +1704,7 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     aa.new_slot_ord = ord;
     aa.dirty = obj->d_dirty;
     aa.stats = counters + 1;
+    if (er) aa.mutual = er->mutual;
     if (upd) {
         aa.removed_cols = tmp.get<uint16_t>((size_t)n_range * 256);
         aa.removed_info = tmp.get<uint32_t>((size_t)n_range * 2);

@@ -181,8 +181,23 @@ struct AbsorbRange {
     uint32_t v0[3], v1[3];  // voxel range
 };
 // the absorbing shape in normalized voxel space: a sphere, or a capsule (segment start, segment vector)
+// mutual absorption between two objects (interaction/absorption.rs:891-1080): the object being modified samples the
+// other one's signed distances — B's voxels directly while A is modified (mode 2), A's pre-modification snapshot while B
+// is modified (mode 3)
+struct MutualArgs {
+    float q[4], t[3];          // transform_from_b_to_a: unit quaternion (x, y, z, w), translation
+    float extent;              // voxel extent of the object being modified
+    float inv_extent_other;    // inverse voxel extent of the other object
+    float dist_scale;          // mode 2: b_dist_to_a = extent_b / extent_a; mode 3: a_dist_to_b
+    float smoothness, qik;     // Smoothness { smoothness, 0.25 / smoothness }
+    const DevChunk* o_chunks;  // mode 2: object B
+    const unsigned char* o_voxels;
+    uint32_t o_nb[3];
+    float* snapshot;           // A's signed distances over the padded intersection ranges [s0, s1)
+    uint32_t s0[3], s1[3];
+};
 struct AbsorbShape {
-    int capsule;               // 0 sphere, 1 capsule
+    int capsule;               // 0 sphere, 1 capsule, 2 / 3 voxel ranges of a mutual absorption (object A / object B)
     float center[3];           // sphere centre / capsule segment start
     float seg[3];              // capsule segment vector
     float seg_over_len2[3];    // CapsulePointContainmentTester (capsule.rs:168-181)
@@ -205,6 +220,7 @@ struct AbsorbArgs {
     // range in its visiting order — 256 columns x 16 bits — and {count, voxel slot} per chunk
     uint16_t* removed_cols;
     uint32_t* removed_info;
+    MutualArgs mutual;  // shape.capsule >= 2
 };
 cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], const AbsorbRange& r, const AbsorbShape& shape,
                                uint32_t* need_slot, uint32_t n_range, cudaStream_t st);

@@ -31,7 +31,7 @@ __device__ __forceinline__ uint32_t sat_u32(float v) {
 //            trimmed capsule's AABB clipped to the chunk (voxel_ranges_touching_aab), intersection.rs:445-461
 __device__ __forceinline__ bool touched_range_in_chunk(const AbsorbShape& s, const AbsorbRange& r, const uint32_t cc[3],
                                                        uint32_t t0[3], uint32_t t1[3]) {
-    if (!s.capsule) {
+    if (s.capsule != 1) {  // sphere, or the voxel ranges of a mutual absorption (modify_voxels_within_ranges)
         for (int d = 0; d < 3; ++d) {
             t0[d] = max(cc[d] * 16u, r.v0[d]);
             t1[d] = min(cc[d] * 16u + 16u, r.v1[d]);
@@ -64,6 +64,98 @@ __device__ __forceinline__ bool touched_range_in_chunk(const AbsorbShape& s, con
         if (t0[d] >= t1[d]) any = false;
     }
     return any;
+}
+
+// ---- mutual absorption (interaction/absorption.rs:891-1094) ---------------------------------------------------
+// glam Quat::mul_vec3a, the order oracle_math.hpp's quat_rotate uses: v (w^2 - b.b) + b (2 v.b) + (b x v)(2 w)
+__device__ __forceinline__ f3 quat_rotate(float qx, float qy, float qz, float qw, f3 v) {
+    const f3 b = mk3(qx, qy, qz);
+    const float b2 = dot3(b, b);
+    const float s1 = qw * qw - b2, s2 = dot3(v, b) * 2.0f, s3 = qw * 2.0f;
+    const f3 c = mk3(b.y * v.z - b.z * v.y, b.z * v.x - b.x * v.z, b.x * v.y - b.y * v.x);
+    return mk3((v.x * s1 + b.x * s2) + c.x * s3, (v.y * s1 + b.y * s2) + c.y * s3, (v.z * s1 + b.z * s2) + c.z * s3);
+}
+// evaluate_sdf_from_corner_samples (object/sdf.rs:579-592); d[x << 2 | y << 1 | z]
+__device__ __forceinline__ float corner_samples(const float d[8], f3 o) {
+    const f3 ro = mk3(1.0f - o.x, 1.0f - o.y, 1.0f - o.z);
+    const float d00 = d[0] * ro.x + d[4] * o.x;
+    const float d01 = d[1] * ro.x + d[5] * o.x;
+    const float d10 = d[2] * ro.x + d[6] * o.x;
+    const float d11 = d[3] * ro.x + d[7] * o.x;
+    const float d0 = d00 * ro.y + d10 * o.y;
+    const float d1 = d01 * ro.y + d11 * o.y;
+    return d0 * ro.z + d1 * o.z;
+}
+// VoxelObject::voxel(i, j, k).signed_distance().to_f32() (object.rs:1050-1062)
+__device__ __forceinline__ float other_voxel_sd(const MutualArgs& m, uint32_t i, uint32_t j, uint32_t k) {
+    const DevChunk c = m.o_chunks[((i >> 4) * m.o_nb[1] + (j >> 4)) * m.o_nb[2] + (k >> 4)];
+    if (c.kind == 0) return sd_decode(127);
+    if (c.kind == 1) return sd_decode((int)c.u_sd);
+    return sd_decode((int)(int8_t)m.o_voxels[(size_t)c.slot * SLOT_BYTES + PLANE_SD + vidx((int)(i & 15u), (int)(j & 15u), (int)(k & 15u))]);
+}
+// a floored coordinate as the lower index of an interpolation cell: false when the cell [out, out + 1] is not inside
+// [lo, hi_exclusive). `sign_bit`: sample_voxel_object_sdf tests has_negative_component (the sign bit, so -0.0 is
+// rejected); the snapshot lookup casts to isize and compares (so -0.0 is index 0)
+__device__ __forceinline__ bool lower_index(float f, uint32_t lo, uint32_t hi_exclusive, uint32_t& out, bool sign_bit) {
+    if ((sign_bit ? sign_neg(f) : f < 0.0f) || !(f < 4294967040.0f)) return false;
+    out = (uint32_t)f;
+    return out >= lo && (uint64_t)out + 1u < (uint64_t)hi_exclusive;
+}
+// sample_voxel_object_sdf (object/sdf.rs:636-675) of object B at a position in B's normalized voxel space
+__device__ __forceinline__ float sample_other_sdf(const MutualArgs& m, f3 p) {
+    const f3 lc = mk3(p.x - 0.5f, p.y - 0.5f, p.z - 0.5f);
+    const f3 li = mk3(floorf(lc.x), floorf(lc.y), floorf(lc.z));
+    const f3 fo = lc - li;
+    uint32_t i, j, k;
+    if (!lower_index(li.x, 0u, m.o_nb[0] * 16u, i, true) || !lower_index(li.y, 0u, m.o_nb[1] * 16u, j, true) ||
+        !lower_index(li.z, 0u, m.o_nb[2] * 16u, k, true))
+        return sd_decode(127);
+    const float d[8] = {other_voxel_sd(m, i, j, k),         other_voxel_sd(m, i, j, k + 1),
+                        other_voxel_sd(m, i, j + 1, k),     other_voxel_sd(m, i, j + 1, k + 1),
+                        other_voxel_sd(m, i + 1, j, k),     other_voxel_sd(m, i + 1, j, k + 1),
+                        other_voxel_sd(m, i + 1, j + 1, k), other_voxel_sd(m, i + 1, j + 1, k + 1)};
+    return corner_samples(d, fo);
+}
+__device__ __forceinline__ size_t snapshot_index(const MutualArgs& m, uint32_t i, uint32_t j, uint32_t k) {
+    return ((size_t)(i - m.s0[0]) * (m.s1[1] - m.s0[1]) + (j - m.s0[1])) * (m.s1[2] - m.s0[2]) + (k - m.s0[2]);
+}
+// compute_subtracted_signed_distance (absorption.rs:1082-1094)
+__device__ __forceinline__ float subtracted_sd(float sd, float inside_other, float k, float qik) {
+    const float inter = fmaxf(sd, inside_other);
+    return op_combine(IVX_SUBTRACTION, sd, inter, k, qik);
+}
+// The closures of apply_mutual_absorption for the voxel (gi, gj, gk) with distance code `code`: false = not visited
+// (maximally outside, or — object B — outside A's snapshot); else `nsd` is the new signed distance.
+__device__ __forceinline__ bool mutual_closure(const MutualArgs& m, int mode, uint32_t gi, uint32_t gj, uint32_t gk, int code,
+                                               float& nsd) {
+    if (code == 127) return false;
+    const float sd = sd_decode(code);
+    const f3 c = mk3(((float)gi + 0.5f) * m.extent, ((float)gj + 0.5f) * m.extent, ((float)gk + 0.5f) * m.extent);
+    if (mode == 2) {
+        m.snapshot[snapshot_index(m, gi, gj, gk)] = sd;
+        // inverse_voxel_extent_b * transform_from_b_to_a.inverse_transform_point(center_in_a)
+        const f3 r = quat_rotate(-m.q[0], -m.q[1], -m.q[2], m.q[3], mk3(c.x - m.t[0], c.y - m.t[1], c.z - m.t[2]));
+        const f3 pb = mk3(m.inv_extent_other * r.x, m.inv_extent_other * r.y, m.inv_extent_other * r.z);
+        nsd = subtracted_sd(sd, sample_other_sdf(m, pb) * m.dist_scale, m.smoothness, m.qik);
+        return true;
+    }
+    // inverse_voxel_extent_a * transform_from_b_to_a.transform_point(center_in_b)
+    const f3 r = quat_rotate(m.q[0], m.q[1], m.q[2], m.q[3], c);
+    const f3 pa = mk3(m.inv_extent_other * (r.x + m.t[0]), m.inv_extent_other * (r.y + m.t[1]), m.inv_extent_other * (r.z + m.t[2]));
+    const f3 lc = mk3(pa.x - 0.5f, pa.y - 0.5f, pa.z - 0.5f);
+    const f3 li = mk3(floorf(lc.x), floorf(lc.y), floorf(lc.z));
+    const f3 fo = lc - li;
+    uint32_t i, j, k;
+    if (!lower_index(li.x, m.s0[0], m.s1[0], i, false) || !lower_index(li.y, m.s0[1], m.s1[1], j, false) ||
+        !lower_index(li.z, m.s0[2], m.s1[2], k, false))
+        return false;
+    const float* s = m.snapshot;
+    const float d[8] = {s[snapshot_index(m, i, j, k)],         s[snapshot_index(m, i, j, k + 1)],
+                        s[snapshot_index(m, i, j + 1, k)],     s[snapshot_index(m, i, j + 1, k + 1)],
+                        s[snapshot_index(m, i + 1, j, k)],     s[snapshot_index(m, i + 1, j, k + 1)],
+                        s[snapshot_index(m, i + 1, j + 1, k)], s[snapshot_index(m, i + 1, j + 1, k + 1)]};
+    nsd = subtracted_sd(sd, corner_samples(d, fo) * m.dist_scale, m.smoothness, m.qik);
+    return true;
 }
 
 __global__ void k_absorb_plan(const DevChunk* __restrict__ chunks, uint3 nb, AbsorbRange r, AbsorbShape shape,
@@ -127,9 +219,11 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
             const float px = (float)gi + 0.5f, py = (float)gj + 0.5f;
             for (uint32_t gk = t0[2]; gk < t1[2]; ++gk) {
                 const float pz = (float)gk + 0.5f;
-                float d2;
+                float d2 = 0.0f, nsd_mutual = 0.0f;
                 bool inside;
-                if (a.shape.capsule) {
+                if (a.shape.capsule >= 2) {
+                    inside = mutual_closure(a.mutual, a.shape.capsule, gi, gj, gk, (int)s_sd[vidx(ti, tj, (int)(gk & 15u))], nsd_mutual);
+                } else if (a.shape.capsule) {
                     // shortest_squared_distance_from_point_to_segment_if_contained (capsule.rs:225-250): boundary included
                     const f3 c0 = mk3(a.shape.center[0], a.shape.center[1], a.shape.center[2]);
                     const f3 sv = mk3(a.shape.seg[0], a.shape.seg[1], a.shape.seg[2]);
@@ -151,7 +245,7 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
                     const int idx = vidx(ti, tj, (int)(gk & 15u));
                     const bool was_empty = (s_fl[idx] & 1) != 0;
                     const float sphere_sd = sqrtf(d2) - a.shape.radius;
-                    const float nsd = fmaxf(sd_decode((int)s_sd[idx]), -sphere_sd);
+                    const float nsd = a.shape.capsule >= 2 ? nsd_mutual : fmaxf(sd_decode((int)s_sd[idx]), -sphere_sd);
                     const int code = sd_encode(nsd);
                     s_sd[idx] = (int8_t)code;
                     if (code >= 0) {

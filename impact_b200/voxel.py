@@ -384,6 +384,28 @@ class VoxelObject:
         return out[: cnt.value]
 
 
+def absorb_mutually(a: VoxelObject, b: VoxelObject, rotation_xyzw, translation, smoothness: float, ranges_in_a,
+                    ranges_in_b, voxel_type_densities=None, moments_a=None, moments_b=None):
+    """`apply_mutual_absorption` (interaction/absorption.rs:891-1080): `transform_from_b_to_a` = (unit quaternion
+    x, y, z, w; translation), the two 3 x 2 voxel ranges from `determine_voxel_ranges_encompassing_intersection`. With
+    densities, the two 10-float moment arrays are updated in place. → (stats_a, stats_b)."""
+    ctx = a.ctx
+    iso = np.concatenate([np.asarray(rotation_xyzw, np.float32), np.asarray(translation, np.float32)]).astype(np.float32)
+    ra = np.ascontiguousarray(ranges_in_a, np.uint32).reshape(6)
+    rb = np.ascontiguousarray(ranges_in_b, np.uint32).reshape(6)
+    sa, sb = L.AbsorbStats(), L.AbsorbStats()
+    dens = None if voxel_type_densities is None else np.ascontiguousarray(voxel_type_densities, np.float32)
+    if dens is not None:
+        for m in (moments_a, moments_b):
+            assert m.dtype == np.float32 and m.shape == (10,) and m.flags.c_contiguous
+    ctx.check(ctx._lib.ivx_objects_absorb_mutually(
+        ctx.h, a.h, b.h, L.ptr(iso), C.c_float(smoothness), L.ptr(ra), L.ptr(rb),
+        L.ptr(dens) if dens is not None else None, C.c_uint32(0 if dens is None else len(dens)),
+        L.ptr(moments_a) if dens is not None else None, L.ptr(moments_b) if dens is not None else None,
+        C.byref(sa), C.byref(sb)))
+    return ({f: getattr(sa, f) for f, _ in L.AbsorbStats._fields_}, {f: getattr(sb, f) for f, _ in L.AbsorbStats._fields_})
+
+
 class VoxelObjectMesh:
     """`VoxelObjectMesh` (mesh.rs:50-58): SoA buffers + chunk submesh table."""
 

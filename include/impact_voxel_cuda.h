@@ -187,6 +187,14 @@ typedef struct ivx_absorb_stats {
     uint32_t dirty_chunks; /* size of invalidated_mesh_chunk_indices after the call */
 } ivx_absorb_stats;
 
+/* `VoxelObjectInertialPropertyManager` (object/inertia.rs:19-25), see "inertial properties" below */
+typedef struct ivx_inertial_moments {
+    float mass;
+    float moments[3];
+    float moments_of_inertia[3];
+    float products_of_inertia[3];
+} ivx_inertial_moments;
+
 typedef struct ivx_ctx ivx_ctx;
 typedef struct ivx_program ivx_program;
 typedef struct ivx_object ivx_object;
@@ -370,6 +378,31 @@ int ivx_object_absorb_sphere(ivx_ctx* ctx, ivx_object* object, const float cente
 int ivx_object_absorb_capsule(ivx_ctx* ctx, ivx_object* object, const float segment_start[3],
                               const float segment_vector[3], float radius, float influence_radius,
                               ivx_absorb_stats* out_stats);
+/* ivx_objects_absorb_mutually replaces apply_mutual_absorption (interaction/absorption.rs:891-1080): two overlapping
+ * voxel objects subtract each other's volume. Object A's voxels in the intersection ranges (padded by
+ * ceil(extent_b / extent_a) voxels, the reference's snapshot ranges) sample B's signed distance field trilinearly
+ * (sample_voxel_object_sdf, object/sdf.rs:636-675) at their centre carried into B's frame; B's voxels sample a snapshot
+ * of A's distances taken before A was modified; both get sdf_subtraction(sd, max(sd, other), smoothness)
+ * (compute_subtracted_signed_distance, absorption.rs:1082-1094) through Voxel::set_signed_distance, then
+ * modify_voxels_within_ranges' bookkeeping (object/intersection.rs:167-261: internal state, removed chunks, invalidated
+ * meshes, boundary refresh).
+ *   transform_from_b_to_a   Isometry3 = transform_from_world_to_a * transform_from_world_to_b.inverted()
+ *   ranges_in_a / _in_b     [dim * 2 + {start, end}]: VoxelObject::determine_voxel_ranges_encompassing_intersection
+ *                           (object/intersection.rs:707-745), a function of the two occupied voxel ranges
+ *                           (ivx_object_info) and the transform that stays with the host's geometry code; when it
+ *                           returns None the host does not call
+ *   inout_a / inout_b       NULL, or both objects' inertial moments: updated like ivx_object_absorb_*_inertial
+ * The rotation follows glam's Quat::mul_vec3a operation order (third party, restated). */
+typedef struct ivx_isometry {
+    float rotation[4];    /* unit quaternion x, y, z, w */
+    float translation[3];
+} ivx_isometry;
+int ivx_objects_absorb_mutually(ivx_ctx* ctx, ivx_object* object_a, ivx_object* object_b,
+                                const ivx_isometry* transform_from_b_to_a, float smoothness,
+                                const uint32_t ranges_in_a[6], const uint32_t ranges_in_b[6],
+                                const float* voxel_type_densities, uint32_t n_densities,
+                                ivx_inertial_moments* inout_a, ivx_inertial_moments* inout_b,
+                                ivx_absorb_stats* stats_a, ivx_absorb_stats* stats_b);
 int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* object, uint32_t* out_linear_indices,
                             uint32_t capacity, uint32_t* out_count);
 int ivx_object_remesh_dirty(ivx_ctx* ctx, ivx_object* object, ivx_mesh_info* out);
@@ -461,12 +494,6 @@ int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* object, ivx
  *   per_chunk_terms    NULL, or room for ten floats per owned chunk in linear chunk order (zero for void chunks)
  * The derived quantities (centre of mass, inertia tensor about it: derive_inertial_properties, inertia.rs:160-167)
  * are a handful of host flops on these ten numbers and stay with the host. */
-typedef struct ivx_inertial_moments {
-    float mass;
-    float moments[3];
-    float moments_of_inertia[3];
-    float products_of_inertia[3];
-} ivx_inertial_moments;
 int ivx_object_inertial_moments(ivx_ctx* ctx, const ivx_object* object, const float* voxel_type_densities,
                                 uint32_t n_densities, const ivx_inertial_moments* initial, ivx_inertial_moments* out,
                                 float* per_chunk_terms, size_t per_chunk_capacity);

@@ -383,6 +383,25 @@ void orc_absorb_capsule_inertial(void* op, const float start[3], const float vec
                    &upd);
 }
 
+// apply_mutual_absorption (absorption.rs:891-1080); ranges = [dim*2 + {start,end}]; densities NULL → no inertial updaters
+void orc_absorb_mutually(void* ap, void* bp, const float q[4], const float t[3], float smoothness, const uint32_t ra[6],
+                         const uint32_t rb[6], const float* densities, float moments_a[10], float moments_b[10],
+                         AbsorbStats* stats_a, AbsorbStats* stats_b) {
+    Object& a = *(Object*)ap;
+    Object& b = *(Object*)bp;
+    uint32_t r_a[3][2], r_b[3][2];
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) {
+            r_a[d][s] = ra[2 * d + s];
+            r_b[d][s] = rb[2 * d + s];
+        }
+    InertialMoments dummy_a, dummy_b;
+    InertialUpdater ua(densities ? (InertialMoments*)moments_a : &dummy_a, a.voxel_extent, densities);
+    InertialUpdater ub(densities ? (InertialMoments*)moments_b : &dummy_b, b.voxel_extent, densities);
+    absorb_mutually(a, b, Isometry{Quat{q[0], q[1], q[2], q[3]}, v3(t[0], t[1], t[2])}, smoothness, r_a, r_b,
+                    densities ? &ua : nullptr, densities ? &ub : nullptr, stats_a, stats_b);
+}
+
 // ---- connected regions ----
 // Runs the whole detection on the object's current state. info (u32 x 24): n_regions, has_two, two[0], two[1],
 // smallest, overflow, n_region_entries, n_label_bytes, then per candidate region 8 words: chunk_count,

@@ -84,6 +84,31 @@ bool trim_capsule(const Shape& s, const uint32_t cc[3], V3& t_start, V3& t_vec) 
     return true;
 }
 
+// handle_chunk_voxels_modified (intersection.rs:539-598)
+void handle_chunk_voxels_modified(Object& obj, Chunk& chunk, Voxel* v, const uint32_t cc[3], uint32_t cidx,
+                                  const uint32_t vr[3][2], const uint32_t tv[3][2], AbsorbStats& st, bool& removed_chunks) {
+    st.touched_chunks++;
+    Sparseness sp = update_all_internal_state(chunk, v);
+    if (sp.is_void) {
+        chunk = Chunk{};
+        removed_chunks = true;
+        st.removed_chunks++;
+    }
+    obj.mark_dirty(cidx);
+    for (int d = 0; d < 3; ++d) {
+        if (cc[d] > 0 && tv[d][0] - vr[d][0] < 2) {
+            uint32_t a[3] = {cc[0], cc[1], cc[2]};
+            a[d] -= 1;
+            obj.mark_dirty(obj.lin(a[0], a[1], a[2]));
+        }
+        if (cc[d] + 1 < obj.chunk_counts[d] && vr[d][1] - tv[d][1] < 2) {
+            uint32_t a[3] = {cc[0], cc[1], cc[2]};
+            a[d] += 1;
+            obj.mark_dirty(obj.lin(a[0], a[1], a[2]));
+        }
+    }
+}
+
 void absorb_shape(Object& obj, const Shape& shape, AbsorbStats* stats, InertialUpdater* updater) {
     AbsorbStats st{0, 0, 0, 0};
     const V3 center = shape.start;
@@ -199,28 +224,7 @@ void absorb_shape(Object& obj, const Shape& shape, AbsorbStats* stats, InertialU
                                 touched = true;
                             }
                         }
-                if (touched) {
-                    st.touched_chunks++;
-                    Sparseness sp = update_all_internal_state(chunk, v);
-                    if (sp.is_void) {
-                        chunk = Chunk{};
-                        removed_chunks = true;
-                        st.removed_chunks++;
-                    }
-                    obj.mark_dirty(cidx);
-                    for (int d = 0; d < 3; ++d) {
-                        if (cc[d] > 0 && tv[d][0] - vr[d][0] < 2) {
-                            uint32_t a[3] = {ci, cj, ck};
-                            a[d] -= 1;
-                            obj.mark_dirty(obj.lin(a[0], a[1], a[2]));
-                        }
-                        if (cc[d] + 1 < obj.chunk_counts[d] && vr[d][1] - tv[d][1] < 2) {
-                            uint32_t a[3] = {ci, cj, ck};
-                            a[d] += 1;
-                            obj.mark_dirty(obj.lin(a[0], a[1], a[2]));
-                        }
-                    }
-                }
+                if (touched) handle_chunk_voxels_modified(obj, chunk, v, cc, cidx, vr, tv, st, removed_chunks);
             }
     if (removed_chunks) {
         update_occupied_chunk_ranges(obj);
@@ -245,6 +249,199 @@ void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius,
 void absorb_capsule(Object& obj, V3 segment_start, V3 segment_vector, float radius, float influence_radius,
                     AbsorbStats* stats, InertialUpdater* updater) {
     absorb_shape(obj, Shape{true, segment_start, segment_vector, radius, influence_radius}, stats, updater);
+}
+
+// ---- mutual absorption between two voxel objects ---------------------------------------------------------------
+//   VoxelObject::modify_voxels_within_ranges          V/object/intersection.rs:167-261
+//   VoxelObject::voxel                                V/object.rs:1050-1062
+//   sample_voxel_object_sdf, evaluate_sdf_from_corner_samples   V/object/sdf.rs:579-592, 636-675
+//   apply_mutual_absorption, compute_subtracted_signed_distance V/interaction/absorption.rs:891-1094
+//   Isometry3::transform_point / inverse_transform_point        impact_math/src/transform/isometry.rs:146-172
+namespace {
+
+template <typename F>
+void modify_voxels_within_ranges(Object& obj, const uint32_t r[3][2], AbsorbStats& st, F&& modify_voxel) {
+    for (int d = 0; d < 3; ++d)
+        if (r[d][0] >= r[d][1]) return;
+    uint32_t cr[3][2];
+    for (int d = 0; d < 3; ++d) {
+        cr[d][0] = r[d][0] / 16;
+        cr[d][1] = (r[d][1] + 15) / 16;
+    }
+    bool removed_chunks = false;
+    for (uint32_t ci = cr[0][0]; ci < cr[0][1]; ++ci)
+        for (uint32_t cj = cr[1][0]; cj < cr[1][1]; ++cj)
+            for (uint32_t ck = cr[2][0]; ck < cr[2][1]; ++ck) {
+                const uint32_t cidx = obj.lin(ci, cj, ck);
+                Chunk& chunk = obj.chunks[cidx];
+                if (chunk.kind == CK_VOID) continue;
+                if (chunk.kind == CK_UNIFORM) {
+                    size_t start = obj.voxels.size();
+                    obj.voxels.resize(start + CHUNK_VOXELS, chunk.uniform_voxel);
+                    chunk.kind = CK_NONUNIFORM;
+                    chunk.data_offset = (uint32_t)(start >> 12);
+                    for (int d = 0; d < 3; ++d) chunk.face[d][0] = chunk.face[d][1] = FD_FULL;
+                    chunk.flags = CF_OBSCURED_ALL;
+                }
+                const uint32_t cc[3] = {ci, cj, ck};
+                uint32_t vr[3][2], tv[3][2];
+                for (int d = 0; d < 3; ++d) {
+                    vr[d][0] = cc[d] * 16;
+                    vr[d][1] = (cc[d] + 1) * 16;
+                    tv[d][0] = std::max(vr[d][0], r[d][0]);
+                    tv[d][1] = std::min(vr[d][1], r[d][1]);
+                }
+                Voxel* v = obj.chunk_voxels(chunk.data_offset);
+                bool touched = false;
+                for (uint32_t i = tv[0][0]; i < tv[0][1]; ++i)
+                    for (uint32_t j = tv[1][0]; j < tv[1][1]; ++j)
+                        for (uint32_t k = tv[2][0]; k < tv[2][1]; ++k) {
+                            const uint32_t ijk[3] = {i, j, k};
+                            if (modify_voxel(ijk, v[vidx(i & 15, j & 15, k & 15)])) {
+                                touched = true;
+                                st.touched_voxels++;
+                            }
+                        }
+                if (touched) handle_chunk_voxels_modified(obj, chunk, v, cc, cidx, vr, tv, st, removed_chunks);
+            }
+    if (removed_chunks) {
+        update_occupied_chunk_ranges(obj);
+        update_occupied_voxel_ranges(obj);
+    }
+    uint32_t br[3][2];
+    for (int d = 0; d < 3; ++d) {
+        br[d][0] = cr[d][0] > 0 ? cr[d][0] - 1 : 0;
+        br[d][1] = cr[d][1];
+    }
+    update_upper_boundary_adjacencies_in_ranges(obj, br);
+}
+
+inline float voxel_sd(const Object& obj, uint32_t i, uint32_t j, uint32_t k) {
+    const Chunk& c = obj.chunks[obj.lin(i >> 4, j >> 4, k >> 4)];
+    if (c.kind == CK_VOID) return sd_decode(127);
+    if (c.kind == CK_UNIFORM) return sd_decode(c.uniform_voxel.sd);
+    return sd_decode(obj.chunk_voxels(c.data_offset)[vidx(i & 15, j & 15, k & 15)].sd);
+}
+
+inline float corner_samples(const float d[8], V3 o) {
+    const V3 ro = v3(1.0f - o.x, 1.0f - o.y, 1.0f - o.z);
+    const float d00 = d[0] * ro.x + d[4] * o.x;
+    const float d01 = d[1] * ro.x + d[5] * o.x;
+    const float d10 = d[2] * ro.x + d[6] * o.x;
+    const float d11 = d[3] * ro.x + d[7] * o.x;
+    const float d0 = d00 * ro.y + d10 * o.y;
+    const float d1 = d01 * ro.y + d11 * o.y;
+    return d0 * ro.z + d1 * o.z;
+}
+
+// `idx as isize` of a floored float (saturating) kept in 64 bits
+inline int64_t floor_index(float f) {
+    if (f != f) return 0;
+    if (f >= 9.2e18f) return INT64_MAX;
+    if (f <= -9.2e18f) return INT64_MIN;
+    return (int64_t)f;
+}
+
+float sample_object_sdf(const Object& obj, const uint32_t dims[3], V3 p) {
+    const V3 lc = v3(p.x - 0.5f, p.y - 0.5f, p.z - 0.5f);
+    const V3 li = v3(std::floor(lc.x), std::floor(lc.y), std::floor(lc.z));
+    const V3 fo = lc - li;
+    if (sign_neg(li.x) || sign_neg(li.y) || sign_neg(li.z)) return SD_MAX_F32;  // has_negative_component: sign bits
+    const uint64_t i = (uint64_t)floor_index(li.x), j = (uint64_t)floor_index(li.y), k = (uint64_t)floor_index(li.z);
+    if (i + 1 >= dims[0] || j + 1 >= dims[1] || k + 1 >= dims[2]) return SD_MAX_F32;
+    const uint32_t a = (uint32_t)i, b = (uint32_t)j, c = (uint32_t)k;
+    const float d[8] = {voxel_sd(obj, a, b, c),         voxel_sd(obj, a, b, c + 1),     voxel_sd(obj, a, b + 1, c),
+                        voxel_sd(obj, a, b + 1, c + 1), voxel_sd(obj, a + 1, b, c),     voxel_sd(obj, a + 1, b, c + 1),
+                        voxel_sd(obj, a + 1, b + 1, c), voxel_sd(obj, a + 1, b + 1, c + 1)};
+    return corner_samples(d, fo);
+}
+
+inline float subtracted_sd(float sd, float inside_other, float k, float qik) {
+    const float inter = std::fmax(sd, inside_other);
+    if (k == 0.0f) return std::fmax(sd, -inter);
+    // -smooth_sdf_union(-d1, d2)
+    const float d1 = -sd, d2 = inter;
+    const float h = std::fmax(k - std::fabs(d1 - d2), 0.0f);
+    return -(std::fmin(d1, d2) - (h * h) * qik);
+}
+
+// Voxel::set_signed_distance + the closures' callback; true if the voxel went from non-empty to empty
+inline void set_sd(Voxel& vx, float nsd, const uint32_t ijk[3], InertialUpdater* upd, AbsorbStats& st) {
+    const bool was_empty = vx.flags & FLAG_EMPTY;
+    vx.sd = sd_encode(nsd);
+    if (!(vx.sd < 0)) {
+        vx.flags |= FLAG_EMPTY;
+        if (!was_empty) {
+            st.emptied_voxels++;
+            if (upd) upd->remove_voxel(ijk, vx.type);
+        }
+    }
+}
+
+}  // namespace
+
+void absorb_mutually(Object& a, Object& b, Isometry b_to_a, float smoothness, const uint32_t ranges_a[3][2],
+                     const uint32_t ranges_b[3][2], InertialUpdater* upd_a, InertialUpdater* upd_b, AbsorbStats* stats_a,
+                     AbsorbStats* stats_b) {
+    AbsorbStats sa{0, 0, 0, 0}, sb{0, 0, 0, 0};
+    const float ea = a.voxel_extent, eb = b.voxel_extent;
+    const float inv_ea = 1.0f / ea, inv_eb = 1.0f / eb;  // VoxelObject::inverse_voxel_extent = voxel_extent.recip()
+    const float b_dist_to_a = eb * inv_ea, a_dist_to_b = ea * inv_eb;
+    const float qik = 0.25f / smoothness;
+    uint32_t dims_a[3], dims_b[3];
+    for (int d = 0; d < 3; ++d) {
+        dims_a[d] = a.chunk_counts[d] * 16;
+        dims_b[d] = b.chunk_counts[d] * 16;
+    }
+    const float pad_f = std::ceil(b_dist_to_a);
+    const uint32_t pad = !(pad_f > 0.0f) ? 0u : (pad_f >= 4294967296.0f ? UINT32_MAX : (uint32_t)pad_f);
+    uint32_t sr[3][2];
+    size_t n_snap = 1;
+    for (int d = 0; d < 3; ++d) {
+        sr[d][0] = ranges_a[d][0] > pad ? ranges_a[d][0] - pad : 0;
+        sr[d][1] = std::min<uint64_t>((uint64_t)ranges_a[d][1] + pad, dims_a[d]);
+        n_snap *= sr[d][1] > sr[d][0] ? sr[d][1] - sr[d][0] : 0;
+    }
+    std::vector<float> snapshot(n_snap, SD_MAX_F32);
+    const size_t sj = sr[1][1] > sr[1][0] ? sr[1][1] - sr[1][0] : 0, sk = sr[2][1] > sr[2][0] ? sr[2][1] - sr[2][0] : 0;
+    auto snap_idx = [&](uint32_t i, uint32_t j, uint32_t k) {
+        return ((size_t)(i - sr[0][0]) * sj + (j - sr[1][0])) * sk + (k - sr[2][0]);
+    };
+    const Quat q = b_to_a.q, qc = quat_conj(b_to_a.q);
+    const V3 t = b_to_a.t;
+
+    modify_voxels_within_ranges(a, sr, sa, [&](const uint32_t ijk[3], Voxel& vx) {
+        if (vx.sd == 127) return false;
+        const float sd_a = sd_decode(vx.sd);
+        snapshot[snap_idx(ijk[0], ijk[1], ijk[2])] = sd_a;
+        const V3 center_a = v3(((float)ijk[0] + 0.5f) * ea, ((float)ijk[1] + 0.5f) * ea, ((float)ijk[2] + 0.5f) * ea);
+        const V3 center_b = inv_eb * quat_rotate(qc, center_a - t);
+        const float inside_b = sample_object_sdf(b, dims_b, center_b) * b_dist_to_a;
+        set_sd(vx, subtracted_sd(sd_a, inside_b, smoothness, qik), ijk, upd_a, sa);
+        return true;
+    });
+
+    modify_voxels_within_ranges(b, ranges_b, sb, [&](const uint32_t ijk[3], Voxel& vx) {
+        if (vx.sd == 127) return false;
+        const V3 center_b = v3(((float)ijk[0] + 0.5f) * eb, ((float)ijk[1] + 0.5f) * eb, ((float)ijk[2] + 0.5f) * eb);
+        const V3 center_a = inv_ea * (quat_rotate(q, center_b) + t);
+        const V3 lc = v3(center_a.x - 0.5f, center_a.y - 0.5f, center_a.z - 0.5f);
+        const V3 lf = v3(std::floor(lc.x), std::floor(lc.y), std::floor(lc.z));
+        const V3 fo = lc - lf;
+        const int64_t li[3] = {floor_index(lf.x), floor_index(lf.y), floor_index(lf.z)};
+        for (int d = 0; d < 3; ++d)
+            if (li[d] < (int64_t)sr[d][0] || li[d] + 1 >= (int64_t)sr[d][1]) return false;
+        const uint32_t i = (uint32_t)li[0], j = (uint32_t)li[1], k = (uint32_t)li[2];
+        const float dd[8] = {snapshot[snap_idx(i, j, k)],         snapshot[snap_idx(i, j, k + 1)],
+                             snapshot[snap_idx(i, j + 1, k)],     snapshot[snap_idx(i, j + 1, k + 1)],
+                             snapshot[snap_idx(i + 1, j, k)],     snapshot[snap_idx(i + 1, j, k + 1)],
+                             snapshot[snap_idx(i + 1, j + 1, k)], snapshot[snap_idx(i + 1, j + 1, k + 1)]};
+        const float inside_a = corner_samples(dd, fo) * a_dist_to_b;
+        set_sd(vx, subtracted_sd(sd_decode(vx.sd), inside_a, smoothness, qik), ijk, upd_b, sb);
+        return true;
+    });
+    if (stats_a) *stats_a = sa;
+    if (stats_b) *stats_b = sb;
 }
 
 }  // namespace orc

@@ -328,6 +328,17 @@ void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius,
 void absorb_capsule(Object& obj, V3 segment_start, V3 segment_vector, float radius, float influence_radius,
                     AbsorbStats* stats, InertialUpdater* updater = nullptr);
 
+// apply_mutual_absorption (interaction/absorption.rs:891-1080) given the voxel ranges encompassing the intersection
+// (determine_voxel_ranges_encompassing_intersection, a pure function of the two occupied ranges and the transform that
+// stays with the caller): both objects subtract each other's volume.
+struct Isometry {
+    Quat q;  // unit quaternion x, y, z, w
+    V3 t;
+};
+void absorb_mutually(Object& a, Object& b, Isometry transform_from_b_to_a, float smoothness,
+                     const uint32_t ranges_in_a[3][2], const uint32_t ranges_in_b[3][2], InertialUpdater* updater_a,
+                     InertialUpdater* updater_b, AbsorbStats* stats_a, AbsorbStats* stats_b);
+
 // --- connected regions (object/split_detection.rs, object/extraction.rs:121-281) ---
 struct ChunkRegions {
     uint16_t region_count;           // local regions in the chunk (uniform chunk: 1)

@@ -381,6 +381,24 @@ def index_materials(vms):
     return [(out[8 * v: 8 * v + 4].copy(), out[8 * v + 4: 8 * v + 8].copy()) for v in range(3)]
 
 
+def absorb_mutually(a: "Object", b: "Object", rotation_xyzw, translation, smoothness: float, ranges_in_a, ranges_in_b,
+                    densities=None, moments_a=None, moments_b=None):
+    """`apply_mutual_absorption` (absorption.rs:891-1080) with the intersection voxel ranges given (3 x 2 each) and
+    `transform_from_b_to_a` = (unit quaternion x, y, z, w; translation). With `densities`, the two 10-float moment arrays
+    are updated in place by the inertial-property updaters. → (stats_a, stats_b)."""
+    q, t = np.asarray(rotation_xyzw, np.float32), np.asarray(translation, np.float32)
+    ra = np.ascontiguousarray(ranges_in_a, np.uint32).reshape(6)
+    rb = np.ascontiguousarray(ranges_in_b, np.uint32).reshape(6)
+    sa, sb = np.zeros(4, np.uint32), np.zeros(4, np.uint32)
+    dens = _densities(densities) if densities is not None else None
+    lib().orc_absorb_mutually(a.h, b.h, _p(q), _p(t), C.c_float(smoothness), _p(ra), _p(rb),
+                              _p(dens) if dens is not None else None,
+                              _p(moments_a) if dens is not None else None, _p(moments_b) if dens is not None else None,
+                              _p(sa), _p(sb))
+    keys = ("touched_chunks", "touched_voxels", "emptied_voxels", "removed_chunks")
+    return dict(zip(keys, map(int, sa))), dict(zip(keys, map(int, sb)))
+
+
 def _densities(densities) -> np.ndarray:
     """voxel_type_densities padded to 256 entries so that any u8 type indexes it (the reference would panic)."""
     d = np.zeros(256, np.float32)

@@ -329,3 +329,39 @@ def random_voxel_chunks(shape, seed, n_types=4, fill=0.5, blobs=True):
     fl = np.where(sd >= 0, 1, 0).astype(np.uint8)
     ty = np.where(sd == 127, 255, ty).astype(np.uint8)
     return (*_chunks_from_dense(ty, sd, fl, shape), list(map(int, shape)))
+
+
+# ---- mutual absorption fixtures -------------------------------------------------------------------------
+
+def quat_from_axis_angle(axis, angle):
+    """Unit quaternion (x, y, z, w) as float32."""
+    a = np.asarray(axis, np.float64)
+    a = a / np.linalg.norm(a)
+    s = np.sin(0.5 * angle)
+    return np.float32([a[0] * s, a[1] * s, a[2] * s, np.cos(0.5 * angle)])
+
+
+def _rotate(q, v):
+    x, y, z, w = [float(c) for c in q]
+    b = np.array([x, y, z])
+    return v * (w * w - b @ b) + b * (2.0 * (v @ b)) + np.cross(b, v) * (2.0 * w)
+
+
+def intersection_voxel_ranges(info_a, info_b, q, t):
+    """Voxel ranges encompassing the intersection of two objects' occupied boxes — a conservative stand-in for
+    `determine_voxel_ranges_encompassing_intersection` (intersection.rs:707-745): each object's occupied box is carried into
+    the other's frame, bounded, intersected with that object's occupied range and clamped. None when they miss."""
+    ea, eb = float(info_a["voxel_extent"]), float(info_b["voxel_extent"])
+    oa, ob = info_a["occupied_voxel_ranges"].astype(np.float64), info_b["occupied_voxel_ranges"].astype(np.float64)
+    qc = np.array([-q[0], -q[1], -q[2], q[3]])
+    corners = lambda o, e: np.array([[o[0, i] * e, o[1, j] * e, o[2, k] * e] for i in (0, 1) for j in (0, 1) for k in (0, 1)])
+    b_in_a = np.array([_rotate(q, c) + np.asarray(t, np.float64) for c in corners(ob, eb)]) / ea
+    a_in_b = np.array([_rotate(qc, c - np.asarray(t, np.float64)) for c in corners(oa, ea)]) / eb
+    out = []
+    for pts, occ in ((b_in_a, oa), (a_in_b, ob)):
+        lo = np.maximum(np.floor(pts.min(0)) - 1, occ[:, 0])
+        hi = np.minimum(np.ceil(pts.max(0)) + 1, occ[:, 1])
+        if (lo >= hi).any():
+            return None
+        out.append(np.stack([lo, hi], 1).astype(np.uint32))
+    return out
