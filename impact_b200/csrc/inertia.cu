@@ -233,8 +233,22 @@ __global__ void __launch_bounds__(256) k_moments_sum(const float* __restrict__ p
             const float* s = s_tile[t & 1] + tid;
             const int rows = (int)min((uint32_t)SUM_TILE, n_rows - t * SUM_TILE);
             if (rows == SUM_TILE) {
-#pragma unroll 32
-                for (int q = 0; q < SUM_TILE; ++q) acc += s[q * 10];
+                // the chain is one dependent FADD per row; the next 32 rows are fetched from shared memory while the
+                // current 32 are being added, so the chain never waits for a load
+                float cur[32], nxt[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) cur[u] = s[u * 10];
+#pragma unroll
+                for (int q0 = 0; q0 < SUM_TILE; q0 += 32) {
+                    if (q0 + 32 < SUM_TILE) {
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) nxt[u] = s[(q0 + 32 + u) * 10];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) acc += cur[u];
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) cur[u] = nxt[u];
+                }
             } else {
                 for (int q = 0; q < rows; ++q) acc += s[q * 10];
             }
