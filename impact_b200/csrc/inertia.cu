@@ -218,10 +218,21 @@ __global__ void __launch_bounds__(256) k_moments_sum(const float* __restrict__ p
     const uint32_t n_tiles = (n_rows + SUM_TILE - 1) / SUM_TILE;
     const float4* part4 = reinterpret_cast<const float4*>(part);
     auto stage = [&](uint32_t tile, int first_thread, int n_threads) {
-        const uint32_t v0 = tile * (SUM_TILE * 10u / 4u);
+        // all of a thread's loads are in flight before the first store: a tile costs one memory latency, not six
+        constexpr uint32_t TILE_VEC = SUM_TILE * 10u / 4u;
+        const uint32_t v0 = tile * TILE_VEC;
         float4* dst = reinterpret_cast<float4*>(s_tile[tile & 1]);
-        for (uint32_t v = (uint32_t)(tid - first_thread); v < SUM_TILE * 10u / 4u; v += (uint32_t)n_threads)
-            if (v0 + v < n_vec) dst[v] = part4[v0 + v];
+        float4 buf[6];  // 6 x 224 threads >= 1280 vectors
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const uint32_t v = (uint32_t)(tid - first_thread) + (uint32_t)(u * n_threads);
+            buf[u] = (v < TILE_VEC && v0 + v < n_vec) ? part4[v0 + v] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const uint32_t v = (uint32_t)(tid - first_thread) + (uint32_t)(u * n_threads);
+            if (v < TILE_VEC) dst[v] = buf[u];
+        }
     };
     if (n_tiles) stage(0, 0, 256);
     __syncthreads();
