@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_dirty_chunks", "ivx_object_remesh_dirty",
     "ivx_object_resolve_connected_regions", "ivx_object_split_detection_download", "ivx_object_extract_disconnected_region",
     "ivx_object_from_generated_chunks", "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",
-    "ivx_objects_absorb_mutually",
+    "ivx_objects_absorb_mutually", "ivx_intersection_voxel_ranges", "ivx_box_intersection_bounds",
 ]
 
 

@@ -384,6 +384,37 @@ class VoxelObject:
         return out[: cnt.value]
 
 
+def box_intersection_bounds(a_lower, a_upper, b_center, b_orientation_xyzw, b_half_extents):
+    """`compute_box_intersection_bounds` (impact_geometry/src/oriented_box.rs:315-431), host only → None or
+    ((lower, upper) in A's frame, (lower, upper) in B's frame relative to B's centre)."""
+    f = lambda v: np.ascontiguousarray(v, np.float32)
+    ia, ib = np.zeros(6, np.float32), np.zeros(6, np.float32)
+    hit = C.c_int()
+    rc = L.lib().ivx_box_intersection_bounds(L.ptr(f(a_lower)), L.ptr(f(a_upper)), L.ptr(f(b_center)),
+                                             L.ptr(f(b_orientation_xyzw)), L.ptr(f(b_half_extents)), L.ptr(ia), L.ptr(ib),
+                                             C.byref(hit))
+    if rc != L.IVX_OK:
+        raise L.IvxError(rc, "ivx_box_intersection_bounds")
+    return ((ia[:3], ia[3:]), (ib[:3], ib[3:])) if hit.value else None
+
+
+def intersection_voxel_ranges(occupied_a, voxel_extent_a: float, occupied_b, voxel_extent_b: float, rotation_xyzw,
+                              translation):
+    """`VoxelObject::determine_voxel_ranges_encompassing_intersection` (object/intersection.rs:707-745), host only:
+    occupied voxel ranges (3 x 2) of the two objects, their voxel extents and `transform_from_b_to_a` → None or the two
+    3 x 2 voxel ranges `absorb_mutually` takes."""
+    oa = np.ascontiguousarray(occupied_a, np.uint32).reshape(6)
+    ob = np.ascontiguousarray(occupied_b, np.uint32).reshape(6)
+    iso = np.concatenate([np.asarray(rotation_xyzw, np.float32), np.asarray(translation, np.float32)]).astype(np.float32)
+    ra, rb = np.zeros(6, np.uint32), np.zeros(6, np.uint32)
+    hit = C.c_int()
+    rc = L.lib().ivx_intersection_voxel_ranges(L.ptr(oa), C.c_float(voxel_extent_a), L.ptr(ob), C.c_float(voxel_extent_b),
+                                               L.ptr(iso), L.ptr(ra), L.ptr(rb), C.byref(hit))
+    if rc != L.IVX_OK:
+        raise L.IvxError(rc, "ivx_intersection_voxel_ranges")
+    return (ra.reshape(3, 2), rb.reshape(3, 2)) if hit.value else None
+
+
 def absorb_mutually(a: VoxelObject, b: VoxelObject, rotation_xyzw, translation, smoothness: float, ranges_in_a,
                     ranges_in_b, voxel_type_densities=None, moments_a=None, moments_b=None):
     """`apply_mutual_absorption` (interaction/absorption.rs:891-1080): `transform_from_b_to_a` = (unit quaternion

@@ -403,6 +403,19 @@ int ivx_objects_absorb_mutually(ivx_ctx* ctx, ivx_object* object_a, ivx_object* 
                                 const float* voxel_type_densities, uint32_t n_densities,
                                 ivx_inertial_moments* inout_a, ivx_inertial_moments* inout_b,
                                 ivx_absorb_stats* stats_a, ivx_absorb_stats* stats_b);
+/* Host-only helpers for the call above (no device, no ctx):
+ * ivx_intersection_voxel_ranges replaces VoxelObject::determine_voxel_ranges_encompassing_intersection
+ * (object/intersection.rs:707-745) from the two objects' occupied voxel ranges ([dim * 2 + {start, end}], as in
+ * ivx_object_info) and voxel extents; *out_intersect = 0 is the reference's `None`.
+ * ivx_box_intersection_bounds is its core, compute_box_intersection_bounds (impact_geometry/src/oriented_box.rs:315-431):
+ * the bounds of the overlap of an axis-aligned box A and an oriented box B (centre, unit quaternion x, y, z, w, half
+ * extents), in A's frame and in B's own frame relative to B's centre, each as lower xyz, upper xyz. */
+int ivx_intersection_voxel_ranges(const uint32_t occupied_a[6], float voxel_extent_a, const uint32_t occupied_b[6],
+                                  float voxel_extent_b, const ivx_isometry* transform_from_b_to_a,
+                                  uint32_t out_ranges_in_a[6], uint32_t out_ranges_in_b[6], int* out_intersect);
+int ivx_box_intersection_bounds(const float a_lower[3], const float a_upper[3], const float b_center[3],
+                                const float b_orientation[4], const float b_half_extents[3], float out_in_a[6],
+                                float out_in_b[6], int* out_intersect);
 int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* object, uint32_t* out_linear_indices,
                             uint32_t capacity, uint32_t* out_count);
 int ivx_object_remesh_dirty(ivx_ctx* ctx, ivx_object* object, ivx_mesh_info* out);

@@ -334,11 +334,13 @@ def random_voxel_chunks(shape, seed, n_types=4, fill=0.5, blobs=True):
 # ---- mutual absorption fixtures -------------------------------------------------------------------------
 
 def quat_from_axis_angle(axis, angle):
-    """Unit quaternion (x, y, z, w) as float32."""
+    """Unit quaternion (x, y, z, w) built in float32 like glam's `Quat::from_axis_angle`: (axis * sin(angle / 2),
+    cos(angle / 2)) with the half angle, sine and cosine all evaluated in f32."""
     a = np.asarray(axis, np.float64)
-    a = a / np.linalg.norm(a)
-    s = np.sin(0.5 * angle)
-    return np.float32([a[0] * s, a[1] * s, a[2] * s, np.cos(0.5 * angle)])
+    a = (a / np.linalg.norm(a)).astype(np.float32)
+    half = np.float32(angle) * np.float32(0.5)
+    s, c = np.sin(half), np.cos(half)
+    return np.float32([a[0] * s, a[1] * s, a[2] * s, c])
 
 
 def _rotate(q, v):

@@ -54,7 +54,9 @@ def test_two_spheres_identity_rotation(ctx, oracle):
     ga, ca = _pair(ctx, oracle, H.sphere_graph(20.0), 1.0, H.SAME0)
     gb, cb = _pair(ctx, oracle, H.sphere_graph(12.0), 1.0, H.SAME0)
     q, t = np.float32([0, 0, 0, 1]), np.float32([26.0, 8.0, 8.0])
-    ranges = H.intersection_voxel_ranges(_info(ca, 1.0), _info(cb, 1.0), q, t)
+    # the library's own determine_voxel_ranges_encompassing_intersection (host side) on the GPU objects' occupied ranges
+    ranges = V.intersection_voxel_ranges(ga.info()["occupied_voxel_ranges"], 1.0, gb.info()["occupied_voxel_ranges"], 1.0, q, t)
+    assert ranges is not None
     sc = _run(oracle, ga, ca, gb, cb, q, t, 0.0, ranges, [1.0])
     assert sc[0]["emptied_voxels"] > 2000 and sc[1]["emptied_voxels"] > 2000
     # whole occupied ranges instead of the intersection's: more voxels visited, same rule
@@ -77,7 +79,7 @@ def test_rotated_objects_extents_and_smoothness(ctx, oracle, ea, eb, k):
     centre_a = 0.5 * ea * np.float64(ia["chunk_counts"]) * 16
     centre_b = 0.5 * eb * np.float64(ib["chunk_counts"]) * 16
     t = (centre_a + ea * np.array([22.0, 3.0, -2.0]) - H._rotate(q, centre_b)).astype(np.float32)
-    ranges = H.intersection_voxel_ranges(ia, ib, q, t)
+    ranges = V.intersection_voxel_ranges(ia["occupied_voxel_ranges"], ea, ib["occupied_voxel_ranges"], eb, q, t)
     assert ranges is not None
     sc = _run(oracle, ga, ca, gb, cb, q, t, k, ranges)
     assert sc[0]["emptied_voxels"] > 50 and sc[1]["emptied_voxels"] > 50

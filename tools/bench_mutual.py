@@ -36,7 +36,7 @@ def main():
     for rep in range(args.reps + 2):
         a, b = VoxelObject.generate(gen), VoxelObject.generate(gen)
         ia, ib = a.info(), b.info()
-        ranges = H.intersection_voxel_ranges(ia, ib, q, t)
+        ranges = V.intersection_voxel_ranges(ia["occupied_voxel_ranges"], 1.0, ib["occupied_voxel_ranges"], 1.0, q, t)
         ma, mb = a.inertial_moments(dens).copy(), b.inertial_moments(dens).copy()
         ctx.synchronize()
         t0 = time.perf_counter()
