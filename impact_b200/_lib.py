@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_resolve_connected_regions", "ivx_object_split_detection_download", "ivx_object_extract_disconnected_region",
     "ivx_object_from_generated_chunks", "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",
     "ivx_objects_absorb_mutually", "ivx_intersection_voxel_ranges", "ivx_box_intersection_bounds",
+    "ivx_object_surface_voxels_in_ranges", "ivx_object_surface_voxels_touching_sphere", "ivx_object_surface_voxels_touching_capsule",
 ]
 
 
@@ -81,6 +82,8 @@ class SplitInfo(C.Structure):
                 ("n_relabelled_chunks", C.c_uint32), ("device_ms", C.c_float), ("host_ms", C.c_float)]
 
 
+SURFACE_VOXEL_DTYPE = np.dtype([("indices", "<u4", (3,)), ("type", "u1"), ("sd", "i1"), ("flags", "u1"), ("placement", "u1")])
+assert SURFACE_VOXEL_DTYPE.itemsize == 16
 CHUNK_REGIONS_DTYPE = np.dtype([("region_count", "<u2"), ("boundary_region_count", "<u2"), ("first_region", "<u4")])
 VOXEL_DTYPE = np.dtype([("type", "u1"), ("sd", "i1"), ("flags", "u1")])
 CHUNK_DTYPE = np.dtype(

@@ -337,6 +337,36 @@ class VoxelObject:
             C.c_uint32(len(dens)), L.ptr(moments), C.byref(st)))
         return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
 
+    def _surface_query(self, call) -> np.ndarray:
+        n = C.c_uint64()
+        cap = 1 << 14
+        while True:
+            out = np.zeros(cap, L.SURFACE_VOXEL_DTYPE)
+            rc = call(L.ptr(out), C.c_size_t(cap), C.byref(n))
+            if rc == 5:  # IVX_ERR_CAPACITY: n holds the number found
+                cap = int(n.value)
+                continue
+            self.ctx.check(rc)
+            return out[: n.value]
+
+    def surface_voxels_in_ranges(self, ranges=None) -> np.ndarray:
+        """`for_each_surface_voxel_in_voxel_ranges` (intersection.rs:97-151) as an array in the closure's call order;
+        `ranges` (3 x 2) defaults to the occupied voxel ranges = `for_each_surface_voxel`."""
+        r = np.ascontiguousarray(self.info()["occupied_voxel_ranges"] if ranges is None else ranges, np.uint32).reshape(6)
+        return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_surface_voxels_in_ranges(self.ctx.h, self.h, L.ptr(r), o, c, n))
+
+    def surface_voxels_touching_sphere(self, center, radius: float) -> np.ndarray:
+        """`for_each_surface_voxel_maybe_intersecting_sphere` (intersection.rs:51-71), sphere in normalized voxel space."""
+        ctr = np.asarray(center, np.float32)
+        return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_surface_voxels_touching_sphere(
+            self.ctx.h, self.h, L.ptr(ctr), C.c_float(radius), o, c, n))
+
+    def surface_voxels_touching_capsule(self, segment_start, segment_vector, radius: float) -> np.ndarray:
+        """`for_each_surface_voxel_maybe_intersecting_capsule` (intersection.rs:73-85)."""
+        a, v = np.asarray(segment_start, np.float32), np.asarray(segment_vector, np.float32)
+        return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_surface_voxels_touching_capsule(
+            self.ctx.h, self.h, L.ptr(a), L.ptr(v), C.c_float(radius), o, c, n))
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113) → (info dict, extracted VoxelObject or
         None). This object is modified in place."""

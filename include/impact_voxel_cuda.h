@@ -492,6 +492,30 @@ typedef struct ivx_extraction_info {
 int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* object, ivx_extraction_info* out_info,
                                            ivx_object** out_extracted);
 
+/* ---- surface voxel queries ---------------------------------------------------
+ * What collision detection and the interaction code ask an object for (collidable.rs, interaction/): the non-empty voxels
+ * with at least one exposed face inside some voxel ranges, in the order the reference's closure would see them (chunks
+ * i → j → k, voxels i → j → k inside the chunk's part of the ranges).
+ *   ivx_object_surface_voxels_in_ranges       VoxelObject::for_each_surface_voxel_in_voxel_ranges (object/intersection.rs:
+ *                                             97-151); with the occupied voxel ranges: for_each_surface_voxel (:87-95)
+ *   ..._touching_sphere / _touching_capsule   for_each_surface_voxel_maybe_intersecting_sphere / _capsule (:51-85): the
+ *                                             ranges of the shape's box clipped to the occupied ranges; shape given in
+ *                                             normalized voxel space (voxel extent 1), like the absorption calls
+ * placement: VoxelSurfacePlacement (lib.rs:109-114) 0 Face (5 blocked faces), 1 Edge (4), 2 Corner (<= 3).
+ * *out_count is always the number found; IVX_ERR_CAPACITY when `capacity` is smaller (nothing is written). */
+typedef struct ivx_surface_voxel {
+    uint32_t indices[3];  /* object voxel indices */
+    ivx_voxel voxel;
+    uint8_t placement;
+} ivx_surface_voxel;
+int ivx_object_surface_voxels_in_ranges(ivx_ctx* ctx, const ivx_object* object, const uint32_t ranges[6],
+                                        ivx_surface_voxel* out, size_t capacity, uint64_t* out_count);
+int ivx_object_surface_voxels_touching_sphere(ivx_ctx* ctx, const ivx_object* object, const float center[3], float radius,
+                                              ivx_surface_voxel* out, size_t capacity, uint64_t* out_count);
+int ivx_object_surface_voxels_touching_capsule(ivx_ctx* ctx, const ivx_object* object, const float segment_start[3],
+                                               const float segment_vector[3], float radius, ivx_surface_voxel* out,
+                                               size_t capacity, uint64_t* out_count);
+
 /* ---- inertial properties ----------------------------------------------------
  * `VoxelObjectInertialPropertyManager` (object/inertia.rs:19-25): mass, moments (m x, m y, m z), moments of inertia
  * (diagonal of the inertia tensor) and products of inertia (m x y, m y z, m z x) integrated over the non-empty voxels

@@ -402,6 +402,20 @@ void orc_absorb_mutually(void* ap, void* bp, const float q[4], const float t[3],
                     densities ? &ua : nullptr, densities ? &ub : nullptr, stats_a, stats_b);
 }
 
+// for_each_surface_voxel_in_voxel_ranges: returns the number found, writes at most `capacity` 16-byte records
+uint64_t orc_surface_voxels_in_ranges(const void* op, const uint32_t ranges[6], SurfaceVoxel* out, uint64_t capacity) {
+    uint32_t r[3][2];
+    for (int d = 0; d < 3; ++d) {
+        r[d][0] = ranges[2 * d];
+        r[d][1] = ranges[2 * d + 1];
+    }
+    std::vector<SurfaceVoxel> found;
+    surface_voxels_in_ranges(*(const Object*)op, r, found);
+    const size_t n = std::min<size_t>(found.size(), capacity);
+    if (n) std::memcpy(out, found.data(), n * sizeof(SurfaceVoxel));
+    return found.size();
+}
+
 // ---- connected regions ----
 // Runs the whole detection on the object's current state. info (u32 x 24): n_regions, has_two, two[0], two[1],
 // smallest, overflow, n_region_entries, n_label_bytes, then per candidate region 8 words: chunk_count,

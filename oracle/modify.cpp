@@ -444,4 +444,33 @@ void absorb_mutually(Object& a, Object& b, Isometry b_to_a, float smoothness, co
     if (stats_b) *stats_b = sb;
 }
 
+// ---- surface voxel queries (object/intersection.rs:51-151) ---------------------------------------------------------
+void surface_voxels_in_ranges(const Object& obj, const uint32_t r[3][2], std::vector<SurfaceVoxel>& out) {
+    out.clear();
+    for (int d = 0; d < 3; ++d)
+        if (r[d][0] >= r[d][1]) return;
+    for (uint32_t ci = r[0][0] / 16; ci < (r[0][1] + 15) / 16; ++ci)
+        for (uint32_t cj = r[1][0] / 16; cj < (r[1][1] + 15) / 16; ++cj)
+            for (uint32_t ck = r[2][0] / 16; ck < (r[2][1] + 15) / 16; ++ck) {
+                const Chunk& c = obj.chunks[obj.lin(ci, cj, ck)];
+                if (c.kind != CK_NONUNIFORM) continue;  // only non-uniform chunks can have surface voxels
+                const Voxel* v = obj.chunk_voxels(c.data_offset);
+                const uint32_t cc[3] = {ci, cj, ck};
+                uint32_t t0[3], t1[3];
+                for (int d = 0; d < 3; ++d) {
+                    t0[d] = std::max(cc[d] * 16, r[d][0]);
+                    t1[d] = std::min((cc[d] + 1) * 16, r[d][1]);
+                }
+                for (uint32_t i = t0[0]; i < t1[0]; ++i)
+                    for (uint32_t j = t0[1]; j < t1[1]; ++j)
+                        for (uint32_t k = t0[2]; k < t1[2]; ++k) {
+                            const Voxel& vx = v[vidx(i & 15, j & 15, k & 15)];
+                            if (vx.flags & FLAG_EMPTY) continue;  // Voxel::placement: None
+                            const int blocked = __builtin_popcount(vx.flags & FLAG_FULL_ADJ);
+                            if (blocked == 6) continue;  // VoxelPlacement::Interior
+                            out.push_back(SurfaceVoxel{{i, j, k}, vx, (uint8_t)(blocked == 5 ? 0 : (blocked == 4 ? 1 : 2))});
+                        }
+            }
+}
+
 }  // namespace orc

@@ -328,6 +328,16 @@ void absorb_sphere(Object& obj, V3 center, float radius, float influence_radius,
 void absorb_capsule(Object& obj, V3 segment_start, V3 segment_vector, float radius, float influence_radius,
                     AbsorbStats* stats, InertialUpdater* updater = nullptr);
 
+// for_each_surface_voxel_in_voxel_ranges (object/intersection.rs:97-151) as a list in the closure's call order;
+// placement: VoxelSurfacePlacement 0 Face, 1 Edge, 2 Corner (lib.rs:109-114, 330-343)
+struct SurfaceVoxel {
+    uint32_t ijk[3];
+    Voxel voxel;
+    uint8_t placement;
+};
+static_assert(sizeof(SurfaceVoxel) == 16, "16-byte records");
+void surface_voxels_in_ranges(const Object& obj, const uint32_t ranges[3][2], std::vector<SurfaceVoxel>& out);
+
 // apply_mutual_absorption (interaction/absorption.rs:891-1080) given the voxel ranges encompassing the intersection
 // (determine_voxel_ranges_encompassing_intersection, a pure function of the two occupied ranges and the transform that
 // stays with the caller): both objects subtract each other's volume.

@@ -304,6 +304,18 @@ class Object:
         return {"touched_chunks": int(st[0]), "touched_voxels": int(st[1]), "emptied_voxels": int(st[2]),
                 "removed_chunks": int(st[3])}
 
+    SURFACE_VOXEL_DTYPE = np.dtype([("indices", "<u4", (3,)), ("type", "u1"), ("sd", "i1"), ("flags", "u1"), ("placement", "u1")])
+
+    def surface_voxels_in_ranges(self, ranges=None) -> np.ndarray:
+        """`for_each_surface_voxel_in_voxel_ranges` (intersection.rs:97-151) in the closure's call order; `ranges` defaults
+        to the occupied voxel ranges (`for_each_surface_voxel`)."""
+        r = np.ascontiguousarray(self.info()["occupied_voxel_ranges"] if ranges is None else ranges, np.uint32).reshape(6)
+        lib().orc_surface_voxels_in_ranges.restype = C.c_uint64
+        n = lib().orc_surface_voxels_in_ranges(self.h, _p(r), None, C.c_uint64(0))
+        out = np.zeros(max(1, n), self.SURFACE_VOXEL_DTYPE)
+        lib().orc_surface_voxels_in_ranges(self.h, _p(r), _p(out), C.c_uint64(n))
+        return out[:n]
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113): → (info, extracted Object or None).
         This object is modified in place (the region's voxels leave it)."""

@@ -1,0 +1,88 @@
+"""Surface voxel queries (object/intersection.rs:51-151): the oracle against a brute-force scan of the dense voxel
+fields (CPU), and `ivx_object_surface_voxels_*` against the oracle record for record, order included (GPU)."""
+import numpy as np
+import pytest
+
+import helpers as H
+import invariants as INV
+
+
+def _brute_force(obj, ranges):
+    cc = obj.info()["chunk_counts"]
+    _, fl, _, _, empty = INV.dense_fields(obj.chunks(), obj.voxels(), cc)
+    blocked = np.zeros(fl.shape, np.int32)
+    for b in range(2, 8):
+        blocked += (fl >> b) & 1
+    kinds = obj.chunks()["kind"].reshape(cc)
+    non_uniform = np.kron(kinds == 2, np.ones((16, 16, 16), bool))
+    surface = ~empty & (blocked < 6) & non_uniform
+    sel = np.zeros_like(surface)
+    sel[tuple(slice(int(a), int(b)) for a, b in ranges)] = True
+    idx = np.argwhere(surface & sel)
+    place = np.where(blocked == 5, 0, np.where(blocked == 4, 1, 2))
+    return {tuple(i): int(place[tuple(i)]) for i in idx}
+
+
+@pytest.mark.parametrize("name", ["sphere", "asteroid_like", "random"])
+def test_oracle_surface_voxels_equal_a_brute_force_scan(oracle, name):
+    if name == "random":
+        vox, sp, grid = H.random_voxel_chunks((40, 37, 50), 5)
+        o = oracle.Object.from_generated_chunks(vox, sp, grid, 1.0)
+    else:
+        g = H.sphere_graph(24.0) if name == "sphere" else H.asteroid_like_graph(12, 24.0)
+        o = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(g.nodes(), g.root_node_id), 1.0, H.GRADIENT4), 2)
+    occ = o.info()["occupied_voxel_ranges"]
+    for ranges in (occ, np.array([[5, 30], [0, 21], [17, 40]], np.uint32), np.array([[3, 3], [0, 9], [0, 9]], np.uint32)):
+        got = o.surface_voxels_in_ranges(ranges)
+        want = _brute_force(o, ranges)
+        assert len(got) == len(want)
+        assert {tuple(int(x) for x in r["indices"]): int(r["placement"]) for r in got} == want
+        # the closure's call order: chunk by chunk, then voxel by voxel
+        key = [(tuple(int(x) >> 4 for x in r["indices"]), tuple(int(x) for x in r["indices"])) for r in got]
+        assert key == sorted(key)
+    assert len(o.surface_voxels_in_ranges()) > 100
+    placements = np.bincount(o.surface_voxels_in_ranges()["placement"], minlength=3)
+    assert placements[0] > 0 and placements.sum() == len(o.surface_voxels_in_ranges())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sphere", "asteroid_like", "random"])
+def test_gpu_surface_voxels_equal_the_oracle_in_order(ctx, oracle, name):
+    from impact_b200.voxel import SDFVoxelGenerator, VoxelObject
+
+    if name == "random":
+        vox, sp, grid = H.random_voxel_chunks((64, 48, 50), 6)
+        c = oracle.Object.from_generated_chunks(vox, sp, grid, 0.5)
+        g = VoxelObject.from_generated_chunks(ctx, 0.5, grid, vox, sp)
+    else:
+        graph = H.sphere_graph(40.0) if name == "sphere" else H.asteroid_like_graph(16, 36.0)
+        c = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(graph.nodes(), graph.root_node_id), 0.5, H.GRADIENT4), 4)
+        g = VoxelObject.generate(SDFVoxelGenerator(0.5, ctx.build_generator(graph), H.GRADIENT4))
+
+    def same(got, want):
+        assert len(got) == len(want), (len(got), len(want))
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+    same(g.surface_voxels_in_ranges(), c.surface_voxels_in_ranges())
+    shape = np.array(c.info()["chunk_counts"]) * 16
+    sub = np.array([[5, shape[0] - 9], [0, 21], [17, shape[2] - 3]], np.uint32)
+    same(g.surface_voxels_in_ranges(sub), c.surface_voxels_in_ranges(sub))
+    assert len(g.surface_voxels_in_ranges(np.array([[3, 3], [0, 9], [0, 9]], np.uint32))) == 0
+    # for_each_surface_voxel_maybe_intersecting_sphere / _capsule: the shape's box clipped to the occupied ranges
+    occ = c.info()["occupied_voxel_ranges"].astype(np.float64)
+    f = np.float32
+    centre, radius = (0.5 * shape + [9.0, -4.0, 3.0]).astype(f), f(11.5)
+    lo, hi = np.floor(np.maximum(centre - radius, 0.0)), np.ceil(centre + radius)
+    r = np.stack([np.maximum(lo, occ[:, 0]), np.minimum(hi, occ[:, 1])], 1).astype(np.uint32)
+    got = g.surface_voxels_touching_sphere(centre, float(radius))
+    same(got, c.surface_voxels_in_ranges(r))
+    assert len(got) > 0
+    a, v = (0.5 * shape - [20.0, 3.0, 1.0]).astype(f), f([40.0, 6.0, 2.0])
+    lo = np.floor(np.maximum(np.minimum(a - f(4.0), a + v - f(4.0)), 0.0))
+    hi = np.ceil(np.maximum(a + f(4.0), a + v + f(4.0)))
+    r = np.stack([np.maximum(lo, occ[:, 0]), np.minimum(hi, occ[:, 1])], 1).astype(np.uint32)
+    same(g.surface_voxels_touching_capsule(a, v, 4.0), c.surface_voxels_in_ranges(r))
+    # after an absorption the exposed voxels change; still the same list
+    g.absorb_sphere(centre, 8.0, 10.0)
+    c.absorb_sphere(centre, 8.0, 10.0)
+    same(g.surface_voxels_in_ranges(), c.surface_voxels_in_ranges())
