@@ -71,7 +71,7 @@ def test_gpu_surface_voxels_equal_the_oracle_in_order(ctx, oracle, name):
     # for_each_surface_voxel_maybe_intersecting_sphere / _capsule: the shape's box clipped to the occupied ranges
     occ = c.info()["occupied_voxel_ranges"].astype(np.float64)
     f = np.float32
-    centre, radius = (0.5 * shape + [9.0, -4.0, 3.0]).astype(f), f(11.5)
+    centre, radius = (0.5 * shape + [0.4 * shape[0], -4.0, 3.0]).astype(f), f(11.5)  # at the object's +x side
     lo, hi = np.floor(np.maximum(centre - radius, 0.0)), np.ceil(centre + radius)
     r = np.stack([np.maximum(lo, occ[:, 0]), np.minimum(hi, occ[:, 1])], 1).astype(np.uint32)
     got = g.surface_voxels_touching_sphere(centre, float(radius))
@@ -83,6 +83,6 @@ def test_gpu_surface_voxels_equal_the_oracle_in_order(ctx, oracle, name):
     r = np.stack([np.maximum(lo, occ[:, 0]), np.minimum(hi, occ[:, 1])], 1).astype(np.uint32)
     same(g.surface_voxels_touching_capsule(a, v, 4.0), c.surface_voxels_in_ranges(r))
     # after an absorption the exposed voxels change; still the same list
-    g.absorb_sphere(centre, 8.0, 10.0)
-    c.absorb_sphere(centre, 8.0, 10.0)
+    g.absorb_sphere(centre, 12.0, 14.0)
+    c.absorb_sphere(centre, 12.0, 14.0)
     same(g.surface_voxels_in_ranges(), c.surface_voxels_in_ranges())

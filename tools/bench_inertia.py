@@ -42,6 +42,12 @@ def main():
         obj.inertial_moments(dens)
     prof = {k: round(v[0] / args.reps, 4) for k, v in ctx.profile_get().items() if k.startswith("moments")}
     ctx.profile_enable(False)
+    # for_each_surface_voxel over the whole object (ivx_object_surface_voxels_in_ranges), wall clock incl. the copy out
+    tq = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        sv = obj.surface_voxels_in_ranges()
+        tq.append((time.perf_counter() - t0) * 1e3)
     n_chunks = int(np.prod(inf["chunk_counts"]))
     ms = float(np.median(ts))
     # algorithmic bytes: 2 B (type + flags) per voxel of every non-uniform chunk + 16 B descriptor per chunk
@@ -49,7 +55,8 @@ def main():
     print(json.dumps({"workload": args.workload, "grid_shape": list(inf["grid_shape"]), "chunks": n_chunks,
                       "non_uniform": inf["n_non_uniform"], "uniform": inf["n_uniform"], "ms_median": ms,
                       "ms_min": float(min(ts)), "algorithmic_GB": bytes_alg / 1e9,
-                      "GBps": bytes_alg / ms / 1e6, "kernel_ms": prof, "moments": [float(x) for x in m]}))
+                      "GBps": bytes_alg / ms / 1e6, "kernel_ms": prof,
+                      "surface_voxels": int(len(sv)), "surface_query_ms_min": float(min(tq)), "moments": [float(x) for x in m]}))
 
 
 if __name__ == "__main__":
