@@ -1586,6 +1586,7 @@ int ivx_objects_absorb_mutually(ivx_ctx* ctx, ivx_object* a, ivx_object* b, cons
         rb.v1[d] = ranges_in_b[2 * d + 1];
         n_snap *= ra.v1[d] > ra.v0[d] ? ra.v1[d] - ra.v0[d] : 0u;
     }
+    if (n_snap > 0xFFFFFFFFull) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "snapshot of more than 2^32 voxels");
     Tmp tmp(ctx);
     float* snapshot = tmp.get<float>((size_t)std::max<uint64_t>(n_snap, 1));
     if (!snapshot) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mutual absorption: out of device memory for the snapshot");
@@ -1616,7 +1617,6 @@ int ivx_objects_absorb_mutually(ivx_ctx* ctx, ivx_object* a, ivx_object* b, cons
     ra.mutual = m;
     shape.capsule = 2;
     const InertialUpdate ua{voxel_type_densities, n_densities, inout_a}, ub{voxel_type_densities, n_densities, inout_b};
-    if (n_snap > 0xFFFFFFFFull) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "snapshot of more than 2^32 voxels");
     if (int rc = absorb_impl(ctx, a, shape, stats_a, inertial ? &ua : nullptr, &ra)) return rc;
     // object B: samples A's snapshot
     m.extent = eb;
