@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_from_generated_chunks", "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",
     "ivx_objects_absorb_mutually", "ivx_intersection_voxel_ranges", "ivx_box_intersection_bounds",
     "ivx_object_surface_voxels_in_ranges", "ivx_object_surface_voxels_touching_sphere", "ivx_object_surface_voxels_touching_capsule",
+    "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane",
 ]
 
 

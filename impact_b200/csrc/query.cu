@@ -151,6 +151,53 @@ static void ranges_touching_box(const ivx_object* obj, const float lo[3], const 
     }
 }
 
+int ivx_voxel_ranges_within_plane(const uint32_t occupied[6], const float unit_normal[3], float displacement, uint32_t out_ranges[6]) {
+    if (!occupied || !unit_normal || !out_ranges) return IVX_ERR_INVALID_ARGUMENT;
+    // normalized_aabb_from_voxel_ranges(occupied).projected_onto_negative_halfspace(plane) (axis_aligned_box.rs:460-488)
+    const float c[2][3] = {{(float)occupied[0], (float)occupied[2], (float)occupied[4]},
+                           {(float)occupied[1], (float)occupied[3], (float)occupied[5]}};
+    float lo[3] = {c[0][0], c[0][1], c[0][2]}, hi[3] = {c[1][0], c[1][1], c[1][2]};
+    const int perm[3][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}};
+    for (const auto& p : perm) {
+        const int i = p[0], j = p[1], k = p[2];
+        if (std::fabs(unit_normal[k]) > 1e-8f) {
+            const float a = unit_normal[i] * c[0][i] + unit_normal[j] * c[0][j];
+            const float b = unit_normal[i] * c[0][i] + unit_normal[j] * c[1][j];
+            const float cc = unit_normal[i] * c[1][i] + unit_normal[j] * c[0][j];
+            const float d = unit_normal[i] * c[1][i] + unit_normal[j] * c[1][j];
+            const float extremal = (displacement - std::fmin(std::fmin(std::fmin(a, b), cc), d)) / unit_normal[k];
+            if (!std::signbit(unit_normal[k])) {
+                lo[k] = std::fmin(lo[k], extremal);
+                hi[k] = std::fmin(hi[k], extremal);
+            } else {
+                lo[k] = std::fmax(lo[k], extremal);
+                hi[k] = std::fmax(hi[k], extremal);
+            }
+        }
+    }
+    // voxel_ranges_touching_aab (object/intersection.rs:766-782)
+    for (int d = 0; d < 3; ++d) {
+        const float fl = std::fmax(std::floor(lo[d]), 0.0f), ce = std::ceil(hi[d]);
+        const uint32_t s = fl >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fl;
+        const uint32_t e = !(ce > 0.0f) ? 0u : (ce >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)ce);
+        out_ranges[2 * d] = std::max(occupied[2 * d], s);
+        out_ranges[2 * d + 1] = std::min(occupied[2 * d + 1], e);
+    }
+    return IVX_OK;
+}
+
+int ivx_object_surface_voxels_within_plane(ivx_ctx* ctx, const ivx_object* obj, const float unit_normal[3], float displacement,
+                                           ivx_surface_voxel* out, size_t capacity, uint64_t* out_count) {
+    if (!ctx || !obj || !unit_normal) return IVX_ERR_INVALID_ARGUMENT;
+    uint32_t occ[6], ranges[6];
+    for (int d = 0; d < 3; ++d) {
+        occ[2 * d] = obj->occ_voxels[d];
+        occ[2 * d + 1] = obj->occ_voxels[3 + d];
+    }
+    if (int rc = ivx_voxel_ranges_within_plane(occ, unit_normal, displacement, ranges)) return rc;
+    return ivx_object_surface_voxels_in_ranges(ctx, obj, ranges, out, capacity, out_count);
+}
+
 int ivx_object_surface_voxels_touching_sphere(ivx_ctx* ctx, const ivx_object* obj, const float center[3], float radius,
                                               ivx_surface_voxel* out, size_t capacity, uint64_t* out_count) {
     if (!ctx || !obj || !center || !(radius >= 0.0f)) return IVX_ERR_INVALID_ARGUMENT;

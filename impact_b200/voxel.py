@@ -367,6 +367,13 @@ class VoxelObject:
         return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_surface_voxels_touching_capsule(
             self.ctx.h, self.h, L.ptr(a), L.ptr(v), C.c_float(radius), o, c, n))
 
+    def surface_voxels_within_plane(self, unit_normal, displacement: float) -> np.ndarray:
+        """`for_each_surface_voxel_maybe_intersecting_negative_halfspace_of_plane` (intersection.rs:30-40), plane in
+        normalized voxel space."""
+        nrm = np.asarray(unit_normal, np.float32)
+        return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_surface_voxels_within_plane(
+            self.ctx.h, self.h, L.ptr(nrm), C.c_float(displacement), o, c, n))
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113) → (info dict, extracted VoxelObject or
         None). This object is modified in place."""
@@ -412,6 +419,17 @@ class VoxelObject:
         out = np.zeros(max(1, cnt.value), np.uint32)
         self.ctx.check(self.ctx._lib.ivx_object_dirty_chunks(self.ctx.h, self.h, L.ptr(out), C.c_uint32(len(out)), C.byref(cnt)))
         return out[: cnt.value]
+
+
+def voxel_ranges_within_plane(occupied_voxel_ranges, unit_normal, displacement: float) -> np.ndarray:
+    """`voxel_ranges_within_plane` (object/intersection.rs:751-761), host only → 3 x 2 voxel ranges."""
+    occ = np.ascontiguousarray(occupied_voxel_ranges, np.uint32).reshape(6)
+    nrm = np.asarray(unit_normal, np.float32)
+    out = np.zeros(6, np.uint32)
+    rc = L.lib().ivx_voxel_ranges_within_plane(L.ptr(occ), L.ptr(nrm), C.c_float(displacement), L.ptr(out))
+    if rc != L.IVX_OK:
+        raise L.IvxError(rc, "ivx_voxel_ranges_within_plane")
+    return out.reshape(3, 2)
 
 
 def box_intersection_bounds(a_lower, a_upper, b_center, b_orientation_xyzw, b_half_extents):

@@ -515,6 +515,14 @@ int ivx_object_surface_voxels_touching_sphere(ivx_ctx* ctx, const ivx_object* ob
 int ivx_object_surface_voxels_touching_capsule(ivx_ctx* ctx, const ivx_object* object, const float segment_start[3],
                                                const float segment_vector[3], float radius, ivx_surface_voxel* out,
                                                size_t capacity, uint64_t* out_count);
+/* for_each_surface_voxel_maybe_intersecting_negative_halfspace_of_plane (object/intersection.rs:30-40): the plane
+ * { x : unit_normal . x = displacement } in normalized voxel space; the ranges are the occupied box fitted to the negative
+ * halfspace (AxisAlignedBox::projected_onto_negative_halfspace, impact_geometry/src/axis_aligned_box.rs:460-488), which
+ * ivx_voxel_ranges_within_plane (host only, voxel_ranges_within_plane :751-761) also returns on its own. */
+int ivx_object_surface_voxels_within_plane(ivx_ctx* ctx, const ivx_object* object, const float unit_normal[3],
+                                           float displacement, ivx_surface_voxel* out, size_t capacity, uint64_t* out_count);
+int ivx_voxel_ranges_within_plane(const uint32_t occupied[6], const float unit_normal[3], float displacement,
+                                  uint32_t out_ranges[6]);
 
 /* ---- inertial properties ----------------------------------------------------
  * `VoxelObjectInertialPropertyManager` (object/inertia.rs:19-25): mass, moments (m x, m y, m z), moments of inertia

@@ -103,3 +103,26 @@ def test_voxel_ranges_encompass_the_overlap_of_two_objects(oracle):
         assert (emptied >= r[:, 0]).all() and (emptied < r[:, 1]).all(), (emptied.min(0), emptied.max(0), r)
     # far apart: None
     assert V.intersection_voxel_ranges(oa, ea, ob, eb, q, t + np.float32([100.0, 0, 0])) is None
+
+
+def test_voxel_ranges_within_plane_keep_every_voxel_of_the_negative_halfspace():
+    # voxel_ranges_within_plane (object/intersection.rs:751-761): axis-aligned planes give the obvious cut ...
+    occ = np.array([[3, 40], [0, 25], [7, 33]], np.uint32)
+    assert np.array_equal(V.voxel_ranges_within_plane(occ, [1.0, 0.0, 0.0], 10.3), [[3, 11], [0, 25], [7, 33]])
+    assert np.array_equal(V.voxel_ranges_within_plane(occ, [0.0, -1.0, 0.0], -10.3), [[3, 40], [10, 25], [7, 33]])
+    assert np.array_equal(V.voxel_ranges_within_plane(occ, [0.0, 0.0, 1.0], 100.0), occ)
+    r = V.voxel_ranges_within_plane(occ, [0.0, 0.0, 1.0], 2.0)  # the whole box is on the positive side
+    assert r[2, 0] >= r[2, 1]
+    # ... and for any plane no voxel whose centre is on the negative side is cut away
+    rng = np.random.default_rng(4)
+    ii, jj, kk = np.meshgrid(*[np.arange(a, b) + 0.5 for a, b in occ], indexing="ij")
+    centres = np.stack([ii, jj, kk], -1).reshape(-1, 3)
+    for _ in range(20):
+        n = rng.normal(size=3)
+        n /= np.linalg.norm(n)
+        d = float(rng.uniform(-5, 45))
+        r = V.voxel_ranges_within_plane(occ, n.astype(np.float32), d).astype(np.float64)
+        neg = centres[centres @ n <= d]
+        if len(neg):
+            assert (neg >= r[:, 0]).all() and (neg <= r[:, 1]).all(), (n, d, r)
+        assert (r[:, 0] >= occ[:, 0]).all() and (r[:, 1] <= occ[:, 1]).all()

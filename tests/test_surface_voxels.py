@@ -82,6 +82,12 @@ def test_gpu_surface_voxels_equal_the_oracle_in_order(ctx, oracle, name):
     hi = np.ceil(np.maximum(a + f(4.0), a + v + f(4.0)))
     r = np.stack([np.maximum(lo, occ[:, 0]), np.minimum(hi, occ[:, 1])], 1).astype(np.uint32)
     same(g.surface_voxels_touching_capsule(a, v, 4.0), c.surface_voxels_in_ranges(r))
+    # ..._negative_halfspace_of_plane: the occupied box fitted to the halfspace (host geometry of the library)
+    from impact_b200 import voxel as V
+    n = f([0.6, -0.64, 0.48])
+    d = float(n @ (0.5 * shape).astype(f)) - 6.0
+    same(g.surface_voxels_within_plane(n, d), c.surface_voxels_in_ranges(V.voxel_ranges_within_plane(occ, n, d)))
+    assert 0 < len(g.surface_voxels_within_plane(n, d)) < len(c.surface_voxels_in_ranges())
     # after an absorption the exposed voxels change; still the same list
     g.absorb_sphere(centre, 12.0, 14.0)
     c.absorb_sphere(centre, 12.0, 14.0)
