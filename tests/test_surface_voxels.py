@@ -84,8 +84,9 @@ def test_gpu_surface_voxels_equal_the_oracle_in_order(ctx, oracle, name):
     same(g.surface_voxels_touching_capsule(a, v, 4.0), c.surface_voxels_in_ranges(r))
     # ..._negative_halfspace_of_plane: the occupied box fitted to the halfspace (host geometry of the library)
     from impact_b200 import voxel as V
-    n = f([0.6, -0.64, 0.48])
-    d = float(n @ (0.5 * shape).astype(f)) - 6.0
+    n = f([1.0, 0.05, -0.03])
+    n = (n / f(np.linalg.norm(n))).astype(f)  # tilted a little off the x axis: the fitted box ends before the object does
+    d = float(n @ (0.5 * shape).astype(f)) - 10.0
     same(g.surface_voxels_within_plane(n, d), c.surface_voxels_in_ranges(V.voxel_ranges_within_plane(occ, n, d)))
     assert 0 < len(g.surface_voxels_within_plane(n, d)) < len(c.surface_voxels_in_ranges())
     # after an absorption the exposed voxels change; still the same list
