@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_from_generated_chunks", "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",
     "ivx_objects_absorb_mutually", "ivx_intersection_voxel_ranges", "ivx_box_intersection_bounds",
     "ivx_object_surface_voxels_in_ranges", "ivx_object_surface_voxels_touching_sphere", "ivx_object_surface_voxels_touching_capsule",
-    "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane",
+    "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane", "ivx_object_sphere_contacts",
 ]
 
 
@@ -85,6 +85,8 @@ class SplitInfo(C.Structure):
 
 SURFACE_VOXEL_DTYPE = np.dtype([("indices", "<u4", (3,)), ("type", "u1"), ("sd", "i1"), ("flags", "u1"), ("placement", "u1")])
 assert SURFACE_VOXEL_DTYPE.itemsize == 16
+CONTACT_DTYPE = np.dtype([("indices", "<u4", (3,)), ("position", "<f4", (3,)), ("normal", "<f4", (3,)), ("depth", "<f4")])
+assert CONTACT_DTYPE.itemsize == 40
 CHUNK_REGIONS_DTYPE = np.dtype([("region_count", "<u2"), ("boundary_region_count", "<u2"), ("first_region", "<u4")])
 VOXEL_DTYPE = np.dtype([("type", "u1"), ("sd", "i1"), ("flags", "u1")])
 CHUNK_DTYPE = np.dtype(

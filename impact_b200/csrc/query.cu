@@ -26,10 +26,53 @@ __device__ __forceinline__ uint32_t surface_mask(uint4 fl, uint32_t k0, uint32_t
     return m;
 }
 
-template <bool EMIT>
+// for_each_sphere_voxel_object_contact (collidable.rs:1097-1127): the sphere in the space `transform_to_object_space`
+// starts from, every surface voxel as a sphere of radius -signed_distance * extent around its centre carried back into
+// that space, determine_sphere_sphere_contact_geometry (impact_physics/src/collision/collidable/sphere.rs:105-136)
+struct SphereContactArgs {
+    float q[4], t[3];   // transform_to_object_space
+    float center[3], radius;
+    float extent;
+};
+__device__ __forceinline__ f3 rotate_by(float qx, float qy, float qz, float qw, f3 v) {
+    const f3 b = mk3(qx, qy, qz);
+    const float b2 = dot3(b, b);
+    const float s1 = qw * qw - b2, s2 = dot3(v, b) * 2.0f, s3 = qw * 2.0f;
+    const f3 c = mk3(b.y * v.z - b.z * v.y, b.z * v.x - b.x * v.z, b.x * v.y - b.y * v.x);
+    return mk3((v.x * s1 + b.x * s2) + c.x * s3, (v.y * s1 + b.y * s2) + c.y * s3, (v.z * s1 + b.z * s2) + c.z * s3);
+}
+__device__ __forceinline__ bool sphere_contact(const SphereContactArgs& a, uint32_t i, uint32_t j, uint32_t k, int code,
+                                               ivx_voxel_contact* out) {
+    const float e = a.extent;
+    const f3 c_voxel = mk3(((float)i + 0.5f) * e, ((float)j + 0.5f) * e, ((float)k + 0.5f) * e);
+    const f3 vc = rotate_by(-a.q[0], -a.q[1], -a.q[2], a.q[3], mk3(c_voxel.x - a.t[0], c_voxel.y - a.t[1], c_voxel.z - a.t[2]));
+    const float vr = -sd_decode(code) * e;
+    const f3 disp = mk3(a.center[0] - vc.x, a.center[1] - vc.y, a.center[2] - vc.z);
+    const float d2 = dot3(disp, disp);
+    const float max_d = a.radius + vr;
+    if (d2 > max_d * max_d) return false;
+    if (out) {
+        const float dist = sqrtf(d2);
+        const f3 n = dist > 1e-8f ? mk3(disp.x / dist, disp.y / dist, disp.z / dist) : mk3(0.0f, 0.0f, 1.0f);
+        out->indices[0] = i;
+        out->indices[1] = j;
+        out->indices[2] = k;
+        out->position[0] = vc.x + vr * n.x;
+        out->position[1] = vc.y + vr * n.y;
+        out->position[2] = vc.z + vr * n.z;
+        out->surface_normal[0] = n.x;
+        out->surface_normal[1] = n.y;
+        out->surface_normal[2] = n.z;
+        out->penetration_depth = fmaxf(0.0f, max_d - dist);
+    }
+    return true;
+}
+
+template <bool EMIT, bool CONTACT>
 __global__ void __launch_bounds__(256) k_surface_voxels(const DevChunk* __restrict__ chunks, uint3 nb, AbsorbRange r, uint32_t n_range,
                                                         const unsigned char* __restrict__ voxels, uint32_t* __restrict__ count,
-                                                        const uint32_t* __restrict__ first, ivx_surface_voxel* __restrict__ out) {
+                                                        const uint32_t* __restrict__ first, ivx_surface_voxel* __restrict__ out,
+                                                        SphereContactArgs ca, ivx_voxel_contact* __restrict__ out_contacts) {
     __shared__ uint32_t s_warp[8];
     const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15, lane = tid & 31, warp = tid >> 5;
     const uint32_t ek = r.c1[2] - r.c0[2], ej = r.c1[1] - r.c0[1];
@@ -47,10 +90,20 @@ __global__ void __launch_bounds__(256) k_surface_voxels(const DevChunk* __restri
         const uint32_t k_hi = min(ck * 16u + 16u, r.v1[2]) - ck * 16u;
         const unsigned char* slot = voxels + (size_t)c.slot * SLOT_BYTES;
         uint32_t m = 0;
-        uint4 fl = make_uint4(0, 0, 0, 0);
+        uint4 fl = make_uint4(0, 0, 0, 0), sdw = make_uint4(0, 0, 0, 0);
         if (in_ij && k_lo < k_hi) {
             fl = *reinterpret_cast<const uint4*>(slot + PLANE_FLAGS + tid * 16);
             m = surface_mask(fl, k_lo, k_hi);
+            if (CONTACT && m) {
+                // keep the surface voxels whose sphere touches the query sphere
+                sdw = *reinterpret_cast<const uint4*>(slot + PLANE_SD + tid * 16);
+                const uint32_t wsd[4] = {sdw.x, sdw.y, sdw.z, sdw.w};
+                for (uint32_t b = m; b; b &= b - 1) {
+                    const uint32_t k = (uint32_t)__ffs(b) - 1u;
+                    const int code = (int)(int8_t)(wsd[k >> 2] >> (8 * (k & 3)));
+                    if (!sphere_contact(ca, gi, gj, ck * 16u + k, code, nullptr)) m &= ~(1u << k);
+                }
+            }
         }
         const uint32_t mine = __popc(m);
         uint32_t x = mine;
@@ -68,6 +121,15 @@ __global__ void __launch_bounds__(256) k_surface_voxels(const DevChunk* __restri
         }
         if (!EMIT) {
             if (tid == 0) count[t] = total;
+        } else if (CONTACT) {
+            if (mine) {
+                const uint32_t wsd[4] = {sdw.x, sdw.y, sdw.z, sdw.w};
+                ivx_voxel_contact* o = out_contacts + first[t] + before;
+                for (uint32_t b = m; b; b &= b - 1) {
+                    const uint32_t k = (uint32_t)__ffs(b) - 1u;
+                    sphere_contact(ca, gi, gj, ck * 16u + k, (int)(int8_t)(wsd[k >> 2] >> (8 * (k & 3))), o++);
+                }
+            }
         } else if (mine) {
             const uint4 sd = *reinterpret_cast<const uint4*>(slot + PLANE_SD + tid * 16);
             const uint4 ty = *reinterpret_cast<const uint4*>(slot + PLANE_TYPE + tid * 16);
@@ -122,7 +184,8 @@ int ivx_object_surface_voxels_in_ranges(ivx_ctx* ctx, const ivx_object* obj, con
     if (!count || !first) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "surface voxels: out of device memory");
     const uint3 nb = make_uint3(obj->nb[0], obj->nb[1], obj->nb[2]);
     const uint32_t grid = ivx_persistent_grid(ctx, n_range, 8);
-    KL(ctx, (k_surface_voxels<false><<<grid, 256, 0, st>>>(obj->d_chunks, nb, r, n_range, obj->d_voxels, count, nullptr, nullptr),
+    KL(ctx, (k_surface_voxels<false, false><<<grid, 256, 0, st>>>(obj->d_chunks, nb, r, n_range, obj->d_voxels, count, nullptr,
+                                                                  nullptr, SphereContactArgs{}, nullptr),
              cudaGetLastError()));
     KL(ctx, launch_exclusive_scan(count, first, n_range, total, st));
     uint32_t n = 0;
@@ -132,7 +195,8 @@ int ivx_object_surface_voxels_in_ranges(ivx_ctx* ctx, const ivx_object* obj, con
     if ((size_t)n > capacity) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "surface voxels: %u found, room for %zu", n, capacity);
     ivx_surface_voxel* d_out = tmp.get<ivx_surface_voxel>(n);
     if (!d_out) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "surface voxels: out of device memory");
-    KL(ctx, (k_surface_voxels<true><<<grid, 256, 0, st>>>(obj->d_chunks, nb, r, n_range, obj->d_voxels, count, first, d_out),
+    KL(ctx, (k_surface_voxels<true, false><<<grid, 256, 0, st>>>(obj->d_chunks, nb, r, n_range, obj->d_voxels, count, first, d_out,
+                                                                 SphereContactArgs{}, nullptr),
              cudaGetLastError()));
     CU(ctx, cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(ivx_surface_voxel), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
@@ -149,6 +213,86 @@ static void ranges_touching_box(const ivx_object* obj, const float lo[3], const 
         out[2 * d] = std::max(obj->occ_voxels[d], s);
         out[2 * d + 1] = std::min(obj->occ_voxels[3 + d], e);
     }
+}
+
+int ivx_object_sphere_contacts(ivx_ctx* ctx, const ivx_object* obj, const ivx_isometry* transform_to_object_space,
+                               const float center[3], float radius, ivx_voxel_contact* out, size_t capacity, uint64_t* out_count) {
+    if (!ctx || !obj || !transform_to_object_space || !center || !out_count || (!out && capacity) || !(radius >= 0.0f))
+        return IVX_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(ivx_voxel_contact) == 40, "ten words");
+    cudaSetDevice(ctx->device);
+    *out_count = 0;
+    if (obj->first_i != 0 || obj->nb[0] != obj->chunk_counts[0])
+        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "contact queries on a slab-partitioned object are not supported");
+    SphereContactArgs ca{};
+    for (int q = 0; q < 4; ++q) ca.q[q] = transform_to_object_space->rotation[q];
+    for (int d = 0; d < 3; ++d) {
+        ca.t[d] = transform_to_object_space->translation[d];
+        ca.center[d] = center[d];
+    }
+    ca.radius = radius;
+    ca.extent = obj->voxel_extent;
+    // sphere.iso_transformed(transform).scaled(inverse_voxel_extent).compute_aabb() clipped to the occupied ranges
+    const float e = obj->voxel_extent, inv_e = 1.0f / e;
+    float c_obj[3];
+    {
+        const float bx = ca.q[0], by = ca.q[1], bz = ca.q[2], w = ca.q[3];
+        const float b2 = (bx * bx + by * by) + bz * bz, vb = (center[0] * bx + center[1] * by) + center[2] * bz;
+        const float s1 = w * w - b2, s2 = vb * 2.0f, s3 = w * 2.0f;
+        const float cx = by * center[2] - bz * center[1], cy = bz * center[0] - bx * center[2], cz = bx * center[1] - by * center[0];
+        c_obj[0] = ((center[0] * s1 + bx * s2) + cx * s3) + ca.t[0];
+        c_obj[1] = ((center[1] * s1 + by * s2) + cy * s3) + ca.t[1];
+        c_obj[2] = ((center[2] * s1 + bz * s2) + cz * s3) + ca.t[2];
+    }
+    const float rn = inv_e * radius;
+    float lo[3], hi[3];
+    for (int d = 0; d < 3; ++d) {
+        const float cn = inv_e * c_obj[d];
+        lo[d] = cn - rn;
+        hi[d] = cn + rn;
+    }
+    uint32_t ranges[6];
+    AbsorbRange r{};
+    {
+        for (int d = 0; d < 3; ++d) {
+            const float fl = std::fmax(std::floor(lo[d]), 0.0f), ce = std::ceil(hi[d]);
+            const uint32_t s = fl >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fl;
+            const uint32_t en = !(ce > 0.0f) ? 0u : (ce >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)ce);
+            ranges[2 * d] = std::max(obj->occ_voxels[d], s);
+            ranges[2 * d + 1] = std::min(obj->occ_voxels[3 + d], en);
+            r.v0[d] = ranges[2 * d];
+            r.v1[d] = ranges[2 * d + 1];
+            if (r.v0[d] >= r.v1[d]) return IVX_OK;
+            r.c0[d] = r.v0[d] / 16;
+            r.c1[d] = (r.v1[d] + 15) / 16;
+        }
+    }
+    const uint32_t n_range = (r.c1[0] - r.c0[0]) * (r.c1[1] - r.c0[1]) * (r.c1[2] - r.c0[2]);
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t* count = tmp.get<uint32_t>(n_range);
+    uint32_t* first = tmp.get<uint32_t>(n_range);
+    uint32_t* total = ctx->d_scratch + 52;
+    if (!count || !first) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "contacts: out of device memory");
+    const uint3 nb = make_uint3(obj->nb[0], obj->nb[1], obj->nb[2]);
+    const uint32_t grid = ivx_persistent_grid(ctx, n_range, 8);
+    KL(ctx, (k_surface_voxels<false, true><<<grid, 256, 0, st>>>(obj->d_chunks, nb, r, n_range, obj->d_voxels, count, nullptr, nullptr,
+                                                                 ca, nullptr),
+             cudaGetLastError()));
+    KL(ctx, launch_exclusive_scan(count, first, n_range, total, st));
+    uint32_t n = 0;
+    if (int rc = ivx_read_words(ctx, total, 1, &n)) return rc;
+    *out_count = n;
+    if (n == 0) return IVX_OK;
+    if ((size_t)n > capacity) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "contacts: %u found, room for %zu", n, capacity);
+    ivx_voxel_contact* d_out = tmp.get<ivx_voxel_contact>(n);
+    if (!d_out) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "contacts: out of device memory");
+    KL(ctx, (k_surface_voxels<true, true><<<grid, 256, 0, st>>>(obj->d_chunks, nb, r, n_range, obj->d_voxels, count, first, nullptr,
+                                                                ca, d_out),
+             cudaGetLastError()));
+    CU(ctx, cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(ivx_voxel_contact), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return IVX_OK;
 }
 
 int ivx_voxel_ranges_within_plane(const uint32_t occupied[6], const float unit_normal[3], float displacement, uint32_t out_ranges[6]) {

@@ -337,11 +337,19 @@ class VoxelObject:
             C.c_uint32(len(dens)), L.ptr(moments), C.byref(st)))
         return {f: getattr(st, f) for f, _ in L.AbsorbStats._fields_}
 
-    def _surface_query(self, call) -> np.ndarray:
+    def sphere_contacts(self, rotation_xyzw, translation, center, radius: float) -> np.ndarray:
+        """`for_each_sphere_voxel_object_contact` (collidable.rs:1097-1127): `transform_to_object_space` as (unit
+        quaternion, translation) and the sphere in the space it starts from → contacts in the closure's call order."""
+        iso = np.concatenate([np.asarray(rotation_xyzw, np.float32), np.asarray(translation, np.float32)]).astype(np.float32)
+        ctr = np.asarray(center, np.float32)
+        return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_sphere_contacts(
+            self.ctx.h, self.h, L.ptr(iso), L.ptr(ctr), C.c_float(radius), o, c, n), L.CONTACT_DTYPE)
+
+    def _surface_query(self, call, dtype=None) -> np.ndarray:
         n = C.c_uint64()
         cap = 1 << 14
         while True:
-            out = np.zeros(cap, L.SURFACE_VOXEL_DTYPE)
+            out = np.zeros(cap, dtype or L.SURFACE_VOXEL_DTYPE)
             rc = call(L.ptr(out), C.c_size_t(cap), C.byref(n))
             if rc == 5:  # IVX_ERR_CAPACITY: n holds the number found
                 cap = int(n.value)

@@ -510,6 +510,21 @@ typedef struct ivx_surface_voxel {
 } ivx_surface_voxel;
 int ivx_object_surface_voxels_in_ranges(ivx_ctx* ctx, const ivx_object* object, const uint32_t ranges[6],
                                         ivx_surface_voxel* out, size_t capacity, uint64_t* out_count);
+/* ivx_object_sphere_contacts replaces for_each_sphere_voxel_object_contact (collidable.rs:1097-1127): the sphere query with
+ * its closure fused in — every surface voxel is a sphere of radius -signed_distance * voxel_extent (compute_voxel_radius,
+ * collidable.rs:1453-1455) around its centre, carried into the sphere's space by the inverse of
+ * `transform_to_object_space`, and determine_sphere_sphere_contact_geometry (impact_physics/src/collision/collidable/
+ * sphere.rs:105-136) decides whether there is a contact and where. `center` / `radius`: the sphere in the space the
+ * transform starts from (world); contacts come in the order the reference's closure `f` would have been called. */
+typedef struct ivx_voxel_contact {
+    uint32_t indices[3];       /* object voxel indices */
+    float position[3];         /* ContactGeometry::position */
+    float surface_normal[3];   /* ContactGeometry::surface_normal */
+    float penetration_depth;
+} ivx_voxel_contact;
+int ivx_object_sphere_contacts(ivx_ctx* ctx, const ivx_object* object, const ivx_isometry* transform_to_object_space,
+                               const float center[3], float radius, ivx_voxel_contact* out, size_t capacity,
+                               uint64_t* out_count);
 int ivx_object_surface_voxels_touching_sphere(ivx_ctx* ctx, const ivx_object* object, const float center[3], float radius,
                                               ivx_surface_voxel* out, size_t capacity, uint64_t* out_count);
 int ivx_object_surface_voxels_touching_capsule(ivx_ctx* ctx, const ivx_object* object, const float segment_start[3],

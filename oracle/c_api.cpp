@@ -416,6 +416,17 @@ uint64_t orc_surface_voxels_in_ranges(const void* op, const uint32_t ranges[6], 
     return found.size();
 }
 
+// for_each_sphere_voxel_object_contact: returns the number of contacts, writes at most `capacity` 40-byte records
+uint64_t orc_sphere_contacts(const void* op, const float q[4], const float t[3], const float center[3], float radius,
+                             VoxelContact* out, uint64_t capacity) {
+    std::vector<VoxelContact> found;
+    sphere_voxel_object_contacts(*(const Object*)op, Isometry{Quat{q[0], q[1], q[2], q[3]}, v3(t[0], t[1], t[2])},
+                                 v3(center[0], center[1], center[2]), radius, found);
+    const size_t n = std::min<size_t>(found.size(), capacity);
+    if (n) std::memcpy(out, found.data(), n * sizeof(VoxelContact));
+    return found.size();
+}
+
 // ---- connected regions ----
 // Runs the whole detection on the object's current state. info (u32 x 24): n_regions, has_two, two[0], two[1],
 // smallest, overflow, n_region_entries, n_label_bytes, then per candidate region 8 words: chunk_count,

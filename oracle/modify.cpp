@@ -473,4 +473,35 @@ void surface_voxels_in_ranges(const Object& obj, const uint32_t r[3][2], std::ve
             }
 }
 
+// ---- sphere contacts (collidable.rs:1097-1127, 1453-1455; impact_physics sphere.rs:105-136) ------------------------
+void sphere_voxel_object_contacts(const Object& obj, const Isometry& T, V3 center, float radius, std::vector<VoxelContact>& out) {
+    out.clear();
+    const float e = obj.voxel_extent, inv_e = 1.0f / e;
+    // sphere.iso_transformed(transform_to_object_space), then .scaled(inverse_voxel_extent) and its box clipped to the
+    // occupied ranges (for_each_surface_voxel_maybe_intersecting_sphere)
+    const V3 c_obj = quat_rotate(T.q, center) + T.t;
+    const V3 cn = inv_e * c_obj;
+    const float rn = inv_e * radius;
+    const float lo[3] = {cn.x - rn, cn.y - rn, cn.z - rn}, hi[3] = {cn.x + rn, cn.y + rn, cn.z + rn};
+    uint32_t r[3][2];
+    ranges_touching(obj.occ_voxels, lo, hi, r);
+    std::vector<SurfaceVoxel> sv;
+    surface_voxels_in_ranges(obj, r, sv);
+    const Quat qc = quat_conj(T.q);
+    for (const SurfaceVoxel& v : sv) {
+        const V3 c_voxel = v3(((float)v.ijk[0] + 0.5f) * e, ((float)v.ijk[1] + 0.5f) * e, ((float)v.ijk[2] + 0.5f) * e);
+        const V3 vc = quat_rotate(qc, c_voxel - T.t);           // inverse_transform_point
+        const float vr = -sd_decode(v.voxel.sd) * e;            // compute_voxel_radius
+        const V3 disp = center - vc;
+        const float d2 = dot(disp, disp);
+        const float max_d = radius + vr;
+        if (d2 > max_d * max_d) continue;
+        const float dist = std::sqrt(d2);
+        const V3 n = dist > 1e-8f ? v3(disp.x / dist, disp.y / dist, disp.z / dist) : v3(0.0f, 0.0f, 1.0f);
+        const V3 pos = vc + vr * n;
+        out.push_back(VoxelContact{{v.ijk[0], v.ijk[1], v.ijk[2]}, {pos.x, pos.y, pos.z}, {n.x, n.y, n.z},
+                                   std::fmax(0.0f, max_d - dist)});
+    }
+}
+
 }  // namespace orc

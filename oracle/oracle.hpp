@@ -338,6 +338,17 @@ struct SurfaceVoxel {
 static_assert(sizeof(SurfaceVoxel) == 16, "16-byte records");
 void surface_voxels_in_ranges(const Object& obj, const uint32_t ranges[3][2], std::vector<SurfaceVoxel>& out);
 
+// for_each_sphere_voxel_object_contact (collidable.rs:1097-1127) + determine_sphere_sphere_contact_geometry
+// (impact_physics/src/collision/collidable/sphere.rs:105-136) as a list in the closure's call order
+struct VoxelContact {
+    uint32_t ijk[3];
+    float position[3], normal[3], penetration_depth;
+};
+static_assert(sizeof(VoxelContact) == 40, "ten words");
+struct Isometry;
+void sphere_voxel_object_contacts(const Object& obj, const Isometry& transform_to_object_space, V3 center, float radius,
+                                  std::vector<VoxelContact>& out);
+
 // apply_mutual_absorption (interaction/absorption.rs:891-1080) given the voxel ranges encompassing the intersection
 // (determine_voxel_ranges_encompassing_intersection, a pure function of the two occupied ranges and the transform that
 // stays with the caller): both objects subtract each other's volume.

@@ -316,6 +316,18 @@ class Object:
         lib().orc_surface_voxels_in_ranges(self.h, _p(r), _p(out), C.c_uint64(n))
         return out[:n]
 
+    CONTACT_DTYPE = np.dtype([("indices", "<u4", (3,)), ("position", "<f4", (3,)), ("normal", "<f4", (3,)), ("depth", "<f4")])
+
+    def sphere_contacts(self, rotation_xyzw, translation, center, radius: float) -> np.ndarray:
+        """`for_each_sphere_voxel_object_contact` (collidable.rs:1097-1127): `transform_to_object_space` as (unit
+        quaternion, translation), the sphere in the space that transform starts from; contacts in call order."""
+        q, t, c = (np.asarray(x, np.float32) for x in (rotation_xyzw, translation, center))
+        lib().orc_sphere_contacts.restype = C.c_uint64
+        n = lib().orc_sphere_contacts(self.h, _p(q), _p(t), _p(c), C.c_float(radius), None, C.c_uint64(0))
+        out = np.zeros(max(1, n), self.CONTACT_DTYPE)
+        lib().orc_sphere_contacts(self.h, _p(q), _p(t), _p(c), C.c_float(radius), _p(out), C.c_uint64(n))
+        return out[:n]
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113): → (info, extracted Object or None).
         This object is modified in place (the region's voxels leave it)."""

@@ -93,3 +93,91 @@ def test_gpu_surface_voxels_equal_the_oracle_in_order(ctx, oracle, name):
     g.absorb_sphere(centre, 12.0, 14.0)
     c.absorb_sphere(centre, 12.0, 14.0)
     same(g.surface_voxels_in_ranges(), c.surface_voxels_in_ranges())
+
+
+def _contacts_float64(obj, extent, q, t, centre, radius):
+    """for_each_sphere_voxel_object_contact in float64: the surface voxels inside the sphere's box (in normalized voxel
+    space, clipped to the occupied ranges — voxels outside it are never visited, even if their own sphere would reach)."""
+    c_norm = (H._rotate(q, np.asarray(centre, np.float64)) + np.asarray(t, np.float64)) / extent
+    occ = obj.info()["occupied_voxel_ranges"].astype(np.float64)
+    lo = np.maximum(np.floor(np.maximum(c_norm - radius / extent, 0.0)), occ[:, 0])
+    hi = np.minimum(np.ceil(c_norm + radius / extent), occ[:, 1])
+    sv = obj.surface_voxels_in_ranges(np.stack([lo, hi], 1).astype(np.uint32))
+    idx = sv["indices"].astype(np.float64)
+    c_obj = (idx + 0.5) * extent
+    x, y, z, w = [float(c) for c in q]
+    b = np.array([-x, -y, -z])
+    v = c_obj - np.asarray(t, np.float64)
+    vc = v * (w * w - b @ b) + np.outer(v @ b, b) * 2.0 + np.cross(b, v) * (2.0 * w)
+    vr = -(sv["sd"].astype(np.float64) * 0.02) * extent
+    disp = np.asarray(centre, np.float64) - vc
+    dist = np.linalg.norm(disp, axis=1)
+    hit = dist <= radius + vr
+    margin = np.abs(dist - (radius + vr))
+    n = disp / dist[:, None]
+    return sv["indices"], hit, margin, vc + vr[:, None] * n, n, np.maximum(0.0, radius + vr - dist)
+
+
+def _check_contacts(got, ref, tol=2e-4):
+    indices, hit, margin, pos, nrm, depth = ref
+    sure = margin > 1e-3  # voxels whose spheres graze the query sphere may go either way in f32
+    got_set = {tuple(int(x) for x in r) for r in got["indices"]}
+    for i in np.flatnonzero(sure):
+        assert (tuple(int(x) for x in indices[i]) in got_set) == bool(hit[i]), indices[i]
+    lookup = {tuple(int(x) for x in ix): n for n, ix in enumerate(indices)}
+    for r in got:
+        n = lookup[tuple(int(x) for x in r["indices"])]
+        assert np.allclose(r["position"], pos[n], atol=tol) and np.allclose(r["normal"], nrm[n], atol=tol)
+        assert abs(float(r["depth"]) - depth[n]) < tol
+    order = [(tuple(int(x) >> 4 for x in r["indices"]), tuple(int(x) for x in r["indices"])) for r in got]
+    assert order == sorted(order)
+
+
+def test_oracle_sphere_contacts_equal_a_float64_evaluation(oracle):
+    g = H.asteroid_like_graph(12, 24.0)
+    extent = 0.5
+    o = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(g.nodes(), g.root_node_id), extent, H.GRADIENT4), 2)
+    shape = np.array(o.info()["chunk_counts"]) * 16
+    q = H.quat_from_axis_angle([0.3, 1.0, -0.2], 0.7)
+    t = np.float32([1.5, -2.0, 0.75])
+    # a sphere whose centre, carried into object space, sits near the +x side of the object
+    target_obj = extent * (0.5 * shape + [0.36 * shape[0] + 0.3, 2.37, -3.41])  # off the voxel lattice: no borderline floor / ceil
+    qc = np.array([-q[0], -q[1], -q[2], q[3]])
+    centre = H._rotate(qc, target_obj - t.astype(np.float64)).astype(np.float32)
+    got = o.sphere_contacts(q, t, centre, 3.0)
+    assert len(got) > 20
+    _check_contacts(got, _contacts_float64(o, extent, q, t, centre, 3.0))
+    assert len(o.sphere_contacts(q, t, centre + np.float32([500.0, 0, 0]), 3.0)) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sphere", "asteroid_like", "random"])
+def test_gpu_sphere_contacts_equal_the_oracle_bit_for_bit(ctx, oracle, name):
+    from impact_b200.voxel import SDFVoxelGenerator, VoxelObject
+
+    extent = 0.5
+    if name == "random":
+        vox, sp, grid = H.random_voxel_chunks((64, 48, 50), 6)
+        c = oracle.Object.from_generated_chunks(vox, sp, grid, extent)
+        g = VoxelObject.from_generated_chunks(ctx, extent, grid, vox, sp)
+    else:
+        graph = H.sphere_graph(40.0) if name == "sphere" else H.asteroid_like_graph(16, 36.0)
+        c = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(graph.nodes(), graph.root_node_id), extent, H.GRADIENT4), 4)
+        g = VoxelObject.generate(SDFVoxelGenerator(extent, ctx.build_generator(graph), H.GRADIENT4))
+    shape = np.array(c.info()["chunk_counts"]) * 16
+    total = 0
+    for case, (axis, angle, t, off, radius) in enumerate([
+            ([0.3, 1.0, -0.2], 0.7, [1.5, -2.0, 0.75], [0.4, 0.03, -0.04], 3.0),
+            ([0.0, 0.0, 1.0], 0.0, [0.0, 0.0, 0.0], [-0.38, 0.1, 0.05], 6.5),
+            ([1.0, 0.2, 0.4], 2.4, [-7.0, 3.0, 11.0], [0.02, -0.41, 0.013], 1.25),
+            ([1.0, 0.0, 0.0], 1.0, [0.0, 0.0, 0.0], [3.0, 3.0, 3.0], 2.0)]):  # far outside: nothing
+        q = H.quat_from_axis_angle(axis, angle)
+        t = np.float32(t)
+        target_obj = extent * (0.5 * shape + np.array(off) * shape)
+        qc = np.array([-q[0], -q[1], -q[2], q[3]])
+        centre = H._rotate(qc, target_obj - t.astype(np.float64)).astype(np.float32)
+        got, want = g.sphere_contacts(q, t, centre, radius), c.sphere_contacts(q, t, centre, radius)
+        assert len(got) == len(want), (case, len(got), len(want))
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), case
+        total += len(got)
+    assert total > 50
