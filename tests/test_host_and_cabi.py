@@ -35,6 +35,34 @@ def test_struct_layouts_match_the_header():
     assert PROG_NODE_DTYPE.itemsize == 144
 
 
+def test_header_is_plain_c_and_record_sizes_match_the_bindings(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (and as C++), and the record types the bindings mirror
+    with numpy dtypes must have the sizes the C compiler gives them."""
+    import shutil
+    import subprocess
+
+    header = os.path.join(ROOT, "include", "impact_voxel_cuda.h")
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", header])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", header])
+    src = tmp_path / "sizes.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "impact_voxel_cuda.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ivx_voxel), sizeof(ivx_chunk_desc), '
+        "sizeof(ivx_chunk_submesh), sizeof(ivx_index_materials), sizeof(ivx_sdf_node), sizeof(ivx_node), "
+        "sizeof(ivx_inertial_moments), sizeof(ivx_isometry), sizeof(ivx_surface_voxel), sizeof(ivx_voxel_contact)); return 0; }\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    from impact_b200.graph import SDF_NODE_DTYPE as NODE_DTYPE
+
+    assert sizes == [L.VOXEL_DTYPE.itemsize, L.CHUNK_DTYPE.itemsize, L.SUBMESH_DTYPE.itemsize,
+                     L.INDEX_MATERIALS_DTYPE.itemsize, NODE_DTYPE.itemsize, PROG_NODE_DTYPE.itemsize, 40, 28,
+                     L.SURFACE_VOXEL_DTYPE.itemsize, L.CONTACT_DTYPE.itemsize], sizes
+
+
 def test_create_fails_loudly_without_a_device():
     import torch
 
