@@ -427,6 +427,28 @@ uint64_t orc_sphere_contacts(const void* op, const float q[4], const float t[3],
     return found.size();
 }
 
+uint64_t orc_plane_contacts(const void* op, const float q[4], const float t[3], const float normal[3], float displacement,
+                            VoxelContact* out, uint64_t capacity) {
+    std::vector<VoxelContact> found;
+    plane_voxel_object_contacts(*(const Object*)op, Isometry{Quat{q[0], q[1], q[2], q[3]}, v3(t[0], t[1], t[2])},
+                                v3(normal[0], normal[1], normal[2]), displacement, found);
+    const size_t n = std::min<size_t>(found.size(), capacity);
+    if (n) std::memcpy(out, found.data(), n * sizeof(VoxelContact));
+    return found.size();
+}
+void orc_voxel_ranges_within_plane(const uint32_t occ[6], const float normal[3], float displacement, uint32_t out[6]) {
+    uint32_t o[3][2], r[3][2];
+    for (int d = 0; d < 3; ++d) {
+        o[d][0] = occ[2 * d];
+        o[d][1] = occ[2 * d + 1];
+    }
+    voxel_ranges_within_plane(o, v3(normal[0], normal[1], normal[2]), displacement, r);
+    for (int d = 0; d < 3; ++d) {
+        out[2 * d] = r[d][0];
+        out[2 * d + 1] = r[d][1];
+    }
+}
+
 // ---- connected regions ----
 // Runs the whole detection on the object's current state. info (u32 x 24): n_regions, has_two, two[0], two[1],
 // smallest, overflow, n_region_entries, n_label_bytes, then per candidate region 8 words: chunk_count,

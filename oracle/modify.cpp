@@ -504,4 +504,58 @@ void sphere_voxel_object_contacts(const Object& obj, const Isometry& T, V3 cente
     }
 }
 
+// ---- plane queries and contacts (object/intersection.rs:30-40, 751-761; collidable.rs:1176-1209) -------------------
+void voxel_ranges_within_plane(const uint32_t occ[3][2], V3 n, float displacement, uint32_t out[3][2]) {
+    const float c[2][3] = {{(float)occ[0][0], (float)occ[1][0], (float)occ[2][0]},
+                           {(float)occ[0][1], (float)occ[1][1], (float)occ[2][1]}};
+    float lo[3] = {c[0][0], c[0][1], c[0][2]}, hi[3] = {c[1][0], c[1][1], c[1][2]};
+    const float nn[3] = {n.x, n.y, n.z};
+    const int perm[3][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}};
+    for (const auto& p : perm) {
+        const int i = p[0], j = p[1], k = p[2];
+        if (std::fabs(nn[k]) > 1e-8f) {
+            const float a = nn[i] * c[0][i] + nn[j] * c[0][j];
+            const float b = nn[i] * c[0][i] + nn[j] * c[1][j];
+            const float cc = nn[i] * c[1][i] + nn[j] * c[0][j];
+            const float d = nn[i] * c[1][i] + nn[j] * c[1][j];
+            const float extremal = (displacement - std::fmin(std::fmin(std::fmin(a, b), cc), d)) / nn[k];
+            if (!std::signbit(nn[k])) {
+                lo[k] = std::fmin(lo[k], extremal);
+                hi[k] = std::fmin(hi[k], extremal);
+            } else {
+                lo[k] = std::fmax(lo[k], extremal);
+                hi[k] = std::fmax(hi[k], extremal);
+            }
+        }
+    }
+    ranges_touching(occ, lo, hi, out);
+}
+
+void plane_voxel_object_contacts(const Object& obj, const Isometry& T, V3 normal, float displacement,
+                                 std::vector<VoxelContact>& out) {
+    out.clear();
+    const float e = obj.voxel_extent, inv_e = 1.0f / e;
+    // plane.iso_transformed(transform_to_object_space) (plane.rs:197-203), then .scaled(inverse_voxel_extent)
+    const V3 point_in_plane = normal * displacement;
+    const V3 tp = quat_rotate(T.q, point_in_plane) + T.t;
+    const V3 tn = quat_rotate(T.q, normal);
+    const float td = dot(tn, tp);
+    uint32_t r[3][2];
+    voxel_ranges_within_plane(obj.occ_voxels, tn, td * inv_e, r);
+    std::vector<SurfaceVoxel> sv;
+    surface_voxels_in_ranges(obj, r, sv);
+    const Quat qc = quat_conj(T.q);
+    for (const SurfaceVoxel& v : sv) {
+        if (v.placement != 2) continue;  // only the corner voxels matter against a plane
+        const V3 c_voxel = v3(((float)v.ijk[0] + 0.5f) * e, ((float)v.ijk[1] + 0.5f) * e, ((float)v.ijk[2] + 0.5f) * e);
+        const V3 vc = quat_rotate(qc, c_voxel - T.t);
+        const float vr = -sd_decode(v.voxel.sd) * e;
+        const float sd = dot(normal, vc) - displacement;
+        const float depth = vr - sd;
+        if (depth < 0.0f) continue;
+        const V3 pos = vc - sd * normal;
+        out.push_back(VoxelContact{{v.ijk[0], v.ijk[1], v.ijk[2]}, {pos.x, pos.y, pos.z}, {normal.x, normal.y, normal.z}, depth});
+    }
+}
+
 }  // namespace orc

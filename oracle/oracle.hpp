@@ -349,6 +349,14 @@ struct Isometry;
 void sphere_voxel_object_contacts(const Object& obj, const Isometry& transform_to_object_space, V3 center, float radius,
                                   std::vector<VoxelContact>& out);
 
+// for_each_voxel_object_plane_contact (collidable.rs:1176-1209) + determine_sphere_plane_contact_geometry (impact_physics
+// sphere.rs:138-158): corner voxels only; the plane { x : normal . x = displacement } in the space the transform starts from
+void plane_voxel_object_contacts(const Object& obj, const Isometry& transform_to_object_space, V3 unit_normal,
+                                 float displacement, std::vector<VoxelContact>& out);
+// voxel_ranges_within_plane (object/intersection.rs:751-761) with AxisAlignedBox::projected_onto_negative_halfspace
+// (impact_geometry/src/axis_aligned_box.rs:460-488); plane in normalized voxel space
+void voxel_ranges_within_plane(const uint32_t occupied[3][2], V3 unit_normal, float displacement, uint32_t out[3][2]);
+
 // apply_mutual_absorption (interaction/absorption.rs:891-1080) given the voxel ranges encompassing the intersection
 // (determine_voxel_ranges_encompassing_intersection, a pure function of the two occupied ranges and the transform that
 // stays with the caller): both objects subtract each other's volume.

@@ -328,6 +328,16 @@ class Object:
         lib().orc_sphere_contacts(self.h, _p(q), _p(t), _p(c), C.c_float(radius), _p(out), C.c_uint64(n))
         return out[:n]
 
+    def plane_contacts(self, rotation_xyzw, translation, unit_normal, displacement: float) -> np.ndarray:
+        """`for_each_voxel_object_plane_contact` (collidable.rs:1176-1209): corner voxels against the plane
+        { x : unit_normal . x = displacement } given in the space `transform_to_object_space` starts from."""
+        q, t, n = (np.asarray(x, np.float32) for x in (rotation_xyzw, translation, unit_normal))
+        lib().orc_plane_contacts.restype = C.c_uint64
+        cnt = lib().orc_plane_contacts(self.h, _p(q), _p(t), _p(n), C.c_float(displacement), None, C.c_uint64(0))
+        out = np.zeros(max(1, cnt), self.CONTACT_DTYPE)
+        lib().orc_plane_contacts(self.h, _p(q), _p(t), _p(n), C.c_float(displacement), _p(out), C.c_uint64(cnt))
+        return out[:cnt]
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113): → (info, extracted Object or None).
         This object is modified in place (the region's voxels leave it)."""
@@ -421,6 +431,15 @@ def absorb_mutually(a: "Object", b: "Object", rotation_xyzw, translation, smooth
                               _p(sa), _p(sb))
     keys = ("touched_chunks", "touched_voxels", "emptied_voxels", "removed_chunks")
     return dict(zip(keys, map(int, sa))), dict(zip(keys, map(int, sb)))
+
+
+def voxel_ranges_within_plane(occupied_voxel_ranges, unit_normal, displacement: float) -> np.ndarray:
+    """`voxel_ranges_within_plane` (object/intersection.rs:751-761) → 3 x 2."""
+    occ = np.ascontiguousarray(occupied_voxel_ranges, np.uint32).reshape(6)
+    n = np.asarray(unit_normal, np.float32)
+    out = np.zeros(6, np.uint32)
+    lib().orc_voxel_ranges_within_plane(_p(occ), _p(n), C.c_float(displacement), _p(out))
+    return out.reshape(3, 2)
 
 
 def _densities(densities) -> np.ndarray:

@@ -126,3 +126,17 @@ def test_voxel_ranges_within_plane_keep_every_voxel_of_the_negative_halfspace():
         if len(neg):
             assert (neg >= r[:, 0]).all() and (neg <= r[:, 1]).all(), (n, d, r)
         assert (r[:, 0] >= occ[:, 0]).all() and (r[:, 1] <= occ[:, 1]).all()
+
+
+def test_voxel_ranges_within_plane_equal_the_oracle(oracle):
+    # the library's host function against the oracle's restatement of projected_onto_negative_halfspace, same f32 steps
+    rng = np.random.default_rng(9)
+    for _ in range(300):
+        lo = rng.integers(0, 40, 3)
+        occ = np.stack([lo, lo + rng.integers(1, 90, 3)], 1).astype(np.uint32)
+        n = rng.normal(size=3)
+        if rng.random() < 0.3:
+            n[rng.integers(0, 3)] = 0.0  # planes parallel to an axis: the tolerance branch
+        n = (n / np.linalg.norm(n)).astype(np.float32)
+        d = float(np.float32(rng.uniform(-20, 150)))
+        assert np.array_equal(V.voxel_ranges_within_plane(occ, n, d), oracle.voxel_ranges_within_plane(occ, n, d)), (occ, n, d)

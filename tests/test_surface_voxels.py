@@ -181,3 +181,41 @@ def test_gpu_sphere_contacts_equal_the_oracle_bit_for_bit(ctx, oracle, name):
         assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), case
         total += len(got)
     assert total > 50
+
+
+def test_oracle_plane_contacts_equal_a_float64_evaluation(oracle):
+    # for_each_voxel_object_plane_contact (collidable.rs:1176-1209): corner voxels whose sphere reaches below the plane
+    g = H.asteroid_like_graph(12, 24.0)
+    extent = 0.5
+    o = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(g.nodes(), g.root_node_id), extent, H.GRADIENT4), 2)
+    shape = np.array(o.info()["chunk_counts"]) * 16
+    q = H.quat_from_axis_angle([0.3, 1.0, -0.2], 0.7)
+    t = np.float32([1.5, -2.0, 0.75])
+    qc = np.array([-q[0], -q[1], -q[2], q[3]])
+    # a plane (in the outer space) that cuts the object a few voxels above its lowest point along `normal`
+    normal = np.float64([0.2, -0.1, 1.0])
+    normal /= np.linalg.norm(normal)
+    sv = o.surface_voxels_in_ranges()
+    centres_outer = np.array([H._rotate(qc, (ix + 0.5) * extent - t.astype(np.float64)) for ix in sv["indices"].astype(np.float64)])
+    heights = centres_outer @ normal
+    displacement = float(np.float32(heights.min() + 2.2))
+    n32 = normal.astype(np.float32)
+    got = o.plane_contacts(q, t, n32, displacement)
+    assert len(got) > 5
+    # float64: corner surface voxels (<= 3 blocked faces) whose sphere reaches the plane
+    blocked = np.zeros(len(sv), np.int32)
+    for b in range(2, 8):
+        blocked += (sv["flags"] >> b) & 1
+    vr = -(sv["sd"].astype(np.float64) * 0.02) * extent
+    sd = centres_outer @ n32.astype(np.float64) - displacement
+    depth = vr - sd
+    want = {tuple(int(x) for x in ix) for ix, dep, bl in zip(sv["indices"], depth, blocked) if bl <= 3 and dep > 1e-4}
+    maybe = {tuple(int(x) for x in ix) for ix, dep, bl in zip(sv["indices"], depth, blocked) if bl <= 3 and dep > -1e-4}
+    got_set = {tuple(int(x) for x in r) for r in got["indices"]}
+    assert want <= got_set <= maybe, (len(want), len(got_set), len(maybe))
+    lookup = {tuple(int(x) for x in ix): n for n, ix in enumerate(sv["indices"])}
+    for r in got:
+        n = lookup[tuple(int(x) for x in r["indices"])]
+        assert abs(float(r["depth"]) - depth[n]) < 2e-4
+        assert np.allclose(r["position"], centres_outer[n] - sd[n] * n32, atol=2e-4)
+        assert np.array_equal(r["normal"], n32)
