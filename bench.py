@@ -8,8 +8,11 @@ derived state → Surface Nets mesh, for every chunk of the grid (for N > 1: of 
 `value` is whole-job voxels/s with the compiled SDF program already resident in HBM; `e2e` is the
 same metric through the host-buffer C ABI (graph nodes in pinned host memory → compile + upload →
 generate → mesh → object and mesh copied back to pinned host memory) inside the timed region.
-`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a
-bounded sample of the same workload.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) over the
+whole grid of the same workload, one contiguous group of chunk planes per step.
+After the timed regions one more step is run and hashed: `parity.digest_ok` says whether the object
+(per chunk plane, on every rank) and the (gathered) mesh equal the CPU oracle's committed digests
+(tests/golden/baseline_digests.json).
 """
 from __future__ import annotations
 
@@ -120,63 +123,146 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(graph, types, target_seconds: float, threads: int) -> dict:
-    """The CPU restatement of the reference (oracle/) on a bounded sample: a slab of chunk planes
-    around the object's centre, generate + derive + mesh, contiguous chunk ranges per thread
-    (the reference's own work split, object.rs:423-427)."""
-    from oracle import oracle_lib as O
+class CpuReference:
+    """The CPU restatement of the reference (oracle/, test infrastructure) as the timed baseline: generate + derive +
+    mesh of contiguous ranges of chunk planes, contiguous chunk ranges per thread (the reference's own work split,
+    object.rs:423-427). Loads only oracle/_build/liboracle.so — never the CUDA library."""
 
-    gen = O.Generator(graph.nodes(), graph.root_node_id)
-    vg = O.VoxelGenerator(gen, 1.0, types)
-    planes = (vg.grid_shape[0] + 15) // 16
-    mid = planes // 2
-    plane_voxels = 16 * vg.grid_shape[1] * vg.grid_shape[2]
+    def __init__(self, graph, types, threads: int):
+        from oracle import oracle_lib as O
 
-    def run(p0, p1):
+        self.O, self.threads = O, threads
+        self.vg = O.VoxelGenerator(O.Generator(graph.nodes(), graph.root_node_id), 1.0, types)
+        self.grid_shape = [int(x) for x in self.vg.grid_shape]
+        self.planes = (self.grid_shape[0] + 15) // 16
+
+    def voxels_in(self, p0: int, p1: int) -> int:
+        gx = self.grid_shape[0]
+        return (min(gx, p1 * 16) - min(gx, p0 * 16)) * self.grid_shape[1] * self.grid_shape[2]
+
+    def run(self, p0: int, p1: int):
+        """→ (seconds, generate s, derive s, mesh s) for the planes [p0, p1)."""
         t0 = time.perf_counter()
-        obj = O.Object.generate_slab(vg, p0, p1, threads)
-        m = obj.mesh(threads)
+        obj = self.O.Object.generate_slab(self.vg, p0, p1, self.threads)
+        m = obj.mesh(self.threads)
         dt = time.perf_counter() - t0
         return dt, obj.t_generate, obj.t_derive, m.t_mesh
 
-    dt1, *_ = run(mid, mid + 1)
-    n = int(max(1, min(planes, round(target_seconds / max(dt1, 1e-6)))))
-    p0 = max(0, mid - n // 2)
-    p1 = min(planes, p0 + n)
-    dt, tg, td, tm = run(p0, p1)
-    vox = (p1 - p0) * plane_voxels
-    return {"value": vox / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"chunk planes [{p0},{p1}) of {planes} ({vox} voxels of the {vg.grid_shape} grid): "
-                      f"generate {tg:.2f}s + derive {td:.2f}s + mesh {tm:.2f}s, {threads} threads",
-            "seconds": dt}
+    def groups(self, n: int):
+        """The plane range [0, planes) cut into min(n, planes) contiguous groups of (nearly) equal thickness."""
+        g = max(1, min(n, self.planes))
+        cuts = [round(i * self.planes / g) for i in range(g + 1)]
+        return [(cuts[i], cuts[i + 1]) for i in range(g)]
+
+
+def cpu_baseline_sample(graph, types, threads: int, target_seconds: float = 12.0) -> dict:
+    """`cpu_baseline` of the GPU arm: a STRATIFIED sample — every stride-th chunk plane over the whole x range, each as
+    its own one-plane slab — so dense central planes and the nearly empty outer ones are weighted as in the grid."""
+    ref = CpuReference(graph, types, threads)
+    mid = ref.planes // 2
+    dt1, *_ = ref.run(mid, mid + 1)  # the densest plane bounds the cost of the sample
+    stride = int(max(1, np.ceil(ref.planes * dt1 / max(target_seconds, 1e-6))))
+    picks = list(range(min(stride // 2, ref.planes - 1), ref.planes, stride))
+    secs = tg = td = tm = 0.0
+    vox = 0
+    for p in picks:
+        dt, g, d, m = ref.run(p, p + 1)
+        secs, tg, td, tm, vox = secs + dt, tg + g, td + d, tm + m, vox + ref.voxels_in(p, p + 1)
+    return {"value": vox / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"stratified: chunk planes {picks[0]}, {picks[0] + stride}, ... (every {stride}th of {ref.planes}, "
+                      f"{len(picks)} planes, {vox} voxels of the {tuple(ref.grid_shape)} grid), each as a one-plane slab: "
+                      f"generate {tg:.2f}s + derive {td:.2f}s + mesh {tm:.2f}s, {threads} threads"}
 
 
 def run_reference(args):
+    """`--impl reference`: the CPU restatement over the WHOLE grid, once: the K timed steps are K contiguous plane
+    groups that together cover every chunk plane exactly once (so value = grid voxels / total seconds is the whole-grid
+    throughput, with no extrapolation from a dense sample); warm-up steps repeat the first groups."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     graph, types, desc = make_workload(args.workload)
     threads = os.cpu_count() or 1
-    per_step = max(2.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        cpu_reference(graph, types, per_step, threads)
-    vals, secs, last = [], 0.0, None
-    for _ in range(args.steps):
-        last = cpu_reference(graph, types, per_step, threads)
-        vals.append(last["value"])
-        secs += last["seconds"]
-    v = float(np.mean(vals))
-    from impact_b200 import workloads as W
-
+    ref = CpuReference(graph, types, threads)
+    groups = ref.groups(args.steps)
+    for w in range(args.warmup):  # one plane of a group each: warms caches and the thread pool, costs little
+        p0 = groups[w % len(groups)][0]
+        ref.run(p0, p0 + 1)
+    secs = tg = td = tm = 0.0
+    passes = max(1, args.steps // len(groups))  # small grids: several whole passes
+    for _ in range(passes):
+        for p0, p1 in groups:
+            dt, g, d, m = ref.run(p0, p1)
+            secs, tg, td, tm = secs + dt, tg + g, td + d, tm + m
+    total_voxels = int(np.prod(ref.grid_shape))
+    v = passes * total_voxels / secs
+    n_steps = passes * len(groups)
+    sample = (f"whole grid: chunk planes [0,{ref.planes}) as {len(groups)} contiguous groups, one per timed step"
+              f"{f', {passes} passes' if passes > 1 else ''} ({passes * total_voxels} voxels): generate {tg:.2f}s + "
+              f"derive {td:.2f}s + mesh {tm:.2f}s, {threads} threads")
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, n_steps), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "grid_shape": list(W.grid_shape_of(graph))},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": last["sample"]},
+        "config": workload_config(args.workload, desc, ref.grid_shape),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "timed_steps": n_steps,
     }
     emit(out)
+
+
+def workload_config(workload: str, desc: str, grid_shape) -> dict:
+    """The `config` keys both arms share (the GPU arm adds its own under config["gpu"])."""
+    return {"workload": workload, "description": desc, "grid_shape": [int(x) for x in grid_shape]}
+
+
+# ---------------------------------------------------------------------------------------------
+def parity_check(workload, step_resident, last_merged, rank: int, world: int) -> dict:
+    """Runs one more (untimed) step and compares it with tests/golden/baseline_digests.json — sha256 digests of the CPU
+    oracle's output for this workload at this size: every rank hashes the chunk planes of its own slab, rank 0 also the
+    mesh (for N > 1: the mesh gathered from all ranks). Pure hashing; the oracle itself is not run here."""
+    import torch.distributed as dist
+
+    from impact_b200 import digests as DG
+    from impact_b200 import distributed as D
+
+    fixture = os.path.join(ROOT, "tests", "golden", "baseline_digests.json")
+    want = None
+    if os.path.exists(fixture):
+        with open(fixture) as f:
+            want = json.load(f).get(workload)
+    if want is None:
+        return {"digest_ok": None, "reason": f"no committed oracle digests for workload {workload!r}"}
+    obj, mesh = step_resident()
+    info = obj.info()
+    chunks, voxels = obj.download()
+    mine = (int(info["chunk_i_begin"]), DG.object_plane_digests(chunks, voxels, info["chunk_counts"]))
+    del chunks, voxels
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    else:
+        parts = [mine]
+    out = None
+    if rank == 0:
+        planes = [d for _, ds in sorted(parts) for d in ds]
+        bad = [p for p, (a, b) in enumerate(zip(planes, want["object_planes"])) if a != b]
+        object_ok = len(planes) == len(want["object_planes"]) and not bad
+        if world > 1:
+            m = D.merged_mesh_to_numpy(last_merged[0])
+        else:
+            m = mesh.download()
+        mesh_ok = (len(m["positions"]), len(m["indices"])) == (want["vertices"], want["indices"]) and \
+            DG.mesh_digest(m["positions"], m["normals"], m["indices"], m["index_materials"], m["submeshes"],
+                           m["vertex_ranges"]) == want["mesh"]
+        out = {"digest_ok": bool(object_ok and mesh_ok), "object_ok": bool(object_ok), "mesh_ok": bool(mesh_ok),
+               "object_planes_checked": len(planes), "object_planes_differing": bad[:8], "ranks": world,
+               "mesh": f"{len(m['positions'])} vertices, {len(m['indices'])} indices" + (" gathered on rank 0" if world > 1 else ""),
+               "against": "tests/golden/baseline_digests.json (sha256 of the CPU oracle's object per chunk plane and of its "
+                          "mesh buffers, tests/golden/make_baseline_digests.py)"}
+    obj.free()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -245,12 +331,14 @@ def run_gpu(args):
             merged = D.gather_mesh(D.device_mesh_tensors(mesh, dev), rank, world, dev)
         ev[4].record(stream)
         phase_events.append(ev)
+        last_merged[0] = merged
         if merged is not None:
             halo_stats["merged_vertices"] = int(merged["positions"].shape[0])
             halo_stats["merged_indices"] = int(merged["indices"].shape[0])
         return obj, mesh
 
     halo_stats = {}
+    last_merged = [None]
     # mesh gather: peer-memory stores (CUDA IPC + NVLink) unless IVX_GATHER=nccl asks for the NCCL send/recv path
     peer_gather = [D.PeerMeshGather(ctx, rank, world, dev) if world > 1 and os.environ.get("IVX_GATHER", "peer") == "peer"
                    else None]
@@ -368,6 +456,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
 
+        # ---- parity: one more step, hashed against the CPU oracle's committed digests (outside every timed region) ----
+        parity = parity_check(args.workload, step_resident, last_merged, rank, world)
+
     t = torch.tensor([ms_total / args.steps, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -404,8 +495,8 @@ def run_gpu(args):
             "metric": METRIC, "value": total_voxels / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic",
-            "config": {
-                "workload": args.workload, "description": desc, "grid_shape": grid_shape,
+            "config": workload_config(args.workload, desc, grid_shape),
+            "details": {
                 "chunks": int(np.prod(info[0]["chunk_counts"])), "parallelism": f"x-slab x{world}" + (" (work-balanced plane ranges)" if world > 1 else ""),
                 "slab_planes": [list(r) for r in ranges], "rank0_exchange": halo_stats,
                 "mesh_gather": ("peer-memory stores into rank 0 (ivx_mesh_push over NVLink, CUDA IPC)"
@@ -418,6 +509,7 @@ def run_gpu(args):
                 "timing": "CUDA events on the library's stream around each step, summed over K steps, max over ranks",
             },
             "clocks": clocks,
+            "parity": parity,
             "gpu_launches": int(launches),
             "e2e": {"value": total_voxels / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(nodes_host.nbytes + 16), "d2h_bytes_per_step": int(d2h),
@@ -443,8 +535,7 @@ def run_gpu(args):
             "whole_path_roofline_frac": (5.0 * total_voxels / step_s / 1e9) / peak,
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = {k: v for k, v in cpu_reference(graph, types, 12.0, os.cpu_count() or 1).items()
-                                   if k != "seconds"}
+            out["cpu_baseline"] = cpu_baseline_sample(graph, types, os.cpu_count() or 1)
         emit(out)
     if peer_gather[0] is not None:
         peer_gather[0].close()

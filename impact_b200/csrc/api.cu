@@ -1713,8 +1713,17 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     }
     KLP(ctx, 6, launch_absorb_apply(aa, persistent_grid(ctx, n_range, 4), st));
     obj->slots_used += w[0];
-    if (upd)
-        if (int rc = ivx_apply_removed_voxels(ctx, obj, r, n_range, aa.removed_info, aa.removed_cols, *upd)) return rc;
+    obj->split_valid = false;  // the voxels changed: labels / roots downloaded from now on must come from a new resolve
+    // The voxels are modified from here on. If the inertial update fails (an emptied voxel's type has no density) the
+    // error is reported only after the boundary refresh, occupied ranges and stale-label marks below have run, so the
+    // object the caller keeps is consistent.
+    int upd_rc = IVX_OK;
+    std::string upd_err;
+    if (upd) {
+        upd_rc = ivx_apply_removed_voxels(ctx, obj, r, n_range, aa.removed_info, aa.removed_cols, *upd);
+        if (upd_rc != IVX_OK && upd_rc != IVX_ERR_INVALID_ARGUMENT) return upd_rc;  // device failure: nothing to salvage
+        if (upd_rc) upd_err = ivx_last_error(ctx);
+    }
 
     // boundary refresh over chunk range [start-1, end) (intersection.rs:391-393)
     AbsorbRange b = r;
@@ -1766,6 +1775,7 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
         ivx_object_dirty_chunks(ctx, obj, nullptr, 0, &cnt);
         out_stats->dirty_chunks = cnt;
     }
+    if (upd_rc) IVX_FAIL(ctx, upd_rc, "%s", upd_err.c_str());
     return IVX_OK;
 }
 

@@ -385,9 +385,18 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
     uint32_t* counters = ctx->d_scratch + 32;  // [0] n_work [1] n_records [2] error
     CU(ctx, cudaMemsetAsync(counters, 0, 16, st));
 
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
+    struct EventPair {  // destroyed on every exit path
+        cudaEvent_t a = nullptr, b = nullptr;
+        EventPair() {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+        }
+        ~EventPair() {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } ev;
+    const cudaEvent_t e0 = ev.a, e1 = ev.b;
     cudaEventRecord(e0, st);
     ctx->launches++;
     k_init_regions<<<(n + 255) / 256, 256, 0, st>>>(obj->d_chunks, n, regions, obj->d_label_stale, flag);
@@ -424,8 +433,6 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
     }
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&out->device_ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (words[2] == 1u)
         IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "a chunk has more than 254 connected regions (the reference asserts, split_detection.rs:798)");
     if (words[2] == 2u)

@@ -358,3 +358,46 @@ def merged_mesh_to_numpy(merged: dict) -> dict:
         "submeshes": np.ascontiguousarray(g["submeshes"]).view(L.SUBMESH_DTYPE).reshape(-1),
         "vertex_ranges": g["vertex_ranges"].view(np.uint32),
     }
+
+
+# ---- several slabs held by ONE process (tests; a host that drives several objects on one device) ---------------
+def exchange_halos_single_process(objs, device=None) -> None:
+    """The slab protocol between the x-slab objects `objs` (in slab order, all on one device): the halo messages are
+    handed over as device buffers, no process group involved."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    live = [o for o in objs if o.info()["chunk_i_begin"] != o.info()["chunk_i_end"]]
+    for a, b in zip(live[:-1], live[1:]):  # exchange A across each cut
+        for src, s_side, dst in ((a, 1, b), (b, 0, a)):
+            cap = src.halo_capacity()
+            buf = torch.empty(cap, dtype=torch.uint8, device=device)
+            n = src.halo_export(s_side, buf.data_ptr(), cap)
+            dst.halo_import(1 - s_side, buf.data_ptr(), n)
+            src.ctx.synchronize()
+    for o in live:
+        o.slab_classify()
+    for a, b in zip(live[:-1], live[1:]):  # exchange B: upper slab's lowest plane kinds → lower slab
+        plane = b.plane_chunks()
+        buf = torch.empty(plane, dtype=torch.uint8, device=device)
+        b.halo_kinds_export(0, buf.data_ptr(), plane)
+        a.halo_kinds_import(1, buf.data_ptr(), plane)
+        a.ctx.synchronize()
+    for o in live:
+        o.slab_finalize()
+
+
+def merge_mesh_parts(parts: list[dict]) -> dict:
+    """`concat_meshes` for downloaded meshes (`VoxelObjectMesh.download()` dicts, numpy): slab order, rebased."""
+    v0 = i0 = 0
+    out = {k: [] for k in ("positions", "normals", "indices", "index_materials", "submeshes", "vertex_ranges")}
+    for p in parts:
+        out["positions"].append(p["positions"])
+        out["normals"].append(p["normals"])
+        out["indices"].append(p["indices"] + np.uint32(v0))
+        out["index_materials"].append(p["index_materials"])
+        sm = p["submeshes"].copy()
+        sm["index_offset"] += np.uint32(i0)
+        out["submeshes"].append(sm)
+        out["vertex_ranges"].append(p["vertex_ranges"] + np.uint32(v0))
+        v0 += len(p["positions"])
+        i0 += len(p["indices"])
+    return {k: np.concatenate(v) for k, v in out.items()}
