@@ -35,87 +35,35 @@ constexpr int TYPES_UNROLL = IVX_TYPES_UNROLL;  // voxel pairs in flight per thr
 #endif
 constexpr int TAB_CAP = 1024;        // gradient-table entries (float4) per batch of types
 constexpr int MAX_TYPES = 255;
-constexpr float CELL_LIMIT = 4096.0f;  // |cell index| < 2^12 and strides <= 2^9: every integer-valued f32 term stays below 2^22
+constexpr float CELL_LIMIT = 4096.0f;  // |cell index| < 2^12 and byte strides <= 2^14: every address term stays below 2^26 (TypeTab2)
 
-struct TypeTab {   // per-type constants of the table walk
-    float x;       // noise x coordinate of this type (already multiplied by voxel_type_frequency)
-    float base;    // MAGIC - entry index of the first lattice cell
-    float sa, sb, sc;  // strides of axes 0..2 in entries (axis 3 has stride 1)
-    float s4;      // sa + sb + sc + 1: entry step to the far corner
-    uint32_t addr; // shared-memory byte address of entry 0, minus 16 * MAGIC_BITS
+// Per-type constants of the table walk, every value duplicated into an f32x2 pair (packed operands are register
+// pairs; a pair loaded from shared memory needs no MOVs). Table positions are carried as *byte addresses held in
+// the bit pattern of a float*: an integer N < 2^24 reinterpreted as f32 is the subnormal (or smallest-binade normal)
+// value N·2^-149, sums and products with small integers of such values are exact in f32 (all terms here are multiples
+// of 16·2^-149 below 2^28·2^-149), and FADD / FFMA handle subnormals at full rate. The walk therefore ends with the
+// shared-memory byte address of the gradient entry *as the float's bits*: no integer instruction per table load.
+struct TypeTab2 {
+    f2 x;       // noise x coordinate of this type (already multiplied by voxel_type_frequency)
+    f2 base;    // bits: byte address of the entry of lattice cell (0,0,0,0) (may be "negative": exact all the same)
+    f2 sa, sb, sc;  // bits: byte strides of axes 0..2 (axis 3 has stride 16)
+    f2 s4;      // sa + sb + sc + 16: byte step to the far corner
 };
-
-
-// simdnoise simplex_4d (see common.cuh simplex4_t for the direct restatement) with the gradient of
-// each corner read from the chunk's lattice table.
-__device__ __forceinline__ float simplex4_tab(float x, float y, float z, float w, const TypeTab& T) {
-    const float F4 = 0.309016994f, G4 = 0.138196601f;
-    const float G24 = 2.0f * 0.138196601f, G34 = 3.0f * 0.138196601f, G44 = 4.0f * 0.138196601f;
-    const float s = F4 * (x + (y + (z + w)));
-    const float ips = floorf(x + s), jps = floorf(y + s), kps = floorf(z + s), lps = floorf(w + s);
-    // (float)(i + (j + (k + l))): the cell indices are small integers, so the f32 sum is exact
-    const float t = (ips + (jps + (kps + lps))) * G4;
-    const float x0 = x - (ips - t), y0 = y - (jps - t), z0 = z - (kps - t), w0 = w - (lps - t);
-
-    // ranks (how many of the other coordinates each one exceeds), as exact small floats
-    const float pxy = x0 > y0 ? 1.0f : 0.0f, pxz = x0 > z0 ? 1.0f : 0.0f, pxw = x0 > w0 ? 1.0f : 0.0f;
-    const float pyz = y0 > z0 ? 1.0f : 0.0f, pyw = y0 > w0 ? 1.0f : 0.0f, pzw = z0 > w0 ? 1.0f : 0.0f;
-    const float rx = (pxy + pxz) + pxw;
-    const float ry = ((1.0f - pxy) + pyz) + pyw;
-    const float rz = ((2.0f - pxz) - pyz) + pzw;
-    const float rw = ((6.0f - rx) - ry) - rz;
-    // corner c steps along the axes whose rank exceeds 3 - c (compares run on the ALU pipe, which
-    // this kernel leaves mostly idle)
-    const float i1 = rx > 2.5f ? 1.0f : 0.0f, j1 = ry > 2.5f ? 1.0f : 0.0f, k1 = rz > 2.5f ? 1.0f : 0.0f,
-                l1 = rw > 2.5f ? 1.0f : 0.0f;
-    const float i2 = rx > 1.5f ? 1.0f : 0.0f, j2 = ry > 1.5f ? 1.0f : 0.0f, k2 = rz > 1.5f ? 1.0f : 0.0f,
-                l2 = rw > 1.5f ? 1.0f : 0.0f;
-    const float i3 = fminf(rx, 1.0f), j3 = fminf(ry, 1.0f), k3 = fminf(rz, 1.0f), l3 = fminf(rw, 1.0f);
-
-    // table addresses: entry = ((a·Db + b)·Dc + c)·Dd + d relative to the first cell, accumulated on top
-    // of MAGIC so that the integer sits in the low mantissa bits (T.base = MAGIC - first cell's entry; all
-    // terms are integers below 2^22, so every FMA is exact); one IMAD turns the bits into an address
-    const float e0 = __fmaf_rn(ips, T.sa, __fmaf_rn(jps, T.sb, __fmaf_rn(kps, T.sc, lps + T.base)));
-    const float e1 = __fmaf_rn(i1, T.sa, __fmaf_rn(j1, T.sb, __fmaf_rn(k1, T.sc, l1 + e0)));
-    const float e2 = __fmaf_rn(i2, T.sa, __fmaf_rn(j2, T.sb, __fmaf_rn(k2, T.sc, l2 + e0)));
-    const float e3 = __fmaf_rn(i3, T.sa, __fmaf_rn(j3, T.sb, __fmaf_rn(k3, T.sc, l3 + e0)));
-    const float e4 = e0 + T.s4;
-    const float4 g0 = lds128(__float_as_uint(e0) * 16u + T.addr);
-    const float4 g1 = lds128(__float_as_uint(e1) * 16u + T.addr);
-    const float4 g2 = lds128(__float_as_uint(e2) * 16u + T.addr);
-    const float4 g3 = lds128(__float_as_uint(e3) * 16u + T.addr);
-    const float4 g4 = lds128(__float_as_uint(e4) * 16u + T.addr);
-
-    const float x1 = (x0 - i1) + G4, y1 = (y0 - j1) + G4, z1 = (z0 - k1) + G4, w1 = (w0 - l1) + G4;
-    const float x2 = (x0 - i2) + G24, y2 = (y0 - j2) + G24, z2 = (z0 - k2) + G24, w2 = (w0 - l2) + G24;
-    const float x3 = (x0 - i3) + G34, y3 = (y0 - j3) + G34, z3 = (z0 - k3) + G34, w3 = (w0 - l3) + G34;
-    const float x4 = (x0 - 1.0f) + G44, y4 = (y0 - 1.0f) + G44, z4 = (z0 - 1.0f) + G44, w4 = (w0 - 1.0f) + G44;
-
-    float t0 = (((0.5f - x0 * x0) - y0 * y0) - z0 * z0) - w0 * w0;
-    float t1 = (((0.5f - x1 * x1) - y1 * y1) - z1 * z1) - w1 * w1;
-    float t2 = (((0.5f - x2 * x2) - y2 * y2) - z2 * z2) - w2 * w2;
-    float t3 = (((0.5f - x3 * x3) - y3 * y3) - z3 * z3) - w3 * w3;
-    float t4 = (((0.5f - x4 * x4) - y4 * y4) - z4 * z4) - w4 * w4;
-    // a corner with t < 0 contributes 0: clamping t first makes its term ±0 instead
-    t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); t2 = fmaxf(t2, 0.0f); t3 = fmaxf(t3, 0.0f); t4 = fmaxf(t4, 0.0f);
-    float q0 = t0 * t0, q1 = t1 * t1, q2 = t2 * t2, q3 = t3 * t3, q4 = t4 * t4;
-    q0 = q0 * q0; q1 = q1 * q1; q2 = q2 * q2; q3 = q3 * q3; q4 = q4 * q4;
-    // products with a gradient component in {-1, 0, +1} are exact, so each FMA rounds exactly once, like
-    // the separate multiply and add it replaces
-    const float n0 = q0 * __fmaf_rn(g0.x, x0, __fmaf_rn(g0.y, y0, __fmaf_rn(g0.z, z0, g0.w * w0)));
-    const float n1 = q1 * __fmaf_rn(g1.x, x1, __fmaf_rn(g1.y, y1, __fmaf_rn(g1.z, z1, g1.w * w1)));
-    const float n2 = q2 * __fmaf_rn(g2.x, x2, __fmaf_rn(g2.y, y2, __fmaf_rn(g2.z, z2, g2.w * w2)));
-    const float n3 = q3 * __fmaf_rn(g3.x, x3, __fmaf_rn(g3.y, y3, __fmaf_rn(g3.z, z3, g3.w * w3)));
-    const float n4 = q4 * __fmaf_rn(g4.x, x4, __fmaf_rn(g4.y, y4, __fmaf_rn(g4.z, z4, g4.w * w4)));
-    return (n0 + (n1 + (n2 + (n3 + n4)))) * 62.77772078955791f;
+__device__ __forceinline__ float addr_as_float(int32_t n) {
+    // n·2^-149, exactly (|n| < 2^24): non-negative n is the bit pattern itself
+    return n >= 0 ? __uint_as_float((uint32_t)n) : -__uint_as_float((uint32_t)(-n));
 }
+__device__ __forceinline__ float4 tab_load_bits(float e) { return lds128(__float_as_uint(e)); }
 
-// simplex4_tab for the voxel pair (y.x, y.y); x, z, w are the same for both. Operation for operation
-// the scalar function above.
-__device__ __forceinline__ f2 simplex4_tab2(f2 x, f2 y, f2 z, f2 w, f2 zw, const TypeTab& T, f2 nz) {
+// simdnoise simplex_4d (see common.cuh simplex4_t for the direct restatement) for the voxel pair (y.x, y.y) — z and w
+// are the same for both — with the gradient of each corner read from the chunk's lattice table; every packed operation
+// rounds like the scalar one it stands for.
+// `yzw` = y + (z + w) (the same for every type of a voxel pair), `T` = the type's constants in shared memory.
+__device__ __forceinline__ f2 simplex4_tab2(f2 y, f2 z, f2 w, f2 yzw, const TypeTab2& T, f2 nz) {
     const float F4 = 0.309016994f, G4 = 0.138196601f;
     const float G24 = 2.0f * 0.138196601f, G34 = 3.0f * 0.138196601f, G44 = 4.0f * 0.138196601f;
-    const f2 s = mul2(bc2(F4), add2(x, add2(y, zw)), nz);
+    const f2 x = T.x;
+    const f2 s = mul2(bc2(F4), add2(x, yzw), nz);
     const f2 ips = floor2(add2(x, s)), jps = floor2(add2(y, s)), kps = floor2(add2(z, s)), lps = floor2(add2(w, s));
     const f2 t = mul2(add2(ips, add2(jps, add2(kps, lps))), bc2(G4), nz);
     const f2 x0 = sub2(x, sub2(ips, t)), y0 = sub2(y, sub2(jps, t)), z0 = sub2(z, sub2(kps, t)), w0 = sub2(w, sub2(lps, t));
@@ -130,17 +78,18 @@ __device__ __forceinline__ f2 simplex4_tab2(f2 x, f2 y, f2 z, f2 w, f2 zw, const
     const f2 i2 = gtc2(rx, 1.5f), j2 = gtc2(ry, 1.5f), k2 = gtc2(rz, 1.5f), l2 = gtc2(rw, 1.5f);
     const f2 i3 = min2c(rx, 1.0f), j3 = min2c(ry, 1.0f), k3 = min2c(rz, 1.0f), l3 = min2c(rw, 1.0f);
 
-    const f2 sa = bc2(T.sa), sb = bc2(T.sb), sc = bc2(T.sc);
-    const f2 e0 = fma2(ips, sa, fma2(jps, sb, fma2(kps, sc, add2(lps, bc2(T.base)))));
-    const f2 e1 = fma2(i1, sa, fma2(j1, sb, fma2(k1, sc, add2(l1, e0))));
-    const f2 e2 = fma2(i2, sa, fma2(j2, sb, fma2(k2, sc, add2(l2, e0))));
-    const f2 e3 = fma2(i3, sa, fma2(j3, sb, fma2(k3, sc, add2(l3, e0))));
-    const f2 e4 = add2(e0, bc2(T.s4));
-    const float4 g0a = tab_load(e0.x, T.addr), g0b = tab_load(e0.y, T.addr);
-    const float4 g1a = tab_load(e1.x, T.addr), g1b = tab_load(e1.y, T.addr);
-    const float4 g2a = tab_load(e2.x, T.addr), g2b = tab_load(e2.y, T.addr);
-    const float4 g3a = tab_load(e3.x, T.addr), g3b = tab_load(e3.y, T.addr);
-    const float4 g4a = tab_load(e4.x, T.addr), g4b = tab_load(e4.y, T.addr);
+    // byte addresses of the five corners' gradient entries, as float bits (see TypeTab2)
+    const f2 sa = T.sa, sb = T.sb, sc = T.sc, sd = bc2(__uint_as_float(16u));
+    const f2 e0 = fma2(ips, sa, fma2(jps, sb, fma2(kps, sc, fma2(lps, sd, T.base))));
+    const f2 e1 = fma2(i1, sa, fma2(j1, sb, fma2(k1, sc, fma2(l1, sd, e0))));
+    const f2 e2 = fma2(i2, sa, fma2(j2, sb, fma2(k2, sc, fma2(l2, sd, e0))));
+    const f2 e3 = fma2(i3, sa, fma2(j3, sb, fma2(k3, sc, fma2(l3, sd, e0))));
+    const f2 e4 = add2(e0, T.s4);
+    const float4 g0a = tab_load_bits(e0.x), g0b = tab_load_bits(e0.y);
+    const float4 g1a = tab_load_bits(e1.x), g1b = tab_load_bits(e1.y);
+    const float4 g2a = tab_load_bits(e2.x), g2b = tab_load_bits(e2.y);
+    const float4 g3a = tab_load_bits(e3.x), g3b = tab_load_bits(e3.y);
+    const float4 g4a = tab_load_bits(e4.x), g4b = tab_load_bits(e4.y);
 
     const f2 c1 = bc2(G4), c2 = bc2(G24), c3 = bc2(G34), c4 = bc2(G44), one = bc2(1.0f), half = bc2(0.5f);
     const f2 x1 = add2(sub2(x0, i1), c1), y1 = add2(sub2(y0, j1), c1), z1 = add2(sub2(z0, k1), c1), w1 = add2(sub2(w0, l1), c1);
@@ -192,8 +141,9 @@ __device__ __forceinline__ float type_axis_coordinate(uint32_t t) {
 
 struct TypesSmem {
     float4 tab[TAB_CAP];
-    float best[16 * TYPES_THREADS];     // [k][thread]
-    uint8_t best_t[16 * TYPES_THREADS];
+    TypeTab2 tt[TAB_CAP / 16];          // per-type constants of the current batch (a type's table has >= 2^4 entries)
+    float best[16 * TYPES_THREADS];     // [k][thread]: running maximum, only between the batches of a multi-batch chunk
+    uint16_t type_pair[8 * TYPES_THREADS];  // [k / 2][thread]: the winning types of a voxel pair (low byte = even k)
     int8_t sd[4096];
     int cmin[MAX_TYPES + 1][4];
     int cmax[MAX_TYPES + 1][4];
@@ -370,43 +320,74 @@ __global__ void __launch_bounds__(TYPES_THREADS, IVX_TYPES_CTAS) k_types(TypesAr
                         }
                     }
                     __syncthreads();
-                    // ---- evaluate the batch's types over this thread's k-column ----
-                    for (uint32_t t = t0; t < t1; ++t) {
-                        TypeTab T;
-                        T.x = type_axis_coordinate(t) * ft;
-                        const uint32_t Dd = (uint32_t)(S.cmax[t][3] - S.cmin[t][3] + 2);
-                        const uint32_t Dc = (uint32_t)(S.cmax[t][2] - S.cmin[t][2] + 2);
-                        const uint32_t Db = (uint32_t)(S.cmax[t][1] - S.cmin[t][1] + 2);
-                        T.sc = (float)Dd;
-                        T.sb = (float)(Dd * Dc);
-                        T.sa = (float)(Dd * Dc * Db);
-                        T.s4 = (float)(Dd * Dc * Db + Dd * Dc + Dd + 1u);
-                        T.base = MAGIC - (((float)S.cmin[t][0] * T.sa + (float)S.cmin[t][1] * T.sb) +
-                                          ((float)S.cmin[t][2] * T.sc + (float)S.cmin[t][3]));
-                        T.addr = tab_base + (uint32_t)S.tab_off[t] * 16u - MAGIC_BITS * 16u;
-                        const f2 X2 = bc2(T.x);
-                        float yacc = lo.z;
-#pragma unroll TYPES_UNROLL
-                        for (int k = 0; k < 16; k += 2) {
-                            const float yacc1 = yacc + 1.0f;
-                            const f2 nv = simplex4_tab2(X2, make_float2(yacc * fn, yacc1 * fn), Z2, W2, ZW2, T, nz);
-                            const int bi = k * TYPES_THREADS + tid;
-                            if (t == 0 || nv.x > S.best[bi]) {
-                                S.best[bi] = nv.x;
-                                S.best_t[bi] = (uint8_t)t;
-                            }
-                            if (t == 0 || nv.y > S.best[bi + TYPES_THREADS]) {
-                                S.best[bi + TYPES_THREADS] = nv.y;
-                                S.best_t[bi + TYPES_THREADS] = (uint8_t)t;
-                            }
-                            yacc = yacc1 + 1.0f;
+                    // ---- per-type constants (one thread per type of the batch) ----
+                    for (uint32_t t = t0 + tid; t < t1; t += TYPES_THREADS) {
+                        const int32_t Dd = S.cmax[t][3] - S.cmin[t][3] + 2, Dc = S.cmax[t][2] - S.cmin[t][2] + 2,
+                                      Db = S.cmax[t][1] - S.cmin[t][1] + 2;
+                        const int32_t sc = 16 * Dd, sb = sc * Dc, sa = sb * Db;
+                        // address of cell (0,0,0,0): |cmin| < 2^12 and strides <= 2^14 bytes keep every term below 2^26
+                        const float base =
+                            ((addr_as_float((int32_t)tab_base + 16 * (int32_t)S.tab_off[t]) -
+                              (float)S.cmin[t][0] * addr_as_float(sa)) - (float)S.cmin[t][1] * addr_as_float(sb)) -
+                            ((float)S.cmin[t][2] * addr_as_float(sc) + (float)S.cmin[t][3] * addr_as_float(16));
+                        TypeTab2 T;
+                        T.x = bc2(type_axis_coordinate(t) * ft);
+                        T.base = bc2(base);
+                        T.sa = bc2(addr_as_float(sa));
+                        T.sb = bc2(addr_as_float(sb));
+                        T.sc = bc2(addr_as_float(sc));
+                        T.s4 = bc2(addr_as_float(sa + sb + sc + 16));
+                        S.tt[t - t0] = T;
+                    }
+                    __syncthreads();
+                    // ---- evaluate the batch's types over this thread's k-column: voxel pair outermost, types
+                    // innermost, the running maximum of the pair in registers ----
+                    const bool first_batch = t0 == 0, last_batch = t1 == n_types;
+                    float yacc = lo.z;
+#pragma unroll 1
+                    for (int k = 0; k < 16; k += 2) {
+                        const float yacc1 = yacc + 1.0f;
+                        const f2 Y2 = make_float2(yacc * fn, yacc1 * fn);
+                        const f2 YZW = add2(Y2, ZW2);
+                        const int bi = k * TYPES_THREADS + tid;
+                        f2 best;
+                        uint32_t bt;
+                        if (first_batch) {
+                            best = make_float2(0.0f, 0.0f);
+                            bt = 0u;
+                        } else {
+                            best = make_float2(S.best[bi], S.best[bi + TYPES_THREADS]);
+                            bt = S.type_pair[(k >> 1) * TYPES_THREADS + tid];
                         }
+#pragma unroll 1
+                        for (uint32_t t = t0; t < t1; ++t) {
+                            const f2 nv = simplex4_tab2(Y2, Z2, W2, YZW, S.tt[t - t0], nz);
+                            // voxel_type.rs:154-165: the first type's noise starts the maximum, later ones need `>`
+                            if (t == 0u || nv.x > best.x) {
+                                best.x = nv.x;
+                                bt = (bt & 0xFF00u) | t;
+                            }
+                            if (t == 0u || nv.y > best.y) {
+                                best.y = nv.y;
+                                bt = (bt & 0x00FFu) | (t << 8);
+                            }
+                        }
+                        S.type_pair[(k >> 1) * TYPES_THREADS + tid] = (uint16_t)bt;
+                        if (!last_batch) {
+                            S.best[bi] = best.x;
+                            S.best[bi + TYPES_THREADS] = best.y;
+                        }
+                        yacc = yacc1 + 1.0f;
                     }
                     __syncthreads();  // the table is rebuilt by the next batch
                     t0 = t1;
                 }
 #pragma unroll
-                for (int k = 0; k < 16; ++k) types[k] = S.best_t[k * TYPES_THREADS + tid];
+                for (int k = 0; k < 16; k += 2) {
+                    const uint32_t bt = S.type_pair[(k >> 1) * TYPES_THREADS + tid];
+                    types[k] = (uint8_t)(bt & 0xFFu);
+                    types[k + 1] = (uint8_t)(bt >> 8);
+                }
             }
         }
 
