@@ -311,38 +311,61 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_comm = world > 1 and os.environ.get("IVX_COMM", "peer") == "peer"
+
+    def step_nccl(step_ranges):
+        """Fallback / calibration path (IVX_COMM=nccl): the explicit slab protocol with NCCL messages and host waits."""
+        obj = VoxelObject.generate(vg, step_ranges[rank])
+        halo_stats.update(D.exchange_halos_and_finalize(obj, step_ranges, rank, dev))
+        mesh = VoxelObjectMesh.create(obj)
+        return obj, mesh
+
     def step_resident():
         if world == 1:
             obj = VoxelObject.generate(vg)
             return obj, VoxelObjectMesh.create(obj)
-        # x-slab per rank → halo planes over NCCL → derived state → mesh → mesh gathered on rank 0
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record(stream)
-        step_ranges = partition()  # the work estimate belongs to the compiled program and is cached with it
-        obj = VoxelObject.generate(vg, step_ranges[rank])
-        ev[1].record(stream)
-        halo_stats.update(D.exchange_halos_and_finalize(obj, step_ranges, rank, dev))
-        ev[2].record(stream)
-        mesh = VoxelObjectMesh.create(obj)
-        ev[3].record(stream)
-        if peer_gather[0] is not None:
-            merged = peer_gather[0].gather(mesh)  # every rank stores its part into rank 0's memory over NVLink
+        if use_comm:
+            # x-slab per rank → boundary planes stored into the neighbours' windows over NVLink, awaited on the device →
+            # derived state → mesh → every rank's part stored into rank 0's merged mesh: three C-ABI calls, one host
+            # synchronisation (at the end of the last)
+            obj = VoxelObject.generate(vg, ranges[rank])
+            ev[1].record(stream)
+            comm[0].exchange_halos(obj, ranges)
+            ev[2].record(stream)
+            mesh, merged = comm[0].mesh_gather(obj)
+            ev[3].record(stream)
+            if merged is not None:
+                halo_stats["merged_vertices"], halo_stats["merged_indices"] = int(merged.n_vertices), int(merged.n_indices)
+                merged = D.PeerComm.merged_to_torch(merged, dev)
         else:
+            obj = VoxelObject.generate(vg, ranges[rank])
+            ev[1].record(stream)
+            halo_stats.update(D.exchange_halos_and_finalize(obj, ranges, rank, dev))
+            ev[2].record(stream)
+            mesh = VoxelObjectMesh.create(obj)
             merged = D.gather_mesh(D.device_mesh_tensors(mesh, dev), rank, world, dev)
-        ev[4].record(stream)
+            ev[3].record(stream)
         phase_events.append(ev)
         last_merged[0] = merged
-        if merged is not None:
-            halo_stats["merged_vertices"] = int(merged["positions"].shape[0])
-            halo_stats["merged_indices"] = int(merged["indices"].shape[0])
         return obj, mesh
 
     halo_stats = {}
     last_merged = [None]
-    # mesh gather: peer-memory stores (CUDA IPC + NVLink) unless IVX_GATHER=nccl asks for the NCCL send/recv path
-    peer_gather = [D.PeerMeshGather(ctx, rank, world, dev) if world > 1 and os.environ.get("IVX_GATHER", "peer") == "peer"
-                   else None]
-    phase_events = []  # multi-GPU: (generate, halo exchange + derive, mesh, gather) per step
+    comm = [None]
+    phase_events = []  # multi-GPU: (generate, halo exchange + derive, mesh + gather) per step
+
+    if use_comm:
+        with torch.cuda.stream(stream):
+            # capacity of the merged mesh: one step over the explicit protocol, sizes summed over the ranks
+            obj, mesh = step_nccl(ranges)
+            sizes = torch.tensor([mesh.n_vertices, mesh.n_indices, mesh.n_submeshes], dtype=torch.int64, device=dev)
+            dist.all_reduce(sizes)
+            cc = obj.info()["chunk_counts"]
+            obj.free()
+            cap = [int(x * 1.25) + 1024 for x in sizes.tolist()]
+            comm[0] = D.PeerComm(ctx, rank, world, int(cc[1]) * int(cc[2]), cap, gather_rank=0, device=dev)
 
     with torch.cuda.stream(stream):
         info = None
@@ -372,10 +395,10 @@ def run_gpu(args):
         barrier()
         if phase_events:
             last = phase_events[-args.steps:]
-            names = ("generate_slab", "halo_exchange_and_derive", "mesh", "gather_mesh")
-            mine = torch.tensor([float(np.mean([e[i].elapsed_time(e[i + 1]) for e in last])) for i in range(4)],
+            names = ("generate_slab", "halo_exchange_and_derive", "mesh_and_gather")
+            mine = torch.tensor([float(np.mean([e[i].elapsed_time(e[i + 1]) for e in last])) for i in range(3)],
                                 dtype=torch.float64, device="cuda")
-            allp = [torch.zeros(4, dtype=torch.float64, device="cuda") for _ in range(world)]
+            allp = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in range(world)]
             dist.all_gather(allp, mine)
             halo_stats["phase_ms_per_rank"] = {n: [round(float(t[i]), 3) for t in allp] for i, n in enumerate(names)}
         launches = ctx.kernel_launch_count - launches0
@@ -415,8 +438,13 @@ def run_gpu(args):
                 ctx.check(lib.ivx_object_generate_slab(ctx.h, prog, C.c_float(1.0), L.ptr(tgp), C.c_uint32(rr[rank][0]),
                                                        C.c_uint32(rr[rank][1]), C.byref(o)))
                 view = VoxelObject(ctx, o)
-                D.exchange_halos_and_finalize(view, rr, rank, dev)
-                view.h = None  # `o` is freed below
+                if use_comm:
+                    comm[0].exchange_halos(view, rr)
+                    # the slab's voxels start their way to the host now; meshing and the gather run beside the transfer
+                    ctx.check(lib.ivx_object_download_async(ctx.h, o, L.ptr(h_chunks), C.c_size_t(n_local_chunks), L.ptr(h_vox),
+                                                            C.c_size_t(cap_vox * 4096), None))
+                else:
+                    D.exchange_halos_and_finalize(view, rr, rank, dev)
             else:
                 # generation with the voxel download overlapped (parts of chunk planes; copy stream)
                 nnu = C.c_uint64()
@@ -425,9 +453,14 @@ def run_gpu(args):
                                                            C.c_size_t(cap_vox * 4096), C.byref(o), C.byref(nnu)))
             mark()
             mi = L.MeshInfo()
-            ctx.check(lib.ivx_object_mesh(ctx.h, o, C.byref(mi)))
-            mark()
+            if world > 1 and use_comm:
+                mi = comm[0].mesh_gather(view)[0].device_info
+            else:
+                ctx.check(lib.ivx_object_mesh(ctx.h, o, C.byref(mi)))
             if world > 1:
+                view.h = None  # `o` is freed below
+            mark()
+            if world > 1 and not use_comm:
                 ctx.check(lib.ivx_object_download(ctx.h, o, L.ptr(h_chunks), C.c_size_t(n_local_chunks), L.ptr(h_vox),
                                                   C.c_size_t(cap_vox * 4096)))
             assert mi.n_vertices <= cap_v and mi.n_indices <= cap_i and mi.n_submeshes <= cap_s
@@ -499,9 +532,9 @@ def run_gpu(args):
             "details": {
                 "chunks": int(np.prod(info[0]["chunk_counts"])), "parallelism": f"x-slab x{world}" + (" (work-balanced plane ranges)" if world > 1 else ""),
                 "slab_planes": [list(r) for r in ranges], "rank0_exchange": halo_stats,
-                "mesh_gather": ("peer-memory stores into rank 0 (ivx_mesh_push over NVLink, CUDA IPC)"
-                                if peer_gather[0] is not None and peer_gather[0].available
-                                else ("NCCL send/recv" if world > 1 else "none")),
+                "multi_gpu": ("ivx_comm: halo planes and mesh parts stored into peer windows over NVLink (CUDA IPC), flags awaited "
+                              "on the device; NCCL only for the handle exchange, the barrier and the timing reduction"
+                              if use_comm else ("explicit slab protocol over NCCL send/recv" if world > 1 else "none")),
                 "rank0_chunks": {"void": oi["n_void"], "uniform": oi["n_uniform"], "non_uniform": oi["n_non_uniform"]},
                 "rank0_mesh": {"vertices": info[1], "indices": info[2], "submeshes": info[3]},
                 "l2": "256 MiB buffer written between timed iterations (outside the timed intervals); the voxel "
@@ -517,9 +550,10 @@ def run_gpu(args):
                     "path": "ivx_program_build(host nodes) → ivx_object_generate_streamed (object download overlapped with "
                             "generation on a copy stream) → ivx_object_mesh → ivx_mesh_download → ivx_synchronize; "
                             "all outputs in pinned host buffers" if world == 1 else
-                            "per rank: ivx_program_build(host nodes) → ivx_object_generate_slab → halo exchange (NCCL) → "
-                            "ivx_object_slab_finalize → ivx_object_mesh → ivx_object_download + ivx_mesh_download of "
-                            "the rank's slab into pinned host buffers; d2h bytes are rank 0's"},
+                            "per rank: ivx_program_build(host nodes) → ivx_object_generate_slab → ivx_object_exchange_halos → "
+                            "ivx_object_download_async (slab voxels to pinned host memory on the copy stream) beside "
+                            "ivx_object_mesh_gather → ivx_mesh_download of the rank's slab mesh → ivx_synchronize; d2h bytes "
+                            "are rank 0's"},
             "roofline": {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": per_voxel, "voxels_per_launch": my_voxels,
@@ -537,8 +571,8 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(graph, types, os.cpu_count() or 1)
         emit(out)
-    if peer_gather[0] is not None:
-        peer_gather[0].close()
+    if comm[0] is not None:
+        comm[0].close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

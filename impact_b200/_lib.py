@@ -27,13 +27,15 @@ EXPORTED_SYMBOLS = [
     "ivx_program_eval_chunks", "ivx_program_eval_blocks", "ivx_object_generate", "ivx_object_generate_streamed", "ivx_object_generate_slab", "ivx_program_plane_work", "ivx_object_halo_capacity", "ivx_object_halo_export",
     "ivx_object_halo_import", "ivx_object_slab_classify", "ivx_object_halo_kinds_export", "ivx_object_halo_kinds_import",
     "ivx_object_slab_finalize", "ivx_object_info_get",
-    "ivx_object_download", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_peer_alloc", "ivx_peer_free", "ivx_peer_open", "ivx_peer_close", "ivx_mesh_push", "ivx_object_absorb_sphere", "ivx_object_absorb_capsule",
+    "ivx_object_download", "ivx_object_download_async", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_peer_alloc", "ivx_peer_free", "ivx_peer_open", "ivx_peer_close", "ivx_mesh_push", "ivx_object_absorb_sphere", "ivx_object_absorb_capsule",
     "ivx_object_dirty_chunks", "ivx_object_remesh_dirty",
     "ivx_object_resolve_connected_regions", "ivx_object_split_detection_download", "ivx_object_extract_disconnected_region",
     "ivx_object_from_generated_chunks", "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",
     "ivx_objects_absorb_mutually", "ivx_intersection_voxel_ranges", "ivx_box_intersection_bounds",
     "ivx_object_surface_voxels_in_ranges", "ivx_object_surface_voxels_touching_sphere", "ivx_object_surface_voxels_touching_capsule",
     "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane", "ivx_object_sphere_contacts",
+    "ivx_comm_create", "ivx_comm_connect", "ivx_comm_connect_local", "ivx_comm_destroy", "ivx_object_exchange_halos",
+    "ivx_object_mesh_gather",
 ]
 
 
@@ -58,6 +60,17 @@ class MeshInfo(C.Structure):
                 ("n_exposed_chunks", C.c_uint32), ("d_positions", C.c_void_p), ("d_normals", C.c_void_p),
                 ("d_index_materials", C.c_void_p), ("d_indices", C.c_void_p), ("d_submeshes", C.c_void_p),
                 ("d_vertex_ranges", C.c_void_p)]
+
+
+class CommConfig(C.Structure):
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("gather_rank", C.c_uint32), ("plane_chunks", C.c_uint32),
+                ("mesh_vertices", C.c_uint64), ("mesh_indices", C.c_uint64), ("mesh_submeshes", C.c_uint64)]
+
+
+class GatheredMesh(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint64), ("n_indices", C.c_uint64), ("n_submeshes", C.c_uint64),
+                ("d_positions", C.c_void_p), ("d_normals", C.c_void_p), ("d_indices", C.c_void_p),
+                ("d_index_materials", C.c_void_p), ("d_submeshes", C.c_void_p), ("d_vertex_ranges", C.c_void_p)]
 
 
 class ExtractionInfo(C.Structure):
@@ -123,6 +136,8 @@ def lib():
         L.ivx_program_free.restype = None
         L.ivx_object_free.argtypes = [C.c_void_p, C.c_void_p]
         L.ivx_object_free.restype = None
+        L.ivx_comm_destroy.argtypes = [C.c_void_p, C.c_void_p]
+        L.ivx_comm_destroy.restype = None
         _lib = L
     return _lib
 

@@ -35,6 +35,71 @@ int read_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t n, uint32_t* out) {
     return IVX_OK;
 }
 
+// ---- plans (api_internal.cuh GenPlan) ----
+struct PlanWords {
+    uint32_t idx[12];
+    uint32_t want[12];
+    uint32_t n;
+};
+// compares device counters with what the plan promised; a mismatch sets the context's sticky plan-error word
+__global__ void k_check_plan(const uint32_t* __restrict__ counters, PlanWords w, uint32_t* __restrict__ err_word) {
+    if (threadIdx.x < w.n && counters[w.idx[threadIdx.x]] != w.want[threadIdx.x]) {
+        *err_word = 1u + w.idx[threadIdx.x];
+        __threadfence_system();
+    }
+}
+cudaError_t check_plan(ivx_ctx* ctx, const uint32_t* d_counters, const PlanWords& w) {
+    k_check_plan<<<1, 32, 0, ctx->stream>>>(d_counters, w, ctx->h_pinned_dev + ivx_ctx::PLAN_ERROR_WORD);
+    return cudaGetLastError();
+}
+// after a stream synchronisation: did any plan check fail since the last look?
+int take_plan_error(ivx_ctx* ctx) {
+    const uint32_t e = ctx->h_pinned[ivx_ctx::PLAN_ERROR_WORD];
+    if (!e) return IVX_OK;
+    ctx->h_pinned[ivx_ctx::PLAN_ERROR_WORD] = 0;
+    ctx->plans.clear();
+    IVX_FAIL(ctx, IVX_ERR_CUDA, "a cached generation plan did not match the device's counters (word %u); the plans were "
+             "dropped, repeat the call", e - 1u);
+}
+GenPlan* lookup_plan(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, const ivx_type_generator* tg, uint32_t i_begin,
+                     uint32_t i_end, bool whole, bool streamed) {
+    if (std::getenv("IVX_NO_PLANS")) return nullptr;
+    for (auto& pl : ctx->plans)
+        if (pl.prog_uid == prog->uid && pl.voxel_extent == voxel_extent && std::memcmp(&pl.types, tg, sizeof(*tg)) == 0 &&
+            pl.i_begin == i_begin && pl.i_end == i_end && pl.whole == whole && pl.streamed == streamed)
+            return &pl;
+    return nullptr;
+}
+GenPlan* new_plan(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, const ivx_type_generator* tg, uint32_t i_begin,
+                  uint32_t i_end, bool whole, bool streamed) {
+    if (ctx->plans.size() >= ivx_ctx::MAX_PLANS) ctx->plans.erase(ctx->plans.begin());
+    GenPlan pl;
+    pl.serial = ctx->next_serial++;
+    pl.prog_uid = prog->uid;
+    pl.voxel_extent = voxel_extent;
+    pl.types = *tg;
+    pl.i_begin = i_begin;
+    pl.i_end = i_end;
+    pl.whole = whole;
+    pl.streamed = streamed;
+    ctx->plans.push_back(pl);
+    return &ctx->plans.back();
+}
+
+// plans are keyed by the program's CONTENT (a host that rebuilds the same graph every frame still hits its plan)
+uint64_t program_content_hash(const HostProgram& h) {
+    uint64_t x = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) x = (x ^ b[i]) * 1099511628211ull;
+    };
+    if (!h.nodes.empty()) mix(h.nodes.data(), h.nodes.size() * sizeof(ivx_node));
+    mix(&h.stack_depth, sizeof(h.stack_depth));
+    mix(h.domain_lo, sizeof(h.domain_lo));
+    mix(h.domain_hi, sizeof(h.domain_hi));
+    return x | 1ull;
+}
+
 void free_mesh(ivx_ctx* ctx, DeviceMesh& m) {
     ctx->release(m.positions);
     ctx->release(m.normals);
@@ -161,8 +226,20 @@ struct StreamOut {
     uint64_t n_non_uniform;  // out
 };
 
+__global__ void k_plane_sum_flags(const uint32_t* __restrict__ flag, uint32_t n, uint32_t plane, uint32_t* __restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n && flag[c]) atomicAdd(&out[c / plane], 1u);
+}
+__global__ void k_plane_sum_stored(const DevChunk* __restrict__ chunks, uint32_t n, uint32_t plane, uint32_t* __restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n && chunks[c].kind != 0) atomicAdd(&out[c / plane], 1u);
+}
+
+// `plane_stats` (planning only, ivx_program_plane_work): [p] = chunks of local plane p the SDF program was evaluated on,
+// [planes + p] = chunks of it that ended up stored (Uniform or NonUniform: the ones that needed voxel types)
 int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, const ivx_type_generator* tg,
-                  uint32_t i_begin, uint32_t i_end, bool whole, ivx_object** out, StreamOut* so = nullptr) {
+                  uint32_t i_begin, uint32_t i_end, bool whole, ivx_object** out, StreamOut* so = nullptr,
+                  std::vector<uint32_t>* plane_stats = nullptr) {
     if (!(voxel_extent > 0.0f)) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "voxel_extent must be > 0");
     if (tg->kind > 1) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "unknown voxel type generator kind %u", tg->kind);
     if (tg->kind == 1 && (tg->n_types == 0 || tg->n_types > 255))
@@ -190,6 +267,10 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     gp.ci_begin = i_begin;
     gp.ci_end = i_end;
     gp.types = *tg;
+    // a plan of an earlier generation of the same object: no host round trips below
+    const GenPlan* plan = plane_stats ? nullptr : lookup_plan(ctx, prog, voxel_extent, tg, i_begin, i_end, whole, so != nullptr);
+    const GenPlan plan_copy = plan ? *plan : GenPlan{};  // ctx->plans may be reshuffled by nested calls
+    if (plan) plan = &plan_copy;
     gp.n_nodes = (uint32_t)prog->host.nodes.size();
     gp.stack_depth = prog->host.stack_depth;
 
@@ -341,13 +422,30 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     if (!active_flag || !slot_flag || !active_scan || !slot_of || !active_list)
         IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "slot planning: out of device memory");
     KL(ctx, launch_plan_slots(obj->d_chunks, n, obj->nb, active_flag, slot_flag, st));
+    uint32_t* d_plane_stats = nullptr;
+    if (plane_stats) {
+        d_plane_stats = tmp.get<uint32_t>(2 * (size_t)obj->nb[0]);
+        if (!d_plane_stats) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "plane statistics: out of device memory");
+        CU(ctx, cudaMemsetAsync(d_plane_stats, 0, 2 * (size_t)obj->nb[0] * 4, st));
+        ctx->launches++;
+        k_plane_sum_flags<<<(n + 255) / 256, 256, 0, st>>>(active_flag, n, obj->nb[1] * obj->nb[2], d_plane_stats);
+        CU(ctx, cudaGetLastError());
+    }
     KL(ctx, launch_exclusive_scan(active_flag, active_scan, n, counters + 9, st));
     KL(ctx, launch_exclusive_scan(slot_flag, slot_of, n, counters + 10, st));
     KL(ctx, launch_scatter_active(active_flag, active_scan, n, active_list, st));
-    if (int rc = read_words(ctx, counters, 16, words)) return rc;
+    if (plan) {
+        words[0] = 0;
+        words[9] = plan->n_active;
+        words[10] = plan->n_slots;
+        words[1] = plan->max_depth;
+    } else {
+        if (int rc = read_words(ctx, counters, 16, words)) return rc;
+        if (int rc = take_plan_error(ctx)) return rc;
+    }
     if (words[0]) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "SDF program needs an operand stack deeper than 64");
     const uint32_t n_active = words[9], n_slots = words[10], max_depth = words[1];
-    if (std::getenv("IVX_DEBUG")) {
+    if (!plan && std::getenv("IVX_DEBUG")) {
         std::vector<uint32_t> hc(n), hact(n);
         cudaMemcpy(hc.data(), ch_len, n * 4, cudaMemcpyDeviceToHost);
         cudaMemcpy(hact.data(), active_flag, n * 4, cudaMemcpyDeviceToHost);
@@ -408,7 +506,9 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     for (uint32_t q = 0; q <= P; ++q) xb[q] = (uint32_t)((uint64_t)q * obj->nb[0] / P);
     ab[0] = 0;
     ab[P] = n_active;
-    if (P > 1) {
+    if (P > 1 && plan && plan->part_active.size() == P + 1) {
+        ab = plan->part_active;
+    } else if (P > 1) {
         // active_scan[c] = number of active chunks before chunk c
         for (uint32_t q = 1; q < P; ++q)
             CU(ctx, store_words(ctx, active_scan + (size_t)xb[q] * plane, 32 + q, 1));
@@ -527,7 +627,41 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
         so->n_non_uniform = base;
     }
 
-    if (int rc = read_words(ctx, counters, 16, words)) return rc;
+    if (plane_stats) {
+        ctx->launches++;
+        k_plane_sum_stored<<<(n + 255) / 256, 256, 0, st>>>(obj->d_chunks, n, obj->nb[1] * obj->nb[2], d_plane_stats + obj->nb[0]);
+        CU(ctx, cudaGetLastError());
+        plane_stats->assign(2 * (size_t)obj->nb[0], 0u);
+        CU(ctx, cudaMemcpyAsync(plane_stats->data(), d_plane_stats, plane_stats->size() * 4, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    }
+    if (plan) {
+        // the device's counters against the plan, checked at the next synchronisation (take_plan_error)
+        PlanWords pw{};
+        const uint32_t idx[10] = {0, 1, 9, 10, 2, 3, 4, 5, 6, 7};
+        const uint32_t want[10] = {0, plan->max_depth, plan->n_active, plan->n_slots, plan->occ[0], plan->occ[1], plan->occ[2],
+                                   plan->occ[3], plan->occ[4], plan->occ[5]};
+        pw.n = 10;
+        for (int q = 0; q < 10; ++q) {
+            pw.idx[q] = idx[q];
+            pw.want[q] = want[q];
+        }
+        CU(ctx, check_plan(ctx, counters, pw));
+        for (int q = 0; q < 6; ++q) words[2 + q] = plan->occ[q];
+        obj->plan_serial = plan->serial;
+    } else {
+        if (int rc = read_words(ctx, counters, 16, words)) return rc;
+        if (int rc = take_plan_error(ctx)) return rc;
+        if (!std::getenv("IVX_NO_PLANS")) {
+            GenPlan* np = new_plan(ctx, prog, voxel_extent, tg, i_begin, i_end, whole, so != nullptr);
+            np->n_active = n_active;
+            np->n_slots = n_slots;
+            np->max_depth = max_depth;
+            for (int q = 0; q < 6; ++q) np->occ[q] = words[2 + q];
+            if (P > 1) np->part_active = ab;
+            obj->plan_serial = np->serial;
+        }
+    }
     const bool any = words[2] != 0xFFFFFFFFu;
     for (int d = 0; d < 3; ++d) {
         obj->occ_voxels[d] = any ? words[2 + d] : 0u;
@@ -660,8 +794,12 @@ __global__ void k_count_kinds(const DevChunk* chunks, uint32_t n, uint32_t lo, u
 
 namespace {
 
-// meshes the chunks flagged in `work_flag` (ascending linear order) into `m`
-int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMesh& m) {
+// meshes the chunks flagged in `work_flag` (ascending linear order) into `m`.
+// `plan`: the mesh counts of an earlier identical call (GenPlan::mesh_counts) — buffers and launches are sized from it
+// and the device's own counts are only compared with it afterwards, so the call has no host round trip before its end.
+// `sync`: wait for the mesh (and report a plan mismatch) before returning; with false the caller does both later.
+int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMesh& m, const uint32_t* plan = nullptr,
+              bool sync = true, uint32_t counts_out[4] = nullptr) {
     free_mesh(ctx, m);
     const uint32_t n = obj->n_chunks;
     if (n == 0) return IVX_OK;
@@ -674,10 +812,24 @@ int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMe
     KL(ctx, launch_exclusive_scan(work_flag, scan, n, counters + 16, st));
     KL(ctx, launch_scatter_active(work_flag, scan, n, work, st));
     uint32_t words[8];
-    if (int rc = read_words(ctx, counters + 16, 1, words)) return rc;
+    if (plan) {
+        words[0] = plan[0];
+    } else {
+        if (int rc = read_words(ctx, counters + 16, 1, words)) return rc;
+    }
     const uint32_t n_work = words[0];
     m.n_work = n_work;
-    if (n_work == 0) return IVX_OK;
+    if (counts_out) counts_out[0] = n_work, counts_out[1] = counts_out[2] = counts_out[3] = 0;
+    if (n_work == 0) {
+        if (plan) {
+            PlanWords pw{};
+            pw.n = 1;
+            pw.idx[0] = 16;
+            pw.want[0] = 0;
+            CU(ctx, check_plan(ctx, counters, pw));
+        }
+        return IVX_OK;
+    }
 
     uint32_t* vcount = tmp.get<uint32_t>(n_work);
     uint32_t* icount = tmp.get<uint32_t>(n_work);
@@ -702,10 +854,27 @@ int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMe
     KL(ctx, launch_exclusive_scan(vcount, voff, n_work, counters + 17, st));
     KL(ctx, launch_exclusive_scan(icount, ioff, n_work, counters + 18, st));
     KL(ctx, launch_exclusive_scan(hsub, sord, n_work, counters + 19, st));
-    if (int rc = read_words(ctx, counters + 17, 3, words)) return rc;
+    if (plan) {
+        words[0] = plan[1];
+        words[1] = plan[2];
+        words[2] = plan[3];
+        PlanWords pw{};
+        pw.n = 4;
+        for (uint32_t q = 0; q < 4; ++q) {
+            pw.idx[q] = 16 + q;
+            pw.want[q] = plan[q];
+        }
+        CU(ctx, check_plan(ctx, counters, pw));
+        ma.cap_vertices = plan[1];
+        ma.cap_indices = plan[2];
+        ma.cap_submeshes = plan[3];
+    } else {
+        if (int rc = read_words(ctx, counters + 17, 3, words)) return rc;
+    }
     m.n_vertices = words[0];
     m.n_indices = words[1];
     m.n_submeshes = words[2];
+    if (counts_out) counts_out[1] = words[0], counts_out[2] = words[1], counts_out[3] = words[2];
     m.positions = static_cast<float*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_vertices) * 12));
     m.normals = static_cast<float*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_vertices) * 12));
     m.indices = static_cast<uint32_t*>(ctx->alloc(std::max<size_t>(1, (size_t)m.n_indices) * 4));
@@ -731,7 +900,10 @@ int mesh_impl(ivx_ctx* ctx, ivx_object* obj, const uint32_t* work_flag, DeviceMe
     CU(ctx, cudaMemsetAsync(ma.mq_count, 0, 4, st));
     KLP(ctx, 5, launch_mesh(true, ma, grid, st));
     KLP(ctx, 5, launch_mesh_materials(ma.mq_entries, ma.mq_count, ma.mq_capacity, m.index_materials, st));
-    CU(ctx, cudaStreamSynchronize(st));
+    if (sync) {
+        CU(ctx, cudaStreamSynchronize(st));
+        if (int rc = take_plan_error(ctx)) return rc;
+    }
     return IVX_OK;
 }
 
@@ -810,6 +982,7 @@ int ivx_create(const ivx_config* config, ivx_ctx** out_ctx) {
         ivx_destroy(ctx);
         return IVX_ERR_OUT_OF_MEMORY;
     }
+    std::memset(ctx->h_pinned, 0, 64 * sizeof(uint32_t));
     *out_ctx = ctx;
     return IVX_OK;
 }
@@ -845,7 +1018,7 @@ int ivx_synchronize(ivx_ctx* ctx) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->aux_stream));
     CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    return IVX_OK;
+    return take_plan_error(ctx);
 }
 
 static void drain_profile(ivx_ctx* ctx) {
@@ -902,6 +1075,7 @@ int ivx_program_build(ivx_ctx* ctx, const ivx_sdf_node* nodes, uint32_t n_nodes,
         ivx_program_free(ctx, p);
         return rc;
     }
+    p->uid = program_content_hash(p->host);
     *out = p;
     return IVX_OK;
 }
@@ -925,6 +1099,7 @@ int ivx_program_upload(ivx_ctx* ctx, const ivx_node* nodes, uint32_t n_nodes, ui
         ivx_program_free(ctx, p);
         return rc;
     }
+    p->uid = program_content_hash(p->host);
     *out = p;
     return IVX_OK;
 }
@@ -1095,6 +1270,42 @@ int ivx_program_plane_work(ivx_ctx* ctx, const ivx_program* prog, float voxel_ex
     *out_planes = nb[0];
     if (!out_work) return IVX_OK;
     if (capacity < nb[0]) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u planes", nb[0]);
+    // Planning by doing: the first request for a (program, extent, type generator) generates the whole object once on
+    // this device and counts, per chunk plane, the chunks the SDF program ran on and the chunks that needed voxel
+    // types — the two costs of generation (k_eval ~45 ns, k_types ~30 ns per voxel type per chunk on a B200) — plus a
+    // small per-chunk share for the fold and the cross-chunk pass. It is kept with the context (keyed by the program's
+    // content), so partitioning the same program again costs nothing. IVX_PLANE_WORK=estimate (or an object whose
+    // storage bound does not fit the device) selects the cheap estimate below instead: conservative folds only.
+    {
+        for (const auto& wp : ctx->work_plans)
+            if (wp.prog_uid == prog->uid && wp.voxel_extent == voxel_extent && std::memcmp(&wp.types, tg, sizeof(*tg)) == 0 &&
+                wp.work.size() == nb[0]) {
+                std::memcpy(out_work, wp.work.data(), nb[0] * 4);
+                return IVX_OK;
+            }
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const char* mode = std::getenv("IVX_PLANE_WORK");
+        const uint64_t bound = (uint64_t)nb[0] * nb[1] * nb[2] * SLOT_BYTES;
+        if (!(mode && std::strcmp(mode, "estimate") == 0) && !prog->host.nodes.empty() && bound < free_b / 2) {
+            ivx_object* dry = nullptr;
+            std::vector<uint32_t> stats;
+            if (int rc = generate_impl(ctx, prog, voxel_extent, tg, 0, 0, true, &dry, nullptr, &stats)) return rc;
+            ivx_object_free(ctx, dry);
+            const uint32_t w_eval = 45u, w_types = tg->kind == 1 ? 30u * std::max(1u, tg->n_types) : 4u, w_chunk = 8u;
+            ivx_ctx::WorkPlan wp;
+            wp.prog_uid = prog->uid;
+            wp.voxel_extent = voxel_extent;
+            wp.types = *tg;
+            wp.work.resize(nb[0]);
+            for (uint32_t p = 0; p < nb[0]; ++p)
+                wp.work[p] = 1u + w_eval * stats[p] + w_types * stats[nb[0] + p] + w_chunk * nb[1] * nb[2];
+            std::memcpy(out_work, wp.work.data(), nb[0] * 4);
+            if (ctx->work_plans.size() >= ivx_ctx::MAX_PLANS) ctx->work_plans.erase(ctx->work_plans.begin());
+            ctx->work_plans.push_back(std::move(wp));
+            return IVX_OK;
+        }
+    }
     // relative cost of a chunk (measured on the 1024^3 asteroid: k_types 0.14 us, k_eval 0.18 us per chunk):
     // an inside chunk needs a type per voxel under GradientNoise and nothing under Same; an undecided chunk needs
     // the SDF program and, when it is not void, types
@@ -1283,6 +1494,9 @@ int ivx_object_halo_kinds_import(ivx_ctx* ctx, ivx_object* obj, int side, const 
 
 int ivx_object_slab_finalize(ivx_ctx* ctx, ivx_object* obj) {
     if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
+    return ivx_internal_slab_finalize(ctx, obj, true);
+}
+int ivx_internal_slab_finalize(ivx_ctx* ctx, ivx_object* obj, bool sync) {
     cudaSetDevice(ctx->device);
     if (!obj->derive_pending) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "object is not a slab with pending derived state");
     if (obj->n_chunks) {
@@ -1291,8 +1505,9 @@ int ivx_object_slab_finalize(ivx_ctx* ctx, ivx_object* obj) {
         KLP(ctx, 3, launch_boundary_apply(obj->d_chunks, obj->n_chunks, obj->nb, nullptr, obj->d_convert_flag, obj->d_slot_of,
                                           obj->d_voxels, nullptr, obj->n_chunks, obj->own_begin - obj->first_i,
                                           obj->own_end - obj->first_i, persistent_grid(ctx, obj->n_chunks, 8), ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (sync) CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    // (released blocks are reused by later work on this same stream only, so no wait is needed for that)
     ctx->release(obj->d_slot_of);
     ctx->release(obj->d_convert_flag);
     obj->d_slot_of = obj->d_convert_flag = nullptr;
@@ -1368,6 +1583,49 @@ int ivx_object_download(ivx_ctx* ctx, const ivx_object* obj, ivx_chunk_desc* chu
     return IVX_OK;
 }
 
+// ivx_object_download with the device→host transfer left running on the context's copy stream: the voxels are packed
+// into a staging block on the compute stream, the copies follow on the copy stream, and later work on the compute stream
+// (meshing, the mesh gather) overlaps them. The host buffers are complete after ivx_synchronize.
+int ivx_object_download_async(ivx_ctx* ctx, ivx_object* obj, ivx_chunk_desc* chunks, size_t chunk_capacity, ivx_voxel* voxels,
+                              size_t voxel_capacity, uint64_t* out_non_uniform_chunks) {
+    if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (out_non_uniform_chunks) *out_non_uniform_chunks = 0;
+    const uint32_t plane = obj->nb[1] * obj->nb[2];
+    const uint32_t n = (obj->own_end - obj->own_begin) * plane;
+    const DevChunk* own_chunks = obj->d_chunks + (size_t)(obj->own_begin - obj->first_i) * plane;
+    if (n == 0) return IVX_OK;
+    if (!chunks || chunk_capacity < n) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u chunk descriptors", n);
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t* flag = tmp.get<uint32_t>(n);
+    uint32_t* ord = tmp.get<uint32_t>(n);
+    if (!flag || !ord) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "download: out of device memory");
+    KL(ctx, launch_nonuniform_flags(own_chunks, n, flag, st));
+    KL(ctx, launch_exclusive_scan(flag, ord, n, ctx->d_scratch + 28, st));
+    uint32_t nnu;
+    if (int rc = read_words(ctx, ctx->d_scratch + 28, 1, &nnu)) return rc;
+    if (voxels && voxel_capacity < (size_t)nnu * 4096) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %zu voxels", (size_t)nnu * 4096);
+    // the staging blocks belong to the object (freed with it): the copy stream reads them after this call returns
+    CU(ctx, cudaStreamSynchronize(ctx->copy_stream));  // an earlier transfer out of the old staging blocks
+    ctx->release(obj->d_stage_voxels);
+    ctx->release(obj->d_stage_chunks);
+    obj->d_stage_voxels = voxels ? static_cast<ivx_voxel*>(ctx->alloc(std::max<size_t>(1, (size_t)nnu) * 12288)) : nullptr;
+    obj->d_stage_chunks = static_cast<ivx_chunk_desc*>(ctx->alloc((size_t)n * sizeof(ivx_chunk_desc)));
+    if ((voxels && !obj->d_stage_voxels) || !obj->d_stage_chunks) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "download: out of device memory");
+    KL(ctx, launch_pack_voxels(own_chunks, n, ord, nullptr, 0, obj->d_voxels, obj->d_stage_voxels, obj->d_stage_chunks,
+                               persistent_grid(ctx, n, 8), st));
+    EventList packed;
+    CU(ctx, packed.create(1));
+    CU(ctx, cudaEventRecord(packed[0], st));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, packed[0], 0));
+    CU(ctx, cudaMemcpyAsync(chunks, obj->d_stage_chunks, (size_t)n * sizeof(ivx_chunk_desc), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (voxels && nnu)
+        CU(ctx, cudaMemcpyAsync(voxels, obj->d_stage_voxels, (size_t)nnu * 12288, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (out_non_uniform_chunks) *out_non_uniform_chunks = nnu;
+    return IVX_OK;
+}
+
 void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     if (!ctx || !obj) return;
     cudaSetDevice(ctx->device);
@@ -1388,10 +1646,10 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     delete obj;
 }
 
-int ivx_object_mesh(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
-    if (!ctx || !obj || !out) return IVX_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+// ivx_object_mesh, optionally without the final synchronisation (comm.cu queues the gather behind the mesh kernels)
+int ivx_internal_mesh(ivx_ctx* ctx, ivx_object* obj, bool sync, uint32_t counts[4], ivx_mesh_info* out) {
     std::memset(out, 0, sizeof(*out));
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
     if (obj->n_chunks == 0) return IVX_OK;
     if (obj->derive_pending)
         IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "slab object: call ivx_object_slab_finalize before meshing");
@@ -1400,9 +1658,38 @@ int ivx_object_mesh(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
     if (!flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh: out of device memory");
     KL(ctx, launch_exposed_flags(obj->d_chunks, obj->n_chunks, obj->nb, obj->own_begin - obj->first_i,
                                  obj->own_end - obj->first_i, flag, ctx->stream));
-    if (int rc = mesh_impl(ctx, obj, flag, obj->mesh)) return rc;
+    // an object that has not been modified since its generation meshes exactly like the last object generated from
+    // the same plan (for a slab: given the same neighbours — the device's counts are checked against the plan)
+    GenPlan* gp = obj->plan_serial ? ctx->find_plan(obj->plan_serial) : nullptr;
+    uint32_t plan_counts[4];
+    const bool planned = gp && gp->mesh_valid;
+    if (planned) std::memcpy(plan_counts, gp->mesh_counts, sizeof(plan_counts));
+    int rc = mesh_impl(ctx, obj, flag, obj->mesh, planned ? plan_counts : nullptr, sync || !planned, counts);
+    if (rc != IVX_OK && planned && sync) {
+        // stale plan (a slab whose neighbours changed): once more, from the device's own counts
+        if ((gp = ctx->find_plan(obj->plan_serial))) gp->mesh_valid = false;
+        rc = mesh_impl(ctx, obj, flag, obj->mesh, nullptr, true, counts);
+    }
+    if (rc) return rc;
+    if (!planned && (gp = obj->plan_serial ? ctx->find_plan(obj->plan_serial) : nullptr)) {
+        gp->mesh_valid = true;
+        std::memcpy(gp->mesh_counts, counts, sizeof(uint32_t) * 4);
+    }
     fill_mesh_info(obj->mesh, out);
     return IVX_OK;
+}
+// after the caller's own stream synchronisation: a plan mismatch flagged by the queued checks
+int ivx_internal_take_plan_error(ivx_ctx* ctx, ivx_object* obj) {
+    const int rc = take_plan_error(ctx);
+    if (rc && obj) obj->plan_serial = 0;
+    return rc;
+}
+
+int ivx_object_mesh(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
+    if (!ctx || !obj || !out) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    uint32_t counts[4];
+    return ivx_internal_mesh(ctx, obj, true, counts, out);
 }
 
 int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* obj, float* positions, float* normals,
@@ -1714,6 +2001,7 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     KLP(ctx, 6, launch_absorb_apply(aa, persistent_grid(ctx, n_range, 4), st));
     obj->slots_used += w[0];
     obj->split_valid = false;  // the voxels changed: labels / roots downloaded from now on must come from a new resolve
+    obj->plan_serial = 0;      // ... and the object no longer is what its generation plan describes
     // The voxels are modified from here on. If the inertial update fails (an emptied voxel's type has no density) the
     // error is reported only after the boundary refresh, occupied ranges and stale-label marks below have run, so the
     // object the caller keeps is consistent.
@@ -2033,6 +2321,7 @@ int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* obj, ivx_ex
     KL(ctx, launch_extract_chunks(xa, persistent_grid(ctx, nE, 4), st));
     CU(ctx, cudaStreamSynchronize(st));  // the host staging vectors go out of scope below
     obj->split_valid = false;
+    obj->plan_serial = 0;
 
     // ---- the object the region left (extraction.rs:556-575) ----
     if (int rc = refresh_occupied_ranges(ctx, obj)) return rc;

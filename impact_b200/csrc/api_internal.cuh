@@ -23,8 +23,43 @@ struct PoolBlock {
     bool used;
 };
 
+// Everything generate_impl / mesh_impl read back from the device for one (program, voxel extent, type generator, plane
+// range): counts that size the next allocations and launches. They are a pure function of those inputs, so — like an
+// FFT plan — they are kept, and the next generation of the same object runs without a host round trip. A kernel
+// compares the device's own counters with the plan afterwards (plan_error word), so a wrong plan is an error, never a
+// wrong object.
+struct GenPlan {
+    uint64_t serial = 0;
+    uint64_t prog_uid = 0;
+    float voxel_extent = 0.0f;
+    ivx_type_generator types{};
+    uint32_t i_begin = 0, i_end = 0;
+    bool whole = false, streamed = false;
+    uint32_t n_active = 0, n_slots = 0, max_depth = 0, occ[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> part_active;  // streamed generation: active-chunk boundaries of the parts
+    // mesh of the object as generated (for a slab: after the halo exchange with the same neighbours)
+    bool mesh_valid = false;
+    uint32_t mesh_counts[4] = {0, 0, 0, 0};  // exposed chunks, vertices, indices, submeshes
+};
+
 struct ivx_ctx {
     int device = 0;
+    std::vector<GenPlan> plans;  // most recent last; at most MAX_PLANS
+    struct WorkPlan {            // ivx_program_plane_work results
+        uint64_t prog_uid = 0;
+        float voxel_extent = 0.0f;
+        ivx_type_generator types{};
+        std::vector<uint32_t> work;
+    };
+    std::vector<WorkPlan> work_plans;
+    uint64_t next_serial = 1;
+    static constexpr size_t MAX_PLANS = 32;
+    static constexpr uint32_t PLAN_ERROR_WORD = 63;  // h_pinned word set by k_check_plan on a mismatch
+    GenPlan* find_plan(uint64_t serial) {
+        for (auto& pl : plans)
+            if (pl.serial == serial) return &pl;
+        return nullptr;
+    }
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;  // device→host copies of streamed generation, beside the compute stream
@@ -88,6 +123,7 @@ struct ivx_ctx {
 };
 
 struct ivx_program {
+    uint64_t uid = 0;  // unique per built program (plans are keyed by it, not by the pointer)
     HostProgram host;
     ivx_node* d_nodes = nullptr;
     Instr* d_root = nullptr;     // the whole program as an instruction list
@@ -120,6 +156,7 @@ struct ivx_object {
     uint32_t occ_voxels[6] = {0, 0, 0, 0, 0, 0};  // lo xyz, hi xyz (exclusive)
     uint32_t n_void = 0, n_uniform = 0, n_non_uniform = 0;
     DeviceMesh mesh;
+    uint64_t plan_serial = 0;  // GenPlan this object was generated with; 0 once the object has been modified
     // slab protocol (multi-GPU): derived state is pending until the halo planes are imported
     bool derive_pending = false;
     uint32_t* d_slot_of = nullptr;       // slot reserved for each chunk (conversion target), 0xFFFFFFFF = none
@@ -209,5 +246,11 @@ int ivx_apply_removed_voxels(ivx_ctx* ctx, const ivx_object* obj, const AbsorbRa
                              const uint32_t* removed_info, const uint16_t* removed_cols, const InertialUpdate& upd);
 
 // api.cu
+#define IVX_HIDDEN __attribute__((visibility("hidden")))
+extern "C" {
+IVX_HIDDEN int ivx_internal_mesh(ivx_ctx* ctx, ivx_object* obj, bool sync, uint32_t counts[4], ivx_mesh_info* out);
+IVX_HIDDEN int ivx_internal_take_plan_error(ivx_ctx* ctx, ivx_object* obj);
+IVX_HIDDEN int ivx_internal_slab_finalize(ivx_ctx* ctx, ivx_object* obj, bool sync);
+}
 int ivx_read_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t n, uint32_t* out);
 uint32_t ivx_persistent_grid(ivx_ctx* ctx, uint32_t n_work, int blocks_per_sm);

@@ -168,6 +168,9 @@ struct MeshArgs {
     uint4* mq_entries;      // 3 x uint4 per quad
     uint32_t* mq_count;
     uint32_t mq_capacity;   // quads; beyond it the emit kernel finishes the quad in place
+    // capacity of the output buffers when they were sized from a plan instead of from this call's own counts
+    // (0 = sized exactly): a chunk that would not fit is skipped, the plan check reports the mismatch
+    uint32_t cap_vertices, cap_indices, cap_submeshes;
 };
 cudaError_t launch_mesh_materials(const uint4* entries, const uint32_t* count, uint32_t capacity,
                                   ivx_index_materials* index_materials, cudaStream_t st);

@@ -298,7 +298,11 @@ __global__ void __launch_bounds__(MESH_THREADS, 4) k_mesh(MeshArgs a) {
                               (float)cj * chunk_extent - 0.5f * extent, (float)ck * chunk_extent - 0.5f * extent);
         const uint32_t voff = EMIT ? a.vertex_offset[w] : 0u;
         const uint32_t ioff = EMIT ? a.index_offset[w] : 0u;
-        const bool skip_emit = EMIT && a.index_count[w] == 0u;  // empty mesh: nothing is appended (mesh.rs:319-321)
+        bool skip_emit = EMIT && a.index_count[w] == 0u;  // empty mesh: nothing is appended (mesh.rs:319-321)
+        if (EMIT && a.cap_indices != 0u && !skip_emit &&
+            (voff + a.vertex_count[w] > a.cap_vertices || ioff + a.index_count[w] > a.cap_indices ||
+             a.submesh_ord[w] >= a.cap_submeshes))
+            skip_emit = true;  // buffers sized from a stale plan: stay inside them, k_check_plan flags the call
 
         // ---- vertex pass: estimate_surface_nets_surface (surface_nets.rs:152-244) ----
         // 1) compact the surface cubes in cube order (i → j → k), which is the reference's vertex order:

@@ -360,6 +360,95 @@ def merged_mesh_to_numpy(merged: dict) -> dict:
     }
 
 
+# ---- the communicator of the C ABI (ivx_comm_*): peer-memory halo exchange and mesh gather ------------------------------
+class PeerComm:
+    """`ivx_comm`: every rank's window mapped on every rank; halo planes, quad-ownership bits and mesh parts are stored
+    straight into the consumer's memory over NVLink and awaited on the device (include/impact_voxel_cuda.h
+    "multi-GPU communicator over peer memory"). The process group is used ONCE, to exchange the 64-byte window handles."""
+
+    def __init__(self, ctx, rank: int, world: int, plane_chunks: int, mesh_capacity, gather_rank: int = 0, group=None,
+                 device=None, local_peers=None):
+        import ctypes as C
+        from . import _lib as L
+
+        self.ctx, self.rank, self.world, self.gather_rank = ctx, rank, world, gather_rank
+        cfg = L.CommConfig(rank, world, gather_rank, plane_chunks, int(mesh_capacity[0]), int(mesh_capacity[1]),
+                           int(mesh_capacity[2]))
+        self.h = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        ctx.check(ctx._lib.ivx_comm_create(ctx.h, C.byref(cfg), C.byref(self.h), handle))
+        self.handle = bytes(handle)
+        self._local = local_peers is not None
+        if local_peers is None:
+            self.connect(group, device)
+
+    def connect(self, group=None, device=None):
+        """Exchanges the window handles through the process group (any backend) and maps the peers' windows."""
+        import ctypes as C
+
+        mine = torch.tensor(list(self.handle), dtype=torch.uint8, device=device)
+        allh = torch.zeros(self.world * 64, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        buf = (C.c_ubyte * (64 * self.world))(*allh.cpu().tolist())
+        self.ctx.check(self.ctx._lib.ivx_comm_connect(self.ctx.h, self.h, buf))
+        dist.barrier(group=group)  # every rank has mapped every window before anybody stores into one
+
+    @staticmethod
+    def connect_local(comms):
+        """Ranks living in one process (one context each): plain pointers instead of CUDA IPC."""
+        import ctypes as C
+
+        arr = (C.c_void_p * len(comms))(*[c.h for c in comms])
+        for c in comms:
+            c.ctx.check(c.ctx._lib.ivx_comm_connect_local(c.ctx.h, c.h, arr))
+
+    def exchange_halos(self, obj, ranges) -> None:
+        """`ivx_object_exchange_halos` for this rank's slab of `ranges` (asynchronous on the context's stream)."""
+        import ctypes as C
+
+        lo, hi = slab_neighbours(ranges, self.rank)
+        self.ctx.check(self.ctx._lib.ivx_object_exchange_halos(self.ctx.h, self.h, obj.h, C.c_int(-1 if lo is None else lo),
+                                                               C.c_int(-1 if hi is None else hi)))
+
+    def mesh_gather(self, obj):
+        """`ivx_object_mesh_gather` → (this slab's `VoxelObjectMesh`, merged mesh as numpy-like device views on the gather
+        rank / None elsewhere). Synchronises the context's stream."""
+        import ctypes as C
+        from . import _lib as L
+        from .voxel import VoxelObjectMesh
+
+        info, merged = L.MeshInfo(), L.GatheredMesh()
+        self.ctx.check(self.ctx._lib.ivx_object_mesh_gather(self.ctx.h, self.h, obj.h, C.byref(info), C.byref(merged)))
+        local = VoxelObjectMesh(obj, info)
+        if self.rank != self.gather_rank:
+            return local, None
+        return local, merged
+
+    @staticmethod
+    def merged_to_torch(merged, device) -> dict:
+        """The `ivx_gathered_mesh` of the gather rank as torch tensors over the window (no copy)."""
+        nv, ni, ns = int(merged.n_vertices), int(merged.n_indices), int(merged.n_submeshes)
+
+        def view(ptr, shape, typestr, dtype):
+            if int(np.prod(shape)) == 0 or not ptr:
+                return torch.empty(shape, dtype=dtype, device=device)
+            return torch.as_tensor(_DeviceArray(ptr, shape, typestr), device=device)
+
+        return {
+            "positions": view(merged.d_positions, (nv, 3), "<f4", torch.float32),
+            "normals": view(merged.d_normals, (nv, 3), "<f4", torch.float32),
+            "indices": view(merged.d_indices, (ni,), "<i4", torch.int32),
+            "index_materials": view(merged.d_index_materials, (ni, 8), "|u1", torch.uint8),
+            "submeshes": view(merged.d_submeshes, (ns, 13), "<i4", torch.int32),
+            "vertex_ranges": view(merged.d_vertex_ranges, (ns, 2), "<i4", torch.int32),
+        }
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx._lib.ivx_comm_destroy(self.ctx.h, self.h)
+        self.h = None
+
+
 # ---- several slabs held by ONE process (tests; a host that drives several objects on one device) ---------------
 def exchange_halos_single_process(objs, device=None) -> None:
     """The slab protocol between the x-slab objects `objs` (in slab order, all on one device): the halo messages are
@@ -371,14 +460,16 @@ def exchange_halos_single_process(objs, device=None) -> None:
             cap = src.halo_capacity()
             buf = torch.empty(cap, dtype=torch.uint8, device=device)
             n = src.halo_export(s_side, buf.data_ptr(), cap)
+            src.ctx.synchronize()  # the slabs may live on different contexts (streams)
             dst.halo_import(1 - s_side, buf.data_ptr(), n)
-            src.ctx.synchronize()
+            dst.ctx.synchronize()
     for o in live:
         o.slab_classify()
     for a, b in zip(live[:-1], live[1:]):  # exchange B: upper slab's lowest plane kinds → lower slab
         plane = b.plane_chunks()
         buf = torch.empty(plane, dtype=torch.uint8, device=device)
         b.halo_kinds_export(0, buf.data_ptr(), plane)
+        b.ctx.synchronize()
         a.halo_kinds_import(1, buf.data_ptr(), plane)
         a.ctx.synchronize()
     for o in live:

@@ -26,6 +26,7 @@ class Context:
 
     def __init__(self, device: int = 0, stream: int | None = None):
         self._lib = L.lib()
+        self.device = device
         cfg = L.Config(self._lib.ivx_abi_version(), device, C.c_void_p(stream) if stream else None, 0)
         h = C.c_void_p()
         rc = self._lib.ivx_create(C.byref(cfg), C.byref(h))

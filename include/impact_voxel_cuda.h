@@ -338,6 +338,11 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* object);
  * ivx_object_mesh replaces VoxelObjectMesh::create / recreate (mesh.rs:280-354):
  * for_each_exposed_chunk_with_sdf + compute_surface_nets_mesh + append. */
 int ivx_object_mesh(ivx_ctx* ctx, ivx_object* object, ivx_mesh_info* out);
+/* ivx_object_download with the transfer left running on the context's copy stream, so that meshing (or anything
+ * else queued afterwards) overlaps it; the host buffers — pinned memory, or the copies serialise — are complete after
+ * ivx_synchronize. *out_non_uniform_chunks = number of 4096-voxel blocks written. */
+int ivx_object_download_async(ivx_ctx* ctx, ivx_object* object, ivx_chunk_desc* chunks, size_t chunk_capacity,
+                              ivx_voxel* voxels, size_t voxel_capacity, uint64_t* out_non_uniform_chunks);
 int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* object, float* positions, float* normals,
                       ivx_index_materials* index_materials, uint32_t* indices,
                       ivx_chunk_submesh* submeshes, uint32_t* vertex_ranges);
@@ -360,6 +365,50 @@ int ivx_peer_open(ivx_ctx* ctx, const unsigned char handle[64], void** out_devic
 int ivx_peer_close(ivx_ctx* ctx, void* device_ptr);
 int ivx_mesh_push(ivx_ctx* ctx, const ivx_object* object, void* merged_base, const uint64_t field_offsets[6],
                   uint32_t vertex_base, uint32_t index_base, uint32_t submesh_base);
+
+/* ---- multi-GPU communicator over peer memory ---------------------------------
+ * The whole multi-GPU plane of the path behind the C ABI — a host needs no NCCL and no torch for it:
+ *
+ *   once:        ivx_comm_create on every rank → 64-byte handle; exchange the handles by any transport (MPI, a socket,
+ *                torch.distributed ...); ivx_comm_connect(all handles in rank order). Ranks living in one process use
+ *                ivx_comm_connect_local instead.
+ *   every step:  ivx_object_generate_slab(planes of this rank)
+ *                ivx_object_exchange_halos(comm, object, lower rank, upper rank)   [asynchronous on the ctx stream]
+ *                ivx_object_mesh_gather(comm, object, &local, &merged)            [synchronises the ctx stream]
+ *
+ * exchange_halos replaces the explicit slab protocol above (halo_export ... slab_finalize): boundary planes and the
+ * quad-ownership bits are stored straight into the neighbour's window over NVLink and published with a flag the
+ * neighbour's stream waits for on the device (V/object.rs:423-427 for the split, :1682-1704 and V/object/sdf.rs:410-428
+ * for what the neighbour plane is needed for, V/object/sdf/surface_nets.rs:252-261 for the bits). mesh_gather meshes
+ * the slab (ivx_object_mesh), publishes its sizes to all ranks, takes its place in the merged mesh from the sizes
+ * of the lower ranks (slab order = the reference's linear chunk order, V/mesh.rs:286-354) and stores its part, rebased,
+ * into the gather rank's window. On the gather rank `merged` describes the result: device pointers into the window,
+ * valid until the gather of the step after the next one. Every rank must make both calls once per step, in the same
+ * order. lower_rank / upper_rank: the ranks owning the planes just below / above this rank's (empty slabs skipped),
+ * -1 for none. The mesh capacities are those of the merged mesh of the whole job; IVX_ERR_CAPACITY (on the rank whose
+ * part does not fit, and on the gather rank) if a step exceeds them — create a larger communicator then. */
+typedef struct ivx_comm ivx_comm;
+typedef struct ivx_comm_config {
+    uint32_t rank, world, gather_rank;
+    uint32_t plane_chunks;  /* chunk_counts[1] * chunk_counts[2] of the objects exchanged */
+    uint64_t mesh_vertices, mesh_indices, mesh_submeshes;
+} ivx_comm_config;
+typedef struct ivx_gathered_mesh {
+    uint64_t n_vertices, n_indices, n_submeshes;
+    void* d_positions;        /* 3 x f32 per vertex */
+    void* d_normals;
+    void* d_indices;          /* u32 per index */
+    void* d_index_materials;  /* ivx_index_materials per index */
+    void* d_submeshes;        /* ivx_chunk_submesh */
+    void* d_vertex_ranges;    /* 2 x u32 per submesh */
+} ivx_gathered_mesh;
+int ivx_comm_create(ivx_ctx* ctx, const ivx_comm_config* config, ivx_comm** out_comm, unsigned char out_handle[64]);
+int ivx_comm_connect(ivx_ctx* ctx, ivx_comm* comm, const unsigned char* all_handles /* world x 64 bytes, rank order */);
+int ivx_comm_connect_local(ivx_ctx* ctx, ivx_comm* comm, ivx_comm* const* all_comms /* world pointers, rank order */);
+void ivx_comm_destroy(ivx_ctx* ctx, ivx_comm* comm);
+int ivx_object_exchange_halos(ivx_ctx* ctx, ivx_comm* comm, ivx_object* object, int lower_rank, int upper_rank);
+int ivx_object_mesh_gather(ivx_ctx* ctx, ivx_comm* comm, ivx_object* object, ivx_mesh_info* out_local,
+                           ivx_gathered_mesh* out_merged);
 
 /* ---- modification -------------------------------------------------------
  * ivx_object_absorb_sphere replaces apply_sphere_absorption

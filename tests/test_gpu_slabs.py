@@ -149,6 +149,22 @@ def _nccl_worker(rank, world, port, name, q):
                 oc, ov = obj.download()
                 H.assert_objects_equal(oc, ov, wc[: len(oc)], wv)
             pg.close()
+            # the communicator of the C ABI (ivx_comm_*): halo exchange + gather over peer memory, three steps
+            wm_counts = torch.tensor([merged["positions"].shape[0], merged["indices"].shape[0], merged["submeshes"].shape[0]]
+                                     if rank == 0 else [0, 0, 0], dtype=torch.int64, device=dev)
+            dist.broadcast(wm_counts, 0)
+            cc = obj.info()["chunk_counts"]
+            comm = D.PeerComm(c, rank, world, int(cc[1]) * int(cc[2]), [int(x) + 64 for x in wm_counts.tolist()], device=dev)
+            for _ in range(3):
+                o2 = VoxelObject.generate(vg, ranges[rank])
+                comm.exchange_halos(o2, ranges)
+                _, gm = comm.mesh_gather(o2)
+                if rank == 0:
+                    H.assert_meshes_equal(D.merged_mesh_to_numpy(D.PeerComm.merged_to_torch(gm, dev)), _MeshLike(wm))
+                    oc2, ov2 = o2.download()
+                    H.assert_objects_equal(oc2, ov2, wc[: len(oc2)], wv)
+                o2.free()
+            comm.close()
             stream.synchronize()
         dist.barrier()
         dist.destroy_process_group()
