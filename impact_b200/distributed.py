@@ -96,7 +96,15 @@ def exchange_halos_and_finalize(obj, ranges, rank: int, device, group=None) -> d
         ops.append(dist.P2POp(dist.irecv, in_buf[side], peer, group))
         stats["halo_bytes_sent"] += cap
         stats["halo_bytes_received"] += cap
+    # halo_export / halo_import / kinds / slab_classify only ENQUEUE on the context's stream (include/impact_voxel_cuda.h);
+    # NCCL runs on torch's current stream. Unless the two are the same stream, order them explicitly.
+    same_stream = device is not None and torch.device(device).type == "cuda" and \
+        getattr(obj.ctx, "stream_handle", None) == torch.cuda.current_stream().cuda_stream
+    fence_lib = (lambda: None) if same_stream or not hasattr(obj, "ctx") else obj.ctx.synchronize
+    fence_torch = (lambda: None) if same_stream or not torch.cuda.is_available() else (lambda: torch.cuda.current_stream().synchronize())
+    fence_lib()
     _p2p(ops, group)
+    fence_torch()
     for side, buf in in_buf.items():
         obj.halo_import(side, buf.data_ptr(), cap)
 
@@ -115,7 +123,9 @@ def exchange_halos_and_finalize(obj, ranges, rank: int, device, group=None) -> d
         k_in = torch.empty(plane, dtype=torch.uint8, device=device)
         ops.append(dist.P2POp(dist.irecv, k_in, hi, group))
         stats["halo_bytes_received"] += plane
+    fence_lib()
     _p2p(ops, group)
+    fence_torch()
     if k_in is not None:
         obj.halo_kinds_import(1, k_in.data_ptr(), plane)
     obj.slab_finalize()

@@ -16,11 +16,11 @@ asteroid is "an asteroid from the reference's graph", not provably the same inst
 produces. Everything downstream (generation, meshing) is checked bit-exactly against the oracle on the
 atomic graph this module emits.
 
-Implemented node kinds: Points, Spheres, Capsules, Boxes, Translation, Rotation, Scaling,
-StratifiedGridTransforms, SphereSurfaceTransforms, RayTranslationToSurface, StochasticSelection,
-SDFInstantiation, MultifractalNoiseSDFModifier, SDFUnion, SDFSubtraction, SDFIntersection, SDFGroupUnion
-(everything engine/benches/data/asteroid.vgen.ron and apps/voxel_generator/examples use except Similarity,
-ClosestTranslationToSurface, RotationToGradient and TransformApplication, which raise NotImplementedError).
+Implemented node kinds — all 21 of meta.rs: Points, Spheres, Capsules, Boxes, Translation, Rotation, Scaling, Similarity,
+StratifiedGridTransforms, SphereSurfaceTransforms, ClosestTranslationToSurface, RayTranslationToSurface,
+RotationToGradient, StochasticSelection, SDFInstantiation, TransformApplication, MultifractalNoiseSDFModifier,
+SDFUnion, SDFSubtraction, SDFIntersection, SDFGroupUnion. The three that probe an SDF (ClosestTranslationToSurface,
+RayTranslationToSurface, RotationToGradient) evaluate it on the device, all instances of the node in one batch.
 """
 from __future__ import annotations
 
@@ -912,7 +912,133 @@ class MetaCompiler:
             return ("sdf", queue[0] if queue else None)
         if t == "RayTranslationToSurface":
             return self._ray_translation(node, outputs)
-        raise NotImplementedError(f"meta node kind {t}")
+        if t == "Similarity":  # meta.rs:1402-1446
+            def make(p, ins):
+                scaling = max(f32(p["scale"]), np.finfo(f32).eps)
+                q = _tilt_turn_roll(p["tilt_angle"], p["turn_angle"], p["roll_angle"])
+                tr = v3(p["translation_x"] * S, p["translation_y"] * S, p["translation_z"] * S)
+                tf = Sim(tr, q, scaling)
+                return Instance(ins.shape, tf.mul(ins.transform) if node["composition"].tag == "Post" else ins.transform.mul(tf))
+            return self._per_instance(node, outputs, seed, ["scale", "tilt_angle", "turn_angle", "roll_angle", "translation_x",
+                                                            "translation_y", "translation_z"], make)
+        if t == "ClosestTranslationToSurface":
+            return self._closest_translation(node, outputs)
+        if t == "RotationToGradient":
+            return self._rotation_to_gradient(node, outputs)
+        if t == "TransformApplication":  # meta.rs:2012-2075
+            kind, val = outputs[node["sdf_id"]]
+            if kind == "instances":
+                raise ValueError("TransformApplication node expects SingleSDF or GroupSDF as input 1, got Instances")
+            sdf_ids = ([] if val is None else [val]) if kind == "sdf" else list(val)
+            k2, inst = outputs[node["instance_id"]]
+            if k2 != "instances":
+                raise ValueError(f"TransformApplication node expects Instances as input 2, got {k2}")
+            eps = np.finfo(f32).eps
+            ids = []
+            for sid in sdf_ids:
+                for ins in inst:
+                    tf, nid = ins.transform, sid
+                    if abs(tf.s - f32(1.0)) > eps:
+                        nid = g.scaling(nid, tf.s)
+                    if np.any(np.abs(tf.r - QID) > eps):
+                        nid = g.rotation(nid, list(tf.r))
+                    if np.any(np.abs(tf.t) > eps):
+                        nid = g.translation(nid, list(tf.t))
+                    ids.append(nid)
+            return ("group", ids)
+        raise ValueError(f"unknown meta node kind {t}")
+
+    # -- the two nodes that sample an SDF's value and gradient around the subject's centre (meta.rs:1620-1688, 1798-1862,
+    #    2411-2540, 2728-2769): 2x2x2 blocks, all instances in lock step through ivx_program_eval_blocks ------------------
+    def _surface_generator(self, sdf_id, what):
+        from .voxel import SDFGenerator
+
+        if self.ctx is None:
+            raise RuntimeError(f"{what} needs a device context for its SDF probes")
+        nodes = self.graph.nodes()
+        gen = SDFGenerator.from_graph(self.ctx, nodes, sdf_id)
+        sn = nodes[sdf_id]  # node_to_parent_transform of the sampled node (atomic.rs:1138-1148)
+        if sn["kind"] == 3:
+            surf = Sim(t=sn["p"][:3])
+        elif sn["kind"] == 4:
+            surf = Sim(r=sn["p"][:4])
+        elif sn["kind"] == 5:
+            surf = Sim(s=sn["p"][0])
+        else:
+            surf = Sim()
+        return gen, surf
+
+    @staticmethod
+    def _sample_with_gradient(gen, pos):
+        """sample_signed_distance_with_gradient for many positions → (centre values, gradients)."""
+        d = gen.compute_signed_distances_for_blocks_preserving_gradients((pos - f32(0.5)).astype(f32), 2)
+        total = np.zeros(len(pos), f32)
+        for q in range(8):  # iter().sum::<f32>() in sample order
+            total = (total + d[:, q]).astype(f32)
+        d000, d001, d010, d011, d100, d101, d110, d111 = [d[:, q] for q in range(8)]
+        grad = (f32(0.25) * np.stack([
+            (d100 + d110 + d101 + d111) - (d000 + d010 + d001 + d011),
+            (d010 + d110 + d011 + d111) - (d000 + d100 + d001 + d101),
+            (d001 + d101 + d011 + d111) - (d000 + d100 + d010 + d110)], 1)).astype(f32)
+        return (total * f32(0.125)).astype(f32), grad
+
+    def _closest_translation(self, node, outputs):
+        subjects = self._instances(outputs[node["subject_id"]], "ClosestTranslationToSurface")
+        kind, sdf_id = outputs[node["surface_sdf_id"]]
+        if kind != "sdf":
+            raise ValueError(f"ClosestTranslationToSurface node expects SingleSDF as input 1, got {kind}")
+        if sdf_id is None or not subjects:
+            return ("instances", list(subjects))
+        gen, surf = self._surface_generator(sdf_id, "ClosestTranslationToSurface")
+        n = len(subjects)
+        start = np.array([surf.inverse_transform_point(ins.transform.transform_point(v3(0, 0, 0))) for ins in subjects],
+                         f32).reshape(n, 3)
+        pos = start.copy()
+        alive = np.ones(n, bool)
+        active = np.ones(n, bool)
+        for _ in range(5):  # Newton-Raphson, max_iterations = 5, max_distance_from_surface = 0.1
+            idx = np.flatnonzero(active)
+            if len(idx) == 0:
+                break
+            sd, grad = self._sample_with_gradient(gen, pos[idx])
+            n2 = ((grad[:, 0] * grad[:, 0] + grad[:, 1] * grad[:, 1]) + grad[:, 2] * grad[:, 2]).astype(f32)
+            flat = np.abs(n2) <= f32(1e-8)
+            alive[idx[flat]] = False
+            active[idx[flat]] = False
+            ok = ~flat
+            step = ((-sd[ok] / n2[ok])[:, None] * grad[ok]).astype(f32)
+            pos[idx[ok]] = (pos[idx[ok]] + step).astype(f32)
+            active[idx[ok][np.abs(sd[ok]) <= f32(0.1)]] = False
+        res = []
+        for i, ins in enumerate(subjects):
+            if alive[i]:
+                tr = surf.transform_vector((pos[i] - start[i]).astype(f32))
+                res.append(Instance(ins.shape, ins.transform.translated(tr)))
+        return ("instances", res)
+
+    def _rotation_to_gradient(self, node, outputs):
+        subjects = self._instances(outputs[node["subject_id"]], "RotationToGradient")
+        kind, sdf_id = outputs[node["gradient_sdf_id"]]
+        if kind != "sdf":
+            raise ValueError(f"RotationToGradient node expects SingleSDF as input 1, got {kind}")
+        if sdf_id is None or not subjects:
+            return ("instances", list(subjects))
+        gen, surf = self._surface_generator(sdf_id, "RotationToGradient")
+        n = len(subjects)
+        centre = np.array([surf.inverse_transform_point(ins.transform.transform_point(v3(0, 0, 0))) for ins in subjects],
+                          f32).reshape(n, 3)
+        _, grad = self._sample_with_gradient(gen, centre)
+        res = []
+        tiny = f32(1e-8) * f32(1e-8)
+        for i, ins in enumerate(subjects):
+            y_axis = ins.transform.transform_vector(v3(0, 1, 0))
+            gp = surf.transform_vector(grad[i].astype(f32))
+            ny, ng = dot(y_axis, y_axis), dot(gp, gp)
+            if not (ny > tiny and ng > tiny):
+                continue
+            q = quat_from_rotation_arc((y_axis / f32(np.sqrt(ny))).astype(f32), (gp / f32(np.sqrt(ng))).astype(f32))
+            res.append(Instance(ins.shape, ins.transform.rotated(q)))
+        return ("instances", res)
 
     # -- RayTranslationToSurface (meta.rs:1690-1796, 2534-2748), all instances in lock step ------------------
     def _ray_translation(self, node, outputs):

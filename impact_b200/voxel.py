@@ -27,6 +27,7 @@ class Context:
     def __init__(self, device: int = 0, stream: int | None = None):
         self._lib = L.lib()
         self.device = device
+        self.stream_handle = stream  # the caller's stream the library works on (None: a stream of its own)
         cfg = L.Config(self._lib.ivx_abi_version(), device, C.c_void_p(stream) if stream else None, 0)
         h = C.c_void_p()
         rc = self._lib.ivx_create(C.byref(cfg), C.byref(h))

@@ -301,7 +301,13 @@ int ivx_object_from_generated_chunks(ivx_ctx* ctx, float voxel_extent, const uin
  * bit per chunk that the quad-ownership rule of Surface Nets reads from the +x
  * neighbour chunk (object/sdf/surface_nets.rs:252-261). Buffers are DEVICE
  * pointers (send them with NCCL or a peer copy); their layout is private to
- * this library version. side: 0 = lower chunk-i, 1 = higher. */
+ * this library version. side: 0 = lower chunk-i, 1 = higher.
+ * ASYNCHRONOUS: halo_export, halo_import, halo_kinds_export, halo_kinds_import,
+ * slab_classify and ivx_mesh_push only enqueue work on the context's stream and
+ * return; order them against the transport yourself (run the transport on the
+ * same stream — ivx_config.stream — or call ivx_synchronize before sending and
+ * synchronise the transport's stream before importing). slab_finalize
+ * synchronises. The communicator below (ivx_comm_*) needs none of this. */
 int ivx_object_generate_slab(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
                              const ivx_type_generator* type_generator, uint32_t chunk_i_begin,
                              uint32_t chunk_i_end, ivx_object** out_object);

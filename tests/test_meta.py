@@ -190,3 +190,137 @@ def test_committed_bench_graphs_equal_a_fresh_compile(ctx):
     fresh = M.asteroid_graph_scaled(112, 128, 0, ctx=ctx, use_cache=False)
     M._CACHE.clear()
     assert np.array_equal(cached.nodes(), fresh.nodes()) and cached.root_node_id == fresh.root_node_id
+
+
+# ---- Similarity, TransformApplication (host only); ClosestTranslationToSurface, RotationToGradient (device probes) ------
+def _spheres(count, radius, seed=0):
+    T = M.Tagged
+    return T("Spheres", {"radius": M._const(radius), "center_x": M._const(0.0), "center_y": M._const(0.0),
+                         "center_z": M._const(0.0), "count": count, "seed": seed, "sampling": T("OnlyOnce", None)})
+
+
+def test_similarity_composes_scale_rotation_translation_like_similarity3():
+    # meta.rs:1402-1446: Similarity3::from_parts(translation * scale_factor, tilt/turn/roll, scale), Post = T * instance
+    T = M.Tagged
+    sim = lambda comp: T("Similarity", {
+        "child_id": 1, "composition": T(comp, None), "scale": M._const(2.0), "tilt_angle": M._const(90.0),
+        "turn_angle": M._const(0.0), "roll_angle": M._const(0.0), "translation_x": M._const(5.0),
+        "translation_y": M._const(0.0), "translation_z": M._const(0.0), "seed": 3, "sampling": T("OnlyOnce", None)})
+    tr = T("Translation", {"child_id": 0, "composition": T("Post", None), "translation_x": M._const(0.0),
+                           "translation_y": M._const(10.0), "translation_z": M._const(0.0), "seed": 1,
+                           "sampling": T("OnlyOnce", None)})
+    out = {}
+    for comp in ("Post", "Pre"):
+        nodes = [_spheres(1, 4.0), tr, sim(comp), T("SDFInstantiation", {"child_id": 2}),
+                 T("SDFGroupUnion", {"child_id": 3, "smoothness": 0.0})]
+        g = M.MetaCompiler(nodes, 3.0, 0).build()
+        n = g.nodes()
+        # sphere(r * scale_factor) -> scaling(2) -> rotation -> translation
+        assert list(n["kind"]) == [0, 5, 4, 3] and n[0]["p"][0] == np.float32(12.0) and n[1]["p"][0] == np.float32(2.0)
+        out[comp] = n[3]["p"][:3].copy()
+    # Post: the earlier translation (0, 30, 0) is scaled by 2 and tilted 90° from +y to +x, then (15, 0, 0) is added
+    assert np.allclose(out["Post"], [75.0, 0.0, 0.0], atol=1e-4)
+    # Pre: the similarity acts inside the instance's frame, the instance's own translation stays (0, 30, 0) + (15, 0, 0)
+    assert np.allclose(out["Pre"], [15.0, 30.0, 0.0], atol=1e-4)
+
+
+def test_transform_application_stamps_every_sdf_onto_every_instance():
+    # meta.rs:2012-2075: (sdf, instance) pairs in that order; scaling, rotation, translation nodes only where needed
+    T = M.Tagged
+    pts = T("Points", {"count": 3})
+    grid = T("StratifiedGridTransforms", {"child_id": 0, "shape_x": M._const(3), "shape_y": M._const(1), "shape_z": M._const(1),
+                                          "cell_extent_x": M._const(10.0), "cell_extent_y": M._const(10.0),
+                                          "cell_extent_z": M._const(10.0), "jitter_fraction": M._const(0.0), "seed": 0})
+    nodes = [pts, grid, _spheres(1, 2.0), T("SDFInstantiation", {"child_id": 2}),
+             T("TransformApplication", {"sdf_id": 3, "instance_id": 1}), T("SDFGroupUnion", {"child_id": 4, "smoothness": 0.0})]
+    g = M.MetaCompiler(nodes, 1.0, 0).build()
+    n = g.nodes()
+    tr = n[n["kind"] == 3]
+    # the middle grid point sits at the origin: no translation node for it (abs_diff_ne), two for the outer ones
+    assert len(tr) == 2 and sorted(float(t["p"][0]) for t in tr) == [-10.0, 10.0]
+    assert (n["kind"] == 0).sum() == 1 and (n["kind"] == 7).sum() == 2  # one shared sphere, a union tree over 3 stamps
+    with pytest.raises(ValueError, match="got Instances"):
+        M.MetaCompiler([pts, pts, T("TransformApplication", {"sdf_id": 0, "instance_id": 1})], 1.0, 0).build()
+
+
+def _surface_scene(subject_kind_node):
+    """surface = sphere r = 20 (ids 0-2), subjects = 12 points on a sphere of radius 26 around it (ids 3-4)."""
+    T = M.Tagged
+    return [
+        _spheres(1, 20.0), T("SDFInstantiation", {"child_id": 0}), T("SDFGroupUnion", {"child_id": 1, "smoothness": 0.0}),
+        _spheres(12, 1.5, seed=5),
+        T("SphereSurfaceTransforms", {"child_id": 3, "radius": M._const(26.0), "jitter_fraction": M._const(0.5),
+                                      "rotation": T("Identity", None), "seed": 2}),
+        subject_kind_node,
+        T("SDFInstantiation", {"child_id": 5}), T("SDFGroupUnion", {"child_id": 6, "smoothness": 0.0}),
+        T("SDFUnion", {"child_1_id": 2, "child_2_id": 7, "smoothness": 0.0}),
+    ]
+
+
+@pytest.mark.gpu
+def test_closest_translation_lands_the_subjects_on_the_surface(ctx, oracle):
+    # meta.rs:1620-1688, 2411-2479: Newton-Raphson on 2x2x2 samples, at most 5 steps, stop within 0.1 of the surface.
+    # The batched device probes must give exactly what the reference's per-instance loop gives with the oracle's block
+    # evaluation, and the subjects must end up on the sphere.
+    T = M.Tagged
+    nodes = _surface_scene(T("ClosestTranslationToSurface", {"surface_sdf_id": 2, "subject_id": 4}))
+    g = M.MetaCompiler(nodes, 1.0, 0, ctx).build()
+    n = g.nodes()
+    centres = np.array([t["p"][:3] for t in n[n["kind"] == 3]], np.float32)
+    assert len(centres) == 12
+    r = np.linalg.norm(centres.astype(np.float64), axis=1)
+    assert np.all(np.abs(r - 20.0) < 0.15), r
+    # the reference's loop, one instance at a time, on the oracle
+    before = M.MetaCompiler(nodes[:5] + [T("SDFInstantiation", {"child_id": 4}), T("SDFGroupUnion", {"child_id": 5, "smoothness": 0.0})],
+                            1.0, 0).build().nodes()
+    starts = np.array([t["p"][:3] for t in before[before["kind"] == 3]], np.float32)
+    surface = M.MetaCompiler(nodes[:3], 1.0, 0).build()
+    ogen = oracle.Generator(surface.nodes(), surface.root_node_id)
+    f32 = np.float32
+    for start, got in zip(starts, centres):
+        pos = start.copy()
+        for _ in range(5):
+            d = ogen.eval_block_preserving_gradients((pos - f32(0.5)).astype(f32), 2)
+            total = f32(0.0)
+            for q in range(8):
+                total = f32(total + d[q])
+            sd = f32(total * f32(0.125))
+            d000, d001, d010, d011, d100, d101, d110, d111 = [f32(x) for x in d]
+            grad = (f32(0.25) * np.array([(d100 + d110 + d101 + d111) - (d000 + d010 + d001 + d011),
+                                          (d010 + d110 + d011 + d111) - (d000 + d100 + d001 + d101),
+                                          (d001 + d101 + d011 + d111) - (d000 + d100 + d010 + d110)], f32)).astype(f32)
+            n2 = f32(f32(grad[0] * grad[0] + grad[1] * grad[1]) + grad[2] * grad[2])
+            pos = (pos + (f32(-sd / n2) * grad).astype(f32)).astype(f32)
+            if abs(sd) <= f32(0.1):
+                break
+        want = (start + (pos - start).astype(f32)).astype(f32)
+        assert H.f32_bits_equal(got, want).all(), (start, got, want)
+
+
+@pytest.mark.gpu
+def test_rotation_to_gradient_turns_the_y_axis_along_the_gradient(ctx):
+    # meta.rs:1798-1862, 2481-2540: the subject's +y ends up along the surface SDF's gradient at the subject's centre —
+    # for a sphere around the origin, radially outwards
+    T = M.Tagged
+    nodes = _surface_scene(T("RotationToGradient", {"gradient_sdf_id": 2, "subject_id": 4}))
+    # capsules instead of spheres so that the rotation is visible in the atomic graph
+    nodes[3] = T("Capsules", {"segment_length": M._const(4.0), "radius": M._const(1.0), "center_x": M._const(0.0),
+                              "center_y": M._const(0.0), "center_z": M._const(0.0), "count": 12, "seed": 5,
+                              "sampling": T("OnlyOnce", None)})
+    g = M.MetaCompiler(nodes, 1.0, 0, ctx).build()
+    n = g.nodes()
+    rot = n[n["kind"] == 4]
+    tra = n[n["kind"] == 3]
+    # where the subjects stood before the node
+    before = M.MetaCompiler(nodes[:5] + [T("SDFInstantiation", {"child_id": 4}), T("SDFGroupUnion", {"child_id": 5, "smoothness": 0.0})],
+                            1.0, 0).build().nodes()
+    t0 = np.array([t["p"][:3] for t in before[before["kind"] == 3]], np.float64)
+    assert len(rot) == 12 and len(tra) == 12 and len(t0) == 12
+    for q, t, start in zip(rot, tra, t0):
+        qq = q["p"][:4].astype(np.float32)
+        y = M.quat_rotate(qq, M.v3(0, 1, 0)).astype(np.float64)
+        radial = start / np.linalg.norm(start)  # gradient of a sphere's SDF at the subject's centre
+        assert np.dot(y, radial) > 0.999, (y, radial)
+        # Similarity3::rotated applies the rotation after the transform: the translation turns with it (similarity.rs:138-144)
+        moved = M.quat_rotate(qq, start.astype(np.float32)).astype(np.float64)
+        assert np.allclose(t["p"][:3], moved, atol=1e-3), (t["p"][:3], moved)
