@@ -920,6 +920,10 @@ void fill_mesh_info(const DeviceMesh& m, ivx_mesh_info* out) {
     out->d_vertex_ranges = m.vertex_ranges;
 }
 
+}  // namespace
+extern "C" void fill_mesh_info_from(const DeviceMesh& m, ivx_mesh_info* out) { fill_mesh_info(m, out); }
+namespace {
+
 // grows the voxel pool so that `extra` more slots fit
 int ensure_slots(ivx_ctx* ctx, ivx_object* obj, uint32_t extra) {
     if (obj->slots_used + extra <= obj->slot_capacity) return IVX_OK;
@@ -1633,6 +1637,8 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     cudaStreamSynchronize(ctx->aux_stream);
     cudaStreamSynchronize(ctx->copy_stream);
     free_mesh(ctx, obj->mesh);
+    ivx_mesh_sync_free(obj->sync);
+    obj->sync = nullptr;
     ctx->release(obj->d_stage_voxels);
     ctx->release(obj->d_stage_chunks);
     ctx->release(obj->d_chunks);
@@ -1653,6 +1659,10 @@ int ivx_internal_mesh(ivx_ctx* ctx, ivx_object* obj, bool sync, uint32_t counts[
     if (obj->n_chunks == 0) return IVX_OK;
     if (obj->derive_pending)
         IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "slab object: call ivx_object_slab_finalize before meshing");
+    // VoxelObjectMesh::recreate clears the chunk submesh manager (mesh.rs:286-296)
+    ivx_mesh_sync_free(obj->sync);
+    obj->sync = nullptr;
+    obj->mesh_is_patch = false;
     Tmp tmp(ctx);
     uint32_t* flag = tmp.get<uint32_t>(obj->n_chunks);
     if (!flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh: out of device memory");
@@ -2402,6 +2412,10 @@ int ivx_object_remesh_dirty(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
     uint32_t* dflag = tmp.get<uint32_t>(n);
     if (!exposed || !dflag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "remesh: out of device memory");
     KL(ctx, launch_flag_dirty_exposed(obj->d_chunks, obj->d_dirty, n, exposed, dflag, ctx->stream));
+    // the patch takes the place of the object's mesh (ivx_object_mesh_sync is the call that keeps the mesh)
+    ivx_mesh_sync_free(obj->sync);
+    obj->sync = nullptr;
+    obj->mesh_is_patch = true;
     if (int rc = mesh_impl(ctx, obj, exposed, obj->mesh)) return rc;
     CU(ctx, cudaMemsetAsync(obj->d_dirty, 0, n, ctx->stream));  // mark_chunk_meshes_synchronized
     CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -131,8 +131,12 @@ struct ivx_program {
     uint32_t* d_root_meta = nullptr;  // [0] = offset (0), [1] = length
 };
 
+struct ivx_mesh_sync;  // mesh_sync.cu: the host-side ChunkSubmeshManager of a mesh that is kept in sync
+void ivx_mesh_sync_free(ivx_mesh_sync* s);
+
 struct DeviceMesh {
     uint32_t n_vertices = 0, n_indices = 0, n_submeshes = 0, n_work = 0;
+    uint32_t cap_vertices = 0, cap_indices = 0, cap_submeshes = 0;  // allocated elements once the mesh is kept in sync (0: exact)
     float* positions = nullptr;
     float* normals = nullptr;
     uint32_t* indices = nullptr;
@@ -156,6 +160,8 @@ struct ivx_object {
     uint32_t occ_voxels[6] = {0, 0, 0, 0, 0, 0};  // lo xyz, hi xyz (exclusive)
     uint32_t n_void = 0, n_uniform = 0, n_non_uniform = 0;
     DeviceMesh mesh;
+    ivx_mesh_sync* sync = nullptr;  // set by ivx_object_mesh_sync
+    bool mesh_is_patch = false;     // `mesh` holds the patch of ivx_object_remesh_dirty, not the object's mesh
     uint64_t plan_serial = 0;  // GenPlan this object was generated with; 0 once the object has been modified
     // slab protocol (multi-GPU): derived state is pending until the halo planes are imported
     bool derive_pending = false;
@@ -250,6 +256,7 @@ int ivx_apply_removed_voxels(ivx_ctx* ctx, const ivx_object* obj, const AbsorbRa
 extern "C" {
 IVX_HIDDEN int ivx_internal_mesh(ivx_ctx* ctx, ivx_object* obj, bool sync, uint32_t counts[4], ivx_mesh_info* out);
 IVX_HIDDEN int ivx_internal_take_plan_error(ivx_ctx* ctx, ivx_object* obj);
+IVX_HIDDEN void fill_mesh_info_from(const DeviceMesh& m, ivx_mesh_info* out);
 IVX_HIDDEN int ivx_internal_slab_finalize(ivx_ctx* ctx, ivx_object* obj, bool sync);
 }
 int ivx_read_words(ivx_ctx* ctx, const uint32_t* d_src, uint32_t n, uint32_t* out);

@@ -517,6 +517,27 @@ class VoxelObjectMesh:
         obj.ctx.check(obj.ctx._lib.ivx_object_remesh_dirty(obj.ctx.h, obj.h, C.byref(info)))
         return cls(obj, info)
 
+    @classmethod
+    def sync(cls, obj: VoxelObject) -> "VoxelObjectMesh":
+        """`VoxelObjectMesh::sync_with_voxel_object` (mesh.rs:360-456) on the mesh `create` left on the device: the
+        invalidated chunks are re-meshed into free ranges of the buffers (or appended), the submesh table follows."""
+        info = L.MeshInfo()
+        obj.ctx.check(obj.ctx._lib.ivx_object_mesh_sync(obj.ctx.h, obj.h, C.byref(info)))
+        return cls(obj, info)
+
+    def modifications(self):
+        """`mesh_modifications` → ((n, 4) updated ranges: vertex start, end, index start, end; chunks_were_removed)."""
+        ctx = self.obj.ctx
+        cnt, removed = C.c_uint64(), C.c_int()
+        ctx.check(ctx._lib.ivx_mesh_modifications(ctx.h, self.obj.h, None, C.c_size_t(0), C.byref(cnt), C.byref(removed)))
+        out = np.zeros((max(1, cnt.value), 4), np.uint32)
+        ctx.check(ctx._lib.ivx_mesh_modifications(ctx.h, self.obj.h, L.ptr(out), C.c_size_t(len(out)), C.byref(cnt),
+                                                  C.byref(removed)))
+        return out[: cnt.value], bool(removed.value)
+
+    def report_synchronized(self):
+        self.obj.ctx.check(self.obj.ctx._lib.ivx_mesh_report_synchronized(self.obj.ctx.h, self.obj.h))
+
     def download(self) -> dict:
         pos = np.zeros((self.n_vertices, 3), np.float32)
         nrm = np.zeros((self.n_vertices, 3), np.float32)

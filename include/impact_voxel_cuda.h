@@ -372,6 +372,22 @@ int ivx_peer_close(ivx_ctx* ctx, void* device_ptr);
 int ivx_mesh_push(ivx_ctx* ctx, const ivx_object* object, void* merged_base, const uint64_t field_offsets[6],
                   uint32_t vertex_base, uint32_t index_base, uint32_t submesh_base);
 
+/* ---- the mesh kept in sync with a modified object --------------------------
+ * ivx_object_mesh_sync replaces VoxelObjectMesh::sync_with_voxel_object (mesh.rs:360-456) including its
+ * ChunkSubmeshManager / RangeAllocator (mesh.rs:703-848): the mesh ivx_object_mesh created stays on the device; the
+ * invalidated chunks are re-meshed and each one is written into the smallest free vertex / index range that fits, else
+ * appended; chunks that are no longer exposed (or mesh to nothing) lose their submesh (swap-remove, like the reference's
+ * table). `out` describes the mesh afterwards: n_vertices / n_indices are the buffer LENGTHS (freed ranges included),
+ * the submesh table and the vertex ranges are the manager's, in its order. Invalidated chunks are visited in ascending
+ * linear chunk index (the reference iterates a HashSet: any order is the reference's). Clears the invalidation marks.
+ * ivx_mesh_modifications = VoxelObjectMesh::mesh_modifications (mesh.rs:105-118, 833-838): the vertex / index ranges
+ * written since the last report (4 words per record: vertex start, end, index start, end) — what a renderer uploads —
+ * and whether submeshes were removed; ivx_mesh_report_synchronized = report_gpu_resources_synchronized. */
+int ivx_object_mesh_sync(ivx_ctx* ctx, ivx_object* object, ivx_mesh_info* out);
+int ivx_mesh_modifications(ivx_ctx* ctx, const ivx_object* object, uint32_t* out_ranges, size_t capacity_records,
+                           uint64_t* out_count, int* out_chunks_were_removed);
+int ivx_mesh_report_synchronized(ivx_ctx* ctx, ivx_object* object);
+
 /* ---- multi-GPU communicator over peer memory ---------------------------------
  * The whole multi-GPU plane of the path behind the C ABI — a host needs no NCCL and no torch for it:
  *

@@ -299,6 +299,43 @@ void orc_mesh_copy(const void* mp, float* positions, float* normals, IndexMateri
 }
 void orc_mesh_free(void* mp) { delete (Mesh*)mp; }
 
+// RangeAllocator on its own (pinned by the reference's unit tests, range_allocator.rs:150-249)
+void* orc_range_allocator_create() { return new RangeAllocator(); }
+void orc_range_allocator_free_range(void* a, uint64_t start, uint64_t end) { ((RangeAllocator*)a)->free_range(start, end); }
+int orc_range_allocator_allocate(void* a, uint64_t len, uint64_t* start) {
+    size_t s = 0;
+    const bool ok = ((RangeAllocator*)a)->allocate_range(len, s);
+    *start = s;
+    return ok ? 1 : 0;
+}
+void orc_range_allocator_merge(void* a) { ((RangeAllocator*)a)->merge_consecutive_ranges(); }
+void orc_range_allocator_destroy(void* a) { delete (RangeAllocator*)a; }
+
+// ---- the mesh kept in sync with a modified object (VoxelObjectMesh::sync_with_voxel_object, mesh.rs:360-456) ----
+void* orc_synced_mesh_create(const void* op, int n_threads) {
+    SyncedMesh* sm = new SyncedMesh();
+    synced_mesh_create(*(const Object*)op, *sm, n_threads);
+    return sm;
+}
+void orc_synced_mesh_sync(void* smp, const void* op, const uint32_t* dirty, uint32_t n_dirty) {
+    synced_mesh_sync(*(const Object*)op, *(SyncedMesh*)smp, dirty, n_dirty);
+}
+const void* orc_synced_mesh_mesh(const void* smp) { return &((const SyncedMesh*)smp)->mesh; }
+// VoxelMeshModifications: → number of updated range records (4 words each) since the last report
+uint32_t orc_synced_mesh_modifications(const void* smp, uint32_t* out, uint32_t capacity_records, int* chunks_were_removed) {
+    const SyncedMesh* sm = (const SyncedMesh*)smp;
+    const uint32_t n = (uint32_t)(sm->updated.size() / 4);
+    if (out) std::memcpy(out, sm->updated.data(), (size_t)std::min(n, capacity_records) * 16);
+    if (chunks_were_removed) *chunks_were_removed = sm->chunks_were_removed ? 1 : 0;
+    return n;
+}
+void orc_synced_mesh_report_synchronized(void* smp) {
+    SyncedMesh* sm = (SyncedMesh*)smp;
+    sm->updated.clear();
+    sm->chunks_were_removed = false;
+}
+void orc_synced_mesh_free(void* smp) { delete (SyncedMesh*)smp; }
+
 // Mesh one chunk (one iteration of sync_with_voxel_object). Returns 0 if the
 // chunk is not exposed / produced no indices; else fills counts. Buffers sized
 // for the worst case: 4913 vertices, 3*6*4913 indices.

@@ -21,6 +21,8 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <map>
+#include <unordered_map>
 #include <vector>
 
 #include "oracle_math.hpp"
@@ -283,6 +285,28 @@ void mesh_object(const Object& obj, Mesh& mesh, int n_threads = 1);
 // false when the chunk is not exposed or yields an empty mesh (→ submesh removed).
 bool mesh_chunk(const Object& obj, uint32_t ci, uint32_t cj, uint32_t ck, ChunkMesh& cm,
                 uint8_t* chunk_flags);
+
+// --- the mesh kept in sync with a modified object (mesh.rs:360-456, 749-848) ---
+// RangeAllocator (impact_containers/src/range_allocator.rs): free ranges ordered by start
+struct RangeAllocator {
+    std::map<size_t, size_t> free_ranges;  // start → end
+    void free_range(size_t start, size_t end);
+    bool allocate_range(size_t required_len, size_t& start);  // smallest fitting range, the first of equals
+    void merge_consecutive_ranges();
+};
+// VoxelObjectMesh + ChunkSubmeshManager: `mesh.submeshes` / `mesh.vertex_ranges` are the manager's tables in its own
+// order (push order, swap-remove on removal); the buffers keep obsolete data in freed ranges.
+struct SyncedMesh {
+    Mesh mesh;
+    std::unordered_map<uint32_t, uint32_t> index_of_chunk;  // KeyIndexMapper: linear chunk index → table index
+    std::vector<uint32_t> chunk_at_index;
+    RangeAllocator free_vertices, free_indices;
+    std::vector<uint32_t> updated;  // ChunkSubmeshDataRanges since the last report: vertex start, end, index start, end
+    bool chunks_were_removed = false;
+};
+void synced_mesh_create(const Object& obj, SyncedMesh& sm, int n_threads = 1);
+// sync_with_voxel_object over `dirty` (linear chunk indices) in the given order — the reference iterates a HashSet
+void synced_mesh_sync(const Object& obj, SyncedMesh& sm, const uint32_t* dirty, size_t n_dirty);
 
 // --- inertial properties (object/inertia.rs) ----------------------------------
 // VoxelObjectInertialPropertyManager (inertia.rs:19-25): mass, moments (m x), moments of inertia, products of inertia,

@@ -396,6 +396,77 @@ class Mesh:
         self.h = None
 
 
+class SyncedMesh:
+    """`VoxelObjectMesh` kept in sync with a modified object (mesh.rs:360-456): `create` = recreate, `sync` =
+    `sync_with_voxel_object` over the given chunks in the given order. Arrays are read back after every call."""
+
+    def __init__(self, obj: "Object", n_threads: int = 1):
+        lib().orc_synced_mesh_create.restype = C.c_void_p
+        lib().orc_synced_mesh_mesh.restype = C.c_void_p
+        self.h = C.c_void_p(lib().orc_synced_mesh_create(obj.h, C.c_int(n_threads)))
+        self._read()
+
+    def _read(self):
+        m = C.c_void_p(lib().orc_synced_mesh_mesh(self.h))
+        nv, ni, ns = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().orc_mesh_sizes(m, C.byref(nv), C.byref(ni), C.byref(ns))
+        self.n_vertices, self.n_indices, self.n_submeshes = nv.value, ni.value, ns.value
+        self.positions = np.zeros((self.n_vertices, 3), np.float32)
+        self.normals = np.zeros((self.n_vertices, 3), np.float32)
+        self.index_materials = np.zeros(self.n_indices, INDEX_MATERIALS_DTYPE)
+        self.indices = np.zeros(self.n_indices, np.uint32)
+        self.submeshes = np.zeros(self.n_submeshes, SUBMESH_DTYPE)
+        self.vertex_ranges = np.zeros((self.n_submeshes, 2), np.uint32)
+        lib().orc_mesh_copy(m, _p(self.positions), _p(self.normals), _p(self.index_materials), _p(self.indices),
+                            _p(self.submeshes), _p(self.vertex_ranges))
+
+    def sync(self, obj: "Object", dirty_chunks) -> None:
+        d = np.ascontiguousarray(dirty_chunks, np.uint32)
+        lib().orc_synced_mesh_sync(self.h, obj.h, _p(d), C.c_uint32(len(d)))
+        self._read()
+
+    def modifications(self):
+        """→ (updated ranges: (n, 4) vertex start, end, index start, end; chunks_were_removed)"""
+        lib().orc_synced_mesh_modifications.restype = C.c_uint32
+        removed = C.c_int()
+        n = lib().orc_synced_mesh_modifications(self.h, None, C.c_uint32(0), C.byref(removed))
+        out = np.zeros((max(n, 1), 4), np.uint32)
+        lib().orc_synced_mesh_modifications(self.h, _p(out), C.c_uint32(n), C.byref(removed))
+        return out[:n], bool(removed.value)
+
+    def report_synchronized(self):
+        lib().orc_synced_mesh_report_synchronized(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_synced_mesh_free(self.h)
+            self.h = None
+
+
+class RangeAllocator:
+    """`RangeAllocator` (impact_containers/src/range_allocator.rs)."""
+
+    def __init__(self):
+        lib().orc_range_allocator_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().orc_range_allocator_create())
+
+    def free_range(self, start, end):
+        lib().orc_range_allocator_free_range(self.h, C.c_uint64(start), C.c_uint64(end))
+
+    def allocate_range(self, length):
+        s = C.c_uint64()
+        ok = lib().orc_range_allocator_allocate(self.h, C.c_uint64(length), C.byref(s))
+        return (s.value, s.value + length) if ok else None
+
+    def merge_consecutive_ranges(self):
+        lib().orc_range_allocator_merge(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_range_allocator_destroy(self.h)
+            self.h = None
+
+
 def vertex_materials(has_voxel, materials):
     has = np.asarray(has_voxel, np.uint8)
     mat = np.asarray(materials, np.uint8)

@@ -347,4 +347,148 @@ void mesh_object(const Object& obj, Mesh& mesh, int n_threads) {
     }
 }
 
+// ---- RangeAllocator (impact_containers/src/range_allocator.rs:24-113) ----
+void RangeAllocator::free_range(size_t start, size_t end) {
+    if (start < end) free_ranges.emplace(start, end);  // BTreeSet::insert keeps an element that is already there
+}
+bool RangeAllocator::allocate_range(size_t required_len, size_t& start) {
+    auto taken = free_ranges.end();
+    size_t best_len = SIZE_MAX;
+    for (auto it = free_ranges.begin(); it != free_ranges.end(); ++it) {
+        const size_t len = it->second - it->first;
+        if (len < best_len && len >= required_len) {
+            taken = it;
+            best_len = len;
+        }
+    }
+    if (taken == free_ranges.end()) return false;
+    const size_t s = taken->first, e = taken->second;
+    free_ranges.erase(taken);
+    if (s + required_len < e) free_ranges.emplace(s + required_len, e);
+    start = s;
+    return true;
+}
+void RangeAllocator::merge_consecutive_ranges() {
+    if (free_ranges.size() < 2) return;
+    std::map<size_t, size_t> merged;
+    auto it = free_ranges.begin();
+    size_t s = it->first, e = it->second;
+    for (++it; it != free_ranges.end(); ++it) {
+        if (it->first == e) {
+            e = it->second;
+        } else {
+            merged.emplace(s, e);
+            s = it->first;
+            e = it->second;
+        }
+    }
+    merged.emplace(s, e);
+    free_ranges.swap(merged);
+}
+
+// ---- ChunkSubmeshManager (mesh.rs:703-848) on top of Mesh ----
+void synced_mesh_create(const Object& obj, SyncedMesh& sm, int n_threads) {
+    sm = SyncedMesh{};
+    mesh_object(obj, sm.mesh, n_threads);
+    for (uint32_t i = 0; i < sm.mesh.submeshes.size(); ++i) {
+        const Submesh& s = sm.mesh.submeshes[i];
+        const uint32_t c = (s.chunk_indices[0] * obj.chunk_counts[1] + s.chunk_indices[1]) * obj.chunk_counts[2] + s.chunk_indices[2];
+        sm.index_of_chunk[c] = i;
+        sm.chunk_at_index.push_back(c);
+    }
+}
+
+static void remove_chunk_if_present(SyncedMesh& sm, uint32_t c) {
+    auto it = sm.index_of_chunk.find(c);
+    if (it == sm.index_of_chunk.end()) return;
+    const uint32_t idx = it->second;
+    sm.index_of_chunk.erase(it);
+    // KeyIndexMapper::try_swap_remove_key + Vec::swap_remove on both tables
+    const uint32_t last_key = sm.chunk_at_index.back();
+    sm.chunk_at_index.pop_back();
+    if (last_key != c) {
+        sm.chunk_at_index[idx] = last_key;
+        sm.index_of_chunk[last_key] = idx;
+    }
+    const uint32_t v0 = sm.mesh.vertex_ranges[2 * idx], v1 = sm.mesh.vertex_ranges[2 * idx + 1];
+    const Submesh removed = sm.mesh.submeshes[idx];
+    const size_t last = sm.mesh.submeshes.size() - 1;
+    sm.mesh.submeshes[idx] = sm.mesh.submeshes[last];
+    sm.mesh.submeshes.pop_back();
+    sm.mesh.vertex_ranges[2 * idx] = sm.mesh.vertex_ranges[2 * last];
+    sm.mesh.vertex_ranges[2 * idx + 1] = sm.mesh.vertex_ranges[2 * last + 1];
+    sm.mesh.vertex_ranges.resize(2 * last);
+    sm.free_vertices.free_range(v0, v1);
+    sm.free_indices.free_range(removed.index_offset, removed.index_offset + removed.index_count);
+    sm.chunks_were_removed = true;
+}
+
+void synced_mesh_sync(const Object& obj, SyncedMesh& sm, const uint32_t* dirty, size_t n_dirty) {
+    Mesh& m = sm.mesh;
+    ChunkMesh cm;
+    for (size_t q = 0; q < n_dirty; ++q) {
+        const uint32_t c = dirty[q];
+        const uint32_t ci = c / (obj.chunk_counts[2] * obj.chunk_counts[1]), cj = (c / obj.chunk_counts[2]) % obj.chunk_counts[1],
+                       ck = c % obj.chunk_counts[2];
+        uint8_t flags = 0;
+        // not exposed any more, or exposed with an empty mesh: the submesh goes (mesh.rs:379-383, 447-452)
+        if (!mesh_chunk(obj, ci, cj, ck, cm, &flags)) {
+            remove_chunk_if_present(sm, c);
+            continue;
+        }
+        const size_t total_v = m.positions.size() / 3, total_i = m.indices.size();
+        const size_t vcount = cm.positions.size() / 3, icount = cm.indices.size();
+        // write_chunk (mesh.rs:749-812)
+        auto found = sm.index_of_chunk.find(c);
+        if (found != sm.index_of_chunk.end()) {
+            const uint32_t idx = found->second;
+            sm.free_vertices.free_range(m.vertex_ranges[2 * idx], m.vertex_ranges[2 * idx + 1]);
+            sm.free_indices.free_range(m.submeshes[idx].index_offset, m.submeshes[idx].index_offset + m.submeshes[idx].index_count);
+        }
+        size_t v0 = total_v, i0 = total_i;
+        if (!sm.free_vertices.allocate_range(vcount, v0)) v0 = total_v;
+        if (!sm.free_indices.allocate_range(icount, i0)) i0 = total_i;
+        Submesh s{};
+        s.chunk_indices[0] = ci;
+        s.chunk_indices[1] = cj;
+        s.chunk_indices[2] = ck;
+        s.index_offset = (uint32_t)i0;
+        s.index_count = (uint32_t)icount;
+        obscuredness_table(flags, s.obscured);
+        if (found != sm.index_of_chunk.end()) {
+            m.submeshes[found->second] = s;
+            m.vertex_ranges[2 * found->second] = (uint32_t)v0;
+            m.vertex_ranges[2 * found->second + 1] = (uint32_t)(v0 + vcount);
+        } else {
+            sm.index_of_chunk[c] = (uint32_t)m.submeshes.size();
+            sm.chunk_at_index.push_back(c);
+            m.submeshes.push_back(s);
+            m.vertex_ranges.push_back((uint32_t)v0);
+            m.vertex_ranges.push_back((uint32_t)(v0 + vcount));
+        }
+        sm.updated.push_back((uint32_t)v0);
+        sm.updated.push_back((uint32_t)(v0 + vcount));
+        sm.updated.push_back((uint32_t)i0);
+        sm.updated.push_back((uint32_t)(i0 + icount));
+        // the data: appended when no free range fitted, else over the obsolete values (mesh.rs:399-445)
+        if (v0 == total_v) {
+            m.positions.insert(m.positions.end(), cm.positions.begin(), cm.positions.end());
+            m.normals.insert(m.normals.end(), cm.normals.begin(), cm.normals.end());
+        } else {
+            std::copy(cm.positions.begin(), cm.positions.end(), m.positions.begin() + 3 * v0);
+            std::copy(cm.normals.begin(), cm.normals.end(), m.normals.begin() + 3 * v0);
+        }
+        if (i0 == total_i) {
+            m.index_materials.insert(m.index_materials.end(), cm.index_materials.begin(), cm.index_materials.end());
+            for (uint16_t idx : cm.indices) m.indices.push_back((uint32_t)v0 + (uint32_t)idx);
+        } else {
+            std::copy(cm.index_materials.begin(), cm.index_materials.end(), m.index_materials.begin() + i0);
+            for (size_t t = 0; t < icount; ++t) m.indices[i0 + t] = (uint32_t)v0 + (uint32_t)cm.indices[t];
+        }
+    }
+    // perform_maintainance (mesh.rs:828-831)
+    sm.free_vertices.merge_consecutive_ranges();
+    sm.free_indices.merge_consecutive_ranges();
+}
+
 }  // namespace orc
