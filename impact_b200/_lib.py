@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_from_generated_chunks", "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",
     "ivx_objects_absorb_mutually", "ivx_intersection_voxel_ranges", "ivx_box_intersection_bounds",
     "ivx_object_surface_voxels_in_ranges", "ivx_object_surface_voxels_touching_sphere", "ivx_object_surface_voxels_touching_capsule",
-    "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane", "ivx_object_sphere_contacts",
+    "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane", "ivx_object_sphere_contacts", "ivx_object_plane_contacts", "ivx_object_capsule_contacts",
     "ivx_comm_create", "ivx_comm_connect", "ivx_comm_connect_local", "ivx_comm_destroy", "ivx_object_exchange_halos",
     "ivx_object_mesh_gather", "ivx_object_mesh_sync", "ivx_mesh_modifications", "ivx_mesh_report_synchronized",
 ]

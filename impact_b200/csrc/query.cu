@@ -29,10 +29,15 @@ __device__ __forceinline__ uint32_t surface_mask(uint4 fl, uint32_t k0, uint32_t
 // for_each_sphere_voxel_object_contact (collidable.rs:1097-1127): the sphere in the space `transform_to_object_space`
 // starts from, every surface voxel as a sphere of radius -signed_distance * extent around its centre carried back into
 // that space, determine_sphere_sphere_contact_geometry (impact_physics/src/collision/collidable/sphere.rs:105-136)
+// for_each_voxel_object_plane_contact (collidable.rs:1176-1209): corner voxels only, determine_sphere_plane_contact_geometry
+// (impact_physics sphere.rs:138-156); for_each_capsule_voxel_object_contact (collidable.rs:1257-1288):
+// determine_capsule_sphere_contact_geometry (impact_physics capsule.rs:212-270).
 struct SphereContactArgs {
     float q[4], t[3];   // transform_to_object_space
-    float center[3], radius;
+    float center[3], radius;  // sphere: centre, radius | plane: unit normal, displacement | capsule: segment start, radius
+    float seg[3];             // capsule: segment vector
     float extent;
+    int shape;                // 0 sphere, 1 plane, 2 capsule
 };
 __device__ __forceinline__ f3 rotate_by(float qx, float qy, float qz, float qw, f3 v) {
     const f3 b = mk3(qx, qy, qz);
@@ -47,6 +52,67 @@ __device__ __forceinline__ bool sphere_contact(const SphereContactArgs& a, uint3
     const f3 c_voxel = mk3(((float)i + 0.5f) * e, ((float)j + 0.5f) * e, ((float)k + 0.5f) * e);
     const f3 vc = rotate_by(-a.q[0], -a.q[1], -a.q[2], a.q[3], mk3(c_voxel.x - a.t[0], c_voxel.y - a.t[1], c_voxel.z - a.t[2]));
     const float vr = -sd_decode(code) * e;
+    if (a.shape == 1) {
+        const f3 n = mk3(a.center[0], a.center[1], a.center[2]);
+        const float sd = dot3(n, vc) - a.radius;  // Plane::compute_signed_distance
+        const float depth = vr - sd;
+        if (depth < 0.0f) return false;
+        if (out) {
+            out->indices[0] = i;
+            out->indices[1] = j;
+            out->indices[2] = k;
+            out->position[0] = vc.x - sd * n.x;
+            out->position[1] = vc.y - sd * n.y;
+            out->position[2] = vc.z - sd * n.z;
+            out->surface_normal[0] = n.x;
+            out->surface_normal[1] = n.y;
+            out->surface_normal[2] = n.z;
+            out->penetration_depth = depth;
+        }
+        return true;
+    }
+    if (a.shape == 2) {
+        const f3 s0 = mk3(a.center[0], a.center[1], a.center[2]), sv = mk3(a.seg[0], a.seg[1], a.seg[2]);
+        // parameter_of_closest_point_on_line_segment_to_point (impact_geometry line.rs:26-45)
+        const float len2 = dot3(sv, sv);
+        float tpar = 0.0f;
+        if (!(len2 <= 1e-8f)) {
+            const f3 sp = mk3(vc.x - s0.x, vc.y - s0.y, vc.z - s0.z);
+            tpar = fminf(fmaxf(dot3(sv, sp) / len2, 0.0f), 1.0f);
+        }
+        const f3 closest = mk3(s0.x + tpar * sv.x, s0.y + tpar * sv.y, s0.z + tpar * sv.z);
+        const f3 sdisp = mk3(vc.x - closest.x, vc.y - closest.y, vc.z - closest.z);
+        const float sd2 = dot3(sdisp, sdisp);
+        const float max_sd = vr + a.radius;
+        if (sd2 > max_sd * max_sd) return false;
+        if (out) {
+            const float sdist = sqrtf(sd2);
+            f3 cn;
+            float depth;
+            if (sdist > 1e-8f) {
+                cn = mk3(sdisp.x / sdist, sdisp.y / sdist, sdisp.z / sdist);
+                depth = fmaxf(0.0f, max_sd - sdist);
+            } else {
+                // the voxel's centre lies on the segment: any vector normal to it (glam Vec3A::any_orthogonal_vector)
+                const f3 o = fabsf(sv.x) > fabsf(sv.y) ? mk3(-sv.z, 0.0f, sv.x) : mk3(0.0f, sv.z, -sv.y);
+                const float on = norm3(o);
+                cn = on > 1e-8f ? mk3(o.x / on, o.y / on, o.z / on) : mk3(0.0f, 0.0f, 1.0f);
+                depth = fmaxf(0.0f, max_sd);
+            }
+            const f3 n = mk3(-cn.x, -cn.y, -cn.z);
+            out->indices[0] = i;
+            out->indices[1] = j;
+            out->indices[2] = k;
+            out->position[0] = vc.x + vr * n.x;
+            out->position[1] = vc.y + vr * n.y;
+            out->position[2] = vc.z + vr * n.z;
+            out->surface_normal[0] = n.x;
+            out->surface_normal[1] = n.y;
+            out->surface_normal[2] = n.z;
+            out->penetration_depth = depth;
+        }
+        return true;
+    }
     const f3 disp = mk3(a.center[0] - vc.x, a.center[1] - vc.y, a.center[2] - vc.z);
     const float d2 = dot3(disp, disp);
     const float max_d = a.radius + vr;
@@ -98,10 +164,13 @@ __global__ void __launch_bounds__(256) k_surface_voxels(const DevChunk* __restri
                 // keep the surface voxels whose sphere touches the query sphere
                 sdw = *reinterpret_cast<const uint4*>(slot + PLANE_SD + tid * 16);
                 const uint32_t wsd[4] = {sdw.x, sdw.y, sdw.z, sdw.w};
+                const uint32_t wfl[4] = {fl.x, fl.y, fl.z, fl.w};
                 for (uint32_t b = m; b; b &= b - 1) {
                     const uint32_t k = (uint32_t)__ffs(b) - 1u;
                     const int code = (int)(int8_t)(wsd[k >> 2] >> (8 * (k & 3)));
-                    if (!sphere_contact(ca, gi, gj, ck * 16u + k, code, nullptr)) m &= ~(1u << k);
+                    // against a plane only the corner voxels (at most three blocked faces) make contacts
+                    const bool corner = __popc((wfl[k >> 2] >> (8 * (k & 3))) & 0xFCu) < 4;
+                    if ((ca.shape == 1 && !corner) || !sphere_contact(ca, gi, gj, ck * 16u + k, code, nullptr)) m &= ~(1u << k);
                 }
             }
         }
@@ -215,57 +284,17 @@ static void ranges_touching_box(const ivx_object* obj, const float lo[3], const 
     }
 }
 
-int ivx_object_sphere_contacts(ivx_ctx* ctx, const ivx_object* obj, const ivx_isometry* transform_to_object_space,
-                               const float center[3], float radius, ivx_voxel_contact* out, size_t capacity, uint64_t* out_count) {
-    if (!ctx || !obj || !transform_to_object_space || !center || !out_count || (!out && capacity) || !(radius >= 0.0f))
-        return IVX_ERR_INVALID_ARGUMENT;
-    static_assert(sizeof(ivx_voxel_contact) == 40, "ten words");
-    cudaSetDevice(ctx->device);
-    *out_count = 0;
-    if (obj->first_i != 0 || obj->nb[0] != obj->chunk_counts[0])
-        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "contact queries on a slab-partitioned object are not supported");
-    SphereContactArgs ca{};
-    for (int q = 0; q < 4; ++q) ca.q[q] = transform_to_object_space->rotation[q];
-    for (int d = 0; d < 3; ++d) {
-        ca.t[d] = transform_to_object_space->translation[d];
-        ca.center[d] = center[d];
-    }
-    ca.radius = radius;
-    ca.extent = obj->voxel_extent;
-    // sphere.iso_transformed(transform).scaled(inverse_voxel_extent).compute_aabb() clipped to the occupied ranges
-    const float e = obj->voxel_extent, inv_e = 1.0f / e;
-    float c_obj[3];
-    {
-        const float bx = ca.q[0], by = ca.q[1], bz = ca.q[2], w = ca.q[3];
-        const float b2 = (bx * bx + by * by) + bz * bz, vb = (center[0] * bx + center[1] * by) + center[2] * bz;
-        const float s1 = w * w - b2, s2 = vb * 2.0f, s3 = w * 2.0f;
-        const float cx = by * center[2] - bz * center[1], cy = bz * center[0] - bx * center[2], cz = bx * center[1] - by * center[0];
-        c_obj[0] = ((center[0] * s1 + bx * s2) + cx * s3) + ca.t[0];
-        c_obj[1] = ((center[1] * s1 + by * s2) + cy * s3) + ca.t[1];
-        c_obj[2] = ((center[2] * s1 + bz * s2) + cz * s3) + ca.t[2];
-    }
-    const float rn = inv_e * radius;
-    float lo[3], hi[3];
-    for (int d = 0; d < 3; ++d) {
-        const float cn = inv_e * c_obj[d];
-        lo[d] = cn - rn;
-        hi[d] = cn + rn;
-    }
-    uint32_t ranges[6];
+// the two passes + scan over the chunks of `ranges` with the contact closure `ca`
+static int contacts_in_ranges(ivx_ctx* ctx, const ivx_object* obj, const ivx::SphereContactArgs& ca, const uint32_t ranges[6],
+                              ivx_voxel_contact* out, size_t capacity, uint64_t* out_count) {
+    using namespace ivx;
     AbsorbRange r{};
-    {
-        for (int d = 0; d < 3; ++d) {
-            const float fl = std::fmax(std::floor(lo[d]), 0.0f), ce = std::ceil(hi[d]);
-            const uint32_t s = fl >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fl;
-            const uint32_t en = !(ce > 0.0f) ? 0u : (ce >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)ce);
-            ranges[2 * d] = std::max(obj->occ_voxels[d], s);
-            ranges[2 * d + 1] = std::min(obj->occ_voxels[3 + d], en);
-            r.v0[d] = ranges[2 * d];
-            r.v1[d] = ranges[2 * d + 1];
-            if (r.v0[d] >= r.v1[d]) return IVX_OK;
-            r.c0[d] = r.v0[d] / 16;
-            r.c1[d] = (r.v1[d] + 15) / 16;
-        }
+    for (int d = 0; d < 3; ++d) {
+        r.v0[d] = ranges[2 * d];
+        r.v1[d] = ranges[2 * d + 1];
+        if (r.v0[d] >= r.v1[d]) return IVX_OK;
+        r.c0[d] = r.v0[d] / 16;
+        r.c1[d] = (r.v1[d] + 15) / 16;
     }
     const uint32_t n_range = (r.c1[0] - r.c0[0]) * (r.c1[1] - r.c0[1]) * (r.c1[2] - r.c0[2]);
     Tmp tmp(ctx);
@@ -293,6 +322,116 @@ int ivx_object_sphere_contacts(ivx_ctx* ctx, const ivx_object* obj, const ivx_is
     CU(ctx, cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(ivx_voxel_contact), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     return IVX_OK;
+}
+
+// glam Quat::mul_vec3a operation order, as in k_surface_voxels' rotate_by
+static void host_rotate(const float q[4], const float v[3], float out[3]) {
+    const float bx = q[0], by = q[1], bz = q[2], w = q[3];
+    const float b2 = (bx * bx + by * by) + bz * bz, vb = (v[0] * bx + v[1] * by) + v[2] * bz;
+    const float s1 = w * w - b2, s2 = vb * 2.0f, s3 = w * 2.0f;
+    const float cx = by * v[2] - bz * v[1], cy = bz * v[0] - bx * v[2], cz = bx * v[1] - by * v[0];
+    out[0] = (v[0] * s1 + bx * s2) + cx * s3;
+    out[1] = (v[1] * s1 + by * s2) + cy * s3;
+    out[2] = (v[2] * s1 + bz * s2) + cz * s3;
+}
+
+static int contact_args(ivx_ctx* ctx, const ivx_object* obj, const ivx_isometry* T, ivx::SphereContactArgs& ca) {
+    if (obj->first_i != 0 || obj->nb[0] != obj->chunk_counts[0])
+        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "contact queries on a slab-partitioned object are not supported");
+    for (int q = 0; q < 4; ++q) ca.q[q] = T->rotation[q];
+    for (int d = 0; d < 3; ++d) ca.t[d] = T->translation[d];
+    ca.extent = obj->voxel_extent;
+    return IVX_OK;
+}
+
+int ivx_object_sphere_contacts(ivx_ctx* ctx, const ivx_object* obj, const ivx_isometry* transform_to_object_space,
+                               const float center[3], float radius, ivx_voxel_contact* out, size_t capacity, uint64_t* out_count) {
+    if (!ctx || !obj || !transform_to_object_space || !center || !out_count || (!out && capacity) || !(radius >= 0.0f))
+        return IVX_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(ivx_voxel_contact) == 40, "ten words");
+    cudaSetDevice(ctx->device);
+    *out_count = 0;
+    ivx::SphereContactArgs ca{};
+    if (int rc = contact_args(ctx, obj, transform_to_object_space, ca)) return rc;
+    for (int d = 0; d < 3; ++d) ca.center[d] = center[d];
+    ca.radius = radius;
+    ca.shape = 0;
+    // sphere.iso_transformed(transform).scaled(inverse_voxel_extent).compute_aabb() clipped to the occupied ranges
+    const float inv_e = 1.0f / obj->voxel_extent;
+    float c_obj[3];
+    host_rotate(ca.q, center, c_obj);
+    const float rn = inv_e * radius;
+    float lo[3], hi[3];
+    for (int d = 0; d < 3; ++d) {
+        const float cn = inv_e * (c_obj[d] + ca.t[d]);
+        lo[d] = cn - rn;
+        hi[d] = cn + rn;
+    }
+    uint32_t ranges[6];
+    ranges_touching_box(obj, lo, hi, ranges);
+    return contacts_in_ranges(ctx, obj, ca, ranges, out, capacity, out_count);
+}
+
+int ivx_object_plane_contacts(ivx_ctx* ctx, const ivx_object* obj, const ivx_isometry* transform_to_object_space,
+                              const float unit_normal[3], float displacement, ivx_voxel_contact* out, size_t capacity,
+                              uint64_t* out_count) {
+    if (!ctx || !obj || !transform_to_object_space || !unit_normal || !out_count || (!out && capacity)) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    *out_count = 0;
+    ivx::SphereContactArgs ca{};
+    if (int rc = contact_args(ctx, obj, transform_to_object_space, ca)) return rc;
+    for (int d = 0; d < 3; ++d) ca.center[d] = unit_normal[d];
+    ca.radius = displacement;
+    ca.shape = 1;
+    // plane.iso_transformed(transform) (plane.rs:197-203): the point normal * displacement and the normal are carried
+    // over, the displacement is their dot product; then .scaled(inverse_voxel_extent) and the box of the occupied ranges
+    // projected onto the plane's negative halfspace (intersection.rs:30-40, 751-761)
+    const float p[3] = {unit_normal[0] * displacement, unit_normal[1] * displacement, unit_normal[2] * displacement};
+    float tp[3], tn[3];
+    host_rotate(ca.q, p, tp);
+    host_rotate(ca.q, unit_normal, tn);
+    for (int d = 0; d < 3; ++d) tp[d] = tp[d] + ca.t[d];
+    const float td = (tn[0] * tp[0] + tn[1] * tp[1]) + tn[2] * tp[2];
+    uint32_t occ[6], ranges[6];
+    for (int d = 0; d < 3; ++d) {
+        occ[2 * d] = obj->occ_voxels[d];
+        occ[2 * d + 1] = obj->occ_voxels[3 + d];
+    }
+    if (int rc = ivx_voxel_ranges_within_plane(occ, tn, td * (1.0f / obj->voxel_extent), ranges)) return rc;
+    return contacts_in_ranges(ctx, obj, ca, ranges, out, capacity, out_count);
+}
+
+int ivx_object_capsule_contacts(ivx_ctx* ctx, const ivx_object* obj, const ivx_isometry* transform_to_object_space,
+                                const float segment_start[3], const float segment_vector[3], float radius,
+                                ivx_voxel_contact* out, size_t capacity, uint64_t* out_count) {
+    if (!ctx || !obj || !transform_to_object_space || !segment_start || !segment_vector || !out_count || (!out && capacity) ||
+        !(radius >= 0.0f))
+        return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    *out_count = 0;
+    ivx::SphereContactArgs ca{};
+    if (int rc = contact_args(ctx, obj, transform_to_object_space, ca)) return rc;
+    for (int d = 0; d < 3; ++d) {
+        ca.center[d] = segment_start[d];
+        ca.seg[d] = segment_vector[d];
+    }
+    ca.radius = radius;
+    ca.shape = 2;
+    // capsule.iso_transformed(transform) (capsule.rs:122-128) .scaled(inverse_voxel_extent) .compute_aabb() (:132-137)
+    const float inv_e = 1.0f / obj->voxel_extent;
+    float s0[3], sv[3];
+    host_rotate(ca.q, segment_start, s0);
+    host_rotate(ca.q, segment_vector, sv);
+    const float rn = inv_e * radius;
+    float lo[3], hi[3];
+    for (int d = 0; d < 3; ++d) {
+        const float a = inv_e * (s0[d] + ca.t[d]), v = inv_e * sv[d], b = a + v;
+        lo[d] = std::fmin(a - rn, b - rn);
+        hi[d] = std::fmax(a + rn, b + rn);
+    }
+    uint32_t ranges[6];
+    ranges_touching_box(obj, lo, hi, ranges);
+    return contacts_in_ranges(ctx, obj, ca, ranges, out, capacity, out_count);
 }
 
 int ivx_voxel_ranges_within_plane(const uint32_t occupied[6], const float unit_normal[3], float displacement, uint32_t out_ranges[6]) {

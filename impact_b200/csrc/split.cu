@@ -65,7 +65,12 @@ cudaError_t launch_mark_box(uint8_t* arr, const uint32_t nb[3], const uint32_t l
     return cudaGetLastError();
 }
 
-__device__ __forceinline__ uint32_t find_root_compress(uint16_t* par, uint32_t idx) {
+// `par` is accessed through a volatile pointer: during the union pass the lanes of a run walk and compress paths of the
+// same forest concurrently. Every racing store writes an ancestor of the slot's set (path compression) or the run's
+// root, so any interleaving leaves a valid forest with the same roots; volatile 16-bit accesses are single relaxed
+// memory operations (ld/st.volatile), which makes those races defined behaviour under the PTX memory model instead of
+// data races on plain stores.
+__device__ __forceinline__ uint32_t find_root_compress(volatile uint16_t* par, uint32_t idx) {
     uint32_t r = idx;
     while (par[r] != r) r = par[r];
     while (par[idx] != r) {
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
                                                       uint32_t* __restrict__ error_flag) {
     __shared__ __align__(16) uint8_t s_flags[4096];
     __shared__ __align__(16) uint8_t s_lab[4096];
-    __shared__ uint16_t s_par[4096];
+    __shared__ volatile uint16_t s_par[4096];
     __shared__ uint32_t s_counts[2];
     const int lane = threadIdx.x;
     for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {

@@ -347,6 +347,21 @@ class VoxelObject:
         return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_sphere_contacts(
             self.ctx.h, self.h, L.ptr(iso), L.ptr(ctr), C.c_float(radius), o, c, n), L.CONTACT_DTYPE)
 
+    def plane_contacts(self, rotation_xyzw, translation, unit_normal, displacement: float) -> np.ndarray:
+        """`for_each_voxel_object_plane_contact` (collidable.rs:1176-1209): contacts of the corner voxels with the plane
+        { x : unit_normal . x = displacement } given in the space `transform_to_object_space` starts from."""
+        iso = np.concatenate([np.asarray(rotation_xyzw, np.float32), np.asarray(translation, np.float32)]).astype(np.float32)
+        nrm = np.asarray(unit_normal, np.float32)
+        return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_plane_contacts(
+            self.ctx.h, self.h, L.ptr(iso), L.ptr(nrm), C.c_float(displacement), o, c, n), L.CONTACT_DTYPE)
+
+    def capsule_contacts(self, rotation_xyzw, translation, segment_start, segment_vector, radius: float) -> np.ndarray:
+        """`for_each_capsule_voxel_object_contact` (collidable.rs:1257-1288)."""
+        iso = np.concatenate([np.asarray(rotation_xyzw, np.float32), np.asarray(translation, np.float32)]).astype(np.float32)
+        a, v = np.asarray(segment_start, np.float32), np.asarray(segment_vector, np.float32)
+        return self._surface_query(lambda o, c, n: self.ctx._lib.ivx_object_capsule_contacts(
+            self.ctx.h, self.h, L.ptr(iso), L.ptr(a), L.ptr(v), C.c_float(radius), o, c, n), L.CONTACT_DTYPE)
+
     def _surface_query(self, call, dtype=None) -> np.ndarray:
         n = C.c_uint64()
         cap = 1 << 14

@@ -596,6 +596,17 @@ typedef struct ivx_voxel_contact {
 int ivx_object_sphere_contacts(ivx_ctx* ctx, const ivx_object* object, const ivx_isometry* transform_to_object_space,
                                const float center[3], float radius, ivx_voxel_contact* out, size_t capacity,
                                uint64_t* out_count);
+/* for_each_voxel_object_plane_contact (collidable.rs:1176-1209): the plane { x : unit_normal . x = displacement } in the
+ * space transform_to_object_space starts from; only corner voxels make contacts (determine_sphere_plane_contact_geometry,
+ * impact_physics sphere.rs:138-156). Same records, same order as the closure's calls. */
+int ivx_object_plane_contacts(ivx_ctx* ctx, const ivx_object* object, const ivx_isometry* transform_to_object_space,
+                              const float unit_normal[3], float displacement, ivx_voxel_contact* out, size_t capacity,
+                              uint64_t* out_count);
+/* for_each_capsule_voxel_object_contact (collidable.rs:1257-1288, determine_capsule_sphere_contact_geometry, impact_physics
+ * capsule.rs:212-270): the capsule (segment start, segment vector, radius) in the space the transform starts from. */
+int ivx_object_capsule_contacts(ivx_ctx* ctx, const ivx_object* object, const ivx_isometry* transform_to_object_space,
+                                const float segment_start[3], const float segment_vector[3], float radius,
+                                ivx_voxel_contact* out, size_t capacity, uint64_t* out_count);
 int ivx_object_surface_voxels_touching_sphere(ivx_ctx* ctx, const ivx_object* object, const float center[3], float radius,
                                               ivx_surface_voxel* out, size_t capacity, uint64_t* out_count);
 int ivx_object_surface_voxels_touching_capsule(ivx_ctx* ctx, const ivx_object* object, const float segment_start[3],

@@ -473,6 +473,16 @@ uint64_t orc_plane_contacts(const void* op, const float q[4], const float t[3], 
     if (n) std::memcpy(out, found.data(), n * sizeof(VoxelContact));
     return found.size();
 }
+uint64_t orc_capsule_contacts(const void* op, const float q[4], const float t[3], const float seg_start[3], const float seg_vector[3],
+                              float radius, VoxelContact* out, uint64_t capacity) {
+    std::vector<VoxelContact> found;
+    capsule_voxel_object_contacts(*(const Object*)op, Isometry{Quat{q[0], q[1], q[2], q[3]}, v3(t[0], t[1], t[2])},
+                                  v3(seg_start[0], seg_start[1], seg_start[2]), v3(seg_vector[0], seg_vector[1], seg_vector[2]),
+                                  radius, found);
+    const size_t n = std::min<size_t>(found.size(), capacity);
+    if (n) std::memcpy(out, found.data(), n * sizeof(VoxelContact));
+    return found.size();
+}
 void orc_voxel_ranges_within_plane(const uint32_t occ[6], const float normal[3], float displacement, uint32_t out[6]) {
     uint32_t o[3][2], r[3][2];
     for (int d = 0; d < 3; ++d) {

@@ -558,4 +558,58 @@ void plane_voxel_object_contacts(const Object& obj, const Isometry& T, V3 normal
     }
 }
 
+// ---- capsule contacts (collidable.rs:1257-1288; impact_physics capsule.rs:212-270; impact_geometry line.rs:26-45) ------
+void capsule_voxel_object_contacts(const Object& obj, const Isometry& T, V3 seg_start, V3 seg_vector, float radius,
+                                   std::vector<VoxelContact>& out) {
+    out.clear();
+    const float e = obj.voxel_extent, inv_e = 1.0f / e;
+    // capsule.iso_transformed(transform_to_object_space) (capsule.rs:122-128), .scaled(inverse_voxel_extent) (:100-106),
+    // .compute_aabb() (:132-137) clipped to the occupied ranges (for_each_surface_voxel_maybe_intersecting_capsule)
+    const V3 s_obj = quat_rotate(T.q, seg_start) + T.t;
+    const V3 v_obj = quat_rotate(T.q, seg_vector);
+    const V3 sn = inv_e * s_obj, vn = inv_e * v_obj;
+    const V3 en = sn + vn;
+    const float rn = inv_e * radius;
+    const float lo[3] = {std::fmin(sn.x - rn, en.x - rn), std::fmin(sn.y - rn, en.y - rn), std::fmin(sn.z - rn, en.z - rn)};
+    const float hi[3] = {std::fmax(sn.x + rn, en.x + rn), std::fmax(sn.y + rn, en.y + rn), std::fmax(sn.z + rn, en.z + rn)};
+    uint32_t r[3][2];
+    ranges_touching(obj.occ_voxels, lo, hi, r);
+    std::vector<SurfaceVoxel> sv;
+    surface_voxels_in_ranges(obj, r, sv);
+    const Quat qc = quat_conj(T.q);
+    const float len2 = dot(seg_vector, seg_vector);
+    for (const SurfaceVoxel& v : sv) {
+        const V3 c_voxel = v3(((float)v.ijk[0] + 0.5f) * e, ((float)v.ijk[1] + 0.5f) * e, ((float)v.ijk[2] + 0.5f) * e);
+        const V3 vc = quat_rotate(qc, c_voxel - T.t);
+        const float vr = -sd_decode(v.voxel.sd) * e;
+        float param = 0.0f;
+        if (!(len2 <= 1e-8f)) {
+            const V3 sp = vc - seg_start;
+            param = std::fmin(std::fmax(dot(seg_vector, sp) / len2, 0.0f), 1.0f);
+        }
+        const V3 closest = seg_start + param * seg_vector;
+        const V3 sdisp = vc - closest;
+        const float sd2 = dot(sdisp, sdisp);
+        const float max_sd = vr + radius;
+        if (sd2 > max_sd * max_sd) continue;
+        const float sdist = std::sqrt(sd2);
+        V3 cn;
+        float depth;
+        if (sdist > 1e-8f) {
+            cn = v3(sdisp.x / sdist, sdisp.y / sdist, sdisp.z / sdist);
+            depth = std::fmax(0.0f, max_sd - sdist);
+        } else {
+            // glam Vec3A::any_orthogonal_vector (third party): cross with Y when |x| > |y|, else with X
+            const V3 o = std::fabs(seg_vector.x) > std::fabs(seg_vector.y) ? v3(-seg_vector.z, 0.0f, seg_vector.x)
+                                                                          : v3(0.0f, seg_vector.z, -seg_vector.y);
+            const float on = std::sqrt(dot(o, o));
+            cn = on > 1e-8f ? v3(o.x / on, o.y / on, o.z / on) : v3(0.0f, 0.0f, 1.0f);
+            depth = std::fmax(0.0f, max_sd);
+        }
+        const V3 n = v3(-cn.x, -cn.y, -cn.z);
+        const V3 pos = vc + vr * n;
+        out.push_back(VoxelContact{{v.ijk[0], v.ijk[1], v.ijk[2]}, {pos.x, pos.y, pos.z}, {n.x, n.y, n.z}, depth});
+    }
+}
+
 }  // namespace orc

@@ -377,6 +377,8 @@ void sphere_voxel_object_contacts(const Object& obj, const Isometry& transform_t
 // sphere.rs:138-158): corner voxels only; the plane { x : normal . x = displacement } in the space the transform starts from
 void plane_voxel_object_contacts(const Object& obj, const Isometry& transform_to_object_space, V3 unit_normal,
                                  float displacement, std::vector<VoxelContact>& out);
+void capsule_voxel_object_contacts(const Object& obj, const Isometry& T, V3 seg_start, V3 seg_vector, float radius,
+                                   std::vector<VoxelContact>& out);
 // voxel_ranges_within_plane (object/intersection.rs:751-761) with AxisAlignedBox::projected_onto_negative_halfspace
 // (impact_geometry/src/axis_aligned_box.rs:460-488); plane in normalized voxel space
 void voxel_ranges_within_plane(const uint32_t occupied[3][2], V3 unit_normal, float displacement, uint32_t out[3][2]);

@@ -338,6 +338,16 @@ class Object:
         lib().orc_plane_contacts(self.h, _p(q), _p(t), _p(n), C.c_float(displacement), _p(out), C.c_uint64(cnt))
         return out[:cnt]
 
+    def capsule_contacts(self, rotation_xyzw, translation, segment_start, segment_vector, radius: float) -> np.ndarray:
+        """`for_each_capsule_voxel_object_contact` (collidable.rs:1257-1288): the capsule in the space
+        `transform_to_object_space` starts from."""
+        q, t, a, v = (np.asarray(x, np.float32) for x in (rotation_xyzw, translation, segment_start, segment_vector))
+        lib().orc_capsule_contacts.restype = C.c_uint64
+        cnt = lib().orc_capsule_contacts(self.h, _p(q), _p(t), _p(a), _p(v), C.c_float(radius), None, C.c_uint64(0))
+        out = np.zeros(max(1, cnt), self.CONTACT_DTYPE)
+        lib().orc_capsule_contacts(self.h, _p(q), _p(t), _p(a), _p(v), C.c_float(radius), _p(out), C.c_uint64(cnt))
+        return out[:cnt]
+
     def extract_any_disconnected_region(self):
         """`VoxelObject::extract_any_disconnected_region` (extraction.rs:78-113): → (info, extracted Object or None).
         This object is modified in place (the region's voxels leave it)."""

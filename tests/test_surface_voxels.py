@@ -219,3 +219,98 @@ def test_oracle_plane_contacts_equal_a_float64_evaluation(oracle):
         assert abs(float(r["depth"]) - depth[n]) < 2e-4
         assert np.allclose(r["position"], centres_outer[n] - sd[n] * n32, atol=2e-4)
         assert np.array_equal(r["normal"], n32)
+
+
+def test_oracle_capsule_contacts_equal_a_float64_evaluation(oracle):
+    # for_each_capsule_voxel_object_contact (collidable.rs:1257-1288): every surface voxel's sphere against the capsule
+    g = H.asteroid_like_graph(12, 24.0)
+    extent = 0.5
+    o = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(g.nodes(), g.root_node_id), extent, H.GRADIENT4), 2)
+    shape = np.array(o.info()["chunk_counts"]) * 16
+    q = H.quat_from_axis_angle([0.3, 1.0, -0.2], 0.7)
+    t = np.float32([1.5, -2.0, 0.75])
+    qc = np.array([-q[0], -q[1], -q[2], q[3]])
+    # a capsule lying across the +x side of the object (given in the outer space)
+    a_obj = extent * (0.5 * shape + [0.36 * shape[0] + 0.3, -6.37, -3.41])
+    b_obj = extent * (0.5 * shape + [0.30 * shape[0] + 0.3, 7.21, 4.13])
+    a = H._rotate(qc, a_obj - t.astype(np.float64)).astype(np.float32)
+    b = H._rotate(qc, b_obj - t.astype(np.float64))
+    v = (b - a.astype(np.float64)).astype(np.float32)
+    radius = 2.5
+    got = o.capsule_contacts(q, t, a, v, radius)
+    assert len(got) > 30
+    # float64 over the voxels the reference's box admits
+    a64, v64 = a.astype(np.float64), v.astype(np.float64)
+    s_n = (H._rotate(q, a64) + t.astype(np.float64)) / extent
+    e_n = s_n + H._rotate(q, v64) / extent
+    occ = o.info()["occupied_voxel_ranges"].astype(np.float64)
+    lo = np.maximum(np.floor(np.maximum(np.minimum(s_n, e_n) - radius / extent, 0.0)), occ[:, 0])
+    hi = np.minimum(np.ceil(np.maximum(s_n, e_n) + radius / extent), occ[:, 1])
+    sv = o.surface_voxels_in_ranges(np.stack([lo, hi], 1).astype(np.uint32))
+    vc = np.array([H._rotate(qc, (ix + 0.5) * extent - t.astype(np.float64)) for ix in sv["indices"].astype(np.float64)])
+    vr = -(sv["sd"].astype(np.float64) * 0.02) * extent
+    par = np.clip(((vc - a64) @ v64) / (v64 @ v64), 0.0, 1.0)
+    closest = a64 + par[:, None] * v64
+    disp = vc - closest
+    dist = np.linalg.norm(disp, axis=1)
+    margin = np.abs(dist - (radius + vr))
+    hit = dist <= radius + vr
+    got_set = {tuple(int(x) for x in r) for r in got["indices"]}
+    for i in np.flatnonzero(margin > 1e-3):
+        assert (tuple(int(x) for x in sv["indices"][i]) in got_set) == bool(hit[i])
+    lookup = {tuple(int(x) for x in ix): n for n, ix in enumerate(sv["indices"])}
+    for r in got:
+        n = lookup[tuple(int(x) for x in r["indices"])]
+        nrm = -disp[n] / dist[n]
+        assert np.allclose(r["normal"], nrm, atol=2e-4) and np.allclose(r["position"], vc[n] + vr[n] * nrm, atol=2e-4)
+        assert abs(float(r["depth"]) - max(0.0, radius + vr[n] - dist[n])) < 2e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sphere", "asteroid_like", "random"])
+def test_gpu_plane_and_capsule_contacts_equal_the_oracle_bit_for_bit(ctx, oracle, name):
+    from impact_b200.voxel import SDFVoxelGenerator, VoxelObject
+
+    extent = 0.5
+    if name == "random":
+        vox, sp, grid = H.random_voxel_chunks((64, 48, 50), 6)
+        c = oracle.Object.from_generated_chunks(vox, sp, grid, extent)
+        g = VoxelObject.from_generated_chunks(ctx, extent, grid, vox, sp)
+    else:
+        graph = H.sphere_graph(40.0) if name == "sphere" else H.asteroid_like_graph(16, 36.0)
+        c = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(graph.nodes(), graph.root_node_id), extent, H.GRADIENT4), 4)
+        g = VoxelObject.generate(SDFVoxelGenerator(extent, ctx.build_generator(graph), H.GRADIENT4))
+    shape = np.array(c.info()["chunk_counts"]) * 16
+    rng = np.random.default_rng(3)
+    n_plane = n_capsule = 0
+    for case in range(6):
+        q = H.quat_from_axis_angle(rng.normal(size=3), float(rng.uniform(0, 3.0))) if case else np.float32([0, 0, 0, 1])
+        t = np.float32(rng.uniform(-8, 8, 3)) if case else np.float32([0, 0, 0])
+        qc = np.array([-q[0], -q[1], -q[2], q[3]])
+        # plane through a point inside the object, random orientation (outer space)
+        normal = rng.normal(size=3)
+        normal = (normal / np.linalg.norm(normal)).astype(np.float32)
+        p_obj = extent * (0.5 * shape + rng.uniform(-0.3, 0.3, 3) * shape)
+        p_outer = H._rotate(qc, p_obj - t.astype(np.float64))
+        displacement = float(np.float32(p_outer @ normal.astype(np.float64)))
+        got, want = g.plane_contacts(q, t, normal, displacement), c.plane_contacts(q, t, normal, displacement)
+        assert len(got) == len(want), ("plane", case, len(got), len(want))
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), ("plane", case)
+        n_plane += len(got)
+        # capsule between two points around the object's surface
+        a_obj = extent * (0.5 * shape + rng.uniform(-0.45, 0.45, 3) * shape)
+        b_obj = extent * (0.5 * shape + rng.uniform(-0.45, 0.45, 3) * shape)
+        a = H._rotate(qc, a_obj - t.astype(np.float64)).astype(np.float32)
+        v = (H._rotate(qc, b_obj - t.astype(np.float64)) - a.astype(np.float64)).astype(np.float32)
+        radius = float(rng.uniform(1.0, 5.0))
+        got, want = g.capsule_contacts(q, t, a, v, radius), c.capsule_contacts(q, t, a, v, radius)
+        assert len(got) == len(want), ("capsule", case, len(got), len(want))
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), ("capsule", case)
+        n_capsule += len(got)
+    # a degenerate capsule (zero segment) is a sphere's contact set
+    centre, r = H._rotate(np.float64([0, 0, 0, 1]), extent * 0.5 * shape + [extent * 0.4 * shape[0], 0.3, 0.2]).astype(np.float32), 3.0
+    gs = g.capsule_contacts([0, 0, 0, 1], [0, 0, 0], centre, [0, 0, 0], r)
+    cs = c.capsule_contacts([0, 0, 0, 1], [0, 0, 0], centre, [0, 0, 0], r)
+    assert np.array_equal(gs.view(np.uint8), cs.view(np.uint8))
+    assert {tuple(x) for x in gs["indices"]} == {tuple(x) for x in g.sphere_contacts([0, 0, 0, 1], [0, 0, 0], centre, r)["indices"]}
+    assert n_plane > 20 and n_capsule > 50
