@@ -403,6 +403,7 @@ def run_gpu(args):
             halo_stats["phase_ms_per_rank"] = {n: [round(float(t[i]), 3) for t in allp] for i, n in enumerate(names)}
         launches = ctx.kernel_launch_count - launches0
         prof = ctx.profile_get()
+        noise_evals = ctx.profile_counter(0)
         ctx.profile_enable(False)
 
         # ---- end to end through the host-buffer ABI ----
@@ -517,13 +518,20 @@ def run_gpu(args):
         step_s = ms_step * 1e-3
         fp32_pipe = None
         if types.kind == 1 and prof.get("types", (0.0, 0))[1]:
-            evals = int(oi["n_non_uniform"]) * 4096 * int(types.n_types)
+            # 4-D simplex evaluations counted ON THE DEVICE by k_types during the timed steps (ivx_profile_counter 0);
+            # f32 operations per evaluation from the kernel's own SASS (profiles/sass_r2_histogram.txt: per voxel PAIR and
+            # type 138 packed FADD2 / FFMA2 = 276 operations + 40 scalar FFMA / FMUL, i.e. 158 per evaluation)
+            OPS = 158
+            evals = noise_evals / args.steps
             t_types = prof["types"][0] / args.steps * 1e-3
             peak_ops = 148 * 128 * float(clocks.get("sm_mhz") or 1965.0) * 1e6
-            fp32_pipe = {"kernel": "k_types", "evaluations_per_step": evals, "f32_ops_per_evaluation": 163,
-                         "achieved_tops": evals * 163 / max(t_types, 1e-12) / 1e12, "peak_tops": peak_ops / 1e12,
-                         "frac": evals * 163 / max(t_types, 1e-12) / peak_ops,
-                         "note": "approximate: evaluations = this rank's NonUniform chunks x 4096 x voxel types"}
+            fp32_pipe = {"bound": "fp32", "kernel": "k_types", "evaluations_per_step": int(evals),
+                         "evaluations": "counted on the device (rank 0's slab)", "f32_ops_per_evaluation": OPS,
+                         "achieved": evals * OPS / max(t_types, 1e-12) / 1e12, "peak": peak_ops / 1e12, "unit": "Tflop/s (f32 add/mul/fma = 1)",
+                         "frac": evals * OPS / max(t_types, 1e-12) / peak_ops,
+                         "note": "peak = 148 SMs x 128 FP32 lanes x the SM clock sampled during the run; the packed-f32x2 "
+                                 "pipe sustains 2.3-2.5 cycles per FADD2 / FFMA2 with distinct operands and ~68 % of the nominal "
+                                 "rate on this kernel's instruction mix (profiles/microbench_r2_pipemix.txt)"}
         out = {
             "metric": METRIC, "value": total_voxels / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -558,9 +566,10 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": per_voxel, "voxels_per_launch": my_voxels,
                          "avg_launch_ms": dom_avg_s * 1e3,
+                         "traffic_source": "ncu --set full capture of this workload (profiles/dominant_kernel_traffic.json), per launch",
                          "note": "dense definition (SURVEY 8d): bytes the reference's layout moves per grid voxel; "
-                                 "the kernel is bound by the FP32 pipe / instruction issue on simplex noise (ncu: FMA pipe 65 %, issue slots "
-                                 "64 % busy, DRAM 1 %), see DESIGN.md §4 and profiles/"},
+                                 "the kernel is bound by the FP32 pipe on simplex noise (ncu: FMA pipe 65 %, issue slots "
+                                 "61 % busy, DRAM 1 %), see fp32_pipe, DESIGN.md §4 and profiles/"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
             # what actually bounds the dominant kernel: 163 f32 instructions-worth of arithmetic per 4-D simplex evaluation
             # (SASS count, FMA = 1; profiles/README.md) on every voxel of every NonUniform chunk and every voxel type,

@@ -22,7 +22,7 @@ STATUS_NAMES = {
 
 # every symbol include/impact_voxel_cuda.h declares
 EXPORTED_SYMBOLS = [
-    "ivx_create", "ivx_destroy", "ivx_last_error", "ivx_abi_version", "ivx_kernel_launch_count", "ivx_synchronize", "ivx_profile_enable", "ivx_profile_reset", "ivx_profile_get",
+    "ivx_create", "ivx_destroy", "ivx_last_error", "ivx_abi_version", "ivx_kernel_launch_count", "ivx_synchronize", "ivx_profile_enable", "ivx_profile_reset", "ivx_profile_get", "ivx_profile_counter",
     "ivx_program_build", "ivx_program_upload", "ivx_program_compile_host", "ivx_program_info_get", "ivx_program_nodes", "ivx_program_free",
     "ivx_program_eval_chunks", "ivx_program_eval_blocks", "ivx_object_generate", "ivx_object_generate_streamed", "ivx_object_generate_slab", "ivx_program_plane_work", "ivx_object_halo_capacity", "ivx_object_halo_export",
     "ivx_object_halo_import", "ivx_object_slab_classify", "ivx_object_halo_kinds_export", "ivx_object_halo_kinds_import",

@@ -494,6 +494,7 @@ int generate_impl(ivx_ctx* ctx, const ivx_program* prog, float voxel_extent, con
     ta.chunks = obj->d_chunks;
     ta.occ = counters + 2;
     ta.neg_zero = -0.0f;
+    ta.noise_evaluations = ctx->profiling ? ctx->d_counters64 : nullptr;
     const int types_bps = std::max(1, types_max_blocks_per_sm());
 
     // A streamed generation (ivx_object_generate_streamed) cuts the chunk planes into parts: each part is evaluated,
@@ -982,7 +983,9 @@ int ivx_create(const ivx_config* config, ivx_ctx** out_ctx) {
     }
     if (cudaHostAlloc(&ctx->h_pinned, 64 * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(&ctx->h_pinned_dev, ctx->h_pinned, 0) != cudaSuccess ||
-        cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counters64, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_counters64, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) {
         ivx_destroy(ctx);
         return IVX_ERR_OUT_OF_MEMORY;
     }
@@ -1010,6 +1013,7 @@ void ivx_destroy(ivx_ctx* ctx) {
     for (auto& b : ctx->pool) cudaFree(b.ptr);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_counters64) cudaFree(ctx->d_counters64);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1053,6 +1057,15 @@ int ivx_profile_reset(ivx_ctx* ctx) {
         ctx->prof_ms[i] = 0;
         ctx->prof_launches[i] = 0;
     }
+    CU(ctx, cudaMemsetAsync(ctx->d_counters64, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    return IVX_OK;
+}
+int ivx_profile_counter(ivx_ctx* ctx, uint32_t counter_id, uint64_t* out_value) {
+    if (!ctx || !out_value || counter_id >= 8) return IVX_ERR_INVALID_ARGUMENT;
+    unsigned long long v = 0;
+    CU(ctx, cudaMemcpyAsync(&v, ctx->d_counters64 + counter_id, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_value = v;
     return IVX_OK;
 }
 int ivx_profile_get(ivx_ctx* ctx, uint32_t kernel_id, double* out_total_ms, uint64_t* out_launches) {

@@ -79,6 +79,7 @@ struct ivx_ctx {
     uint32_t* h_pinned_dev = nullptr;  // the same words as the device sees them (mapped): counters are stored by a
                                        // kernel, not by the copy engine, which may be busy with a bulk transfer
     uint32_t* d_scratch = nullptr; // 64 words of device counters
+    unsigned long long* d_counters64 = nullptr;  // profiling counters: [0] 4-D simplex evaluations of k_types
 
     void* alloc(size_t bytes) {
         if (bytes == 0) bytes = 16;

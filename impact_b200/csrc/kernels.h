@@ -75,6 +75,7 @@ struct TypesArgs {
     DevChunk* chunks;
     uint32_t* occ;
     float neg_zero;           // -0.0f, deliberately a run-time value (see simplex4_tab2 in types.cu)
+    unsigned long long* noise_evaluations;  // profiling: 4-D simplex evaluations performed (null: not counted)
 };
 cudaError_t launch_types(const TypesArgs& a, uint32_t grid, cudaStream_t st);
 int types_max_blocks_per_sm();

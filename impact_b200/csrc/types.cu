@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(TYPES_THREADS, IVX_TYPES_CTAS) k_types(TypesAr
 #pragma unroll
             for (int k = 0; k < 16; ++k) types[k] = (uint8_t)a.gp.types.same_type;
         } else {
+            if (a.noise_evaluations && tid == 0) atomicAdd(a.noise_evaluations, 4096ull * n_types);
             // gradient_4d_offset(0, n, o.z, 16, o.y, 16, o.x, 16): x = type axis,
             // y / z / w = our k / j / i, each walked by repeated += 1.0
             const float ft = a.gp.types.voxel_type_frequency, fn = a.gp.types.noise_frequency;

@@ -72,6 +72,12 @@ class Context:
             out[name] = (ms.value, n.value)
         return out
 
+    def profile_counter(self, counter_id: int = 0) -> int:
+        """Device-side work counters while profiling is on: 0 = 4-D simplex evaluations of the voxel type kernel."""
+        v = C.c_uint64()
+        self.check(self._lib.ivx_profile_counter(self.h, C.c_uint32(counter_id), C.byref(v)))
+        return int(v.value)
+
     def build_generator(self, graph: SDFGraph) -> "SDFGenerator":
         """`SDFGraph::build_in` → `SDFGenerator::new_in` (atomic.rs:1031-1037, 228-493)."""
         return SDFGenerator.from_graph(self, graph.nodes(), graph.root_node_id)

@@ -216,6 +216,9 @@ int ivx_synchronize(ivx_ctx* ctx);
 int ivx_profile_enable(ivx_ctx* ctx, int enabled);
 int ivx_profile_reset(ivx_ctx* ctx);
 int ivx_profile_get(ivx_ctx* ctx, uint32_t kernel_id, double* out_total_ms, uint64_t* out_launches);
+/* work counters accumulated on the device while profiling is enabled (reset by ivx_profile_reset):
+ * 0 = 4-D simplex noise evaluations performed by the voxel type kernel (voxel_type.rs:125-168). */
+int ivx_profile_counter(ivx_ctx* ctx, uint32_t counter_id, uint64_t* out_value);
 
 /* ---- graph compile ------------------------------------------------------
  * ivx_program_build  replaces SDFGraph::build_in → SDFGenerator::new_in
