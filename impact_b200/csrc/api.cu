@@ -983,7 +983,7 @@ int ivx_create(const ivx_config* config, ivx_ctx** out_ctx) {
     }
     if (cudaHostAlloc(&ctx->h_pinned, 64 * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(&ctx->h_pinned_dev, ctx->h_pinned, 0) != cudaSuccess ||
-        cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_scratch, 128 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters64, 8 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_counters64, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) {
         ivx_destroy(ctx);
@@ -2000,9 +2000,20 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     }
     KL(ctx, launch_absorb_plan(obj->d_chunks, obj->nb, r, shape, need, n_range, st));
     KL(ctx, launch_exclusive_scan(need, ord, n_range, counters, st));
-    uint32_t w[12];
-    if (int rc = read_words(ctx, counters, 1, w)) return rc;
-    if (int rc = ensure_slots(ctx, obj, w[0])) return rc;
+    // Slots for Uniform chunks that become NonUniform. How many is known on the device only; as long as the pool holds
+    // the worst case (every chunk of the range here, every chunk of the refreshed box below) nothing has to be read
+    // back before the end of the call — the usual case, since the pool grows by half whenever it grows.
+    uint32_t w[16] = {0};
+    // (the cross-chunk pass below refreshes the upper faces of the chunks [start - 1, end): it can convert chunks up to `end`)
+    uint64_t n_box = 1;
+    for (int d = 0; d < 3; ++d) n_box *= std::min(obj->nb[d], r.c1[d] + 1u) - (r.c0[d] > 0 ? r.c0[d] - 1u : 0u);
+    const bool roomy = !upd && (uint64_t)obj->slots_used + n_range + n_box <= obj->slot_capacity;
+    if (!roomy) {
+        if (int rc = read_words(ctx, counters, 1, w)) return rc;
+        // (room for the worst case of a range like this one: the following calls then run without this read-back)
+        if (int rc = ensure_slots(ctx, obj, upd ? w[0] : (uint32_t)std::min<uint64_t>(n_range + n_box, 0x7FFFFFFFu))) return rc;
+    }
+    const uint32_t slots_at_entry = obj->slots_used;
     AbsorbArgs aa{};
     aa.chunks = obj->d_chunks;
     aa.nb = make_uint3(obj->nb[0], obj->nb[1], obj->nb[2]);
@@ -2022,7 +2033,7 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
         CU(ctx, cudaMemsetAsync(aa.removed_info, 0, (size_t)n_range * 8, st));  // chunks the kernel skips removed nothing
     }
     KLP(ctx, 6, launch_absorb_apply(aa, persistent_grid(ctx, n_range, 4), st));
-    obj->slots_used += w[0];
+    if (!roomy) obj->slots_used += w[0];
     obj->split_valid = false;  // the voxels changed: labels / roots downloaded from now on must come from a new resolve
     obj->plan_serial = 0;      // ... and the object no longer is what its generation plan describes
     // The voxels are modified from here on. If the inertial update fails (an emptied voxel's type has no density) the
@@ -2049,12 +2060,16 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, face_mask, convert_flag, 0, obj->nb[0], st));
     KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need2, st));
     KL(ctx, launch_exclusive_scan(need2, ord2, n, counters + 5, st));
-    if (int rc = read_words(ctx, counters, 12, w)) return rc;
-    if (int rc = ensure_slots(ctx, obj, w[5])) return rc;
-    KL(ctx, launch_assign_slots(obj->d_chunks, need2, ord2, obj->slots_used, n, slot_of, st));
-    obj->slots_used += w[5];
+    if (!roomy) {
+        if (int rc = read_words(ctx, counters, 12, w)) return rc;
+        if (int rc = ensure_slots(ctx, obj, w[5])) return rc;
+    }
+    // the conversions of the boundary pass take the slots after those of the absorption itself
+    KL(ctx, launch_assign_slots(obj->d_chunks, need2, ord2, obj->slots_used, roomy ? counters : nullptr, n, slot_of, st));
+    if (!roomy) obj->slots_used += w[5];
+    // (only the chunk planes of the refreshed box can have work: the others are not even looked at)
     KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n,
-                                  0, obj->nb[0], persistent_grid(ctx, n, 8), st));
+                                  b.c0[0], std::min(obj->nb[0], r.c1[0] + 1u), persistent_grid(ctx, n, 8), st));
     {
         // region labels of the touched chunks and of any neighbour converted to non-uniform are stale (split.cu)
         uint32_t lo3[3], hi3[3];
@@ -2064,9 +2079,14 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
         }
         KL(ctx, launch_mark_box(obj->d_label_stale, obj->nb, lo3, hi3, 1, st));
     }
+    // everything the host wants to know, in one read: slots handed out, statistics, invalidated chunks
+    CU(ctx, cudaMemsetAsync(counters + 12, 0, 4, st));
+    KL(ctx, launch_count_nonzero_u8(obj->d_dirty, n, counters + 12, st));
+    if (int rc = read_words(ctx, counters, 13, w)) return rc;
+    if (roomy) obj->slots_used = slots_at_entry + w[0] + w[5];
     if (w[4]) {
         // removed chunks → update_occupied_ranges (intersection.rs:387-389)
-        KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, counters + 6,
+        KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, counters + 6, ctx->d_scratch + 64,
                                        persistent_grid(ctx, n, 8), st));
         uint32_t o[6];
         if (int rc = read_words(ctx, counters + 6, 6, o)) return rc;
@@ -2076,15 +2096,12 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
             obj->occ_voxels[3 + d] = any ? o[3 + d] + 1u : 0u;
         }
     }
-    CU(ctx, cudaStreamSynchronize(st));
     if (out_stats) {
         out_stats->touched_chunks = w[1];
         out_stats->touched_voxels = w[2];
         out_stats->emptied_voxels = w[3];
         out_stats->removed_chunks = w[4];
-        uint32_t cnt = 0;
-        ivx_object_dirty_chunks(ctx, obj, nullptr, 0, &cnt);
-        out_stats->dirty_chunks = cnt;
+        out_stats->dirty_chunks = w[12];
     }
     if (upd_rc) IVX_FAIL(ctx, upd_rc, "%s", upd_err.c_str());
     return IVX_OK;
@@ -2115,10 +2132,11 @@ int refresh_boundaries(ivx_ctx* ctx, ivx_object* obj, const AbsorbRange* range) 
     uint32_t w;
     if (int rc = read_words(ctx, counters + 5, 1, &w)) return rc;
     if (int rc = ensure_slots(ctx, obj, w)) return rc;
-    KL(ctx, launch_assign_slots(obj->d_chunks, need, ord, obj->slots_used, n, slot_of, st));
+    KL(ctx, launch_assign_slots(obj->d_chunks, need, ord, obj->slots_used, nullptr, n, slot_of, st));
     obj->slots_used += w;
-    KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n, 0,
-                                  obj->nb[0], persistent_grid(ctx, n, 8), st));
+    KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n,
+                                  range ? range->c0[0] : 0u, range ? std::min(obj->nb[0], range->c1[0] + 1u) : obj->nb[0],
+                                  persistent_grid(ctx, n, 8), st));
     if (obj->d_label_stale) {
         // a neighbour converted to non-uniform has no labels yet
         uint32_t lo3[3] = {0, 0, 0}, hi3[3] = {obj->nb[0], obj->nb[1], obj->nb[2]};
@@ -2138,8 +2156,8 @@ int refresh_occupied_ranges(ivx_ctx* ctx, ivx_object* obj) {
     uint32_t* occ = ctx->d_scratch + 38;
     const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
     CU(ctx, cudaMemcpyAsync(occ, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, occ, persistent_grid(ctx, n, 8),
-                                   ctx->stream));
+    KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, occ, ctx->d_scratch + 64,
+                                   persistent_grid(ctx, n, 8), ctx->stream));
     uint32_t o[6];
     if (int rc = read_words(ctx, occ, 6, o)) return rc;
     const bool any = o[0] != 0xFFFFFFFFu;

@@ -233,10 +233,13 @@ cudaError_t launch_absorb_face_mask(const uint32_t nb[3], const AbsorbRange& b, 
                                     cudaStream_t st);
 cudaError_t launch_need_slot_for_convert(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t n, uint32_t* need,
                                          cudaStream_t st);
+cudaError_t launch_count_nonzero_u8(const uint8_t* a, uint32_t n, uint32_t* out, cudaStream_t st);
 cudaError_t launch_assign_slots(const DevChunk* chunks, const uint32_t* need, const uint32_t* ord, uint32_t first,
+                                const uint32_t* first_extra,
                                 uint32_t n, uint32_t* slot_of, cudaStream_t st);
 cudaError_t launch_occupied_ranges(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t first_i,
-                                   const unsigned char* voxels, uint32_t* occ, uint32_t grid, cudaStream_t st);
+                                   const unsigned char* voxels, uint32_t* occ, uint32_t* chunk_minmax_scratch, uint32_t grid,
+                                   cudaStream_t st);
 
 // ---- split.cu ------------------------------------------------------------------
 // sets arr[chunk] = value for the chunks of the box [lo, hi) (clamped to the grid); no-op when arr is null

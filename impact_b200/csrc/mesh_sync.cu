@@ -27,6 +27,7 @@ struct ivx_mesh_sync {
     std::vector<uint32_t> updated;  // ChunkSubmeshDataRanges: vertex start, end, index start, end
     bool chunks_were_removed = false;
     uint32_t n_vertices = 0, n_indices = 0;  // lengths of the buffers (holes included)
+    std::vector<uint32_t> touched_rows;      // rows written or moved by the current sync (for the device mirror)
 };
 
 namespace {
@@ -76,6 +77,7 @@ void drop_chunk(ivx_mesh_sync& s, uint32_t chunk) {
     release_range(s.free_vertices, s.vertex_ranges[2 * row], s.vertex_ranges[2 * row + 1]);
     release_range(s.free_indices, s.submeshes[row].index_offset, s.submeshes[row].index_offset + s.submeshes[row].index_count);
     if (row != last) {
+        s.touched_rows.push_back(row);
         s.chunk_of_row[row] = s.chunk_of_row[last];
         s.row_of_chunk[s.chunk_of_row[row]] = row;
         s.submeshes[row] = s.submeshes[last];
@@ -86,6 +88,18 @@ void drop_chunk(ivx_mesh_sync& s, uint32_t chunk) {
     s.submeshes.pop_back();
     s.vertex_ranges.resize(2 * (size_t)last);
     s.chunks_were_removed = true;
+}
+
+// rows of the manager's tables that changed → their place in the device mirror (15 words each: submesh + vertex range)
+__global__ void k_scatter_rows(const uint32_t* __restrict__ packed, uint32_t n_rows, ivx_chunk_submesh* __restrict__ submeshes,
+                               uint32_t* __restrict__ vertex_ranges) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = t / 16u, wi = t % 16u;
+    if (q >= n_rows) return;
+    const uint32_t* src = packed + (size_t)q * 16u;
+    const uint32_t row = src[0];
+    if (wi >= 1u && wi <= 13u) reinterpret_cast<uint32_t*>(&submeshes[row])[wi - 1u] = src[wi];
+    else if (wi >= 14u) vertex_ranges[2 * (size_t)row + (wi - 14u)] = src[wi];
 }
 
 template <typename T>
@@ -244,6 +258,7 @@ int ivx_object_mesh_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
         }
         s.vertex_ranges[2 * row] = v0;
         s.vertex_ranges[2 * row + 1] = v0 + vc;
+        s.touched_rows.push_back(row);
         s.updated.insert(s.updated.end(), {v0, v0 + vc, i0, i0 + ic});
         h_voff[wi] = v0;
         h_ioff[wi] = i0;
@@ -295,20 +310,48 @@ int ivx_object_mesh_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
     coalesce(s.free_vertices);
     coalesce(s.free_indices);
 
-    // ---- mirror of the tables on the device ----
+    // ---- mirror of the tables on the device: only the rows this sync wrote or moved ----
     const uint32_t rows = (uint32_t)s.submeshes.size();
     if (rows > m.cap_submeshes || !m.submeshes) {
         const uint32_t want = rows + rows / 4 + 16;
+        ivx_chunk_submesh* ns = static_cast<ivx_chunk_submesh*>(ctx->alloc((size_t)want * sizeof(ivx_chunk_submesh)));
+        uint32_t* nv = static_cast<uint32_t*>(ctx->alloc((size_t)want * 8));
+        if (!ns || !nv) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh sync: out of device memory");
+        const uint32_t keep = std::min(m.n_submeshes, rows);
+        if (m.submeshes && keep) {
+            CU(ctx, cudaMemcpyAsync(ns, m.submeshes, (size_t)keep * sizeof(ivx_chunk_submesh), cudaMemcpyDeviceToDevice, st));
+            CU(ctx, cudaMemcpyAsync(nv, m.vertex_ranges, (size_t)keep * 8, cudaMemcpyDeviceToDevice, st));
+        }
         ctx->release(m.submeshes);
         ctx->release(m.vertex_ranges);
-        m.submeshes = static_cast<ivx_chunk_submesh*>(ctx->alloc((size_t)want * sizeof(ivx_chunk_submesh)));
-        m.vertex_ranges = static_cast<uint32_t*>(ctx->alloc((size_t)want * 8));
-        if (!m.submeshes || !m.vertex_ranges) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh sync: out of device memory");
+        m.submeshes = ns;
+        m.vertex_ranges = nv;
         m.cap_submeshes = want;
     }
-    if (rows) {
-        CU(ctx, cudaMemcpyAsync(m.submeshes, s.submeshes.data(), (size_t)rows * sizeof(ivx_chunk_submesh), cudaMemcpyHostToDevice, st));
-        CU(ctx, cudaMemcpyAsync(m.vertex_ranges, s.vertex_ranges.data(), (size_t)rows * 8, cudaMemcpyHostToDevice, st));
+    {
+        std::sort(s.touched_rows.begin(), s.touched_rows.end());
+        s.touched_rows.erase(std::unique(s.touched_rows.begin(), s.touched_rows.end()), s.touched_rows.end());
+        std::vector<uint32_t> packed;
+        packed.reserve(s.touched_rows.size() * 16);
+        for (uint32_t row : s.touched_rows) {
+            if (row >= rows) continue;  // the row was swap-removed later in this sync
+            packed.push_back(row);
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(&s.submeshes[row]);
+            packed.insert(packed.end(), sw, sw + 13);
+            packed.push_back(s.vertex_ranges[2 * row]);
+            packed.push_back(s.vertex_ranges[2 * row + 1]);
+        }
+        s.touched_rows.clear();
+        const uint32_t n_rows = (uint32_t)(packed.size() / 16);
+        if (n_rows) {
+            uint32_t* d_packed = tmp.get<uint32_t>(packed.size());
+            if (!d_packed) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh sync: out of device memory");
+            CU(ctx, cudaMemcpyAsync(d_packed, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, st));
+            ctx->launches++;
+            k_scatter_rows<<<(n_rows * 16u + 255u) / 256u, 256, 0, st>>>(d_packed, n_rows, m.submeshes, m.vertex_ranges);
+            CU(ctx, cudaGetLastError());
+            CU(ctx, cudaStreamSynchronize(st));  // `packed` goes out of scope
+        }
     }
     m.n_vertices = s.n_vertices;
     m.n_indices = s.n_indices;

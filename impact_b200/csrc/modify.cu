@@ -382,23 +382,49 @@ __global__ void k_need_slot_for_convert(const DevChunk* __restrict__ chunks, con
     if (c >= n) return;
     need[c] = (convert_flag[c] && chunks[c].slot == 0xFFFFFFFFu) ? 1u : 0u;
 }
+// `first_extra`: slots handed out earlier in the same call whose number is only known on the device
 __global__ void k_assign_slots(const DevChunk* __restrict__ chunks, const uint32_t* __restrict__ need,
-                               const uint32_t* __restrict__ ord, uint32_t first, uint32_t n, uint32_t* __restrict__ slot_of) {
+                               const uint32_t* __restrict__ ord, uint32_t first, const uint32_t* __restrict__ first_extra, uint32_t n,
+                               uint32_t* __restrict__ slot_of) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
-    slot_of[c] = need[c] ? first + ord[c] : chunks[c].slot;
+    slot_of[c] = need[c] ? first + (first_extra ? *first_extra : 0u) + ord[c] : chunks[c].slot;
+}
+// number of non-zero bytes (invalidated chunks)
+__global__ void k_count_nonzero_u8(const uint8_t* __restrict__ a, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = __ballot_sync(0xffffffffu, c < n && a[c] != 0);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (uint32_t)__popc(b));
 }
 
-// bounding range of non-empty voxels over the whole object (object.rs:1149-1280)
+// update_occupied_chunk_ranges (object.rs:1156-1182): chunk-level bounds of the chunks that hold a non-empty voxel
+__global__ void k_occupied_chunk_ranges(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb, uint32_t* __restrict__ cmm) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const DevChunk ch = chunks[c];
+    if (ch.kind == 0 || (ch.kind == 2 && (ch.flags & (1u << 6)))) return;  // contains_only_empty_voxels
+    const uint32_t k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
+    atomicMin(&cmm[0], i);
+    atomicMin(&cmm[1], j);
+    atomicMin(&cmm[2], k);
+    atomicMax(&cmm[3], i);
+    atomicMax(&cmm[4], j);
+    atomicMax(&cmm[5], k);
+}
+
+// bounding range of non-empty voxels over the whole object (object.rs:1149-1280). Like the reference, voxels are
+// looked at only in the outermost occupied chunk planes (`cmm`, from k_occupied_chunk_ranges): no other chunk can
+// hold the first or the last non-empty voxel of an axis.
 __global__ void __launch_bounds__(256) k_occupied_ranges(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
                                                          uint32_t first_i, const unsigned char* __restrict__ voxels,
-                                                         uint32_t* __restrict__ occ) {
+                                                         const uint32_t* __restrict__ cmm, uint32_t* __restrict__ occ) {
     __shared__ uint32_t s_mm[6];
     const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
     for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
         const DevChunk ch = chunks[c];
         if (ch.kind == 0 || (ch.kind == 2 && (ch.flags & (1u << 6)))) continue;
         const uint32_t k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
+        if (cmm && i != cmm[0] && i != cmm[3] && j != cmm[1] && j != cmm[4] && k != cmm[2] && k != cmm[5]) continue;
         const uint32_t org[3] = {(i + first_i) * 16u, j * 16u, k * 16u};
         if (ch.kind == 1) {
             if (tid == 0)
@@ -458,15 +484,28 @@ cudaError_t launch_need_slot_for_convert(const DevChunk* chunks, const uint32_t*
     return cudaGetLastError();
 }
 cudaError_t launch_assign_slots(const DevChunk* chunks, const uint32_t* need, const uint32_t* ord, uint32_t first,
-                                uint32_t n, uint32_t* slot_of, cudaStream_t st) {
+                                const uint32_t* first_extra, uint32_t n, uint32_t* slot_of, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_assign_slots<<<(n + 255) / 256, 256, 0, st>>>(chunks, need, ord, first, n, slot_of);
+    k_assign_slots<<<(n + 255) / 256, 256, 0, st>>>(chunks, need, ord, first, first_extra, n, slot_of);
+    return cudaGetLastError();
+}
+cudaError_t launch_count_nonzero_u8(const uint8_t* a, uint32_t n, uint32_t* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_count_nonzero_u8<<<(n + 255) / 256, 256, 0, st>>>(a, n, out);
     return cudaGetLastError();
 }
 cudaError_t launch_occupied_ranges(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t first_i,
-                                   const unsigned char* voxels, uint32_t* occ, uint32_t grid, cudaStream_t st) {
+                                   const unsigned char* voxels, uint32_t* occ, uint32_t* chunk_minmax_scratch, uint32_t grid,
+                                   cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_occupied_ranges<<<grid, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), first_i, voxels, occ);
+    const uint3 nb3 = make_uint3(nb[0], nb[1], nb[2]);
+    if (chunk_minmax_scratch) {
+        const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+        cudaError_t e = cudaMemcpyAsync(chunk_minmax_scratch, init, sizeof(init), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        k_occupied_chunk_ranges<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, nb3, chunk_minmax_scratch);
+    }
+    k_occupied_ranges<<<grid, 256, 0, st>>>(chunks, n, nb3, first_i, voxels, chunk_minmax_scratch, occ);
     return cudaGetLastError();
 }
 

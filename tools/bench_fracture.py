@@ -39,6 +39,10 @@ def main():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=0)
     ap.add_argument("--split", action="store_true", help="also resolve connected regions and split off disconnected ones after every step")
+    ap.add_argument("--synced-mesh", action="store_true",
+                    help="keep the object's mesh on the device and patch it in place (ivx_object_mesh_sync = "
+                         "VoxelObjectMesh::sync_with_voxel_object with RangeAllocator placement) instead of returning the "
+                         "re-meshed chunks as a compact patch (ivx_object_remesh_dirty)")
     ap.add_argument("--inertial", action="store_true",
                     help="attach the inertial-property updater to every absorption (ivx_object_absorb_sphere_inertial)")
     args = ap.parse_args()
@@ -74,7 +78,7 @@ def main():
             st = obj.absorb_sphere(c, radius, influence)
         n_dirty = len(obj.invalidated_mesh_chunk_indices())
         t1 = time.perf_counter()
-        patch = VoxelObjectMesh.sync_with_voxel_object(obj)
+        patch = VoxelObjectMesh.sync(obj) if args.synced_mesh else VoxelObjectMesh.sync_with_voxel_object(obj)
         ctx.synchronize()
         t2 = time.perf_counter()
         regions = None
@@ -95,7 +99,7 @@ def main():
                 else:
                     n_discarded += 1
             if n_extracted or n_discarded:
-                VoxelObjectMesh.sync_with_voxel_object(obj)
+                VoxelObjectMesh.sync(obj) if args.synced_mesh else VoxelObjectMesh.sync_with_voxel_object(obj)
             ctx.synchronize()
         t3 = time.perf_counter()
         per_step.append({"absorb_ms": 1e3 * (t1 - t0), "remesh_ms": 1e3 * (t2 - t1), "split_ms": 1e3 * (t3 - t2),
@@ -112,7 +116,14 @@ def main():
     out = {
         "metric": "fracture_step_ms", "workload": args.workload, "description": desc, "grid_shape": list(shape),
         "steps": args.steps, "absorber_radius_voxels": radius,
+        "remesh": "ivx_object_mesh_sync (mesh patched in place on the device)" if args.synced_mesh else "ivx_object_remesh_dirty (compact patch)",
         "ms_per_step": 1e3 * wall / args.steps, "absorb_ms": mean("absorb_ms"), "remesh_ms": mean("remesh_ms"),
+        # steps that touch the object (the absorber leaves it after ~13 steps), medians: without the one-off device
+        # allocations of the first steps (pool growth, first buffers of a new size)
+        "active_steps": len([x for x in per_step if x["touched_chunks"]]),
+        "median_active_absorb_ms": float(np.median([x["absorb_ms"] for x in per_step if x["touched_chunks"]] or [0.0])),
+        "median_active_remesh_ms": float(np.median([x["remesh_ms"] for x in per_step if x["touched_chunks"]] or [0.0])),
+        "median_active_split_ms": float(np.median([x["split_ms"] for x in per_step if x["touched_chunks"]] or [0.0])) if args.split else None,
         "split_ms": mean("split_ms") if args.split else None,
         "fragments_extracted": sum(s["extracted"] for s in per_step), "fragments_dropped": sum(s["discarded"] for s in per_step),
         "split_note": "resolve connected regions + extract_any_disconnected_region until one region is left + mesh the fragments",
@@ -125,6 +136,7 @@ def main():
         "mesh_kernel_ms_per_step": (prof["mesh_count"][0] + prof["mesh_emit"][0]) / max(1, args.steps),
         "gpu_launches": int(launches), "timing": "host wall clock around synchronous C-ABI calls; kernel times from CUDA events",
         "last_step": per_step[-1],
+        "per_step_ms": [[round(x["absorb_ms"], 3), round(x["remesh_ms"], 3), round(x["split_ms"], 3), x["dirty_chunks"]] for x in per_step],
     }
     if args.inertial:
         scratch = obj.inertial_moments(densities)
