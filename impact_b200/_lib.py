@@ -24,7 +24,7 @@ STATUS_NAMES = {
 EXPORTED_SYMBOLS = [
     "ivx_create", "ivx_destroy", "ivx_last_error", "ivx_abi_version", "ivx_kernel_launch_count", "ivx_synchronize", "ivx_profile_enable", "ivx_profile_reset", "ivx_profile_get", "ivx_profile_counter",
     "ivx_program_build", "ivx_program_upload", "ivx_program_compile_host", "ivx_program_info_get", "ivx_program_nodes", "ivx_program_free",
-    "ivx_program_eval_chunks", "ivx_program_eval_blocks", "ivx_object_generate", "ivx_object_generate_streamed", "ivx_object_generate_slab", "ivx_program_plane_work", "ivx_object_halo_capacity", "ivx_object_halo_export",
+    "ivx_meta_compile", "ivx_program_eval_chunks", "ivx_program_eval_blocks", "ivx_object_generate", "ivx_object_generate_streamed", "ivx_object_generate_slab", "ivx_program_plane_work", "ivx_object_halo_capacity", "ivx_object_halo_export",
     "ivx_object_halo_import", "ivx_object_slab_classify", "ivx_object_halo_kinds_export", "ivx_object_halo_kinds_import",
     "ivx_object_slab_finalize", "ivx_object_info_get",
     "ivx_object_download", "ivx_object_download_async", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_peer_alloc", "ivx_peer_free", "ivx_peer_open", "ivx_peer_close", "ivx_mesh_push", "ivx_object_absorb_sphere", "ivx_object_absorb_capsule",
@@ -65,6 +65,25 @@ class MeshInfo(C.Structure):
 class CommConfig(C.Structure):
     _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("gather_rank", C.c_uint32), ("plane_chunks", C.c_uint32),
                 ("mesh_vertices", C.c_uint64), ("mesh_indices", C.c_uint64), ("mesh_submeshes", C.c_uint64)]
+
+
+class MetaSource(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("idx", C.c_uint32), ("value", C.c_float), ("scale", C.c_float)]
+
+
+class MetaParam(C.Structure):
+    _fields_ = [("dist", C.c_uint32), ("src", MetaSource * 3)]
+
+
+META_MAX_PARAMS = 8
+
+
+class MetaNode(C.Structure):
+    """`ivx_meta_node` (include/impact_voxel_cuda.h)."""
+    _fields_ = [("kind", C.c_uint32), ("child", C.c_uint32 * 2), ("count", C.c_uint32), ("seed", C.c_uint32),
+                ("sampling", C.c_uint32), ("composition", C.c_uint32), ("rotation", C.c_uint32), ("anchor", C.c_uint32),
+                ("min_pick_count", C.c_uint32), ("max_pick_count", C.c_uint32), ("pick_probability", C.c_float),
+                ("smoothness", C.c_float), ("params", MetaParam * META_MAX_PARAMS)]
 
 
 class GatheredMesh(C.Structure):

@@ -1,4 +1,6 @@
-"""Host-side mirror of the reference's meta SDF graph compiler.
+"""Meta SDF graph compile: file readers, the binding of the library's `ivx_meta_compile` (csrc/meta.cpp, the product path:
+`compile_meta_nodes`, `compile_file`, `compile_graph_file`) and `MetaCompiler`, a Python mirror of the same compile that
+the tests hold the C++ against node for node (tests/test_meta_native.py).
 
 `MetaSDFGraph::build_in(scale_factor, seed) -> SDFGraph`
 (engine/crates/impact_voxel/src/generation/sdf/meta.rs:741-896, node resolvers :1194-2260, parameter
@@ -306,7 +308,7 @@ def compile_graph_file(path, ctx=None):
     """`build_sdf_graph` (build.rs:102-128): the editor file compiled with its own scale factor and seed →
     (atomic SDFGraph, voxel_extent)."""
     nodes, voxel_extent, scale_factor, seed = load_graph_ron(path)
-    return MetaCompiler(nodes, scale_factor, seed, ctx).build(), voxel_extent
+    return compile_meta_nodes(nodes, scale_factor, seed, ctx), voxel_extent
 
 
 # ------------------------------------------------------------------------------------------------
@@ -680,8 +682,10 @@ def _jittered_direction(direction, max_angle, rng):
 
 
 class MetaCompiler:
-    """One `MetaSDFGraph::build_in` run. `ctx` (impact_b200.voxel.Context) is needed only by the
-    surface-probing nodes; graphs without them compile without a device."""
+    """One `MetaSDFGraph::build_in` run, in Python: the readable mirror that tests/test_meta_native.py holds the library's
+    `ivx_meta_compile` (csrc/meta.cpp, the product path: `compile_meta_nodes` below) against, node for node. `ctx`
+    (impact_b200.voxel.Context) is needed only by the surface-probing nodes; graphs without them compile without a
+    device."""
 
     def __init__(self, nodes, scale_factor=1.0, seed=0, ctx=None):
         self.nodes, self.scale, self.seed, self.ctx = nodes, f32(scale_factor), seed, ctx
@@ -1181,6 +1185,102 @@ class MetaCompiler:
         return ("instances", res)
 
 
+# ------------------------------------------------------------------------------------------------
+# the product path: the same compile inside the library (csrc/meta.cpp) behind `ivx_meta_compile`. The class above is the
+# test mirror it is compared with node for node (tests/test_meta.py); hosts other than Python hand the library PODs.
+
+META_KIND_IDS = {k: i for i, k in enumerate(EDITOR_NODE_KINDS)}
+# the kind's distributed parameters in the reference struct's declaration order (= the index space of `FromParam`)
+META_PARAM_NAMES = {
+    "Spheres": ["radius", "center_x", "center_y", "center_z"],
+    "Capsules": ["segment_length", "radius", "center_x", "center_y", "center_z"],
+    "Boxes": ["extent_x", "extent_y", "extent_z", "center_x", "center_y", "center_z"],
+    "Translation": ["translation_x", "translation_y", "translation_z"],
+    "Rotation": ["tilt_angle", "turn_angle", "roll_angle"],
+    "Scaling": ["scaling"],
+    "Similarity": ["scale", "tilt_angle", "turn_angle", "roll_angle", "translation_x", "translation_y", "translation_z"],
+    "StratifiedGridTransforms": ["shape_x", "shape_y", "shape_z", "cell_extent_x", "cell_extent_y", "cell_extent_z",
+                                 "jitter_fraction"],
+    "SphereSurfaceTransforms": ["radius", "jitter_fraction"],
+    "MultifractalNoiseSDFModifier": ["octaves", "frequency", "lacunarity", "persistence", "amplitude"],
+}
+_DIST_IDS = {"Constant": 0, "Uniform": 1, "UniformCosAngle": 2, "PowerLaw": 3}
+_DIST_FIELDS = {"Uniform": ("min", "max"), "UniformCosAngle": ("min_angle", "max_angle"), "PowerLaw": ("min", "max", "exponent")}
+
+
+def meta_nodes_to_pod(nodes):
+    """Meta nodes (as `load_vgen_ron` / `load_graph_ron` / `asteroid_meta_nodes` give them) → ctypes array of
+    `ivx_meta_node`."""
+    from . import _lib as L
+
+    def put_source(dst, src):
+        if src.tag == "Fixed":
+            dst.kind, dst.idx, dst.value, dst.scale = 0, 0, float(src.fields), 0.0
+        else:
+            dst.kind, dst.idx = 1, int(src["idx"])
+            dst.value, dst.scale = float(src["mapping"]["offset"]), float(src["mapping"]["scale"])
+
+    arr = (L.MetaNode * max(len(nodes), 1))()
+    for pod, node in zip(arr, nodes):
+        t = node.tag
+        if t not in META_KIND_IDS:
+            raise ValueError(f"unknown meta node kind {t}")
+        pod.kind = META_KIND_IDS[t]
+        for slot, c in enumerate(_children(node)):
+            pod.child[slot] = int(c)
+        f = node.fields or {}
+        pod.count = int(f.get("count", 0))
+        pod.seed = int(f.get("seed", 0))
+        pod.sampling = _SAMPLING.index(f["sampling"].tag) if "sampling" in f else 0
+        pod.composition = _COMPOSITION.index(f["composition"].tag) if "composition" in f else 0
+        pod.rotation = _ROTATION.index(f["rotation"].tag) if "rotation" in f else 0
+        pod.anchor = _ANCHOR.index(f["anchor"].tag) if "anchor" in f else 0
+        pod.min_pick_count = int(f.get("min_pick_count", 0))
+        pod.max_pick_count = int(f.get("max_pick_count", 0))
+        pod.pick_probability = float(f.get("pick_probability", 0.0))
+        pod.smoothness = float(f.get("smoothness", 0.0))
+        for i, name in enumerate(META_PARAM_NAMES.get(t, ())):
+            spec = f[name]
+            pod.params[i].dist = _DIST_IDS[spec.tag]
+            if spec.tag == "Constant":
+                put_source(pod.params[i].src[0], spec.fields)
+            else:
+                for q, key in enumerate(_DIST_FIELDS[spec.tag]):
+                    put_source(pod.params[i].src[q], spec[key])
+    return arr
+
+
+def compile_meta_nodes(nodes, scale_factor=1.0, seed=0, ctx=None) -> SDFGraph:
+    """`MetaSDFGraph::build_in` through the library's `ivx_meta_compile` → atomic SDFGraph (empty when the meta graph
+    resolves to nothing). `ctx` is needed only for graphs with surface-probing nodes."""
+    import ctypes as C
+
+    from . import _lib as L
+    from .graph import SDF_NODE_DTYPE
+
+    lib = L.lib()
+    pods = meta_nodes_to_pod(nodes)
+    handle = ctx.h if ctx is not None else None
+    count, root, empty = C.c_uint32(), C.c_uint32(), C.c_int()
+    err = C.create_string_buffer(512)
+    capacity = 4096
+    while True:
+        out = np.zeros(capacity, SDF_NODE_DTYPE)
+        rc = lib.ivx_meta_compile(handle, pods, C.c_uint32(len(nodes)),
+                                  C.c_float(scale_factor), C.c_uint64(seed & M64), L.ptr(out), C.c_uint32(capacity),
+                                  C.byref(count), C.byref(root), C.byref(empty), err, C.c_size_t(len(err)))
+        if rc == 5 and count.value > capacity:  # IVX_ERR_CAPACITY
+            capacity = count.value
+            continue
+        break
+    if rc != 0:
+        msg = err.value.decode() or f"ivx_meta_compile failed with status {rc}"
+        raise (RuntimeError if rc == 1 else ValueError)(msg)
+    if empty.value:
+        return SDFGraph()
+    return graph_from_nodes(out[: count.value], root.value)
+
+
 def _fixed(v):
     return Tagged("Fixed", v)
 
@@ -1246,7 +1346,7 @@ def asteroid_meta_nodes():
 
 
 def compile_file(path, scale_factor=1.0, seed=0, ctx=None) -> SDFGraph:
-    return MetaCompiler(load_vgen_ron(path), scale_factor, seed, ctx).build()
+    return compile_meta_nodes(load_vgen_ron(path), scale_factor, seed, ctx)
 
 
 _CACHE = {}
@@ -1285,9 +1385,9 @@ def asteroid_graph_scaled(max_dim_lo, max_dim_hi, seed=0, ctx=None, use_cache=Tr
         ctx = Context(0)
     nodes = asteroid_meta_nodes()
     try:
-        s = W.scale_to_max_dim(lambda sc: MetaCompiler(nodes, sc, seed, ctx).build(), max_dim_lo, max_dim_hi,
+        s = W.scale_to_max_dim(lambda sc: compile_meta_nodes(nodes, sc, seed, ctx), max_dim_lo, max_dim_hi,
                                max_dim_hi / 330.0)
-        g = MetaCompiler(nodes, s, seed, ctx).build()
+        g = compile_meta_nodes(nodes, s, seed, ctx)
     finally:
         if own:
             ctx.close()

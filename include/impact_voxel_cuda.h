@@ -240,6 +240,101 @@ int ivx_program_info_get(ivx_ctx* ctx, const ivx_program* program, ivx_program_i
 int ivx_program_nodes(ivx_ctx* ctx, const ivx_program* program, ivx_node* out, uint32_t capacity);
 void ivx_program_free(ivx_ctx* ctx, ivx_program* program);
 
+/* ---- meta graph compile ---------------------------------------------------
+ * ivx_meta_compile replaces MetaSDFGraph::build_in (generation/sdf/meta.rs:741-896): it resolves the meta nodes
+ * (instances, transforms, placements, selections, SDF instantiation and combination; all 21 `MetaSDFNode` kinds,
+ * meta.rs:55-80) into the atomic `SDFNode` list that ivx_program_build takes. The host parses its file format
+ * (RON in the engine) into these PODs; sampling, seeding and the emitted node order are the reference's.
+ *
+ * ivx_meta_source  = `ParamSource` after name resolution (meta/params.rs:40-62): kind 0 a fixed value, kind 1
+ *                    `offset + scale * value of parameter idx of the same node` (value = offset).
+ * ivx_meta_param   = `ContParamSpec` / `DiscreteParamSpec` (params.rs:20-38): dist 0 Constant(src[0]),
+ *                    1 Uniform{min,max}, 2 UniformCosAngle{min_angle,max_angle} (degrees), 3 PowerLaw{min,max,exponent}.
+ * ivx_meta_node    = one `MetaSDFNode`; params[] holds the kind's parameters in the declaration order of the reference
+ *                    struct:
+ *   Points                    count
+ *   Spheres                   count, sampling, seed; radius, center_x, center_y, center_z
+ *   Capsules                  count, sampling, seed; segment_length, radius, center_x, center_y, center_z
+ *   Boxes                     count, sampling, seed; extent_x, extent_y, extent_z, center_x, center_y, center_z
+ *   Translation               child[0], composition, sampling, seed; translation_x, _y, _z
+ *   Rotation                  child[0], composition, sampling, seed; tilt_angle, turn_angle, roll_angle (degrees)
+ *   Scaling                   child[0], composition, sampling, seed; scaling
+ *   Similarity                child[0], composition, sampling, seed; scale, tilt_angle, turn_angle, roll_angle,
+ *                             translation_x, _y, _z
+ *   StratifiedGridTransforms  child[0], seed; shape_x, shape_y, shape_z (discrete), cell_extent_x, _y, _z, jitter_fraction
+ *   SphereSurfaceTransforms   child[0], rotation, seed; radius, jitter_fraction
+ *   ClosestTranslationToSurface / RotationToGradient   child[0] = surface SDF, child[1] = subject instances
+ *   RayTranslationToSurface   child[0] = surface SDF, child[1] = subject instances, anchor
+ *   StochasticSelection       child[0], min_pick_count, max_pick_count, pick_probability, seed
+ *   SDFInstantiation          child[0]
+ *   TransformApplication      child[0] = SDF or group, child[1] = instances
+ *   MultifractalNoiseSDFModifier  child[0], sampling, seed; octaves (discrete), frequency, lacunarity, persistence,
+ *                             amplitude
+ *   SDFUnion / SDFSubtraction / SDFIntersection   child[0], child[1], smoothness
+ *   SDFGroupUnion             child[0], smoothness
+ * The root is the last node (meta.rs:766). */
+#define IVX_META_MAX_PARAMS 8
+typedef enum ivx_meta_kind {
+    IVX_META_POINTS = 0,
+    IVX_META_SPHERES = 1,
+    IVX_META_CAPSULES = 2,
+    IVX_META_BOXES = 3,
+    IVX_META_TRANSLATION = 4,
+    IVX_META_ROTATION = 5,
+    IVX_META_SCALING = 6,
+    IVX_META_SIMILARITY = 7,
+    IVX_META_STRATIFIED_GRID_TRANSFORMS = 8,
+    IVX_META_SPHERE_SURFACE_TRANSFORMS = 9,
+    IVX_META_CLOSEST_TRANSLATION_TO_SURFACE = 10,
+    IVX_META_RAY_TRANSLATION_TO_SURFACE = 11,
+    IVX_META_ROTATION_TO_GRADIENT = 12,
+    IVX_META_STOCHASTIC_SELECTION = 13,
+    IVX_META_SDF_INSTANTIATION = 14,
+    IVX_META_TRANSFORM_APPLICATION = 15,
+    IVX_META_MULTIFRACTAL_NOISE = 16,
+    IVX_META_SDF_UNION = 17,
+    IVX_META_SDF_SUBTRACTION = 18,
+    IVX_META_SDF_INTERSECTION = 19,
+    IVX_META_SDF_GROUP_UNION = 20
+} ivx_meta_kind;
+
+typedef struct ivx_meta_source {
+    uint32_t kind;  /* 0 Fixed, 1 FromParam */
+    uint32_t idx;   /* FromParam: index into the node's params */
+    float value;    /* Fixed: the value (discrete: the integer); FromParam: offset */
+    float scale;    /* FromParam: scale */
+} ivx_meta_source;
+
+typedef struct ivx_meta_param {
+    uint32_t dist;  /* 0 Constant, 1 Uniform, 2 UniformCosAngle, 3 PowerLaw */
+    ivx_meta_source src[3];
+} ivx_meta_param;
+
+typedef struct ivx_meta_node {
+    uint32_t kind;            /* ivx_meta_kind */
+    uint32_t child[2];
+    uint32_t count;
+    uint32_t seed;
+    uint32_t sampling;        /* ParameterSamplingMode: 0 OnlyOnce, 1 PerInstance */
+    uint32_t composition;     /* CompositionMode: 0 Post, 1 Pre */
+    uint32_t rotation;        /* SphereSurfaceRotation: 0 Identity, 1 RadialOutwards, 2 RadialInwards */
+    uint32_t anchor;          /* RayTranslationAnchor: 0 Origin, 1 ShapeBoundaryAtOrigin */
+    uint32_t min_pick_count;
+    uint32_t max_pick_count;
+    float pick_probability;
+    float smoothness;
+    ivx_meta_param params[IVX_META_MAX_PARAMS];
+} ivx_meta_node;
+
+/* Writes the atomic nodes to out_nodes and the root id to *out_root. *out_empty = 1 when the graph resolves to nothing
+ * (`SDFGraph` without root; no nodes are written). IVX_ERR_CAPACITY with *out_count set when `capacity` is too small.
+ * ctx may be NULL for graphs without ClosestTranslationToSurface / RayTranslationToSurface / RotationToGradient nodes;
+ * those probe the partial SDF on the device (ivx_program_eval_blocks, all instances of a node per launch).
+ * err receives the reference's error text on IVX_ERR_GRAPH. */
+int ivx_meta_compile(ivx_ctx* ctx, const ivx_meta_node* nodes, uint32_t n_nodes, float scale_factor, uint64_t seed,
+                     ivx_sdf_node* out_nodes, uint32_t capacity, uint32_t* out_count, uint32_t* out_root,
+                     int* out_empty, char* err, size_t err_capacity);
+
 /* SDFGenerator::compute_signed_distances_for_chunk (atomic.rs:207-216) for a
  * batch of chunks: origins = n_chunks x 3 chunk lower corners in root space;
  * out = n_chunks x 4096 f32 (host). Used by the parity tests and by the

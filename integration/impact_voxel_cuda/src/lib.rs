@@ -27,6 +27,17 @@ pub enum IvxCtx {} pub enum IvxProgram {} pub enum IvxObject {} pub enum IvxComm
                                         pub d_index_materials: *mut c_void, pub d_submeshes: *mut c_void,
                                         pub d_vertex_ranges: *mut c_void }
 
+/// `ParamSource` after name resolution (meta/params.rs:40-62): kind 0 Fixed(value), 1 FromParam { idx, Linear { offset: value, scale } }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct IvxMetaSource { pub kind: u32, pub idx: u32, pub value: f32, pub scale: f32 }
+/// `ContParamSpec` / `DiscreteParamSpec`: dist 0 Constant, 1 Uniform, 2 UniformCosAngle, 3 PowerLaw
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct IvxMetaParam { pub dist: u32, pub src: [IvxMetaSource; 3] }
+/// one `MetaSDFNode` (meta.rs:55-80); `kind` = the variant's position in the enum, `params` in field order
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct IvxMetaNode { pub kind: u32, pub child: [u32; 2], pub count: u32, pub seed: u32, pub sampling: u32,
+                         pub composition: u32, pub rotation: u32, pub anchor: u32, pub min_pick_count: u32,
+                         pub max_pick_count: u32, pub pick_probability: f32, pub smoothness: f32,
+                         pub params: [IvxMetaParam; 8] }
+
 dynamic_lib::define_lib! {
     name = VoxelCudaLib,
     path_env_var = "IMPACT_VOXEL_CUDA_LIB",
@@ -38,6 +49,9 @@ dynamic_lib::define_lib! {
     unsafe fn ivx_program_build(ctx: *mut IvxCtx, nodes: *const IvxSdfNode, n_nodes: u32, root: u32,
                                 out: *mut *mut IvxProgram) -> i32;
     unsafe fn ivx_program_free(ctx: *mut IvxCtx, program: *mut IvxProgram) -> ();
+    unsafe fn ivx_meta_compile(ctx: *mut IvxCtx, nodes: *const IvxMetaNode, n_nodes: u32, scale_factor: f32, seed: u64,
+                               out_nodes: *mut IvxSdfNode, capacity: u32, out_count: *mut u32, out_root: *mut u32,
+                               out_empty: *mut i32, err: *mut c_char, err_capacity: usize) -> i32;
     unsafe fn ivx_object_generate(ctx: *mut IvxCtx, program: *const IvxProgram, voxel_extent: f32,
                                   types: *const IvxTypeGenerator, out: *mut *mut IvxObject) -> i32;
     unsafe fn ivx_object_info_get(ctx: *mut IvxCtx, object: *const IvxObject, out: *mut IvxObjectInfo) -> i32;
