@@ -1662,6 +1662,9 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     ctx->release(obj->d_labels);
     ctx->release(obj->d_regions);
     ctx->release(obj->d_label_stale);
+    ctx->release(obj->d_region_first);
+    ctx->release(obj->d_region_label);
+    ctx->release(obj->d_region_root);
     delete obj;
 }
 
@@ -2288,33 +2291,45 @@ int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* obj, ivx_ex
         info->origin_offset_in_parent[d] = r0[d] * 16u;
     }
     const uint32_t nE = nbE[0] * nbE[1] * nbE[2];
-    const std::vector<uint32_t>&creg = obj->h_chunk_regions, &first = obj->h_first_region, &roots = obj->h_region_roots;
 
-    // ---- the region's chunks inside its bounding box, in linear order (extraction.rs:137-245, 339-349) ----
-    std::vector<uint8_t> mode(nE, 0), is_r(roots.size());
-    std::vector<uint32_t> src_index(nE, 0xFFFFFFFFu), first_region(nE, 0), dst_slot(nE, 0xFFFFFFFFu);
-    for (size_t q = 0; q < roots.size(); ++q) is_r[q] = roots[q] == R ? 1 : 0;
-    uint32_t n_uniform = 0, n_non_uniform = 0, e = 0;
-    for (uint32_t i = 0; i < nbE[0]; ++i)
-        for (uint32_t j = 0; j < nbE[1]; ++j)
-            for (uint32_t k = 0; k < nbE[2]; ++k, ++e) {
-                const uint32_t c = ((r0[0] + i) * obj->nb[1] + (r0[1] + j)) * obj->nb[2] + (r0[2] + k);
-                const uint32_t rc = creg[c] & 255u, kind = creg[c] >> 16;
-                bool in_region = false, mixed = false;
-                for (uint32_t r = 0; r < rc; ++r) {
-                    if (is_r[first[c] + r]) in_region = true; else mixed = true;
-                }
-                if (!in_region || kind == 0u) continue;
-                src_index[e] = c;
-                first_region[e] = first[c];
-                if (kind == 1u) {
-                    mode[e] = 1;
-                    n_uniform++;
-                } else {
-                    mode[e] = mixed ? 3 : 2;
-                    dst_slot[e] = n_non_uniform++;
-                }
-            }
+    // ---- the region's chunks inside its bounding box, in linear order (extraction.rs:137-245, 339-349): classified on
+    //      the device from the roots the resolve left there ----
+    Tmp tmp(ctx);
+    cudaStream_t st = ctx->stream;
+    uint8_t* d_mode = tmp.get<uint8_t>(nE);
+    uint32_t* d_src = tmp.get<uint32_t>(nE);
+    uint32_t* d_first = tmp.get<uint32_t>(nE);
+    uint32_t* d_slot = tmp.get<uint32_t>(nE);
+    uint32_t* d_nu_flag = tmp.get<uint32_t>(nE);
+    uint8_t* d_is_r = tmp.get<uint8_t>(std::max<size_t>(1, obj->region_total));
+    uint32_t* d_count = ctx->d_scratch + 44;  // [0] non-empty voxels moved [1] uniform chunks [2] non-uniform chunks
+    if (!d_mode || !d_src || !d_first || !d_slot || !d_nu_flag || !d_is_r) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "extraction: out of device memory");
+    CU(ctx, cudaMemsetAsync(d_count, 0, 12, st));
+    ExtractPlanArgs pa{};
+    pa.regions = obj->d_regions;
+    pa.first = obj->d_region_first;
+    pa.root = obj->d_region_root;
+    pa.total = obj->region_total;
+    pa.region_root = obj->region_two[si.smallest];
+    pa.n_ext = nE;
+    for (int d = 0; d < 3; ++d) {
+        pa.ext[d] = nbE[d];
+        pa.lo[d] = r0[d];
+    }
+    pa.nb1 = obj->nb[1];
+    pa.nb2 = obj->nb[2];
+    pa.mode = d_mode;
+    pa.src_index = d_src;
+    pa.first_region = d_first;
+    pa.non_uniform_flag = d_nu_flag;
+    pa.dst_slot = d_slot;
+    pa.uniform_count = d_count + 1;
+    pa.is_member = d_is_r;
+    ctx->launches += 4;
+    CU(ctx, launch_extract_plan(pa, d_count + 2, st));
+    uint32_t plan_words[3];
+    if (int rc = read_words(ctx, d_count, 3, plan_words)) return rc;
+    const uint32_t n_uniform = plan_words[1], n_non_uniform = plan_words[2];
     info->region_chunks = n_uniform + n_non_uniform;
 
     ivx_object* ext = nullptr;
@@ -2329,21 +2344,6 @@ int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* obj, ivx_ex
     } guard{ctx, ext};
     ext->slots_used = n_non_uniform;
 
-    Tmp tmp(ctx);
-    cudaStream_t st = ctx->stream;
-    uint8_t* d_mode = tmp.get<uint8_t>(nE);
-    uint32_t* d_src = tmp.get<uint32_t>(nE);
-    uint32_t* d_first = tmp.get<uint32_t>(nE);
-    uint32_t* d_slot = tmp.get<uint32_t>(nE);
-    uint8_t* d_is_r = tmp.get<uint8_t>(std::max<size_t>(1, is_r.size()));
-    uint32_t* d_count = ctx->d_scratch + 44;
-    if (!d_mode || !d_src || !d_first || !d_slot || !d_is_r) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "extraction: out of device memory");
-    CU(ctx, cudaMemcpyAsync(d_mode, mode.data(), nE, cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(d_src, src_index.data(), (size_t)nE * 4, cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(d_first, first_region.data(), (size_t)nE * 4, cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(d_slot, dst_slot.data(), (size_t)nE * 4, cudaMemcpyHostToDevice, st));
-    if (!is_r.empty()) CU(ctx, cudaMemcpyAsync(d_is_r, is_r.data(), is_r.size(), cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemsetAsync(d_count, 0, 4, st));
     ExtractArgs xa{};
     xa.src_chunks = obj->d_chunks;
     xa.src_voxels = obj->d_voxels;
@@ -2360,7 +2360,6 @@ int ivx_object_extract_disconnected_region(ivx_ctx* ctx, ivx_object* obj, ivx_ex
     xa.dst_voxels = ext->d_voxels;
     xa.non_empty_count = d_count;
     KL(ctx, launch_extract_chunks(xa, persistent_grid(ctx, nE, 4), st));
-    CU(ctx, cudaStreamSynchronize(st));  // the host staging vectors go out of scope below
     obj->split_valid = false;
     obj->plan_serial = 0;
 

@@ -174,9 +174,14 @@ struct ivx_object {
     uint32_t label_slots = 0;
     uint32_t* d_regions = nullptr;      // per chunk: kind << 16 | boundary_region_count << 8 | region_count
     uint8_t* d_label_stale = nullptr;   // per chunk: modified since its labels were computed
-    std::vector<uint32_t> h_chunk_regions;  // per chunk: kind << 16 | boundary_region_count << 8 | region_count
-    std::vector<uint32_t> h_first_region;
-    std::vector<uint32_t> h_region_roots;
+    // results of the last resolve (regions.cu), valid while split_valid
+    uint32_t* d_region_first = nullptr;  // per chunk: index of its region 0 among all local regions
+    uint32_t* d_region_label = nullptr;  // per local region: chunk << 8 | region
+    uint32_t* d_region_root = nullptr;   // per local region: index of the root of its connected region
+    uint32_t region_cap = 0;             // capacity of the per-region arrays
+    uint32_t region_total = 0;           // local regions
+    uint32_t region_records = 0;         // connection records of the last resolve (sizes the next one)
+    uint32_t region_two[2] = {0, 0};     // region indices of the two roots find_two_disconnected_regions reports
     bool split_valid = false;
     // streamed generation: packed voxels / descriptors staged for the copy stream
     ivx_voxel* d_stage_voxels = nullptr;

@@ -246,6 +246,78 @@ cudaError_t launch_occupied_ranges(const DevChunk* chunks, uint32_t n, const uin
 cudaError_t launch_mark_box(uint8_t* arr, const uint32_t nb[3], const uint32_t lo[3], const uint32_t hi[3], uint8_t value,
                             cudaStream_t st);
 
+// ---- regions.cu: the global pass of connected-region detection ------------------
+// words of the result block (device counters, read back once per resolve)
+enum RegionWord : uint32_t {
+    RW_WORK = 0,          // chunks re-labelled
+    RW_RECORDS = 1,       // connection records found (may exceed the capacity: retry)
+    RW_LABEL_ERROR = 2,   // k_local_regions / k_region_connections limits
+    RW_TOTAL = 3,         // local regions of the object
+    RW_TREES = 4,
+    RW_EVENTS = 5,
+    RW_ERROR = 6,         // RegionError
+    RW_ROOTS = 7,         // connected regions
+    RW_FIRST_ROOT = 8,    // region index of the first / second root in linear order
+    RW_SECOND_ROOT = 9,
+    RW_FIRST_LABEL = 10,  // the same as GlobalRegionLabel (chunk << 8 | region)
+    RW_SECOND_LABEL = 11,
+    RW_ERROR_INFO = 12,   // 4 words
+    RW_CANDIDATES = 16,   // 2 x { chunks, NonUniform chunks, chunk min[3], chunk max[3] }
+    RW_COUNT = 32
+};
+enum RegionError : uint32_t { RERR_REGION_CAPACITY = 1, RERR_TOO_MANY_CONNECTIONS = 2, RERR_PAIR_TABLE_FULL = 3 };
+
+struct RegionPass {
+    uint32_t n;                  // chunks
+    uint32_t stride0, stride1;   // linear chunk index strides of dimension 0 and 1
+    const uint32_t* regions;     // per chunk: kind << 16 | boundary_region_count << 8 | region_count
+    uint32_t* words;             // RegionWord
+    uint32_t cap;                // capacity of the per-region arrays
+    uint32_t* counts;            // per chunk (scratch)
+    uint32_t* first;             // per chunk: index of its region 0
+    uint32_t* label;             // per region: chunk << 8 | region
+    uint32_t* root;              // per region: region index of its root
+    uint32_t* lowest;            // per region: lowest adjacent region below it, else itself
+    uint32_t* tree;              // per region: fixed point of `lowest`
+    uint32_t* degree;            // zeroed by the caller
+    uint32_t* fresh_flag;        // zeroed by the caller
+    uint32_t* tree_number;
+    uint32_t* tree_vertex;       // per tree: its fresh region
+    uint32_t* tree_root;         // per tree: region index of the root of its set
+    uint32_t* tree_parent;       // replay forest when the trees do not fit shared memory
+    uint32_t* event_count;       // per region (as visiting time); zeroed by the caller
+    uint32_t* event_offset;
+    uint32_t* event_cursor;      // zeroed by the caller
+    const uint2* records;        // k_region_connections output
+    uint32_t record_cap;
+    uint2* edges;                // per record: (lower region, upper region)
+    uint2* events;               // per tree pair, in time order: (absorbing tree, absorbed tree)
+    unsigned long long* slot_keys;  // pair table, all ones = empty; slot_values all ones
+    uint32_t* slot_values;
+    uint32_t slot_mask;
+};
+cudaError_t launch_region_result_init(uint32_t* words, cudaStream_t st);
+cudaError_t launch_region_global_pass(const RegionPass& p, uint32_t n_scan, uint32_t* launches, int max_shared_bytes,
+                                      cudaStream_t st);
+cudaError_t launch_region_root_labels(const uint32_t* root, const uint32_t* label, uint32_t total, uint32_t* out, cudaStream_t st);
+
+struct ExtractPlanArgs {
+    const uint32_t* regions;
+    const uint32_t* first;
+    const uint32_t* root;
+    uint32_t total;          // local regions of the source object
+    uint32_t region_root;    // region index of the extracted region's root
+    uint32_t n_ext, ext[3], lo[3], nb1, nb2;
+    uint8_t* mode;
+    uint32_t* src_index;
+    uint32_t* first_region;
+    uint32_t* non_uniform_flag;
+    uint32_t* dst_slot;
+    uint32_t* uniform_count;
+    uint8_t* is_member;      // per local region of the source
+};
+cudaError_t launch_extract_plan(const ExtractPlanArgs& a, uint32_t* slot_total, cudaStream_t st);
+
 // ---- api.cu helpers ------------------------------------------------------------
 cudaError_t launch_flag_dirty_exposed(const DevChunk* chunks, const uint8_t* dirty, uint32_t n, uint32_t* exposed_flag,
                                       uint32_t* dirty_flag, cudaStream_t st);

@@ -5,9 +5,9 @@
 //                         (split_detection.rs:662-893) with ITS label numbering
 //   k_region_connections  per chunk and upper face: the distinct (region, adjacent region) pairs across the
 //                         face (what the connection updaters of split_detection.rs:1046-1326, 1424-1463 record)
-//   resolve (host)        the chunk-level union-find of resolve_connected_regions_between_all_chunks
-//                         (split_detection.rs:323-488), count_regions / find_two_disconnected_regions
-//                         (:193-301) and the smallest-region choice of extraction.rs:121-281
+//   regions.cu            the roots resolve_connected_regions_between_all_chunks (split_detection.rs:323-488) leaves,
+//                         count_regions / find_two_disconnected_regions (:193-301) and the counts behind the
+//                         smallest-region choice of extraction.rs:121-281 — on the device, one read-back per resolve
 //
 // Why the labelling is emulated sequentially. Which local region ends up representing a global region — and so
 // which two regions find_two_disconnected_regions reports and which one an extraction splits off — depends on
@@ -18,8 +18,8 @@
 // on shared-memory state (8 KiB parents + 4 KiB flags + 4 KiB labels, ~13 chunks in flight per SM), parallel
 // only where the order provably does not matter: all merges of one k-run go under the same root, the
 // boundary traversal is taken 32 positions at a time with the earliest lane winning a contested root, and
-// label numbers are ballot prefix counts. The global pass works on ~10^5 regions and stays on the host, as
-// in the reference.
+// label numbers are ballot prefix counts. The global pass over ~10^5 regions has the same kind of order
+// dependence; regions.cu reduces it to a replay of ~10^3 events (see there).
 #include <chrono>
 
 #include "api_internal.cuh"
@@ -82,7 +82,7 @@ __device__ __forceinline__ uint32_t find_root_compress(volatile uint16_t* par, u
 }
 
 __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict__ chunks, const uint32_t* __restrict__ work,
-                                                      uint32_t n_work, const unsigned char* __restrict__ voxels,
+                                                      const uint32_t* __restrict__ n_work_ptr, const unsigned char* __restrict__ voxels,
                                                       uint8_t* __restrict__ labels, uint32_t* __restrict__ regions,
                                                       uint32_t* __restrict__ error_flag) {
     __shared__ __align__(16) uint8_t s_flags[4096];
@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
     __shared__ volatile uint16_t s_par[4096];
     __shared__ uint32_t s_counts[2];
     const int lane = threadIdx.x;
+    const uint32_t n_work = *n_work_ptr;  // written by the scan before this launch: no host round trip for the grid size
     for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
         const uint32_t chunk = work[w];
         const uint32_t slot = chunks[chunk].slot;
@@ -325,27 +326,6 @@ __global__ void __launch_bounds__(256) k_pack_labels(const DevChunk* __restrict_
 
 }  // namespace ivx
 
-// ---------------------------------------------------------------------------
-namespace {
-
-struct RegionForest {
-    std::vector<uint32_t>& parent;  // per region entry: GlobalRegionLabel of its parent
-    const std::vector<uint32_t>& first;
-    uint32_t entry(uint32_t label) const { return first[label >> 8] + (label & 255u); }
-    uint32_t find(uint32_t label) {
-        uint32_t r = label;
-        while (parent[entry(r)] != r) r = parent[entry(r)];
-        while (parent[entry(label)] != r) {
-            const uint32_t nx = parent[entry(label)];
-            parent[entry(label)] = r;
-            label = nx;
-        }
-        return r;
-    }
-};
-
-}  // namespace
-
 extern "C" {
 
 int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_split_info* out) {
@@ -357,15 +337,13 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
         IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "connected regions are resolved on whole objects (gather the slabs on one rank first)");
     const uint32_t n = obj->n_chunks;
     if (n == 0) {
-        obj->h_chunk_regions.clear();
-        obj->h_first_region.clear();
-        obj->h_region_roots.clear();
+        obj->region_total = 0;
         obj->split_valid = true;
         return IVX_OK;
     }
     if (n > (1u << 24)) IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "GlobalRegionLabel holds 24 bits of chunk index");
     cudaStream_t st = ctx->stream;
-    Tmp tmp(ctx);
+    const auto t_begin = std::chrono::steady_clock::now();
     if (obj->label_slots < obj->slot_capacity || !obj->d_labels) {
         ctx->release(obj->d_labels);
         obj->d_labels = static_cast<uint8_t*>(ctx->alloc(std::max<size_t>(1, (size_t)obj->slot_capacity) * 4096));
@@ -382,13 +360,16 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
         if (!obj->d_regions || !obj->d_label_stale) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "split detection: out of device memory");
         CU(ctx, cudaMemsetAsync(obj->d_label_stale, 1, n, st));  // nothing labelled yet
     }
-    uint32_t* regions = obj->d_regions;
-    uint32_t* flag = tmp.get<uint32_t>(n);
-    uint32_t* scan = tmp.get<uint32_t>(n);
-    uint32_t* work = tmp.get<uint32_t>(n);
-    if (!regions || !flag || !scan || !work) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "split detection: out of device memory");
-    uint32_t* counters = ctx->d_scratch + 32;  // [0] n_work [1] n_records [2] error
-    CU(ctx, cudaMemsetAsync(counters, 0, 16, st));
+    if (!obj->d_region_first) {
+        obj->d_region_first = static_cast<uint32_t*>(ctx->alloc((size_t)n * 4));
+        if (!obj->d_region_first) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "split detection: out of device memory");
+    }
+    // Capacities from the last resolve of this object where there was one; the kernels never write past them and report
+    // what they needed, so a guess that turns out too small costs one more pass, not a wrong answer.
+    uint32_t region_cap = std::max(obj->region_cap, n + 1024u);
+    uint32_t record_cap = obj->region_records ? obj->region_records + obj->region_records / 4u + 4096u : std::max<uint32_t>(4096u, 4u * n);
+    uint32_t* words = ctx->d_scratch + 64;  // RegionWord
+    uint32_t h[RW_COUNT];
 
     struct EventPair {  // destroyed on every exit path
         cudaEvent_t a = nullptr, b = nullptr;
@@ -401,172 +382,146 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
             if (b) cudaEventDestroy(b);
         }
     } ev;
-    const cudaEvent_t e0 = ev.a, e1 = ev.b;
-    cudaEventRecord(e0, st);
-    ctx->launches++;
-    k_init_regions<<<(n + 255) / 256, 256, 0, st>>>(obj->d_chunks, n, regions, obj->d_label_stale, flag);
-    CU(ctx, cudaGetLastError());
-    KL(ctx, launch_exclusive_scan(flag, scan, n, counters, st));
-    KL(ctx, launch_scatter_active(flag, scan, n, work, st));
-    uint32_t words[4];
-    if (int rc = ivx_read_words(ctx, counters, 3, words)) return rc;
-    const uint32_t n_work = words[0];
-    if (n_work) {
+    cudaEventRecord(ev.a, st);
+    int shared_optin = 0;
+    cudaDeviceGetAttribute(&shared_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    for (int attempt = 0;; ++attempt) {
+        if (attempt == 4) IVX_FAIL(ctx, IVX_ERR_CUDA, "split detection: capacities did not settle");
+        Tmp tmp(ctx);
+        if (obj->region_cap < region_cap || !obj->d_region_root) {
+            ctx->release(obj->d_region_root);
+            ctx->release(obj->d_region_label);
+            obj->d_region_root = static_cast<uint32_t*>(ctx->alloc((size_t)region_cap * 4));
+            obj->d_region_label = static_cast<uint32_t*>(ctx->alloc((size_t)region_cap * 4));
+            obj->region_cap = (obj->d_region_root && obj->d_region_label) ? region_cap : 0;
+            if (!obj->region_cap) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "split detection: out of device memory");
+        }
+        uint32_t slots = 1024;
+        while (slots < 2u * record_cap) slots <<= 1;
+        uint32_t* flag = tmp.get<uint32_t>(n);
+        uint32_t* scan = tmp.get<uint32_t>(n);
+        uint32_t* work = tmp.get<uint32_t>(n);
+        uint32_t* per_region = tmp.get<uint32_t>((size_t)region_cap * 6);   // lowest, tree, tree_number, tree_vertex, tree_root, tree_parent
+        uint32_t* zeroed = tmp.get<uint32_t>((size_t)region_cap * 4);       // degree, fresh_flag, event_count, event_cursor
+        uint32_t* event_offset = tmp.get<uint32_t>(region_cap);
+        uint2* records = tmp.get<uint2>(record_cap);
+        uint2* edges = tmp.get<uint2>(record_cap);
+        uint2* events = tmp.get<uint2>(record_cap);
+        unsigned long long* slot_keys = tmp.get<unsigned long long>(slots);
+        uint32_t* slot_values = tmp.get<uint32_t>(slots);
+        if (!flag || !scan || !work || !per_region || !zeroed || !event_offset || !records || !edges || !events || !slot_keys || !slot_values)
+            IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "split detection: out of device memory");
+        KL(ctx, launch_region_result_init(words, st));
+        CU(ctx, cudaMemsetAsync(zeroed, 0, (size_t)region_cap * 16, st));
+        CU(ctx, cudaMemsetAsync(slot_keys, 0xFF, (size_t)slots * 8, st));
+        CU(ctx, cudaMemsetAsync(slot_values, 0xFF, (size_t)slots * 4, st));
+
+        // chunk-local labels of the chunks modified since the last resolve
         ctx->launches++;
-        const uint32_t grid = std::min<uint32_t>(n_work, (uint32_t)ctx->sm_count * 13u);
-        k_local_regions<<<grid, 32, 0, st>>>(obj->d_chunks, work, n_work, obj->d_voxels, obj->d_labels, regions, counters + 2);
+        k_init_regions<<<(n + 255) / 256, 256, 0, st>>>(obj->d_chunks, n, obj->d_regions, obj->d_label_stale, flag);
         CU(ctx, cudaGetLastError());
-    }
-    // connection records: a few per face; grown and re-run if the first guess is too small
-    uint32_t capacity = std::max<uint32_t>(4096u, 4u * (n - 0u));
-    uint2* records = nullptr;
-    uint32_t n_records = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        records = tmp.get<uint2>(capacity);
-        if (!records) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "split detection: out of device memory");
-        CU(ctx, cudaMemsetAsync(counters + 1, 0, 4, st));
+        KL(ctx, launch_exclusive_scan(flag, scan, n, words + RW_WORK, st));
+        KL(ctx, launch_scatter_active(flag, scan, n, work, st));
+        ctx->launches++;
+        k_local_regions<<<std::min<uint32_t>(n, (uint32_t)ctx->sm_count * 13u), 32, 0, st>>>(
+            obj->d_chunks, work, words + RW_WORK, obj->d_voxels, obj->d_labels, obj->d_regions, words + RW_LABEL_ERROR);
+        CU(ctx, cudaGetLastError());
+        // connections across chunk faces
         ctx->launches++;
         k_region_connections<<<(n + CONN_WARPS - 1) / CONN_WARPS, CONN_WARPS * 32, 0, st>>>(
-            obj->d_chunks, n, make_uint3(obj->nb[0], obj->nb[1], obj->nb[2]), obj->d_labels, records, capacity, counters + 1,
-            counters + 2);
+            obj->d_chunks, n, make_uint3(obj->nb[0], obj->nb[1], obj->nb[2]), obj->d_labels, records, record_cap, words + RW_RECORDS,
+            words + RW_LABEL_ERROR);
         CU(ctx, cudaGetLastError());
-        if (attempt == 0) cudaEventRecord(e1, st);
-        if (int rc = ivx_read_words(ctx, counters, 3, words)) return rc;
-        n_records = words[1];
-        if (n_records <= capacity) break;
-        capacity = n_records;
+        // roots of the connected regions
+        RegionPass p{};
+        p.n = n;
+        p.stride0 = obj->nb[1] * obj->nb[2];
+        p.stride1 = obj->nb[2];
+        p.regions = obj->d_regions;
+        p.words = words;
+        p.cap = region_cap;
+        p.counts = flag;
+        p.first = obj->d_region_first;
+        p.label = obj->d_region_label;
+        p.root = obj->d_region_root;
+        p.lowest = per_region;
+        p.tree = per_region + (size_t)region_cap;
+        p.tree_number = per_region + (size_t)region_cap * 2;
+        p.tree_vertex = per_region + (size_t)region_cap * 3;
+        p.tree_root = per_region + (size_t)region_cap * 4;
+        p.tree_parent = per_region + (size_t)region_cap * 5;
+        p.degree = zeroed;
+        p.fresh_flag = zeroed + (size_t)region_cap;
+        p.event_count = zeroed + (size_t)region_cap * 2;
+        p.event_cursor = zeroed + (size_t)region_cap * 3;
+        p.event_offset = event_offset;
+        p.records = records;
+        p.record_cap = record_cap;
+        p.edges = edges;
+        p.events = events;
+        p.slot_keys = slot_keys;
+        p.slot_values = slot_values;
+        p.slot_mask = slots - 1u;
+        uint32_t launched = 0;
+        CU(ctx, launch_region_global_pass(p, region_cap, &launched, shared_optin, st));
+        ctx->launches += launched;
+        cudaEventRecord(ev.b, st);
+        if (int rc = ivx_read_words(ctx, words, RW_COUNT, h)) return rc;  // the one synchronisation of a resolve
+        if (h[RW_LABEL_ERROR] == 1u)
+            IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "a chunk has more than 254 connected regions (the reference asserts, split_detection.rs:798)");
+        if (h[RW_LABEL_ERROR] == 2u)
+            IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "a chunk face has more than %d distinct region connections", CONN_SEEN);
+        bool again = false;
+        if (h[RW_RECORDS] > record_cap) {
+            record_cap = h[RW_RECORDS] + h[RW_RECORDS] / 8u + 1024u;
+            again = true;
+        }
+        if (h[RW_TOTAL] > region_cap) {
+            region_cap = h[RW_TOTAL] + h[RW_TOTAL] / 4u + 1024u;
+            again = true;
+        }
+        if (h[RW_ERROR] == RERR_PAIR_TABLE_FULL) {
+            record_cap *= 2u;
+            again = true;
+        }
+        if (again) continue;
+        if (h[RW_ERROR] == RERR_TOO_MANY_CONNECTIONS)
+            IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "chunk %u region %u has %u adjacent regions, the reference keeps %u (split_detection.rs:1519-1546)",
+                     h[RW_ERROR_INFO], h[RW_ERROR_INFO + 1], h[RW_ERROR_INFO + 2], h[RW_ERROR_INFO + 3]);
+        if (h[RW_ERROR]) IVX_FAIL(ctx, IVX_ERR_CUDA, "split detection: unexpected error word %u", h[RW_ERROR]);
+        break;
     }
-    cudaEventSynchronize(e1);
-    cudaEventElapsedTime(&out->device_ms, e0, e1);
-    if (words[2] == 1u)
-        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "a chunk has more than 254 connected regions (the reference asserts, split_detection.rs:798)");
-    if (words[2] == 2u)
-        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "a chunk face has more than %d distinct region connections", CONN_SEEN);
+    cudaEventElapsedTime(&out->device_ms, ev.a, ev.b);
+    obj->region_total = h[RW_TOTAL];
+    obj->region_records = h[RW_RECORDS];
+    obj->region_two[0] = h[RW_FIRST_ROOT];
+    obj->region_two[1] = h[RW_SECOND_ROOT];
 
-    std::vector<uint32_t>& creg = obj->h_chunk_regions;
-    creg.resize(n);
-    // host scratch keeps its capacity across calls (a resolve per modification step: no page faults on MBs of vectors)
-    static thread_local std::vector<uint2> recs;
-    recs.resize(n_records);
-    CU(ctx, cudaMemcpyAsync(creg.data(), regions, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (n_records) CU(ctx, cudaMemcpyAsync(recs.data(), records, (size_t)n_records * sizeof(uint2), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaStreamSynchronize(st));
-
-    // ---- host: chunk-level union-find in the reference's visiting order ----
-    const auto t0 = std::chrono::steady_clock::now();
-    std::vector<uint32_t>& first = obj->h_first_region;
-    first.resize(n + 1);
-    uint32_t total = 0;
-    for (uint32_t c = 0; c < n; ++c) {
-        first[c] = total;
-        total += creg[c] & 255u;
-    }
-    first[n] = total;
-    static thread_local std::vector<uint32_t> parent, deg, start, adj, fill;
-    parent.resize(total);
-    for (uint32_t c = 0; c < n; ++c)
-        for (uint32_t r = 0; r < (creg[c] & 255u); ++r) parent[first[c] + r] = (c << 8) | r;
-    // adjacency in CSR form, both directions
-    const uint32_t stride[3] = {obj->nb[1] * obj->nb[2], obj->nb[2], 1u};
-    deg.assign(total + 1, 0);
-    for (const uint2& r : recs) {
-        const uint32_t c = r.x, d = r.y >> 16, la = (r.y >> 8) & 255u, lb = r.y & 255u, cu = c + stride[d];
-        deg[first[c] + la]++;
-        deg[first[cu] + lb]++;
-    }
-    start.assign(total + 1, 0);
-    for (uint32_t i = 0; i < total; ++i) start[i + 1] = start[i] + deg[i];
-    adj.resize(start[total]);
-    fill.assign(start.begin(), start.end() - 1);
-    for (const uint2& r : recs) {
-        const uint32_t c = r.x, d = r.y >> 16, la = (r.y >> 8) & 255u, lb = r.y & 255u, cu = c + stride[d];
-        adj[fill[first[c] + la]++] = (cu << 8) | lb;
-        adj[fill[first[cu] + lb]++] = (c << 8) | la;
-    }
-    // the reference gives each boundary region 256 / boundary_region_count connection slots (uniform chunks: 256)
-    for (uint32_t c = 0; c < n; ++c) {
-        const uint32_t kind = creg[c] >> 16, bc = (creg[c] >> 8) & 255u;
-        const uint32_t cap = kind == 1u ? 256u : 256u / std::max(1u, bc);
-        for (uint32_t r = 0; r < (creg[c] & 255u); ++r)
-            if (deg[first[c] + r] > cap)
-                IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "chunk %u region %u has %u adjacent regions, the reference keeps %u (split_detection.rs:1519-1546)",
-                         c, r, deg[first[c] + r], cap);
-    }
-    RegionForest F{parent, first};
-    uint32_t occ[3][2];
-    for (int d = 0; d < 3; ++d) {
-        occ[d][0] = obj->occ_voxels[d] / 16;
-        occ[d][1] = (obj->occ_voxels[3 + d] + 15) / 16;
-    }
-    const auto lin = [&](uint32_t i, uint32_t j, uint32_t k) { return (i * obj->nb[1] + j) * obj->nb[2] + k; };
-    for (uint32_t i = occ[0][0]; i < occ[0][1]; ++i)
-        for (uint32_t j = occ[1][0]; j < occ[1][1]; ++j)
-            for (uint32_t k = occ[2][0]; k < occ[2][1]; ++k) {
-                const uint32_t c = lin(i, j, k);
-                const uint32_t bc = (creg[c] >> 8) & 255u;
-                for (uint32_t r = 0; r < bc; ++r) {
-                    const uint32_t root = F.find((c << 8) | r);
-                    const uint32_t e = first[c] + r;
-                    for (uint32_t q = start[e]; q < start[e + 1]; ++q) {
-                        const uint32_t oroot = F.find(adj[q]);
-                        if (oroot != root) parent[F.entry(oroot)] = root;
-                    }
-                }
-            }
-    std::vector<uint32_t>& roots = obj->h_region_roots;
-    roots.resize(total);
-    for (uint32_t c = 0; c < n; ++c)
-        for (uint32_t r = 0; r < (creg[c] & 255u); ++r) roots[first[c] + r] = F.find((c << 8) | r);
-
-    // count_regions / find_two_disconnected_regions
-    uint32_t two[2] = {0, 0}, n_regions = 0;
-    for (uint32_t i = occ[0][0]; i < occ[0][1]; ++i)
-        for (uint32_t j = occ[1][0]; j < occ[1][1]; ++j)
-            for (uint32_t k = occ[2][0]; k < occ[2][1]; ++k) {
-                const uint32_t c = lin(i, j, k);
-                for (uint32_t r = 0; r < (creg[c] & 255u); ++r)
-                    if (roots[first[c] + r] == ((c << 8) | r)) {
-                        if (n_regions < 2) two[n_regions] = (c << 8) | r;
-                        n_regions++;
-                    }
-            }
-    out->n_regions = n_regions;
-    out->has_two = n_regions >= 2 ? 1u : 0u;
-    out->n_local_regions = total;
-    out->n_connections = n_records;
-    out->n_relabelled_chunks = n_work;
+    // count_regions / find_two_disconnected_regions (split_detection.rs:193-301) and the choice of
+    // extract_smallest_region (extraction.rs:121-281)
+    out->n_regions = h[RW_ROOTS];
+    out->has_two = h[RW_ROOTS] >= 2u ? 1u : 0u;
+    out->n_local_regions = h[RW_TOTAL];
+    out->n_connections = h[RW_RECORDS];
+    out->n_relabelled_chunks = h[RW_WORK];
     if (out->has_two) {
         for (int q = 0; q < 2; ++q) {
-            out->candidates[q].label = two[q];
-            for (int d = 0; d < 3; ++d) out->candidates[q].chunk_min[d] = 0xFFFFFFFFu;
+            ivx_region_candidate& cd = out->candidates[q];
+            const uint32_t* sw = h + RW_CANDIDATES + q * 8;
+            cd.label = h[RW_FIRST_LABEL + q];
+            cd.chunk_count = sw[0];
+            cd.non_uniform_chunk_count = sw[1];
+            for (int d = 0; d < 3; ++d) {
+                cd.chunk_min[d] = sw[2 + d];
+                cd.chunk_max[d] = sw[5 + d];
+            }
         }
-        for (uint32_t i = occ[0][0]; i < occ[0][1]; ++i)
-            for (uint32_t j = occ[1][0]; j < occ[1][1]; ++j)
-                for (uint32_t k = occ[2][0]; k < occ[2][1]; ++k) {
-                    const uint32_t c = lin(i, j, k);
-                    const uint32_t idx3[3] = {i, j, k};
-                    bool found[2] = {false, false};
-                    for (uint32_t r = 0; r < (creg[c] & 255u); ++r) {
-                        const uint32_t root = roots[first[c] + r];
-                        int q;
-                        if (root == two[0] && !found[0]) q = 0;
-                        else if (root == two[1] && !found[1]) q = 1;
-                        else continue;
-                        found[q] = true;
-                        ivx_region_candidate& cd = out->candidates[q];
-                        cd.chunk_count++;
-                        if ((creg[c] >> 16) == 2u) cd.non_uniform_chunk_count++;
-                        for (int d = 0; d < 3; ++d) {
-                            cd.chunk_min[d] = std::min(cd.chunk_min[d], idx3[d]);
-                            cd.chunk_max[d] = std::max(cd.chunk_max[d], idx3[d]);
-                        }
-                    }
-                }
         const ivx_region_candidate &a = out->candidates[0], &b = out->candidates[1];
         if (a.non_uniform_chunk_count != b.non_uniform_chunk_count) out->smallest = a.non_uniform_chunk_count < b.non_uniform_chunk_count ? 0u : 1u;
         else out->smallest = a.chunk_count < b.chunk_count ? 0u : 1u;
     }
-    out->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    // what the host spent around the device work (launches, the wait); there is no host-side pass over the regions
+    out->host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count() - out->device_ms;
     obj->split_valid = true;
     return IVX_OK;
 }
@@ -578,18 +533,26 @@ int ivx_object_split_detection_download(ivx_ctx* ctx, const ivx_object* obj, uin
     cudaSetDevice(ctx->device);
     if (!obj->split_valid) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "call ivx_object_resolve_connected_regions first");
     const uint32_t n = obj->n_chunks;
-    if (per_chunk) {
+    if (per_chunk && n) {
         if (chunk_capacity < n) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u chunk entries", n);
+        std::vector<uint32_t> creg(n), first(n);
+        CU(ctx, cudaMemcpyAsync(creg.data(), obj->d_regions, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(first.data(), obj->d_region_first, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
         for (uint32_t c = 0; c < n; ++c) {
-            per_chunk[c].region_count = (uint16_t)(obj->h_chunk_regions[c] & 255u);
-            per_chunk[c].boundary_region_count = (uint16_t)((obj->h_chunk_regions[c] >> 8) & 255u);
-            per_chunk[c].first_region = obj->h_first_region[c];
+            per_chunk[c].region_count = (uint16_t)(creg[c] & 255u);
+            per_chunk[c].boundary_region_count = (uint16_t)((creg[c] >> 8) & 255u);
+            per_chunk[c].first_region = first[c];
         }
     }
-    if (region_roots) {
-        if (region_capacity < obj->h_region_roots.size())
-            IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %zu region roots", obj->h_region_roots.size());
-        std::memcpy(region_roots, obj->h_region_roots.data(), obj->h_region_roots.size() * 4);
+    if (region_roots && obj->region_total) {
+        if (region_capacity < obj->region_total) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u region roots", obj->region_total);
+        Tmp tmp(ctx);
+        uint32_t* d_out = tmp.get<uint32_t>(obj->region_total);
+        if (!d_out) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "download: out of device memory");
+        KL(ctx, launch_region_root_labels(obj->d_region_root, obj->d_region_label, obj->region_total, d_out, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(region_roots, d_out, (size_t)obj->region_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (voxel_labels && n) {
         Tmp tmp(ctx);
