@@ -2027,6 +2027,7 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     aa.first_new_slot = obj->slots_used;
     aa.new_slot_ord = ord;
     aa.dirty = obj->d_dirty;
+    aa.label_stale = obj->d_label_stale;
     aa.stats = counters + 1;
     if (er) aa.mutual = er->mutual;
     if (upd) {
@@ -2061,7 +2062,7 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     if (!face_mask || !convert_flag || !need2 || !ord2 || !slot_of) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
     KL(ctx, launch_absorb_face_mask(obj->nb, b, face_mask, n, st));
     KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, face_mask, convert_flag, 0, obj->nb[0], st));
-    KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need2, st));
+    KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need2, obj->d_label_stale, st));
     KL(ctx, launch_exclusive_scan(need2, ord2, n, counters + 5, st));
     if (!roomy) {
         if (int rc = read_words(ctx, counters, 12, w)) return rc;
@@ -2073,15 +2074,6 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     // (only the chunk planes of the refreshed box can have work: the others are not even looked at)
     KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n,
                                   b.c0[0], std::min(obj->nb[0], r.c1[0] + 1u), persistent_grid(ctx, n, 8), st));
-    {
-        // region labels of the touched chunks and of any neighbour converted to non-uniform are stale (split.cu)
-        uint32_t lo3[3], hi3[3];
-        for (int d = 0; d < 3; ++d) {
-            lo3[d] = b.c0[d];
-            hi3[d] = r.c1[d] + 1;
-        }
-        KL(ctx, launch_mark_box(obj->d_label_stale, obj->nb, lo3, hi3, 1, st));
-    }
     // everything the host wants to know, in one read: slots handed out, statistics, invalidated chunks
     CU(ctx, cudaMemsetAsync(counters + 12, 0, 4, st));
     KL(ctx, launch_count_nonzero_u8(obj->d_dirty, n, counters + 12, st));
@@ -2130,7 +2122,7 @@ int refresh_boundaries(ivx_ctx* ctx, ivx_object* obj, const AbsorbRange* range) 
         IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "boundary refresh: out of device memory");
     if (range) KL(ctx, launch_absorb_face_mask(obj->nb, *range, face_mask, n, st));
     KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, face_mask, convert_flag, 0, obj->nb[0], st));
-    KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need, st));
+    KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need, obj->d_label_stale, st));
     KL(ctx, launch_exclusive_scan(need, ord, n, counters + 5, st));
     uint32_t w;
     if (int rc = read_words(ctx, counters + 5, 1, &w)) return rc;
@@ -2140,16 +2132,6 @@ int refresh_boundaries(ivx_ctx* ctx, ivx_object* obj, const AbsorbRange* range) 
     KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n,
                                   range ? range->c0[0] : 0u, range ? std::min(obj->nb[0], range->c1[0] + 1u) : obj->nb[0],
                                   persistent_grid(ctx, n, 8), st));
-    if (obj->d_label_stale) {
-        // a neighbour converted to non-uniform has no labels yet
-        uint32_t lo3[3] = {0, 0, 0}, hi3[3] = {obj->nb[0], obj->nb[1], obj->nb[2]};
-        if (range)
-            for (int d = 0; d < 3; ++d) {
-                lo3[d] = range->c0[d];
-                hi3[d] = std::min(obj->nb[d], range->c1[d] + 1);
-            }
-        KL(ctx, launch_mark_box(obj->d_label_stale, obj->nb, lo3, hi3, 1, st));
-    }
     return IVX_OK;
 }
 

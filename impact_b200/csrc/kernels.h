@@ -219,6 +219,8 @@ struct AbsorbArgs {
     uint32_t first_new_slot;
     const uint32_t* new_slot_ord;
     uint8_t* dirty;
+    uint8_t* label_stale;  // may be null: set for chunks whose region labels no longer hold (a voxel was emptied, or the
+                           // chunk was Uniform and has none yet)
     uint32_t* stats;  // touched chunks, touched voxels, emptied voxels, removed chunks
     // inertial-property update (null unless asked for): which voxels went from non-empty to empty, per chunk of the
     // range in its visiting order — 256 columns x 16 bits — and {count, voxel slot} per chunk
@@ -231,8 +233,9 @@ cudaError_t launch_absorb_plan(const DevChunk* chunks, const uint32_t nb[3], con
 cudaError_t launch_absorb_apply(const AbsorbArgs& a, uint32_t grid, cudaStream_t st);
 cudaError_t launch_absorb_face_mask(const uint32_t nb[3], const AbsorbRange& b, uint8_t* face_mask, uint32_t n,
                                     cudaStream_t st);
+// also marks the converted chunks' region labels stale (label_stale may be null)
 cudaError_t launch_need_slot_for_convert(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t n, uint32_t* need,
-                                         cudaStream_t st);
+                                         uint8_t* label_stale, cudaStream_t st);
 cudaError_t launch_count_nonzero_u8(const uint8_t* a, uint32_t n, uint32_t* out, cudaStream_t st);
 cudaError_t launch_assign_slots(const DevChunk* chunks, const uint32_t* need, const uint32_t* ord, uint32_t first,
                                 const uint32_t* first_extra,

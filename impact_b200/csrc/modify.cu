@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
             // convert_to_non_uniform_if_uniform: every uniform chunk of the touched range (intersection.rs:318-331)
             if (me.slot == 0xFFFFFFFFu) me.slot = a.first_new_slot + a.new_slot_ord[t];
             me.kind = 2;
+            if (tid == 0 && a.label_stale) a.label_stale[cidx] = 1;  // no region labels yet
             for (int q = 0; q < 6; ++q) me.face[q] = 1;
             me.flags = 0x3F;
             slot = a.voxels + (size_t)me.slot * SLOT_BYTES;
@@ -327,6 +328,8 @@ __global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
                 atomicAdd(&a.stats[1], s_cnt[6]);
                 atomicAdd(&a.stats[2], s_cnt[7]);
                 if (is_void) atomicAdd(&a.stats[3], 1u);
+                // region labels are a function of which voxels are empty
+                if (a.label_stale && s_cnt[7] != 0u) a.label_stale[cidx] = 1;
                 // invalidated meshes: this chunk and face neighbours whose border band was touched
                 a.dirty[cidx] = 1;
                 for (int d = 0; d < 3; ++d) {
@@ -377,10 +380,11 @@ __global__ void k_absorb_face_mask(uint3 nb, AbsorbRange b, uint8_t* __restrict_
 
 // slots for uniform chunks converted by the boundary refresh that have none reserved
 __global__ void k_need_slot_for_convert(const DevChunk* __restrict__ chunks, const uint32_t* __restrict__ convert_flag,
-                                        uint32_t n, uint32_t* __restrict__ need) {
+                                        uint32_t n, uint32_t* __restrict__ need, uint8_t* __restrict__ label_stale) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     need[c] = (convert_flag[c] && chunks[c].slot == 0xFFFFFFFFu) ? 1u : 0u;
+    if (label_stale && convert_flag[c]) label_stale[c] = 1;  // a chunk that becomes NonUniform has no region labels yet
 }
 // `first_extra`: slots handed out earlier in the same call whose number is only known on the device
 __global__ void k_assign_slots(const DevChunk* __restrict__ chunks, const uint32_t* __restrict__ need,
@@ -478,9 +482,9 @@ cudaError_t launch_absorb_face_mask(const uint32_t nb[3], const AbsorbRange& b, 
     return cudaGetLastError();
 }
 cudaError_t launch_need_slot_for_convert(const DevChunk* chunks, const uint32_t* convert_flag, uint32_t n, uint32_t* need,
-                                         cudaStream_t st) {
+                                         uint8_t* label_stale, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_need_slot_for_convert<<<(n + 255) / 256, 256, 0, st>>>(chunks, convert_flag, n, need);
+    k_need_slot_for_convert<<<(n + 255) / 256, 256, 0, st>>>(chunks, convert_flag, n, need, label_stale);
     return cudaGetLastError();
 }
 cudaError_t launch_assign_slots(const DevChunk* chunks, const uint32_t* need, const uint32_t* ord, uint32_t first,

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
     __shared__ __align__(16) uint8_t s_flags[4096];
     __shared__ __align__(16) uint8_t s_lab[4096];
     __shared__ volatile uint16_t s_par[4096];
+    __shared__ uint32_t s_seen[256];
     __shared__ uint32_t s_counts[2];
     const int lane = threadIdx.x;
     const uint32_t n_work = *n_work_ptr;  // written by the scan before this launch: no host round trip for the grid size
@@ -116,50 +117,172 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
             __syncwarp();
             continue;
         }
-        for (int idx = lane; idx < 4096; idx += 32) s_par[idx] = (uint16_t)idx;
-        __syncwarp();
         // ---- union pass (split_detection.rs:701-744) ----
-        // The reference visits the voxels in linear order; the visited voxel's root absorbs the roots of its
-        // upper x / y / z neighbours. Along a k-run of linked voxels every voxel therefore ends up under the
-        // root the run's FIRST voxel had when it was visited, and so do all upper neighbours of the run — in
-        // whatever order those merges happen. One run per step: lane 0 finds the run's root, then the lanes of
-        // the run's voxels merge their upper neighbours' sets under it concurrently (racing writes all store
-        // the same root; path compression only ever stores an ancestor).
-        for (uint32_t row = 0; row < 256u; ++row) {
-            const uint32_t f = lane < 16 ? (uint32_t)s_flags[row * 16u + lane] : 1u;
-            const uint32_t present = __ballot_sync(0xffffffffu, (f & 1u) == 0u) & 0xFFFFu;
-            if (present == 0u) continue;
-            // voxel k is linked to k + 1 when it is present and carries HAS_ADJACENT_Z_UP
-            const uint32_t link = __ballot_sync(0xffffffffu, (f & 1u) == 0u && (f & 0x80u) != 0u && lane < 15) & 0x7FFFu;
-            const uint32_t i = row >> 4, j = row & 15u;
-            uint32_t todo = present;
-            while (todo) {
-                const uint32_t k0 = (uint32_t)__ffs(todo) - 1u;
-                // the run [k0, k1]: extend while linked
-                uint32_t k1 = k0;
-                while (k1 < 15u && ((link >> k1) & 1u) && ((present >> (k1 + 1u)) & 1u)) ++k1;
-                const uint32_t run = ((2u << k1) - 1u) & ~((1u << k0) - 1u);
-                todo &= ~run;
-                uint32_t root = 0;
-                if (lane == 0) root = find_root_compress(s_par, row * 16u + k0);
-                root = __shfl_sync(0xffffffffu, root, 0);
-                __syncwarp();
-                if ((run >> lane) & 1u) {
-                    const uint32_t idx = row * 16u + (uint32_t)lane;
-                    if (i < 15u && (f & (1u << 5))) {
-                        const uint32_t r = find_root_compress(s_par, idx + 256u);
-                        if (r != root) s_par[r] = (uint16_t)root;
+        // The reference visits the voxels in linear order; the visited voxel's root absorbs the roots of its upper
+        // x / y / z neighbours. Which voxel ends up as the root of a region depends on that order — and the labels below
+        // depend on the roots — but the order only matters between a few sets (regions.cu has the argument for the
+        // chunk-level pass; it is the same rule): a voxel v with a linked LOWER neighbour joins the set of the lowest one,
+        // a(v), when that one is visited and stays with it, so chasing a() to a voxel without lower neighbours gives
+        // trees that are merged wholesale; only links between different trees can move a root, and they are replayed in
+        // visiting order by one lane. Voxels are taken 32 at a time in increasing order, so a(v) of earlier batches is
+        // already a tree root and the chase is two or three steps.
+        //   link u -> u + 256: u present and HAS_ADJACENT_X_UP; u -> u + 16: Y_UP; u -> u + 1: Z_UP and u + 1 present
+        uint16_t* s_events = reinterpret_cast<uint16_t*>(s_lab);  // (absorbing tree, absorbed tree) pairs; labels come later
+        constexpr uint32_t MAX_EVENTS = 1024;
+        for (uint32_t base = 0; base < 4096u; base += 32u) {
+            const uint32_t idx = base + (uint32_t)lane, vi = idx >> 8, vj = (idx >> 4) & 15u, vk = idx & 15u;
+            uint32_t a = idx;
+            if (vi > 0u) {
+                const uint32_t fu = s_flags[idx - 256u];
+                if ((fu & 1u) == 0u && (fu & 0x20u)) a = idx - 256u;
+            }
+            if (a == idx && vj > 0u) {
+                const uint32_t fu = s_flags[idx - 16u];
+                if ((fu & 1u) == 0u && (fu & 0x40u)) a = idx - 16u;
+            }
+            if (a == idx && vk > 0u && (s_flags[idx] & 1u) == 0u) {
+                const uint32_t fu = s_flags[idx - 1u];
+                if ((fu & 1u) == 0u && (fu & 0x80u)) a = idx - 1u;
+            }
+            s_par[idx] = (uint16_t)a;
+            __syncwarp();
+            uint32_t x = a, up;
+            while ((up = s_par[x]) != x) x = up;
+            __syncwarp();
+            s_par[idx] = (uint16_t)x;
+            __syncwarp();
+        }
+        // links between different trees, in visiting order. Most links repeat a pair of trees that an earlier link has
+        // already brought together, and a repeated pair is a no-op in the replay (a dropped FIRST occurrence would not
+        // be). Two filters: (1) if v and its upper neighbour w both hang below the voxels one step down the same axis
+        // (a(v) = v - s, a(w) = w - s) and v - s is linked to w - s in the same direction, that earlier link has the
+        // same two trees — rods of voxels growing side by side from a surface produce one link per rod pair instead of
+        // one per voxel pair; (2) a small direct-mapped memory of recent pairs (look first, note after the batch).
+        const auto lowest_step = [&](uint32_t idx) -> uint32_t {  // idx - a(idx)
+            const uint32_t vi = idx >> 8, vj = (idx >> 4) & 15u, vk = idx & 15u;
+            if (vi > 0u) {
+                const uint32_t fu = s_flags[idx - 256u];
+                if ((fu & 1u) == 0u && (fu & 0x20u)) return 256u;
+            }
+            if (vj > 0u) {
+                const uint32_t fu = s_flags[idx - 16u];
+                if ((fu & 1u) == 0u && (fu & 0x40u)) return 16u;
+            }
+            if (vk > 0u && (s_flags[idx] & 1u) == 0u) {
+                const uint32_t fu = s_flags[idx - 1u];
+                if ((fu & 1u) == 0u && (fu & 0x80u)) return 1u;
+            }
+            return 0u;
+        };
+        for (int t = lane; t < 256; t += 32) s_seen[t] = 0xFFFFFFFFu;
+        __syncwarp();
+        uint32_t n_events = 0;
+        bool overflow = false;
+        for (uint32_t base = 0; base < 4096u; base += 32u) {
+            const uint32_t idx = base + (uint32_t)lane, vi = idx >> 8, vj = (idx >> 4) & 15u, vk = idx & 15u;
+            const uint32_t f = s_flags[idx];
+            uint32_t other[3], keys[3], count = 0;
+            if ((f & 1u) == 0u) {
+                const uint32_t mine = s_par[idx];
+                const uint32_t w3[3] = {idx + 256u, idx + 16u, idx + 1u};
+                const uint32_t bit3[3] = {0x20u, 0x40u, 0x80u};
+                const bool linked[3] = {vi < 15u && (f & 0x20u) != 0u, vj < 15u && (f & 0x40u) != 0u,
+                                        vk < 15u && (f & 0x80u) != 0u && (s_flags[(idx + 1u) & 4095u] & 1u) == 0u};
+                uint32_t my_step = 0xFFFFFFFFu;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    if (!linked[d]) continue;
+                    const uint32_t theirs = s_par[w3[d]];
+                    if (theirs == mine) continue;
+                    if (my_step == 0xFFFFFFFFu) my_step = lowest_step(idx);
+                    if (my_step != 0u && my_step != (w3[d] - idx) && lowest_step(w3[d]) == my_step) {
+                        // the voxels one step down: is v - s linked to w - s the same way?
+                        const uint32_t fl = s_flags[idx - my_step];
+                        const bool lower_link = (fl & bit3[d]) != 0u && (d != 2 || (s_flags[w3[d] - my_step] & 1u) == 0u);
+                        if (lower_link) continue;
                     }
-                    if (j < 15u && (f & (1u << 6))) {
-                        const uint32_t r = find_root_compress(s_par, idx + 16u);
-                        if (r != root) s_par[r] = (uint16_t)root;
-                    }
-                    if ((link >> lane) & 1u) {
-                        const uint32_t r = find_root_compress(s_par, idx + 1u);
-                        if (r != root) s_par[r] = (uint16_t)root;
-                    }
+                    const uint32_t key = (min(mine, theirs) << 12) | max(mine, theirs);
+                    if (s_seen[(key * 0x9E3779B1u) >> 24] == key) continue;
+                    other[count] = theirs;
+                    keys[count] = key;
+                    count++;
                 }
-                __syncwarp();
+            }
+            __syncwarp();
+            for (uint32_t q = 0; q < count; ++q) s_seen[(keys[q] * 0x9E3779B1u) >> 24] = keys[q];
+            uint32_t offset = count;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, offset, d);
+                if (lane >= d) offset += y;
+            }
+            const uint32_t batch = __shfl_sync(0xffffffffu, offset, 31);
+            offset -= count;
+            if (n_events + batch > MAX_EVENTS) {
+                overflow = true;
+                break;
+            }
+            for (uint32_t q = 0; q < count; ++q) {
+                s_events[2u * (n_events + offset + q)] = (uint16_t)s_par[idx];
+                s_events[2u * (n_events + offset + q) + 1u] = (uint16_t)other[q];
+            }
+            n_events += batch;
+            __syncwarp();
+        }
+        if (!overflow) {
+            __syncwarp();
+            if (lane == 0) {
+                for (uint32_t e = 0; e < n_events; ++e) {
+                    const uint32_t ra = find_root_compress(s_par, s_events[2u * e]);
+                    const uint32_t rb = find_root_compress(s_par, s_events[2u * e + 1u]);
+                    if (ra != rb) s_par[rb] = (uint16_t)ra;
+                }
+            }
+            __syncwarp();
+        } else {
+            // more links between trees than the list holds (a very ragged chunk): the reference's sequence, one k-run of
+            // linked voxels per step — lane 0 finds the run's root, the lanes of the run's voxels merge their upper
+            // neighbours' sets under it concurrently (racing writes all store the same root; path compression only ever
+            // stores an ancestor)
+            __syncwarp();
+            for (int idx = lane; idx < 4096; idx += 32) s_par[idx] = (uint16_t)idx;
+            __syncwarp();
+            for (uint32_t row = 0; row < 256u; ++row) {
+                const uint32_t f = lane < 16 ? (uint32_t)s_flags[row * 16u + lane] : 1u;
+                const uint32_t present = __ballot_sync(0xffffffffu, (f & 1u) == 0u) & 0xFFFFu;
+                if (present == 0u) continue;
+                // voxel k is linked to k + 1 when it is present and carries HAS_ADJACENT_Z_UP
+                const uint32_t link = __ballot_sync(0xffffffffu, (f & 1u) == 0u && (f & 0x80u) != 0u && lane < 15) & 0x7FFFu;
+                const uint32_t i = row >> 4, j = row & 15u;
+                uint32_t todo = present;
+                while (todo) {
+                    const uint32_t k0 = (uint32_t)__ffs(todo) - 1u;
+                    // the run [k0, k1]: extend while linked
+                    uint32_t k1 = k0;
+                    while (k1 < 15u && ((link >> k1) & 1u) && ((present >> (k1 + 1u)) & 1u)) ++k1;
+                    const uint32_t run = ((2u << k1) - 1u) & ~((1u << k0) - 1u);
+                    todo &= ~run;
+                    uint32_t root = 0;
+                    if (lane == 0) root = find_root_compress(s_par, row * 16u + k0);
+                    root = __shfl_sync(0xffffffffu, root, 0);
+                    __syncwarp();
+                    if ((run >> lane) & 1u) {
+                        const uint32_t idx = row * 16u + (uint32_t)lane;
+                        if (i < 15u && (f & (1u << 5))) {
+                            const uint32_t r = find_root_compress(s_par, idx + 256u);
+                            if (r != root) s_par[r] = (uint16_t)root;
+                        }
+                        if (j < 15u && (f & (1u << 6))) {
+                            const uint32_t r = find_root_compress(s_par, idx + 16u);
+                            if (r != root) s_par[r] = (uint16_t)root;
+                        }
+                        if ((link >> lane) & 1u) {
+                            const uint32_t r = find_root_compress(s_par, idx + 1u);
+                            if (r != root) s_par[r] = (uint16_t)root;
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
         // ---- representative voxels of boundary regions, in the reference's face order (:760-796) ----
@@ -345,14 +468,17 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
     cudaStream_t st = ctx->stream;
     const auto t_begin = std::chrono::steady_clock::now();
     if (obj->label_slots < obj->slot_capacity || !obj->d_labels) {
+        // the voxel storage grew (chunks converted to NonUniform took new slots): the labels move along; the new slots
+        // belong to chunks that were marked stale when they were converted
+        uint8_t* grown = static_cast<uint8_t*>(ctx->alloc(std::max<size_t>(1, (size_t)obj->slot_capacity) * 4096));
+        if (!grown) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "region labels (%u chunks): out of device memory", obj->slot_capacity);
+        if (obj->d_labels && obj->label_slots)
+            CU(ctx, cudaMemcpyAsync(grown, obj->d_labels, (size_t)obj->label_slots * 4096, cudaMemcpyDeviceToDevice, st));
+        else if (obj->d_label_stale)
+            CU(ctx, cudaMemsetAsync(obj->d_label_stale, 1, n, st));  // no labels at all yet
         ctx->release(obj->d_labels);
-        obj->d_labels = static_cast<uint8_t*>(ctx->alloc(std::max<size_t>(1, (size_t)obj->slot_capacity) * 4096));
-        if (!obj->d_labels) {
-            obj->label_slots = 0;
-            IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "region labels (%u chunks): out of device memory", obj->slot_capacity);
-        }
+        obj->d_labels = grown;
         obj->label_slots = obj->slot_capacity;
-        if (obj->d_label_stale) CU(ctx, cudaMemsetAsync(obj->d_label_stale, 1, n, st));  // the new buffer holds no labels
     }
     if (!obj->d_regions) {
         obj->d_regions = static_cast<uint32_t*>(ctx->alloc((size_t)n * 4));
