@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_surface_voxels_in_ranges", "ivx_object_surface_voxels_touching_sphere", "ivx_object_surface_voxels_touching_capsule",
     "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane", "ivx_object_sphere_contacts", "ivx_object_plane_contacts", "ivx_object_capsule_contacts",
     "ivx_comm_create", "ivx_comm_connect", "ivx_comm_connect_local", "ivx_comm_destroy", "ivx_object_exchange_halos",
-    "ivx_object_mesh_gather", "ivx_object_mesh_sync", "ivx_mesh_modifications", "ivx_mesh_report_synchronized",
+    "ivx_object_mesh_gather", "ivx_object_mesh_sync", "ivx_mesh_modifications", "ivx_mesh_report_synchronized", "ivx_object_collision_probes", "ivx_object_collision_probes_sync", "ivx_collision_probes_download",
 ]
 
 
@@ -65,6 +65,14 @@ class MeshInfo(C.Structure):
 class CommConfig(C.Structure):
     _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("gather_rank", C.c_uint32), ("plane_chunks", C.c_uint32),
                 ("mesh_vertices", C.c_uint64), ("mesh_indices", C.c_uint64), ("mesh_submeshes", C.c_uint64)]
+
+
+class ProbesInfo(C.Structure):
+    _fields_ = [("log2_block_size", C.c_uint32), ("_pad", C.c_uint32), ("n_points", C.c_uint64), ("n_chunks", C.c_uint64),
+                ("d_points", C.c_void_p)]
+
+
+PROBE_RANGE_DTYPE = np.dtype([("chunk_indices", "<u4", (3,)), ("point_start", "<u4"), ("point_end", "<u4")])
 
 
 class MetaSource(C.Structure):

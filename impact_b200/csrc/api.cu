@@ -1664,6 +1664,7 @@ void ivx_object_free(ivx_ctx* ctx, ivx_object* obj) {
     ctx->release(obj->d_label_stale);
     ctx->release(obj->d_region_first);
     ctx->release(obj->d_region_label);
+    ivx_probes_free(ctx, obj->probes);
     ctx->release(obj->d_region_root);
     delete obj;
 }

@@ -134,6 +134,9 @@ struct ivx_program {
 
 struct ivx_mesh_sync;  // mesh_sync.cu: the host-side ChunkSubmeshManager of a mesh that is kept in sync
 void ivx_mesh_sync_free(ivx_mesh_sync* s);
+struct ivx_probes;     // probes.cu: collision probes beside the mesh
+struct ivx_ctx;
+void ivx_probes_free(ivx_ctx* ctx, ivx_probes* p);
 
 struct DeviceMesh {
     uint32_t n_vertices = 0, n_indices = 0, n_submeshes = 0, n_work = 0;
@@ -162,6 +165,7 @@ struct ivx_object {
     uint32_t n_void = 0, n_uniform = 0, n_non_uniform = 0;
     DeviceMesh mesh;
     ivx_mesh_sync* sync = nullptr;  // set by ivx_object_mesh_sync
+    ivx_probes* probes = nullptr;   // set by ivx_object_collision_probes
     bool mesh_is_patch = false;     // `mesh` holds the patch of ivx_object_remesh_dirty, not the object's mesh
     uint64_t plan_serial = 0;  // GenPlan this object was generated with; 0 once the object has been modified
     // slab protocol (multi-GPU): derived state is pending until the halo planes are imported

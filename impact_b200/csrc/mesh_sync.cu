@@ -12,61 +12,11 @@
 //
 // The reference walks a HashSet of invalidated chunks, i.e. in no defined order; this implementation walks them in
 // ascending linear chunk index, which is one of the orders the reference may take.
-#include <unordered_map>
-
-#include "api_internal.cuh"
-
-struct ivx_mesh_sync {
-    // KeyIndexMapper<[usize; 3]>: table row of a chunk (by linear chunk index) and the chunk of a row
-    std::unordered_map<uint32_t, uint32_t> row_of_chunk;
-    std::vector<uint32_t> chunk_of_row;
-    std::vector<ivx_chunk_submesh> submeshes;  // chunk_submeshes
-    std::vector<uint32_t> vertex_ranges;       // chunk_vertex_ranges, 2 words per row
-    // RangeAllocator x 2: free ranges [first, second) sorted by start
-    std::vector<std::pair<uint32_t, uint32_t>> free_vertices, free_indices;
-    std::vector<uint32_t> updated;  // ChunkSubmeshDataRanges: vertex start, end, index start, end
-    bool chunks_were_removed = false;
-    uint32_t n_vertices = 0, n_indices = 0;  // lengths of the buffers (holes included)
-    std::vector<uint32_t> touched_rows;      // rows written or moved by the current sync (for the device mirror)
-};
+#include "mesh_sync.cuh"
 
 namespace {
 
-using Ranges = std::vector<std::pair<uint32_t, uint32_t>>;
-
-// RangeAllocator::free_range: a range whose start is already free stays as it is (BTreeSet::insert)
-void release_range(Ranges& fr, uint32_t a, uint32_t b) {
-    if (a >= b) return;
-    auto it = std::lower_bound(fr.begin(), fr.end(), a, [](const std::pair<uint32_t, uint32_t>& r, uint32_t v) { return r.first < v; });
-    if (it != fr.end() && it->first == a) return;
-    fr.insert(it, {a, b});
-}
-// RangeAllocator::allocate_range: the smallest free range that fits (the lowest one of equals), its tail stays free
-bool take_range(Ranges& fr, uint32_t len, uint32_t& start) {
-    size_t best = fr.size();
-    uint32_t best_len = 0xFFFFFFFFu;
-    for (size_t q = 0; q < fr.size(); ++q) {
-        const uint32_t l = fr[q].second - fr[q].first;
-        if (l >= len && l < best_len) {
-            best = q;
-            best_len = l;
-        }
-    }
-    if (best == fr.size()) return false;
-    start = fr[best].first;
-    if (best_len == len) fr.erase(fr.begin() + best);
-    else fr[best].first += len;
-    return true;
-}
-// RangeAllocator::merge_consecutive_ranges
-void coalesce(Ranges& fr) {
-    size_t w = 0;
-    for (size_t q = 0; q < fr.size(); ++q) {
-        if (w > 0 && fr[w - 1].second == fr[q].first) fr[w - 1].second = fr[q].second;
-        else fr[w++] = fr[q];
-    }
-    fr.resize(w);
-}
+using namespace ivx_ranges;
 
 // remove_chunk_if_present (mesh.rs:814-826): swap-remove of the row, its ranges become free
 void drop_chunk(ivx_mesh_sync& s, uint32_t chunk) {
@@ -185,6 +135,7 @@ int ivx_object_mesh_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
         fill_mesh_info_from(m, out);
         return IVX_OK;
     };
+    s.last_dirty.clear();
     if (n_dirty == 0) return finish();
     std::vector<uint32_t> h_dirty(n_dirty), h_work(n_work), h_vc(n_work), h_ic(n_work);
     uint32_t* vcount = tmp.get<uint32_t>(std::max(1u, n_work));
@@ -218,6 +169,7 @@ int ivx_object_mesh_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
     }
     CU(ctx, cudaStreamSynchronize(st));
 
+    s.last_dirty = h_dirty;
     // ---- placement, chunk by chunk (write_chunk / remove_chunk_if_present, mesh.rs:749-826) ----
     std::vector<uint32_t> h_voff(n_work, 0u), h_ioff(n_work, 0u), row_of_work(n_work, 0xFFFFFFFFu);
     size_t w = 0;

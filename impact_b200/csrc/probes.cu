@@ -1,0 +1,393 @@
+// Collision probes of a meshed voxel object (sm_100a): `VoxelObjectCollisionProbes` (collidable.rs:97-101, 346-780) —
+// per meshed chunk and per block of 1^3 .. 8^3 voxels, the mesh vertex with the lowest (most convex) curvature; the
+// points the physics uses to probe other objects. `MeshedVoxelObject::create` computes them for all chunks right after
+// the mesh, `sync_mesh_with_object` for the invalidated chunks right after the mesh sync (mesh.rs:156-205).
+//
+//   k_probe_points   one CTA per chunk submesh. The reference walks the triangles in index order and adds a curvature
+//                    sample (normal . outgoing edge - normal . incoming edge) to each of the three vertices; f32 sums
+//                    depend on that order, so every thread takes ONE vertex and walks the chunk's triangles in order
+//                    (the index loads are the same address for the whole warp: one broadcast per triangle). The block a
+//                    vertex falls in keeps the vertex with the smallest mean curvature, the first one of equals:
+//                    atomicMin on (ordered curvature bits << 32 | vertex) in shared memory. The survivors are written in
+//                    block order to a scratch row of the chunk.
+//   placement        on the host from the per-chunk point counts: all chunks in submesh order (recompute_for_all_chunks),
+//                    or, after a mesh sync, the invalidated chunks through the reference's RangeAllocator (smallest free
+//                    range that fits, else the end) — the same code the synced mesh uses.
+//   k_probe_scatter  scratch rows → their places in the persistent point buffer.
+#include "mesh_sync.cuh"
+
+struct ivx_probes {
+    std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> range_of_chunk;  // chunk_point_ranges by linear chunk index
+    ivx_ranges::Ranges free_points;                                                // point_range_allocator
+    uint32_t n_points = 0;    // length of the point buffer (holes included)
+    uint32_t cap_points = 0;
+    float* d_points = nullptr;
+    uint32_t log2_block_size = 3;
+};
+
+void ivx_probes_free(ivx_ctx* ctx, ivx_probes* p) {
+    if (!p) return;
+    ctx->release(p->d_points);
+    delete p;
+}
+
+namespace {
+
+using namespace ivx_ranges;
+
+struct ProbeArgs {
+    const float* positions;
+    const float* normals;
+    const uint32_t* indices;
+    const ivx_chunk_submesh* submeshes;
+    const uint32_t* vertex_ranges;
+    const uint32_t* rows;  // submesh rows to work on (null: all of them)
+    uint32_t n_items;
+    uint32_t log2_block_size;
+    float inverse_voxel_extent;
+    uint32_t nb1, nb2;
+    float* scratch_points;  // n_items x blocks-per-chunk x 3
+    uint32_t* counts;       // per item: points
+    uint32_t* chunk_of;     // per item: linear chunk index
+};
+
+constexpr int PROBE_THREADS = 128;
+
+__device__ __forceinline__ uint32_t ordered_bits(float f) {  // monotonic in f; -0 == +0
+    uint32_t u = __float_as_uint(f == 0.0f ? 0.0f : f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(PROBE_THREADS) k_probe_points(ProbeArgs a) {
+    extern __shared__ unsigned long long s_best[];  // per block of the chunk: ordered curvature << 32 | vertex
+    __shared__ uint32_t s_warp[PROBE_THREADS / 32];
+    __shared__ uint32_t s_base;
+    const uint32_t log2_blocks = 4u - a.log2_block_size, n_blocks = 1u << (3u * log2_blocks);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        const uint32_t row = a.rows ? a.rows[item] : item;
+        const ivx_chunk_submesh sm = a.submeshes[row];
+        const uint32_t v0 = a.vertex_ranges[2 * (size_t)row], v1 = a.vertex_ranges[2 * (size_t)row + 1];
+        const uint32_t n_vertices = v1 - v0, n_triangles = sm.index_count / 3u;
+        const uint32_t* idx = a.indices + sm.index_offset;
+        for (uint32_t b = tid; b < n_blocks; b += PROBE_THREADS) s_best[b] = ~0ull;
+        __syncthreads();
+        float lower[3], upper[3];
+        for (int d = 0; d < 3; ++d) {
+            lower[d] = (float)(sm.chunk_indices[d] * 16u);
+            upper[d] = (float)((sm.chunk_indices[d] + 1u) * 16u);
+        }
+        for (uint32_t v = tid; v < n_vertices; v += PROBE_THREADS) {
+            const uint32_t me = v0 + v;
+            const float px = a.positions[3 * (size_t)me], py = a.positions[3 * (size_t)me + 1], pz = a.positions[3 * (size_t)me + 2];
+            const float nx = a.normals[3 * (size_t)me], ny = a.normals[3 * (size_t)me + 1], nz = a.normals[3 * (size_t)me + 2];
+            float sum = 0.0f, count = 0.0f;
+            for (uint32_t t = 0; t < n_triangles; ++t) {
+                const uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
+                if (i0 != me && i1 != me && i2 != me) continue;
+                // corner c of the triangle: outgoing edge to corner c + 1, incoming edge from corner c - 1
+                const uint32_t tri[3] = {i0, i1, i2};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (tri[c] != me) continue;
+                    const uint32_t nxt = tri[(c + 1) % 3], prv = tri[(c + 2) % 3];
+                    const float ox = a.positions[3 * (size_t)nxt] - px, oy = a.positions[3 * (size_t)nxt + 1] - py,
+                                oz = a.positions[3 * (size_t)nxt + 2] - pz;  // edge c -> c + 1
+                    const float ix = px - a.positions[3 * (size_t)prv], iy = py - a.positions[3 * (size_t)prv + 1],
+                                iz = pz - a.positions[3 * (size_t)prv + 2];  // edge c - 1 -> c
+                    const float out_dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, ox), __fmul_rn(ny, oy)), __fmul_rn(nz, oz));
+                    const float in_dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, ix), __fmul_rn(ny, iy)), __fmul_rn(nz, iz));
+                    sum = __fadd_rn(sum, __fsub_rn(out_dot, in_dot));
+                    count += 2.0f;
+                }
+            }
+            if (count == 0.0f) continue;  // a vertex no triangle of the chunk uses
+            uint32_t block[3];
+            const float p3[3] = {px, py, pz};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float norm = __fmul_rn(p3[d], a.inverse_voxel_extent);
+                const float clamped = fminf(fmaxf(norm, lower[d]), upper[d]);
+                const uint32_t voxel = (uint32_t)clamped;  // `as usize`
+                block[d] = (voxel & 15u) >> a.log2_block_size;  // clamped to the upper face: block 0, like the reference
+            }
+            const uint32_t b = (block[0] << (2u * log2_blocks)) + (block[1] << log2_blocks) + block[2];
+            const float curvature = __fdiv_rn(sum, count);
+            if (!(curvature < INFINITY)) continue;  // `curvature < min_curvature` never holds for these
+            atomicMin(&s_best[b], ((unsigned long long)ordered_bits(curvature) << 32) | v);
+        }
+        __syncthreads();
+        // the blocks that have a vertex, in block order
+        float* out = a.scratch_points + (size_t)item * n_blocks * 3;
+        if (tid == 0) s_base = 0;
+        __syncthreads();
+        for (uint32_t b0 = 0; b0 < n_blocks; b0 += PROBE_THREADS) {
+            const uint32_t b = b0 + tid;
+            const unsigned long long key = b < n_blocks ? s_best[b] : ~0ull;
+            const bool has = key != ~0ull;
+            const uint32_t ballot = __ballot_sync(0xffffffffu, has);
+            if (lane == 0) s_warp[warp] = __popc(ballot);
+            __syncthreads();
+            uint32_t before = s_base;
+            for (int w = 0; w < warp; ++w) before += s_warp[w];
+            if (has) {
+                const uint32_t at = before + __popc(ballot & ((1u << lane) - 1u));
+                const uint32_t me = v0 + (uint32_t)(key & 0xFFFFFFFFull);
+                out[3 * at] = a.positions[3 * (size_t)me];
+                out[3 * at + 1] = a.positions[3 * (size_t)me + 1];
+                out[3 * at + 2] = a.positions[3 * (size_t)me + 2];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t all = 0;
+                for (int w = 0; w < PROBE_THREADS / 32; ++w) all += s_warp[w];
+                s_base += all;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            a.counts[item] = s_base;
+            a.chunk_of[item] = (sm.chunk_indices[0] * a.nb1 + sm.chunk_indices[1]) * a.nb2 + sm.chunk_indices[2];
+        }
+        __syncthreads();
+    }
+}
+
+// scratch rows → the point buffer; offsets[item] = 0xFFFFFFFF: nothing to copy
+__global__ void k_probe_scatter(const float* __restrict__ scratch, const uint32_t* __restrict__ counts,
+                                const uint32_t* __restrict__ offsets, uint32_t n_items, uint32_t blocks_per_chunk,
+                                float* __restrict__ points) {
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t off = offsets[item];
+        if (off == 0xFFFFFFFFu) continue;
+        const uint32_t words = counts[item] * 3u;
+        const float* src = scratch + (size_t)item * blocks_per_chunk * 3;
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) points[3 * (size_t)off + w] = src[w];
+    }
+}
+
+int ensure_points(ivx_ctx* ctx, ivx_probes& pr, uint32_t keep, uint32_t want) {
+    if (want <= pr.cap_points && pr.d_points) return IVX_OK;
+    const uint32_t cap = want + want / 4 + 64;
+    float* grown = static_cast<float*>(ctx->alloc((size_t)cap * 12));
+    if (!grown) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "collision probes: out of device memory");
+    if (pr.d_points && keep) CU(ctx, cudaMemcpyAsync(grown, pr.d_points, (size_t)keep * 12, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->release(pr.d_points);
+    pr.d_points = grown;
+    pr.cap_points = cap;
+    return IVX_OK;
+}
+
+// determine_log2_block_size_for_object (collidable.rs:451-471)
+uint32_t log2_block_size_for(const ivx_object* obj) {
+    uint32_t min_extent = 0xFFFFFFFFu;
+    for (int d = 0; d < 3; ++d) min_extent = std::min(min_extent, obj->occ_voxels[3 + d] - obj->occ_voxels[d]);
+    return min_extent >= 16u ? 3u : (min_extent >= 8u ? 2u : (min_extent >= 4u ? 1u : 0u));
+}
+
+// runs k_probe_points over `rows` (null: all submeshes) and brings the counts back
+int probe_items(ivx_ctx* ctx, ivx_object* obj, const uint32_t* d_rows, uint32_t n_items, uint32_t log2_bs, Tmp& tmp, float*& scratch,
+                uint32_t*& d_counts, std::vector<uint32_t>& counts, std::vector<uint32_t>& chunk_of) {
+    const DeviceMesh& m = obj->mesh;
+    const uint32_t blocks_per_chunk = 1u << (3u * (4u - log2_bs));
+    scratch = tmp.get<float>((size_t)n_items * blocks_per_chunk * 3);
+    d_counts = tmp.get<uint32_t>(2 * (size_t)n_items);
+    if (!scratch || !d_counts) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "collision probes: out of device memory");
+    ProbeArgs a{};
+    a.positions = m.positions;
+    a.normals = m.normals;
+    a.indices = m.indices;
+    a.submeshes = m.submeshes;
+    a.vertex_ranges = m.vertex_ranges;
+    a.rows = d_rows;
+    a.n_items = n_items;
+    a.log2_block_size = log2_bs;
+    a.inverse_voxel_extent = 1.0f / obj->voxel_extent;
+    a.nb1 = obj->nb[1];
+    a.nb2 = obj->nb[2];
+    a.scratch_points = scratch;
+    a.counts = d_counts;
+    a.chunk_of = d_counts + n_items;
+    const size_t smem = (size_t)blocks_per_chunk * 8;
+    CU(ctx, cudaFuncSetAttribute(k_probe_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->launches++;
+    k_probe_points<<<ivx_persistent_grid(ctx, n_items, 8), PROBE_THREADS, smem, ctx->stream>>>(a);
+    CU(ctx, cudaGetLastError());
+    counts.resize(n_items);
+    chunk_of.resize(n_items);
+    CU(ctx, cudaMemcpyAsync(counts.data(), d_counts, (size_t)n_items * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(chunk_of.data(), d_counts + n_items, (size_t)n_items * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IVX_OK;
+}
+
+int scatter_items(ivx_ctx* ctx, ivx_probes& pr, const float* scratch, const uint32_t* d_counts, const std::vector<uint32_t>& offsets,
+                  uint32_t log2_bs, Tmp& tmp) {
+    const uint32_t n_items = (uint32_t)offsets.size();
+    if (n_items == 0) return IVX_OK;
+    uint32_t* d_off = tmp.get<uint32_t>(n_items);
+    if (!d_off) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "collision probes: out of device memory");
+    CU(ctx, cudaMemcpyAsync(d_off, offsets.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches++;
+    k_probe_scatter<<<ivx_persistent_grid(ctx, n_items, 8), 64, 0, ctx->stream>>>(scratch, d_counts, d_off, n_items,
+                                                                                1u << (3u * (4u - log2_bs)), pr.d_points);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // `offsets` is the caller's
+    return IVX_OK;
+}
+
+void fill_info(const ivx_probes& pr, ivx_probes_info* out) {
+    out->log2_block_size = pr.log2_block_size;
+    out->n_points = pr.n_points;
+    out->n_chunks = pr.range_of_chunk.size();
+    out->d_points = pr.d_points;
+}
+
+int check_object(ivx_ctx* ctx, const ivx_object* obj) {
+    if (obj->derive_pending || obj->first_i != 0 || obj->nb[0] != obj->chunk_counts[0])
+        IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "collision probes are kept for whole objects");
+    if (obj->mesh_is_patch || !obj->mesh.positions)
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "the object has no mesh: call ivx_object_mesh first (ivx_object_remesh_dirty "
+                 "replaces the mesh by a patch)");
+    return IVX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ivx_object_collision_probes(ivx_ctx* ctx, ivx_object* obj, ivx_probes_info* out) {
+    if (!ctx || !obj || !out) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    std::memset(out, 0, sizeof(*out));
+    if (int rc = check_object(ctx, obj)) return rc;
+    if (!obj->probes) {
+        obj->probes = new (std::nothrow) ivx_probes();
+        if (!obj->probes) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    ivx_probes& pr = *obj->probes;
+    pr.range_of_chunk.clear();
+    pr.free_points.clear();
+    pr.n_points = 0;
+    pr.log2_block_size = log2_block_size_for(obj);
+    const uint32_t n_items = obj->mesh.n_submeshes;
+    if (n_items == 0) {
+        fill_info(pr, out);
+        return IVX_OK;
+    }
+    Tmp tmp(ctx);
+    float* scratch = nullptr;
+    uint32_t* d_counts = nullptr;
+    std::vector<uint32_t> counts, chunk_of;
+    if (int rc = probe_items(ctx, obj, nullptr, n_items, pr.log2_block_size, tmp, scratch, d_counts, counts, chunk_of)) return rc;
+    std::vector<uint32_t> offsets(n_items, 0xFFFFFFFFu);
+    uint32_t total = 0;
+    for (uint32_t q = 0; q < n_items; ++q) {
+        if (counts[q] == 0u) continue;
+        offsets[q] = total;
+        pr.range_of_chunk[chunk_of[q]] = {total, total + counts[q]};
+        total += counts[q];
+    }
+    if (int rc = ensure_points(ctx, pr, 0, total)) return rc;
+    pr.n_points = total;
+    if (int rc = scatter_items(ctx, pr, scratch, d_counts, offsets, pr.log2_block_size, tmp)) return rc;
+    fill_info(pr, out);
+    return IVX_OK;
+}
+
+int ivx_object_collision_probes_sync(ivx_ctx* ctx, ivx_object* obj, ivx_probes_info* out) {
+    if (!ctx || !obj || !out) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    std::memset(out, 0, sizeof(*out));
+    if (int rc = check_object(ctx, obj)) return rc;
+    if (!obj->probes || !obj->sync)
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "collision probes follow a synced mesh: ivx_object_collision_probes once, then "
+                 "ivx_object_mesh_sync + ivx_object_collision_probes_sync after every modification");
+    ivx_probes& pr = *obj->probes;
+    const ivx_mesh_sync& s = *obj->sync;
+    pr.log2_block_size = log2_block_size_for(obj);
+    const std::vector<uint32_t>& dirty = s.last_dirty;
+    // the invalidated chunks that (still) have a submesh are probed; all of them are placed or removed in the order the
+    // mesh sync took them
+    std::vector<uint32_t> rows, item_of(dirty.size(), 0xFFFFFFFFu);
+    for (size_t q = 0; q < dirty.size(); ++q) {
+        auto it = s.row_of_chunk.find(dirty[q]);
+        if (it == s.row_of_chunk.end()) continue;
+        item_of[q] = (uint32_t)rows.size();
+        rows.push_back(it->second);
+    }
+    Tmp tmp(ctx);
+    float* scratch = nullptr;
+    uint32_t* d_counts = nullptr;
+    std::vector<uint32_t> counts, chunk_of;
+    const uint32_t n_items = (uint32_t)rows.size();
+    if (n_items) {
+        uint32_t* d_rows = tmp.get<uint32_t>(n_items);
+        if (!d_rows) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "collision probes: out of device memory");
+        CU(ctx, cudaMemcpyAsync(d_rows, rows.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (int rc = probe_items(ctx, obj, d_rows, n_items, pr.log2_block_size, tmp, scratch, d_counts, counts, chunk_of)) return rc;
+    }
+    // update_for_chunk (collidable.rs:542-612)
+    std::vector<uint32_t> offsets(n_items, 0xFFFFFFFFu);
+    const uint32_t kept_points = pr.n_points;
+    for (size_t q = 0; q < dirty.size(); ++q) {
+        const uint32_t chunk = dirty[q];
+        const uint32_t count = item_of[q] == 0xFFFFFFFFu ? 0u : counts[item_of[q]];
+        auto old = pr.range_of_chunk.find(chunk);
+        if (count == 0u) {
+            if (old != pr.range_of_chunk.end()) {
+                release_range(pr.free_points, old->second.first, old->second.second);
+                pr.range_of_chunk.erase(old);
+            }
+            continue;
+        }
+        if (old != pr.range_of_chunk.end()) release_range(pr.free_points, old->second.first, old->second.second);
+        uint32_t start = 0;
+        if (!take_range(pr.free_points, count, start)) {
+            start = pr.n_points;
+            pr.n_points += count;
+        }
+        pr.range_of_chunk[chunk] = {start, start + count};
+        offsets[item_of[q]] = start;
+    }
+    coalesce(pr.free_points);  // merge_consecutive_ranges
+    if (int rc = ensure_points(ctx, pr, kept_points, pr.n_points)) return rc;
+    if (int rc = scatter_items(ctx, pr, scratch, d_counts, offsets, pr.log2_block_size, tmp)) return rc;
+    fill_info(pr, out);
+    return IVX_OK;
+}
+
+int ivx_collision_probes_download(ivx_ctx* ctx, const ivx_object* obj, float* points, size_t capacity_points, ivx_probe_range* ranges,
+                                  size_t capacity_ranges) {
+    if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    const ivx_probes* pr = obj->probes;
+    if (!pr) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "call ivx_object_collision_probes first");
+    if (points) {
+        if (capacity_points < pr->n_points) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u probe points", pr->n_points);
+        if (pr->n_points) {
+            CU(ctx, cudaMemcpyAsync(points, pr->d_points, (size_t)pr->n_points * 12, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    if (ranges) {
+        if (capacity_ranges < pr->range_of_chunk.size())
+            IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %zu chunk point ranges", pr->range_of_chunk.size());
+        std::vector<uint32_t> keys;
+        keys.reserve(pr->range_of_chunk.size());
+        for (const auto& kv : pr->range_of_chunk) keys.push_back(kv.first);
+        std::sort(keys.begin(), keys.end());
+        for (size_t q = 0; q < keys.size(); ++q) {
+            const uint32_t c = keys[q];
+            const auto& r = pr->range_of_chunk.at(c);
+            ranges[q].chunk_indices[0] = c / (obj->nb[1] * obj->nb[2]);
+            ranges[q].chunk_indices[1] = (c / obj->nb[2]) % obj->nb[1];
+            ranges[q].chunk_indices[2] = c % obj->nb[2];
+            ranges[q].point_start = r.first;
+            ranges[q].point_end = r.second;
+        }
+    }
+    return IVX_OK;
+}
+
+}  // extern "C"

@@ -559,6 +559,20 @@ class VoxelObjectMesh:
     def report_synchronized(self):
         self.obj.ctx.check(self.obj.ctx._lib.ivx_mesh_report_synchronized(self.obj.ctx.h, self.obj.h))
 
+    def collision_probes(self, sync: bool = False) -> dict:
+        """`VoxelObjectCollisionProbes` beside this mesh (collidable.rs:346-780): all chunks (`compute_for_all_chunks`,
+        MeshedVoxelObject::create) or, with sync=True right after `VoxelObjectMesh.sync`, the chunks that sync visited
+        (`sync_with_voxel_object_and_mesh`). → log2_block_size, points (buffer incl. freed ranges), ranges per chunk."""
+        ctx = self.obj.ctx
+        info = L.ProbesInfo()
+        fn = ctx._lib.ivx_object_collision_probes_sync if sync else ctx._lib.ivx_object_collision_probes
+        ctx.check(fn(ctx.h, self.obj.h, C.byref(info)))
+        points = np.zeros((max(1, info.n_points), 3), np.float32)
+        ranges = np.zeros(max(1, info.n_chunks), L.PROBE_RANGE_DTYPE)
+        ctx.check(ctx._lib.ivx_collision_probes_download(ctx.h, self.obj.h, L.ptr(points), C.c_size_t(len(points)), L.ptr(ranges),
+                                                         C.c_size_t(len(ranges))))
+        return {"log2_block_size": int(info.log2_block_size), "points": points[: info.n_points], "ranges": ranges[: info.n_chunks]}
+
     def download(self) -> dict:
         pos = np.zeros((self.n_vertices, 3), np.float32)
         nrm = np.zeros((self.n_vertices, 3), np.float32)

@@ -486,6 +486,35 @@ int ivx_mesh_modifications(ivx_ctx* ctx, const ivx_object* object, uint32_t* out
                            uint64_t* out_count, int* out_chunks_were_removed);
 int ivx_mesh_report_synchronized(ivx_ctx* ctx, ivx_object* object);
 
+/* ---- collision probes ------------------------------------------------------
+ * VoxelObjectCollisionProbes (collidable.rs:97-101, 346-780): per meshed chunk and per block of 1^3 .. 8^3 voxels
+ * (determine_log2_block_size_for_object, :451-471) the mesh vertex of lowest mean curvature — the points the physics
+ * probes other objects with. They live beside the mesh (MeshedVoxelObject, mesh.rs:36-44):
+ *   ivx_object_collision_probes       replaces compute_for_all_chunks / recompute_for_all_chunks (:355-392, MeshedVoxelObject::
+ *                                     create, mesh.rs:156-168) on the object's current mesh (ivx_object_mesh or the synced mesh)
+ *   ivx_object_collision_probes_sync  replaces sync_with_voxel_object_and_mesh (:394-433, 524-612) — call it right after
+ *                                     ivx_object_mesh_sync (MeshedVoxelObject::sync_mesh_with_object, mesh.rs:193-205): the
+ *                                     chunks that sync visited are re-probed and their points go into the smallest free
+ *                                     range that fits, else to the end (the reference's RangeAllocator), in the same order
+ *   ivx_collision_probes_download     probe_points() (buffer length n_points, freed ranges keep obsolete points) and
+ *                                     chunk_point_ranges(), here in ascending linear chunk index
+ * d_points stays valid until the next probes call on the object. */
+typedef struct ivx_probes_info {
+    uint32_t log2_block_size;
+    uint32_t _pad;
+    uint64_t n_points;   /* length of the point buffer */
+    uint64_t n_chunks;   /* chunks that have points */
+    const float* d_points;  /* device, 3 floats per point */
+} ivx_probes_info;
+typedef struct ivx_probe_range {
+    uint32_t chunk_indices[3];
+    uint32_t point_start, point_end;
+} ivx_probe_range;
+int ivx_object_collision_probes(ivx_ctx* ctx, ivx_object* object, ivx_probes_info* out);
+int ivx_object_collision_probes_sync(ivx_ctx* ctx, ivx_object* object, ivx_probes_info* out);
+int ivx_collision_probes_download(ivx_ctx* ctx, const ivx_object* object, float* points, size_t capacity_points,
+                                  ivx_probe_range* ranges, size_t capacity_ranges);
+
 /* ---- multi-GPU communicator over peer memory ---------------------------------
  * The whole multi-GPU plane of the path behind the C ABI — a host needs no NCCL and no torch for it:
  *

@@ -38,6 +38,11 @@ pub struct IvxMetaNode { pub kind: u32, pub child: [u32; 2], pub count: u32, pub
                          pub max_pick_count: u32, pub pick_probability: f32, pub smoothness: f32,
                          pub params: [IvxMetaParam; 8] }
 
+/// `ivx_probes_info` / `ivx_probe_range`: VoxelObjectCollisionProbes as the library keeps them (collidable.rs:97-101)
+#[repr(C)] pub struct IvxProbesInfo { pub log2_block_size: u32, pub _pad: u32, pub n_points: u64, pub n_chunks: u64,
+                                      pub d_points: *const f32 }
+#[repr(C)] pub struct IvxProbeRange { pub chunk_indices: [u32; 3], pub point_start: u32, pub point_end: u32 }
+
 dynamic_lib::define_lib! {
     name = VoxelCudaLib,
     path_env_var = "IMPACT_VOXEL_CUDA_LIB",
@@ -133,6 +138,10 @@ dynamic_lib::define_lib! {
     unsafe fn ivx_object_download_async(ctx: *mut IvxCtx, object: *mut IvxObject, chunks: *mut IvxChunkDesc,
                                         chunk_capacity: usize, voxels: *mut Voxel, voxel_capacity: usize,
                                         out_non_uniform_chunks: *mut u64) -> i32;
+    unsafe fn ivx_object_collision_probes(ctx: *mut IvxCtx, object: *mut IvxObject, out: *mut IvxProbesInfo) -> i32;
+    unsafe fn ivx_object_collision_probes_sync(ctx: *mut IvxCtx, object: *mut IvxObject, out: *mut IvxProbesInfo) -> i32;
+    unsafe fn ivx_collision_probes_download(ctx: *mut IvxCtx, object: *const IvxObject, points: *mut f32, capacity_points: usize,
+                                            ranges: *mut IvxProbeRange, capacity_ranges: usize) -> i32;
     unsafe fn ivx_object_free(ctx: *mut IvxCtx, object: *mut IvxObject) -> ();
 }
 /// one call of the closures of `for_each_surface_voxel_*`: indices, the voxel, `VoxelSurfacePlacement` as u8

@@ -336,6 +336,64 @@ void orc_synced_mesh_report_synchronized(void* smp) {
 }
 void orc_synced_mesh_free(void* smp) { delete (SyncedMesh*)smp; }
 
+// ---- collision probes (VoxelObjectCollisionProbes, collidable.rs:346-780) ----
+void* orc_probes_create(const void* op, const void* mp) {
+    CollisionProbes* pr = new CollisionProbes();
+    probes_compute_for_all_chunks(*(const Object*)op, *(const Mesh*)mp, *pr);
+    return pr;
+}
+// the same on mesh arrays the caller holds (oracle_lib.Mesh copies the arrays out and frees the C++ mesh)
+void* orc_probes_create_arrays(const void* op, const float* positions, const float* normals, const uint32_t* indices,
+                               const Submesh* submeshes, const uint32_t* vertex_ranges, uint32_t n_vertices, uint32_t n_indices,
+                               uint32_t n_submeshes) {
+    Mesh m;
+    m.positions.assign(positions, positions + 3 * (size_t)n_vertices);
+    m.normals.assign(normals, normals + 3 * (size_t)n_vertices);
+    m.indices.assign(indices, indices + n_indices);
+    m.submeshes.assign(submeshes, submeshes + n_submeshes);
+    m.vertex_ranges.assign(vertex_ranges, vertex_ranges + 2 * (size_t)n_submeshes);
+    CollisionProbes* pr = new CollisionProbes();
+    probes_compute_for_all_chunks(*(const Object*)op, m, *pr);
+    return pr;
+}
+void orc_probes_sync(void* pp, const void* op, const void* smp, const uint32_t* dirty, uint32_t n_dirty) {
+    probes_sync(*(const Object*)op, *(const SyncedMesh*)smp, dirty, n_dirty, *(CollisionProbes*)pp);
+}
+uint32_t orc_probes_log2_block_size(const void* op) { return probes_log2_block_size(*(const Object*)op); }
+void orc_probes_sizes(const void* pp, uint64_t* n_points, uint64_t* n_chunks) {
+    const CollisionProbes* pr = (const CollisionProbes*)pp;
+    *n_points = pr->points.size() / 3;
+    *n_chunks = pr->range_of_chunk.size();
+}
+// ranges: per chunk with points {linear chunk index, start, end}, sorted by chunk index
+void orc_probes_copy(const void* pp, float* points, uint32_t* ranges) {
+    const CollisionProbes* pr = (const CollisionProbes*)pp;
+    if (points) std::memcpy(points, pr->points.data(), pr->points.size() * sizeof(float));
+    if (ranges) {
+        std::vector<uint32_t> keys;
+        for (const auto& kv : pr->range_of_chunk) keys.push_back(kv.first);
+        std::sort(keys.begin(), keys.end());
+        for (size_t q = 0; q < keys.size(); ++q) {
+            const auto& r = pr->range_of_chunk.at(keys[q]);
+            ranges[3 * q] = keys[q];
+            ranges[3 * q + 1] = (uint32_t)r.first;
+            ranges[3 * q + 2] = (uint32_t)r.second;
+        }
+    }
+}
+void orc_probes_free(void* pp) { delete (CollisionProbes*)pp; }
+// add_points_for_vertices_in_blocks on caller-provided data (unit tests)
+uint32_t orc_probes_points_for_chunk(uint32_t log2_block_size, const uint32_t* chunk_indices, const float* positions,
+                                     const float* normals, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
+                                     uint32_t start_index, float inverse_voxel_extent, float* out, uint32_t capacity_points) {
+    std::vector<float> pts;
+    probes_points_for_chunk(log2_block_size, chunk_indices, positions, normals, n_vertices, indices, n_indices, start_index,
+                            inverse_voxel_extent, pts);
+    const uint32_t n = (uint32_t)(pts.size() / 3);
+    if (out) std::memcpy(out, pts.data(), (size_t)std::min(n, capacity_points) * 12);
+    return n;
+}
+
 // Mesh one chunk (one iteration of sync_with_voxel_object). Returns 0 if the
 // chunk is not exposed / produced no indices; else fills counts. Buffers sized
 // for the worst case: 4913 vertices, 3*6*4913 indices.

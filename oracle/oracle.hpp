@@ -308,6 +308,19 @@ void synced_mesh_create(const Object& obj, SyncedMesh& sm, int n_threads = 1);
 // sync_with_voxel_object over `dirty` (linear chunk indices) in the given order — the reference iterates a HashSet
 void synced_mesh_sync(const Object& obj, SyncedMesh& sm, const uint32_t* dirty, size_t n_dirty);
 
+// --- collision probes (collidable.rs:97-101, 346-780) --------------------------
+struct CollisionProbes {
+    std::vector<float> points;  // xyz; freed ranges keep obsolete points
+    std::unordered_map<uint32_t, std::pair<size_t, size_t>> range_of_chunk;  // linear chunk index → point range
+    RangeAllocator free_points;
+};
+uint32_t probes_log2_block_size(const Object& obj);
+void probes_points_for_chunk(uint32_t log2_block_size, const uint32_t chunk_indices[3], const float* positions, const float* normals,
+                             size_t n_vertices, const uint32_t* indices, size_t n_indices, uint32_t start_index,
+                             float inverse_voxel_extent, std::vector<float>& points);
+void probes_compute_for_all_chunks(const Object& obj, const Mesh& mesh, CollisionProbes& pr);
+void probes_sync(const Object& obj, const SyncedMesh& sm, const uint32_t* dirty, size_t n_dirty, CollisionProbes& pr);
+
 // --- inertial properties (object/inertia.rs) ----------------------------------
 // VoxelObjectInertialPropertyManager (inertia.rs:19-25): mass, moments (m x), moments of inertia, products of inertia,
 // all with respect to the origin of the voxel grid.

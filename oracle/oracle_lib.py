@@ -571,3 +571,55 @@ def fbm3(x, y, z, lac, gain, octaves, seed):
 
 def simplex4(x, y, z, w, seed):
     return float(lib().orc_simplex4(C.c_float(x), C.c_float(y), C.c_float(z), C.c_float(w), C.c_int32(seed)))
+
+
+class CollisionProbes:
+    """`VoxelObjectCollisionProbes` (collidable.rs:346-780): `CollisionProbes(obj, mesh)` = compute_for_all_chunks on a
+    `Mesh` or on a `SyncedMesh`'s mesh; `sync` = sync_with_voxel_object_and_mesh over the given chunks in the given order.
+    `points` (n, 3) keeps obsolete points in freed ranges; `ranges` = (linear chunk index, start, end) sorted by chunk."""
+
+    def __init__(self, obj: "Object", mesh):
+        lib().orc_probes_create.restype = C.c_void_p
+        lib().orc_probes_log2_block_size.restype = C.c_uint32
+        if isinstance(mesh, SyncedMesh):
+            self.h = C.c_void_p(lib().orc_probes_create(obj.h, C.c_void_p(lib().orc_synced_mesh_mesh(mesh.h))))
+        else:
+            lib().orc_probes_create_arrays.restype = C.c_void_p
+            self.h = C.c_void_p(lib().orc_probes_create_arrays(
+                obj.h, _p(mesh.positions), _p(mesh.normals), _p(mesh.indices), _p(mesh.submeshes), _p(mesh.vertex_ranges),
+                C.c_uint32(mesh.n_vertices), C.c_uint32(mesh.n_indices), C.c_uint32(mesh.n_submeshes)))
+        self.log2_block_size = int(lib().orc_probes_log2_block_size(obj.h))
+        self._read()
+
+    def _read(self):
+        n_points, n_chunks = C.c_uint64(), C.c_uint64()
+        lib().orc_probes_sizes(self.h, C.byref(n_points), C.byref(n_chunks))
+        self.points = np.zeros((n_points.value, 3), np.float32)
+        self.ranges = np.zeros((n_chunks.value, 3), np.uint32)
+        lib().orc_probes_copy(self.h, _p(self.points), _p(self.ranges))
+
+    def sync(self, obj: "Object", synced_mesh: "SyncedMesh", dirty_chunks) -> None:
+        d = np.ascontiguousarray(dirty_chunks, np.uint32)
+        lib().orc_probes_sync(self.h, obj.h, synced_mesh.h, _p(d), C.c_uint32(len(d)))
+        self.log2_block_size = int(lib().orc_probes_log2_block_size(obj.h))
+        self._read()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_probes_free(self.h)
+            self.h = None
+
+
+def probes_points_for_chunk(log2_block_size, chunk_indices, positions, normals, indices, start_index=0,
+                            inverse_voxel_extent=1.0) -> np.ndarray:
+    """`add_points_for_vertices_in_blocks` (collidable.rs:614-731) on the given chunk mesh → (n, 3) points."""
+    pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, np.uint32)
+    ci = np.ascontiguousarray(chunk_indices, np.uint32)
+    out = np.zeros((4096, 3), np.float32)
+    lib().orc_probes_points_for_chunk.restype = C.c_uint32
+    n = lib().orc_probes_points_for_chunk(C.c_uint32(log2_block_size), _p(ci), _p(pos), _p(nrm), C.c_uint32(len(pos)), _p(idx),
+                                          C.c_uint32(len(idx)), C.c_uint32(start_index), C.c_float(inverse_voxel_extent),
+                                          _p(out), C.c_uint32(len(out)))
+    return out[:n].copy()
