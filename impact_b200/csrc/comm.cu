@@ -151,6 +151,23 @@ __global__ void __launch_bounds__(256) k_push_dyn(const uint32_t* __restrict__ s
         for (size_t q = t; q < n_words; q += stride) dst[q] = fix(src[q], q);
     }
 }
+// The mesh stays where it is (ivx_object_mesh_distributed): indices, submesh index offsets and vertex ranges become the
+// ones the part has in the mesh of the whole job; my bases go to the host
+__global__ void __launch_bounds__(256) k_rebase_local(uint32_t* __restrict__ indices, size_t n_indices, uint32_t* __restrict__ submesh_words,
+                                                      size_t n_submeshes, uint32_t* __restrict__ vertex_ranges,
+                                                      const uint32_t* __restrict__ bases, uint32_t* __restrict__ host_words) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (t == 0) {
+        host_words[4] = bases[0];
+        host_words[5] = bases[1];
+        host_words[6] = bases[2];
+    }
+    if (bases[3] == 0u) return;
+    const uint32_t vb = bases[0], ib = bases[1];
+    for (size_t q = t; q < n_indices; q += stride) indices[q] += vb;
+    for (size_t q = t; q < n_submeshes; q += stride) submesh_words[13 * q + 3] += ib;  // ChunkSubmesh::index_offset
+    for (size_t q = t; q < 2 * n_submeshes; q += stride) vertex_ranges[q] += vb;
+}
 // gather rank: all parts have landed → merged sizes for the host, "step complete" to everybody
 __global__ void k_complete_step(CommHeader* mine, PeerHeaders peers, uint32_t world, uint32_t parity, uint32_t epoch,
                                 uint32_t* __restrict__ host_words) {
@@ -377,7 +394,8 @@ int ivx_object_exchange_halos(ivx_ctx* ctx, ivx_comm* c, ivx_object* obj, int lo
     return ivx_internal_slab_finalize(ctx, obj, /*sync=*/false);
 }
 
-int ivx_object_mesh_gather(ivx_ctx* ctx, ivx_comm* c, ivx_object* obj, ivx_mesh_info* out_local, ivx_gathered_mesh* out_merged) {
+static int mesh_gather_impl(ivx_ctx* ctx, ivx_comm* c, ivx_object* obj, ivx_mesh_info* out_local, ivx_gathered_mesh* out_merged,
+                            bool distributed, uint64_t* out_bases) {
     if (!ctx || !c || !obj || !out_local) return IVX_ERR_INVALID_ARGUMENT;
     if (!c->connected) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "call ivx_comm_connect first");
     cudaSetDevice(ctx->device);
@@ -427,7 +445,14 @@ int ivx_object_mesh_gather(ivx_ctx* ctx, ivx_comm* c, ivx_object* obj, ivx_mesh_
         {m.indices, ni, 1, 1, 0, 1, 0},             {m.index_materials, ni * 2, 2, 1, 0, 0, 0},
         {m.submeshes, ns * 13, 13, 2, 1, 13, 3},    {m.vertex_ranges, ns * 2, 2, 2, 0, 1, 0},
     };
-    for (int f = 0; f < 6; ++f) {
+    if (distributed) {
+        // every rank keeps its part; only the sizes travelled
+        ctx->launches++;
+        k_rebase_local<<<grid, 256, 0, st>>>(m.indices, ni, reinterpret_cast<uint32_t*>(m.submeshes), ns, m.vertex_ranges, bases,
+                                             c->h_words_dev);
+        CU(ctx, cudaGetLastError());
+    }
+    for (int f = 0; f < 6 && !distributed; ++f) {
         if (fields[f].words == 0) continue;
         ctx->launches++;
         k_push_dyn<<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(fields[f].src),
@@ -457,7 +482,9 @@ int ivx_object_mesh_gather(ivx_ctx* ctx, ivx_comm* c, ivx_object* obj, ivx_mesh_
     if (err == 2u) IVX_FAIL(ctx, IVX_ERR_CAPACITY, "multi-GPU step %u: the merged mesh does not fit the communicator's capacity "
                             "(%llu vertices, %llu indices, %llu submeshes)", epoch, (unsigned long long)c->cfg.mesh_vertices,
                             (unsigned long long)c->cfg.mesh_indices, (unsigned long long)c->cfg.mesh_submeshes);
-    if (rank == dst && out_merged) {
+    if (out_bases)
+        for (int q = 0; q < 3; ++q) out_bases[q] = c->h_words[4 + q];
+    if (rank == dst && out_merged && !distributed) {
         out_merged->n_vertices = c->h_words[0];
         out_merged->n_indices = c->h_words[1];
         out_merged->n_submeshes = c->h_words[2];
@@ -469,6 +496,15 @@ int ivx_object_mesh_gather(ivx_ctx* ctx, ivx_comm* c, ivx_object* obj, ivx_mesh_
         out_merged->d_vertex_ranges = c->base + c->off_mesh[par][5];
     }
     return IVX_OK;
+}
+
+int ivx_object_mesh_gather(ivx_ctx* ctx, ivx_comm* c, ivx_object* obj, ivx_mesh_info* out_local, ivx_gathered_mesh* out_merged) {
+    return mesh_gather_impl(ctx, c, obj, out_local, out_merged, /*distributed=*/false, nullptr);
+}
+
+int ivx_object_mesh_distributed(ivx_ctx* ctx, ivx_comm* c, ivx_object* obj, ivx_mesh_info* out_local, uint64_t out_bases[3]) {
+    if (!out_bases) return IVX_ERR_INVALID_ARGUMENT;
+    return mesh_gather_impl(ctx, c, obj, out_local, nullptr, /*distributed=*/true, out_bases);
 }
 
 }  // extern "C"

@@ -434,6 +434,19 @@ class PeerComm:
             return local, None
         return local, merged
 
+    def mesh_distributed(self, obj):
+        """`ivx_object_mesh_distributed`: the step's mesh stays on its rank, rebased in place to the numbering of the whole
+        job's mesh → (this slab's `VoxelObjectMesh`, (vertex base, index base, submesh base)). Takes the place of
+        `mesh_gather` in a step; synchronises the context's stream."""
+        import ctypes as C
+        from . import _lib as L
+        from .voxel import VoxelObjectMesh
+
+        info = L.MeshInfo()
+        bases = (C.c_uint64 * 3)()
+        self.ctx.check(self.ctx._lib.ivx_object_mesh_distributed(self.ctx.h, self.h, obj.h, C.byref(info), bases))
+        return VoxelObjectMesh(obj, info), (int(bases[0]), int(bases[1]), int(bases[2]))
+
     @staticmethod
     def merged_to_torch(merged, device) -> dict:
         """The `ivx_gathered_mesh` of the gather rank as torch tensors over the window (no copy)."""

@@ -558,6 +558,13 @@ void ivx_comm_destroy(ivx_ctx* ctx, ivx_comm* comm);
 int ivx_object_exchange_halos(ivx_ctx* ctx, ivx_comm* comm, ivx_object* object, int lower_rank, int upper_rank);
 int ivx_object_mesh_gather(ivx_ctx* ctx, ivx_comm* comm, ivx_object* object, ivx_mesh_info* out_local,
                            ivx_gathered_mesh* out_merged);
+/* The same step with the mesh left where it was made ("or leave the mesh distributed and return per-rank
+ * views"): only the mesh sizes travel; every rank's part is rebased in place to the numbering it has in the mesh of the
+ * whole job (vertex indices and vertex ranges + out_bases[0], ChunkSubmesh::index_offset + out_bases[1]; out_bases[2] =
+ * submeshes of the lower ranks) and described by out_local. For hosts that consume the parts rank by rank — e.g. each
+ * rank downloading its part over its own PCIe link (ivx_mesh_download) instead of one rank downloading everything.
+ * Takes the place of ivx_object_mesh_gather in a step; call it once per object. */
+int ivx_object_mesh_distributed(ivx_ctx* ctx, ivx_comm* comm, ivx_object* object, ivx_mesh_info* out_local, uint64_t out_bases[3]);
 
 /* ---- modification -------------------------------------------------------
  * ivx_object_absorb_sphere replaces apply_sphere_absorption

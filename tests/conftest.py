@@ -3,6 +3,12 @@ import sys
 
 import pytest
 
+# tests/test_gpu_comm.py runs several ranks of the peer-memory protocol as threads of THIS process on one device: while one
+# rank's stream spins in an on-device wait, another rank's first launch of a kernel must not need the device to go idle.
+# Lazy module loading does (loading code is an allocation, an implicit synchronisation point), so load everything up front.
+# (One process per GPU — the way the library is deployed and bench.py runs — is not affected.)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

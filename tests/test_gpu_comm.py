@@ -118,6 +118,46 @@ def test_comm_steps_equal_the_whole_object(name, world):
         assert e is None, f"rank {r}: {e}"
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_mesh_parts_concatenate_to_the_whole_mesh(world):
+    # ivx_object_mesh_distributed: the parts stay on their ranks, rebased in place; laid end to end at their bases they
+    # are the whole object's mesh. Gathered and distributed steps alternate on the same communicator (epochs, parities).
+    make, types = GRAPHS["zoo"]
+    ctxs, vgs, whole, wi, wmesh, comms = _setup(make, types, world)
+    wm = wmesh.download()
+    ranges = D.slab_ranges(wi["chunk_counts"][0], world)
+    steps = 5
+    parts = [[None] * world for _ in range(steps)]
+
+    def rank(r):
+        for step in range(steps):
+            obj = VoxelObject.generate(vgs[r], ranges[r])
+            comms[r].exchange_halos(obj, ranges)
+            if step % 2 == 0:
+                local, bases = comms[r].mesh_distributed(obj)
+                parts[step][r] = (local.download(), bases)
+            else:
+                local, merged = comms[r].mesh_gather(obj)
+                if r == 0:
+                    got = D.merged_mesh_to_numpy(D.PeerComm.merged_to_torch(merged, torch.device("cuda", 0)))
+                    H.assert_meshes_equal(got, _MeshLike(wm))
+            obj.free()
+
+    errors = _run(world, rank)
+    for c in comms:
+        c.close()
+    for r, e in enumerate(errors):
+        assert e is None, f"rank {r}: {e}"
+    for step in range(0, steps, 2):
+        v = i = s = 0
+        for r in range(world):
+            m, bases = parts[step][r]
+            assert bases == (v, i, s), (step, r, bases, (v, i, s))
+            v, i, s = v + len(m["positions"]), i + len(m["indices"]), s + len(m["submeshes"])
+        cat = {k: np.concatenate([parts[step][r][0][k] for r in range(world)]) for k in wm}
+        H.assert_meshes_equal(cat, _MeshLike(wm))
+
+
 def test_comm_reports_a_merged_mesh_that_does_not_fit():
     make, types = GRAPHS["zoo"]
     world = 2
