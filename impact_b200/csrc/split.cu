@@ -369,6 +369,7 @@ constexpr int CONN_WARPS = 4;
 constexpr int CONN_SEEN = 96;
 
 __global__ void __launch_bounds__(CONN_WARPS * 32) k_region_connections(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
+                                                                        const uint32_t* __restrict__ regions,
                                                                         const uint8_t* __restrict__ labels,
                                                                         uint2* __restrict__ records, uint32_t capacity,
                                                                         uint32_t* __restrict__ counter,
@@ -389,18 +390,22 @@ __global__ void __launch_bounds__(CONN_WARPS * 32) k_region_connections(const De
         const DevChunk up = chunks[cu];
         if (up.kind == 0u) continue;
         uint32_t count = 0;
-        if (lo.kind == 1u && up.kind == 1u) {
+        // FaceVoxelDistribution of the two touching faces (0 Empty, 1 Full, 2 Mixed; Uniform chunks are full): an empty
+        // face connects nothing, two full faces of chunks with one region each connect exactly those two — no labels read
+        const uint32_t face_lo = lo.kind == 1u ? 1u : lo.face[2 * d + 1], face_up = up.kind == 1u ? 1u : up.face[2 * d];
+        if (face_lo == 0u || face_up == 0u) continue;
+        if (face_lo == 1u && face_up == 1u && (regions[c] & 255u) == 1u && (regions[cu] & 255u) == 1u) {
             if (lane == 0) seen[0] = 0u;
             count = 1;
         } else {
             const uint8_t* ll = lo.kind == 2u ? labels + (size_t)lo.slot * 4096 : nullptr;
             const uint8_t* lu = up.kind == 2u ? labels + (size_t)up.slot * 4096 : nullptr;
             const uint32_t stride_a = d == 0 ? 16u : 256u, stride_b = d == 2 ? 16u : 1u;  // the two in-face axes
-            const uint32_t face_lo = d == 0 ? 15u * 256u : (d == 1 ? 15u * 16u : 15u);
+            const uint32_t upper_face = d == 0 ? 15u * 256u : (d == 1 ? 15u * 16u : 15u);
             for (int round = 0; round < 8; ++round) {
                 const uint32_t p = (uint32_t)round * 32u + (uint32_t)lane;  // 0..255
                 const uint32_t off = (p >> 4) * stride_a + (p & 15u) * stride_b;
-                const uint32_t la = ll ? ll[face_lo + off] : 0u;
+                const uint32_t la = ll ? ll[upper_face + off] : 0u;
                 const uint32_t lb = lu ? lu[off] : 0u;
                 const uint32_t key = (la == LABEL_EMPTY || lb == LABEL_EMPTY) ? 0xFFFFFFFFu : ((la << 8) | lb);
                 const uint32_t peers = __match_any_sync(0xffffffffu, key);
@@ -555,7 +560,8 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
         // connections across chunk faces
         ctx->launches++;
         k_region_connections<<<(n + CONN_WARPS - 1) / CONN_WARPS, CONN_WARPS * 32, 0, st>>>(
-            obj->d_chunks, n, make_uint3(obj->nb[0], obj->nb[1], obj->nb[2]), obj->d_labels, records, record_cap, words + RW_RECORDS,
+            obj->d_chunks, n, make_uint3(obj->nb[0], obj->nb[1], obj->nb[2]), obj->d_regions, obj->d_labels, records, record_cap,
+            words + RW_RECORDS,
             words + RW_LABEL_ERROR);
         CU(ctx, cudaGetLastError());
         // roots of the connected regions
