@@ -2401,16 +2401,24 @@ int ivx_object_dirty_chunks(ivx_ctx* ctx, const ivx_object* obj, uint32_t* out, 
     *out_count = 0;
     const uint32_t n = obj->n_chunks;
     if (n == 0) return IVX_OK;
-    std::vector<uint8_t> h(n);
-    CU(ctx, cudaMemcpyAsync(h.data(), obj->d_dirty, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    // the marks are compacted on the device (ascending linear chunk index); only the list crosses the bus
+    Tmp tmp(ctx);
+    uint32_t* flag = tmp.get<uint32_t>(n);
+    uint32_t* scan = tmp.get<uint32_t>(n);
+    uint32_t* list = tmp.get<uint32_t>(n);
+    uint32_t* unused = tmp.get<uint32_t>(n);
+    if (!flag || !scan || !list || !unused) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "dirty chunks: out of device memory");
+    cudaStream_t st = ctx->stream;
+    KL(ctx, launch_flag_dirty_exposed(obj->d_chunks, obj->d_dirty, n, unused, flag, st));
+    KL(ctx, launch_exclusive_scan(flag, scan, n, ctx->d_scratch + 28, st));
+    KL(ctx, launch_scatter_active(flag, scan, n, list, st));
     uint32_t cnt = 0;
-    for (uint32_t c = 0; c < n; ++c)
-        if (h[c]) {
-            if (out && cnt < capacity) out[cnt] = c;
-            cnt++;
-        }
+    if (int rc = read_words(ctx, ctx->d_scratch + 28, 1, &cnt)) return rc;
     *out_count = cnt;
+    if (out && cnt) {
+        CU(ctx, cudaMemcpyAsync(out, list, (size_t)std::min(cnt, capacity) * 4, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    }
     return IVX_OK;
 }
 

@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""The rows around the hot path, measured on the 1024^3 asteroid beside the CPU restatement (oracle/, 16 threads where it
+threads): meta-graph compile, collision probes, connected regions. One JSON object on stdout.
+
+    python tools/bench_aux.py [--workload asteroid1024] [--no-cpu]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def best_of(fn, n=5):
+    ts = []
+    out = None
+    for _ in range(n):
+        t0 = time.perf_counter()
+        out = fn()
+        ts.append(1e3 * (time.perf_counter() - t0))
+    return min(ts), float(np.median(ts)), out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="asteroid1024")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import bench
+    from impact_b200 import meta as M
+    from impact_b200.voxel import Context, SDFVoxelGenerator, VoxelObject, VoxelObjectMesh
+
+    ctx = Context(0)
+    out = {"workload": args.workload}
+
+    # ---- meta-graph compile (MetaSDFGraph::build_in): the library against its Python mirror, same atomic graph ----
+    nodes = M.asteroid_meta_nodes()
+    z = np.load(os.path.join(M.DATA_DIR, "asteroid_1024_seed0.npz"))
+    scale = float(z["scale_factor"])
+    M.compile_meta_nodes(nodes, scale, 0, ctx)  # first call: kernels loaded, pools filled
+    t_min, t_med, g = best_of(lambda: M.compile_meta_nodes(nodes, scale, 0, ctx))
+    t0 = time.perf_counter()
+    g_py = M.MetaCompiler(nodes, scale, 0, ctx).build()
+    t_py = 1e3 * (time.perf_counter() - t0)
+    out["meta_compile"] = {"ivx_meta_compile_ms": round(t_med, 3), "best_ms": round(t_min, 3), "python_mirror_ms": round(t_py, 1),
+                           "atomic_nodes": len(g), "identical": bool(np.array_equal(g.nodes(), g_py.nodes())),
+                           "note": "asteroid.vgen.ron (29 meta nodes, three ray-cast crater passes: 440 instances probed on "
+                                   "the device per pass), scale factor of the 1024^3 workload"}
+
+    # ---- the object, its mesh, its probes ----
+    graph, types, _ = bench.make_workload(args.workload)
+    obj = VoxelObject.generate(SDFVoxelGenerator(1.0, ctx.build_generator(graph), types))
+    mesh = VoxelObjectMesh.create(obj)
+    mesh.collision_probes()
+    ctx.synchronize()
+    t_min, t_med, pr = best_of(lambda: mesh.collision_probes())
+    info = ctx._lib  # noqa: F841
+    out["collision_probes"] = {"gpu_ms_incl_download": round(t_med, 3), "best_ms": round(t_min, 3), "points": int(len(pr["points"])),
+                               "chunks": int(len(pr["ranges"])), "submeshes": int(mesh.n_submeshes),
+                               "vertices": int(mesh.n_vertices), "log2_block_size": pr["log2_block_size"]}
+    r0 = obj.resolve_connected_regions()
+    t_min, t_med, r = best_of(lambda: obj.resolve_connected_regions())
+    out["connected_regions_unchanged_object"] = {"gpu_ms": round(t_med, 3), "best_ms": round(t_min, 3),
+                                                 "first_resolve_device_ms": round(r0["device_ms"], 3),
+                                                 "local_regions": r["n_local_regions"], "connections": r["n_connections"],
+                                                 "regions": r["n_regions"]}
+
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_lib as O
+        O.build()
+        threads = min(16, os.cpu_count() or 1)
+        ogen = O.Generator(graph.nodes(), graph.root_node_id)
+        t0 = time.perf_counter()
+        ocpu = O.Object.generate(O.VoxelGenerator(ogen, 1.0, types), threads)
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        omesh = ocpu.mesh(threads)
+        t_mesh = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        opr = O.CollisionProbes(ocpu, omesh)
+        t_pr = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        sd = ocpu.split_detection()
+        t_sd = 1e3 * (time.perf_counter() - t0)
+        same = bool(len(opr.points) == len(pr["points"]) and
+                    np.array_equal(opr.points.view(np.uint32), pr["points"].view(np.uint32)))
+        out["cpu_port"] = {"threads": threads, "generate_s": round(t_gen, 2), "mesh_s": round(t_mesh, 2),
+                           "collision_probes_ms_1_thread": round(t_pr, 2), "probes_identical_to_gpu": same,
+                           "split_detection_first_ms_1_thread": round(t_sd, 1), "regions": sd["n_regions"],
+                           "regions_identical_to_gpu": bool(sd["n_regions"] == r["n_regions"])}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

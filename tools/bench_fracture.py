@@ -76,7 +76,7 @@ def main():
             st = obj.absorb_sphere_inertial(c, radius, influence, densities, moments)
         else:
             st = obj.absorb_sphere(c, radius, influence)
-        n_dirty = len(obj.invalidated_mesh_chunk_indices())
+        n_dirty = st["dirty_chunks"]  # size of invalidated_mesh_chunk_indices, part of the call's statistics
         t1 = time.perf_counter()
         patch = VoxelObjectMesh.sync(obj) if args.synced_mesh else VoxelObjectMesh.sync_with_voxel_object(obj)
         ctx.synchronize()

@@ -10,8 +10,10 @@ tail -2 gpurun_out/${tag}_bench.err
 for w in sphere64 sphere202 noisybox256 asteroid512; do
   timeout 600 python bench.py --steps 20 --warmup 5 --workload $w --no-cpu-baseline > gpurun_out/${tag}_bench_$w.json 2>> gpurun_out/${tag}_bench.err
 done
-timeout 900 python tools/bench_fracture.py --steps 32 > gpurun_out/${tag}_fracture_plain.json 2>> gpurun_out/${tag}_bench.err
-timeout 900 python tools/bench_fracture.py --steps 32 --split > gpurun_out/${tag}_fracture_split.json 2>> gpurun_out/${tag}_bench.err
+timeout 900 python tools/bench_fracture.py --steps 32 --synced-mesh > gpurun_out/${tag}_fracture_plain.json 2>> gpurun_out/${tag}_bench.err
+timeout 900 python tools/bench_fracture.py --steps 32 --synced-mesh --split > gpurun_out/${tag}_fracture_split.json 2>> gpurun_out/${tag}_bench.err
+timeout 900 python tools/bench_aux.py > gpurun_out/${tag}_aux.json 2>> gpurun_out/${tag}_bench.err
+cat gpurun_out/${tag}_aux.json
 python - <<PY
 import json
 for w in ("asteroid1024","sphere64","sphere202","noisybox256","asteroid512"):
@@ -24,7 +26,7 @@ for w in ("asteroid1024","sphere64","sphere202","noisybox256","asteroid512"):
 for f in ("plain","split"):
     try:
         d = json.load(open("gpurun_out/${tag}_fracture_%s.json" % f))
-        print("fracture", f, "ms/step", round(d["ms_per_step"],3), "absorb", round(d["absorb_ms"],3), "remesh", round(d["remesh_ms"],3), "split", d["split_ms"])
+        print("fracture", f, "ms/step", round(d["ms_per_step"],3), "absorb", round(d["absorb_ms"],3), "remesh", round(d["remesh_ms"],3), "split", d["split_ms"], "medians", d.get("median_active_absorb_ms"), d.get("median_active_remesh_ms"), d.get("median_active_split_ms"))
     except Exception as e:
         print("fracture", f, "failed:", e)
 PY
