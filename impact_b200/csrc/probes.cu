@@ -17,7 +17,20 @@
 #include "mesh_sync.cuh"
 
 struct ivx_probes {
-    std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> range_of_chunk;  // chunk_point_ranges by linear chunk index
+    // chunk_point_ranges by linear chunk index: a flat table (start == NONE: the chunk has no points) instead of the
+    // reference's HashMap — thousands of chunks are placed per call
+    static constexpr uint32_t NONE = 0xFFFFFFFFu;
+    std::vector<std::pair<uint32_t, uint32_t>> range_of_chunk;
+    uint32_t n_with_points = 0;
+    bool has(uint32_t chunk) const { return range_of_chunk[chunk].first != NONE; }
+    void put(uint32_t chunk, uint32_t a, uint32_t b) {
+        if (!has(chunk)) ++n_with_points;
+        range_of_chunk[chunk] = {a, b};
+    }
+    void drop(uint32_t chunk) {
+        if (has(chunk)) --n_with_points;
+        range_of_chunk[chunk] = {NONE, NONE};
+    }
     ivx_ranges::Ranges free_points;                                                // point_range_allocator
     uint32_t n_points = 0;    // length of the point buffer (holes included)
     uint32_t cap_points = 0;
@@ -49,9 +62,12 @@ struct ProbeArgs {
     float* scratch_points;  // n_items x blocks-per-chunk x 3
     uint32_t* counts;       // per item: points
     uint32_t* chunk_of;     // per item: linear chunk index
+    uint32_t walk_all;      // 1: every chunk takes the path of chunks too large for the shared-memory lists (tests)
 };
 
 constexpr int PROBE_THREADS = 128;
+constexpr uint32_t PROBE_MAX_VERTICES = 2048;  // of a chunk whose triangle corners are sorted by vertex in shared memory
+constexpr uint32_t PROBE_MAX_CORNERS = 12288;  // (a chunk has ~300 vertices and ~1600 corners on average, at most 4913 / ~29 000)
 
 __device__ __forceinline__ uint32_t ordered_bits(float f) {  // monotonic in f; -0 == +0
     uint32_t u = __float_as_uint(f == 0.0f ? 0.0f : f);
@@ -62,6 +78,9 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_points(ProbeArgs a) {
     extern __shared__ unsigned long long s_best[];  // per block of the chunk: ordered curvature << 32 | vertex
     __shared__ uint32_t s_warp[PROBE_THREADS / 32];
     __shared__ uint32_t s_base;
+    __shared__ uint32_t s_first[PROBE_MAX_VERTICES + 1];  // per vertex: where its corners start in s_corner
+    __shared__ uint32_t s_fill[PROBE_MAX_VERTICES];
+    __shared__ uint16_t s_corner[PROBE_MAX_CORNERS];      // positions in the chunk's index list, grouped by vertex
     const uint32_t log2_blocks = 4u - a.log2_block_size, n_blocks = 1u << (3u * log2_blocks);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -77,28 +96,88 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_points(ProbeArgs a) {
             lower[d] = (float)(sm.chunk_indices[d] * 16u);
             upper[d] = (float)((sm.chunk_indices[d] + 1u) * 16u);
         }
+        // Which triangle corners use a vertex, in index order. Chunks of ordinary size (PROBE_MAX_VERTICES vertices,
+        // PROBE_MAX_CORNERS corners) sort the corners by vertex in shared memory — count, prefix sum, fill, then every
+        // vertex orders its own few corners — so the work is linear in the chunk's mesh; larger chunks let every vertex
+        // walk all triangles.
+        const uint32_t n_corners = 3u * n_triangles;
+        const bool listed = n_vertices <= PROBE_MAX_VERTICES && n_corners <= PROBE_MAX_CORNERS && !a.walk_all;
+        if (listed) {
+            for (uint32_t v = tid; v <= n_vertices; v += PROBE_THREADS) s_first[v] = 0u;
+            __syncthreads();
+            for (uint32_t q = tid; q < n_corners; q += PROBE_THREADS) atomicAdd(&s_first[idx[q] - v0], 1u);
+            __syncthreads();
+            // exclusive prefix sum over the vertices, PROBE_MAX_VERTICES / PROBE_THREADS consecutive entries per thread
+            constexpr uint32_t PER = PROBE_MAX_VERTICES / PROBE_THREADS;
+            uint32_t mine[PER], total = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < PER; ++q) {
+                const uint32_t v = tid * PER + q;
+                mine[q] = v < n_vertices ? s_first[v] : 0u;
+                total += mine[q];
+            }
+            uint32_t incl = total;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += y;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t before = incl - total;
+            for (int w = 0; w < warp; ++w) before += s_warp[w];
+#pragma unroll
+            for (uint32_t q = 0; q < PER; ++q) {
+                const uint32_t v = tid * PER + q;
+                if (v < n_vertices) {
+                    s_first[v] = before;
+                    s_fill[v] = before;
+                }
+                before += mine[q];
+            }
+            if (tid == PROBE_THREADS - 1) s_first[n_vertices] = before;
+            __syncthreads();
+            for (uint32_t q = tid; q < n_corners; q += PROBE_THREADS) s_corner[atomicAdd(&s_fill[idx[q] - v0], 1u)] = (uint16_t)q;
+            __syncthreads();
+        }
         for (uint32_t v = tid; v < n_vertices; v += PROBE_THREADS) {
             const uint32_t me = v0 + v;
             const float px = a.positions[3 * (size_t)me], py = a.positions[3 * (size_t)me + 1], pz = a.positions[3 * (size_t)me + 2];
             const float nx = a.normals[3 * (size_t)me], ny = a.normals[3 * (size_t)me + 1], nz = a.normals[3 * (size_t)me + 2];
             float sum = 0.0f, count = 0.0f;
-            for (uint32_t t = 0; t < n_triangles; ++t) {
-                const uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
-                if (i0 != me && i1 != me && i2 != me) continue;
-                // corner c of the triangle: outgoing edge to corner c + 1, incoming edge from corner c - 1
-                const uint32_t tri[3] = {i0, i1, i2};
+            // corner c of a triangle: outgoing edge to corner c + 1, incoming edge from corner c - 1
+            const auto add_corner = [&](uint32_t nxt, uint32_t prv) {
+                const float ox = a.positions[3 * (size_t)nxt] - px, oy = a.positions[3 * (size_t)nxt + 1] - py,
+                            oz = a.positions[3 * (size_t)nxt + 2] - pz;  // edge c -> c + 1
+                const float ix = px - a.positions[3 * (size_t)prv], iy = py - a.positions[3 * (size_t)prv + 1],
+                            iz = pz - a.positions[3 * (size_t)prv + 2];  // edge c - 1 -> c
+                const float out_dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, ox), __fmul_rn(ny, oy)), __fmul_rn(nz, oz));
+                const float in_dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, ix), __fmul_rn(ny, iy)), __fmul_rn(nz, iz));
+                sum = __fadd_rn(sum, __fsub_rn(out_dot, in_dot));
+                count += 2.0f;
+            };
+            if (listed) {
+                const uint32_t b0 = s_first[v], b1 = s_first[v + 1];
+                for (uint32_t q = b0 + 1; q < b1; ++q) {  // the fill order is arbitrary: insertion sort of a handful
+                    const uint16_t key = s_corner[q];
+                    uint32_t at = q;
+                    while (at > b0 && s_corner[at - 1] > key) {
+                        s_corner[at] = s_corner[at - 1];
+                        --at;
+                    }
+                    s_corner[at] = key;
+                }
+                for (uint32_t q = b0; q < b1; ++q) {
+                    const uint32_t corner = s_corner[q], t3 = corner - corner % 3u, c = corner % 3u;
+                    add_corner(idx[t3 + (c + 1u) % 3u], idx[t3 + (c + 2u) % 3u]);
+                }
+            } else {
+                for (uint32_t t = 0; t < n_triangles; ++t) {
+                    const uint32_t tri[3] = {idx[3 * t], idx[3 * t + 1], idx[3 * t + 2]};
+                    if (tri[0] != me && tri[1] != me && tri[2] != me) continue;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (tri[c] != me) continue;
-                    const uint32_t nxt = tri[(c + 1) % 3], prv = tri[(c + 2) % 3];
-                    const float ox = a.positions[3 * (size_t)nxt] - px, oy = a.positions[3 * (size_t)nxt + 1] - py,
-                                oz = a.positions[3 * (size_t)nxt + 2] - pz;  // edge c -> c + 1
-                    const float ix = px - a.positions[3 * (size_t)prv], iy = py - a.positions[3 * (size_t)prv + 1],
-                                iz = pz - a.positions[3 * (size_t)prv + 2];  // edge c - 1 -> c
-                    const float out_dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, ox), __fmul_rn(ny, oy)), __fmul_rn(nz, oz));
-                    const float in_dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, ix), __fmul_rn(ny, iy)), __fmul_rn(nz, iz));
-                    sum = __fadd_rn(sum, __fsub_rn(out_dot, in_dot));
-                    count += 2.0f;
+                    for (int c = 0; c < 3; ++c)
+                        if (tri[c] == me) add_corner(tri[(c + 1) % 3], tri[(c + 2) % 3]);
                 }
             }
             if (count == 0.0f) continue;  // a vertex no triangle of the chunk uses
@@ -208,6 +287,7 @@ int probe_items(ivx_ctx* ctx, ivx_object* obj, const uint32_t* d_rows, uint32_t 
     a.scratch_points = scratch;
     a.counts = d_counts;
     a.chunk_of = d_counts + n_items;
+    a.walk_all = std::getenv("IVX_PROBES_WALK_ALL") ? 1u : 0u;
     const size_t smem = (size_t)blocks_per_chunk * 8;
     CU(ctx, cudaFuncSetAttribute(k_probe_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->launches++;
@@ -239,7 +319,7 @@ int scatter_items(ivx_ctx* ctx, ivx_probes& pr, const float* scratch, const uint
 void fill_info(const ivx_probes& pr, ivx_probes_info* out) {
     out->log2_block_size = pr.log2_block_size;
     out->n_points = pr.n_points;
-    out->n_chunks = pr.range_of_chunk.size();
+    out->n_chunks = pr.n_with_points;
     out->d_points = pr.d_points;
 }
 
@@ -266,7 +346,8 @@ int ivx_object_collision_probes(ivx_ctx* ctx, ivx_object* obj, ivx_probes_info* 
         if (!obj->probes) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "host allocation failed");
     }
     ivx_probes& pr = *obj->probes;
-    pr.range_of_chunk.clear();
+    pr.range_of_chunk.assign(obj->n_chunks, {ivx_probes::NONE, ivx_probes::NONE});
+    pr.n_with_points = 0;
     pr.free_points.clear();
     pr.n_points = 0;
     pr.log2_block_size = log2_block_size_for(obj);
@@ -285,7 +366,7 @@ int ivx_object_collision_probes(ivx_ctx* ctx, ivx_object* obj, ivx_probes_info* 
     for (uint32_t q = 0; q < n_items; ++q) {
         if (counts[q] == 0u) continue;
         offsets[q] = total;
-        pr.range_of_chunk[chunk_of[q]] = {total, total + counts[q]};
+        pr.put(chunk_of[q], total, total + counts[q]);
         total += counts[q];
     }
     if (int rc = ensure_points(ctx, pr, 0, total)) return rc;
@@ -333,21 +414,22 @@ int ivx_object_collision_probes_sync(ivx_ctx* ctx, ivx_object* obj, ivx_probes_i
     for (size_t q = 0; q < dirty.size(); ++q) {
         const uint32_t chunk = dirty[q];
         const uint32_t count = item_of[q] == 0xFFFFFFFFu ? 0u : counts[item_of[q]];
-        auto old = pr.range_of_chunk.find(chunk);
+        const bool had = pr.has(chunk);
+        const std::pair<uint32_t, uint32_t> old = pr.range_of_chunk[chunk];
         if (count == 0u) {
-            if (old != pr.range_of_chunk.end()) {
-                release_range(pr.free_points, old->second.first, old->second.second);
-                pr.range_of_chunk.erase(old);
+            if (had) {
+                release_range(pr.free_points, old.first, old.second);
+                pr.drop(chunk);
             }
             continue;
         }
-        if (old != pr.range_of_chunk.end()) release_range(pr.free_points, old->second.first, old->second.second);
+        if (had) release_range(pr.free_points, old.first, old.second);
         uint32_t start = 0;
         if (!take_range(pr.free_points, count, start)) {
             start = pr.n_points;
             pr.n_points += count;
         }
-        pr.range_of_chunk[chunk] = {start, start + count};
+        pr.put(chunk, start, start + count);
         offsets[item_of[q]] = start;
     }
     coalesce(pr.free_points);  // merge_consecutive_ranges
@@ -371,20 +453,18 @@ int ivx_collision_probes_download(ivx_ctx* ctx, const ivx_object* obj, float* po
         }
     }
     if (ranges) {
-        if (capacity_ranges < pr->range_of_chunk.size())
-            IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %zu chunk point ranges", pr->range_of_chunk.size());
-        std::vector<uint32_t> keys;
-        keys.reserve(pr->range_of_chunk.size());
-        for (const auto& kv : pr->range_of_chunk) keys.push_back(kv.first);
-        std::sort(keys.begin(), keys.end());
-        for (size_t q = 0; q < keys.size(); ++q) {
-            const uint32_t c = keys[q];
-            const auto& r = pr->range_of_chunk.at(c);
+        if (capacity_ranges < pr->n_with_points)
+            IVX_FAIL(ctx, IVX_ERR_CAPACITY, "need room for %u chunk point ranges", pr->n_with_points);
+        size_t q = 0;
+        for (uint32_t c = 0; c < (uint32_t)pr->range_of_chunk.size(); ++c) {
+            if (!pr->has(c)) continue;
+            const auto& r = pr->range_of_chunk[c];
             ranges[q].chunk_indices[0] = c / (obj->nb[1] * obj->nb[2]);
             ranges[q].chunk_indices[1] = (c / obj->nb[2]) % obj->nb[1];
             ranges[q].chunk_indices[2] = c % obj->nb[2];
             ranges[q].point_start = r.first;
             ranges[q].point_end = r.second;
+            ++q;
         }
     }
     return IVX_OK;

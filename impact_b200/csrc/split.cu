@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) nonempty += __shfl_xor_sync(0xffffffffu, nonempty, d);
+        __syncwarp();  // the staged flags are read across lanes from here on
         uint8_t* out = labels + (size_t)slot * 4096;
         if (nonempty == 4096u || nonempty == 0u) {
             // one region filling the chunk (label 0, it touches the boundary) / no region at all
@@ -209,7 +210,8 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
                 }
             }
             __syncwarp();
-            for (uint32_t q = 0; q < count; ++q) s_seen[(keys[q] * 0x9E3779B1u) >> 24] = keys[q];
+            // (several lanes may note pairs that share an entry: any of them may stay, so an exchange, not a plain store)
+            for (uint32_t q = 0; q < count; ++q) atomicExch(&s_seen[(keys[q] * 0x9E3779B1u) >> 24], keys[q]);
             uint32_t offset = count;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {

@@ -137,6 +137,22 @@ def test_probes_of_all_chunks_match_the_oracle(ctx, oracle, name):
 
 
 @pytest.mark.gpu
+def test_chunks_too_large_for_the_shared_memory_lists_take_the_walk(ctx, oracle, monkeypatch):
+    # IVX_PROBES_WALK_ALL sends every chunk down the path of chunks with more than 2048 vertices / 12288 corners
+    from impact_b200.voxel import SDFVoxelGenerator, VoxelObject, VoxelObjectMesh
+    g = H.noisy_box_graph(38.0, 8)
+    obj_cpu = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(g.nodes(), g.root_node_id), 1.0, H.SAME0), 4)
+    obj_gpu = VoxelObject.generate(SDFVoxelGenerator(1.0, ctx.build_generator(g), H.SAME0))
+    want = oracle.CollisionProbes(obj_cpu, obj_cpu.mesh(4))
+    mesh = VoxelObjectMesh.create(obj_gpu)
+    monkeypatch.setenv("IVX_PROBES_WALK_ALL", "1")
+    got = mesh.collision_probes()
+    monkeypatch.delenv("IVX_PROBES_WALK_ALL")
+    assert H.f32_bits_equal(got["points"], want.points).all() and len(got["ranges"]) == len(want.ranges)
+    assert H.f32_bits_equal(mesh.collision_probes()["points"], want.points).all()
+
+
+@pytest.mark.gpu
 def test_probes_follow_the_synced_mesh_through_an_absorption_sequence(ctx, oracle):
     from impact_b200.voxel import SDFVoxelGenerator, VoxelObject, VoxelObjectMesh
     g = H.asteroid_like_graph(16, 36.0)
