@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_surface_voxels_in_ranges", "ivx_object_surface_voxels_touching_sphere", "ivx_object_surface_voxels_touching_capsule",
     "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane", "ivx_object_sphere_contacts", "ivx_object_plane_contacts", "ivx_object_capsule_contacts",
     "ivx_comm_create", "ivx_comm_connect", "ivx_comm_connect_local", "ivx_comm_destroy", "ivx_object_exchange_halos",
-    "ivx_object_mesh_gather", "ivx_object_mesh_distributed", "ivx_object_mesh_sync", "ivx_mesh_modifications", "ivx_mesh_report_synchronized", "ivx_object_collision_probes", "ivx_object_collision_probes_sync", "ivx_collision_probes_download",
+    "ivx_object_mesh_gather", "ivx_object_mesh_distributed", "ivx_object_mesh_sync", "ivx_mesh_modifications", "ivx_mesh_report_synchronized", "ivx_object_collision_probes", "ivx_object_collision_probes_sync", "ivx_collision_probes_download", "ivx_objects_mutual_contacts",
 ]
 
 

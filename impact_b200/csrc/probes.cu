@@ -471,3 +471,257 @@ int ivx_collision_probes_download(ivx_ctx* ctx, const ivx_object* obj, float* po
 }
 
 }  // extern "C"
+
+// ---- mutual voxel-object contacts (collidable.rs:859-1050, 1288-1440) ----------------------------------------------------
+// for_each_mutual_voxel_object_contact: the probes of one object that lie in the box of the intersection are taken to the
+// other object's voxel space, where the distance field is sampled trilinearly (2x2x2 samples around the point) for the
+// penetration depth and its gradient for the contact normal; deep inside (uniform chunk, or the clamped minimum distance)
+// the direction from the centre of mass stands in for the normal. One thread per probe point; the contacts keep the
+// order of the points (flag, prefix sum, compaction).
+namespace {
+
+struct MutualArgs2 {
+    // the probing object
+    const float* points;
+    const uint32_t* range_first;  // per selected chunk: first point / first flattened position (n_ranges + 1 entries)
+    const uint32_t* flat_first;
+    uint32_t n_ranges, n_points;
+    float q_from[4], t_from[3], inv_extent_from;
+    float lo[3], hi[3];           // box of the intersection in the probing object's space, expanded
+    // the probed object
+    const DevChunk* chunks;
+    const unsigned char* voxels;
+    uint32_t nb1, nb2, dims[3];
+    float q_into[4], t_into[3], extent_into, inv_extent_into, norm_center[3];
+    uint32_t flip_normal;
+    uint32_t* flag;
+    ivx_voxel_contact* records;
+};
+
+__device__ __forceinline__ f3 rot(const float q[4], f3 v, bool inverse) {  // glam Quat::mul_vec3a (modify.cu quat_rotate)
+    const float s = inverse ? -1.0f : 1.0f;
+    const float bx = s * q[0], by = s * q[1], bz = s * q[2], w = q[3];
+    const float b2 = (bx * bx + by * by) + bz * bz, vb = (v.x * bx + v.y * by) + v.z * bz;
+    const float s1 = w * w - b2, s2 = vb * 2.0f, s3 = w * 2.0f;
+    const float cx = by * v.z - bz * v.y, cy = bz * v.x - bx * v.z, cz = bx * v.y - by * v.x;
+    return mk3((v.x * s1 + bx * s2) + cx * s3, (v.y * s1 + by * s2) + cy * s3, (v.z * s1 + bz * s2) + cz * s3);
+}
+__device__ __forceinline__ bool sign_set(float f) { return (__float_as_uint(f) >> 31) != 0u; }
+__device__ __forceinline__ float voxel_distance(const MutualArgs2& a, uint32_t i, uint32_t j, uint32_t k) {
+    const DevChunk c = a.chunks[((i >> 4) * a.nb1 + (j >> 4)) * a.nb2 + (k >> 4)];
+    if (c.kind == 0) return sd_decode(127);
+    if (c.kind == 1) return sd_decode((int)c.u_sd);
+    const int8_t code = reinterpret_cast<const int8_t*>(a.voxels + (size_t)c.slot * SLOT_BYTES + PLANE_SD)[((i & 15u) << 8) | ((j & 15u) << 4) | (k & 15u)];
+    return sd_decode((int)code);
+}
+__device__ __forceinline__ bool unit_if_above(f3 v, f3& out) {  // normalized_from_if_above(v, 1e-8)
+    const float n2 = dot3(v, v);
+    if (!(n2 > 1e-8f * 1e-8f)) return false;
+    const float n = sqrtf(n2);
+    out = mk3(v.x / n, v.y / n, v.z / n);
+    return true;
+}
+
+__global__ void k_mutual_contacts(MutualArgs2 a) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_points) return;
+    a.flag[t] = 0u;
+    // which selected chunk range this flattened position belongs to
+    uint32_t lo_r = 0, hi_r = a.n_ranges;
+    while (hi_r - lo_r > 1u) {
+        const uint32_t mid = (lo_r + hi_r) >> 1;
+        if (a.flat_first[mid] <= t) lo_r = mid;
+        else hi_r = mid;
+    }
+    const uint32_t pt = a.range_first[lo_r] + (t - a.flat_first[lo_r]);
+    const f3 pf = mk3(a.points[3 * (size_t)pt], a.points[3 * (size_t)pt + 1], a.points[3 * (size_t)pt + 2]);
+    if (sign_set(pf.x - a.lo[0]) || sign_set(pf.y - a.lo[1]) || sign_set(pf.z - a.lo[2]) || sign_set(a.hi[0] - pf.x) ||
+        sign_set(a.hi[1] - pf.y) || sign_set(a.hi[2] - pf.z))
+        return;
+    const f3 world = rot(a.q_from, mk3(pf.x - a.t_from[0], pf.y - a.t_from[1], pf.z - a.t_from[2]), true);
+    const f3 ri = rot(a.q_into, world, false);
+    const f3 p = mk3((ri.x + a.t_into[0]) * a.inv_extent_into, (ri.y + a.t_into[1]) * a.inv_extent_into, (ri.z + a.t_into[2]) * a.inv_extent_into);
+    // determine_sdf_value_and_normal_at_point_if_intersecting
+    const float MIN_SD = 0.02f * -128.0f, HALF_DIAGONAL = 0.5f * 1.7320508f;
+    const f3 nc = mk3(a.norm_center[0], a.norm_center[1], a.norm_center[2]);
+    const f3 lower = mk3(p.x - 0.5f, p.y - 0.5f, p.z - 0.5f);
+    if (sign_set(lower.x) || sign_set(lower.y) || sign_set(lower.z)) return;
+    if (!(lower.x < 4.0e9f && lower.y < 4.0e9f && lower.z < 4.0e9f)) return;  // (`as usize` saturates: beyond any grid; NaN too)
+    const uint32_t li = (uint32_t)lower.x, lj = (uint32_t)lower.y, lk = (uint32_t)lower.z;
+    if ((li + 1u >= a.dims[0]) | (lj + 1u >= a.dims[1]) | (lk + 1u >= a.dims[2])) return;
+    const uint32_t ci = (uint32_t)p.x, cj = (uint32_t)p.y, ck = (uint32_t)p.z;
+    const DevChunk chunk = a.chunks[((ci >> 4) * a.nb1 + (cj >> 4)) * a.nb2 + (ck >> 4)];
+    float sd = MIN_SD;
+    f3 normal;
+    bool deep = chunk.kind == 1;
+    if (chunk.kind == 0) return;
+    if (!deep) {
+        if (voxel_distance(a, ci, cj, ck) > HALF_DIAGONAL) return;
+        const float d[8] = {voxel_distance(a, li, lj, lk),         voxel_distance(a, li, lj, lk + 1),
+                            voxel_distance(a, li, lj + 1, lk),     voxel_distance(a, li, lj + 1, lk + 1),
+                            voxel_distance(a, li + 1, lj, lk),     voxel_distance(a, li + 1, lj, lk + 1),
+                            voxel_distance(a, li + 1, lj + 1, lk), voxel_distance(a, li + 1, lj + 1, lk + 1)};
+        const f3 o = mk3(lower.x - floorf(lower.x), lower.y - floorf(lower.y), lower.z - floorf(lower.z));
+        const f3 r = mk3(1.0f - o.x, 1.0f - o.y, 1.0f - o.z);
+        // evaluate_sdf_from_corner_samples (object/sdf.rs:579-592)
+        const float d00 = d[0] * r.x + d[4] * o.x, d01 = d[1] * r.x + d[5] * o.x;
+        const float d10 = d[2] * r.x + d[6] * o.x, d11 = d[3] * r.x + d[7] * o.x;
+        const float d0 = d00 * r.y + d10 * o.y, d1 = d01 * r.y + d11 * o.y;
+        sd = d0 * r.z + d1 * o.z;
+        if (sd > 0.0f) return;
+        if (fabsf(sd - MIN_SD) < 1e-3f) {
+            deep = true;
+        } else {
+            // compute_sdf_gradient_from_corner_samples (object/sdf.rs:603-633)
+            const f3 e00 = mk3(d[4] - d[0], d[2] - d[0], d[1] - d[0]), e01 = mk3(d[5] - d[1], d[6] - d[4], d[3] - d[2]);
+            const f3 e10 = mk3(d[6] - d[2], d[3] - d[1], d[5] - d[4]), e11 = mk3(d[7] - d[3], d[7] - d[5], d[7] - d[6]);
+            f3 g;
+            g.x = (((r.y * r.z) * e00.x + (r.y * o.z) * e01.x) + (o.y * r.z) * e10.x) + (o.y * o.z) * e11.x;
+            g.y = (((r.z * r.x) * e00.y + (r.z * o.x) * e01.y) + (o.z * r.x) * e10.y) + (o.z * o.x) * e11.y;
+            g.z = (((r.x * r.y) * e00.z + (r.x * o.y) * e01.z) + (o.x * r.y) * e10.z) + (o.x * o.y) * e11.z;
+            if (!unit_if_above(g, normal)) return;
+        }
+    }
+    if (deep) {  // estimate_sdf_value_and_normal_at_point_deep_inside
+        sd = MIN_SD;
+        if (!unit_if_above(mk3(p.x - nc.x, p.y - nc.y, p.z - nc.z), normal)) return;
+    }
+    f3 n = rot(a.q_into, normal, true);
+    if (a.flip_normal) n = mk3(-n.x, -n.y, -n.z);
+    ivx_voxel_contact rec;
+    rec.indices[0] = (uint32_t)(pf.x * a.inv_extent_from);
+    rec.indices[1] = (uint32_t)(pf.y * a.inv_extent_from);
+    rec.indices[2] = (uint32_t)(pf.z * a.inv_extent_from);
+    rec.position[0] = world.x;
+    rec.position[1] = world.y;
+    rec.position[2] = world.z;
+    rec.surface_normal[0] = n.x;
+    rec.surface_normal[1] = n.y;
+    rec.surface_normal[2] = n.z;
+    rec.penetration_depth = -sd * a.extent_into;
+    a.records[t] = rec;
+    a.flag[t] = 1u;
+}
+
+__global__ void k_compact_contacts(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ scan, const ivx_voxel_contact* __restrict__ in,
+                                   uint32_t n, uint32_t capacity, ivx_voxel_contact* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && flag[t] && scan[t] < capacity) out[scan[t]] = in[t];
+}
+
+// the probes of `from` against the distance field of `into` → contacts appended to d_out (device) from `base` on
+int probes_against(ivx_ctx* ctx, const ivx_object* from, const ivx_isometry* world_to_from, const ivx_object* into,
+                   const ivx_inertial_moments* inertial_into, const ivx_isometry* world_to_into, const uint32_t ranges_in_from[6],
+                   float aabb_margin, bool flip_normal, ivx_voxel_contact* d_out, uint32_t base, uint32_t capacity, uint32_t* out_count) {
+    *out_count = 0;
+    const ivx_probes& pr = *from->probes;
+    uint32_t cr[3][2];
+    for (int d = 0; d < 3; ++d) {
+        cr[d][0] = ranges_in_from[2 * d] / 16u;
+        cr[d][1] = std::min(from->nb[d], (ranges_in_from[2 * d + 1] + 15u) / 16u);
+    }
+    std::vector<uint32_t> first, flat;
+    uint32_t total = 0;
+    for (uint32_t i = cr[0][0]; i < cr[0][1]; ++i)
+        for (uint32_t j = cr[1][0]; j < cr[1][1]; ++j)
+            for (uint32_t k = cr[2][0]; k < cr[2][1]; ++k) {
+                const uint32_t c = (i * from->nb[1] + j) * from->nb[2] + k;
+                if (c >= pr.range_of_chunk.size() || !pr.has(c)) continue;
+                first.push_back(pr.range_of_chunk[c].first);
+                flat.push_back(total);
+                total += pr.range_of_chunk[c].second - pr.range_of_chunk[c].first;
+            }
+    if (total == 0) return IVX_OK;
+    flat.push_back(total);
+    first.push_back(0);
+    Tmp tmp(ctx);
+    const uint32_t n_ranges = (uint32_t)first.size() - 1u;
+    uint32_t* d_first = tmp.get<uint32_t>(first.size());
+    uint32_t* d_flat = tmp.get<uint32_t>(flat.size());
+    uint32_t* flag = tmp.get<uint32_t>(total);
+    uint32_t* scan = tmp.get<uint32_t>(total);
+    ivx_voxel_contact* recs = tmp.get<ivx_voxel_contact>(total);
+    if (!d_first || !d_flat || !flag || !scan || !recs) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mutual contacts: out of device memory");
+    cudaStream_t st = ctx->stream;
+    CU(ctx, cudaMemcpyAsync(d_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_flat, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
+    MutualArgs2 a{};
+    a.points = pr.d_points;
+    a.range_first = d_first;
+    a.flat_first = d_flat;
+    a.n_ranges = n_ranges;
+    a.n_points = total;
+    for (int q = 0; q < 4; ++q) {
+        a.q_from[q] = world_to_from->rotation[q];
+        a.q_into[q] = world_to_into->rotation[q];
+    }
+    const float inv_into = 1.0f / into->voxel_extent;
+    for (int d = 0; d < 3; ++d) {
+        a.t_from[d] = world_to_from->translation[d];
+        a.t_into[d] = world_to_into->translation[d];
+        a.lo[d] = from->voxel_extent * (float)ranges_in_from[2 * d] - aabb_margin;
+        a.hi[d] = from->voxel_extent * (float)ranges_in_from[2 * d + 1] + aabb_margin;
+        a.dims[d] = into->nb[d] * 16u;
+        // derive_center_of_mass() * inverse_voxel_extent
+        a.norm_center[d] = (inertial_into->moments[d] / inertial_into->mass) * inv_into;
+    }
+    a.inv_extent_from = 1.0f / from->voxel_extent;
+    a.chunks = into->d_chunks;
+    a.voxels = into->d_voxels;
+    a.nb1 = into->nb[1];
+    a.nb2 = into->nb[2];
+    a.extent_into = into->voxel_extent;
+    a.inv_extent_into = inv_into;
+    a.flip_normal = flip_normal ? 1u : 0u;
+    a.flag = flag;
+    a.records = recs;
+    ctx->launches++;
+    k_mutual_contacts<<<(total + 127) / 128, 128, 0, st>>>(a);
+    CU(ctx, cudaGetLastError());
+    KL(ctx, launch_exclusive_scan(flag, scan, total, ctx->d_scratch + 30, st));
+    ctx->launches++;
+    k_compact_contacts<<<(total + 255) / 256, 256, 0, st>>>(flag, scan, recs, total, capacity > base ? capacity - base : 0u, d_out + base);
+    CU(ctx, cudaGetLastError());
+    uint32_t cnt = 0;
+    if (int rc = ivx_read_words(ctx, ctx->d_scratch + 30, 1, &cnt)) return rc;  // (also keeps `first` / `flat` alive long enough)
+    *out_count = cnt;
+    return IVX_OK;
+}
+
+}  // namespace
+
+extern "C" int ivx_objects_mutual_contacts(ivx_ctx* ctx, const ivx_object* a, const ivx_object* b, const ivx_isometry* world_to_a,
+                                           const ivx_isometry* world_to_b, const uint32_t ranges_in_a[6], const uint32_t ranges_in_b[6],
+                                           const ivx_inertial_moments* inertial_a, const ivx_inertial_moments* inertial_b,
+                                           ivx_voxel_contact* out, size_t capacity, uint64_t* out_count_a_against_b,
+                                           uint64_t* out_count_b_against_a) {
+    if (!ctx || !a || !b || !world_to_a || !world_to_b || !ranges_in_a || !ranges_in_b || !inertial_a || !inertial_b ||
+        !out_count_a_against_b || !out_count_b_against_a)
+        return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    *out_count_a_against_b = *out_count_b_against_a = 0;
+    if (!a->probes || !b->probes) IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "both objects need collision probes: ivx_object_collision_probes");
+    for (const ivx_object* o : {a, b})
+        if (o->derive_pending || o->first_i != 0 || o->nb[0] != o->chunk_counts[0])
+            IVX_FAIL(ctx, IVX_ERR_UNSUPPORTED, "contact queries on a slab-partitioned object are not supported");
+    const uint32_t cap = (uint32_t)std::min<size_t>(capacity, 0xFFFFFFFFu);
+    Tmp tmp(ctx);
+    ivx_voxel_contact* d_out = tmp.get<ivx_voxel_contact>(std::max<size_t>(1, cap));
+    if (!d_out) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mutual contacts: out of device memory");
+    uint32_t n_ab = 0, n_ba = 0;
+    if (int rc = probes_against(ctx, a, world_to_a, b, inertial_b, world_to_b, ranges_in_a, a->voxel_extent, false, d_out, 0, cap, &n_ab))
+        return rc;
+    // (the reference expands B's box by A's voxel extent too, collidable.rs:969-973)
+    if (int rc = probes_against(ctx, b, world_to_b, a, inertial_a, world_to_a, ranges_in_b, a->voxel_extent, true, d_out,
+                                std::min(n_ab, cap), cap, &n_ba))
+        return rc;
+    *out_count_a_against_b = n_ab;
+    *out_count_b_against_a = n_ba;
+    if ((uint64_t)n_ab + n_ba > cap) return out ? IVX_ERR_CAPACITY : IVX_OK;
+    if (out && n_ab + n_ba) {
+        CU(ctx, cudaMemcpyAsync(out, d_out, (size_t)(n_ab + n_ba) * sizeof(ivx_voxel_contact), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return IVX_OK;
+}
+

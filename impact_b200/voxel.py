@@ -494,6 +494,29 @@ def intersection_voxel_ranges(occupied_a, voxel_extent_a: float, occupied_b, vox
     return (ra.reshape(3, 2), rb.reshape(3, 2)) if hit.value else None
 
 
+def mutual_contacts(a: VoxelObject, b: VoxelObject, world_to_a, world_to_b, ranges_in_a, ranges_in_b, moments_a, moments_b):
+    """`for_each_mutual_voxel_object_contact` (collidable.rs:859-1050) for two objects with collision probes: isometries
+    as 7 floats (unit quaternion x, y, z, w; translation), the two 3 x 2 voxel ranges from `intersection_voxel_ranges`, the
+    inertial managers' 10-float moment arrays → (contacts of A's probes in B, contacts of B's probes in A)."""
+    ctx = a.ctx
+    wa, wb = np.ascontiguousarray(world_to_a, np.float32), np.ascontiguousarray(world_to_b, np.float32)
+    ra, rb = np.ascontiguousarray(ranges_in_a, np.uint32).reshape(6), np.ascontiguousarray(ranges_in_b, np.uint32).reshape(6)
+    ma, mb = np.ascontiguousarray(moments_a, np.float32), np.ascontiguousarray(moments_b, np.float32)
+    assert wa.shape == (7,) and wb.shape == (7,) and ma.shape == (10,) and mb.shape == (10,)
+    n_ab, n_ba = C.c_uint64(), C.c_uint64()
+    capacity = 4096
+    while True:
+        out = np.zeros(capacity, L.CONTACT_DTYPE)
+        rc = ctx._lib.ivx_objects_mutual_contacts(ctx.h, a.h, b.h, L.ptr(wa), L.ptr(wb), L.ptr(ra), L.ptr(rb), L.ptr(ma), L.ptr(mb),
+                                                  L.ptr(out), C.c_size_t(capacity), C.byref(n_ab), C.byref(n_ba))
+        if rc == 5 and n_ab.value + n_ba.value > capacity:  # IVX_ERR_CAPACITY
+            capacity = int(n_ab.value + n_ba.value)
+            continue
+        ctx.check(rc)
+        break
+    return out[: n_ab.value].copy(), out[n_ab.value: n_ab.value + n_ba.value].copy()
+
+
 def absorb_mutually(a: VoxelObject, b: VoxelObject, rotation_xyzw, translation, smoothness: float, ranges_in_a,
                     ranges_in_b, voxel_type_densities=None, moments_a=None, moments_b=None):
     """`apply_mutual_absorption` (interaction/absorption.rs:891-1080): `transform_from_b_to_a` = (unit quaternion

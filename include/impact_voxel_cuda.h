@@ -741,6 +741,21 @@ int ivx_object_plane_contacts(ivx_ctx* ctx, const ivx_object* object, const ivx_
 int ivx_object_capsule_contacts(ivx_ctx* ctx, const ivx_object* object, const ivx_isometry* transform_to_object_space,
                                 const float segment_start[3], const float segment_vector[3], float radius,
                                 ivx_voxel_contact* out, size_t capacity, uint64_t* out_count);
+/* for_each_mutual_voxel_object_contact (collidable.rs:859-1050) for two objects that both have collision probes
+ * (ivx_object_collision_probes): the probes of A inside the box of the intersection are sampled in B's distance field
+ * (determine_sdf_value_and_normal_at_point_if_intersecting, :1288-1440: trilinear value → penetration depth, gradient →
+ * normal; centre of mass direction where the field is clamped), then B's probes in A with the normal flipped. The shim
+ * keeps `transform_from_b_to_a = world_to_a * world_to_b.inverted()` and the ranges
+ * (ivx_intersection_voxel_ranges, like for ivx_objects_absorb_mutually) and returns early when there is no intersection.
+ * Only mass and moments of the inertial managers are read (derive_center_of_mass). Records: indices = voxel of the
+ * probing object the probe lies in (the reference's contact id is [0, i, j, k]); first the out_count_a_against_b
+ * contacts of A's probes, then B's; within each, ascending chunk and point order (the reference walks a HashMap).
+ * IVX_ERR_CAPACITY with both counts set when `capacity` is too small. */
+int ivx_objects_mutual_contacts(ivx_ctx* ctx, const ivx_object* object_a, const ivx_object* object_b,
+                                const ivx_isometry* world_to_a, const ivx_isometry* world_to_b, const uint32_t ranges_in_a[6],
+                                const uint32_t ranges_in_b[6], const ivx_inertial_moments* inertial_a,
+                                const ivx_inertial_moments* inertial_b, ivx_voxel_contact* out, size_t capacity,
+                                uint64_t* out_count_a_against_b, uint64_t* out_count_b_against_a);
 int ivx_object_surface_voxels_touching_sphere(ivx_ctx* ctx, const ivx_object* object, const float center[3], float radius,
                                               ivx_surface_voxel* out, size_t capacity, uint64_t* out_count);
 int ivx_object_surface_voxels_touching_capsule(ivx_ctx* ctx, const ivx_object* object, const float segment_start[3],

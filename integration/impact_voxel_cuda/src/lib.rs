@@ -142,6 +142,12 @@ dynamic_lib::define_lib! {
     unsafe fn ivx_object_collision_probes_sync(ctx: *mut IvxCtx, object: *mut IvxObject, out: *mut IvxProbesInfo) -> i32;
     unsafe fn ivx_collision_probes_download(ctx: *mut IvxCtx, object: *const IvxObject, points: *mut f32, capacity_points: usize,
                                             ranges: *mut IvxProbeRange, capacity_ranges: usize) -> i32;
+    unsafe fn ivx_objects_mutual_contacts(ctx: *mut IvxCtx, object_a: *const IvxObject, object_b: *const IvxObject,
+                                          world_to_a: *const IvxIsometry, world_to_b: *const IvxIsometry,
+                                          ranges_in_a: *const u32, ranges_in_b: *const u32,
+                                          inertial_a: *const IvxInertialMoments, inertial_b: *const IvxInertialMoments,
+                                          out: *mut IvxVoxelContact, capacity: usize, out_count_a_against_b: *mut u64,
+                                          out_count_b_against_a: *mut u64) -> i32;
     unsafe fn ivx_object_free(ctx: *mut IvxCtx, object: *mut IvxObject) -> ();
 }
 /// one call of the closures of `for_each_surface_voxel_*`: indices, the voxel, `VoxelSurfacePlacement` as u8

@@ -382,6 +382,37 @@ void orc_probes_copy(const void* pp, float* points, uint32_t* ranges) {
     }
 }
 void orc_probes_free(void* pp) { delete (CollisionProbes*)pp; }
+// for_each_mutual_voxel_object_contact: isometries as 7 floats (quaternion x, y, z, w, translation), moments as 10 floats
+// (mass, moments, ...), ranges as [dim][start, end]. → the two contact lists concatenated; counts[0] = A against B
+uint32_t orc_mutual_contacts(const void* oa, const void* pa, const float* moments_a, const float* world_to_a, const void* ob,
+                             const void* pb, const float* moments_b, const float* world_to_b, const uint32_t* ranges_in_a,
+                             const uint32_t* ranges_in_b, VoxelContact* out, uint32_t capacity, uint32_t* counts) {
+    const auto iso = [](const float* f) { return Isometry{Quat{f[0], f[1], f[2], f[3]}, v3(f[4], f[5], f[6])}; };
+    InertialMoments ia, ib;
+    ia.mass = moments_a[0];
+    ib.mass = moments_b[0];
+    for (int d = 0; d < 3; ++d) {
+        ia.moments[d] = moments_a[1 + d];
+        ib.moments[d] = moments_b[1 + d];
+    }
+    uint32_t ra[3][2], rb[3][2];
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) {
+            ra[d][s] = ranges_in_a[2 * d + s];
+            rb[d][s] = ranges_in_b[2 * d + s];
+        }
+    std::vector<VoxelContact> ab, ba;
+    mutual_voxel_object_contacts(*(const Object*)oa, *(const CollisionProbes*)pa, ia, iso(world_to_a), *(const Object*)ob,
+                                 *(const CollisionProbes*)pb, ib, iso(world_to_b), ra, rb, ab, ba);
+    counts[0] = (uint32_t)ab.size();
+    counts[1] = (uint32_t)ba.size();
+    const uint32_t n = counts[0] + counts[1];
+    if (out && n <= capacity) {
+        if (!ab.empty()) std::memcpy(out, ab.data(), ab.size() * sizeof(VoxelContact));
+        if (!ba.empty()) std::memcpy(out + ab.size(), ba.data(), ba.size() * sizeof(VoxelContact));
+    }
+    return n;
+}
 // add_points_for_vertices_in_blocks on caller-provided data (unit tests)
 uint32_t orc_probes_points_for_chunk(uint32_t log2_block_size, const uint32_t* chunk_indices, const float* positions,
                                      const float* normals, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,

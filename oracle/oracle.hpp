@@ -320,6 +320,14 @@ void probes_points_for_chunk(uint32_t log2_block_size, const uint32_t chunk_indi
                              float inverse_voxel_extent, std::vector<float>& points);
 void probes_compute_for_all_chunks(const Object& obj, const Mesh& mesh, CollisionProbes& pr);
 void probes_sync(const Object& obj, const SyncedMesh& sm, const uint32_t* dirty, size_t n_dirty, CollisionProbes& pr);
+struct VoxelContact;
+struct Isometry;
+struct InertialMoments;
+void mutual_voxel_object_contacts(const Object& a, const CollisionProbes& probes_a, const InertialMoments& inertial_a,
+                                  const Isometry& world_to_a, const Object& b, const CollisionProbes& probes_b,
+                                  const InertialMoments& inertial_b, const Isometry& world_to_b, const uint32_t ranges_in_a[3][2],
+                                  const uint32_t ranges_in_b[3][2], std::vector<VoxelContact>& a_against_b,
+                                  std::vector<VoxelContact>& b_against_a);
 
 // --- inertial properties (object/inertia.rs) ----------------------------------
 // VoxelObjectInertialPropertyManager (inertia.rs:19-25): mass, moments (m x), moments of inertia, products of inertia,

@@ -623,3 +623,21 @@ def probes_points_for_chunk(log2_block_size, chunk_indices, positions, normals, 
                                           C.c_uint32(len(idx)), C.c_uint32(start_index), C.c_float(inverse_voxel_extent),
                                           _p(out), C.c_uint32(len(out)))
     return out[:n].copy()
+
+
+def mutual_contacts(obj_a: "Object", probes_a: "CollisionProbes", moments_a, world_to_a, obj_b: "Object",
+                    probes_b: "CollisionProbes", moments_b, world_to_b, ranges_in_a, ranges_in_b):
+    """`for_each_mutual_voxel_object_contact` (collidable.rs:859-1050) given the voxel ranges encompassing the intersection:
+    isometries as 7 floats (unit quaternion x, y, z, w; translation), moments as the managers' 10 floats →
+    (contacts of A's probes in B, contacts of B's probes in A), each in ascending chunk / point order."""
+    ma, mb = np.ascontiguousarray(moments_a, np.float32), np.ascontiguousarray(moments_b, np.float32)
+    wa, wb = np.ascontiguousarray(world_to_a, np.float32), np.ascontiguousarray(world_to_b, np.float32)
+    ra, rb = np.ascontiguousarray(ranges_in_a, np.uint32).reshape(6), np.ascontiguousarray(ranges_in_b, np.uint32).reshape(6)
+    assert ma.shape == (10,) and mb.shape == (10,) and wa.shape == (7,) and wb.shape == (7,)
+    counts = np.zeros(2, np.uint32)
+    lib().orc_mutual_contacts.restype = C.c_uint32
+    args = (obj_a.h, probes_a.h, _p(ma), _p(wa), obj_b.h, probes_b.h, _p(mb), _p(wb), _p(ra), _p(rb))
+    n = lib().orc_mutual_contacts(*args, None, C.c_uint32(0), _p(counts))
+    out = np.zeros(max(1, n), Object.CONTACT_DTYPE)
+    lib().orc_mutual_contacts(*args, _p(out), C.c_uint32(len(out)), _p(counts))
+    return out[: counts[0]].copy(), out[counts[0]: n].copy()
