@@ -501,6 +501,10 @@ int ivx_object_resolve_connected_regions(ivx_ctx* ctx, ivx_object* obj, ivx_spli
     // what they needed, so a guess that turns out too small costs one more pass, not a wrong answer.
     uint32_t region_cap = std::max(obj->region_cap, n + 1024u);
     uint32_t record_cap = obj->region_records ? obj->region_records + obj->region_records / 4u + 4096u : std::max<uint32_t>(4096u, 4u * n);
+    if (std::getenv("IVX_REGIONS_TINY_CAPACITIES")) {  // tests: every capacity starts too small, the retries find the sizes
+        region_cap = std::max(obj->region_cap, 8u);
+        record_cap = 16u;
+    }
     uint32_t* words = ctx->d_scratch + 64;  // RegionWord
     uint32_t h[RW_COUNT];
 

@@ -67,6 +67,17 @@ def test_connected_regions_match_the_oracle(ctx, oracle, name):
         assert g["n_regions"] == expected
 
 
+def test_capacities_that_start_too_small_are_found_by_retrying(ctx, oracle, monkeypatch):
+    # the per-region arrays, the connection records and the tree-pair table are sized from the previous resolve; a
+    # kernel that needs more reports it and the pass runs again. IVX_REGIONS_TINY_CAPACITIES starts all of them at
+    # almost nothing: same result, region for region.
+    monkeypatch.setenv("IVX_REGIONS_TINY_CAPACITIES", "1")
+    make, types, expected = CASES["noisy_debris"]
+    obj_gpu, obj_cpu = _both(ctx, oracle, make(), types)
+    assert_split_equal(obj_gpu, obj_cpu)
+    assert_split_equal(obj_gpu, obj_cpu)  # and again, with the object's own capacities in place
+
+
 def test_absorption_splits_a_dumbbell(ctx, oracle):
     from impact_b200.graph import SDFGraph
 
