@@ -175,7 +175,10 @@ int plan_eval_stack(ivx_ctx* ctx, uint32_t max_depth, Tmp& tmp, uint32_t n_activ
     const int need = max_depth > 0 ? (int)max_depth - 1 : 0;
     // most specialised programs need one or two operand levels; keeping the shared-memory share small
     // lets several CTAs share an SM, the rare deeper levels go to an L2-resident spill buffer
-    const int smem_levels = std::min(need, 2);
+#ifndef IVX_EVAL_SMEM_LEVELS
+#define IVX_EVAL_SMEM_LEVELS 2
+#endif
+    const int smem_levels = std::min(need, IVX_EVAL_SMEM_LEVELS);
     ea.smem_levels = smem_levels;
     ea.spill_levels = need - smem_levels;
     int bps = eval_max_blocks_per_sm(smem_levels);

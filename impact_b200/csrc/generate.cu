@@ -971,7 +971,10 @@ __device__ __forceinline__ float* stack_level(float* smem_stack, float* spill, i
     return level < smem_levels ? smem_stack + (size_t)level * 4096 : spill + (size_t)(level - smem_levels) * 4096;
 }
 
-__global__ void __launch_bounds__(EVAL_THREADS, 3) k_eval(EvalArgs a) {
+#ifndef IVX_EVAL_CTAS
+#define IVX_EVAL_CTAS 3
+#endif
+__global__ void __launch_bounds__(EVAL_THREADS, IVX_EVAL_CTAS) k_eval(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_stack = reinterpret_cast<float*>(smem_raw);
     __shared__ float s_coord[48];
