@@ -125,32 +125,43 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
         // chunk-level pass; it is the same rule): a voxel v with a linked LOWER neighbour joins the set of the lowest one,
         // a(v), when that one is visited and stays with it, so chasing a() to a voxel without lower neighbours gives
         // trees that are merged wholesale; only links between different trees can move a root, and they are replayed in
-        // visiting order by one lane. Voxels are taken 32 at a time in increasing order, so a(v) of earlier batches is
-        // already a tree root and the chase is two or three steps.
+        // visiting order by one lane.
         //   link u -> u + 256: u present and HAS_ADJACENT_X_UP; u -> u + 16: Y_UP; u -> u + 1: Z_UP and u + 1 present
         uint16_t* s_events = reinterpret_cast<uint16_t*>(s_lab);  // (absorbing tree, absorbed tree) pairs; labels come later
         constexpr uint32_t MAX_EVENTS = 1024;
-        for (uint32_t base = 0; base < 4096u; base += 32u) {
-            const uint32_t idx = base + (uint32_t)lane, vi = idx >> 8, vj = (idx >> 4) & 15u, vk = idx & 15u;
-            uint32_t a = idx;
-            if (vi > 0u) {
-                const uint32_t fu = s_flags[idx - 256u];
-                if ((fu & 1u) == 0u && (fu & 0x20u)) a = idx - 256u;
+        // a(v) for every voxel (independent of each other), then six rounds of pointer jumping: a() goes down by 256, 16
+        // or 1, so a chain has at most 45 links and par[v] <- par[par[v]] reaches its end in six rounds. A round reads
+        // entries other lanes may be rewriting; every value it can see is an ancestor on the same chain at least as far
+        // up as the previous round guaranteed, so the in-place rounds converge like separate ones. (The accesses are
+        // volatile: grouped four at a time by hand so that four loads are in flight per lane.)
+        for (uint32_t base = 0; base < 4096u; base += 128u) {
+            uint32_t a4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t idx = base + 32u * u + (uint32_t)lane, vi = idx >> 8, vj = (idx >> 4) & 15u, vk = idx & 15u;
+                const uint32_t f_x = vi > 0u ? s_flags[idx - 256u] : 1u, f_y = vj > 0u ? s_flags[idx - 16u] : 1u;
+                const uint32_t f_z = (vk > 0u && (s_flags[idx] & 1u) == 0u) ? s_flags[idx - 1u] : 1u;
+                uint32_t a = idx;
+                if ((f_z & 1u) == 0u && (f_z & 0x80u)) a = idx - 1u;
+                if ((f_y & 1u) == 0u && (f_y & 0x40u)) a = idx - 16u;
+                if ((f_x & 1u) == 0u && (f_x & 0x20u)) a = idx - 256u;  // the lowest linked neighbour wins
+                a4[u] = a;
             }
-            if (a == idx && vj > 0u) {
-                const uint32_t fu = s_flags[idx - 16u];
-                if ((fu & 1u) == 0u && (fu & 0x40u)) a = idx - 16u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s_par[base + 32u * u + (uint32_t)lane] = (uint16_t)a4[u];
+        }
+        __syncwarp();
+        for (int round = 0; round < 6; ++round) {
+            for (uint32_t base = 0; base < 4096u; base += 128u) {
+                uint32_t p4[4], g4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) p4[u] = s_par[base + 32u * u + (uint32_t)lane];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) g4[u] = s_par[p4[u]];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (g4[u] != p4[u]) s_par[base + 32u * u + (uint32_t)lane] = (uint16_t)g4[u];
             }
-            if (a == idx && vk > 0u && (s_flags[idx] & 1u) == 0u) {
-                const uint32_t fu = s_flags[idx - 1u];
-                if ((fu & 1u) == 0u && (fu & 0x80u)) a = idx - 1u;
-            }
-            s_par[idx] = (uint16_t)a;
-            __syncwarp();
-            uint32_t x = a, up;
-            while ((up = s_par[x]) != x) x = up;
-            __syncwarp();
-            s_par[idx] = (uint16_t)x;
             __syncwarp();
         }
         // links between different trees, in visiting order. Most links repeat a pair of trees that an earlier link has
@@ -179,12 +190,19 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
         __syncwarp();
         uint32_t n_events = 0;
         bool overflow = false;
-        for (uint32_t base = 0; base < 4096u; base += 32u) {
-            const uint32_t idx = base + (uint32_t)lane, vi = idx >> 8, vj = (idx >> 4) & 15u, vk = idx & 15u;
-            const uint32_t f = s_flags[idx];
-            uint32_t other[3], keys[3], count = 0;
-            if ((f & 1u) == 0u) {
-                const uint32_t mine = s_par[idx];
+        // 128 voxels per step, four consecutive ones per lane (their loads overlap; the forest is only read here: plain
+        // loads): the links of a lane come out in voxel order, the lanes in order behind each other
+        const uint16_t* par = const_cast<const uint16_t*>(s_par);
+        for (uint32_t base = 0; base < 4096u; base += 128u) {
+            uint32_t mine4[4], other[12], keys[12], count = 0;
+            uint8_t owner[12];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t idx = base + 4u * (uint32_t)lane + (uint32_t)u, vi = idx >> 8, vj = (idx >> 4) & 15u, vk = idx & 15u;
+                const uint32_t f = s_flags[idx];
+                mine4[u] = par[idx];
+                if ((f & 1u) != 0u) continue;
+                const uint32_t mine = mine4[u];
                 const uint32_t w3[3] = {idx + 256u, idx + 16u, idx + 1u};
                 const uint32_t bit3[3] = {0x20u, 0x40u, 0x80u};
                 const bool linked[3] = {vi < 15u && (f & 0x20u) != 0u, vj < 15u && (f & 0x40u) != 0u,
@@ -193,7 +211,7 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     if (!linked[d]) continue;
-                    const uint32_t theirs = s_par[w3[d]];
+                    const uint32_t theirs = par[w3[d]];
                     if (theirs == mine) continue;
                     if (my_step == 0xFFFFFFFFu) my_step = lowest_step(idx);
                     if (my_step != 0u && my_step != (w3[d] - idx) && lowest_step(w3[d]) == my_step) {
@@ -206,6 +224,7 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
                     if (s_seen[(key * 0x9E3779B1u) >> 24] == key) continue;
                     other[count] = theirs;
                     keys[count] = key;
+                    owner[count] = (uint8_t)u;
                     count++;
                 }
             }
@@ -225,7 +244,7 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
                 break;
             }
             for (uint32_t q = 0; q < count; ++q) {
-                s_events[2u * (n_events + offset + q)] = (uint16_t)s_par[idx];
+                s_events[2u * (n_events + offset + q)] = (uint16_t)mine4[owner[q]];
                 s_events[2u * (n_events + offset + q) + 1u] = (uint16_t)other[q];
             }
             n_events += batch;
@@ -349,11 +368,16 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
         }
         __syncwarp();
         // ---- every other non-empty voxel takes its root's label (:837-855) ----
-        for (int idx = lane; idx < 4096; idx += 32) {
-            if (s_flags[idx] & 1u) continue;
-            uint32_t r = idx;
-            while (s_par[r] != r) r = s_par[r];
-            if (r != (uint32_t)idx) s_lab[idx] = s_lab[r];
+        {
+            // nobody writes the forest any more: plain loads, four voxels in flight per lane
+            const uint16_t* par = const_cast<const uint16_t*>(s_par);
+#pragma unroll 4
+            for (int idx = lane; idx < 4096; idx += 32) {
+                if (s_flags[idx] & 1u) continue;
+                uint32_t r = idx;
+                while (par[r] != r) r = par[r];
+                if (r != (uint32_t)idx) s_lab[idx] = s_lab[r];
+            }
         }
         __syncwarp();
 #pragma unroll
