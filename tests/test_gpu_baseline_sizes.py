@@ -123,3 +123,34 @@ def test_config5_fracture_sequence_matches_step_by_step(ctx):
     assert (mesh.n_vertices, mesh.n_indices) == (want["vertices"], want["indices"])
     assert _mesh_digest(mesh.download()) == want["mesh"]
     obj.free()
+
+
+def test_config5_split_handling_matches_the_oracle_at_512(ctx, oracle):
+    """Config 5's split handler at the size of config 3 (472 x 412 x 498, ~10^4 local regions), live against the oracle: after
+    every absorption the roots of all local regions, the two reported regions and the extraction that follows."""
+    import bench
+    from test_gpu_split_detection import assert_split_equal
+    graph, types, _ = bench.make_workload("asteroid512")
+    obj_cpu = oracle.Object.generate(oracle.VoxelGenerator(oracle.Generator(graph.nodes(), graph.root_node_id), 1.0, types), 16)
+    obj_gpu = VoxelObject.generate(SDFVoxelGenerator(1.0, ctx.build_generator(graph), types))
+    shape = np.array(obj_cpu.info()["chunk_counts"]) * 16
+    R = 0.5 * float(shape.max())
+    radius = np.float32(0.15 * R)
+    start = (0.5 * shape - R / np.sqrt(3.0)).astype(np.float32)
+    d = np.float32(1.0 / np.sqrt(3.0))
+    pieces = 0
+    for step in range(6):
+        c = (start + np.float32(step) * radius * d).astype(np.float32)
+        obj_cpu.absorb_sphere(c, float(radius), float(radius + 2.0))
+        obj_gpu.absorb_sphere(c, float(radius), float(radius + 2.0))
+        g = assert_split_equal(obj_gpu, obj_cpu)
+        for _ in range(4):  # split pieces off while there are any, piece by piece like the engine
+            if g["n_regions"] < 2:
+                break
+            ic, ec = obj_cpu.extract_any_disconnected_region()
+            ig, eg = obj_gpu.extract_any_disconnected_region()
+            for k in ("found_two", "extracted", "discarded", "single_chunk"):
+                assert bool(ig[k]) == bool(ic[k]), (step, k)
+            pieces += 1
+            g = assert_split_equal(obj_gpu, obj_cpu)
+    assert g["n_local_regions"] > 5000
