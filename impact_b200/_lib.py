@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "ivx_meta_compile", "ivx_program_eval_chunks", "ivx_program_eval_blocks", "ivx_object_generate", "ivx_object_generate_streamed", "ivx_object_generate_slab", "ivx_program_plane_work", "ivx_object_halo_capacity", "ivx_object_halo_export",
     "ivx_object_halo_import", "ivx_object_slab_classify", "ivx_object_halo_kinds_export", "ivx_object_halo_kinds_import",
     "ivx_object_slab_finalize", "ivx_object_info_get",
-    "ivx_object_download", "ivx_object_download_async", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_peer_alloc", "ivx_peer_free", "ivx_peer_open", "ivx_peer_close", "ivx_mesh_push", "ivx_object_absorb_sphere", "ivx_object_absorb_capsule",
+    "ivx_object_download", "ivx_object_download_async", "ivx_object_free", "ivx_object_mesh", "ivx_mesh_download", "ivx_mesh_download_checked", "ivx_peer_alloc", "ivx_peer_free", "ivx_peer_open", "ivx_peer_close", "ivx_mesh_push", "ivx_object_absorb_sphere", "ivx_object_absorb_capsule",
     "ivx_object_dirty_chunks", "ivx_object_remesh_dirty",
     "ivx_object_resolve_connected_regions", "ivx_object_split_detection_download", "ivx_object_extract_disconnected_region",
     "ivx_object_from_generated_chunks", "ivx_object_inertial_moments", "ivx_object_absorb_sphere_inertial", "ivx_object_absorb_capsule_inertial",

@@ -1105,12 +1105,25 @@ int ivx_program_upload(ivx_ctx* ctx, const ivx_node* nodes, uint32_t n_nodes, ui
     if (!ctx || !out || (n_nodes && !nodes) || !domain_lo || !domain_hi) return IVX_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     cudaSetDevice(ctx->device);
-    for (uint32_t i = 0; i < n_nodes; ++i)
-        if (nodes[i].kind > IVX_INTERSECTION) IVX_FAIL(ctx, IVX_ERR_GRAPH, "Invalid SDF node kind %u", nodes[i].kind);
+    // The list is a post-order program: walk it like the evaluators will (primitives push, transforms and noise replace the
+    // top, combinations pop two and push one) instead of trusting the caller — an operator without its operands would make
+    // the kernels read below their operand stacks.
+    uint32_t depth = 0, max_depth = 0;
+    for (uint32_t i = 0; i < n_nodes; ++i) {
+        const uint32_t kind = nodes[i].kind;
+        if (kind > IVX_INTERSECTION) IVX_FAIL(ctx, IVX_ERR_GRAPH, "Invalid SDF node kind %u", kind);
+        const uint32_t operands = kind <= IVX_BOX ? 0u : (kind <= IVX_MULTIFRACTAL_NOISE ? 1u : 2u);
+        if (depth < operands) IVX_FAIL(ctx, IVX_ERR_GRAPH, "SDF program node %u (kind %u) has %u of its %u operands", i, kind, depth, operands);
+        depth = depth - operands + 1u;
+        max_depth = std::max(max_depth, depth);
+        if (kind == IVX_MULTIFRACTAL_NOISE && nodes[i].octaves > 64u)
+            IVX_FAIL(ctx, IVX_ERR_GRAPH, "SDF program node %u: %u noise octaves", i, nodes[i].octaves);
+    }
+    if (n_nodes && depth != 1u) IVX_FAIL(ctx, IVX_ERR_GRAPH, "SDF program leaves %u values instead of one", depth);
     ivx_program* p = new (std::nothrow) ivx_program();
     if (!p) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "host allocation failed");
     p->host.nodes.assign(nodes, nodes + n_nodes);
-    p->host.stack_depth = stack_depth;
+    p->host.stack_depth = std::max(stack_depth, max_depth);
     for (int d = 0; d < 3; ++d) {
         p->host.domain_lo[d] = domain_lo[d];
         p->host.domain_hi[d] = domain_hi[d];
@@ -1720,6 +1733,18 @@ int ivx_object_mesh(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
     cudaSetDevice(ctx->device);
     uint32_t counts[4];
     return ivx_internal_mesh(ctx, obj, true, counts, out);
+}
+
+int ivx_mesh_download_checked(ivx_ctx* ctx, const ivx_object* obj, uint32_t n_vertices, uint32_t n_indices, uint32_t n_submeshes,
+                              float* positions, float* normals, ivx_index_materials* index_materials, uint32_t* indices,
+                              ivx_chunk_submesh* submeshes, uint32_t* vertex_ranges) {
+    if (!ctx || !obj) return IVX_ERR_INVALID_ARGUMENT;
+    const DeviceMesh& m = obj->mesh;
+    if (m.n_vertices != n_vertices || m.n_indices != n_indices || m.n_submeshes != n_submeshes)
+        IVX_FAIL(ctx, IVX_ERR_INVALID_ARGUMENT, "the object's mesh (%u vertices, %u indices, %u submeshes) is not the one these buffers "
+                 "were sized for (%u, %u, %u): it was re-created or patched since", m.n_vertices, m.n_indices, m.n_submeshes,
+                 n_vertices, n_indices, n_submeshes);
+    return ivx_mesh_download(ctx, obj, positions, normals, index_materials, indices, submeshes, vertex_ranges);
 }
 
 int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* obj, float* positions, float* normals,

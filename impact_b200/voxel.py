@@ -604,7 +604,10 @@ class VoxelObjectMesh:
         sm = np.zeros(self.n_submeshes, L.SUBMESH_DTYPE)
         vr = np.zeros((self.n_submeshes, 2), np.uint32)
         ctx = self.obj.ctx
-        ctx.check(ctx._lib.ivx_mesh_download(ctx.h, self.obj.h, L.ptr(pos), L.ptr(nrm), L.ptr(im), L.ptr(idx), L.ptr(sm), L.ptr(vr)))
+        # (the checked form: a handle made before a later create / sync of the same object must not be read with its sizes)
+        ctx.check(ctx._lib.ivx_mesh_download_checked(ctx.h, self.obj.h, C.c_uint32(self.n_vertices), C.c_uint32(self.n_indices),
+                                                     C.c_uint32(self.n_submeshes), L.ptr(pos), L.ptr(nrm), L.ptr(im), L.ptr(idx),
+                                                     L.ptr(sm), L.ptr(vr)))
         return {"positions": pos, "normals": nrm, "index_materials": im, "indices": idx, "submeshes": sm,
                 "vertex_ranges": vr}
 

@@ -450,6 +450,11 @@ int ivx_object_download_async(ivx_ctx* ctx, ivx_object* object, ivx_chunk_desc* 
 int ivx_mesh_download(ivx_ctx* ctx, const ivx_object* object, float* positions, float* normals,
                       ivx_index_materials* index_materials, uint32_t* indices,
                       ivx_chunk_submesh* submeshes, uint32_t* vertex_ranges);
+/* The same for a caller that sized its buffers from an earlier ivx_mesh_info: IVX_ERR_INVALID_ARGUMENT (nothing copied)
+ * when the object's mesh no longer has those sizes — it was re-created, patched (ivx_object_remesh_dirty) or synced since. */
+int ivx_mesh_download_checked(ivx_ctx* ctx, const ivx_object* object, uint32_t n_vertices, uint32_t n_indices,
+                              uint32_t n_submeshes, float* positions, float* normals, ivx_index_materials* index_materials,
+                              uint32_t* indices, ivx_chunk_submesh* submeshes, uint32_t* vertex_ranges);
 
 /* ---- multi-GPU mesh gather over peer memory ------------------------------
  * VoxelObjectMesh::recreate appends the chunk meshes in linear chunk order (mesh.rs:286-354); with x-slabs on several

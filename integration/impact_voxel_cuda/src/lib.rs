@@ -66,6 +66,10 @@ dynamic_lib::define_lib! {
     unsafe fn ivx_mesh_download(ctx: *mut IvxCtx, object: *const IvxObject, positions: *mut f32, normals: *mut f32,
                                 index_materials: *mut VoxelMeshIndexMaterials, indices: *mut u32,
                                 submeshes: *mut ChunkSubmesh, vertex_ranges: *mut u32) -> i32;
+    unsafe fn ivx_mesh_download_checked(ctx: *mut IvxCtx, object: *const IvxObject, n_vertices: u32, n_indices: u32,
+                                        n_submeshes: u32, positions: *mut f32, normals: *mut f32,
+                                        index_materials: *mut VoxelMeshIndexMaterials, indices: *mut u32,
+                                        submeshes: *mut ChunkSubmesh, vertex_ranges: *mut u32) -> i32;
     unsafe fn ivx_object_absorb_sphere(ctx: *mut IvxCtx, object: *mut IvxObject, center: *const f32, radius: f32,
                                        influence_radius: f32, stats: *mut IvxAbsorbStats) -> i32;
     unsafe fn ivx_object_absorb_capsule(ctx: *mut IvxCtx, object: *mut IvxObject, segment_start: *const f32,
