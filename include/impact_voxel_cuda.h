@@ -409,10 +409,14 @@ int ivx_object_from_generated_chunks(ivx_ctx* ctx, float voxel_extent, const uin
 int ivx_object_generate_slab(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
                              const ivx_type_generator* type_generator, uint32_t chunk_i_begin,
                              uint32_t chunk_i_end, ivx_object** out_object);
-/* Work estimate per chunk plane of the x-major chunk grid (arbitrary integer units), for partitioning the
- * planes into slabs of equal work instead of equal thickness: the conservative program-specialisation levels of
- * generation run over the whole grid and classify 2^3-chunk blocks as void / inside / undecided. Deterministic, so
- * every rank that calls it derives the same partition. out_work may be NULL to query *out_planes only. */
+/* Work per chunk plane of the x-major chunk grid (arbitrary integer units), for partitioning the planes into slabs of
+ * equal work instead of equal thickness. Planning by doing: the first request for a (program content, voxel extent, type
+ * generator) generates the whole object once on the calling device and counts, per plane, the chunks the SDF program ran
+ * on and the chunks that needed voxel types; the result is kept with the context, so asking again — also for a program
+ * rebuilt from the same nodes — costs nothing. When the object's storage bound does not fit the device, or with
+ * IVX_PLANE_WORK=estimate in the environment, the conservative program-specialisation levels alone classify 2^3-chunk
+ * blocks as void / inside / undecided and weigh them. Deterministic either way, so every rank that calls it derives the
+ * same partition. out_work may be NULL to query *out_planes only. */
 int ivx_program_plane_work(ivx_ctx* ctx, const ivx_program* program, float voxel_extent,
                            const ivx_type_generator* type_generator, uint32_t* out_work, uint32_t capacity,
                            uint32_t* out_planes);
