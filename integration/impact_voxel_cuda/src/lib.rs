@@ -16,6 +16,8 @@ use std::ffi::{c_char, c_void};
 #[repr(C)] pub struct IvxChunkDesc { pub kind: u8, pub flags: u8, pub face: [u8; 6], pub uniform_voxel: [u8; 3],
                                      pub _pad: u8, pub data_offset: u32 }
 #[repr(C)] pub struct IvxObjectInfo { /* include/impact_voxel_cuda.h: ivx_object_info */ }
+#[repr(C)] pub struct IvxNode        { /* include/impact_voxel_cuda.h: ivx_node (ProcessedSDFNode, 144 bytes) */ }
+#[repr(C)] pub struct IvxProgramInfo { /* include/impact_voxel_cuda.h: ivx_program_info */ }
 #[repr(C)] pub struct IvxMeshInfo   { /* include/impact_voxel_cuda.h: ivx_mesh_info   */ }
 #[repr(C)] pub struct IvxAbsorbStats { pub touched_chunks: u32, pub touched_voxels: u32, pub emptied_voxels: u32,
                                        pub removed_chunks: u32, pub dirty_chunks: u32 }
@@ -152,6 +154,68 @@ dynamic_lib::define_lib! {
                                           inertial_a: *const IvxInertialMoments, inertial_b: *const IvxInertialMoments,
                                           out: *mut IvxVoxelContact, capacity: usize, out_count_a_against_b: *mut u64,
                                           out_count_b_against_a: *mut u64) -> i32;
+    // ---- the rest of include/impact_voxel_cuda.h (generated by tools/gen_rust_bindings.py from the prototypes) ----
+    unsafe fn ivx_abi_version() -> u32;
+    unsafe fn ivx_kernel_launch_count(ctx: *const IvxCtx) -> u64;
+    unsafe fn ivx_profile_enable(ctx: *mut IvxCtx, enabled: i32) -> i32;
+    unsafe fn ivx_profile_reset(ctx: *mut IvxCtx) -> i32;
+    unsafe fn ivx_profile_get(ctx: *mut IvxCtx, kernel_id: u32, out_total_ms: *mut f64, out_launches: *mut u64) -> i32;
+    unsafe fn ivx_profile_counter(ctx: *mut IvxCtx, counter_id: u32, out_value: *mut u64) -> i32;
+    unsafe fn ivx_program_upload(ctx: *mut IvxCtx, nodes: *const IvxNode, n_nodes: u32, stack_depth: u32,
+                                 domain_lo: *const f32, domain_hi: *const f32, out_program: *mut *mut IvxProgram) -> i32;
+    unsafe fn ivx_program_compile_host(nodes: *const IvxSdfNode, n_nodes: u32, root_node_id: u32, out_nodes: *mut IvxNode,
+                                       capacity: u32, out_count: *mut u32, out_info: *mut IvxProgramInfo, err: *mut c_char,
+                                       err_capacity: usize) -> i32;
+    unsafe fn ivx_program_info_get(ctx: *mut IvxCtx, program: *const IvxProgram, out: *mut IvxProgramInfo) -> i32;
+    unsafe fn ivx_program_nodes(ctx: *mut IvxCtx, program: *const IvxProgram, out: *mut IvxNode, capacity: u32) -> i32;
+    unsafe fn ivx_program_eval_chunks(ctx: *mut IvxCtx, program: *const IvxProgram, chunk_origins: *const f32,
+                                      n_chunks: u32, out_signed_distances: *mut f32) -> i32;
+    unsafe fn ivx_program_eval_blocks(ctx: *mut IvxCtx, program: *const IvxProgram, block_origins: *const f32,
+                                      n_blocks: u32, size: u32, out_signed_distances: *mut f32) -> i32;
+    unsafe fn ivx_object_halo_capacity(ctx: *mut IvxCtx, object: *const IvxObject, out_bytes: *mut usize) -> i32;
+    unsafe fn ivx_object_halo_export(ctx: *mut IvxCtx, object: *const IvxObject, side: i32, device_buffer: *mut c_void,
+                                     capacity: usize, out_bytes: *mut usize) -> i32;
+    unsafe fn ivx_object_halo_import(ctx: *mut IvxCtx, object: *mut IvxObject, side: i32, device_buffer: *const c_void,
+                                     bytes: usize) -> i32;
+    unsafe fn ivx_object_slab_classify(ctx: *mut IvxCtx, object: *mut IvxObject) -> i32;
+    unsafe fn ivx_object_halo_kinds_export(ctx: *mut IvxCtx, object: *const IvxObject, side: i32,
+                                           device_buffer: *mut c_void, capacity: usize) -> i32;
+    unsafe fn ivx_object_halo_kinds_import(ctx: *mut IvxCtx, object: *mut IvxObject, side: i32,
+                                           device_buffer: *const c_void, bytes: usize) -> i32;
+    unsafe fn ivx_object_slab_finalize(ctx: *mut IvxCtx, object: *mut IvxObject) -> i32;
+    unsafe fn ivx_peer_alloc(ctx: *mut IvxCtx, bytes: usize, out_device_ptr: *mut *mut c_void, out_handle: *mut u8) -> i32;
+    unsafe fn ivx_peer_free(ctx: *mut IvxCtx, device_ptr: *mut c_void) -> i32;
+    unsafe fn ivx_peer_open(ctx: *mut IvxCtx, handle: *const u8, out_device_ptr: *mut *mut c_void) -> i32;
+    unsafe fn ivx_peer_close(ctx: *mut IvxCtx, device_ptr: *mut c_void) -> i32;
+    unsafe fn ivx_mesh_push(ctx: *mut IvxCtx, object: *const IvxObject, merged_base: *mut c_void,
+                            field_offsets: *const u64, vertex_base: u32, index_base: u32, submesh_base: u32) -> i32;
+    unsafe fn ivx_object_mesh_sync(ctx: *mut IvxCtx, object: *mut IvxObject, out: *mut IvxMeshInfo) -> i32;
+    unsafe fn ivx_mesh_modifications(ctx: *mut IvxCtx, object: *const IvxObject, out_ranges: *mut u32,
+                                     capacity_records: usize, out_count: *mut u64,
+                                     out_chunks_were_removed: *mut i32) -> i32;
+    unsafe fn ivx_mesh_report_synchronized(ctx: *mut IvxCtx, object: *mut IvxObject) -> i32;
+    unsafe fn ivx_comm_connect_local(ctx: *mut IvxCtx, comm: *mut IvxComm, all_comms: *mut *mut IvxComm) -> i32;
+    unsafe fn ivx_object_mesh_distributed(ctx: *mut IvxCtx, comm: *mut IvxComm, object: *mut IvxObject,
+                                          out_local: *mut IvxMeshInfo, out_bases: *mut u64) -> i32;
+    unsafe fn ivx_box_intersection_bounds(a_lower: *const f32, a_upper: *const f32, b_center: *const f32,
+                                          b_orientation: *const f32, b_half_extents: *const f32, out_in_a: *mut f32,
+                                          out_in_b: *mut f32, out_intersect: *mut i32) -> i32;
+    unsafe fn ivx_object_dirty_chunks(ctx: *mut IvxCtx, object: *const IvxObject, out_linear_indices: *mut u32,
+                                      capacity: u32, out_count: *mut u32) -> i32;
+    unsafe fn ivx_object_plane_contacts(ctx: *mut IvxCtx, object: *const IvxObject,
+                                        transform_to_object_space: *const IvxIsometry, unit_normal: *const f32,
+                                        displacement: f32, out: *mut IvxVoxelContact, capacity: usize,
+                                        out_count: *mut u64) -> i32;
+    unsafe fn ivx_object_capsule_contacts(ctx: *mut IvxCtx, object: *const IvxObject,
+                                          transform_to_object_space: *const IvxIsometry, segment_start: *const f32,
+                                          segment_vector: *const f32, radius: f32, out: *mut IvxVoxelContact,
+                                          capacity: usize, out_count: *mut u64) -> i32;
+    unsafe fn ivx_object_surface_voxels_touching_capsule(ctx: *mut IvxCtx, object: *const IvxObject,
+                                                         segment_start: *const f32, segment_vector: *const f32,
+                                                         radius: f32, out: *mut IvxSurfaceVoxel, capacity: usize,
+                                                         out_count: *mut u64) -> i32;
+    unsafe fn ivx_voxel_ranges_within_plane(occupied: *const u32, unit_normal: *const f32, displacement: f32,
+                                            out_ranges: *mut u32) -> i32;
     unsafe fn ivx_object_free(ctx: *mut IvxCtx, object: *mut IvxObject) -> ();
 }
 /// one call of the closures of `for_each_surface_voxel_*`: indices, the voxel, `VoxelSurfacePlacement` as u8

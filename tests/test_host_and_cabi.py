@@ -26,6 +26,21 @@ def test_library_exports_every_symbol_declared_in_the_header():
     assert lib.ivx_abi_version() == 1
 
 
+def test_the_rust_shim_binds_every_entry_point_with_the_header_s_arity():
+    # integration/impact_voxel_cuda/src/lib.rs is the reference-side binding a maintainer adds; it is not
+    # compiled here (no Rust toolchain), so at least keep it in step with the header: every function, same parameter count
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "impact_voxel_cuda.h")).read(), flags=re.S)
+    shim = open(os.path.join(ROOT, "integration", "impact_voxel_cuda", "src", "lib.rs")).read()
+    protos = re.findall(r"^(?:int|void|const char\*|uint32_t|uint64_t)\s+(ivx_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, re.M | re.S)
+    assert len(protos) >= 75
+    for name, args in protos:
+        m = re.search(r"unsafe fn %s\(([^;]*?)\)\s*->" % name, shim, re.S)
+        assert m, f"{name} is not bound in lib.rs"
+        n_c = 0 if args.strip() in ("", "void") else len(args.split(","))
+        n_rs = 0 if not m.group(1).strip() else len(m.group(1).split(","))
+        assert n_c == n_rs, (name, n_c, n_rs)
+
+
 def test_struct_layouts_match_the_header():
     assert C.sizeof(L.Config) == 24
     assert C.sizeof(L.ProgramInfo) == 32
