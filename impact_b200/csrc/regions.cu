@@ -313,7 +313,8 @@ cudaError_t launch_region_global_pass(const RegionPass& p, uint32_t n_trees_scan
     k_region_event_counts<<<blocks(slots), 256, 0, st>>>(p);
     if (cudaError_t e = launch_exclusive_scan(p.event_count, p.event_offset, n_trees_scan, p.words + RW_EVENTS, st)) return e;
     k_region_events<<<blocks(slots), 256, 0, st>>>(p);
-    const uint32_t shared_trees = (uint32_t)std::max(0, max_shared_bytes - (int)(REPLAY_STAGE * sizeof(uint2)) - 1024) / 4u;
+    uint32_t shared_trees = (uint32_t)std::max(0, max_shared_bytes - (int)(REPLAY_STAGE * sizeof(uint2)) - 1024) / 4u;
+    if (std::getenv("IVX_REGIONS_GLOBAL_FOREST")) shared_trees = 0;  // tests: the path of objects with more trees than fit
     if (cudaError_t e = cudaFuncSetAttribute(k_region_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(shared_trees * 4u)))
         return e;
     k_region_replay<<<1, REPLAY_THREADS, shared_trees * 4u, st>>>(p, shared_trees);

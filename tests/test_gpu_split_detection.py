@@ -78,6 +78,16 @@ def test_capacities_that_start_too_small_are_found_by_retrying(ctx, oracle, monk
     assert_split_equal(obj_gpu, obj_cpu)  # and again, with the object's own capacities in place
 
 
+def test_the_replay_forest_in_global_memory_gives_the_same_roots(ctx, oracle, monkeypatch):
+    # the disjoint-set forest of the replay lives in shared memory while the trees fit (~5 x 10^4); beyond that it is an
+    # array in global memory. IVX_REGIONS_GLOBAL_FOREST takes that path for any object.
+    monkeypatch.setenv("IVX_REGIONS_GLOBAL_FOREST", "1")
+    for name in ("noisy_debris", "two_spheres_unequal"):
+        make, types, expected = CASES[name]
+        obj_gpu, obj_cpu = _both(ctx, oracle, make(), types)
+        assert_split_equal(obj_gpu, obj_cpu)
+
+
 def test_absorption_splits_a_dumbbell(ctx, oracle):
     from impact_b200.graph import SDFGraph
 
