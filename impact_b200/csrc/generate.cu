@@ -110,7 +110,10 @@ __constant__ int8_t c_sample_ijk[14][3] = {{0, 0, 0},   {15, 0, 0},  {0, 15, 0},
 // ---------------------------------------------------------------------------
 constexpr int FOLD_WARPS = 4;
 constexpr int FOLD_TILE = 256;   // instructions classified per phase-1 tile
-constexpr int FOLD_MAX_DEPTH = 64;
+#ifndef IVX_FOLD_MAX_DEPTH
+#define IVX_FOLD_MAX_DEPTH 64
+#endif
+constexpr int FOLD_MAX_DEPTH = IVX_FOLD_MAX_DEPTH;
 
 struct FoldWarpSmem {
     uint8_t cls[FOLD_TILE];
