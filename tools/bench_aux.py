@@ -71,6 +71,39 @@ def main():
                                                  "local_regions": r["n_local_regions"], "connections": r["n_connections"],
                                                  "regions": r["n_regions"]}
 
+    # ---- contacts between two copies of the object pushed into each other ----
+    from impact_b200 import voxel as V
+    other = VoxelObject.generate(SDFVoxelGenerator(1.0, ctx.build_generator(graph), types))
+    mesh_other = VoxelObjectMesh.create(other)
+    mesh_other.collision_probes()
+    dens = np.float32([1.0, 2.7, 0.3, 5.5])
+    mom_a, mom_b = obj.inertial_moments(dens).copy(), other.inertial_moments(dens).copy()
+    shape = np.float64(obj.info()["grid_shape"])
+    q = np.float64([0.0, np.sin(0.35), 0.0, np.cos(0.35)])  # B turned 40 degrees about y and shifted by 0.8 of the width
+    centre = 0.5 * shape
+
+    def rot(qq, v):
+        b, w = qq[:3], qq[3]
+        return v * (w * w - b @ b) + b * (2.0 * (v @ b)) + np.cross(b, v) * (2.0 * w)
+
+    world_to_a = np.float32([0, 0, 0, 1, *centre])
+    world_to_b = np.float32([*q, *(centre - rot(q, np.float64([0.8 * shape[0], 0.05 * shape[1], 0.0])))])
+    qa_inv = np.float64([0, 0, 0, 1])
+    qb_inv = np.float64([-q[0], -q[1], -q[2], q[3]])
+    # transform_from_b_to_a = world_to_a * world_to_b.inverted()
+    t_inv = -rot(qb_inv, np.float64(world_to_b[4:]))
+    b_to_a = np.float32([*qb_inv, *(t_inv + centre)])
+    ranges = V.intersection_voxel_ranges(obj.info()["occupied_voxel_ranges"], 1.0, other.info()["occupied_voxel_ranges"], 1.0,
+                                         b_to_a[:4], b_to_a[4:])
+    if ranges is not None:
+        V.mutual_contacts(obj, other, world_to_a, world_to_b, ranges[0], ranges[1], mom_a, mom_b)
+        t_min, t_med, (c_ab, c_ba) = best_of(lambda: V.mutual_contacts(obj, other, world_to_a, world_to_b, ranges[0], ranges[1], mom_a, mom_b))
+        out["mutual_contacts"] = {"gpu_ms_incl_download": round(t_med, 3), "best_ms": round(t_min, 3), "contacts_a_in_b": int(len(c_ab)),
+                                  "contacts_b_in_a": int(len(c_ba)),
+                                  "note": "two copies of the object, the second turned 40 degrees about y and shifted by 0.8 of the width"}
+    else:
+        out["mutual_contacts"] = {"note": "the chosen pose does not intersect"}
+
     if not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_lib as O
@@ -91,6 +124,15 @@ def main():
         t_sd = 1e3 * (time.perf_counter() - t0)
         same = bool(len(opr.points) == len(pr["points"]) and
                     np.array_equal(opr.points.view(np.uint32), pr["points"].view(np.uint32)))
+        if ranges is not None:
+            t0 = time.perf_counter()
+            o_ab, o_ba = O.mutual_contacts(ocpu, opr, mom_a, world_to_a, ocpu, opr, mom_b, world_to_b, ranges[0], ranges[1])
+            out["mutual_contacts"]["cpu_ms_1_thread"] = round(1e3 * (time.perf_counter() - t0), 2)
+            out["mutual_contacts"]["identical_to_cpu"] = bool(
+                len(o_ab) == len(c_ab) and len(o_ba) == len(c_ba) and
+                np.array_equal(o_ab["position"].view(np.uint32), c_ab["position"].view(np.uint32)) and
+                np.array_equal(o_ba["normal"].view(np.uint32), c_ba["normal"].view(np.uint32)) and
+                np.array_equal(o_ab["depth"].view(np.uint32), c_ab["depth"].view(np.uint32)))
         out["cpu_port"] = {"threads": threads, "generate_s": round(t_gen, 2), "mesh_s": round(t_mesh, 2),
                            "collision_probes_ms_1_thread": round(t_pr, 2), "probes_identical_to_gpu": same,
                            "split_detection_first_ms_1_thread": round(t_sd, 1), "regions": sd["n_regions"],
