@@ -54,8 +54,8 @@ def make_workload(name: str):
         return W.sphere(100.0), W.same_type(0), "engine bench shape: Sphere(r=100), Same(0)"
     if name == "noisybox256":
         return W.noisy_box(246.0, 8), W.same_type(0), "config 2: Box(246^3) + 8-octave noise, Same(0)"
-    if name in ("asteroid512", "asteroid1024"):
-        hi = 512 if name == "asteroid512" else 1024
+    if name in ("asteroid512", "asteroid1024", "asteroid2048"):  # 2048: beyond BASELINE's largest, same recipe
+        hi = int(name[len("asteroid"):])
         from impact_b200 import meta  # meta-graph compiler; bench graphs cached under impact_b200/data/
 
         graph = meta.asteroid_graph_scaled(hi - 16, hi)

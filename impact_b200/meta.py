@@ -1401,7 +1401,7 @@ if __name__ == "__main__":  # writes the bench workloads' atomic graphs (run on 
 
     out_dir = sys.argv[1] if len(sys.argv) > 1 else DATA_DIR
     os.makedirs(out_dir, exist_ok=True)
-    for hi in (128, 512, 1024):
+    for hi in (128, 512, 1024, 2048):
         g = asteroid_graph_scaled(hi - 16, hi, 0, use_cache=False)
         np.savez(os.path.join(out_dir, f"asteroid_{hi}_seed0.npz"), nodes=g.nodes(), root=np.int64(g.root_node_id),
                  scale_factor=np.float64(getattr(g, "scale_factor", 0.0)))

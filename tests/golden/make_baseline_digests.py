@@ -5,6 +5,7 @@ partition can be checked), config 5 the 32-step absorption sequence on the confi
 object, final mesh).
 
     python tests/golden/make_baseline_digests.py [workload ...]        # ≈ 6 min on 8 cores for everything
+    python tests/golden/make_baseline_digests.py asteroid2048          # one size beyond BASELINE; ≈ 11 min on 8 cores
 
 The `-m gpu` tests (tests/test_gpu_baseline_sizes.py) and bench.py's `parity` block compare the CUDA path against
 these committed digests without the oracle in the loop."""

@@ -2,8 +2,9 @@
 committed digests of the CPU oracle's output (tests/golden/baseline_digests.json, written by
 tests/golden/make_baseline_digests.py) — chunk table, every voxel, and the mesh buffers in the reference's order, for
 config 1 (64³ sphere, + the 202³ engine-bench sphere), config 2 (256³ noisy box), config 3 (asteroid ≤ 512³), config 4
-(asteroid ≤ 1024³: whole object on one GPU, and as x-slabs with the halo protocol) and config 5 (32 absorption steps on
-the config-4 object: dirty set of every step, final object, final mesh, dirty remesh patches against a full re-mesh).
+(asteroid ≤ 1024³: whole object on one GPU, and as x-slabs with the halo protocol; plus the same recipe one size beyond
+BASELINE, ≤ 2048³) and config 5 (32 absorption steps on the config-4 object: dirty set of every step, final object,
+final mesh, dirty remesh patches against a full re-mesh).
 The oracle is not in the loop here: the digests are the fixture."""
 import hashlib
 import json
@@ -35,8 +36,10 @@ def _mesh_digest(m):
                           m["vertex_ranges"])
 
 
-@pytest.mark.parametrize("name", ["sphere64", "sphere202", "noisybox256", "asteroid512", "asteroid1024"])
+@pytest.mark.parametrize("name", ["sphere64", "sphere202", "noisybox256", "asteroid512", "asteroid1024", "asteroid2048"])
 def test_object_and_mesh_match_the_oracle_digests_at_full_size(ctx, name):
+    # asteroid2048 (1930 x 1685 x 2039 voxels, 8x the non-uniform chunks of config 4) is beyond BASELINE's largest
+    # configuration: the same recipe one size up, to pin the 32-bit offsets and the capacities of a 4 GB object
     want = WANT[name]
     obj, _ = _generate(ctx, name)
     info = obj.info()
