@@ -2080,44 +2080,43 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
         if (upd_rc) upd_err = ivx_last_error(ctx);
     }
 
-    // boundary refresh over chunk range [start-1, end) (intersection.rs:391-393)
+    // boundary refresh over chunk range [start-1, end) (intersection.rs:391-393). Every chunk with a face in one of
+    // those pairs lies in the box [start-1, end+1) clipped to the grid: the pass is local to it (`ChunkBox`).
     AbsorbRange b = r;
     for (int d = 0; d < 3; ++d) b.c0[d] = r.c0[d] > 0 ? r.c0[d] - 1 : 0;
-    uint8_t* face_mask = tmp.get<uint8_t>(n);
-    uint32_t* convert_flag = tmp.get<uint32_t>(n);
-    uint32_t* need2 = tmp.get<uint32_t>(n);
-    uint32_t* ord2 = tmp.get<uint32_t>(n);
-    uint32_t* slot_of = tmp.get<uint32_t>(n);
-    if (!face_mask || !convert_flag || !need2 || !ord2 || !slot_of) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
-    KL(ctx, launch_absorb_face_mask(obj->nb, b, face_mask, n, st));
-    KL(ctx, launch_boundary_classify(obj->d_chunks, n, obj->nb, face_mask, convert_flag, 0, obj->nb[0], st));
-    KL(ctx, launch_need_slot_for_convert(obj->d_chunks, convert_flag, n, need2, obj->d_label_stale, st));
-    KL(ctx, launch_exclusive_scan(need2, ord2, n, counters + 5, st));
+    ChunkBox box{};
+    for (int d = 0; d < 3; ++d) {
+        box.c0[d] = b.c0[d];
+        box.d[d] = std::min(obj->nb[d], r.c1[d] + 1u) - b.c0[d];
+    }
+    const uint32_t n_in_box = box.d[0] * box.d[1] * box.d[2];
+    uint8_t* face_mask = tmp.get<uint8_t>(n_in_box);
+    uint32_t* convert_flag = tmp.get<uint32_t>(n_in_box);
+    uint32_t* slot_of = tmp.get<uint32_t>(n_in_box);
+    if (!face_mask || !convert_flag || !slot_of) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
+    // the conversions of the boundary pass take the slots after those of the absorption itself
+    KL(ctx, launch_boundary_refresh_box(obj->d_chunks, n, obj->nb, box, b, obj->slots_used, roomy ? counters : nullptr, face_mask,
+                                        convert_flag, slot_of, obj->d_label_stale, counters + 5, true, false, nullptr, 0, st));
     if (!roomy) {
         if (int rc = read_words(ctx, counters, 12, w)) return rc;
         if (int rc = ensure_slots(ctx, obj, w[5])) return rc;
+        obj->slots_used += w[5];
     }
-    // the conversions of the boundary pass take the slots after those of the absorption itself
-    KL(ctx, launch_assign_slots(obj->d_chunks, need2, ord2, obj->slots_used, roomy ? counters : nullptr, n, slot_of, st));
-    if (!roomy) obj->slots_used += w[5];
-    // (only the chunk planes of the refreshed box can have work: the others are not even looked at)
-    KL(ctx, launch_boundary_apply(obj->d_chunks, n, obj->nb, face_mask, convert_flag, slot_of, obj->d_voxels, nullptr, n,
-                                  b.c0[0], std::min(obj->nb[0], r.c1[0] + 1u), persistent_grid(ctx, n, 8), st));
-    // everything the host wants to know, in one read: slots handed out, statistics, invalidated chunks
+    KL(ctx, launch_boundary_refresh_box(obj->d_chunks, n, obj->nb, box, b, 0, nullptr, face_mask, convert_flag, slot_of, nullptr,
+                                        nullptr, false, true, obj->d_voxels, persistent_grid(ctx, n_in_box, 8), st));
+    // everything the host wants to know, in one read: slots handed out, statistics, invalidated chunks, and — computed
+    // on the device only if chunks were removed (`counters[4]`) — the occupied ranges (intersection.rs:387-389)
     CU(ctx, cudaMemsetAsync(counters + 12, 0, 4, st));
     KL(ctx, launch_count_nonzero_u8(obj->d_dirty, n, counters + 12, st));
+    KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, counters + 6, ctx->d_scratch + 64,
+                                   counters + 4, st));
     if (int rc = read_words(ctx, counters, 13, w)) return rc;
     if (roomy) obj->slots_used = slots_at_entry + w[0] + w[5];
     if (w[4]) {
-        // removed chunks → update_occupied_ranges (intersection.rs:387-389)
-        KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, counters + 6, ctx->d_scratch + 64,
-                                       persistent_grid(ctx, n, 8), st));
-        uint32_t o[6];
-        if (int rc = read_words(ctx, counters + 6, 6, o)) return rc;
-        const bool any = o[0] != 0xFFFFFFFFu;
+        const bool any = w[6] != 0xFFFFFFFFu;
         for (int d = 0; d < 3; ++d) {
-            obj->occ_voxels[d] = any ? o[d] : 0u;
-            obj->occ_voxels[3 + d] = any ? o[3 + d] + 1u : 0u;
+            obj->occ_voxels[d] = any ? w[6 + d] : 0u;
+            obj->occ_voxels[3 + d] = any ? w[9 + d] + 1u : 0u;
         }
     }
     if (out_stats) {
@@ -2170,8 +2169,8 @@ int refresh_occupied_ranges(ivx_ctx* ctx, ivx_object* obj) {
     uint32_t* occ = ctx->d_scratch + 38;
     const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
     CU(ctx, cudaMemcpyAsync(occ, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, occ, ctx->d_scratch + 64,
-                                   persistent_grid(ctx, n, 8), ctx->stream));
+    KL(ctx, launch_occupied_ranges(obj->d_chunks, n, obj->nb, obj->first_i, obj->d_voxels, occ, ctx->d_scratch + 64, nullptr,
+                                   ctx->stream));
     uint32_t o[6];
     if (int rc = read_words(ctx, occ, 6, o)) return rc;
     const bool any = o[0] != 0xFFFFFFFFu;

@@ -35,8 +35,16 @@ struct Neighbour {
     uint32_t slot;
 };
 
+// position of chunk (i, j, k) in the arrays of a box-local pass, or ~0 outside the box
+__device__ __forceinline__ uint32_t box_index(const ChunkBox& box, int i, int j, int k) {
+    const uint32_t a = (uint32_t)i - box.c0[0], b = (uint32_t)j - box.c0[1], c = (uint32_t)k - box.c0[2];
+    return (a < box.d[0] && b < box.d[1] && c < box.d[2]) ? (a * box.d[1] + b) * box.d[2] + c : 0xFFFFFFFFu;
+}
+
+// `box`: convert_flag is indexed by position in that box (chunks outside it are not being converted) instead of by chunk
 __device__ __forceinline__ Neighbour neighbour_of(const DevChunk* __restrict__ chunks, uint3 nb, int i, int j, int k,
-                                                  int dim, int side, const uint32_t* __restrict__ convert_flag) {
+                                                  int dim, int side, const uint32_t* __restrict__ convert_flag,
+                                                  const ChunkBox* box = nullptr) {
     int n[3] = {i, j, k};
     n[dim] += side ? 1 : -1;
     Neighbour r{0, 0, 0};
@@ -47,7 +55,12 @@ __device__ __forceinline__ Neighbour neighbour_of(const DevChunk* __restrict__ c
     r.slot = c.slot;
     if (c.kind == 2) r.face = c.face[dim * 2 + (1 - side)];
     // a uniform neighbour that is being converted in this pass presents Full faces either way
-    if (c.kind == 1 || (convert_flag && convert_flag[idx])) { r.kind = 1; }
+    bool converting = false;
+    if (convert_flag) {
+        const uint32_t at = box ? box_index(*box, n[0], n[1], n[2]) : idx;
+        converting = at != 0xFFFFFFFFu && convert_flag[at] != 0;
+    }
+    if (c.kind == 1 || converting) { r.kind = 1; }
     return r;
 }
 
@@ -73,29 +86,42 @@ __global__ void k_boundary_classify(const DevChunk* __restrict__ chunks, uint32_
     convert_flag[c] = conv;
 }
 
+// BOX: the pass of a modification — the work items are the chunks of `box` and face_mask / convert_flag / slot_of are
+// indexed by position in it (written by k_boundary_prep_box), so that nothing of the size of the chunk table is touched.
+template <bool BOX>
 __global__ void __launch_bounds__(256, 8) k_boundary_apply(DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
                                                          const uint8_t* __restrict__ face_mask,
                                                          const uint32_t* __restrict__ convert_flag,
                                                          const uint32_t* __restrict__ slot_of,
                                                          unsigned char* __restrict__ voxels,
                                                          const uint32_t* __restrict__ work_list, uint32_t n_work,
-                                                         uint32_t work_first, uint32_t own_lo, uint32_t own_hi) {
+                                                         uint32_t work_first, uint32_t own_lo, uint32_t own_hi,
+                                                         ChunkBox box) {
     __shared__ __align__(16) uint8_t s_flags[4096];
     __shared__ Neighbour s_nb[6];
     const int tid = threadIdx.x;
     for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const uint32_t c = work_list ? work_list[w] : w + work_first;
+        uint32_t c, at;  // the chunk, and its position in the per-pass arrays
+        if (BOX) {
+            const uint32_t bk = w % box.d[2], bj = (w / box.d[2]) % box.d[1], bi = w / (box.d[2] * box.d[1]);
+            c = ((box.c0[0] + bi) * nb.y + box.c0[1] + bj) * nb.z + box.c0[2] + bk;
+            at = w;
+        } else {
+            c = work_list ? work_list[w] : w + work_first;
+            at = c;
+        }
         DevChunk me = chunks[c];
-        const bool converting = convert_flag[c] != 0;
+        const bool converting = convert_flag[at] != 0;
         const uint32_t plane = c / (nb.z * nb.y);
         if ((me.kind != 2 && !converting) || plane < own_lo || plane >= own_hi) continue;  // uniform across the CTA
-        const uint8_t mask = face_mask ? face_mask[c] : 0x3F;
+        const uint8_t mask = face_mask ? face_mask[at] : 0x3F;
+        if (BOX && mask == 0) continue;  // (a corner of the box: none of its faces belongs to a refreshed pair)
         const int ck = c % nb.z, cj = (c / nb.z) % nb.y, ci = c / (nb.z * nb.y);
         unsigned char* slot;
         if (converting) {
             // convert_to_non_uniform_if_uniform (object.rs:2530-2550)
             me.kind = 2;
-            me.slot = slot_of[c];
+            me.slot = slot_of[at];
             for (int q = 0; q < 6; ++q) me.face[q] = 1;
             me.flags = 0x3F;
             slot = voxels + (size_t)me.slot * SLOT_BYTES;
@@ -109,7 +135,7 @@ __global__ void __launch_bounds__(256, 8) k_boundary_apply(DevChunk* __restrict_
             *reinterpret_cast<uint4*>(&s_flags[tid * 16]) = *reinterpret_cast<const uint4*>(slot + PLANE_FLAGS + tid * 16);
         }
         // the six neighbours' descriptors in one round trip
-        if (tid < 6) s_nb[tid] = neighbour_of(chunks, nb, ci, cj, ck, tid >> 1, tid & 1, convert_flag);
+        if (tid < 6) s_nb[tid] = neighbour_of(chunks, nb, ci, cj, ck, tid >> 1, tid & 1, convert_flag, BOX ? &box : nullptr);
         __syncthreads();
         uint8_t cflags = me.flags;
         // this thread's face voxel per face, and for faces against a Mixed neighbour face the adjacent voxel's
@@ -189,8 +215,100 @@ cudaError_t launch_boundary_apply(DevChunk* chunks, uint32_t n, const uint32_t n
         n_work = std::min(n_work, (hi - lo) * plane);
         grid = std::max(1u, std::min(grid, n_work));
     }
-    k_boundary_apply<<<grid, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), face_mask, convert_flag, slot_of,
-                                           voxels, work_list, n_work, work_first, own_lo, own_hi);
+    k_boundary_apply<false><<<grid, 256, 0, st>>>(chunks, n, make_uint3(nb[0], nb[1], nb[2]), face_mask, convert_flag,
+                                                  slot_of, voxels, work_list, n_work, work_first, own_lo, own_hi, ChunkBox{});
+    return cudaGetLastError();
+}
+
+// ---- the boundary refresh of a modification, local to the refreshed box -------------------------------------
+// One CTA does for the chunks of `box` what k_absorb_face_mask, k_boundary_classify, k_need_slot_for_convert, the prefix
+// sum and k_assign_slots do for a whole chunk table: which faces belong to a refreshed pair (`range`: the chunks whose
+// upper faces are refreshed, intersection.rs:391-393), which Uniform chunks stop being uniform, and the slots those get —
+// `first_slot` + *first_extra + their rank among the converted chunks of the box in chunk order, the numbering the
+// whole-table pass gives. Outputs are indexed by position in the box; *total = the slots handed out.
+__global__ void __launch_bounds__(1024) k_boundary_prep_box(const DevChunk* __restrict__ chunks, uint3 nb, ChunkBox box,
+                                                            AbsorbRange range, uint32_t first_slot,
+                                                            const uint32_t* __restrict__ first_extra,
+                                                            uint8_t* __restrict__ face_mask, uint32_t* __restrict__ convert_flag,
+                                                            uint32_t* __restrict__ slot_of, uint8_t* __restrict__ label_stale,
+                                                            uint32_t* __restrict__ total) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_box = box.d[0] * box.d[1] * box.d[2];
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t first = first_slot + (first_extra ? *first_extra : 0u);
+    for (uint32_t base = 0; base < n_box; base += 1024) {
+        const uint32_t w = base + tid;
+        uint32_t conv = 0, need = 0, own_slot = 0, c = 0;
+        uint8_t mask = 0;
+        if (w < n_box) {
+            const int i = (int)(box.c0[0] + w / (box.d[2] * box.d[1])), j = (int)(box.c0[1] + (w / box.d[2]) % box.d[1]),
+                      k = (int)(box.c0[2] + w % box.d[2]);
+            c = ((uint32_t)i * nb.y + (uint32_t)j) * nb.z + (uint32_t)k;
+            auto in_range = [&](int x, int y, int z) {
+                return (uint32_t)x >= range.c0[0] && (uint32_t)x < range.c1[0] && (uint32_t)y >= range.c0[1] &&
+                       (uint32_t)y < range.c1[1] && (uint32_t)z >= range.c0[2] && (uint32_t)z < range.c1[2];
+            };
+            if (in_range(i, j, k)) mask |= (1u << 1) | (1u << 3) | (1u << 5);  // upper faces
+            if (i > 0 && in_range(i - 1, j, k)) mask |= 1u << 0;               // lower faces: the pair belongs to the lower chunk
+            if (j > 0 && in_range(i, j - 1, k)) mask |= 1u << 2;
+            if (k > 0 && in_range(i, j, k - 1)) mask |= 1u << 4;
+            const DevChunk me = chunks[c];
+            own_slot = me.slot;
+            if (me.kind == 1) {
+                for (int f = 0; f < 6; ++f) {
+                    if (!((mask >> f) & 1)) continue;
+                    const Neighbour nbh = neighbour_of(chunks, nb, i, j, k, f >> 1, f & 1, nullptr);
+                    if (!(nbh.kind == 1 || (nbh.kind == 2 && nbh.face == 1))) conv = 1;
+                }
+            }
+            need = (conv && own_slot == 0xFFFFFFFFu) ? 1u : 0u;
+        }
+        // exclusive prefix sum of `need` over the CTA, carried from tile to tile
+        const uint32_t bal = __ballot_sync(0xffffffffu, need != 0);
+        if (lane == 0) s_warp[warp] = (uint32_t)__popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = s_warp[lane];
+            uint32_t incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            s_warp[lane] = incl - v;
+        }
+        __syncthreads();
+        const uint32_t ord = s_carry + s_warp[warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+        if (w < n_box) {
+            face_mask[w] = mask;
+            convert_flag[w] = conv;
+            slot_of[w] = need ? first + ord : own_slot;
+            if (conv && label_stale) label_stale[c] = 1;  // a chunk that becomes NonUniform has no region labels yet
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = ord + need;
+        __syncthreads();
+    }
+    if (tid == 0) *total = s_carry;
+}
+
+cudaError_t launch_boundary_refresh_box(DevChunk* chunks, uint32_t n, const uint32_t nb[3], const ChunkBox& box,
+                                        const AbsorbRange& range, uint32_t first_slot, const uint32_t* first_extra,
+                                        uint8_t* face_mask, uint32_t* convert_flag, uint32_t* slot_of, uint8_t* label_stale,
+                                        uint32_t* total, bool prep, bool apply, unsigned char* voxels, uint32_t grid,
+                                        cudaStream_t st) {
+    const uint32_t n_box = box.d[0] * box.d[1] * box.d[2];
+    if (n_box == 0) return cudaSuccess;
+    const uint3 nb3 = make_uint3(nb[0], nb[1], nb[2]);
+    if (prep)
+        k_boundary_prep_box<<<1, 1024, 0, st>>>(chunks, nb3, box, range, first_slot, first_extra, face_mask, convert_flag,
+                                                slot_of, label_stale, total);
+    if (apply)
+        k_boundary_apply<true><<<std::max(1u, std::min(grid, n_box)), 256, 0, st>>>(chunks, n, nb3, face_mask, convert_flag,
+                                                                                   slot_of, voxels, nullptr, n_box, 0, 0,
+                                                                                   nb[0], box);
     return cudaGetLastError();
 }
 

@@ -93,6 +93,20 @@ cudaError_t launch_scatter_active(const uint32_t* active_flag, const uint32_t* a
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t n, uint32_t v, cudaStream_t st);
 
 // ---- derive.cu ---------------------------------------------------------------
+struct AbsorbRange;
+// a box of chunks: first chunk and extent per axis
+struct ChunkBox {
+    uint32_t c0[3], d[3];
+};
+// The boundary refresh after a modification, over the chunks of `box` only (every chunk with a face in a refreshed
+// pair lies in it): `prep` decides conversions and their slots (one CTA; *total = slots handed out, numbered from
+// first_slot + *first_extra in chunk order), `apply` rewrites adjacency bits and obscuredness. face_mask /
+// convert_flag / slot_of hold one entry per chunk of the box.
+cudaError_t launch_boundary_refresh_box(DevChunk* chunks, uint32_t n, const uint32_t nb[3], const ChunkBox& box,
+                                        const AbsorbRange& range, uint32_t first_slot, const uint32_t* first_extra,
+                                        uint8_t* face_mask, uint32_t* convert_flag, uint32_t* slot_of, uint8_t* label_stale,
+                                        uint32_t* total, bool prep, bool apply, unsigned char* voxels, uint32_t grid,
+                                        cudaStream_t st);
 // own_lo / own_hi: only chunks of local planes [own_lo, own_hi) are classified / updated (halo planes belong to
 // the neighbour rank)
 cudaError_t launch_boundary_classify(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], const uint8_t* face_mask,
@@ -240,9 +254,10 @@ cudaError_t launch_count_nonzero_u8(const uint8_t* a, uint32_t n, uint32_t* out,
 cudaError_t launch_assign_slots(const DevChunk* chunks, const uint32_t* need, const uint32_t* ord, uint32_t first,
                                 const uint32_t* first_extra,
                                 uint32_t n, uint32_t* slot_of, cudaStream_t st);
+// `gate` (may be null): a device word; when it is zero the kernels return at once and `occ` keeps its initial value
 cudaError_t launch_occupied_ranges(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t first_i,
-                                   const unsigned char* voxels, uint32_t* occ, uint32_t* chunk_minmax_scratch, uint32_t grid,
-                                   cudaStream_t st);
+                                   const unsigned char* voxels, uint32_t* occ, uint32_t* chunk_minmax_scratch,
+                                   const uint32_t* gate, cudaStream_t st);
 
 // ---- split.cu ------------------------------------------------------------------
 // sets arr[chunk] = value for the chunks of the box [lo, hi) (clamped to the grid); no-op when arr is null

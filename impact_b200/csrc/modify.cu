@@ -402,7 +402,9 @@ __global__ void k_count_nonzero_u8(const uint8_t* __restrict__ a, uint32_t n, ui
 }
 
 // update_occupied_chunk_ranges (object.rs:1156-1182): chunk-level bounds of the chunks that hold a non-empty voxel
-__global__ void k_occupied_chunk_ranges(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb, uint32_t* __restrict__ cmm) {
+__global__ void k_occupied_chunk_ranges(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb, uint32_t* __restrict__ cmm,
+                                        const uint32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const DevChunk ch = chunks[c];
@@ -418,17 +420,37 @@ __global__ void k_occupied_chunk_ranges(const DevChunk* __restrict__ chunks, uin
 
 // bounding range of non-empty voxels over the whole object (object.rs:1149-1280). Like the reference, voxels are
 // looked at only in the outermost occupied chunk planes (`cmm`, from k_occupied_chunk_ranges): no other chunk can
-// hold the first or the last non-empty voxel of an axis.
+// hold the first or the last non-empty voxel of an axis. A CTA tests 256 consecutive chunks at once (one per thread)
+// and then walks the few that lie in such a plane.
 __global__ void __launch_bounds__(256) k_occupied_ranges(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
                                                          uint32_t first_i, const unsigned char* __restrict__ voxels,
-                                                         const uint32_t* __restrict__ cmm, uint32_t* __restrict__ occ) {
+                                                         const uint32_t* __restrict__ cmm, uint32_t* __restrict__ occ,
+                                                         const uint32_t* __restrict__ gate) {
     __shared__ uint32_t s_mm[6];
+    __shared__ uint32_t s_list[256];
+    __shared__ uint32_t s_count;
+    if (gate && *gate == 0) return;
     const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
-    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    {
+        const uint32_t c = blockIdx.x * 256u + tid;
+        if (c < n) {
+            const DevChunk ch = chunks[c];
+            bool take = !(ch.kind == 0 || (ch.kind == 2 && (ch.flags & (1u << 6))));
+            if (take && cmm) {
+                const uint32_t k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
+                take = i == cmm[0] || i == cmm[3] || j == cmm[1] || j == cmm[4] || k == cmm[2] || k == cmm[5];
+            }
+            if (take) s_list[atomicAdd(&s_count, 1u)] = c;
+        }
+    }
+    __syncthreads();
+    const uint32_t count = s_count;
+    for (uint32_t q = 0; q < count; ++q) {
+        const uint32_t c = s_list[q];
         const DevChunk ch = chunks[c];
-        if (ch.kind == 0 || (ch.kind == 2 && (ch.flags & (1u << 6)))) continue;
         const uint32_t k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
-        if (cmm && i != cmm[0] && i != cmm[3] && j != cmm[1] && j != cmm[4] && k != cmm[2] && k != cmm[5]) continue;
         const uint32_t org[3] = {(i + first_i) * 16u, j * 16u, k * 16u};
         if (ch.kind == 1) {
             if (tid == 0)
@@ -444,8 +466,8 @@ __global__ void __launch_bounds__(256) k_occupied_ranges(const DevChunk* __restr
         const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
         uint32_t nonempty = 0;
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-            if ((ws[q >> 2] >> (8 * (q & 3) + 7)) & 1u) nonempty |= 1u << q;
+        for (int b = 0; b < 16; ++b)
+            if ((ws[b >> 2] >> (8 * (b & 3) + 7)) & 1u) nonempty |= 1u << b;
         if (nonempty) {
             atomicMin(&s_mm[0], (uint32_t)ti);
             atomicMin(&s_mm[1], (uint32_t)tj);
@@ -499,17 +521,17 @@ cudaError_t launch_count_nonzero_u8(const uint8_t* a, uint32_t n, uint32_t* out,
     return cudaGetLastError();
 }
 cudaError_t launch_occupied_ranges(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], uint32_t first_i,
-                                   const unsigned char* voxels, uint32_t* occ, uint32_t* chunk_minmax_scratch, uint32_t grid,
-                                   cudaStream_t st) {
+                                   const unsigned char* voxels, uint32_t* occ, uint32_t* chunk_minmax_scratch,
+                                   const uint32_t* gate, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const uint3 nb3 = make_uint3(nb[0], nb[1], nb[2]);
     if (chunk_minmax_scratch) {
         const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
         cudaError_t e = cudaMemcpyAsync(chunk_minmax_scratch, init, sizeof(init), cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) return e;
-        k_occupied_chunk_ranges<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, nb3, chunk_minmax_scratch);
+        k_occupied_chunk_ranges<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, nb3, chunk_minmax_scratch, gate);
     }
-    k_occupied_ranges<<<grid, 256, 0, st>>>(chunks, n, nb3, first_i, voxels, chunk_minmax_scratch, occ);
+    k_occupied_ranges<<<(n + 255) / 256, 256, 0, st>>>(chunks, n, nb3, first_i, voxels, chunk_minmax_scratch, occ, gate);
     return cudaGetLastError();
 }
 
