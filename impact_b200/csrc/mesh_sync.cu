@@ -280,10 +280,10 @@ int ivx_object_mesh_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
         m.vertex_ranges = nv;
         m.cap_submeshes = want;
     }
+    std::vector<uint32_t> packed;  // (read by an asynchronous copy: lives until the synchronisation at the end)
     {
         std::sort(s.touched_rows.begin(), s.touched_rows.end());
         s.touched_rows.erase(std::unique(s.touched_rows.begin(), s.touched_rows.end()), s.touched_rows.end());
-        std::vector<uint32_t> packed;
         packed.reserve(s.touched_rows.size() * 16);
         for (uint32_t row : s.touched_rows) {
             if (row >= rows) continue;  // the row was swap-removed later in this sync
@@ -302,7 +302,6 @@ int ivx_object_mesh_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
             ctx->launches++;
             k_scatter_rows<<<(n_rows * 16u + 255u) / 256u, 256, 0, st>>>(d_packed, n_rows, m.submeshes, m.vertex_ranges);
             CU(ctx, cudaGetLastError());
-            CU(ctx, cudaStreamSynchronize(st));  // `packed` goes out of scope
         }
     }
     m.n_vertices = s.n_vertices;
