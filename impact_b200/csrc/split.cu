@@ -158,11 +158,12 @@ __global__ void __launch_bounds__(32) k_local_regions(const DevChunk* __restrict
                 for (int u = 0; u < 4; ++u) p4[u] = s_par[base + 32u * u + (uint32_t)lane];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) g4[u] = s_par[p4[u]];
+                __syncwarp();  // (in place: every value read is an ancestor either way; the barriers order the accesses)
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (g4[u] != p4[u]) s_par[base + 32u * u + (uint32_t)lane] = (uint16_t)g4[u];
+                __syncwarp();
             }
-            __syncwarp();
         }
         // links between different trees, in visiting order. Most links repeat a pair of trees that an earlier link has
         // already brought together, and a repeated pair is a no-op in the replay (a dropped FIRST occurrence would not
