@@ -406,31 +406,44 @@ __global__ void k_occupied_chunk_ranges(const DevChunk* __restrict__ chunks, uin
                                         const uint32_t* __restrict__ gate) {
     if (gate && *gate == 0) return;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    const DevChunk ch = chunks[c];
-    if (ch.kind == 0 || (ch.kind == 2 && (ch.flags & (1u << 6)))) return;  // contains_only_empty_voxels
-    const uint32_t k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
-    atomicMin(&cmm[0], i);
-    atomicMin(&cmm[1], j);
-    atomicMin(&cmm[2], k);
-    atomicMax(&cmm[3], i);
-    atomicMax(&cmm[4], j);
-    atomicMax(&cmm[5], k);
+    uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+    bool any = false;
+    if (c < n) {
+        const DevChunk ch = chunks[c];
+        if (!(ch.kind == 0 || (ch.kind == 2 && (ch.flags & (1u << 6))))) {  // contains_only_empty_voxels
+            any = true;
+            lo[2] = hi[2] = c % nb.z;
+            lo[1] = hi[1] = (c / nb.z) % nb.y;
+            lo[0] = hi[0] = c / (nb.z * nb.y);
+        }
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = __reduce_min_sync(0xffffffffu, lo[d]);
+        hi[d] = __reduce_max_sync(0xffffffffu, hi[d]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&cmm[d], lo[d]);
+            atomicMax(&cmm[3 + d], hi[d]);
+        }
+    }
 }
 
 // bounding range of non-empty voxels over the whole object (object.rs:1149-1280). Like the reference, voxels are
 // looked at only in the outermost occupied chunk planes (`cmm`, from k_occupied_chunk_ranges): no other chunk can
-// hold the first or the last non-empty voxel of an axis. A CTA tests 256 consecutive chunks at once (one per thread)
-// and then walks the few that lie in such a plane.
+// hold the first or the last non-empty voxel of an axis. A CTA tests 256 consecutive chunks at once (one per thread);
+// its warps then take the few that lie in such a plane, one chunk per warp at a time.
 __global__ void __launch_bounds__(256) k_occupied_ranges(const DevChunk* __restrict__ chunks, uint32_t n, uint3 nb,
                                                          uint32_t first_i, const unsigned char* __restrict__ voxels,
                                                          const uint32_t* __restrict__ cmm, uint32_t* __restrict__ occ,
                                                          const uint32_t* __restrict__ gate) {
-    __shared__ uint32_t s_mm[6];
     __shared__ uint32_t s_list[256];
     __shared__ uint32_t s_count;
     if (gate && *gate == 0) return;
-    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_count = 0;
     __syncthreads();
     {
@@ -447,42 +460,47 @@ __global__ void __launch_bounds__(256) k_occupied_ranges(const DevChunk* __restr
     }
     __syncthreads();
     const uint32_t count = s_count;
-    for (uint32_t q = 0; q < count; ++q) {
+    for (uint32_t q = warp; q < count; q += 8u) {
         const uint32_t c = s_list[q];
         const DevChunk ch = chunks[c];
         const uint32_t k = c % nb.z, j = (c / nb.z) % nb.y, i = c / (nb.z * nb.y);
         const uint32_t org[3] = {(i + first_i) * 16u, j * 16u, k * 16u};
+        uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
         if (ch.kind == 1) {
-            if (tid == 0)
-                for (int d = 0; d < 3; ++d) {
-                    atomicMin(&occ[d], org[d]);
-                    atomicMax(&occ[3 + d], org[d] + 15u);
-                }
-            continue;
-        }
-        if (tid < 6) s_mm[tid] = tid < 3 ? 0xFFFFFFFFu : 0u;
-        __syncthreads();
-        const uint4 w = *reinterpret_cast<const uint4*>(voxels + (size_t)ch.slot * SLOT_BYTES + PLANE_SD + tid * 16);
-        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-        uint32_t nonempty = 0;
+            lo[0] = lo[1] = lo[2] = 0u;
+            hi[0] = hi[1] = hi[2] = 15u;
+        } else {
+            // a lane takes the voxel rows lane, lane + 32, ... (row = i * 16 + j: 16 voxels along k, 16 sign bytes)
+            const unsigned char* sd = voxels + (size_t)ch.slot * SLOT_BYTES + PLANE_SD;
 #pragma unroll
-        for (int b = 0; b < 16; ++b)
-            if ((ws[b >> 2] >> (8 * (b & 3) + 7)) & 1u) nonempty |= 1u << b;
-        if (nonempty) {
-            atomicMin(&s_mm[0], (uint32_t)ti);
-            atomicMin(&s_mm[1], (uint32_t)tj);
-            atomicMin(&s_mm[2], (uint32_t)(__ffs(nonempty) - 1));
-            atomicMax(&s_mm[3], (uint32_t)ti);
-            atomicMax(&s_mm[4], (uint32_t)tj);
-            atomicMax(&s_mm[5], (uint32_t)(31 - __clz(nonempty)));
-        }
-        __syncthreads();
-        if (tid == 0 && s_mm[0] != 0xFFFFFFFFu)
-            for (int d = 0; d < 3; ++d) {
-                atomicMin(&occ[d], org[d] + s_mm[d]);
-                atomicMax(&occ[3 + d], org[d] + s_mm[3 + d]);
+            for (uint32_t t = 0; t < 8u; ++t) {
+                const uint32_t row = lane + 32u * t;
+                const uint4 w = *reinterpret_cast<const uint4*>(sd + row * 16u);
+                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                uint32_t nonempty = 0;
+#pragma unroll
+                for (int b = 0; b < 16; ++b)
+                    if ((ws[b >> 2] >> (8 * (b & 3) + 7)) & 1u) nonempty |= 1u << b;
+                if (nonempty) {
+                    lo[0] = min(lo[0], row >> 4);
+                    hi[0] = max(hi[0], row >> 4);
+                    lo[1] = min(lo[1], row & 15u);
+                    hi[1] = max(hi[1], row & 15u);
+                    lo[2] = min(lo[2], (uint32_t)(__ffs(nonempty) - 1));
+                    hi[2] = max(hi[2], (uint32_t)(31 - __clz(nonempty)));
+                }
             }
-        __syncthreads();
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = __reduce_min_sync(0xffffffffu, lo[d]);
+                hi[d] = __reduce_max_sync(0xffffffffu, hi[d]);
+            }
+        }
+        if (lane == 0 && lo[0] != 0xFFFFFFFFu)
+            for (int d = 0; d < 3; ++d) {
+                atomicMin(&occ[d], org[d] + lo[d]);
+                atomicMax(&occ[3 + d], org[d] + hi[d]);
+            }
     }
 }
 
