@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = [
     "ivx_object_surface_voxels_within_plane", "ivx_voxel_ranges_within_plane", "ivx_object_sphere_contacts", "ivx_object_plane_contacts", "ivx_object_capsule_contacts",
     "ivx_comm_create", "ivx_comm_connect", "ivx_comm_connect_local", "ivx_comm_destroy", "ivx_object_exchange_halos",
     "ivx_object_mesh_gather", "ivx_object_mesh_distributed", "ivx_object_mesh_sync", "ivx_mesh_modifications", "ivx_mesh_report_synchronized", "ivx_object_collision_probes", "ivx_object_collision_probes_sync", "ivx_collision_probes_download", "ivx_objects_mutual_contacts",
+    "ivx_mesh_gpu_buffers_create", "ivx_mesh_gpu_buffers_sync", "ivx_mesh_gpu_buffers_destroy",
 ]
 
 
@@ -70,6 +71,19 @@ class CommConfig(C.Structure):
 class ProbesInfo(C.Structure):
     _fields_ = [("log2_block_size", C.c_uint32), ("_pad", C.c_uint32), ("n_points", C.c_uint64), ("n_chunks", C.c_uint64),
                 ("d_points", C.c_void_p)]
+
+
+class MeshGpuBufferInfo(C.Structure):
+    _fields_ = [("fd", C.c_int32), ("recreated", C.c_uint32), ("allocation_bytes", C.c_uint64), ("valid_bytes", C.c_uint64),
+                ("device_ptr", C.c_void_p)]
+
+
+MESH_BUFFER_NAMES = ("positions", "normals", "index_materials", "indices", "chunk_submeshes")
+
+
+class MeshGpuBuffersInfo(C.Structure):
+    _fields_ = [("buffer", MeshGpuBufferInfo * 5), ("n_vertices", C.c_uint64), ("n_indices", C.c_uint64),
+                ("n_chunks", C.c_uint64), ("bytes_copied", C.c_uint64), ("n_updated_ranges", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 PROBE_RANGE_DTYPE = np.dtype([("chunk_indices", "<u4", (3,)), ("point_start", "<u4"), ("point_end", "<u4")])
@@ -165,6 +179,8 @@ def lib():
         L.ivx_object_free.restype = None
         L.ivx_comm_destroy.argtypes = [C.c_void_p, C.c_void_p]
         L.ivx_comm_destroy.restype = None
+        L.ivx_mesh_gpu_buffers_destroy.argtypes = [C.c_void_p, C.c_void_p]
+        L.ivx_mesh_gpu_buffers_destroy.restype = None
         _lib = L
     return _lib
 

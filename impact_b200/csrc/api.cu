@@ -107,7 +107,9 @@ void free_mesh(ivx_ctx* ctx, DeviceMesh& m) {
     ctx->release(m.index_materials);
     ctx->release(m.submeshes);
     ctx->release(m.vertex_ranges);
+    const uint64_t serial = m.serial;
     m = DeviceMesh{};
+    m.serial = serial;
 }
 
 // SDFVoxelGenerator::new (generation.rs:207-258)
@@ -1696,6 +1698,7 @@ int ivx_internal_mesh(ivx_ctx* ctx, ivx_object* obj, bool sync, uint32_t counts[
     ivx_mesh_sync_free(obj->sync);
     obj->sync = nullptr;
     obj->mesh_is_patch = false;
+    obj->mesh.serial++;
     Tmp tmp(ctx);
     uint32_t* flag = tmp.get<uint32_t>(obj->n_chunks);
     if (!flag) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "mesh: out of device memory");
@@ -2464,6 +2467,7 @@ int ivx_object_remesh_dirty(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_info* out) {
     ivx_mesh_sync_free(obj->sync);
     obj->sync = nullptr;
     obj->mesh_is_patch = true;
+    obj->mesh.serial++;
     if (int rc = mesh_impl(ctx, obj, exposed, obj->mesh)) return rc;
     CU(ctx, cudaMemsetAsync(obj->d_dirty, 0, n, ctx->stream));  // mark_chunk_meshes_synchronized
     CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -141,6 +141,7 @@ void ivx_probes_free(ivx_ctx* ctx, ivx_probes* p);
 struct DeviceMesh {
     uint32_t n_vertices = 0, n_indices = 0, n_submeshes = 0, n_work = 0;
     uint32_t cap_vertices = 0, cap_indices = 0, cap_submeshes = 0;  // allocated elements once the mesh is kept in sync (0: exact)
+    uint64_t serial = 0;  // counts the times the mesh was created anew (ivx_object_mesh, ivx_object_remesh_dirty)
     float* positions = nullptr;
     float* normals = nullptr;
     uint32_t* indices = nullptr;

@@ -14,6 +14,7 @@ marshals POD buffers.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -610,6 +611,63 @@ class VoxelObjectMesh:
                                                      L.ptr(sm), L.ptr(vr)))
         return {"positions": pos, "normals": nrm, "index_materials": im, "indices": idx, "submeshes": sm,
                 "vertex_ranges": vr}
+
+
+class VoxelMeshGPUBuffers:
+    """`VoxelMeshGPUBuffers` (gpu_resource.rs:460-900): the five buffers a renderer draws a meshed voxel object from, as
+    exportable device allocations. `fds[name]` is the POSIX file descriptor of the current allocation behind a buffer
+    (import it as external memory; this object closes it when the buffer is re-created and on `close`), `device_ptrs`
+    the same buffers for a CUDA consumer in this process."""
+
+    def __init__(self, obj: VoxelObject, handle, info):
+        self.obj, self.h = obj, handle
+        self.fds = {n: -1 for n in L.MESH_BUFFER_NAMES}
+        self._take(info)
+
+    def _take(self, info):
+        self.recreated = []
+        for b, name in enumerate(L.MESH_BUFFER_NAMES):
+            bi = info.buffer[b]
+            if bi.fd >= 0:
+                if self.fds[name] >= 0:
+                    os.close(self.fds[name])
+                self.fds[name] = int(bi.fd)
+            if bi.recreated:
+                self.recreated.append(name)
+        self.allocation_bytes = {n: int(info.buffer[b].allocation_bytes) for b, n in enumerate(L.MESH_BUFFER_NAMES)}
+        self.valid_bytes = {n: int(info.buffer[b].valid_bytes) for b, n in enumerate(L.MESH_BUFFER_NAMES)}
+        self.device_ptrs = {n: int(info.buffer[b].device_ptr or 0) for b, n in enumerate(L.MESH_BUFFER_NAMES)}
+        self.n_vertices, self.n_indices, self.n_chunks = int(info.n_vertices), int(info.n_indices), int(info.n_chunks)
+        self.bytes_copied, self.n_updated_ranges = int(info.bytes_copied), int(info.n_updated_ranges)
+
+    @classmethod
+    def for_voxel_object(cls, obj: VoxelObject) -> "VoxelMeshGPUBuffers":
+        """`for_voxel_object` (gpu_resource.rs:484-600): buffers holding the object's current mesh."""
+        ctx = obj.ctx
+        h, info = C.c_void_p(), L.MeshGpuBuffersInfo()
+        ctx.check(ctx._lib.ivx_mesh_gpu_buffers_create(ctx.h, obj.h, C.byref(h), C.byref(info)))
+        return cls(obj, h, info)
+
+    def sync_with_voxel_object(self) -> "VoxelMeshGPUBuffers":
+        """`sync_with_voxel_object` (gpu_resource.rs:714-900), after `VoxelObjectMesh.sync`: the updated ranges device to
+        device; `recreated` names the buffers that outgrew their allocation (new `fds`)."""
+        ctx = self.obj.ctx
+        info = L.MeshGpuBuffersInfo()
+        ctx.check(ctx._lib.ivx_mesh_gpu_buffers_sync(ctx.h, self.obj.h, self.h, C.byref(info)))
+        self._take(info)
+        return self
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.obj.ctx, "h", None):
+            self.obj.ctx._lib.ivx_mesh_gpu_buffers_destroy(self.obj.ctx.h, self.h)
+        self.h = None
+        for n, fd in getattr(self, "fds", {}).items():
+            if fd >= 0:
+                os.close(fd)
+            self.fds[n] = -1
+
+    def __del__(self):
+        self.close()
 
 
 def compile_program_host(graph: SDFGraph):

@@ -495,6 +495,52 @@ int ivx_mesh_modifications(ivx_ctx* ctx, const ivx_object* object, uint32_t* out
                            uint64_t* out_count, int* out_chunks_were_removed);
 int ivx_mesh_report_synchronized(ivx_ctx* ctx, ivx_object* object);
 
+/* ---- the mesh buffers a renderer draws from -------------------------------
+ * VoxelMeshGPUBuffers (gpu_resource.rs:460-900): the five buffers of a meshed voxel object — vertex positions, normal
+ * vectors, index materials, indices, chunk submeshes — created from the object's mesh (for_voxel_object, :484-600) and
+ * brought up to date after a mesh sync by writing only the updated ranges (sync_with_voxel_object, :714-900). The
+ * reference stages those ranges from host memory into wgpu buffers; here the mesh is on the device already, so each
+ * buffer is an exportable device allocation: `fd` is a POSIX file descriptor a graphics API imports ONCE as external
+ * memory (VK_KHR_external_memory_fd, handle type OPAQUE_FD, allocation_bytes; cuMemImportFromShareableHandle for a CUDA
+ * consumer), and a sync is device-to-device copies on the context's stream, no host round trip.
+ *   ivx_mesh_gpu_buffers_create   for_voxel_object: the object's current mesh (ivx_object_mesh or the synced mesh), whole.
+ *   ivx_mesh_gpu_buffers_sync     sync_with_voxel_object, call it after ivx_object_mesh_sync: nothing when there are no
+ *                                 modifications; the updated vertex / index ranges (ivx_mesh_modifications) while the
+ *                                 slices fit their buffers; a buffer pair whose slice outgrew it is re-created with the
+ *                                 whole slice (`recreated` = 1 and a NEW `fd` to import); the chunk submesh table is
+ *                                 rewritten whenever anything changed; ends with ivx_mesh_report_synchronized, like the
+ *                                 reference. A mesh that was re-created by ivx_object_mesh since is copied whole.
+ * Descriptors are handed over: the caller closes every `fd` >= 0 it receives (importing does not consume it). The
+ * copies are asynchronous on the context's stream; a consumer on another queue orders itself after ivx_synchronize or
+ * an event on that stream. Element layouts: positions / normals 3 x f32, ivx_index_materials, u32,
+ * ivx_chunk_submesh — the reference's buffer contents byte for byte. */
+enum {
+    IVX_MESH_BUFFER_POSITIONS = 0,
+    IVX_MESH_BUFFER_NORMALS = 1,
+    IVX_MESH_BUFFER_INDEX_MATERIALS = 2,
+    IVX_MESH_BUFFER_INDICES = 3,
+    IVX_MESH_BUFFER_CHUNK_SUBMESHES = 4,
+    IVX_MESH_BUFFER_COUNT = 5
+};
+typedef struct ivx_mesh_gpu_buffers ivx_mesh_gpu_buffers;
+typedef struct ivx_mesh_gpu_buffer_info {
+    int32_t fd;                /* >= 0: a descriptor of the (new) allocation, owned by the caller; -1: unchanged */
+    uint32_t recreated;        /* 1 when this call made the allocation */
+    uint64_t allocation_bytes; /* size of the allocation (what an importer maps) */
+    uint64_t valid_bytes;      /* bytes of mesh data in it (n_valid_bytes) */
+    void* device_ptr;          /* the buffer in this process, for CUDA consumers */
+} ivx_mesh_gpu_buffer_info;
+typedef struct ivx_mesh_gpu_buffers_info {
+    ivx_mesh_gpu_buffer_info buffer[IVX_MESH_BUFFER_COUNT];
+    uint64_t n_vertices, n_indices, n_chunks; /* lengths of the mesh slices (freed ranges included), submesh rows */
+    uint64_t bytes_copied;                    /* device-to-device bytes this call moved */
+    uint32_t n_updated_ranges;                /* records of ivx_mesh_modifications this call consumed */
+    uint32_t reserved;
+} ivx_mesh_gpu_buffers_info;
+int ivx_mesh_gpu_buffers_create(ivx_ctx* ctx, ivx_object* object, ivx_mesh_gpu_buffers** out, ivx_mesh_gpu_buffers_info* info);
+int ivx_mesh_gpu_buffers_sync(ivx_ctx* ctx, ivx_object* object, ivx_mesh_gpu_buffers* buffers, ivx_mesh_gpu_buffers_info* info);
+void ivx_mesh_gpu_buffers_destroy(ivx_ctx* ctx, ivx_mesh_gpu_buffers* buffers);
+
 /* ---- collision probes ------------------------------------------------------
  * VoxelObjectCollisionProbes (collidable.rs:97-101, 346-780): per meshed chunk and per block of 1^3 .. 8^3 voxels
  * (determine_log2_block_size_for_object, :451-471) the mesh vertex of lowest mean curvature — the points the physics

@@ -21,7 +21,7 @@ use std::ffi::{c_char, c_void};
 #[repr(C)] pub struct IvxMeshInfo   { /* include/impact_voxel_cuda.h: ivx_mesh_info   */ }
 #[repr(C)] pub struct IvxAbsorbStats { pub touched_chunks: u32, pub touched_voxels: u32, pub emptied_voxels: u32,
                                        pub removed_chunks: u32, pub dirty_chunks: u32 }
-pub enum IvxCtx {} pub enum IvxProgram {} pub enum IvxObject {} pub enum IvxComm {}
+pub enum IvxCtx {} pub enum IvxProgram {} pub enum IvxObject {} pub enum IvxComm {} pub enum IvxMeshGpuBuffers {}
 #[repr(C)] pub struct IvxCommConfig { pub rank: u32, pub world: u32, pub gather_rank: u32, pub plane_chunks: u32,
                                       pub mesh_vertices: u64, pub mesh_indices: u64, pub mesh_submeshes: u64 }
 #[repr(C)] pub struct IvxGatheredMesh { pub n_vertices: u64, pub n_indices: u64, pub n_submeshes: u64,
@@ -44,6 +44,14 @@ pub struct IvxMetaNode { pub kind: u32, pub child: [u32; 2], pub count: u32, pub
 #[repr(C)] pub struct IvxProbesInfo { pub log2_block_size: u32, pub _pad: u32, pub n_points: u64, pub n_chunks: u64,
                                       pub d_points: *const f32 }
 #[repr(C)] pub struct IvxProbeRange { pub chunk_indices: [u32; 3], pub point_start: u32, pub point_end: u32 }
+
+/// `ivx_mesh_gpu_buffers_info`: VoxelMeshGPUBuffers (gpu_resource.rs:460-900) as exportable device allocations — one
+/// descriptor per buffer (positions, normals, index materials, indices, chunk submeshes) for
+/// `wgpu::hal` / Vulkan external-memory import instead of the staging-belt upload.
+#[repr(C)] #[derive(Clone, Copy)] pub struct IvxMeshGpuBufferInfo { pub fd: i32, pub recreated: u32, pub allocation_bytes: u64,
+                                                                   pub valid_bytes: u64, pub device_ptr: *mut c_void }
+#[repr(C)] pub struct IvxMeshGpuBuffersInfo { pub buffer: [IvxMeshGpuBufferInfo; 5], pub n_vertices: u64, pub n_indices: u64,
+                                              pub n_chunks: u64, pub bytes_copied: u64, pub n_updated_ranges: u32, pub reserved: u32 }
 
 dynamic_lib::define_lib! {
     name = VoxelCudaLib,
@@ -154,6 +162,9 @@ dynamic_lib::define_lib! {
                                           inertial_a: *const IvxInertialMoments, inertial_b: *const IvxInertialMoments,
                                           out: *mut IvxVoxelContact, capacity: usize, out_count_a_against_b: *mut u64,
                                           out_count_b_against_a: *mut u64) -> i32;
+    unsafe fn ivx_mesh_gpu_buffers_create(ctx: *mut IvxCtx, object: *mut IvxObject, out: *mut *mut IvxMeshGpuBuffers, info: *mut IvxMeshGpuBuffersInfo) -> i32;
+    unsafe fn ivx_mesh_gpu_buffers_sync(ctx: *mut IvxCtx, object: *mut IvxObject, buffers: *mut IvxMeshGpuBuffers, info: *mut IvxMeshGpuBuffersInfo) -> i32;
+    unsafe fn ivx_mesh_gpu_buffers_destroy(ctx: *mut IvxCtx, buffers: *mut IvxMeshGpuBuffers) -> ();
     // ---- the rest of include/impact_voxel_cuda.h (generated by tools/gen_rust_bindings.py from the prototypes) ----
     unsafe fn ivx_abi_version() -> u32;
     unsafe fn ivx_kernel_launch_count(ctx: *const IvxCtx) -> u64;

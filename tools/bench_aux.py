@@ -104,6 +104,38 @@ def main():
     else:
         out["mutual_contacts"] = {"note": "the chosen pose does not intersect"}
 
+    # ---- the renderer's mesh buffers (VoxelMeshGPUBuffers): creation, and a sync after absorb + mesh sync ----
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from bench_fracture import absorber_path
+    robj = VoxelObject.generate(SDFVoxelGenerator(1.0, ctx.build_generator(graph), types))
+    VoxelObjectMesh.create(robj)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    bufs = V.VoxelMeshGPUBuffers.for_voxel_object(robj)
+    ctx.synchronize()
+    t_create = 1e3 * (time.perf_counter() - t0)
+    created_bytes = bufs.bytes_copied
+    centers, radius = absorber_path(robj.info()["grid_shape"], 10)
+    ts, moved, ranges = [], [], []
+    for c in centers:
+        st = robj.absorb_sphere(c, radius, radius + 2.0)
+        VoxelObjectMesh.sync(robj)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        bufs.sync_with_voxel_object()
+        ctx.synchronize()
+        if st["touched_chunks"] > 100:
+            ts.append(1e3 * (time.perf_counter() - t0))
+            moved.append(bufs.bytes_copied)
+            ranges.append(bufs.n_updated_ranges)
+    out["render_buffers"] = {"create_ms": round(t_create, 3), "create_bytes": int(created_bytes),
+                             "sync_ms_median": round(float(np.median(ts)), 3), "sync_bytes_median": int(np.median(moved)),
+                             "updated_ranges_median": int(np.median(ranges)), "recreated_in_last_sync": bufs.recreated,
+                             "note": "five exportable device allocations (one file descriptor each); a sync copies the updated "
+                                     "ranges and the submesh table device to device, after an absorption step of config 5"}
+    bufs.close()
+    robj.free()
+
     if not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_lib as O
