@@ -116,7 +116,7 @@ def main():
     t_create = 1e3 * (time.perf_counter() - t0)
     created_bytes = bufs.bytes_copied
     centers, radius = absorber_path(robj.info()["grid_shape"], 10)
-    ts, moved, ranges = [], [], []
+    ts, moved, n_ranges = [], [], []
     for c in centers:
         st = robj.absorb_sphere(c, radius, radius + 2.0)
         VoxelObjectMesh.sync(robj)
@@ -127,10 +127,10 @@ def main():
         if st["touched_chunks"] > 100:
             ts.append(1e3 * (time.perf_counter() - t0))
             moved.append(bufs.bytes_copied)
-            ranges.append(bufs.n_updated_ranges)
+            n_ranges.append(bufs.n_updated_ranges)
     out["render_buffers"] = {"create_ms": round(t_create, 3), "create_bytes": int(created_bytes),
                              "sync_ms_median": round(float(np.median(ts)), 3), "sync_bytes_median": int(np.median(moved)),
-                             "updated_ranges_median": int(np.median(ranges)), "recreated_in_last_sync": bufs.recreated,
+                             "updated_ranges_median": int(np.median(n_ranges)), "recreated_in_last_sync": bufs.recreated,
                              "note": "five exportable device allocations (one file descriptor each); a sync copies the updated "
                                      "ranges and the submesh table device to device, after an absorption step of config 5"}
     bufs.close()
