@@ -233,12 +233,7 @@ int ivx_mesh_gpu_buffers_create(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_gpu_buff
     return IVX_OK;
 }
 
-int ivx_mesh_gpu_buffers_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_gpu_buffers* g, ivx_mesh_gpu_buffers_info* info) {
-    if (!ctx || !obj || !g || !info) return IVX_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
-    if (int rc = check(ctx, obj)) return rc;
-    std::memset(info, 0, sizeof(*info));
-    for (auto& b : info->buffer) b.fd = -1;
+static int sync_impl(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_gpu_buffers* g, ivx_mesh_gpu_buffers_info* info) {
     const DeviceMesh& m = obj->mesh;
     cudaStream_t st = ctx->stream;
     ivx_mesh_sync* s = obj->sync;
@@ -308,6 +303,21 @@ int ivx_mesh_gpu_buffers_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_gpu_buffer
     if (s) ivx_mesh_report_synchronized(ctx, obj);  // report_gpu_resources_synchronized
     fill_info(*g, m, info);
     return IVX_OK;
+}
+
+int ivx_mesh_gpu_buffers_sync(ivx_ctx* ctx, ivx_object* obj, ivx_mesh_gpu_buffers* g, ivx_mesh_gpu_buffers_info* info) {
+    if (!ctx || !obj || !g || !info) return IVX_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    std::memset(info, 0, sizeof(*info));
+    for (auto& b : info->buffer) b.fd = -1;
+    if (int rc = check(ctx, obj)) return rc;
+    const int rc = sync_impl(ctx, obj, g, info);
+    if (rc != IVX_OK)  // no descriptor is handed out by a call that failed
+        for (auto& b : info->buffer) {
+            if (b.fd >= 0) close(b.fd);
+            b.fd = -1;
+        }
+    return rc;
 }
 
 void ivx_mesh_gpu_buffers_destroy(ivx_ctx* ctx, ivx_mesh_gpu_buffers* g) {
