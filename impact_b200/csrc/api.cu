@@ -2096,17 +2096,23 @@ static int absorb_impl(ivx_ctx* ctx, ivx_object* obj, const ivx::AbsorbShape& sh
     uint8_t* face_mask = tmp.get<uint8_t>(n_in_box);
     uint32_t* convert_flag = tmp.get<uint32_t>(n_in_box);
     uint32_t* slot_of = tmp.get<uint32_t>(n_in_box);
-    if (!face_mask || !convert_flag || !slot_of) IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
+    const bool large_box = n_in_box > BOUNDARY_BOX_ONE_CTA;  // (a mutual absorption over most of an object, say)
+    uint32_t* need2 = large_box ? tmp.get<uint32_t>(n_in_box) : nullptr;
+    uint32_t* ord2 = large_box ? tmp.get<uint32_t>(n_in_box) : nullptr;
+    if (!face_mask || !convert_flag || !slot_of || (large_box && (!need2 || !ord2)))
+        IVX_FAIL(ctx, IVX_ERR_OUT_OF_MEMORY, "absorb: out of device memory");
     // the conversions of the boundary pass take the slots after those of the absorption itself
     KL(ctx, launch_boundary_refresh_box(obj->d_chunks, n, obj->nb, box, b, obj->slots_used, roomy ? counters : nullptr, face_mask,
-                                        convert_flag, slot_of, obj->d_label_stale, counters + 5, true, false, nullptr, 0, st));
+                                        convert_flag, slot_of, obj->d_label_stale, counters + 5, need2, ord2, true, false, nullptr,
+                                        0, st));
     if (!roomy) {
         if (int rc = read_words(ctx, counters, 12, w)) return rc;
         if (int rc = ensure_slots(ctx, obj, w[5])) return rc;
         obj->slots_used += w[5];
     }
     KL(ctx, launch_boundary_refresh_box(obj->d_chunks, n, obj->nb, box, b, 0, nullptr, face_mask, convert_flag, slot_of, nullptr,
-                                        nullptr, false, true, obj->d_voxels, persistent_grid(ctx, n_in_box, 8), st));
+                                        nullptr, nullptr, nullptr, false, true, obj->d_voxels, persistent_grid(ctx, n_in_box, 8),
+                                        st));
     // everything the host wants to know, in one read: slots handed out, statistics, invalidated chunks, and — computed
     // on the device only if chunks were removed (`counters[4]`) — the occupied ranges (intersection.rs:387-389)
     CU(ctx, cudaMemsetAsync(counters + 12, 0, 4, st));

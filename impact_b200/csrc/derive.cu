@@ -226,6 +226,37 @@ cudaError_t launch_boundary_apply(DevChunk* chunks, uint32_t n, const uint32_t n
 // upper faces are refreshed, intersection.rs:391-393), which Uniform chunks stop being uniform, and the slots those get —
 // `first_slot` + *first_extra + their rank among the converted chunks of the box in chunk order, the numbering the
 // whole-table pass gives. Outputs are indexed by position in the box; *total = the slots handed out.
+// what the refresh decides for chunk `w` of the box: its face mask, whether it stops being uniform, the slot it has
+struct BoxChunk {
+    uint32_t c, conv, own_slot;
+    uint8_t mask;
+};
+__device__ __forceinline__ BoxChunk box_chunk(const DevChunk* __restrict__ chunks, uint3 nb, const ChunkBox& box,
+                                              const AbsorbRange& range, uint32_t w) {
+    BoxChunk r{0, 0, 0, 0};
+    const int i = (int)(box.c0[0] + w / (box.d[2] * box.d[1])), j = (int)(box.c0[1] + (w / box.d[2]) % box.d[1]),
+              k = (int)(box.c0[2] + w % box.d[2]);
+    r.c = ((uint32_t)i * nb.y + (uint32_t)j) * nb.z + (uint32_t)k;
+    auto in_range = [&](int x, int y, int z) {
+        return (uint32_t)x >= range.c0[0] && (uint32_t)x < range.c1[0] && (uint32_t)y >= range.c0[1] &&
+               (uint32_t)y < range.c1[1] && (uint32_t)z >= range.c0[2] && (uint32_t)z < range.c1[2];
+    };
+    if (in_range(i, j, k)) r.mask |= (1u << 1) | (1u << 3) | (1u << 5);  // upper faces
+    if (i > 0 && in_range(i - 1, j, k)) r.mask |= 1u << 0;               // lower faces: the pair belongs to the lower chunk
+    if (j > 0 && in_range(i, j - 1, k)) r.mask |= 1u << 2;
+    if (k > 0 && in_range(i, j, k - 1)) r.mask |= 1u << 4;
+    const DevChunk me = chunks[r.c];
+    r.own_slot = me.slot;
+    if (me.kind == 1) {
+        for (int f = 0; f < 6; ++f) {
+            if (!((r.mask >> f) & 1)) continue;
+            const Neighbour nbh = neighbour_of(chunks, nb, i, j, k, f >> 1, f & 1, nullptr);
+            if (!(nbh.kind == 1 || (nbh.kind == 2 && nbh.face == 1))) r.conv = 1;
+        }
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(1024) k_boundary_prep_box(const DevChunk* __restrict__ chunks, uint3 nb, ChunkBox box,
                                                             AbsorbRange range, uint32_t first_slot,
                                                             const uint32_t* __restrict__ first_extra,
@@ -241,30 +272,11 @@ __global__ void __launch_bounds__(1024) k_boundary_prep_box(const DevChunk* __re
     const uint32_t first = first_slot + (first_extra ? *first_extra : 0u);
     for (uint32_t base = 0; base < n_box; base += 1024) {
         const uint32_t w = base + tid;
-        uint32_t conv = 0, need = 0, own_slot = 0, c = 0;
-        uint8_t mask = 0;
+        BoxChunk bc{0, 0, 0, 0};
+        uint32_t need = 0;
         if (w < n_box) {
-            const int i = (int)(box.c0[0] + w / (box.d[2] * box.d[1])), j = (int)(box.c0[1] + (w / box.d[2]) % box.d[1]),
-                      k = (int)(box.c0[2] + w % box.d[2]);
-            c = ((uint32_t)i * nb.y + (uint32_t)j) * nb.z + (uint32_t)k;
-            auto in_range = [&](int x, int y, int z) {
-                return (uint32_t)x >= range.c0[0] && (uint32_t)x < range.c1[0] && (uint32_t)y >= range.c0[1] &&
-                       (uint32_t)y < range.c1[1] && (uint32_t)z >= range.c0[2] && (uint32_t)z < range.c1[2];
-            };
-            if (in_range(i, j, k)) mask |= (1u << 1) | (1u << 3) | (1u << 5);  // upper faces
-            if (i > 0 && in_range(i - 1, j, k)) mask |= 1u << 0;               // lower faces: the pair belongs to the lower chunk
-            if (j > 0 && in_range(i, j - 1, k)) mask |= 1u << 2;
-            if (k > 0 && in_range(i, j, k - 1)) mask |= 1u << 4;
-            const DevChunk me = chunks[c];
-            own_slot = me.slot;
-            if (me.kind == 1) {
-                for (int f = 0; f < 6; ++f) {
-                    if (!((mask >> f) & 1)) continue;
-                    const Neighbour nbh = neighbour_of(chunks, nb, i, j, k, f >> 1, f & 1, nullptr);
-                    if (!(nbh.kind == 1 || (nbh.kind == 2 && nbh.face == 1))) conv = 1;
-                }
-            }
-            need = (conv && own_slot == 0xFFFFFFFFu) ? 1u : 0u;
+            bc = box_chunk(chunks, nb, box, range, w);
+            need = (bc.conv && bc.own_slot == 0xFFFFFFFFu) ? 1u : 0u;
         }
         // exclusive prefix sum of `need` over the CTA, carried from tile to tile
         const uint32_t bal = __ballot_sync(0xffffffffu, need != 0);
@@ -282,10 +294,10 @@ __global__ void __launch_bounds__(1024) k_boundary_prep_box(const DevChunk* __re
         __syncthreads();
         const uint32_t ord = s_carry + s_warp[warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u));
         if (w < n_box) {
-            face_mask[w] = mask;
-            convert_flag[w] = conv;
-            slot_of[w] = need ? first + ord : own_slot;
-            if (conv && label_stale) label_stale[c] = 1;  // a chunk that becomes NonUniform has no region labels yet
+            face_mask[w] = bc.mask;
+            convert_flag[w] = bc.conv;
+            slot_of[w] = need ? first + ord : bc.own_slot;
+            if (bc.conv && label_stale) label_stale[bc.c] = 1;  // a chunk that becomes NonUniform has no region labels yet
         }
         __syncthreads();
         if (tid == 1023) s_carry = ord + need;
@@ -294,17 +306,46 @@ __global__ void __launch_bounds__(1024) k_boundary_prep_box(const DevChunk* __re
     if (tid == 0) *total = s_carry;
 }
 
+// the same in three steps for a box too large for one CTA: flags over a grid, the library's prefix sum, slots over a grid
+__global__ void k_boundary_box_flags(const DevChunk* __restrict__ chunks, uint3 nb, ChunkBox box, AbsorbRange range,
+                                     uint32_t n_box, uint8_t* __restrict__ face_mask, uint32_t* __restrict__ convert_flag,
+                                     uint32_t* __restrict__ need, uint32_t* __restrict__ slot_of,
+                                     uint8_t* __restrict__ label_stale) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_box) return;
+    const BoxChunk bc = box_chunk(chunks, nb, box, range, w);
+    face_mask[w] = bc.mask;
+    convert_flag[w] = bc.conv;
+    need[w] = (bc.conv && bc.own_slot == 0xFFFFFFFFu) ? 1u : 0u;
+    slot_of[w] = bc.own_slot;
+    if (bc.conv && label_stale) label_stale[bc.c] = 1;
+}
+__global__ void k_boundary_box_slots(const uint32_t* __restrict__ need, const uint32_t* __restrict__ ord, uint32_t n_box,
+                                     uint32_t first_slot, const uint32_t* __restrict__ first_extra,
+                                     uint32_t* __restrict__ slot_of) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_box || !need[w]) return;
+    slot_of[w] = first_slot + (first_extra ? *first_extra : 0u) + ord[w];
+}
+
 cudaError_t launch_boundary_refresh_box(DevChunk* chunks, uint32_t n, const uint32_t nb[3], const ChunkBox& box,
                                         const AbsorbRange& range, uint32_t first_slot, const uint32_t* first_extra,
                                         uint8_t* face_mask, uint32_t* convert_flag, uint32_t* slot_of, uint8_t* label_stale,
-                                        uint32_t* total, bool prep, bool apply, unsigned char* voxels, uint32_t grid,
-                                        cudaStream_t st) {
+                                        uint32_t* total, uint32_t* need, uint32_t* ord, bool prep, bool apply,
+                                        unsigned char* voxels, uint32_t grid, cudaStream_t st) {
     const uint32_t n_box = box.d[0] * box.d[1] * box.d[2];
     if (n_box == 0) return cudaSuccess;
     const uint3 nb3 = make_uint3(nb[0], nb[1], nb[2]);
-    if (prep)
+    if (prep && n_box <= BOUNDARY_BOX_ONE_CTA) {
         k_boundary_prep_box<<<1, 1024, 0, st>>>(chunks, nb3, box, range, first_slot, first_extra, face_mask, convert_flag,
                                                 slot_of, label_stale, total);
+    } else if (prep) {
+        if (!need || !ord) return cudaErrorInvalidValue;
+        k_boundary_box_flags<<<(n_box + 255) / 256, 256, 0, st>>>(chunks, nb3, box, range, n_box, face_mask, convert_flag, need,
+                                                                  slot_of, label_stale);
+        if (cudaError_t e = launch_exclusive_scan(need, ord, n_box, total, st)) return e;
+        k_boundary_box_slots<<<(n_box + 255) / 256, 256, 0, st>>>(need, ord, n_box, first_slot, first_extra, slot_of);
+    }
     if (apply)
         k_boundary_apply<true><<<std::max(1u, std::min(grid, n_box)), 256, 0, st>>>(chunks, n, nb3, face_mask, convert_flag,
                                                                                    slot_of, voxels, nullptr, n_box, 0, 0,

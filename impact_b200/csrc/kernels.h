@@ -101,12 +101,14 @@ struct ChunkBox {
 // The boundary refresh after a modification, over the chunks of `box` only (every chunk with a face in a refreshed
 // pair lies in it): `prep` decides conversions and their slots (one CTA; *total = slots handed out, numbered from
 // first_slot + *first_extra in chunk order), `apply` rewrites adjacency bits and obscuredness. face_mask /
-// convert_flag / slot_of hold one entry per chunk of the box.
+// convert_flag / slot_of hold one entry per chunk of the box; a box of more than BOUNDARY_BOX_ONE_CTA chunks is prepared
+// by a grid and the library's prefix sum instead and needs `need` / `ord` (one word per chunk of the box each).
+constexpr uint32_t BOUNDARY_BOX_ONE_CTA = 8192;
 cudaError_t launch_boundary_refresh_box(DevChunk* chunks, uint32_t n, const uint32_t nb[3], const ChunkBox& box,
                                         const AbsorbRange& range, uint32_t first_slot, const uint32_t* first_extra,
                                         uint8_t* face_mask, uint32_t* convert_flag, uint32_t* slot_of, uint8_t* label_stale,
-                                        uint32_t* total, bool prep, bool apply, unsigned char* voxels, uint32_t grid,
-                                        cudaStream_t st);
+                                        uint32_t* total, uint32_t* need, uint32_t* ord, bool prep, bool apply,
+                                        unsigned char* voxels, uint32_t grid, cudaStream_t st);
 // own_lo / own_hi: only chunks of local planes [own_lo, own_hi) are classified / updated (halo planes belong to
 // the neighbour rank)
 cudaError_t launch_boundary_classify(const DevChunk* chunks, uint32_t n, const uint32_t nb[3], const uint8_t* face_mask,

@@ -316,3 +316,23 @@ def test_generation_is_deterministic_and_pool_reuse_is_clean(ctx):
     assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
     for k in ma:
         assert np.array_equal(ma[k].view(np.uint8), mb[k].view(np.uint8)), k
+
+
+def test_absorption_over_a_box_of_many_chunks_is_bit_exact(ctx, oracle):
+    # a sphere of influence reaching over 24^3 chunks: the boundary refresh of a box this large (more chunks than
+    # BOUNDARY_BOX_ONE_CTA, csrc/kernels.h) is prepared by a grid and the library's prefix sum instead of one CTA;
+    # uniform chunks deep inside are converted, many chunks are emptied and removed
+    g = H.sphere_graph(190.0)
+    _, _, _, obj_gpu, obj_cpu = _both(ctx, oracle, g, H.SAME0, threads=8)
+    shape = np.array(obj_cpu.info()["chunk_counts"]) * 16
+    for c, r in ((0.5 * shape + np.float32([20.0, -10.0, 5.0]), 170.0), (0.5 * shape, 185.0)):
+        c = np.float32(c)
+        st_c = obj_cpu.absorb_sphere(c, r, r + 2.0)
+        st_g = obj_gpu.absorb_sphere(c, r, r + 2.0)
+        assert st_c["touched_chunks"] > 3000  # (the refreshed box around them: 23^3 - 24^3 chunks)
+        for f in ("touched_chunks", "touched_voxels", "emptied_voxels", "removed_chunks"):
+            assert st_g[f] == st_c[f], (f, st_g, st_c)
+        gch, gvx = obj_gpu.download()
+        H.assert_objects_equal(gch, gvx, obj_cpu.chunks(), obj_cpu.voxels())
+        assert np.array_equal(obj_gpu.info()["occupied_voxel_ranges"], obj_cpu.info()["occupied_voxel_ranges"])
+        assert np.array_equal(np.sort(obj_gpu.invalidated_mesh_chunk_indices()), np.sort(obj_cpu.dirty()))
