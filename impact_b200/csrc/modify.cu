@@ -172,7 +172,10 @@ __global__ void k_absorb_plan(const DevChunk* __restrict__ chunks, uint3 nb, Abs
     need_slot[t] = (reached && c.kind == 1 && c.slot == 0xFFFFFFFFu) ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) k_absorb_apply(AbsorbArgs a) {
+#ifndef IVX_ABSORB_CTAS
+#define IVX_ABSORB_CTAS 3  // 80 registers, no spills: the CTAs of a usual absorption are resident at once (one wave)
+#endif
+__global__ void __launch_bounds__(256, IVX_ABSORB_CTAS) k_absorb_apply(AbsorbArgs a) {
     __shared__ __align__(16) int8_t s_sd[4096];
     __shared__ __align__(16) uint8_t s_fl[4096];
     __shared__ uint32_t s_cnt[8];
